@@ -1,0 +1,167 @@
+"""ctypes loaders for the checker libraries (TEST INFRASTRUCTURE ONLY).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module.  Nothing under asif_b200/ does.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF_SO = os.path.join(HERE, "_ref", "libasif_ref.so")
+ORACLE_SO = os.path.join(HERE, "liboracle.so")
+
+CFG_DI_EXPLICIT, CFG_DI_IMPLICIT_TB, CFG_IP_IMPLICIT, CFG_IP_ROBUST, CFG_IP_REALIZABLE, CFG_SEGWAY_TB = 1, 2, 3, 4, 5, 6
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+
+
+def _d(a):
+    return None if a is None else a.ctypes.data_as(_dp)
+
+
+class RefLib:
+    """oracle/_ref/libasif_ref.so: unmodified reference sources + OSQP stand-in."""
+
+    def __init__(self, path=REF_SO):
+        if not os.path.exists(path):
+            raise FileNotFoundError(path + " (build with `make -C oracle/ref_build`; needs /root/reference)")
+        L = self.lib = C.CDLL(path)
+        L.ref_set_qp_mode.argtypes = [C.c_double, C.c_int, C.c_int, C.c_int]
+        L.ref_qp_stats.argtypes = [C.POINTER(C.c_longlong)] * 3
+        L.ref_create.restype = C.c_void_p
+        L.ref_create.argtypes = [C.c_int, _dp, C.c_int]
+        L.ref_destroy.argtypes = [C.c_void_p]
+        L.ref_dims.argtypes = [C.c_void_p, _ip]
+        L.ref_filter_batch.argtypes = [C.c_void_p, C.c_int64, _dp, _dp, _dp, _dp, _ip, _dp]
+        L.ref_rollout.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_double, _dp, _dp, _dp, _ip, C.POINTER(C.c_int64)]
+
+    def set_qp_mode(self, eps=1e-8, polish=1, warm_start=0, max_iter=20000, polish_refine_iter=10):
+        """Oracle setting by default; set_qp_mode(-1, -1, -1, -1, -1) restores the reference defaults."""
+        self.lib.ref_set_qp_mode(eps, polish, warm_start, max_iter)
+        self.lib.ref_set_polish_refine(polish_refine_iter)
+
+    def qp_stats(self):
+        a, b, c = C.c_longlong(), C.c_longlong(), C.c_longlong()
+        self.lib.ref_qp_stats(C.byref(a), C.byref(b), C.byref(c))
+        return a.value, b.value, c.value
+
+    def create(self, cfg, opts=None):
+        o = None if opts is None else np.ascontiguousarray(opts, dtype=np.float64)
+        h = self.lib.ref_create(cfg, _d(o), 0 if o is None else o.size)
+        if not h:
+            raise RuntimeError("ref_create(%d) failed" % cfg)
+        return RefFilter(self, h)
+
+
+class RefFilter:
+    def __init__(self, lib, h):
+        self.lib, self.h = lib, h
+        dims = np.zeros(6, dtype=np.int32)
+        lib.lib.ref_dims(h, dims.ctypes.data_as(_ip))
+        self.nx, self.nu, self.n_relax, self.nc, self.nv, self.n_diag = (int(v) for v in dims)
+
+    def filter_batch(self, x, u_des, want_diag=False):
+        x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1, self.nx)
+        u_des = np.ascontiguousarray(u_des, dtype=np.float64).reshape(-1, self.nu)
+        n = x.shape[0]
+        u = np.zeros((n, self.nu))
+        relax = np.zeros((n, self.n_relax))
+        rc = np.zeros(n, dtype=np.int32)
+        diag = np.zeros((n, self.n_diag)) if want_diag else None
+        r = self.lib.lib.ref_filter_batch(self.h, n, _d(x), _d(u_des), _d(u), _d(relax), rc.ctypes.data_as(_ip), _d(diag))
+        assert r == 0
+        return (u, relax, rc, diag) if want_diag else (u, relax, rc)
+
+    def rollout(self, x0, u_des, steps, dt):
+        x = np.array(x0, dtype=np.float64).reshape(-1, self.nx).copy()
+        u_des = np.ascontiguousarray(u_des, dtype=np.float64).reshape(-1, self.nu)
+        n = x.shape[0]
+        u = np.zeros((n, self.nu))
+        rc = np.zeros(n, dtype=np.int32)
+        hist = np.zeros(8, dtype=np.int64)
+        r = self.lib.lib.ref_rollout(self.h, n, steps, dt, _d(x), _d(u_des), _d(u), rc.ctypes.data_as(_ip),
+                                     hist.ctypes.data_as(C.POINTER(C.c_int64)))
+        assert r == 0
+        return x, u, rc, hist
+
+    def close(self):
+        if self.h:
+            self.lib.lib.ref_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class OracleLib:
+    """oracle/liboracle.so: the C restatement (asif_oracle.c, oracle_models.c, qp_enum.c)."""
+
+    def __init__(self, path=ORACLE_SO):
+        if not os.path.exists(path):
+            raise FileNotFoundError(path + " (build with `make -C oracle`)")
+        L = self.lib = C.CDLL(path)
+        L.oracle_dims.argtypes = [C.c_int, _dp, C.c_int, _ip]
+        L.oracle_filter_batch.argtypes = [C.c_int, _dp, C.c_int, C.c_int64, _dp, _dp, _dp, _dp, _ip, _dp]
+        L.oracle_rollout.argtypes = [C.c_int, _dp, C.c_int, C.c_int64, C.c_int32, C.c_double, _dp, _dp, _dp, _ip,
+                                     C.POINTER(C.c_int64)]
+        L.oracle_qp_solve.argtypes = [C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp,
+                                      C.POINTER(C.c_ubyte), _dp]
+
+    def dims(self, cfg, opts=None):
+        o = None if opts is None else np.ascontiguousarray(opts, dtype=np.float64)
+        dims = np.zeros(6, dtype=np.int32)
+        r = self.lib.oracle_dims(cfg, _d(o), 0 if o is None else o.size, dims.ctypes.data_as(_ip))
+        if r != 0:
+            raise RuntimeError("oracle_dims(%d) failed" % cfg)
+        return tuple(int(v) for v in dims)
+
+    def filter_batch(self, cfg, x, u_des, opts=None, want_diag=False):
+        o = None if opts is None else np.ascontiguousarray(opts, dtype=np.float64)
+        nx, nu, n_relax, nc, nv, n_diag = self.dims(cfg, opts)
+        x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1, nx)
+        u_des = np.ascontiguousarray(u_des, dtype=np.float64).reshape(-1, nu)
+        n = x.shape[0]
+        u = np.zeros((n, nu))
+        relax = np.zeros((n, n_relax))
+        rc = np.zeros(n, dtype=np.int32)
+        diag = np.zeros((n, n_diag)) if want_diag else None
+        r = self.lib.oracle_filter_batch(cfg, _d(o), 0 if o is None else o.size, n, _d(x), _d(u_des), _d(u), _d(relax),
+                                         rc.ctypes.data_as(_ip), _d(diag))
+        assert r == 0
+        return (u, relax, rc, diag) if want_diag else (u, relax, rc)
+
+    def rollout(self, cfg, x0, u_des, steps, dt, opts=None):
+        o = None if opts is None else np.ascontiguousarray(opts, dtype=np.float64)
+        nx, nu = self.dims(cfg, opts)[:2]
+        x = np.array(x0, dtype=np.float64).reshape(-1, nx).copy()
+        u_des = np.ascontiguousarray(u_des, dtype=np.float64).reshape(-1, nu)
+        n = x.shape[0]
+        u = np.zeros((n, nu))
+        rc = np.zeros(n, dtype=np.int32)
+        hist = np.zeros(8, dtype=np.int64)
+        r = self.lib.oracle_rollout(cfg, _d(o), 0 if o is None else o.size, n, steps, dt, _d(x), _d(u_des), _d(u),
+                                    rc.ctypes.data_as(_ip), hist.ctypes.data_as(C.POINTER(C.c_int64)))
+        assert r == 0
+        return x, u, rc, hist
+
+    def qp_solve(self, H, c, A, b, lb, ub, be=None, diagonal_cost=True):
+        """A is (nc, nv); returns (status, sol)."""
+        A = np.asarray(A, dtype=np.float64)
+        nc, nv = A.shape
+        Af = np.asfortranarray(A)
+        Hf = np.asfortranarray(np.asarray(H, dtype=np.float64).reshape(nv, nv))
+        c, b, lb, ub = (np.ascontiguousarray(v, dtype=np.float64) for v in (c, b, lb, ub))
+        sol = np.zeros(nv)
+        bep = None
+        if be is not None:
+            be = np.ascontiguousarray(be, dtype=np.uint8)
+            bep = be.ctypes.data_as(C.POINTER(C.c_ubyte))
+        st = self.lib.oracle_qp_solve(nv, nc, int(diagonal_cost), Hf.ctypes.data_as(_dp), _d(c), Af.ctypes.data_as(_dp),
+                                      _d(b), _d(lb), _d(ub), bep, _d(sol))
+        return st, sol

@@ -1,0 +1,89 @@
+/* ref_harness.cpp -- C entry points of libasif_ref.so (TEST INFRASTRUCTURE ONLY; see ref_api.h). */
+#include "ref_api.h"
+#include "ref_common.h"
+#include "osqp.h"
+#include <vector>
+
+extern "C" {
+
+void ref_set_qp_mode(double eps, int polish, int warm_start, int max_iter)
+{
+	osqp_shim_configure(eps, polish, warm_start, max_iter);
+}
+
+void ref_set_polish_refine(int iters) { osqp_shim_configure_refine(iters); }
+
+void ref_qp_stats(long long *n_solves, long long *n_iters, long long *n_polish_ok)
+{
+	osqp_shim_stats(n_solves, n_iters, n_polish_ok);
+}
+
+void *ref_create(int cfg, const double *opts, int n_opts)
+{
+	switch (cfg) {
+	case REF_CFG_DI_EXPLICIT: return make_di_explicit(opts, n_opts);
+	case REF_CFG_DI_IMPLICIT_TB: return make_di_implicit_tb(opts, n_opts);
+	case REF_CFG_IP_IMPLICIT: return make_ip_implicit(opts, n_opts);
+	case REF_CFG_IP_ROBUST: return make_ip_robust(opts, n_opts);
+	case REF_CFG_IP_REALIZABLE: return make_ip_realizable(opts, n_opts);
+	case REF_CFG_SEGWAY_TB: return make_segway_tb(opts, n_opts);
+	default: return 0;
+	}
+}
+
+void ref_destroy(void *h) { delete (RefFilter *)h; }
+
+int ref_dims(void *h, int32_t *dims)
+{
+	RefFilter *f = (RefFilter *)h;
+	if (!f) return -1;
+	dims[0] = f->nx; dims[1] = f->nu; dims[2] = f->n_relax; dims[3] = f->nc; dims[4] = f->nv; dims[5] = f->n_diag;
+	return 0;
+}
+
+int ref_filter_batch(void *h, int64_t n, const double *x, const double *u_des,
+                     double *u_act, double *relax, int32_t *rc, double *diag)
+{
+	RefFilter *f = (RefFilter *)h;
+	if (!f) return -1;
+	for (int64_t k = 0; k < n; k++) {
+		double r[2] = {0.0, 0.0};
+		rc[k] = f->filter(x + k * f->nx, u_des + k * f->nu, u_act + k * f->nu, r, diag ? diag + k * f->n_diag : 0);
+		for (int j = 0; j < f->n_relax; j++) relax[k * f->n_relax + j] = r[j];
+	}
+	return 0;
+}
+
+int ref_rollout(void *h, int64_t n, int32_t steps, double dt, double *x, const double *u_des,
+                double *u_act_last, int32_t *rc_last, int64_t *rc_hist)
+{
+	RefFilter *f = (RefFilter *)h;
+	if (!f) return -1;
+	const int nx = f->nx, nu = f->nu;
+	std::vector<double> fo(nx), go(nx * nu), fcl(nx), ua(nu);
+	if (rc_hist) for (int i = 0; i < 8; i++) rc_hist[i] = 0;
+	for (int64_t k = 0; k < n; k++) {
+		double *xk = x + k * nx;
+		int32_t rc = 0;
+		for (int j = 0; j < nu; j++) ua[j] = 0.0;
+		for (int32_t s = 0; s < steps; s++) {
+			double r[2];
+			rc = f->filter(xk, u_des + k * nu, ua.data(), r, 0);
+			if (rc_hist) rc_hist[(rc >= -3 && rc <= 2) ? rc + 3 : 7]++;
+			/* plant step exactly as the example mains: fCl = 0; fCl += f; fCl += g*uAct; x += dt*fCl
+			   (examples/segway_implicit_tb.cpp:265-283) */
+			f->plant(xk, fo.data(), go.data());
+			for (int i = 0; i < nx; i++) {
+				fcl[i] = 0.0;
+				fcl[i] += fo[i];
+				for (int j = 0; j < nu; j++) fcl[i] += go[i + j * nx] * ua[j];
+			}
+			for (int i = 0; i < nx; i++) xk[i] += dt * fcl[i];
+		}
+		for (int j = 0; j < nu; j++) u_act_last[k * nu + j] = ua[j];
+		rc_last[k] = rc;
+	}
+	return 0;
+}
+
+} /* extern "C" */

@@ -1,0 +1,120 @@
+/* ref_model_di.cpp -- reference filters on the DoubleIntegrator example callbacks
+ * (TEST INFRASTRUCTURE ONLY).  The example files are included verbatim; their main() lands
+ * in a namespace and is never called. */
+#include "ref_std_includes.h"
+
+namespace ex_di {
+#include "examples/DoubleIntegrator.cpp"
+}
+namespace ex_di_tb {
+#include "examples/DoubleIntegrator_implicit_tb.cpp"
+}
+
+namespace {
+
+struct AsifAccess : ASIF::ASIF {
+	using ASIF::ASIF::ASIF;
+	const double *A() const { return A_; }
+	const double *b() const { return b_; }
+};
+
+struct DiExplicit : RefFilter {
+	AsifAccess f;
+	DiExplicit(const double *opts, int n_opts) : f(ex_di::nx, ex_di::nu, ex_di::npSS, ex_di::safetySet, ex_di::dynamics)
+	{
+		ASIF::ASIF::Options o; /* defaults: relaxLb 5, relaxCost 50 (include/asif.h:11-17) */
+		if (opts && n_opts >= 2) {
+			o.relaxLb = opts[0];
+			o.relaxCost = opts[1];
+		}
+		f.initialize(ex_di::lb, ex_di::ub, o);
+		nx = 2; nu = 1; n_relax = 1; nc = 4; nv = 2; n_diag = nc * nv + nc;
+	}
+	int32_t filter(const double *x, const double *u_des, double *u_act, double *relax, double *diag) override
+	{
+		int32_t rc = f.filter(x, u_des, u_act, relax[0]);
+		if (diag) {
+			memcpy(diag, f.A(), sizeof(double) * nc * nv);
+			memcpy(diag + nc * nv, f.b(), sizeof(double) * nc);
+		}
+		return rc;
+	}
+	void plant(const double *x, double *fo, double *go) override { ex_di::dynamics(x, fo, go); }
+};
+
+struct TbAccess : ASIF::ASIFimplicitTB {
+	using ASIF::ASIFimplicitTB::ASIFimplicitTB;
+	const double *A() const { return A_; }
+	const double *b() const { return b_; }
+};
+
+/* Deviation D3: examples/DoubleIntegrator_implicit_tb.cpp:49 writes only DDh[0..1]
+ * of the 2x2 Hessian (DDh[i] with i<nx) and the library reads all four entries
+ * (src/asif_implicit_tb.cpp:623).  The callback below calls the shipped one and then
+ * completes DDh = mPpPt. */
+void di_tb_backup_set_fixed(const double *x, double *h, double *Dh, double *DDh)
+{
+	ex_di_tb::backupSet(x, h, Dh, DDh);
+	for (uint32_t k = 0; k < ex_di_tb::nx * ex_di_tb::nx; k++) DDh[k] = ex_di_tb::mPpPt[k];
+}
+
+} // namespace
+
+/* diag layout shared by the TB configs:
+ * [TTS, BTorthoBS, hSafetyNow, hBackupEnd, critIdx[npBTSS] (-1 = absent), A_[nc*nv], b_[nc]] */
+void ref_tb_fill_diag(const ASIF::ASIFimplicitTB &f, const double *A, const double *b, int npBTSS, int nc, int nv, double *diag)
+{
+	diag[0] = f.TTS_;
+	diag[1] = f.BTorthoBS_;
+	diag[2] = f.hSafetyNow_;
+	diag[3] = f.hBackupEnd_;
+	for (int i = 0; i < npBTSS; i++) diag[4 + i] = i < (int)f.backTrajCritIdx_.size() ? (double)f.backTrajCritIdx_[i] : -1.0;
+	memcpy(diag + 4 + npBTSS, A, sizeof(double) * nc * nv);
+	memcpy(diag + 4 + npBTSS + nc * nv, b, sizeof(double) * nc);
+}
+
+void ref_tb_options(const double *opts, int n_opts, ASIF::ASIFimplicitTB::Options &o)
+{
+	/* [relaxCost, relaxSafeLb, relaxTTS, relaxMinOrtho, backTrajHorizon, backTrajExtend, backTrajDt, backTrajMinOrtho, satSharpness] */
+	if (!opts || n_opts < 9) return;
+	o.relaxCost = opts[0];
+	o.relaxSafeLb = opts[1];
+	o.relaxTTS = opts[2];
+	o.relaxMinOrtho = opts[3];
+	o.backTrajHorizon = opts[4];
+	o.backTrajExtend = opts[5];
+	o.backTrajDt = opts[6];
+	o.backTrajMinOrtho = opts[7];
+	o.satSharpness = opts[8];
+}
+
+namespace {
+struct DiTb : RefFilter {
+	TbAccess f;
+	DiTb(const double *opts, int n_opts)
+	    : f(ex_di_tb::nx, ex_di_tb::nu, ex_di_tb::npSS, ex_di_tb::npBTSS, ex_di_tb::safetySet, di_tb_backup_set_fixed,
+	        ex_di_tb::dynamicsWithGradient, ex_di_tb::backupController)
+	{
+		ASIF::ASIFimplicitTB::Options o;
+		/* options of the example's main() (examples/DoubleIntegrator_implicit_tb.cpp:90-95) */
+		o.backTrajHorizon = 2.0;
+		o.backTrajDt = 0.001;
+		o.relaxSafeLb = 10.0;
+		o.relaxTTS = 5.0;
+		o.relaxMinOrtho = 5.0;
+		ref_tb_options(opts, n_opts, o);
+		f.initialize(ex_di_tb::lb, ex_di_tb::ub, o);
+		nx = 2; nu = 1; n_relax = 1; nc = 18; nv = 2; n_diag = 4 + 4 + nc * nv + nc;
+	}
+	int32_t filter(const double *x, const double *u_des, double *u_act, double *relax, double *diag) override
+	{
+		int32_t rc = f.filter(x, u_des, u_act, relax[0]);
+		if (diag) ref_tb_fill_diag(f, f.A(), f.b(), 4, nc, nv, diag);
+		return rc;
+	}
+	void plant(const double *x, double *fo, double *go) override { ex_di_tb::dynamics(x, fo, go); }
+};
+} // namespace
+
+RefFilter *make_di_explicit(const double *opts, int n_opts) { return new DiExplicit(opts, n_opts); }
+RefFilter *make_di_implicit_tb(const double *opts, int n_opts) { return new DiTb(opts, n_opts); }
