@@ -1,0 +1,227 @@
+"""ctypes binding of include/asif_b200.h.  No numerics here; every call goes to libasif_b200.so."""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+FILTER_EXPLICIT, FILTER_IMPLICIT_TB, FILTER_IMPLICIT, FILTER_ROBUST, FILTER_REALIZABLE = 1, 2, 3, 4, 5
+MODEL_DOUBLE_INTEGRATOR, MODEL_DOUBLE_INTEGRATOR_TB, MODEL_INVERTED_PENDULUM, MODEL_INVERTED_PENDULUM_TABLE = 1, 2, 3, 4
+MODEL_SEGWAY, MODEL_SEGWAY_SHIPPED = 6, 7
+MEM_HOST, MEM_DEVICE = 0, 1
+QP_SHARED_H, QP_SHARED_BOUNDS = 1, 2
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+
+
+class AsifError(RuntimeError):
+    pass
+
+
+class EngineConfig(C.Structure):
+    """Mirror of struct asif_engine_config (include/asif_b200.h)."""
+    _fields_ = [
+        ("struct_size", C.c_uint32), ("filter", C.c_int32), ("model", C.c_int32), ("device", C.c_int32),
+        ("npBTSS", C.c_int32), ("npSSmax", C.c_int32),
+        ("lb", C.c_double * 2), ("ub", C.c_double * 2),
+        ("relaxCost", C.c_double), ("relaxLb", C.c_double), ("relaxReachLb", C.c_double),
+        ("relaxTTS", C.c_double), ("relaxMinOrtho", C.c_double),
+        ("backTrajHorizon", C.c_double), ("backTrajExtend", C.c_double), ("backTrajDt", C.c_double),
+        ("backTrajMinOrtho", C.c_double), ("satSharpness", C.c_double), ("inf", C.c_double),
+        ("relaxDes", C.c_double), ("relaxOffset", C.c_double),
+        ("uncertaintyBounds", C.c_double * 4), ("dynParam", C.c_double * 4),
+        ("halfplanes", _dp), ("n_halfplanes", C.c_int32),
+        ("kernel_vertices", _dp), ("n_vertices", C.c_int32),
+        ("facet_normals", _dp), ("facet_vertices", _ip), ("facet_active", _ip),
+        ("n_facets", C.c_int32), ("max_critical_facets", C.c_int32), ("max_active_constraints", C.c_int32),
+    ]
+
+
+_lib = None
+
+
+def lib_path():
+    return os.path.join(HERE, "libasif_b200.so")
+
+
+def load_library():
+    """Load libasif_b200.so (in-tree).  Raises if it has not been built: there is no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    p = lib_path()
+    if not os.path.exists(p):
+        raise AsifError("%s is missing: build it with `python -m asif_b200._build` (nvcc, sm_100a). "
+                        "There is no CPU fallback." % p)
+    L = C.CDLL(p)
+    L.asif_b200_abi_version.restype = C.c_int32
+    L.asif_last_error.restype = C.c_char_p
+    L.asif_device_count.restype = C.c_int32
+    L.asif_engine_config_init.argtypes = [C.POINTER(EngineConfig), C.c_int32, C.c_int32]
+    L.asif_engine_create.argtypes = [C.POINTER(EngineConfig), C.POINTER(C.c_void_p)]
+    L.asif_engine_destroy.argtypes = [C.c_void_p]
+    L.asif_engine_dims.argtypes = [C.c_void_p, _ip]
+    L.asif_engine_filter_batch.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                           C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+    L.asif_engine_rollout.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_double, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.c_int32, C.c_void_p]
+    L.asif_engine_last_qp_iterations.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+    L.asif_qp_solve_batch.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int32] + [C.c_void_p] * 9 + \
+                                     [C.c_int32, C.c_int32, C.c_void_p]
+    L.asif_measure_fp64_peak.argtypes = [C.c_int32, _dp, _dp]
+    _lib = L
+    return L
+
+
+def _check(rc):
+    if rc != 0:
+        raise AsifError("asif_b200 error %d: %s" % (rc, load_library().asif_last_error().decode()))
+
+
+def device_count():
+    n = load_library().asif_device_count()
+    if n < 0:
+        raise AsifError(load_library().asif_last_error().decode())
+    return n
+
+
+def measure_fp64_peak(device=0):
+    tf, mhz = C.c_double(), C.c_double()
+    _check(load_library().asif_measure_fp64_peak(device, C.byref(tf), C.byref(mhz)))
+    return tf.value, mhz.value
+
+
+def _ptr(a):
+    """Host numpy array or torch tensor (host or device) -> (address, is_device)."""
+    if a is None:
+        return None, None
+    if isinstance(a, np.ndarray):
+        assert a.flags["C_CONTIGUOUS"], "arrays must be C-contiguous"
+        return a.ctypes.data, False
+    # torch tensor (duck-typed so that torch stays optional)
+    assert a.is_contiguous(), "tensors must be contiguous"
+    return a.data_ptr(), bool(a.is_cuda)
+
+
+class Engine:
+    """One filter object = constructor + initialize(lb, ub, options) of the reference class."""
+
+    def __init__(self, filter, model, device=0, **options):
+        L = load_library()
+        cfg = EngineConfig()
+        _check(L.asif_engine_config_init(C.byref(cfg), filter, model))
+        cfg.device = device
+        self._keep = []
+        for k, v in options.items():
+            if k in ("lb", "ub"):
+                for i, vi in enumerate(np.atleast_1d(v)):
+                    getattr(cfg, k)[i] = float(vi)
+            elif not hasattr(cfg, k):
+                raise AsifError("unknown option %r" % k)
+            else:
+                setattr(cfg, k, v)
+        self.cfg = cfg
+        h = C.c_void_p()
+        _check(L.asif_engine_create(C.byref(cfg), C.byref(h)))
+        self._h = h
+        dims = (C.c_int32 * 6)()
+        _check(L.asif_engine_dims(h, dims))
+        self.nx, self.nu, self.n_relax, self.nc, self.nv, self.n_diag = (int(v) for v in dims)
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load_library().asif_engine_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- numpy convenience: allocates outputs on the host
+    def filter_batch(self, x, u_des, want_diag=False):
+        x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1, self.nx)
+        u_des = np.ascontiguousarray(u_des, dtype=np.float64).reshape(-1, self.nu)
+        n = x.shape[0]
+        u = np.empty((n, self.nu))
+        relax = np.empty((n, self.n_relax))
+        rc = np.empty(n, dtype=np.int32)
+        diag = np.empty((n, self.n_diag)) if want_diag else None
+        self.filter_batch_into(n, x, u_des, u, relax, rc, diag)
+        return (u, relax, rc, diag) if want_diag else (u, relax, rc)
+
+    # -- raw: caller-owned numpy arrays (host) or torch tensors (host pinned / device)
+    def filter_batch_into(self, n, x, u_des, u_act, relax, rc, diag=None, stream=None):
+        ptrs = [_ptr(a) for a in (x, u_des, u_act, relax, rc)]
+        dev = {d for _, d in ptrs}
+        assert len(dev) == 1, "all batch arrays must live in the same memory space"
+        mem = MEM_DEVICE if dev.pop() else MEM_HOST
+        dptr = _ptr(diag)[0] if diag is not None else None
+        _check(load_library().asif_engine_filter_batch(self._h, n, ptrs[0][0], ptrs[1][0], ptrs[2][0], ptrs[3][0],
+                                                       ptrs[4][0], dptr, mem, stream))
+
+    def rollout(self, x0, u_des, steps, dt):
+        x = np.array(x0, dtype=np.float64).reshape(-1, self.nx).copy()
+        u_des = np.ascontiguousarray(u_des, dtype=np.float64).reshape(-1, self.nu)
+        n = x.shape[0]
+        u = np.empty((n, self.nu))
+        rc = np.empty(n, dtype=np.int32)
+        hist = (C.c_int64 * 8)()
+        _check(load_library().asif_engine_rollout(self._h, n, steps, dt, x.ctypes.data, u_des.ctypes.data, u.ctypes.data,
+                                                  rc.ctypes.data, hist, MEM_HOST, None))
+        return x, u, rc, np.array(list(hist), dtype=np.int64)
+
+    def rollout_into(self, n, steps, dt, x, u_des, u_act_last, rc_last, want_hist=False, stream=None):
+        ptrs = [_ptr(a) for a in (x, u_des, u_act_last, rc_last)]
+        dev = {d for _, d in ptrs}
+        assert len(dev) == 1
+        mem = MEM_DEVICE if dev.pop() else MEM_HOST
+        hist = (C.c_int64 * 8)() if want_hist else None
+        _check(load_library().asif_engine_rollout(self._h, n, steps, dt, ptrs[0][0], ptrs[1][0], ptrs[2][0], ptrs[3][0],
+                                                  hist, mem, stream))
+        return np.array(list(hist), dtype=np.int64) if want_hist else None
+
+    def last_qp_iterations(self):
+        v = C.c_uint64()
+        _check(load_library().asif_engine_last_qp_iterations(self._h, C.byref(v)))
+        return int(v.value)
+
+
+def qp_solve_batch(H, c, A, b, lb, ub, be=None, diagonal_cost=True, device=0):
+    """n QPs  min v'Hv + c'v, A v >= b, lb <= v <= ub.
+
+    c: (n, nv); A: (n, nc, nv) in natural (row, col) indexing (converted to the reference's
+    column-major layout here); b: (n, nc); H: (nv, nv) shared or (n, nv, nv); lb/ub: (nv,) shared or (n, nv).
+    Returns (sol (n, nv), status (n,)).
+    """
+    c = np.ascontiguousarray(c, dtype=np.float64)
+    n, nv = c.shape
+    A = np.asarray(A, dtype=np.float64).reshape(n, -1, nv)
+    nc = A.shape[1]
+    Acm = np.ascontiguousarray(np.transpose(A, (0, 2, 1)))  # per problem column-major
+    b = np.ascontiguousarray(b, dtype=np.float64).reshape(n, nc)
+    H = np.asarray(H, dtype=np.float64)
+    share = 0
+    if H.ndim == 2:
+        share |= QP_SHARED_H
+        Hcm = np.ascontiguousarray(H.T)
+    else:
+        Hcm = np.ascontiguousarray(np.transpose(H, (0, 2, 1)))
+    lb = np.ascontiguousarray(lb, dtype=np.float64)
+    ub = np.ascontiguousarray(ub, dtype=np.float64)
+    if lb.ndim == 1:
+        share |= QP_SHARED_BOUNDS
+    bep = None
+    if be is not None:
+        be = np.ascontiguousarray(be, dtype=np.uint8)
+        bep = be.ctypes.data
+    sol = np.empty((n, nv))
+    status = np.empty(n, dtype=np.int32)
+    _check(load_library().asif_qp_solve_batch(device, nv, nc, n, int(diagonal_cost), Hcm.ctypes.data, c.ctypes.data,
+                                              Acm.ctypes.data, b.ctypes.data, lb.ctypes.data, ub.ctypes.data, bep,
+                                              sol.ctypes.data, status.ctypes.data, share, MEM_HOST, None))
+    return sol, status

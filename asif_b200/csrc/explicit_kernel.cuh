@@ -1,0 +1,134 @@
+// explicit_kernel.cuh -- batched ASIF::filter (explicit CBF filter), one state per thread:
+// safety set + dynamics -> rows  Lgh u + h delta >= -Lfh  -> exact QP -> saturation.
+// Reference path replaced: src/asif.cpp:176-210 (filter), :233-312 (updateConstraints) and the
+// OSQP solve behind it.  44 B of HBM traffic and ~150 FP64 operations per state: this is the one
+// config where HBM can bind, so loads/stores are the coalesced state-major streams and nothing
+// else touches global memory.
+#pragma once
+#include "filter_common.cuh"
+#include "qp_gi.cuh"
+
+namespace asifb {
+
+constexpr int EXPL_THREADS = 256;
+
+template <int NV, int NC>
+struct RegRows {
+	// rows in shared memory [(NC)*(NV+1)][T]; bounds appended
+	const double *rows;
+	int stride;
+	double lb[NV], ub[NV];
+	__device__ __forceinline__ int count() const { return NC + 2 * NV; }
+	__device__ __forceinline__ void get(int j, double (&n)[NV], double &rhs) const
+	{
+		if (j < NC) {
+#pragma unroll
+			for (int i = 0; i < NV; i++) n[i] = rows[(j * (NV + 1) + i) * stride];
+			rhs = rows[(j * (NV + 1) + NV) * stride];
+		} else {
+			const int k = j - NC;
+			const int var = k >> 1;
+			const bool upper = k & 1;
+			double bnd = 0.0;
+#pragma unroll
+			for (int i = 0; i < NV; i++) {
+				n[i] = (i == var) ? (upper ? -1.0 : 1.0) : 0.0;
+				if (i == var) bnd = upper ? -ub[i] : lb[i];
+			}
+			rhs = bnd;
+		}
+	}
+};
+
+template <class M, bool WITH_DIAG>
+__global__ void __launch_bounds__(EXPL_THREADS)
+explicit_filter_kernel(const ExplicitParams p, const int64_t n, const double *__restrict__ x_in,
+                       const double *__restrict__ u_des, double *__restrict__ u_act, double *__restrict__ relax_out,
+                       int32_t *__restrict__ rc_out, double *__restrict__ diag,
+                       unsigned long long *__restrict__ qp_iter_sum)
+{
+	constexpr int NX = M::NX, NU = M::NU, NPSS = M::NPSS, NV = NU + 1, NC = NPSS;
+	__shared__ double smem[NC * (NV + 1) * EXPL_THREADS];
+	const int T = EXPL_THREADS;
+	double *rows = smem + threadIdx.x;
+	const int64_t k = (int64_t)blockIdx.x * T + threadIdx.x;
+	const bool live = k < n;
+	const int64_t kk = live ? k : (n - 1);
+	double x[NX], ud[NU];
+#pragma unroll
+	for (int i = 0; i < NX; i++) x[i] = x_in[kk * NX + i];
+#pragma unroll
+	for (int i = 0; i < NU; i++) ud[i] = u_des[kk * NU + i];
+
+	double h[NPSS], Dh[NPSS * NX], f[NX], g[NX * NU];
+	M::safety_set(x, h, Dh);
+	M::dynamics(x, f, g);
+#pragma unroll
+	for (int j = 0; j < NPSS; j++) {
+		// Lfh = Dh f, Lgh = Dh g (src/asif.cpp:276-285), A = [Lgh | h], b = -Lfh (:295-303)
+		double lf = Dh[j] * f[0];
+#pragma unroll
+		for (int m = 1; m < NX; m++) lf = lf + Dh[j + m * NPSS] * f[m];
+#pragma unroll
+		for (int i = 0; i < NU; i++) {
+			double lg = Dh[j] * g[i * NX];
+#pragma unroll
+			for (int m = 1; m < NX; m++) lg = lg + Dh[j + m * NPSS] * g[m + i * NX];
+			rows[(j * (NV + 1) + i) * T] = lg;
+		}
+		rows[(j * (NV + 1) + NU) * T] = h[j];
+		rows[(j * (NV + 1) + NV) * T] = -lf;
+	}
+	RegRows<NV, NC> R;
+	R.rows = rows;
+	R.stride = T;
+	double c[NV], v[NV];
+	DiagMetric<NV> mt;
+#pragma unroll
+	for (int i = 0; i < NU; i++) {
+		c[i] = -2.0 * ud[i];
+		R.lb[i] = p.lb[i];
+		R.ub[i] = p.ub[i];
+	}
+	c[NU] = -2.0 * p.relaxCost * p.relaxLb;
+	R.lb[NU] = p.relaxLb; // both bounds pinned (src/asif.cpp:88-91)
+	R.ub[NU] = p.relaxLb;
+#pragma unroll
+	for (int i = 0; i < NV; i++) {
+		mt.gi[i] = p.gi[i];
+		mt.gih[i] = p.gih[i];
+	}
+	int iters = 0;
+	const int st = qp_gi_solve<NV>(mt, c, R, v, &iters);
+	if (live) {
+		if (st == QP_OK) {
+#pragma unroll
+			for (int i = 0; i < NU; i++) u_act[k * NU + i] = input_saturate(v[i], p.lb[i], p.ub[i]);
+			relax_out[k] = v[NU];
+			rc_out[k] = 1;
+		} else {
+			// the reference leaves uAct and relax untouched on failure (src/asif.cpp:207-209);
+			// a batch has no "previous value", so the outputs are defined as 0 here
+#pragma unroll
+			for (int i = 0; i < NU; i++) u_act[k * NU + i] = 0.0;
+			relax_out[k] = 0.0;
+			rc_out[k] = -1;
+		}
+		if (WITH_DIAG) {
+			constexpr int NDIAG = NC * NV + NC;
+			double *d = diag + k * NDIAG;
+			for (int j = 0; j < NC; j++) {
+				for (int i = 0; i < NV; i++) d[j + i * NC] = rows[(j * (NV + 1) + i) * T];
+				d[NC * NV + j] = rows[(j * (NV + 1) + NV) * T];
+			}
+		}
+	}
+	if (qp_iter_sum) {
+		unsigned int it = live ? (unsigned int)iters : 0u;
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) it += __shfl_xor_sync(0xffffffffu, it, o);
+		if ((threadIdx.x & 31) == 0 && it) atomicAdd(qp_iter_sum, (unsigned long long)it);
+	}
+}
+
+} // namespace asifb

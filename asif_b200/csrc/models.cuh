@@ -1,0 +1,247 @@
+// models.cuh -- device functors for the models of the named configs.
+//
+// A model keeps the reference's five callback signatures and layouts:
+// column-major Dh[NPSS x NX], g[NX x NU], Du[NU x NX], Df[NX x NX], Dg[i + k*NX + j*NX*NU],
+// so that a user model ports by copy-paste from its std::function form.  Constants are those
+// of the reference's example programs (cited per functor); the floating-point operation order
+// of each example is preserved (terms that are an exact 0.0 product added to a +0.0
+// accumulator are dropped, which cannot change an IEEE result for finite inputs).
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+
+namespace asifb {
+
+// ------------------------------------------------------------------ DoubleIntegrator (explicit)
+// examples/DoubleIntegrator.cpp:12-61
+struct DoubleIntegratorExplicit {
+	static constexpr int NX = 2, NU = 1, NPSS = 4;
+	__device__ static void safety_set(const double *x, double *h, double *Dh)
+	{
+		if (x[1] > 0) {
+			h[0] = 1.0 - x[0] - (x[1] * x[1]) / 2.0; Dh[0] = -1.0; Dh[4] = -x[1];
+			h[1] = x[0] - (-1.0);                    Dh[1] = 1.0;  Dh[5] = 0.0;
+		} else {
+			h[0] = -x[0] + 1.0;                         Dh[0] = -1.0; Dh[4] = 0.0;
+			h[1] = x[0] - (-1.0) - (x[1] * x[1]) / 2.0; Dh[1] = 1.0;  Dh[5] = -x[1];
+		}
+		h[2] = x[1] - (-1.0); Dh[2] = 0.0; Dh[6] = 1.0;
+		h[3] = -x[1] + 1.0;   Dh[3] = 0.0; Dh[7] = -1.0;
+	}
+	__device__ static void dynamics(const double *x, double *f, double *g)
+	{
+		f[0] = x[1]; // A = [0 1; 0 0]
+		f[1] = 0.0;
+		g[0] = 0.0;
+		g[1] = 1.0;
+	}
+};
+
+// ------------------------------------------------------------------ DoubleIntegrator (implicit TB)
+// examples/DoubleIntegrator_implicit_tb.cpp:13-85 ; backup-set Hessian completed
+struct DoubleIntegratorTB {
+	static constexpr int NX = 2, NU = 1, NPSS = 4;
+	static constexpr bool FUSED_GRADIENT = true; // DYNAMICS_WITH_GRADIENT, :9
+	__device__ static void safety_set(const double *x, double *h, double *Dh)
+	{
+		h[0] = -x[0] + 1.0;   Dh[0] = -1.0; Dh[4] = 0.0;
+		h[1] = x[0] - (-1.0); Dh[1] = 1.0;  Dh[5] = 0.0;
+		h[2] = x[1] - (-1.0); Dh[2] = 0.0;  Dh[6] = 1.0;
+		h[3] = -x[1] + 1.0;   Dh[3] = 0.0;  Dh[7] = -1.0;
+	}
+	__device__ static double backup_set_value(const double *x)
+	{
+		// h = Pv^2 - sum P_ij x_i x_j with P = I: ((h - x0*x0) - 0) - 0) - x1*x1
+		double h = 0.01 * 0.01;
+		h -= x[0] * x[0];
+		h -= x[1] * x[1];
+		return h;
+	}
+	__device__ static void backup_set(const double *x, double &h, double *Dh, double *DDh)
+	{
+		h = backup_set_value(x);
+		Dh[0] = -2.0 * x[0];
+		Dh[1] = -2.0 * x[1];
+		DDh[0] = -2.0; DDh[1] = 0.0; DDh[2] = 0.0; DDh[3] = -2.0;
+	}
+	__device__ static void backup_controller(const double *x, double *u, double *Du)
+	{
+		u[0] = (-10.0) * x[0] + (-20.0) * x[1];
+		Du[0] = -10.0;
+		Du[1] = -20.0;
+	}
+	__device__ static void dynamics(const double *x, double *f, double *g)
+	{
+		f[0] = x[1];
+		f[1] = 0.0;
+		g[0] = 0.0;
+		g[1] = 1.0;
+	}
+	__device__ static void dynamics_with_gradient(const double *x, const double *u, double *f, double *g, double *d)
+	{
+		dynamics(x, f, g);
+		d[0] = 0.0; d[1] = 0.0; d[2] = 1.0; d[3] = 0.0;
+	}
+	__device__ static void dynamics_gradients(const double *x, double *Df, double *Dg)
+	{
+		Df[0] = 0.0; Df[1] = 0.0; Df[2] = 1.0; Df[3] = 0.0;
+		Dg[0] = Dg[1] = Dg[2] = Dg[3] = 0.0;
+	}
+};
+
+// ------------------------------------------------------------------ Segway (implicit TB)
+// examples/segway_implicit_tb.cpp:13-212.  CENTRED selects the backup set centred on the backup
+// controller's equilibrium (SURVEY 8c deviation D6); false = the set as shipped.
+template <bool CENTRED>
+struct SegwayTB {
+	static constexpr int NX = 4, NU = 1, NPSS = 4;
+	static constexpr bool FUSED_GRADIENT = false;
+	__device__ static double bound(int i)
+	{
+		return i == 0 ? 3.0 : (i == 1 ? 3.0 : (i == 2 ? (M_PI / 6) : M_PI));
+	}
+	__device__ static void safety_set(const double *x, double *h, double *Dh)
+	{
+#pragma unroll
+		for (int i = 0; i < 16; i++) Dh[i] = 0.0;
+#pragma unroll
+		for (int i = 0; i < 4; i++) {
+			h[i] = (bound(i) * bound(i)) - (x[i] * x[i]);
+			Dh[i * 5] = -2.0 * x[i];
+		}
+	}
+	__device__ static double backup_set_value(const double *xin)
+	{
+		double h = 0.05 * 0.05;
+#pragma unroll
+		for (int i = 0; i < 4; i++) {
+			const double xi = (CENTRED && i == 2) ? (xin[i] - 0.1383244254) : (CENTRED ? (xin[i] - 0.0) : xin[i]);
+			h -= (xi / bound(i)) * (xi / bound(i));
+		}
+		return h;
+	}
+	__device__ static void backup_set(const double *xin, double &h, double *Dh, double *DDh)
+	{
+		h = backup_set_value(xin);
+#pragma unroll
+		for (int i = 0; i < 16; i++) DDh[i] = 0.0;
+#pragma unroll
+		for (int i = 0; i < 4; i++) {
+			const double xi = (CENTRED && i == 2) ? (xin[i] - 0.1383244254) : (CENTRED ? (xin[i] - 0.0) : xin[i]);
+			Dh[i] = -2.0 * xi / (bound(i) * bound(i));
+			DDh[i * 5] = -2.0 / (bound(i) * bound(i));
+		}
+	}
+	__device__ static void backup_controller(const double *x, double *u, double *Du)
+	{
+		const double K[4] = {44.7214, 44.6528, 150.1612, 37.6492};
+		double xt[4] = {0., 0., -0.1383244254, 0.};
+#pragma unroll
+		for (int i = 0; i < 4; i++) xt[i] += x[i];
+		double s = K[0] * xt[0];
+#pragma unroll
+		for (int k = 1; k < 4; k++) s = s + K[k] * xt[k];
+		u[0] = s;
+#pragma unroll
+		for (int k = 0; k < 4; k++) Du[k] = K[k];
+	}
+	__device__ static void dynamics(const double *X, double *f, double *g)
+	{
+		// The friction term of the shipped model carries a literal factor 0.0 (:80), so every
+		// product with it is an exact zero; those terms are dropped (adding +-0.0 to a non-zero
+		// partial sum is the identity in IEEE arithmetic).
+		f[0] = X[1];
+		const double w2 = X[3] * X[3];
+		double s1, c1, s2, c2;
+		sincos(X[2], &s1, &c1);
+		sincos(2.0 * X[2], &s2, &c2);
+		const double den = 1.0 / ((14.553176960783997 + -2.0831375273848773 * c2) + -0.59146430898882 * s2);
+		f[1] = 0.0975 *
+		       (((((((44.798 *
+		                  ((-0.2693850964936445 * w2 + -0.0022454764220255392 * w2) + -0.11586336477125109 * w2) *
+		                  0.195 * c1 +
+		              59.510408935182809 * c2) +
+		             86.686408318784913 * w2 * 0.195 * s1) +
+		            0.72258001100852454 * w2 * 0.195 * s1) +
+		           37.284092841364554 * w2 * 0.195 * s1) +
+		          4.1423245261005457 * s2) +
+		         -213.73800805067131 * s2)) *
+		       den;
+		f[2] = X[3];
+		f[3] = den * (((((((89.596 * -0.45669752988922296 * c1 + 15.554616935932147 * w2 * 0.038025 * c2) +
+		                   16.405863695295427 * s1) +
+		                  249.80488266222164 * s1) +
+		                 27.713966400983114 * s1) +
+		                1.0827059060875992 * w2 * 0.038025 * s2) +
+		               -55.866072832711595 * w2 * 0.038025 * s2));
+		g[0] = 0.0;
+		const double a = 1.4575004011882324 * c1;
+		const double b = 0.20290365220710288 * s1;
+		g[1] = 0.551244194154502 * ((4.1706936767483551 + a) + b) *
+		       (1.0 / (((8.3593271361634187 + -2.1243074194638587 * (c1 * c1)) + -0.04116989207898096 * (s1 * s1)) +
+		               -0.29573215449441 * s2));
+		g[2] = 0.0;
+		g[3] = -5.65378660671284 * ((2.0043013906215941 + a) + b) * den;
+	}
+	__device__ static void dynamics_gradients(const double *x, double *Df, double *Dg)
+	{
+		double s1, c1, s2, c2;
+		sincos(x[2], &s1, &c1);
+		sincos(x[2] * 2.0, &s2, &c2);
+		const double w2 = x[3] * x[3];
+		const double th = tanh(x[1] * 1000.0);
+		const double th2 = th * th;
+		const double t25 = th * 15.13175750513302 - 40.918271887954823;
+		const double t26 = w2 * 3.3849959169972448 + th * 30.26351501026604;
+		const double t23 = 1.0 / ((c2 * 2.0831375273848769 + s2 * 0.59146430898882) - 14.553176960784);
+		Df[0] = 0.0; Df[1] = 0.0; Df[2] = 0.0; Df[3] = 0.0;
+		Df[4] = 1.0;
+		const double p = s1 * (th2 * 1000.0 - 1000.0);
+		Df[5] = -t23 * (((th2 * 8443.5211353581435 + p * 0.41077609832706019) +
+		                 c1 * (th2 * 30263.515010266041 - 30263.515010266041) * 0.0975) -
+		                8443.5211353581435);
+		Df[6] = 0.0;
+		Df[7] = t23 * (((th2 * 20808.641003022261 + p * 2.1065440939849238) +
+		                c1 * (th2 * 15131.75750513302 - 15131.75750513302)) -
+		               20808.641003022261);
+		Df[8] = 0.0;
+		const double cth = c1 * th;
+		const double sth = s1 * th;
+		const double cc = (c2 * 1.18292861797764 + -(s2 * 4.1662750547697547)) * (t23 * t23);
+		Df[9] = t23 * ((((c2 * 40.8711582872913 + s2 * 11.604529742360651) - c1 * w2 * 2.3707272057666411) +
+		                cth * 0.41077609832706019) -
+		               s1 * t26 * 0.0975) -
+		        cc * (((((c2 * -5.8022648711803244 + s2 * 20.435579143645651) + th * 8.443521135358143) -
+		                s1 * w2 * 2.3707272057666411) +
+		               sth * 0.41077609832706019) +
+		              c1 * t26 * 0.0975);
+		Df[10] = 0.0;
+		const double wc = w2 * c2;
+		const double ws = w2 * s2;
+		Df[11] = t23 * ((((c1 * -293.92471275850022 - cth * 2.1065440939849238) + wc * 4.1662750547697547) +
+		                 ws * 1.18292861797764) +
+		                s1 * t25) +
+		         cc * (((((s1 * 293.92471275850022 + th * 20.808641003022259) + wc * 0.59146430898881985) +
+		                 sth * 2.1065440939849238) -
+		                ws * 2.0831375273848769) +
+		               c1 * t25);
+		Df[12] = 0.0;
+		Df[13] = t23 * (c1 * x[3] * 0.6600742038144628 - s1 * x[3] * 4.7414544115332831);
+		Df[14] = 1.0;
+		Df[15] = -t23 * (c2 * x[3] * 1.18292861797764 - s2 * x[3] * 4.1662750547697547);
+		const double d4 = (c2 * 2.0831375273848769 + s2 * 0.59146430898882) - 14.553176960784;
+		const double d26 =
+		    ((c1 * c1 * 2.1243074194638591 + s2 * 0.29573215449441) + s1 * s1 * 0.04116989207898096) - 8.3593271361634187;
+#pragma unroll
+		for (int i = 0; i < 16; i++) Dg[i] = 0.0;
+		Dg[9] = -(c1 * 0.1118494602519098 - s1 * 0.80343863413287053) / d26 +
+		        1.0 / (d26 * d26) * (c2 * 0.59146430898882 - c1 * s1 * 4.1662750547697547) *
+		            ((c1 * 0.80343863413287053 + s1 * 0.1118494602519098) + 2.2990706749044238);
+		Dg[11] = (c1 * 1.1471739513016379 - s1 * 8.24039624751662) / d4 -
+		         1.0 / (d4 * d4) * (c2 * 1.18292861797764 - s2 * 4.1662750547697547) *
+		             ((c1 * 8.24039624751662 + s1 * 1.1471739513016379) + 11.33189235811229);
+	}
+	__device__ static void dynamics_with_gradient(const double *, const double *, double *, double *, double *) {}
+};
+
+} // namespace asifb

@@ -1,0 +1,346 @@
+// qp_gi.cuh -- exact per-thread solver for the tiny strictly convex QPs of the safety filters.
+//
+// Replaces the reference's QPWrapperOsqp::solve (src/qpwrapper_osqp.cpp:217-239, OSQP ADMM) for
+//      min v'Hv + c'v   s.t.  rows(v) >= rhs,   nv <= 4, H diagonal (diagonalCost, the default)
+// with the Goldfarb-Idnani dual active-set method: start at the unconstrained minimiser, add the
+// most violated row, take primal/dual steps that keep every multiplier non-negative, drop blocking
+// rows.  It terminates at the unique optimum (what "OSQP with polish, eps 1e-8" converges to) in
+// a handful of iterations and detects infeasibility exactly (OSQP_PRIMAL_INFEASIBLE = -3).
+//
+// Everything is per thread and in registers: NV is a template constant, all loops over NV are
+// unrolled, the active set holds at most NV rows.  Rows are presented by a functor so that the
+// caller decides where they live (shared memory for the implicit filters, computed on the fly
+// from a table for the robust/realizable ones, global memory for the generic batch entry).
+// Work is done in the metric of the Hessian (v-hat = sqrt(2H) v) with every processed row
+// normalised to unit length, so the thresholds below are scale free.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace asifb {
+
+constexpr int QP_OK = 1;
+constexpr int QP_MAX_ITER = -2;          // OSQP_MAX_ITER_REACHED
+constexpr int QP_PRIMAL_INFEASIBLE = -3; // OSQP_PRIMAL_INFEASIBLE
+
+constexpr double QP_FEAS_TOL = 1e-9;   // a row is violated when row.v - rhs < -tol * max(1, |row|_inf)
+constexpr double QP_INDEP_TOL = 1e-18; // sin^2 of the angle to the active span below this: dependent
+constexpr double QP_DUAL_TOL = 1e-12;  // dual direction entries below this are treated as <= 0
+
+// Metric of a diagonal Hessian (diagonalCost = true, the reference default):
+// gi[i] = 1/(2 H_ii), gih[i] = sqrt(gi[i]).
+template <int NV>
+struct DiagMetric {
+	double gi[NV], gih[NV];
+	__device__ __forceinline__ void unconstrained(const double (&c)[NV], double (&v)[NV]) const
+	{
+#pragma unroll
+		for (int i = 0; i < NV; i++) v[i] = -(gi[i] * c[i]);
+	}
+	__device__ __forceinline__ void to_hat(const double (&n)[NV], double (&nh)[NV]) const
+	{
+#pragma unroll
+		for (int i = 0; i < NV; i++) nh[i] = gih[i] * n[i];
+	}
+	__device__ __forceinline__ void from_hat(const double (&zh)[NV], double (&z)[NV]) const
+	{
+#pragma unroll
+		for (int i = 0; i < NV; i++) z[i] = gih[i] * zh[i];
+	}
+};
+
+// Metric of a dense SPD Hessian: 2H = L L' (lower Cholesky factor, L[i][j], j <= i).
+template <int NV>
+struct CholMetric {
+	double L[NV][NV];
+	// returns false when 2H is not positive definite
+	__device__ __forceinline__ bool factor(const double *H /* column-major NV x NV */)
+	{
+		bool ok = true;
+#pragma unroll
+		for (int j = 0; j < NV; j++) {
+			double d = 2.0 * H[j + j * NV];
+#pragma unroll
+			for (int k = 0; k < NV; k++)
+				if (k < j) d -= L[j][k] * L[j][k];
+			ok = ok && (d > 0.0);
+			d = sqrt(d);
+			L[j][j] = d;
+#pragma unroll
+			for (int i = 0; i < NV; i++) {
+				if (i > j) {
+					double t = 2.0 * H[i + j * NV];
+#pragma unroll
+					for (int k = 0; k < NV; k++)
+						if (k < j) t -= L[i][k] * L[j][k];
+					L[i][j] = t / d;
+				}
+			}
+		}
+		return ok;
+	}
+	__device__ __forceinline__ void fwd(double (&y)[NV]) const // y <- L^-1 y
+	{
+#pragma unroll
+		for (int i = 0; i < NV; i++) {
+			double t = y[i];
+#pragma unroll
+			for (int k = 0; k < NV; k++)
+				if (k < i) t -= L[i][k] * y[k];
+			y[i] = t / L[i][i];
+		}
+	}
+	__device__ __forceinline__ void bwd(double (&y)[NV]) const // y <- L^-T y
+	{
+#pragma unroll
+		for (int i = NV - 1; i >= 0; i--) {
+			double t = y[i];
+#pragma unroll
+			for (int k = 0; k < NV; k++)
+				if (k > i) t -= L[k][i] * y[k];
+			y[i] = t / L[i][i];
+		}
+	}
+	__device__ __forceinline__ void unconstrained(const double (&c)[NV], double (&v)[NV]) const
+	{
+#pragma unroll
+		for (int i = 0; i < NV; i++) v[i] = -c[i];
+		fwd(v);
+		bwd(v);
+	}
+	__device__ __forceinline__ void to_hat(const double (&n)[NV], double (&nh)[NV]) const
+	{
+#pragma unroll
+		for (int i = 0; i < NV; i++) nh[i] = n[i];
+		fwd(nh);
+	}
+	__device__ __forceinline__ void from_hat(const double (&zh)[NV], double (&z)[NV]) const
+	{
+#pragma unroll
+		for (int i = 0; i < NV; i++) z[i] = zh[i];
+		bwd(z);
+	}
+};
+
+template <int NV>
+struct QpWork {
+	double v[NV];
+	double mu[NV];
+	double Q[NV][NV]; // Q[a][:] orthonormal basis vector a (hat space)
+	double R[NV][NV]; // upper triangular, R[b][a] for b <= a
+	int act[NV];
+	int q;
+};
+
+// fetch row j, scale into hat space and normalise.  returns the hat-space length.
+template <int NV, class Rows, class Metric>
+__device__ __forceinline__ double qp_fetch_unit_row(const Rows &rows, int j, const Metric &mt, double (&nh)[NV],
+                                                    double &rhs)
+{
+	double n[NV];
+	rows.get(j, n, rhs);
+	mt.to_hat(n, nh);
+	double len2 = 0.0;
+#pragma unroll
+	for (int i = 0; i < NV; i++) len2 += nh[i] * nh[i];
+	const double len = sqrt(len2);
+	const double inv = 1.0 / len;
+#pragma unroll
+	for (int i = 0; i < NV; i++) nh[i] *= inv;
+	return len;
+}
+
+// rebuild Q, R from the current active set (modified Gram-Schmidt in hat space)
+template <int NV, class Rows, class Metric>
+__device__ __forceinline__ void qp_rebuild(QpWork<NV> &w, const Rows &rows, const Metric &mt)
+{
+#pragma unroll
+	for (int a = 0; a < NV; a++) {
+		if (a < w.q) {
+			double nh[NV], rhs;
+			qp_fetch_unit_row<NV>(rows, w.act[a], mt, nh, rhs);
+#pragma unroll
+			for (int b = 0; b < NV; b++) {
+				if (b < a) {
+					double d = 0.0;
+#pragma unroll
+					for (int i = 0; i < NV; i++) d += w.Q[b][i] * nh[i];
+					w.R[b][a] = d;
+#pragma unroll
+					for (int i = 0; i < NV; i++) nh[i] -= d * w.Q[b][i];
+				}
+			}
+			double l2 = 0.0;
+#pragma unroll
+			for (int i = 0; i < NV; i++) l2 += nh[i] * nh[i];
+			const double l = sqrt(l2);
+			w.R[a][a] = l;
+			const double inv = 1.0 / l;
+#pragma unroll
+			for (int i = 0; i < NV; i++) w.Q[a][i] = nh[i] * inv;
+		}
+	}
+}
+
+// v returns the minimiser when the result is QP_OK.
+// iters (optional) returns the number of rows processed (for the K-bar statistic).
+template <int NV, class Rows, class Metric>
+__device__ __forceinline__ int qp_gi_solve(const Metric &mt, const double (&c)[NV], const Rows &rows, double (&v)[NV],
+                                           int *iters = nullptr)
+{
+	QpWork<NV> w;
+	w.q = 0;
+	mt.unconstrained(c, w.v);
+#pragma unroll
+	for (int i = 0; i < NV; i++) {
+		w.mu[i] = 0.0;
+		w.act[i] = -1;
+	}
+	const int m = rows.count();
+	int status = QP_MAX_ITER;
+	int it = 0;
+	const int max_outer = 4 * NV + 24;
+	for (; it < max_outer; it++) {
+		// ---- most violated row that is not active
+		int p = -1;
+		double sp = 0.0;
+		for (int j = 0; j < m; j++) {
+			double n[NV], rhs;
+			rows.get(j, n, rhs);
+			double s = -rhs, nmax = 1.0;
+#pragma unroll
+			for (int i = 0; i < NV; i++) {
+				s += n[i] * w.v[i];
+				nmax = fmax(nmax, fabs(n[i]));
+			}
+			bool is_act = false;
+#pragma unroll
+			for (int a = 0; a < NV; a++) is_act |= (a < w.q) && (w.act[a] == j);
+			if (!is_act && s < -QP_FEAS_TOL * nmax && s < sp) {
+				sp = s;
+				p = j;
+			}
+		}
+		if (p < 0) {
+			status = QP_OK;
+			break;
+		}
+		double nh[NV], rhs;
+		const double len = qp_fetch_unit_row<NV>(rows, p, mt, nh, rhs);
+		if (!(len > 0.0)) { // 0 >= rhs with rhs > 0
+			status = QP_PRIMAL_INFEASIBLE;
+			break;
+		}
+		sp = sp / len;
+		double mu_p = 0.0;
+		bool failed = false;
+		// ---- primal/dual steps until row p becomes active (at most q drops)
+		for (int inner = 0; inner <= NV + 1; inner++) {
+			double d[NV], zh[NV], r[NV];
+#pragma unroll
+			for (int i = 0; i < NV; i++) zh[i] = nh[i];
+#pragma unroll
+			for (int a = 0; a < NV; a++) {
+				d[a] = 0.0;
+				if (a < w.q) {
+					double t = 0.0;
+#pragma unroll
+					for (int i = 0; i < NV; i++) t += w.Q[a][i] * zh[i];
+					d[a] = t;
+#pragma unroll
+					for (int i = 0; i < NV; i++) zh[i] -= t * w.Q[a][i];
+				}
+			}
+			double zz = 0.0;
+#pragma unroll
+			for (int i = 0; i < NV; i++) zz += zh[i] * zh[i];
+			// r = R^-1 d (back substitution over the active part)
+#pragma unroll
+			for (int a = NV - 1; a >= 0; a--) {
+				r[a] = 0.0;
+				if (a < w.q) {
+					double t = d[a];
+#pragma unroll
+					for (int b = a + 1; b < NV; b++)
+						if (b < w.q) t -= w.R[a][b] * r[b];
+					r[a] = t / w.R[a][a];
+				}
+			}
+			double t1 = INFINITY;
+			int l = -1;
+#pragma unroll
+			for (int a = 0; a < NV; a++) {
+				if (a < w.q && r[a] > QP_DUAL_TOL) {
+					const double t = w.mu[a] / r[a];
+					if (t < t1) {
+						t1 = t;
+						l = a;
+					}
+				}
+			}
+			const bool indep = (w.q < NV) && (zz > QP_INDEP_TOL);
+			const double t2 = indep ? (-sp / zz) : INFINITY;
+			if (l < 0 && !indep) {
+				failed = true;
+				break;
+			}
+			if (t2 <= t1) { // full step: row p becomes active
+				double z[NV];
+				mt.from_hat(zh, z);
+#pragma unroll
+				for (int i = 0; i < NV; i++) w.v[i] += t2 * z[i];
+#pragma unroll
+				for (int a = 0; a < NV; a++)
+					if (a < w.q) w.mu[a] -= t2 * r[a];
+				mu_p += t2;
+				const double zl = sqrt(zz);
+				const double inv = 1.0 / zl;
+#pragma unroll
+				for (int a = 0; a < NV; a++) {
+					if (a == w.q) {
+						w.act[a] = p;
+						w.mu[a] = mu_p;
+						w.R[a][a] = zl;
+#pragma unroll
+						for (int i = 0; i < NV; i++) w.Q[a][i] = zh[i] * inv;
+#pragma unroll
+						for (int b = 0; b < NV; b++)
+							if (b < a) w.R[b][a] = d[b];
+					}
+				}
+				w.q++;
+				break;
+			}
+			// partial step: blocking row l leaves the active set
+			if (indep) {
+				double z[NV];
+				mt.from_hat(zh, z);
+#pragma unroll
+				for (int i = 0; i < NV; i++) w.v[i] += t1 * z[i];
+				sp += t1 * zz;
+			}
+#pragma unroll
+			for (int a = 0; a < NV; a++)
+				if (a < w.q) w.mu[a] -= t1 * r[a];
+			mu_p += t1;
+#pragma unroll
+			for (int a = 0; a < NV - 1; a++) {
+				if (a >= l && a + 1 < w.q) {
+					w.act[a] = w.act[a + 1];
+					w.mu[a] = w.mu[a + 1];
+				}
+			}
+			w.q--;
+			qp_rebuild<NV>(w, rows, mt);
+		}
+		if (failed) {
+			status = QP_PRIMAL_INFEASIBLE;
+			break;
+		}
+	}
+	if (iters) *iters = it;
+#pragma unroll
+	for (int i = 0; i < NV; i++) v[i] = w.v[i];
+	return status;
+}
+
+} // namespace asifb

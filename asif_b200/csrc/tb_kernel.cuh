@@ -1,0 +1,530 @@
+// tb_kernel.cuh -- batched ASIFimplicitTB::filter, one state per thread, everything fused:
+// backup-trajectory + sensitivity integration -> streaming critical-point selection ->
+// time-to-safety -> constraint-row assembly -> exact QP -> saturation / fallback.
+//
+// Reference path replaced: src/asif_implicit_tb.cpp:261-363 (filter), :407-714
+// (updateConstraints), :833-909 (closed-loop rhs), plus the OSQP solve behind
+// src/qpwrapper_osqp.cpp:217-239.
+//
+// Design (B200): the per-state work is a strictly sequential FP64 recurrence of a few thousand
+// operations on 6..20 doubles, with 44 B of HBM traffic per state, so the kernel is bound by the
+// FP64 pipe, not by memory.  One state per *thread* keeps all 32 lanes of a warp on the FP64
+// pipe (one state per warp would idle >= 26 of 32 lanes for nx = 2).  The trajectory is never
+// stored: each thread keeps a running list of the NPBTSS smallest min-h points seen so far
+// (keys in registers, (x_i, Q_i) snapshots in shared memory, laid out [slot][element][thread] so
+// that every access is bank-conflict free whatever slot a lane writes), frozen at the first
+// point inside the backup set.  Rows go to shared memory in the same layout and are consumed by
+// the register-resident dual active-set QP.
+#pragma once
+#include "filter_common.cuh"
+#include "qp_gi.cuh"
+
+namespace asifb {
+
+constexpr int TB_THREADS = 128;
+
+template <int NPBTSS>
+struct TbDiagLayout {
+	// [TTS, BTorthoBS, hSafetyNow, hBackupEnd, critIdx[NPBTSS], A (nc*nv col-major), b (nc)]
+	static constexpr int HEAD = 4 + NPBTSS;
+};
+
+// rows of the TB QP in shared memory + the variable bounds
+template <int NV, int NC>
+struct TbRows {
+	const double *rows; // [(NC)*(NV+1)][blockDim] view, already offset by threadIdx.x
+	int stride;         // blockDim.x
+	double lb[NV], ub[NV];
+	__device__ __forceinline__ int count() const { return NC + 2 * NV; }
+	__device__ __forceinline__ void get(int j, double (&n)[NV], double &rhs) const
+	{
+		if (j < NC) {
+#pragma unroll
+			for (int i = 0; i < NV; i++) n[i] = rows[(j * (NV + 1) + i) * stride];
+			rhs = rows[(j * (NV + 1) + NV) * stride];
+		} else {
+			const int k = j - NC;
+			const int var = k >> 1;
+			const bool upper = k & 1;
+#pragma unroll
+			for (int i = 0; i < NV; i++) n[i] = (i == var) ? (upper ? -1.0 : 1.0) : 0.0;
+			double bnd = 0.0;
+#pragma unroll
+			for (int i = 0; i < NV; i++)
+				if (i == var) bnd = upper ? -ub[i] : lb[i];
+			rhs = bnd;
+		}
+	}
+};
+
+// shared memory doubles per thread
+template <class M, int NPBTSS>
+__host__ __device__ constexpr int tb_smem_doubles_per_thread()
+{
+	constexpr int NS = M::NX + M::NX * M::NX;
+	constexpr int NC = NPBTSS * M::NPSS + 2;
+	constexpr int NV = M::NU + 1;
+	return (NPBTSS + 1) * NS + NC * (NV + 1);
+}
+
+template <int NPBTSS>
+struct TbDiagRec {
+	double TTS, ortho, hSafetyNow, hBackupEnd;
+	int critIdx[NPBTSS];
+	bool have_rows;
+};
+
+// One reference filter() call for one state (src/asif_implicit_tb.cpp:261-363).  snap / rows are
+// this thread's shared-memory views (already offset by threadIdx.x, element stride T).  Must be
+// called by all 32 lanes of a warp together (warp-uniform early exit from the trajectory loop).
+template <class M, int NPBTSS, bool WITH_DIAG>
+__device__ __forceinline__ int32_t tb_filter_one(const TbParams &p, const double (&x0)[M::NX], const double (&ud)[M::NU],
+                                                 double *snap, double *rows, const int T, double (&uo)[M::NU],
+                                                 double &relax, int &qp_iters, TbDiagRec<NPBTSS> &dg)
+{
+	constexpr int NX = M::NX, NU = M::NU, NPSS = M::NPSS;
+	constexpr int NS = NX + NX * NX;
+	constexpr int NC = NPBTSS * NPSS + 2;
+	constexpr int NV = NU + 1;
+
+	// ---- filter(): h_BS(x), hSafetyNow (:278-283)
+	double hs[NPSS], Dhs[NPSS * NX];
+	M::safety_set(x0, hs, Dhs);
+	double hSafetyNow = hs[0];
+#pragma unroll
+	for (int j = 1; j < NPSS; j++) hSafetyNow = (hs[j] < hSafetyNow) ? hs[j] : hSafetyNow;
+	const bool inside = M::backup_set_value(x0) >= 0;
+
+	// ---- backup trajectory (Euler, :464-487) with streaming selection and hit detection (:505-528)
+	double X[NS];
+#pragma unroll
+	for (int i = 0; i < NS; i++) X[i] = 0.0;
+#pragma unroll
+	for (int i = 0; i < NX; i++) X[i] = x0[i];
+#pragma unroll
+	for (int i = 0; i < NX; i++) X[NX + i * (NX + 1)] = 1.0;
+
+	double key[NPBTSS]; // ascending; +inf = empty
+	int kidx[NPBTSS], kslot[NPBTSS];
+#pragma unroll
+	for (int s = 0; s < NPBTSS; s++) {
+		key[s] = INFINITY;
+		kidx[s] = -1;
+		kslot[s] = s;
+	}
+	int nkept = 0;
+	// point 0
+	{
+		key[0] = hSafetyNow;
+		kidx[0] = 0;
+		nkept = 1;
+#pragma unroll
+		for (int e = 0; e < NS; e++) snap[(kslot[0] * NS + e) * T] = X[e];
+	}
+	bool hit = false;
+	int idxHit = 0;
+	double tHit = 0.0, tNow = 0.0;
+	double hBackupEnd = 0.0;
+	const int N = p.npBT;
+	const bool run = !inside;
+	for (int i = 1; i < N; i++) {
+		if (!WITH_DIAG) {
+			if (__all_sync(0xffffffffu, hit || !run)) break;
+		}
+		tNow = tNow + p.backTrajDt;
+		// rhs (:899-909)
+		double Xd[NS], DfCL[NX * NX];
+		backup_cl_dynamics<M>(p.sat, p.lb, p.ub, X, Xd, DfCL);
+#pragma unroll
+		for (int r = 0; r < NX; r++)
+#pragma unroll
+			for (int c = 0; c < NX; c++) {
+				double acc = DfCL[r] * X[NX + c * NX];
+#pragma unroll
+				for (int m = 1; m < NX; m++) acc = acc + DfCL[r + m * NX] * X[NX + m + c * NX];
+				Xd[NX + r + c * NX] = acc;
+			}
+		// Euler: (rhs*dt) + prev, two roundings (:477-480)
+#pragma unroll
+		for (int e = 0; e < NS; e++) X[e] = Xd[e] * p.backTrajDt + X[e];
+		if (hit) continue; // selection and hit scan are frozen after the first hit (:507,539)
+		M::safety_set(X, hs, Dhs);
+		double hmin = hs[0];
+#pragma unroll
+		for (int j = 1; j < NPSS; j++) hmin = (hs[j] < hmin) ? hs[j] : hmin;
+		if (run && hmin < key[NPBTSS - 1]) {
+			// evict the largest key, insert (hmin, i) keeping ascending order; ties keep the earlier index first
+			const int slot = kslot[NPBTSS - 1];
+#pragma unroll
+			for (int e = 0; e < NS; e++) snap[(slot * NS + e) * T] = X[e];
+			double ck = hmin;
+			int ci = i, cs = slot;
+			bool ins = false; // once placed, everything behind shifts by one
+#pragma unroll
+			for (int s = 0; s < NPBTSS; s++) {
+				const bool sw = ins || (ck < key[s]);
+				ins = sw;
+				const double tk = key[s];
+				const int ti = kidx[s], ts = kslot[s];
+				key[s] = sw ? ck : tk;
+				kidx[s] = sw ? ci : ti;
+				kslot[s] = sw ? cs : ts;
+				ck = sw ? tk : ck;
+				ci = sw ? ti : ci;
+				cs = sw ? ts : cs;
+			}
+			nkept = nkept < NPBTSS ? nkept + 1 : NPBTSS;
+		}
+		if (run && M::backup_set_value(X) >= 0.0) {
+			hit = true;
+			idxHit = i;
+			tHit = tNow;
+#pragma unroll
+			for (int e = 0; e < NS; e++) snap[(NPBTSS * NS + e) * T] = X[e];
+		}
+	}
+	if (WITH_DIAG) hBackupEnd = M::backup_set_value(X);
+
+	// ---- cost (:198-212, 735-746) and bounds
+	double c[NV];
+	DiagMetric<NV> mt;
+	TbRows<NV, NC> R;
+	R.rows = rows;
+	R.stride = T;
+#pragma unroll
+	for (int i = 0; i < NU; i++) {
+		c[i] = -2.0 * ud[i];
+		R.lb[i] = p.lb[i];
+		R.ub[i] = p.ub[i];
+	}
+	c[NU] = -2.0 * p.relaxCost * p.relaxSafeLb;
+	R.lb[NU] = p.relaxSafeLb;
+	R.ub[NU] = p.inf;
+#pragma unroll
+	for (int i = 0; i < NV; i++) {
+		mt.gi[i] = p.gi[i];
+		mt.gih[i] = p.gih[i];
+	}
+
+	double TTS = 0.0, ortho = 1.0;
+	int32_t rc;
+	bool solve = true;
+	if (inside) {
+		// updateConstraintsTrivial (:716-733): A = 0, b = -inf
+#pragma unroll
+		for (int j = 0; j < NC; j++) {
+#pragma unroll
+			for (int i = 0; i < NV; i++) rows[(j * (NV + 1) + i) * T] = 0.0;
+			rows[(j * (NV + 1) + NV) * T] = -p.inf;
+		}
+		rc = 2;
+	} else if (!hit) {
+		ortho = 0.0;
+		rc = -3; // backup set not reached (:354-361)
+		solve = false;
+	} else {
+		rc = 1;
+		double f[NX], g[NX * NU];
+		if (M::FUSED_GRADIENT) {
+			double u0[NU], dtmp[NX * NX];
+#pragma unroll
+			for (int i = 0; i < NU; i++) u0[i] = 0.0;
+			M::dynamics_with_gradient(x0, u0, f, g, dtmp); // the dynamics_ lambda of :79-86
+		} else {
+			M::dynamics(x0, f, g);
+		}
+		// safety rows of the critical points (:554-586)
+#pragma unroll
+		for (int s = 0; s < NPBTSS; s++) {
+			if (s >= nkept) {
+#pragma unroll
+				for (int j = 0; j < NPSS; j++) {
+					const int row = s * NPSS + j;
+#pragma unroll
+					for (int i = 0; i < NU; i++) rows[(row * (NV + 1) + i) * T] = 0.0;
+					rows[(row * (NV + 1) + NU) * T] = 1.0; // h = 1, Dh = 0 (:556-566)
+					rows[(row * (NV + 1) + NV) * T] = -0.0;
+				}
+			} else {
+				double xs[NS];
+				const int slot = kslot[s];
+#pragma unroll
+				for (int e = 0; e < NS; e++) xs[e] = snap[(slot * NS + e) * T];
+				M::safety_set(xs, hs, Dhs);
+#pragma unroll
+				for (int j = 0; j < NPSS; j++) {
+					// Dh_row = DhSS(x_i) Q_i  (:574-584), then Lfh = Dh f, Lgh = Dh g (:643-653)
+					double dh[NX];
+#pragma unroll
+					for (int cc = 0; cc < NX; cc++) {
+						double acc = Dhs[j] * xs[NX + cc * NX];
+#pragma unroll
+						for (int m = 1; m < NX; m++) acc = acc + Dhs[j + m * NPSS] * xs[NX + m + cc * NX];
+						dh[cc] = acc;
+					}
+					double lf = dh[0] * f[0];
+#pragma unroll
+					for (int m = 1; m < NX; m++) lf = lf + dh[m] * f[m];
+					const int row = s * NPSS + j;
+#pragma unroll
+					for (int i = 0; i < NU; i++) {
+						double lg = dh[0] * g[i * NX];
+#pragma unroll
+						for (int m = 1; m < NX; m++) lg = lg + dh[m] * g[m + i * NX];
+						rows[(row * (NV + 1) + i) * T] = lg;
+					}
+					rows[(row * (NV + 1) + NU) * T] = hs[j];
+					rows[(row * (NV + 1) + NV) * T] = -lf;
+				}
+			}
+		}
+		// time-to-safety and orthogonality rows (:588-641)
+		double xh[NS];
+#pragma unroll
+		for (int e = 0; e < NS; e++) xh[e] = snap[(NPBTSS * NS + e) * T];
+		double hBS, DhBS[NX], DDhBS[NX * NX], fCl[NX], DfCl[NX * NX];
+		M::backup_set(xh, hBS, DhBS, DDhBS);
+		backup_cl_dynamics<M>(p.sat, p.lb, p.ub, xh, fCl, DfCl);
+		double cosT = DhBS[0] * fCl[0];
+#pragma unroll
+		for (int m = 1; m < NX; m++) cosT = cosT + DhBS[m] * fCl[m];
+		double n1 = 0.0, n2 = 0.0;
+#pragma unroll
+		for (int m = 0; m < NX; m++) {
+			n1 += DhBS[m] * DhBS[m];
+			n2 += fCl[m] * fCl[m];
+		}
+		const double den1 = sqrt(n1), den2 = sqrt(n2);
+		const double den = den1 * den2;
+		ortho = cosT / den;
+		TTS = tHit;
+		const double hReach = p.backTrajHorizon - tHit;
+		double DhBSDx[NX];
+#pragma unroll
+		for (int cc = 0; cc < NX; cc++) {
+			double acc = DhBS[0] * xh[NX + cc * NX];
+#pragma unroll
+			for (int m = 1; m < NX; m++) acc = acc + DhBS[m] * xh[NX + m + cc * NX];
+			DhBSDx[cc] = acc;
+		}
+		double dhT[NX], dhO[NX];
+#pragma unroll
+		for (int i = 0; i < NX; i++) dhT[i] = DhBSDx[i] / cosT;
+		const double hOrtho = ortho - p.backTrajMinOrtho;
+		double DxHit[NX * NX];
+#pragma unroll
+		for (int r = 0; r < NX; r++)
+#pragma unroll
+			for (int cc = 0; cc < NX; cc++) DxHit[r + cc * NX] = xh[NX + r + cc * NX] - fCl[r] * DhBSDx[cc];
+		const double denSq = den * den;
+#pragma unroll
+		for (int i = 0; i < NX; i++) {
+			double Dnum = 0.0, Dden1 = 0.0, Dden2 = 0.0;
+#pragma unroll
+			for (int kq = 0; kq < NX; kq++) {
+				double t1 = 0.0, t2 = 0.0;
+#pragma unroll
+				for (int l = 0; l < NX; l++) {
+					t1 += DDhBS[kq + l * NX] * DxHit[l + i * NX];
+					t2 += DfCl[kq + l * NX] * DxHit[l + i * NX];
+				}
+				const double t3 = DhBS[kq] * t2;
+				const double t4 = t1 * fCl[kq];
+				Dden1 += t3;
+				Dden2 += t4;
+				Dnum += t3 + t4;
+			}
+			const double Dden = den2 * Dden1 / den1 + den1 * Dden2 / den2;
+			dhO[i] = (Dnum * den - cosT * Dden) / denSq;
+		}
+		// TTS row and ortho row: Lgh u >= -Lfh - relax*h, no relax-variable column (:655-674)
+		{
+			double lfT = dhT[0] * f[0], lfO = dhO[0] * f[0];
+#pragma unroll
+			for (int m = 1; m < NX; m++) {
+				lfT = lfT + dhT[m] * f[m];
+				lfO = lfO + dhO[m] * f[m];
+			}
+			const int rT = NPBTSS * NPSS, rO = NPBTSS * NPSS + 1;
+#pragma unroll
+			for (int i = 0; i < NU; i++) {
+				double lgT = dhT[0] * g[i * NX], lgO = dhO[0] * g[i * NX];
+#pragma unroll
+				for (int m = 1; m < NX; m++) {
+					lgT = lgT + dhT[m] * g[m + i * NX];
+					lgO = lgO + dhO[m] * g[m + i * NX];
+				}
+				rows[(rT * (NV + 1) + i) * T] = lgT;
+				rows[(rO * (NV + 1) + i) * T] = lgO;
+			}
+			rows[(rT * (NV + 1) + NU) * T] = 0.0;
+			rows[(rO * (NV + 1) + NU) * T] = 0.0;
+			rows[(rT * (NV + 1) + NV) * T] = -lfT - p.relaxTTS * hReach;
+			rows[(rO * (NV + 1) + NV) * T] = -lfO - p.relaxMinOrtho * hOrtho;
+		}
+	}
+
+	// ---- QP + post-solve (:324-352)
+	double v[NV];
+	relax = 0.0;
+	qp_iters = 0;
+	int st = QP_PRIMAL_INFEASIBLE;
+	if (solve) st = qp_gi_solve<NV>(mt, c, R, v, &qp_iters);
+	if (solve && st == QP_OK) {
+#pragma unroll
+		for (int i = 0; i < NU; i++) uo[i] = input_saturate(v[i], p.lb[i], p.ub[i]);
+		relax = v[NU];
+	} else {
+		double Du[NU * NX];
+		M::backup_controller(x0, uo, Du);
+#pragma unroll
+		for (int i = 0; i < NU; i++) uo[i] = input_saturate(uo[i], p.lb[i], p.ub[i]);
+		if (solve) rc = (rc == 2) ? -1 : st;
+	}
+	if (WITH_DIAG) {
+		dg.TTS = TTS;
+		dg.ortho = ortho;
+		dg.hSafetyNow = hSafetyNow;
+		dg.hBackupEnd = hBackupEnd;
+#pragma unroll
+		for (int s = 0; s < NPBTSS; s++) dg.critIdx[s] = (!inside && hit && s < nkept) ? kidx[s] : -1;
+		dg.have_rows = inside || hit;
+	}
+	return rc;
+}
+
+template <class M, int NPBTSS, bool WITH_DIAG>
+__global__ void __launch_bounds__(TB_THREADS)
+tb_filter_kernel(const TbParams p, const int64_t n, const double *__restrict__ x_in, const double *__restrict__ u_des,
+                 double *__restrict__ u_act, double *__restrict__ relax_out, int32_t *__restrict__ rc_out,
+                 double *__restrict__ diag, unsigned long long *__restrict__ qp_iter_sum)
+{
+	constexpr int NX = M::NX, NU = M::NU, NPSS = M::NPSS;
+	constexpr int NS = NX + NX * NX;
+	constexpr int NC = NPBTSS * NPSS + 2;
+	constexpr int NV = NU + 1;
+	constexpr int NDIAG = TbDiagLayout<NPBTSS>::HEAD + NC * NV + NC;
+
+	extern __shared__ double smem[];
+	const int T = blockDim.x;
+	double *snap = smem + threadIdx.x;                                  // [(NPBTSS+1)*NS][T]
+	double *rows = smem + (size_t)(NPBTSS + 1) * NS * T + threadIdx.x; // [NC*(NV+1)][T]
+
+	const int64_t k = (int64_t)blockIdx.x * T + threadIdx.x;
+	const bool live = k < n;
+	const int64_t kk = live ? k : (n - 1); // tail lanes redo the last state and do not store
+
+	double x0[NX], ud[NU];
+#pragma unroll
+	for (int i = 0; i < NX; i++) x0[i] = x_in[kk * NX + i];
+#pragma unroll
+	for (int i = 0; i < NU; i++) ud[i] = u_des[kk * NU + i];
+
+	double uo[NU], relax;
+	int qp_iters;
+	TbDiagRec<NPBTSS> dg;
+	const int32_t rc = tb_filter_one<M, NPBTSS, WITH_DIAG>(p, x0, ud, snap, rows, T, uo, relax, qp_iters, dg);
+
+	if (live) {
+#pragma unroll
+		for (int i = 0; i < NU; i++) u_act[k * NU + i] = uo[i];
+		relax_out[k] = relax;
+		rc_out[k] = rc;
+		if (WITH_DIAG) {
+			double *d = diag + k * NDIAG;
+			d[0] = dg.TTS;
+			d[1] = dg.ortho;
+			d[2] = dg.hSafetyNow;
+			d[3] = dg.hBackupEnd;
+#pragma unroll
+			for (int s = 0; s < NPBTSS; s++) d[4 + s] = (double)dg.critIdx[s];
+			for (int j = 0; j < NC; j++) {
+				for (int i = 0; i < NV; i++)
+					d[4 + NPBTSS + j + i * NC] = dg.have_rows ? rows[(j * (NV + 1) + i) * T] : 0.0;
+				d[4 + NPBTSS + NC * NV + j] = dg.have_rows ? rows[(j * (NV + 1) + NV) * T] : 0.0;
+			}
+		}
+	}
+	if (qp_iter_sum) {
+		unsigned int it = live ? (unsigned int)qp_iters : 0u;
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) it += __shfl_xor_sync(0xffffffffu, it, o);
+		if ((threadIdx.x & 31) == 0 && it) atomicAdd(qp_iter_sum, (unsigned long long)it);
+	}
+}
+
+// Closed-loop rollout (examples/segway_implicit_tb.cpp:251-283): the state never leaves the
+// registers between control steps; one launch covers all steps of every agent.
+template <class M, int NPBTSS>
+__global__ void __launch_bounds__(TB_THREADS)
+tb_rollout_kernel(const TbParams p, const int64_t n, const int32_t steps, const double dt_plant, double *__restrict__ x_io,
+                  const double *__restrict__ u_des, double *__restrict__ u_act_last, int32_t *__restrict__ rc_last,
+                  unsigned long long *__restrict__ rc_hist, unsigned long long *__restrict__ qp_iter_sum)
+{
+	constexpr int NX = M::NX, NU = M::NU;
+	constexpr int NS = NX + NX * NX;
+	extern __shared__ double smem[];
+	const int T = blockDim.x;
+	double *snap = smem + threadIdx.x;
+	double *rows = smem + (size_t)(NPBTSS + 1) * NS * T + threadIdx.x;
+	const int64_t k = (int64_t)blockIdx.x * T + threadIdx.x;
+	const bool live = k < n;
+	const int64_t kk = live ? k : (n - 1);
+	double x[NX], ud[NU], uo[NU];
+#pragma unroll
+	for (int i = 0; i < NX; i++) x[i] = x_io[kk * NX + i];
+#pragma unroll
+	for (int i = 0; i < NU; i++) {
+		ud[i] = u_des[kk * NU + i];
+		uo[i] = 0.0;
+	}
+	int32_t rc = 0;
+	unsigned int hist[8];
+#pragma unroll
+	for (int i = 0; i < 8; i++) hist[i] = 0;
+	unsigned long long iters = 0;
+	for (int32_t s = 0; s < steps; s++) {
+		double relax;
+		int qp_iters;
+		TbDiagRec<NPBTSS> dg;
+		rc = tb_filter_one<M, NPBTSS, false>(p, x, ud, snap, rows, T, uo, relax, qp_iters, dg);
+		iters += (unsigned long long)qp_iters;
+		const int slot = (rc >= -3 && rc <= 2) ? rc + 3 : 7;
+#pragma unroll
+		for (int i = 0; i < 8; i++) hist[i] += (i == slot) ? 1u : 0u;
+		// plant step: fCl = f + g uAct ; x += dt*fCl  (:265-283)
+		double f[NX], g[NX * NU];
+		M::dynamics(x, f, g);
+#pragma unroll
+		for (int i = 0; i < NX; i++) {
+			double fcl = f[i];
+#pragma unroll
+			for (int j = 0; j < NU; j++) fcl += g[i + j * NX] * uo[j];
+			x[i] += dt_plant * fcl;
+		}
+	}
+	if (live) {
+#pragma unroll
+		for (int i = 0; i < NX; i++) x_io[k * NX + i] = x[i];
+#pragma unroll
+		for (int i = 0; i < NU; i++) u_act_last[k * NU + i] = uo[i];
+		rc_last[k] = rc;
+	}
+	if (rc_hist) {
+#pragma unroll
+		for (int i = 0; i < 8; i++) {
+			unsigned int c = live ? hist[i] : 0u;
+#pragma unroll
+			for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+			if ((threadIdx.x & 31) == 0 && c) atomicAdd(rc_hist + i, (unsigned long long)c);
+		}
+	}
+	if (qp_iter_sum) {
+		unsigned long long it = live ? iters : 0ull;
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) it += __shfl_xor_sync(0xffffffffu, it, o);
+		if ((threadIdx.x & 31) == 0 && it) atomicAdd(qp_iter_sum, it);
+	}
+}
+
+} // namespace asifb

@@ -1,0 +1,163 @@
+/*
+ * asif_b200.h -- C ABI of the B200 batched safety-filter engine (libasif_b200.so).
+ *
+ * This is the drop-in boundary: plain C types, pointers and sizes only.  The C++ host layer
+ * (asif_b200/host/asif_b200.hpp: ASIF::QPWrapperB200, ASIF::FilterBatch*) and any foreign
+ * binding (ctypes, cgo, JNI ...) sit on top of exactly these entry points.  Every entry point
+ * names the reference interface it replaces (paths relative to DrewSingletary/asif).
+ *
+ * Conventions (same as the reference):
+ *   - all reals are FP64; matrices are dense column-major (A[i + j*nc]), include/qpwrapper_abstract.h:11-15
+ *   - a batch is an array of states: x[n][nx], u_des[n][nu], u_act[n][nu], relax[n][n_relax], rc[n]
+ *   - per-state outcomes are reported only through rc[] with the reference's codes
+ *     (src/asif_implicit_tb.cpp:300-361,911-933; src/asif.cpp:199-209); a failing state never
+ *     aborts the batch.  Function return values are 0 on success or a negative ASIF_ERR_* code;
+ *     asif_last_error() gives the message (thread local).
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef ASIF_B200_H
+#define ASIF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ASIF_B200_ABI_VERSION 1
+
+/* error codes (function return values) */
+#define ASIF_OK 0
+#define ASIF_ERR_INVALID_ARGUMENT (-1)
+#define ASIF_ERR_UNSUPPORTED (-2)
+#define ASIF_ERR_CUDA (-3)
+#define ASIF_ERR_NO_DEVICE (-4)
+
+/* filter classes of the reference */
+#define ASIF_FILTER_EXPLICIT 1    /* ASIF::ASIF            include/asif.h:39-65           */
+#define ASIF_FILTER_IMPLICIT_TB 2 /* ASIF::ASIFimplicitTB  include/asif_implicit_tb.h:93-110 */
+#define ASIF_FILTER_IMPLICIT 3    /* ASIF::ASIFimplicit    include/asif_implicit.h:96-113 */
+#define ASIF_FILTER_ROBUST 4      /* ASIF::ASIFrobust      include/asif_robust.h:41-59    */
+#define ASIF_FILTER_REALIZABLE 5  /* ASIF::ASIFrealizable  include/asif_realizable.h:58-76 */
+
+/* models: the reference passes std::function callbacks; on the device a model is a compiled-in
+ * functor with the same five callback signatures (asif_b200/csrc/models.cuh). */
+#define ASIF_MODEL_DOUBLE_INTEGRATOR 1    /* examples/DoubleIntegrator.cpp:12-61              */
+#define ASIF_MODEL_DOUBLE_INTEGRATOR_TB 2 /* examples/DoubleIntegrator_implicit_tb.cpp:13-85  */
+#define ASIF_MODEL_INVERTED_PENDULUM 3    /* examples/InvertedPendulum_Implicit.cpp:13-80     */
+#define ASIF_MODEL_INVERTED_PENDULUM_TABLE 4 /* examples/InvertedPendulum_Robust.cpp:53-79 + half-plane table */
+#define ASIF_MODEL_SEGWAY 6               /* examples/segway_implicit_tb.cpp:13-212, backup set centred on the controller equilibrium */
+#define ASIF_MODEL_SEGWAY_SHIPPED 7       /* same, backup set exactly as shipped (:41-55)     */
+
+/* memory-space flags for the batch calls */
+#define ASIF_MEM_HOST 0   /* all batch pointers are host memory (pinned memory overlaps copies with compute) */
+#define ASIF_MEM_DEVICE 1 /* all batch pointers are device memory on the engine's device; nothing is copied */
+
+typedef struct asif_engine asif_engine;
+
+/*
+ * Engine configuration = the reference's per-class Options struct + the constructor/initialize
+ * arguments (dims, lb, ub), flattened.  Fill with asif_engine_config_init() first: it sets every
+ * option to the reference default of the filter class (include/asif.h:11-17,
+ * include/asif_implicit_tb.h:19-33, include/asif_implicit.h:20-34, include/asif_robust.h:14-19,
+ * include/asif_realizable.h:14-20) and lb/ub/npBTSS to the values of the model's example program.
+ */
+typedef struct asif_engine_config {
+	uint32_t struct_size; /* sizeof(asif_engine_config), set by asif_engine_config_init */
+	int32_t filter;       /* ASIF_FILTER_* */
+	int32_t model;        /* ASIF_MODEL_*  */
+	int32_t device;       /* CUDA device ordinal */
+	int32_t npBTSS;       /* critical trajectory points (implicit filters) */
+	int32_t npSSmax;      /* explicit/realizable: rows kept after sorting by h; <= 0 means all */
+	double lb[2], ub[2];  /* input bounds passed to initialize(lb, ub) */
+	/* Options */
+	double relaxCost;
+	double relaxLb;      /* ASIF/ASIFrobust relaxLb; implicit classes: relaxSafeLb */
+	double relaxReachLb; /* ASIFimplicit */
+	double relaxTTS, relaxMinOrtho;                                        /* ASIFimplicitTB */
+	double backTrajHorizon, backTrajExtend, backTrajDt, backTrajMinOrtho;  /* implicit classes */
+	double satSharpness;
+	double inf;
+	double relaxDes, relaxOffset;    /* ASIFrealizable */
+	double uncertaintyBounds[4];     /* ASIFrealizable */
+	double dynParam[4];              /* model parameters, e.g. IP input gain interval [pMin, pMax] */
+	/* tables (host pointers, copied at create): half-planes {a0,a1} for ASIFrobust
+	 * (include/KernelData_70-135kg.h) or the polytope kernel for ASIFrealizable */
+	const double *halfplanes;
+	int32_t n_halfplanes;
+	const double *kernel_vertices; /* [nVertices][nx] */
+	int32_t n_vertices;
+	const double *facet_normals;   /* [nFacets][nx] */
+	const int32_t *facet_vertices; /* [nFacets][nx] vertex ids */
+	const int32_t *facet_active;   /* [nFacets][maxActiveConstraints] facet ids */
+	int32_t n_facets, max_critical_facets, max_active_constraints;
+} asif_engine_config;
+
+int32_t asif_b200_abi_version(void);
+const char *asif_last_error(void);
+/* number of CUDA devices visible, or a negative error */
+int32_t asif_device_count(void);
+
+/* defaults for (filter, model); replaces the Options() default constructors cited above */
+int32_t asif_engine_config_init(asif_engine_config *cfg, int32_t filter, int32_t model);
+
+/* constructor + initialize(lb, ub, options) of the filter classes
+ * (e.g. src/asif_implicit_tb.cpp:89-154,169-232) */
+int32_t asif_engine_create(const asif_engine_config *cfg, asif_engine **out);
+int32_t asif_engine_destroy(asif_engine *e);
+
+/* dims[0..5] = nx, nu, n_relax, nc (rows of A), nv, n_diag (doubles per state of the diag record) */
+int32_t asif_engine_dims(const asif_engine *e, int32_t dims[6]);
+
+/*
+ * filter(x, uDes, uAct, relax) of the selected class on n independent states
+ * (src/asif_implicit_tb.cpp:243-363, src/asif.cpp:144-210, ...).  New surface: the reference has no
+ * batched call.  diag may be NULL; when given it receives n_diag doubles per state:
+ *   TB       : TTS_, BTorthoBS_, hSafetyNow_, hBackupEnd_, backTrajCritIdx_[npBTSS] (-1 = absent),
+ *              A_[nc*nv] column-major, b_[nc]                 (include/asif_implicit_tb.h:112-117)
+ *   explicit : A_[nc*nv], b_[nc]
+ * mem = ASIF_MEM_HOST | ASIF_MEM_DEVICE.  stream: a cudaStream_t (device-memory calls are
+ * enqueued on it and return without synchronising) or NULL (engine's own stream; host-memory
+ * calls always return with the outputs complete).
+ */
+int32_t asif_engine_filter_batch(asif_engine *e, int64_t n, const double *x, const double *u_des, double *u_act,
+                                 double *relax, int32_t *rc, double *diag, int32_t mem, void *stream);
+
+/*
+ * Closed-loop rollout as in the example main loops (examples/segway_implicit_tb.cpp:251-283):
+ * steps x { filter ; x += dt*(f(x) + g(x) uAct) } with the state resident on the device.
+ * x is updated in place; u_des is held per state.  rc_hist[8] (host memory, optional) counts
+ * return codes over all state-steps: index rc+3 for rc in [-3,2], index 7 = other.
+ */
+int32_t asif_engine_rollout(asif_engine *e, int64_t n, int32_t steps, double dt, double *x, const double *u_des,
+                            double *u_act_last, int32_t *rc_last, int64_t *rc_hist, int32_t mem, void *stream);
+
+/* mean QP work of the last filter_batch/rollout call: rows processed by the active-set solver,
+ * summed over states (the "K-bar" of SURVEY 8d is this / states) */
+int32_t asif_engine_last_qp_iterations(asif_engine *e, uint64_t *rows_processed);
+
+/*
+ * The QPWrapper backend: n independent dense QPs of identical shape
+ *      min v'Hv + c'v   s.t.  A v >= b (row i equality where be[i]),  lb <= v <= ub
+ * replacing QPWrapperOsqp::initialize/updateCost/updateA/updateb/solve/getSolution
+ * (src/qpwrapper_osqp.cpp:55-261) for nv <= 4.  Layout per problem as in the reference:
+ * H[nv*nv] (diagonal_cost: only the diagonal is read, src/qpwrapper_osqp.cpp:267-283), c[nv],
+ * A[nc*nv] column-major, b[nc], lb[nv], ub[nv]; problems are consecutive.  H, lb, ub, be may be
+ * shared by all problems (stride flags).  status[k] = 1 (QPWrapperAbstract::SOLVER_STATUS::FEASIBLE)
+ * or the OSQP code the reference would pass through (-3 primal infeasible, -2 iteration limit).
+ */
+#define ASIF_QP_SHARED_H 1      /* one H for all problems */
+#define ASIF_QP_SHARED_BOUNDS 2 /* one lb/ub for all problems */
+int32_t asif_qp_solve_batch(int32_t device, int32_t nv, int32_t nc, int64_t n, int32_t diagonal_cost,
+                            const double *H, const double *c, const double *A, const double *b, const double *lb,
+                            const double *ub, const uint8_t *be, double *sol, int32_t *status, int32_t share_flags,
+                            int32_t mem, void *stream);
+
+/* measured FP64 FMA rate of the device (dependent-chain DFMA microbenchmark), TFLOP/s; the
+ * roofline denominator bench.py reports next to the filter throughput */
+int32_t asif_measure_fp64_peak(int32_t device, double *tflops, double *sm_clock_mhz_est);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

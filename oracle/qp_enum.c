@@ -67,54 +67,93 @@ typedef struct {
 	const double *G; /* m x nv row-major normals (row >= rhs form) */
 	const double *r; /* rhs */
 	const char *eq;  /* equality flag */
-	double Hinv[NVMAX][NVMAX]; /* (2H)^-1 */
+	double G2[NVMAX][NVMAX];   /* 2H */
+	const double *c;
 	double v0[NVMAX];          /* unconstrained minimiser */
 } qp_t;
+
+/* dense LU with partial pivoting for the (nv+k) x (nv+k) KKT system; returns 0 when singular */
+#define KMAX (2 * NVMAX)
+static int solve_kkt(int n, double M[KMAX][KMAX], double r[KMAX])
+{
+	for (int c = 0; c < n; c++) {
+		int p = c;
+		double best = fabs(M[c][c]);
+		for (int i = c + 1; i < n; i++)
+			if (fabs(M[i][c]) > best) {
+				best = fabs(M[i][c]);
+				p = i;
+			}
+		if (best < 1e-14) return 0;
+		if (p != c) {
+			for (int j = 0; j < n; j++) {
+				double t = M[c][j];
+				M[c][j] = M[p][j];
+				M[p][j] = t;
+			}
+			double t = r[c];
+			r[c] = r[p];
+			r[p] = t;
+		}
+		for (int i = c + 1; i < n; i++) {
+			double f = M[i][c] / M[c][c];
+			for (int j = c; j < n; j++) M[i][j] -= f * M[c][j];
+			r[i] -= f * r[c];
+		}
+	}
+	for (int i = n - 1; i >= 0; i--) {
+		double s = r[i];
+		for (int j = i + 1; j < n; j++) s -= M[i][j] * r[j];
+		r[i] = s / M[i][i];
+	}
+	return 1;
+}
 
 static int try_set(const qp_t *q, const int *S, int k, double *v_out, const double *rown, double ftol)
 {
 	const int nv = q->nv;
-	double v[NVMAX], mu[NVMAX];
+	double v[NVMAX];
 	if (k == 0) {
 		memcpy(v, q->v0, sizeof(double) * nv);
 	} else {
-		/* v = v0 + Hinv N mu, N'v = r_S  =>  (N' Hinv N) mu = r_S - N' v0 */
-		double HN[NVMAX][NVMAX]; /* HN[a] = Hinv n_a */
-		double M[NVMAX][NVMAX], rhs[NVMAX];
-		for (int a = 0; a < k; a++) {
-			const double *na = q->G + (size_t)S[a] * nv;
-			for (int i = 0; i < nv; i++) {
-				double s = 0;
-				for (int j = 0; j < nv; j++) s += q->Hinv[i][j] * na[j];
-				HN[a][i] = s;
-			}
-		}
-		for (int a = 0; a < k; a++) {
-			const double *na = q->G + (size_t)S[a] * nv;
-			double s = 0;
-			for (int i = 0; i < nv; i++) s += na[i] * q->v0[i];
-			rhs[a] = q->r[S[a]] - s;
-			for (int b = 0; b < k; b++) {
-				double t = 0;
-				for (int i = 0; i < nv; i++) t += na[i] * HN[b][i];
-				M[a][b] = t;
-			}
-		}
-		/* normalise rows/cols by the row norms so the singularity test is scale free */
-		for (int a = 0; a < k; a++) {
-			double sa = 1.0 / rown[S[a]];
-			rhs[a] *= sa;
-			for (int b = 0; b < k; b++) M[a][b] *= sa / rown[S[b]];
-		}
-		if (!solve_small(k, M, rhs)) return 0;
-		for (int a = 0; a < k; a++) mu[a] = rhs[a] / rown[S[a]];
-		for (int a = 0; a < k; a++)
-			if (!q->eq[S[a]] && mu[a] < 0.0) return 0;
+		/* KKT system of the equality-constrained problem on S, rows scaled to unit length:
+		 *   [ 2H  -N ] [v ]   [ -c  ]
+		 *   [ N'   0 ] [mu] = [ r_S ]      (N = scaled normals as columns)
+		 * solved by LU with partial pivoting; one step of iterative refinement. */
+		double K[KMAX][KMAX], K0[KMAX][KMAX], rhs[KMAX], rhs0[KMAX], sol[KMAX];
+		const int n = nv + k;
+		for (int i = 0; i < n; i++)
+			for (int j = 0; j < n; j++) K[i][j] = 0.0;
 		for (int i = 0; i < nv; i++) {
-			double s = q->v0[i];
-			for (int a = 0; a < k; a++) s += HN[a][i] * mu[a];
-			v[i] = s;
+			for (int j = 0; j < nv; j++) K[i][j] = q->G2[i][j];
+			rhs[i] = -q->c[i];
 		}
+		for (int a = 0; a < k; a++) {
+			const double *na = q->G + (size_t)S[a] * nv;
+			const double sc = 1.0 / rown[S[a]];
+			for (int i = 0; i < nv; i++) {
+				K[i][nv + a] = -na[i] * sc;
+				K[nv + a][i] = na[i] * sc;
+			}
+			rhs[nv + a] = q->r[S[a]] * sc;
+		}
+		memcpy(K0, K, sizeof(K));
+		memcpy(rhs0, rhs, sizeof(rhs));
+		if (!solve_kkt(n, K, rhs)) return 0;
+		memcpy(sol, rhs, sizeof(sol));
+		/* refinement: residual with the unfactored matrix */
+		double res[KMAX];
+		for (int i = 0; i < n; i++) {
+			double t = rhs0[i];
+			for (int j = 0; j < n; j++) t -= K0[i][j] * sol[j];
+			res[i] = t;
+		}
+		memcpy(K, K0, sizeof(K));
+		if (solve_kkt(n, K, res))
+			for (int i = 0; i < n; i++) sol[i] += res[i];
+		for (int a = 0; a < k; a++)
+			if (!q->eq[S[a]] && sol[nv + a] < 0.0) return 0;
+		for (int i = 0; i < nv; i++) v[i] = sol[i];
 	}
 	/* primal feasibility of every row */
 	for (int i = 0; i < q->m; i++) {
@@ -162,27 +201,22 @@ int oracle_qp_solve(int nv, int nc, int diagonal_cost, const double *H, const do
 	q.G = G;
 	q.r = r;
 	q.eq = eq;
-	/* (2H)^-1 and v0 = -(2H)^-1 c */
+	/* 2H and v0 = -(2H)^-1 c */
 	{
-		double M[NVMAX][NVMAX];
-		for (int col = 0; col < nv; col++) {
-			double e[NVMAX];
-			for (int i = 0; i < nv; i++) {
-				e[i] = (i == col) ? 1.0 : 0.0;
-				for (int j = 0; j < nv; j++)
-					M[i][j] = (diagonal_cost && i != j) ? 0.0 : 2.0 * H[i + j * nv];
-			}
-			if (!solve_small(nv, M, e)) {
-				free(G); free(r); free(rown); free(eq); free(cand);
-				return -7; /* OSQP_NON_CVX */
-			}
-			for (int i = 0; i < nv; i++) q.Hinv[i][col] = e[i];
-		}
+		double M[NVMAX][NVMAX], e[NVMAX];
 		for (int i = 0; i < nv; i++) {
-			double s = 0;
-			for (int j = 0; j < nv; j++) s -= q.Hinv[i][j] * c[j];
-			q.v0[i] = s;
+			for (int j = 0; j < nv; j++) {
+				q.G2[i][j] = (diagonal_cost && i != j) ? 0.0 : 2.0 * H[i + j * nv];
+				M[i][j] = q.G2[i][j];
+			}
+			e[i] = -c[i];
 		}
+		q.c = c;
+		if (!solve_small(nv, M, e)) {
+			free(G); free(r); free(rown); free(eq); free(cand);
+			return -7; /* OSQP_NON_CVX */
+		}
+		for (int i = 0; i < nv; i++) q.v0[i] = e[i];
 	}
 	/* candidate rows: non-zero normal.  Zero rows (pads / trivial rows) only matter for feasibility. */
 	int ncand = 0, neq = 0, infeasible = 0;

@@ -1,0 +1,23 @@
+#!/bin/bash
+# usage: bash scripts/gpu_run.sh [tests] [bench] [ncu-launches] [ncu-full]
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.max.sm,clocks.sm --format=csv,noheader
+echo "host cores: $(nproc)"
+for what in "$@"; do
+case $what in
+tests)
+  timeout 1500 python -m pytest tests -m gpu -x -q -s 2>&1 | tail -40 ;;
+bench)
+  timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"; cat gpurun_out/bench.json; tail -5 gpurun_out/bench.err ;;
+bench-ref)
+  timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "bench-ref rc=$?"; cat gpurun_out/bench_ref.json; tail -5 gpurun_out/bench_ref.err ;;
+ncu-launches)
+  python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/plain.log 2>&1 &&
+  ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches.csv \
+      python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launches.log 2>&1; echo "ncu-launches rc=$?" ;;
+ncu-full)
+  python bench.py --steps 2 --warmup 3 --no-cpu-baseline --states 2000000 > gpurun_out/plain2.log 2>&1 &&
+  ncu --set full --clock-control none --import-source on -k regex:tb_filter_kernel -s 3 -c 2 -f -o gpurun_out/prof_tb \
+      python bench.py --steps 2 --warmup 3 --no-cpu-baseline --states 2000000 > gpurun_out/ncu_full.log 2>&1; echo "ncu-full rc=$?" ;;
+esac
+done
