@@ -103,10 +103,13 @@ void make_softsat(double r, const double *lb, const double *ub, int nu, SoftSat 
 	for (int i = 0; i < MAX_NU; i++) {
 		s.range[i] = 1.0;
 		s.middle[i] = 0.0;
+		s.inv_range_exact[i] = 0.0;
 	}
 	for (int i = 0; i < nu; i++) {
 		s.range[i] = ub[i] - lb[i];
 		s.middle[i] = (ub[i] + lb[i]) / 2;
+		int ex;
+		if (frexp(s.range[i], &ex) == 0.5) s.inv_range_exact[i] = 1.0 / s.range[i]; // power of two: exact reciprocal
 	}
 }
 

@@ -19,6 +19,16 @@ struct RegRows {
 	int stride;
 	double lb[NV], ub[NV];
 	__device__ __forceinline__ int count() const { return NC + 2 * NV; }
+	template <class F>
+	__device__ __forceinline__ void scan(F &&fn) const
+	{
+		const int m = count();
+		for (int j = 0; j < m; j++) {
+			double n[NV], rhs;
+			get(j, n, rhs);
+			fn(j, n, rhs);
+		}
+	}
 	__device__ __forceinline__ void get(int j, double (&n)[NV], double &rhs) const
 	{
 		if (j < NC) {

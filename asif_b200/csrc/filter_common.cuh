@@ -20,7 +20,16 @@ struct SoftSat {
 	double bevelYc;    // 1 - r
 	double range[MAX_NU];  // ub - lb
 	double middle[MAX_NU]; // (ub + lb)/2
+	// 1/range when range is a power of two (then x/range == x*(1/range) bit for bit and the FP64
+	// division, ~10 dependent DFMAs per Euler step, is not needed); 0 otherwise
+	double inv_range_exact[MAX_NU];
 };
+
+// Structural patterns a model may declare for its callback outputs: an entry that is the literal
+// 0.0 or 1.0 for every state.  The kernels skip the multiplications by such entries; for finite
+// operands this cannot change an IEEE result (x*0 = +-0, acc + +-0 = acc, 1*x = x) except for the
+// sign of an exact zero.  PG = general (no assumption).
+enum : int { PZ = 0, P1 = 1, PG = 2 };
 
 // Options of ASIFimplicitTB (include/asif_implicit_tb.h:19-33) + what initialize() derives from them
 // (src/asif_implicit_tb.cpp:169-223).
@@ -55,7 +64,8 @@ __device__ __forceinline__ void input_saturate_soft(const SoftSat &s, int i, dou
                                                     double &DuSat)
 {
 	const double range = s.range[i], middle = s.middle[i];
-	const double uc = 2 * (u - middle) / range;
+	const double inv = s.inv_range_exact[i];
+	const double uc = (inv != 0.0) ? (2 * (u - middle)) * inv : 2 * (u - middle) / range;
 	if (uc >= s.bevelStop) {
 		uSat = ub;
 		DuSat = 0;
@@ -83,51 +93,108 @@ __device__ __forceinline__ void input_saturate_soft(const SoftSat &s, int i, dou
 	}
 }
 
+// structural pattern of DfCL = d_fcl_dx (or Df + Dg uSat) + g diag(DuSat) Du, entry (i,j)
+template <class M>
+__host__ __device__ constexpr int dfcl_pattern(int i, int j)
+{
+	bool g_zero = true;
+	for (int k = 0; k < M::NU; k++) g_zero = g_zero && (M::g_pat(i + k * M::NX) == PZ);
+	bool dg_zero = true;
+	if (!M::FUSED_GRADIENT)
+		for (int k = 0; k < M::NU; k++) dg_zero = dg_zero && (M::dg_pat(i + k * M::NX + j * M::NX * M::NU) == PZ);
+	if (g_zero && dg_zero) return M::df_pat(i + j * M::NX);
+	return PG;
+}
+
 // Closed-loop backup dynamics and their Jacobian, src/asif_implicit_tb.cpp:833-897.
+// Entries of DfCL whose dfcl_pattern is PZ / P1 are not written (callers must not read them).
 template <class M>
 __device__ __forceinline__ void backup_cl_dynamics(const SoftSat &sat, const double *lb, const double *ub, const double *x,
                                                    double *fCL, double *DfCL)
 {
 	constexpr int NX = M::NX, NU = M::NU;
 	double f[NX], g[NX * NU], u[NU], Du[NU * NX], uSat[NU], DuSat[NU];
+	double d[NX * NX], Dg[M::FUSED_GRADIENT ? 1 : NX * NU * NX];
 	M::backup_controller(x, u, Du);
 #pragma unroll
 	for (int k = 0; k < NU; k++) input_saturate_soft(sat, k, lb[k], ub[k], u[k], uSat[k], DuSat[k]);
 	if (M::FUSED_GRADIENT) {
-		double d[NX * NX];
 		M::dynamics_with_gradient(x, uSat, f, g, d);
-#pragma unroll
-		for (int i = 0; i < NX; i++)
-#pragma unroll
-			for (int j = 0; j < NX; j++) {
-				double acc = d[i + j * NX];
-#pragma unroll
-				for (int k = 0; k < NU; k++) acc += g[i + k * NX] * DuSat[k] * Du[k + j * NU];
-				DfCL[i + j * NX] = acc;
-			}
 	} else {
-		double Df[NX * NX], Dg[NX * NU * NX];
 		M::dynamics(x, f, g);
-		M::dynamics_gradients(x, Df, Dg);
-#pragma unroll
-		for (int i = 0; i < NX; i++)
-#pragma unroll
-			for (int j = 0; j < NX; j++) {
-				double acc = Df[i + j * NX];
-#pragma unroll
-				for (int k = 0; k < NU; k++)
-					acc += Dg[i + k * NX + j * NX * NU] * uSat[k] + g[i + k * NX] * DuSat[k] * Du[k + j * NU];
-				DfCL[i + j * NX] = acc;
-			}
+		M::dynamics_gradients(x, d, Dg);
 	}
+#pragma unroll
+	for (int i = 0; i < NX; i++)
+#pragma unroll
+		for (int j = 0; j < NX; j++) {
+			if (dfcl_pattern<M>(i, j) != PG) continue;
+			// DfCL = d; DfCL += Dg*uSat + g*DuSat*Du   (:857-888), structural zeros skipped
+			const int pd = M::df_pat(i + j * NX);
+			bool have = (pd != PZ);
+			double acc = (pd == P1) ? 1.0 : d[i + j * NX];
+#pragma unroll
+			for (int k = 0; k < NU; k++) {
+				const int pg = M::g_pat(i + k * NX);
+				bool tz = true;
+				double term = 0.0;
+				if (!M::FUSED_GRADIENT) {
+					if (M::dg_pat(i + k * NX + j * NX * NU) != PZ) {
+						term = Dg[i + k * NX + j * NX * NU] * uSat[k];
+						tz = false;
+					}
+				}
+				if (pg != PZ) {
+					const double gd = (pg == P1) ? DuSat[k] : g[i + k * NX] * DuSat[k];
+					const double t2 = gd * Du[k + j * NU];
+					term = tz ? t2 : term + t2;
+					tz = false;
+				}
+				if (!tz) {
+					acc = have ? acc + term : term;
+					have = true;
+				}
+			}
+			DfCL[i + j * NX] = acc;
+		}
 	// fCL = g uSat + f   (matrixVectorMultiply then += f, :892-896)
 #pragma unroll
 	for (int i = 0; i < NX; i++) {
-		double acc = g[i] * uSat[0];
+		bool have = false;
+		double acc = 0.0;
 #pragma unroll
-		for (int k = 1; k < NU; k++) acc = acc + g[i + k * NX] * uSat[k];
-		fCL[i] = acc + f[i];
+		for (int k = 0; k < NU; k++) {
+			const int pg = M::g_pat(i + k * NX);
+			if (pg == PZ) continue;
+			const double t = (pg == P1) ? uSat[k] : g[i + k * NX] * uSat[k];
+			acc = have ? acc + t : t;
+			have = true;
+		}
+		fCL[i] = have ? acc + f[i] : f[i];
 	}
+}
+
+// Q-dot = DfCL Q (src/asif_implicit_tb.cpp:906-908) with the structural pattern of DfCL
+template <class M>
+__device__ __forceinline__ void sensitivity_rhs(const double *DfCL, const double *Q, double *Qd)
+{
+	constexpr int NX = M::NX;
+#pragma unroll
+	for (int r = 0; r < NX; r++)
+#pragma unroll
+		for (int c = 0; c < NX; c++) {
+			bool have = false;
+			double acc = 0.0;
+#pragma unroll
+			for (int m = 0; m < NX; m++) {
+				const int pt = dfcl_pattern<M>(r, m);
+				if (pt == PZ) continue;
+				const double t = (pt == P1) ? Q[m + c * NX] : DfCL[r + m * NX] * Q[m + c * NX];
+				acc = have ? acc + t : t;
+				have = true;
+			}
+			Qd[r + c * NX] = acc;
+		}
 }
 
 } // namespace asifb

@@ -42,6 +42,22 @@ struct DoubleIntegratorExplicit {
 struct DoubleIntegratorTB {
 	static constexpr int NX = 2, NU = 1, NPSS = 4;
 	static constexpr bool FUSED_GRADIENT = true; // DYNAMICS_WITH_GRADIENT, :9
+	// structural patterns (filter_common.cuh): B = {0,1}; d_fcl_dx = A = {0,0,1,0} column-major
+	__host__ __device__ static constexpr int g_pat(int i)
+	{
+		constexpr int t[2] = {0, 1};
+		return t[i];
+	}
+	__host__ __device__ static constexpr int df_pat(int i)
+	{
+		constexpr int t[4] = {0, 0, 1, 0};
+		return t[i];
+	}
+	__host__ __device__ static constexpr int dg_pat(int i)
+	{
+		constexpr int t[4] = {0, 0, 0, 0};
+		return t[i];
+	}
 	__device__ static void safety_set(const double *x, double *h, double *Dh)
 	{
 		h[0] = -x[0] + 1.0;   Dh[0] = -1.0; Dh[4] = 0.0;
@@ -96,6 +112,23 @@ template <bool CENTRED>
 struct SegwayTB {
 	static constexpr int NX = 4, NU = 1, NPSS = 4;
 	static constexpr bool FUSED_GRADIENT = false;
+	// structural patterns: g = {0,*,0,*}; Df rows 0 and 2 are unit rows, column 0 is zero (:145-201);
+	// Dg is zero except entries 9 and 11 (:203-211)
+	__host__ __device__ static constexpr int g_pat(int i)
+	{
+		constexpr int t[4] = {0, 2, 0, 2};
+		return t[i];
+	}
+	__host__ __device__ static constexpr int df_pat(int i)
+	{
+		constexpr int t[16] = {0, 0, 0, 0, 1, 2, 0, 2, 0, 2, 0, 2, 0, 2, 1, 2};
+		return t[i];
+	}
+	__host__ __device__ static constexpr int dg_pat(int i)
+	{
+		constexpr int t[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 2, 0, 2, 0, 0, 0, 0};
+		return t[i];
+	}
 	__device__ static double bound(int i)
 	{
 		return i == 0 ? 3.0 : (i == 1 ? 3.0 : (i == 2 ? (M_PI / 6) : M_PI));

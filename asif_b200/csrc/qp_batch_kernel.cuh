@@ -22,6 +22,16 @@ struct BatchRows {
 	bool has_eq;
 	// rows: [0,nc) A rows; [nc, nc+2NV) bounds; [nc+2NV, 2nc+2NV) negated equality rows
 	__device__ __forceinline__ int count() const { return has_eq ? 2 * nc + 2 * NV : nc + 2 * NV; }
+	template <class F>
+	__device__ __forceinline__ void scan(F &&fn) const
+	{
+		const int m = count();
+		for (int j = 0; j < m; j++) {
+			double n[NV], rhs;
+			get(j, n, rhs);
+			fn(j, n, rhs);
+		}
+	}
 	__device__ __forceinline__ void get(int j, double (&n)[NV], double &rhs) const
 	{
 		if (j < nc) {

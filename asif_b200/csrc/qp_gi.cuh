@@ -8,8 +8,9 @@
 // a handful of iterations and detects infeasibility exactly (OSQP_PRIMAL_INFEASIBLE = -3).
 //
 // Everything is per thread and in registers: NV is a template constant, all loops over NV are
-// unrolled, the active set holds at most NV rows.  Rows are presented by a functor so that the
-// caller decides where they live (shared memory for the implicit filters, computed on the fly
+// unrolled, the active set holds at most NV rows.  Rows are presented by a functor with two
+// members -- scan(f): call f(j, normal, rhs) for every row j in order; get(j, normal, rhs): one
+// row -- so that the caller decides where they live (shared memory for the implicit filters, computed on the fly
 // from a table for the robust/realizable ones, global memory for the generic batch entry).
 // Work is done in the metric of the Hessian (v-hat = sqrt(2H) v) with every processed row
 // normalised to unit length, so the thresholds below are scale free.
@@ -195,17 +196,17 @@ __device__ __forceinline__ int qp_gi_solve(const Metric &mt, const double (&c)[N
 		w.mu[i] = 0.0;
 		w.act[i] = -1;
 	}
-	const int m = rows.count();
 	int status = QP_MAX_ITER;
 	int it = 0;
 	const int max_outer = 4 * NV + 24;
 	for (; it < max_outer; it++) {
-		// ---- most violated row that is not active
+		// ---- most violated row that is not active (rows.scan visits every row once, in order)
 		int p = -1;
 		double sp = 0.0;
-		for (int j = 0; j < m; j++) {
-			double n[NV], rhs;
-			rows.get(j, n, rhs);
+		double np_[NV], rhs_p = 0.0;
+#pragma unroll
+		for (int i = 0; i < NV; i++) np_[i] = 0.0;
+		rows.scan([&](const int j, const double(&n)[NV], const double rhs) {
 			double s = -rhs, nmax = 1.0;
 #pragma unroll
 			for (int i = 0; i < NV; i++) {
@@ -218,17 +219,29 @@ __device__ __forceinline__ int qp_gi_solve(const Metric &mt, const double (&c)[N
 			if (!is_act && s < -QP_FEAS_TOL * nmax && s < sp) {
 				sp = s;
 				p = j;
+				rhs_p = rhs;
+#pragma unroll
+				for (int i = 0; i < NV; i++) np_[i] = n[i];
 			}
-		}
+		});
 		if (p < 0) {
 			status = QP_OK;
 			break;
 		}
-		double nh[NV], rhs;
-		const double len = qp_fetch_unit_row<NV>(rows, p, mt, nh, rhs);
+		double nh[NV];
+		mt.to_hat(np_, nh);
+		double len2 = 0.0;
+#pragma unroll
+		for (int i = 0; i < NV; i++) len2 += nh[i] * nh[i];
+		const double len = sqrt(len2);
 		if (!(len > 0.0)) { // 0 >= rhs with rhs > 0
 			status = QP_PRIMAL_INFEASIBLE;
 			break;
+		}
+		{
+			const double inv = 1.0 / len;
+#pragma unroll
+			for (int i = 0; i < NV; i++) nh[i] *= inv;
 		}
 		sp = sp / len;
 		double mu_p = 0.0;

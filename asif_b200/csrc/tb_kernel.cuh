@@ -1,20 +1,25 @@
 // tb_kernel.cuh -- batched ASIFimplicitTB::filter, one state per thread, everything fused:
 // backup-trajectory + sensitivity integration -> streaming critical-point selection ->
-// time-to-safety -> constraint-row assembly -> exact QP -> saturation / fallback.
+// time-to-safety -> constraint rows -> exact QP -> saturation / fallback.
 //
 // Reference path replaced: src/asif_implicit_tb.cpp:261-363 (filter), :407-714
 // (updateConstraints), :833-909 (closed-loop rhs), plus the OSQP solve behind
 // src/qpwrapper_osqp.cpp:217-239.
 //
 // Design (B200): the per-state work is a strictly sequential FP64 recurrence of a few thousand
-// operations on 6..20 doubles, with 44 B of HBM traffic per state, so the kernel is bound by the
-// FP64 pipe, not by memory.  One state per *thread* keeps all 32 lanes of a warp on the FP64
-// pipe (one state per warp would idle >= 26 of 32 lanes for nx = 2).  The trajectory is never
-// stored: each thread keeps a running list of the NPBTSS smallest min-h points seen so far
-// (keys in registers, (x_i, Q_i) snapshots in shared memory, laid out [slot][element][thread] so
-// that every access is bank-conflict free whatever slot a lane writes), frozen at the first
-// point inside the backup set.  Rows go to shared memory in the same layout and are consumed by
-// the register-resident dual active-set QP.
+// operations on 6..20 doubles against 44 B of HBM traffic per state, so the kernel is bound by
+// the FP64 pipe (and by the latency of its dependent chains), never by memory.  Consequences:
+//   * one state per *thread*: all 32 lanes of a warp stay on the FP64 pipe (one state per warp
+//     would idle >= 26 of 32 lanes for nx = 2);
+//   * the trajectory is never stored: each thread keeps a running list of the NPBTSS smallest
+//     min-h points seen so far (keys in registers, (x_i, Q_i) snapshots in shared memory laid
+//     out [slot][element][thread], so every access is bank-conflict free whatever slot a lane
+//     writes), frozen at the first point inside the backup set;
+//   * constraint rows are NOT materialised: the QP's row functor recomputes the four safety rows
+//     of a critical point from its snapshot each time the active-set solver scans them (about 1.6
+//     scans per state).  That costs ~4 % extra flops and removes 54 doubles of shared memory per
+//     thread, which is what limits occupancy - and occupancy (warps to cover the FP64 dependent-
+//     issue latency) is what limits this kernel (ncu: stall "wait" dominant at 2 warps/SMSP).
 #pragma once
 #include "filter_common.cuh"
 #include "qp_gi.cuh"
@@ -29,43 +34,152 @@ struct TbDiagLayout {
 	static constexpr int HEAD = 4 + NPBTSS;
 };
 
-// rows of the TB QP in shared memory + the variable bounds
-template <int NV, int NC>
-struct TbRows {
-	const double *rows; // [(NC)*(NV+1)][blockDim] view, already offset by threadIdx.x
-	int stride;         // blockDim.x
-	double lb[NV], ub[NV];
-	__device__ __forceinline__ int count() const { return NC + 2 * NV; }
-	__device__ __forceinline__ void get(int j, double (&n)[NV], double &rhs) const
-	{
-		if (j < NC) {
-#pragma unroll
-			for (int i = 0; i < NV; i++) n[i] = rows[(j * (NV + 1) + i) * stride];
-			rhs = rows[(j * (NV + 1) + NV) * stride];
-		} else {
-			const int k = j - NC;
-			const int var = k >> 1;
-			const bool upper = k & 1;
-#pragma unroll
-			for (int i = 0; i < NV; i++) n[i] = (i == var) ? (upper ? -1.0 : 1.0) : 0.0;
-			double bnd = 0.0;
-#pragma unroll
-			for (int i = 0; i < NV; i++)
-				if (i == var) bnd = upper ? -ub[i] : lb[i];
-			rhs = bnd;
-		}
-	}
-};
-
-// shared memory doubles per thread
+// shared memory doubles per thread: NPBTSS critical-point snapshots + the hit point
 template <class M, int NPBTSS>
 __host__ __device__ constexpr int tb_smem_doubles_per_thread()
 {
-	constexpr int NS = M::NX + M::NX * M::NX;
-	constexpr int NC = NPBTSS * M::NPSS + 2;
-	constexpr int NV = M::NU + 1;
-	return (NPBTSS + 1) * NS + NC * (NV + 1);
+	return (NPBTSS + 1) * (M::NX + M::NX * M::NX);
 }
+
+// Rows of the TB QP (src/asif_implicit_tb.cpp:554-674), computed on demand.
+template <class M, int NPBTSS>
+struct TbRows {
+	static constexpr int NX = M::NX, NU = M::NU, NPSS = M::NPSS, NS = NX + NX * NX;
+	static constexpr int NC = NPBTSS * NPSS + 2, NV = NU + 1;
+	const double *snap; // this thread's view, element stride T
+	int T;
+	double f[NX], g[NX * NU]; // open-loop dynamics at the current state (:416-418)
+	int kslot[NPBTSS];
+	int nkept;
+	bool trivial;         // inside the backup set: A = 0, b = -inf (:716-733)
+	double lgT[NU], rhsT; // time-to-safety row
+	double lgO[NU], rhsO; // orthogonality row
+	double lb[NV], ub[NV];
+	double neg_inf;
+
+	// the NPSS safety rows of the critical point stored in `slot` (:567-585, :643-674)
+	__device__ __forceinline__ void point_rows(const int slot, double (&n)[NPSS][NV], double (&rhs)[NPSS]) const
+	{
+		double xs[NS], hs[NPSS], Dhs[NPSS * NX];
+#pragma unroll
+		for (int e = 0; e < NS; e++) xs[e] = snap[(slot * NS + e) * T];
+		M::safety_set(xs, hs, Dhs);
+#pragma unroll
+		for (int j = 0; j < NPSS; j++) {
+			double dh[NX]; // Dh_row = DhSS(x_i) Q_i
+#pragma unroll
+			for (int cc = 0; cc < NX; cc++) {
+				double acc = Dhs[j] * xs[NX + cc * NX];
+#pragma unroll
+				for (int m = 1; m < NX; m++) acc = acc + Dhs[j + m * NPSS] * xs[NX + m + cc * NX];
+				dh[cc] = acc;
+			}
+			double lf = dh[0] * f[0];
+#pragma unroll
+			for (int m = 1; m < NX; m++) lf = lf + dh[m] * f[m];
+#pragma unroll
+			for (int i = 0; i < NU; i++) {
+				double lg = dh[0] * g[i * NX];
+#pragma unroll
+				for (int m = 1; m < NX; m++) lg = lg + dh[m] * g[m + i * NX];
+				n[j][i] = lg;
+			}
+			n[j][NU] = hs[j];
+			rhs[j] = -lf;
+		}
+	}
+	__device__ __forceinline__ void bound_row(const int k, double (&n)[NV], double &rhs) const
+	{
+		const int var = k >> 1;
+		const bool upper = k & 1;
+		double bnd = 0.0;
+#pragma unroll
+		for (int i = 0; i < NV; i++) {
+			n[i] = (i == var) ? (upper ? -1.0 : 1.0) : 0.0;
+			if (i == var) bnd = upper ? -ub[i] : lb[i];
+		}
+		rhs = bnd;
+	}
+	// every row once, in the reference's row order, then the 2*NV variable bounds
+	template <class F>
+	__device__ __forceinline__ void scan(F &&fn) const
+	{
+		if (!trivial) {
+#pragma unroll 1
+			for (int s = 0; s < NPBTSS; s++) { // not unrolled: one copy of point_rows keeps registers down
+				double n[NPSS][NV], rhs[NPSS];
+				if (s < nkept) {
+					int slot = 0;
+#pragma unroll
+					for (int t = 0; t < NPBTSS; t++) slot = (t == s) ? kslot[t] : slot;
+					point_rows(slot, n, rhs);
+				} else { // h = 1, Dh = 0 (:556-566)
+#pragma unroll
+					for (int j = 0; j < NPSS; j++) {
+#pragma unroll
+						for (int i = 0; i < NU; i++) n[j][i] = 0.0;
+						n[j][NU] = 1.0;
+						rhs[j] = -0.0;
+					}
+				}
+#pragma unroll
+				for (int j = 0; j < NPSS; j++) fn(s * NPSS + j, n[j], rhs[j]);
+			}
+			double n[NV];
+#pragma unroll
+			for (int i = 0; i < NU; i++) n[i] = lgT[i];
+			n[NU] = 0.0;
+			fn(NC - 2, n, rhsT);
+#pragma unroll
+			for (int i = 0; i < NU; i++) n[i] = lgO[i];
+			fn(NC - 1, n, rhsO);
+		}
+#pragma unroll
+		for (int k = 0; k < 2 * NV; k++) {
+			double n[NV], rhs;
+			bound_row(k, n, rhs);
+			fn(NC + k, n, rhs);
+		}
+	}
+	__device__ __forceinline__ void get(const int j, double (&n)[NV], double &rhs) const
+	{
+		if (j >= NC) {
+			bound_row(j - NC, n, rhs);
+		} else if (trivial) {
+#pragma unroll
+			for (int i = 0; i < NV; i++) n[i] = 0.0;
+			rhs = neg_inf;
+		} else if (j >= NC - 2) {
+			const bool o = (j == NC - 1);
+#pragma unroll
+			for (int i = 0; i < NU; i++) n[i] = o ? lgO[i] : lgT[i];
+			n[NU] = 0.0;
+			rhs = o ? rhsO : rhsT;
+		} else {
+			const int s = j / NPSS, jj = j - s * NPSS;
+			if (s < nkept) {
+				int slot = 0;
+#pragma unroll
+				for (int t = 0; t < NPBTSS; t++) slot = (t == s) ? kslot[t] : slot;
+				double nn[NPSS][NV], rr[NPSS];
+				point_rows(slot, nn, rr);
+#pragma unroll
+				for (int t = 0; t < NPSS; t++) {
+					if (t == jj) {
+#pragma unroll
+						for (int i = 0; i < NV; i++) n[i] = nn[t][i];
+						rhs = rr[t];
+					}
+				}
+			} else {
+#pragma unroll
+				for (int i = 0; i < NU; i++) n[i] = 0.0;
+				n[NU] = 1.0;
+				rhs = -0.0;
+			}
+		}
+	}
+};
 
 template <int NPBTSS>
 struct TbDiagRec {
@@ -74,17 +188,17 @@ struct TbDiagRec {
 	bool have_rows;
 };
 
-// One reference filter() call for one state (src/asif_implicit_tb.cpp:261-363).  snap / rows are
-// this thread's shared-memory views (already offset by threadIdx.x, element stride T).  Must be
-// called by all 32 lanes of a warp together (warp-uniform early exit from the trajectory loop).
+// One reference filter() call for one state (src/asif_implicit_tb.cpp:261-363).  snap is this
+// thread's shared-memory view (already offset by threadIdx.x, element stride T).  Must be called
+// by all 32 lanes of a warp together (warp-uniform early exit from the trajectory loop).
+// R is left describing the state's QP rows (the diag writer re-scans them).
 template <class M, int NPBTSS, bool WITH_DIAG>
 __device__ __forceinline__ int32_t tb_filter_one(const TbParams &p, const double (&x0)[M::NX], const double (&ud)[M::NU],
-                                                 double *snap, double *rows, const int T, double (&uo)[M::NU],
-                                                 double &relax, int &qp_iters, TbDiagRec<NPBTSS> &dg)
+                                                 double *snap, const int T, double (&uo)[M::NU], double &relax,
+                                                 int &qp_iters, TbDiagRec<NPBTSS> &dg, TbRows<M, NPBTSS> &R)
 {
 	constexpr int NX = M::NX, NU = M::NU, NPSS = M::NPSS;
 	constexpr int NS = NX + NX * NX;
-	constexpr int NC = NPBTSS * NPSS + 2;
 	constexpr int NV = NU + 1;
 
 	// ---- filter(): h_BS(x), hSafetyNow (:278-283)
@@ -105,24 +219,21 @@ __device__ __forceinline__ int32_t tb_filter_one(const TbParams &p, const double
 	for (int i = 0; i < NX; i++) X[NX + i * (NX + 1)] = 1.0;
 
 	double key[NPBTSS]; // ascending; +inf = empty
-	int kidx[NPBTSS], kslot[NPBTSS];
+	int kidx[NPBTSS];
 #pragma unroll
 	for (int s = 0; s < NPBTSS; s++) {
 		key[s] = INFINITY;
 		kidx[s] = -1;
-		kslot[s] = s;
+		R.kslot[s] = s;
 	}
-	int nkept = 0;
 	// point 0
-	{
-		key[0] = hSafetyNow;
-		kidx[0] = 0;
-		nkept = 1;
+	key[0] = hSafetyNow;
+	kidx[0] = 0;
+	int nkept = 1;
 #pragma unroll
-		for (int e = 0; e < NS; e++) snap[(kslot[0] * NS + e) * T] = X[e];
-	}
+	for (int e = 0; e < NS; e++) snap[(R.kslot[0] * NS + e) * T] = X[e];
+
 	bool hit = false;
-	int idxHit = 0;
 	double tHit = 0.0, tNow = 0.0;
 	double hBackupEnd = 0.0;
 	const int N = p.npBT;
@@ -132,29 +243,21 @@ __device__ __forceinline__ int32_t tb_filter_one(const TbParams &p, const double
 			if (__all_sync(0xffffffffu, hit || !run)) break;
 		}
 		tNow = tNow + p.backTrajDt;
-		// rhs (:899-909)
+		// rhs (:899-909) and Euler step: (rhs*dt) + prev, two roundings (:477-480)
 		double Xd[NS], DfCL[NX * NX];
 		backup_cl_dynamics<M>(p.sat, p.lb, p.ub, X, Xd, DfCL);
-#pragma unroll
-		for (int r = 0; r < NX; r++)
-#pragma unroll
-			for (int c = 0; c < NX; c++) {
-				double acc = DfCL[r] * X[NX + c * NX];
-#pragma unroll
-				for (int m = 1; m < NX; m++) acc = acc + DfCL[r + m * NX] * X[NX + m + c * NX];
-				Xd[NX + r + c * NX] = acc;
-			}
-		// Euler: (rhs*dt) + prev, two roundings (:477-480)
+		sensitivity_rhs<M>(DfCL, X + NX, Xd + NX);
 #pragma unroll
 		for (int e = 0; e < NS; e++) X[e] = Xd[e] * p.backTrajDt + X[e];
-		if (hit) continue; // selection and hit scan are frozen after the first hit (:507,539)
+		// selection and hit scan are frozen after the first hit (:507,539)
+		const bool active = run && !hit;
 		M::safety_set(X, hs, Dhs);
 		double hmin = hs[0];
 #pragma unroll
 		for (int j = 1; j < NPSS; j++) hmin = (hs[j] < hmin) ? hs[j] : hmin;
-		if (run && hmin < key[NPBTSS - 1]) {
+		if (active && hmin < key[NPBTSS - 1]) {
 			// evict the largest key, insert (hmin, i) keeping ascending order; ties keep the earlier index first
-			const int slot = kslot[NPBTSS - 1];
+			const int slot = R.kslot[NPBTSS - 1];
 #pragma unroll
 			for (int e = 0; e < NS; e++) snap[(slot * NS + e) * T] = X[e];
 			double ck = hmin;
@@ -165,19 +268,18 @@ __device__ __forceinline__ int32_t tb_filter_one(const TbParams &p, const double
 				const bool sw = ins || (ck < key[s]);
 				ins = sw;
 				const double tk = key[s];
-				const int ti = kidx[s], ts = kslot[s];
+				const int ti = kidx[s], ts = R.kslot[s];
 				key[s] = sw ? ck : tk;
 				kidx[s] = sw ? ci : ti;
-				kslot[s] = sw ? cs : ts;
+				R.kslot[s] = sw ? cs : ts;
 				ck = sw ? tk : ck;
 				ci = sw ? ti : ci;
 				cs = sw ? ts : cs;
 			}
 			nkept = nkept < NPBTSS ? nkept + 1 : NPBTSS;
 		}
-		if (run && M::backup_set_value(X) >= 0.0) {
+		if (active && M::backup_set_value(X) >= 0.0) {
 			hit = true;
-			idxHit = i;
 			tHit = tNow;
 #pragma unroll
 			for (int e = 0; e < NS; e++) snap[(NPBTSS * NS + e) * T] = X[e];
@@ -185,18 +287,27 @@ __device__ __forceinline__ int32_t tb_filter_one(const TbParams &p, const double
 	}
 	if (WITH_DIAG) hBackupEnd = M::backup_set_value(X);
 
-	// ---- cost (:198-212, 735-746) and bounds
+	// ---- cost (:198-212, 735-746), bounds
 	double c[NV];
 	DiagMetric<NV> mt;
-	TbRows<NV, NC> R;
-	R.rows = rows;
-	R.stride = T;
+	R.snap = snap;
+	R.T = T;
+	R.nkept = nkept;
+	R.trivial = inside;
+	R.neg_inf = -p.inf;
 #pragma unroll
 	for (int i = 0; i < NU; i++) {
 		c[i] = -2.0 * ud[i];
 		R.lb[i] = p.lb[i];
 		R.ub[i] = p.ub[i];
+		R.lgT[i] = 0.0;
+		R.lgO[i] = 0.0;
 	}
+#pragma unroll
+	for (int i = 0; i < NX; i++) R.f[i] = 0.0;
+#pragma unroll
+	for (int i = 0; i < NX * NU; i++) R.g[i] = 0.0;
+	R.rhsT = R.rhsO = -p.inf;
 	c[NU] = -2.0 * p.relaxCost * p.relaxSafeLb;
 	R.lb[NU] = p.relaxSafeLb;
 	R.ub[NU] = p.inf;
@@ -210,13 +321,6 @@ __device__ __forceinline__ int32_t tb_filter_one(const TbParams &p, const double
 	int32_t rc;
 	bool solve = true;
 	if (inside) {
-		// updateConstraintsTrivial (:716-733): A = 0, b = -inf
-#pragma unroll
-		for (int j = 0; j < NC; j++) {
-#pragma unroll
-			for (int i = 0; i < NV; i++) rows[(j * (NV + 1) + i) * T] = 0.0;
-			rows[(j * (NV + 1) + NV) * T] = -p.inf;
-		}
 		rc = 2;
 	} else if (!hit) {
 		ortho = 0.0;
@@ -224,59 +328,13 @@ __device__ __forceinline__ int32_t tb_filter_one(const TbParams &p, const double
 		solve = false;
 	} else {
 		rc = 1;
-		double f[NX], g[NX * NU];
 		if (M::FUSED_GRADIENT) {
 			double u0[NU], dtmp[NX * NX];
 #pragma unroll
 			for (int i = 0; i < NU; i++) u0[i] = 0.0;
-			M::dynamics_with_gradient(x0, u0, f, g, dtmp); // the dynamics_ lambda of :79-86
+			M::dynamics_with_gradient(x0, u0, R.f, R.g, dtmp); // the dynamics_ lambda of :79-86
 		} else {
-			M::dynamics(x0, f, g);
-		}
-		// safety rows of the critical points (:554-586)
-#pragma unroll
-		for (int s = 0; s < NPBTSS; s++) {
-			if (s >= nkept) {
-#pragma unroll
-				for (int j = 0; j < NPSS; j++) {
-					const int row = s * NPSS + j;
-#pragma unroll
-					for (int i = 0; i < NU; i++) rows[(row * (NV + 1) + i) * T] = 0.0;
-					rows[(row * (NV + 1) + NU) * T] = 1.0; // h = 1, Dh = 0 (:556-566)
-					rows[(row * (NV + 1) + NV) * T] = -0.0;
-				}
-			} else {
-				double xs[NS];
-				const int slot = kslot[s];
-#pragma unroll
-				for (int e = 0; e < NS; e++) xs[e] = snap[(slot * NS + e) * T];
-				M::safety_set(xs, hs, Dhs);
-#pragma unroll
-				for (int j = 0; j < NPSS; j++) {
-					// Dh_row = DhSS(x_i) Q_i  (:574-584), then Lfh = Dh f, Lgh = Dh g (:643-653)
-					double dh[NX];
-#pragma unroll
-					for (int cc = 0; cc < NX; cc++) {
-						double acc = Dhs[j] * xs[NX + cc * NX];
-#pragma unroll
-						for (int m = 1; m < NX; m++) acc = acc + Dhs[j + m * NPSS] * xs[NX + m + cc * NX];
-						dh[cc] = acc;
-					}
-					double lf = dh[0] * f[0];
-#pragma unroll
-					for (int m = 1; m < NX; m++) lf = lf + dh[m] * f[m];
-					const int row = s * NPSS + j;
-#pragma unroll
-					for (int i = 0; i < NU; i++) {
-						double lg = dh[0] * g[i * NX];
-#pragma unroll
-						for (int m = 1; m < NX; m++) lg = lg + dh[m] * g[m + i * NX];
-						rows[(row * (NV + 1) + i) * T] = lg;
-					}
-					rows[(row * (NV + 1) + NU) * T] = hs[j];
-					rows[(row * (NV + 1) + NV) * T] = -lf;
-				}
-			}
+			M::dynamics(x0, R.f, R.g);
 		}
 		// time-to-safety and orthogonality rows (:588-641)
 		double xh[NS];
@@ -285,6 +343,14 @@ __device__ __forceinline__ int32_t tb_filter_one(const TbParams &p, const double
 		double hBS, DhBS[NX], DDhBS[NX * NX], fCl[NX], DfCl[NX * NX];
 		M::backup_set(xh, hBS, DhBS, DDhBS);
 		backup_cl_dynamics<M>(p.sat, p.lb, p.ub, xh, fCl, DfCl);
+#pragma unroll
+		for (int r = 0; r < NX; r++)
+#pragma unroll
+			for (int cc = 0; cc < NX; cc++) { // structural entries are not written by backup_cl_dynamics
+				const int pt = dfcl_pattern<M>(r, cc);
+				if (pt == PZ) DfCl[r + cc * NX] = 0.0;
+				if (pt == P1) DfCl[r + cc * NX] = 1.0;
+			}
 		double cosT = DhBS[0] * fCl[0];
 #pragma unroll
 		for (int m = 1; m < NX; m++) cosT = cosT + DhBS[m] * fCl[m];
@@ -338,30 +404,25 @@ __device__ __forceinline__ int32_t tb_filter_one(const TbParams &p, const double
 			dhO[i] = (Dnum * den - cosT * Dden) / denSq;
 		}
 		// TTS row and ortho row: Lgh u >= -Lfh - relax*h, no relax-variable column (:655-674)
-		{
-			double lfT = dhT[0] * f[0], lfO = dhO[0] * f[0];
+		double lfT = dhT[0] * R.f[0], lfO = dhO[0] * R.f[0];
+#pragma unroll
+		for (int m = 1; m < NX; m++) {
+			lfT = lfT + dhT[m] * R.f[m];
+			lfO = lfO + dhO[m] * R.f[m];
+		}
+#pragma unroll
+		for (int i = 0; i < NU; i++) {
+			double a = dhT[0] * R.g[i * NX], b = dhO[0] * R.g[i * NX];
 #pragma unroll
 			for (int m = 1; m < NX; m++) {
-				lfT = lfT + dhT[m] * f[m];
-				lfO = lfO + dhO[m] * f[m];
+				a = a + dhT[m] * R.g[m + i * NX];
+				b = b + dhO[m] * R.g[m + i * NX];
 			}
-			const int rT = NPBTSS * NPSS, rO = NPBTSS * NPSS + 1;
-#pragma unroll
-			for (int i = 0; i < NU; i++) {
-				double lgT = dhT[0] * g[i * NX], lgO = dhO[0] * g[i * NX];
-#pragma unroll
-				for (int m = 1; m < NX; m++) {
-					lgT = lgT + dhT[m] * g[m + i * NX];
-					lgO = lgO + dhO[m] * g[m + i * NX];
-				}
-				rows[(rT * (NV + 1) + i) * T] = lgT;
-				rows[(rO * (NV + 1) + i) * T] = lgO;
-			}
-			rows[(rT * (NV + 1) + NU) * T] = 0.0;
-			rows[(rO * (NV + 1) + NU) * T] = 0.0;
-			rows[(rT * (NV + 1) + NV) * T] = -lfT - p.relaxTTS * hReach;
-			rows[(rO * (NV + 1) + NV) * T] = -lfO - p.relaxMinOrtho * hOrtho;
+			R.lgT[i] = a;
+			R.lgO[i] = b;
 		}
+		R.rhsT = -lfT - p.relaxTTS * hReach;
+		R.rhsO = -lfO - p.relaxMinOrtho * hOrtho;
 	}
 
 	// ---- QP + post-solve (:324-352)
@@ -393,22 +454,27 @@ __device__ __forceinline__ int32_t tb_filter_one(const TbParams &p, const double
 	return rc;
 }
 
+// resident CTAs per SM the register allocation is tuned for (nx = 2 models: 16 warps/SM)
+template <class M>
+__host__ __device__ constexpr int tb_min_blocks()
+{
+	return M::NX <= 2 ? 4 : 2;
+}
+
 template <class M, int NPBTSS, bool WITH_DIAG>
-__global__ void __launch_bounds__(TB_THREADS)
+__global__ void __launch_bounds__(TB_THREADS, tb_min_blocks<M>())
 tb_filter_kernel(const TbParams p, const int64_t n, const double *__restrict__ x_in, const double *__restrict__ u_des,
                  double *__restrict__ u_act, double *__restrict__ relax_out, int32_t *__restrict__ rc_out,
                  double *__restrict__ diag, unsigned long long *__restrict__ qp_iter_sum)
 {
 	constexpr int NX = M::NX, NU = M::NU, NPSS = M::NPSS;
-	constexpr int NS = NX + NX * NX;
 	constexpr int NC = NPBTSS * NPSS + 2;
 	constexpr int NV = NU + 1;
 	constexpr int NDIAG = TbDiagLayout<NPBTSS>::HEAD + NC * NV + NC;
 
 	extern __shared__ double smem[];
 	const int T = blockDim.x;
-	double *snap = smem + threadIdx.x;                                  // [(NPBTSS+1)*NS][T]
-	double *rows = smem + (size_t)(NPBTSS + 1) * NS * T + threadIdx.x; // [NC*(NV+1)][T]
+	double *snap = smem + threadIdx.x; // [(NPBTSS+1)*NS][T]
 
 	const int64_t k = (int64_t)blockIdx.x * T + threadIdx.x;
 	const bool live = k < n;
@@ -423,7 +489,8 @@ tb_filter_kernel(const TbParams p, const int64_t n, const double *__restrict__ x
 	double uo[NU], relax;
 	int qp_iters;
 	TbDiagRec<NPBTSS> dg;
-	const int32_t rc = tb_filter_one<M, NPBTSS, WITH_DIAG>(p, x0, ud, snap, rows, T, uo, relax, qp_iters, dg);
+	TbRows<M, NPBTSS> R;
+	const int32_t rc = tb_filter_one<M, NPBTSS, WITH_DIAG>(p, x0, ud, snap, T, uo, relax, qp_iters, dg, R);
 
 	if (live) {
 #pragma unroll
@@ -438,10 +505,19 @@ tb_filter_kernel(const TbParams p, const int64_t n, const double *__restrict__ x
 			d[3] = dg.hBackupEnd;
 #pragma unroll
 			for (int s = 0; s < NPBTSS; s++) d[4 + s] = (double)dg.critIdx[s];
+			double *A = d + 4 + NPBTSS, *b = A + NC * NV;
 			for (int j = 0; j < NC; j++) {
-				for (int i = 0; i < NV; i++)
-					d[4 + NPBTSS + j + i * NC] = dg.have_rows ? rows[(j * (NV + 1) + i) * T] : 0.0;
-				d[4 + NPBTSS + NC * NV + j] = dg.have_rows ? rows[(j * (NV + 1) + NV) * T] : 0.0;
+				for (int i = 0; i < NV; i++) A[j + i * NC] = 0.0;
+				b[j] = (dg.have_rows && R.trivial) ? -p.inf : 0.0;
+			}
+			if (dg.have_rows && !R.trivial) {
+				R.scan([&](const int j, const double(&nn)[NV], const double rhs) {
+					if (j < NC) {
+#pragma unroll
+						for (int i = 0; i < NV; i++) A[j + i * NC] = nn[i];
+						b[j] = rhs;
+					}
+				});
 			}
 		}
 	}
@@ -456,17 +532,15 @@ tb_filter_kernel(const TbParams p, const int64_t n, const double *__restrict__ x
 // Closed-loop rollout (examples/segway_implicit_tb.cpp:251-283): the state never leaves the
 // registers between control steps; one launch covers all steps of every agent.
 template <class M, int NPBTSS>
-__global__ void __launch_bounds__(TB_THREADS)
+__global__ void __launch_bounds__(TB_THREADS, tb_min_blocks<M>())
 tb_rollout_kernel(const TbParams p, const int64_t n, const int32_t steps, const double dt_plant, double *__restrict__ x_io,
                   const double *__restrict__ u_des, double *__restrict__ u_act_last, int32_t *__restrict__ rc_last,
                   unsigned long long *__restrict__ rc_hist, unsigned long long *__restrict__ qp_iter_sum)
 {
 	constexpr int NX = M::NX, NU = M::NU;
-	constexpr int NS = NX + NX * NX;
 	extern __shared__ double smem[];
 	const int T = blockDim.x;
 	double *snap = smem + threadIdx.x;
-	double *rows = smem + (size_t)(NPBTSS + 1) * NS * T + threadIdx.x;
 	const int64_t k = (int64_t)blockIdx.x * T + threadIdx.x;
 	const bool live = k < n;
 	const int64_t kk = live ? k : (n - 1);
@@ -487,7 +561,8 @@ tb_rollout_kernel(const TbParams p, const int64_t n, const int32_t steps, const 
 		double relax;
 		int qp_iters;
 		TbDiagRec<NPBTSS> dg;
-		rc = tb_filter_one<M, NPBTSS, false>(p, x, ud, snap, rows, T, uo, relax, qp_iters, dg);
+		TbRows<M, NPBTSS> R;
+		rc = tb_filter_one<M, NPBTSS, false>(p, x, ud, snap, T, uo, relax, qp_iters, dg, R);
 		iters += (unsigned long long)qp_iters;
 		const int slot = (rc >= -3 && rc <= 2) ? rc + 3 : 7;
 #pragma unroll
