@@ -1,0 +1,356 @@
+// asif_b200.hpp -- C++ host layer over the C ABI (include/asif_b200.h); header only.
+//
+// Mirrors the reference's C++ surface for the filter path so that it drops in:
+//   * ASIF::QPWrapperAbstract            the solver interface (include/qpwrapper_abstract.h:16-51);
+//                                        declared here only when the reference header is absent
+//   * ASIF::QPWrapperB200                a QPWrapperAbstract backend on the B200 kernels, the
+//                                        sibling of QPWrapperOsqp (src/qpwrapper_osqp.cpp)
+//   * ASIF::FilterBatchImplicitTB / FilterBatchExplicit
+//                                        the batched counterparts of ASIFimplicitTB / ASIF with the
+//                                        same Options structs, initialize / updateOptions semantics
+//                                        and return codes, plus filterBatch(n, X, UDes, UAct, Relax, rc)
+// Models are device functors selected by id (the reference passes std::function callbacks, which
+// cannot run on the device); asif_b200/csrc/models.cuh keeps their five callback signatures.
+// Everything computes on the GPU; there is no CPU fallback - errors surface as negative return
+// values with the message available from lastError().
+#ifndef ASIF_B200_HPP
+#define ASIF_B200_HPP
+
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/asif_b200.h"
+
+namespace ASIF
+{
+
+#ifndef _QPWRAPPER_ABSTRACT_H_
+#define _QPWRAPPER_ABSTRACT_H_
+	// min (x'Hx + c'x)  s.t.  A x >= b,  lb <= x <= ub      (no 1/2; dense column-major A[i + j*nc])
+	class QPWrapperAbstract
+	{
+	public:
+		enum class SOLVER_STATUS : int32_t { INFEASIBLE = 0, FEASIBLE = 1 };
+
+		QPWrapperAbstract(const uint32_t nv, const uint32_t nc, const bool diagonalCost)
+		    : nv_(nv), nc_(nc), diagonalCost_(diagonalCost)
+		{
+			be_ = new bool[nc];
+			for (uint32_t i = 0; i < nc_; i++) be_[i] = false;
+		}
+		virtual ~QPWrapperAbstract(void) { delete[] be_; }
+
+		virtual int32_t initialize(const double H[], const double c[], const double A[], const double b[],
+		                           const double lb[], const double ub[], const bool be[] = nullptr) = 0;
+		virtual int32_t updateCost(const double H[], const double c[]) = 0;
+		virtual int32_t updateA(const double A[]) = 0;
+		virtual int32_t updateb(const double b[]) = 0;
+		virtual int32_t updateBounds(const double lb[], const double ub[]) = 0;
+		virtual int32_t solve(void) = 0;
+		virtual int32_t getSolution(double sol[]) = 0;
+
+	protected:
+		const uint32_t nv_;
+		const uint32_t nc_;
+		const bool diagonalCost_;
+		bool *be_;
+	};
+#endif
+
+	// A QPWrapperAbstract whose solve() runs on the B200 (asif_qp_solve_batch with n = 1).
+	// Argument meaning, copies and return values follow QPWrapperOsqp (src/qpwrapper_osqp.cpp:55-261):
+	// initialize() returns 0 on success (the polarity of osqp_setup, :121), the update*() calls return 1,
+	// solve() returns 1 (FEASIBLE) or the OSQP status code the reference would pass through (:225-238),
+	// getSolution() copies nv values.  nullptr arguments of updateCost / updateBounds mean "unchanged".
+	class QPWrapperB200 : public QPWrapperAbstract
+	{
+	public:
+		QPWrapperB200(const uint32_t nv, const uint32_t nc, const bool diagonalCost, const int32_t device = 0)
+		    : QPWrapperAbstract(nv, nc, diagonalCost), device_(device), H_(nv * nv, 0.0), c_(nv, 0.0), A_((size_t)nv * nc, 0.0),
+		      b_(nc, 0.0), lb_(nv, 0.0), ub_(nv, 0.0), sol_(nv, 0.0), beU8_(nc, 0), hasEq_(false), status_(-10)
+		{
+		}
+		virtual ~QPWrapperB200(void) {}
+
+		virtual int32_t initialize(const double H[], const double c[], const double A[], const double b[],
+		                           const double lb[], const double ub[], const bool be[] = nullptr)
+		{
+			if (nv_ < 1 || nv_ > 4) return ASIF_ERR_UNSUPPORTED;
+			if (be != nullptr) {
+				for (uint32_t i = 0; i < nc_; i++) {
+					be_[i] = be[i];
+					beU8_[i] = be[i] ? 1 : 0;
+					hasEq_ = hasEq_ || be[i];
+				}
+			}
+			std::memcpy(H_.data(), H, sizeof(double) * nv_ * nv_);
+			std::memcpy(c_.data(), c, sizeof(double) * nv_);
+			std::memcpy(A_.data(), A, sizeof(double) * nv_ * nc_);
+			std::memcpy(b_.data(), b, sizeof(double) * nc_);
+			std::memcpy(lb_.data(), lb, sizeof(double) * nv_);
+			std::memcpy(ub_.data(), ub, sizeof(double) * nv_);
+			return asif_device_count() > 0 ? 0 : ASIF_ERR_NO_DEVICE;
+		}
+		virtual int32_t updateCost(const double H[], const double c[])
+		{
+			if (H != nullptr) std::memcpy(H_.data(), H, sizeof(double) * nv_ * nv_);
+			if (c != nullptr) std::memcpy(c_.data(), c, sizeof(double) * nv_);
+			return 1;
+		}
+		virtual int32_t updateA(const double A[])
+		{
+			std::memcpy(A_.data(), A, sizeof(double) * nv_ * nc_);
+			return 1;
+		}
+		virtual int32_t updateb(const double b[])
+		{
+			std::memcpy(b_.data(), b, sizeof(double) * nc_);
+			return 1;
+		}
+		virtual int32_t updateBounds(const double lb[], const double ub[])
+		{
+			if (lb != nullptr) std::memcpy(lb_.data(), lb, sizeof(double) * nv_);
+			if (ub != nullptr) std::memcpy(ub_.data(), ub, sizeof(double) * nv_);
+			return 1;
+		}
+		virtual int32_t solve(void)
+		{
+			int32_t st = -10; // OSQP_UNSOLVED
+			const int32_t r = asif_qp_solve_batch(device_, (int32_t)nv_, (int32_t)nc_, 1, diagonalCost_ ? 1 : 0, H_.data(),
+			                                      c_.data(), A_.data(), b_.data(), lb_.data(), ub_.data(),
+			                                      hasEq_ ? beU8_.data() : nullptr, sol_.data(), &st,
+			                                      ASIF_QP_SHARED_H | ASIF_QP_SHARED_BOUNDS, ASIF_MEM_HOST, nullptr);
+			status_ = (r == ASIF_OK) ? st : r;
+			return status_;
+		}
+		virtual int32_t getSolution(double sol[])
+		{
+			for (uint32_t i = 0; i < nv_; i++) sol[i] = sol_[i];
+			return 1;
+		}
+
+	protected:
+		int32_t device_;
+		std::vector<double> H_, c_, A_, b_, lb_, ub_, sol_;
+		std::vector<uint8_t> beU8_;
+		bool hasEq_;
+		int32_t status_;
+	};
+
+	namespace b200
+	{
+		enum class Model : int32_t {
+			DoubleIntegrator = ASIF_MODEL_DOUBLE_INTEGRATOR,
+			DoubleIntegratorTB = ASIF_MODEL_DOUBLE_INTEGRATOR_TB,
+			InvertedPendulum = ASIF_MODEL_INVERTED_PENDULUM,
+			Segway = ASIF_MODEL_SEGWAY,
+			SegwayShipped = ASIF_MODEL_SEGWAY_SHIPPED
+		};
+
+		inline std::string lastError(void) { return std::string(asif_last_error()); }
+
+		// common plumbing of the batched filters
+		class FilterBatchBase
+		{
+		public:
+			virtual ~FilterBatchBase(void) { asif_engine_destroy(engine_); }
+			// filter(x, uDes, uAct, relax) of the reference class on n states; host arrays
+			// X[n*nx], UDes[n*nu], UAct[n*nu], Relax[n*nRelax], rc[n]; returns 0 or a negative ASIF_ERR_*
+			int32_t filterBatch(const int64_t n, const double X[], const double UDes[], double UAct[], double Relax[],
+			                    int32_t rc[], double diag[] = nullptr)
+			{
+				if (engine_ == nullptr) return ASIF_ERR_INVALID_ARGUMENT;
+				return asif_engine_filter_batch(engine_, n, X, UDes, UAct, Relax, rc, diag, ASIF_MEM_HOST, nullptr);
+			}
+			// same with device pointers on the caller's CUDA stream (cudaStream_t); returns without synchronising
+			int32_t filterBatchDevice(const int64_t n, const double *X, const double *UDes, double *UAct, double *Relax,
+			                          int32_t *rc, void *stream, double *diag = nullptr)
+			{
+				if (engine_ == nullptr) return ASIF_ERR_INVALID_ARGUMENT;
+				return asif_engine_filter_batch(engine_, n, X, UDes, UAct, Relax, rc, diag, ASIF_MEM_DEVICE, stream);
+			}
+			uint32_t nx(void) const { return dims_[0]; }
+			uint32_t nu(void) const { return dims_[1]; }
+			uint32_t nDiag(void) const { return dims_[5]; }
+
+		protected:
+			FilterBatchBase(void) : engine_(nullptr) { std::memset(dims_, 0, sizeof(dims_)); }
+			int32_t create(const asif_engine_config &cfg)
+			{
+				asif_engine *e = nullptr;
+				const int32_t r = asif_engine_create(&cfg, &e);
+				if (r != ASIF_OK) return r;
+				asif_engine_destroy(engine_);
+				engine_ = e;
+				asif_engine_dims(engine_, dims_);
+				return 1;
+			}
+			asif_engine *engine_;
+			int32_t dims_[6];
+		};
+
+		// Batched ASIF::ASIF (include/asif.h): explicit CBF filter.
+		class FilterBatchExplicit : public FilterBatchBase
+		{
+		public:
+			typedef struct {
+				double relaxLb = 5.0;
+				double relaxCost = 50.0;
+				double satSharpness = 5.0;
+				double inf = 1e20;
+			} Options; // include/asif.h:11-17
+
+			explicit FilterBatchExplicit(const Model model, const int32_t device = 0) : model_(model), device_(device) {}
+			int32_t initialize(const double lb[], const double ub[]) { return initialize(lb, ub, Options()); }
+			int32_t initialize(const double lb[], const double ub[], const Options &options)
+			{
+				options_ = options;
+				asif_engine_config cfg;
+				int32_t r = asif_engine_config_init(&cfg, ASIF_FILTER_EXPLICIT, (int32_t)model_);
+				if (r != ASIF_OK) return r;
+				cfg.device = device_;
+				cfg.lb[0] = lb[0];
+				cfg.ub[0] = ub[0];
+				lb_ = lb[0];
+				ub_ = ub[0];
+				cfg.relaxLb = options.relaxLb;
+				cfg.relaxCost = options.relaxCost;
+				cfg.inf = options.inf;
+				return create(cfg);
+			}
+			// src/asif.cpp:213-231 moves only the LOWER bound of the relax variable and leaves the upper
+			// bound at the value of initialize(): lowering relaxLb frees the variable on [new, old], raising
+			// it makes OSQP reject the bound update (l > u) so the old pin stays.  That asymmetry is an
+			// accident of the wrapper; the batched engine pins both bounds to the new value (documented
+			// deviation, DESIGN.md "quirks").
+			int32_t updateOptions(const Options &options)
+			{
+				const double lb[1] = {lb_}, ub[1] = {ub_};
+				return initialize(lb, ub, options);
+			}
+			int32_t filter(const double x[], const double uDes[], double uAct[], double &relax)
+			{
+				int32_t rc = 0;
+				double ua = uAct[0], rl = 0.0;
+				const int32_t r = filterBatch(1, x, uDes, &ua, &rl, &rc);
+				if (r != ASIF_OK) return r;
+				if (rc == 1) { // the reference leaves uAct/relax untouched on failure (src/asif.cpp:207-209)
+					uAct[0] = ua;
+					relax = rl;
+				}
+				return rc;
+			}
+
+		protected:
+			Model model_;
+			int32_t device_;
+			Options options_;
+			double lb_, ub_;
+		};
+
+		// Batched ASIF::ASIFimplicitTB (include/asif_implicit_tb.h).
+		class FilterBatchImplicitTB : public FilterBatchBase
+		{
+		public:
+			typedef struct {
+				double relaxCost = 50.0;
+				double relaxSafeLb = 5.0;
+				double relaxTTS = 5.0;
+				double relaxMinOrtho = 5.0;
+				double backTrajHorizon = 1.0;
+				double backTrajExtend = 0.05;
+				double backTrajDt = 0.01;
+				double backTrajMinOrtho = 0.01;
+				double backTrajAbsTol = 1.0e-6;
+				double backTrajRelTol = 1.0e-6;
+				double satSharpness = 0.1;
+				double inf = 1e20;
+			} Options; // include/asif_implicit_tb.h:19-33
+
+			FilterBatchImplicitTB(const Model model, const uint32_t npBTSS = 4, const int32_t device = 0)
+			    : model_(model), npBTSS_(npBTSS), device_(device)
+			{
+			}
+			int32_t initialize(const double lb[], const double ub[]) { return initialize(lb, ub, Options()); }
+			int32_t initialize(const double lb[], const double ub[], const Options &options)
+			{
+				options_ = options;
+				lb_ = lb[0];
+				ub_ = ub[0];
+				return build(options_, options_.backTrajExtend);
+			}
+			// src/asif_implicit_tb.cpp:365-405: the trajectory length is recomputed WITHOUT backTrajExtend (:377),
+			// satSharpness is clamped to [0.01, 2] with return codes 3 / 2 (:391-404), otherwise 1.
+			int32_t updateOptions(const Options &options)
+			{
+				options_ = options;
+				int32_t code = 1;
+				if (options_.satSharpness > 2) {
+					options_.satSharpness = 2;
+					code = 2;
+				} else if (options_.satSharpness < 0.01) {
+					options_.satSharpness = 0.01;
+					code = 3;
+				}
+				const int32_t r = build(options_, 0.0);
+				return r == 1 ? code : r;
+			}
+			int32_t filter(const double x[], const double uDes[], double uAct[], double &relax)
+			{
+				int32_t rc = 0;
+				const int32_t r = filterBatch(1, x, uDes, uAct, &relax, &rc);
+				return r == ASIF_OK ? rc : r;
+			}
+			// closed-loop rollout of n independent agents (example main loops), state resident on the device
+			int32_t rollout(const int64_t n, const int32_t steps, const double dt, double X[], const double UDes[],
+			                double UActLast[], int32_t rcLast[], int64_t rcHist[8] = nullptr)
+			{
+				return asif_engine_rollout(engine_, n, steps, dt, X, UDes, UActLast, rcLast, rcHist, ASIF_MEM_HOST, nullptr);
+			}
+			// src/asif_implicit_tb.cpp:911-933
+			static std::string filterErrorMsgString(const int32_t rc)
+			{
+				switch (rc) {
+				case 1: return "Success";
+				case 2: return "Inside backup set";
+				case -1: return "Inside backup set QP failed";
+				case -2: return "QP failed";
+				case -3: return "Backup set not reached";
+				default: return "Unkown";
+				}
+			}
+
+		protected:
+			int32_t build(const Options &o, const double extend)
+			{
+				asif_engine_config cfg;
+				int32_t r = asif_engine_config_init(&cfg, ASIF_FILTER_IMPLICIT_TB, (int32_t)model_);
+				if (r != ASIF_OK) return r;
+				cfg.device = device_;
+				cfg.npBTSS = (int32_t)npBTSS_;
+				cfg.lb[0] = lb_;
+				cfg.ub[0] = ub_;
+				cfg.relaxCost = o.relaxCost;
+				cfg.relaxLb = o.relaxSafeLb;
+				cfg.relaxTTS = o.relaxTTS;
+				cfg.relaxMinOrtho = o.relaxMinOrtho;
+				cfg.backTrajHorizon = o.backTrajHorizon;
+				cfg.backTrajExtend = extend;
+				cfg.backTrajDt = o.backTrajDt;
+				cfg.backTrajMinOrtho = o.backTrajMinOrtho;
+				cfg.satSharpness = o.satSharpness;
+				cfg.inf = o.inf;
+				return create(cfg);
+			}
+			Model model_;
+			uint32_t npBTSS_;
+			int32_t device_;
+			Options options_;
+			double lb_, ub_;
+		};
+	} // namespace b200
+} // namespace ASIF
+#endif

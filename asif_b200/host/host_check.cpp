@@ -1,0 +1,87 @@
+// host_check.cpp -- exercises the C++ host layer the way the reference's example mains do
+// (examples/DoubleIntegrator_implicit_tb.cpp:87-131): construct, initialize(lb, ub, opts),
+// filter() in a closed loop, updateOptions() half-way; plus the QPWrapperB200 backend through the
+// abstract interface, and a filterBatch call.  Prints "host_check ok" and returns 0 on success.
+// Needs a GPU at run time; build() only checks that it compiles and links.
+#include "asif_b200.hpp"
+
+#include <cstdio>
+#include <memory>
+
+static int fail(const char *what)
+{
+	std::fprintf(stderr, "host_check FAILED: %s (%s)\n", what, ASIF::b200::lastError().c_str());
+	return 1;
+}
+
+int main()
+{
+	using namespace ASIF;
+	// --- 1. the QP backend behind the abstract interface: min (v0-2)^2 + 50 (v1-10)^2, v0 + v1 >= 13, 0<=v0<=1
+	{
+		std::unique_ptr<QPWrapperAbstract> qp(new QPWrapperB200(2, 1, true));
+		const double H[4] = {1, 0, 0, 50}, c[2] = {-4, -1000}, A[2] = {1, 1}, b[1] = {13}, lb[2] = {0, 10}, ub[2] = {1, 1e20};
+		if (qp->initialize(H, c, A, b, lb, ub) != 0) return fail("QPWrapperB200::initialize");
+		if (qp->solve() != (int32_t)QPWrapperAbstract::SOLVER_STATUS::FEASIBLE) return fail("QPWrapperB200::solve");
+		double v[2];
+		qp->getSolution(v);
+		if (std::fabs(v[0] - 1.0) > 1e-9 || std::fabs(v[1] - 12.0) > 1e-9) return fail("QPWrapperB200 solution");
+		const double b2[1] = {1e9}; // infeasible with v0 <= 1 only if v1 cannot grow: it can, so still feasible
+		qp->updateb(b2);
+		if (qp->solve() != 1) return fail("QPWrapperB200 after updateb");
+		const double ub2[2] = {1, 11};
+		qp->updateBounds(nullptr, ub2);
+		if (qp->solve() != -3) return fail("QPWrapperB200 infeasible status"); // OSQP_PRIMAL_INFEASIBLE passes through
+	}
+	// --- 2. the example main loop on the batched TB filter (one state)
+	{
+		b200::FilterBatchImplicitTB asif(b200::Model::DoubleIntegratorTB, 4);
+		b200::FilterBatchImplicitTB::Options opts;
+		opts.backTrajHorizon = 2.0;
+		opts.backTrajDt = 0.001;
+		opts.relaxSafeLb = 10.0;
+		opts.relaxTTS = 5.0;
+		opts.relaxMinOrtho = 5.0;
+		const double lb[1] = {-1.0}, ub[1] = {1.0};
+		if (asif.initialize(lb, ub, opts) != 1) return fail("FilterBatchImplicitTB::initialize");
+		double x[2] = {0.1, 0.1}, uDes[1] = {0.9}, uAct[1] = {0.0}, relax = 0.0;
+		const double dt = 0.001;
+		int n_fail = 0;
+		for (int s = 0; s < 400; s++) {
+			if (s == 200) {
+				opts.backTrajHorizon = 7.0;
+				if (asif.updateOptions(opts) != 1) return fail("updateOptions");
+			}
+			const int32_t rc = asif.filter(x, uDes, uAct, relax);
+			if (rc < 0) n_fail++;
+			x[0] += dt * x[1]; // examples/DoubleIntegrator_implicit_tb.cpp:139-154
+			x[1] += dt * uAct[0];
+		}
+		if (!(std::fabs(x[0]) <= 1.0 && std::fabs(x[1]) <= 1.0)) return fail("closed loop left the safe set");
+		std::printf("closed loop: x = (%.6f, %.6f) uAct = %.6f relax = %.3f filter failures = %d\n", x[0], x[1], uAct[0], relax, n_fail);
+		b200::FilterBatchImplicitTB::Options bad = opts;
+		bad.satSharpness = 5.0;
+		if (asif.updateOptions(bad) != 2) return fail("satSharpness clamp code 2");
+		bad.satSharpness = 0.001;
+		if (asif.updateOptions(bad) != 3) return fail("satSharpness clamp code 3");
+	}
+	// --- 3. a batch
+	{
+		b200::FilterBatchExplicit asif(b200::Model::DoubleIntegrator);
+		const double lb[1] = {-1.0}, ub[1] = {1.0};
+		if (asif.initialize(lb, ub) != 1) return fail("FilterBatchExplicit::initialize");
+		const int n = 1000;
+		std::vector<double> X(2 * n), U(n), UA(n), R(n);
+		std::vector<int32_t> rc(n);
+		for (int i = 0; i < n; i++) {
+			X[2 * i] = -0.9 + 1.8 * i / n;
+			X[2 * i + 1] = 0.3;
+			U[i] = 1.0;
+		}
+		if (asif.filterBatch(n, X.data(), U.data(), UA.data(), R.data(), rc.data()) != 0) return fail("filterBatch");
+		for (int i = 0; i < n; i++)
+			if (rc[i] == 1 && (UA[i] > 1.0 || UA[i] < -1.0)) return fail("uAct outside bounds");
+	}
+	std::printf("host_check ok\n");
+	return 0;
+}

@@ -1,0 +1,37 @@
+"""The oracle restatement against the reference compiled from its own sources (oracle/_ref), on
+fresh random states.  Runs where libasif_ref.so exists (dev container: built on demand from
+/root/reference; GPU box: shipped prebuilt); skipped otherwise.  CPU only."""
+import numpy as np
+import pytest
+
+import conftest as cf
+from oracle import pyref
+
+
+@pytest.mark.parametrize("cfg,opts,gen,n", [
+    (pyref.CFG_DI_EXPLICIT, cf.C1_OPTS, cf.c1_inputs, 20000),
+    (pyref.CFG_DI_IMPLICIT_TB, cf.C2_TB_OPTS, cf.c2_inputs, 6000),
+    (pyref.CFG_SEGWAY_TB, cf.SEGWAY_TB_OPTS, cf.c5_inputs, 600),
+])
+def test_oracle_matches_reference(oracle, reflib, cfg, opts, gen, n):
+    x, ud = gen(n, seed=cf.SEED + 100 + cfg)
+    f = reflib.create(cfg, opts)
+    u0, relax0, rc0, diag0 = f.filter_batch(x, ud, want_diag=True)
+    u, relax, rc, diag = oracle.filter_batch(cfg, x, ud, opts, want_diag=True)
+    unpinned = np.isin(rc0, (-2, 3, 4)) | ((rc0 == -3) & (rc == 1) & (relax[:, 0] > 50.0))
+    print("cfg", cfg, "rc", dict(zip(*np.unique(rc0, return_counts=True))), "unpinned", int(unpinned.sum()))
+    assert unpinned.mean() < 0.01
+    k = ~unpinned
+    cf.assert_parity("cfg%d" % cfg, (u[k], relax[k], rc[k]), (u0[k], relax0[k], rc0[k]))
+    m = k & (rc0 == 1)
+    assert np.array_equal(diag[m], diag0[m])
+
+
+def test_rollout_matches_reference(oracle, reflib):
+    f = reflib.create(pyref.CFG_DI_IMPLICIT_TB, cf.C2_TB_OPTS)
+    x0, ud = cf.c2_inputs(50, seed=99)
+    x0 *= 0.3
+    xr, ur, rcr, hr = f.rollout(x0, ud, 40, 1e-3)
+    xo, uo, rco, ho = oracle.rollout(pyref.CFG_DI_IMPLICIT_TB, x0, ud, 40, 1e-3, cf.C2_TB_OPTS)
+    assert np.array_equal(rcr, rco)
+    assert np.abs(xr - xo).max() < 1e-9
