@@ -115,9 +115,14 @@ class Engine:
         cfg.device = device
         self._keep = []
         for k, v in options.items():
-            if k in ("lb", "ub"):
+            if k in ("lb", "ub", "dynParam", "uncertaintyBounds"):
                 for i, vi in enumerate(np.atleast_1d(v)):
                     getattr(cfg, k)[i] = float(vi)
+            elif k == "halfplanes":
+                t = np.ascontiguousarray(v, dtype=np.float64).reshape(-1, 2)
+                self._keep.append(t)
+                cfg.halfplanes = t.ctypes.data_as(_dp)
+                cfg.n_halfplanes = t.shape[0]
             elif not hasattr(cfg, k):
                 raise AsifError("unknown option %r" % k)
             else:

@@ -6,6 +6,8 @@
 
 #include "explicit_kernel.cuh"
 #include "filter_common.cuh"
+#include "implicit_kernel.cuh"
+#include "robust_kernel.cuh"
 #include "models.cuh"
 #include "qp_batch_kernel.cuh"
 #include "tb_kernel.cuh"
@@ -56,6 +58,9 @@ struct asif_engine {
 	int nx, nu, n_relax, nc, nv, n_diag;
 	TbParams tb;
 	ExplicitParams ex;
+	ImplicitParams im;
+	RobustParams rb;
+	double *d_table = nullptr; // half-plane table (robust filter)
 	Slot slot[N_SLOTS];
 	cudaStream_t stream = nullptr; // device-memory calls without a caller stream
 	unsigned long long *d_counters = nullptr; // [0] qp rows processed, [1..8] rc histogram
@@ -155,6 +160,40 @@ int launch_explicit(asif_engine *e, int64_t n, const double *x, const double *ud
 	return ASIF_OK;
 }
 
+template <class M, int NPBTSS>
+int launch_implicit(asif_engine *e, int64_t n, const double *x, const double *ud, double *ua, double *relax, int32_t *rc,
+                    double *diag, cudaStream_t st)
+{
+	const size_t smem = sizeof(double) * imp_smem_doubles_per_thread<M, NPBTSS>() * IMP_THREADS;
+	const unsigned blocks = (unsigned)((n + IMP_THREADS - 1) / IMP_THREADS);
+	if (diag) {
+		auto k = implicit_filter_kernel<M, NPBTSS, true>;
+		int r = set_smem(k, smem);
+		if (r) return r;
+		k<<<blocks, IMP_THREADS, smem, st>>>(e->im, n, x, ud, ua, relax, rc, diag, e->d_counters);
+	} else {
+		auto k = implicit_filter_kernel<M, NPBTSS, false>;
+		int r = set_smem(k, smem);
+		if (r) return r;
+		k<<<blocks, IMP_THREADS, smem, st>>>(e->im, n, x, ud, ua, relax, rc, nullptr, e->d_counters);
+	}
+	CUDA_TRY(cudaGetLastError());
+	return ASIF_OK;
+}
+
+int launch_robust(asif_engine *e, int64_t n, const double *x, const double *ud, double *ua, double *relax, int32_t *rc,
+                  double *diag, cudaStream_t st)
+{
+	const size_t smem = sizeof(double) * 2 * (size_t)e->rb.n_halfplanes;
+	const unsigned blocks = (unsigned)((n + ROB_THREADS - 1) / ROB_THREADS);
+	if (diag)
+		robust_ip_filter_kernel<true><<<blocks, ROB_THREADS, smem, st>>>(e->rb, n, x, ud, ua, relax, rc, diag, e->d_counters);
+	else
+		robust_ip_filter_kernel<false><<<blocks, ROB_THREADS, smem, st>>>(e->rb, n, x, ud, ua, relax, rc, nullptr, e->d_counters);
+	CUDA_TRY(cudaGetLastError());
+	return ASIF_OK;
+}
+
 int launch_filter(asif_engine *e, int64_t n, const double *x, const double *ud, double *ua, double *relax, int32_t *rc,
                   double *diag, cudaStream_t st)
 {
@@ -168,6 +207,13 @@ int launch_filter(asif_engine *e, int64_t n, const double *x, const double *ud, 
 		case ASIF_MODEL_SEGWAY: return launch_tb<SegwayTB<true>, 4>(e, n, x, ud, ua, relax, rc, diag, st);
 		case ASIF_MODEL_SEGWAY_SHIPPED: return launch_tb<SegwayTB<false>, 4>(e, n, x, ud, ua, relax, rc, diag, st);
 		}
+		break;
+	case ASIF_FILTER_IMPLICIT:
+		if (e->cfg.model == ASIF_MODEL_INVERTED_PENDULUM)
+			return launch_implicit<InvertedPendulumImplicit, 10>(e, n, x, ud, ua, relax, rc, diag, st);
+		break;
+	case ASIF_FILTER_ROBUST:
+		if (e->cfg.model == ASIF_MODEL_INVERTED_PENDULUM_TABLE) return launch_robust(e, n, x, ud, ua, relax, rc, diag, st);
 		break;
 	}
 	return fail(ASIF_ERR_UNSUPPORTED, "no kernel for filter %d / model %d", e->cfg.filter, e->cfg.model);
@@ -280,6 +326,7 @@ int32_t asif_engine_config_init(asif_engine_config *cfg, int32_t filter, int32_t
 	case ASIF_MODEL_INVERTED_PENDULUM:
 	case ASIF_MODEL_INVERTED_PENDULUM_TABLE:
 		cfg->lb[0] = -1.5; cfg->ub[0] = 1.5; /* examples/InvertedPendulum_Implicit.cpp:19-20 */
+		cfg->dynParam[0] = 0.8; cfg->dynParam[1] = 1.2; /* input-gain interval, examples/InvertedPendulum_Robust.cpp:35-38 */
 		break;
 	case ASIF_MODEL_SEGWAY:
 	case ASIF_MODEL_SEGWAY_SHIPPED:
@@ -394,6 +441,96 @@ int32_t asif_engine_create(const asif_engine_config *cfg, asif_engine **out)
 		p.gih[nu] = sqrt(p.gi[nu]);
 		break;
 	}
+	case ASIF_FILTER_IMPLICIT: {
+		if (cfg->model != ASIF_MODEL_INVERTED_PENDULUM) {
+			delete e;
+			return fail(ASIF_ERR_UNSUPPORTED, "implicit filter: model %d not compiled in", cfg->model);
+		}
+		if (cfg->npBTSS != 10) {
+			delete e;
+			return fail(ASIF_ERR_UNSUPPORTED, "implicit filter: npBTSS = %d not compiled in (10 is)", cfg->npBTSS);
+		}
+		if (!(cfg->backTrajDt > 0) || !(cfg->backTrajHorizon > 0)) {
+			delete e;
+			return fail(ASIF_ERR_INVALID_ARGUMENT, "backTrajDt and backTrajHorizon must be > 0");
+		}
+		const int npBS = 1;
+		e->n_relax = 2;
+		e->nv = nu + 2;
+		e->nc = cfg->npBTSS * npSS + npBS;
+		e->n_diag = 2 + cfg->npBTSS + e->nc * e->nv + e->nc;
+		ImplicitParams &p = e->im;
+		memset(&p, 0, sizeof(p));
+		for (int i = 0; i < nu; i++) {
+			p.lb[i] = cfg->lb[i];
+			p.ub[i] = cfg->ub[i];
+			p.gi[i] = 1.0 / 2.0;
+			p.gih[i] = sqrt(p.gi[i]);
+		}
+		p.relaxCost = cfg->relaxCost;
+		p.relaxSafeLb = cfg->relaxLb;
+		p.relaxReachLb = cfg->relaxReachLb;
+		p.backTrajDt = cfg->backTrajDt;
+		p.inf = cfg->inf;
+		// src/asif_implicit.cpp:211-216 (this class has no backTrajExtend)
+		int64_t npBT = (int64_t)round(cfg->backTrajHorizon / cfg->backTrajDt) + 1;
+		if (npBT < cfg->npBTSS) {
+			npBT = cfg->npBTSS;
+			p.backTrajDt = cfg->backTrajHorizon / (double)(npBT - 1);
+		}
+		if (npBT > (1 << 24)) {
+			delete e;
+			return fail(ASIF_ERR_INVALID_ARGUMENT, "backup trajectory of %lld points is not sensible", (long long)npBT);
+		}
+		p.npBT = (int32_t)npBT;
+		make_softsat(cfg->satSharpness, cfg->lb, cfg->ub, nu, p.sat);
+		for (int i = nu; i < nu + 2; i++) {
+			p.gi[i] = 1.0 / (2.0 * cfg->relaxCost);
+			p.gih[i] = sqrt(p.gi[i]);
+		}
+		break;
+	}
+	case ASIF_FILTER_ROBUST: {
+		if (cfg->model != ASIF_MODEL_INVERTED_PENDULUM_TABLE) {
+			delete e;
+			return fail(ASIF_ERR_UNSUPPORTED, "robust filter: model %d not compiled in", cfg->model);
+		}
+		if (!cfg->halfplanes || cfg->n_halfplanes < 1 || cfg->n_halfplanes > 4096) {
+			delete e;
+			return fail(ASIF_ERR_INVALID_ARGUMENT, "robust filter needs a half-plane table (1..4096 rows)");
+		}
+		if (!(cfg->dynParam[0] <= cfg->dynParam[1])) {
+			delete e;
+			return fail(ASIF_ERR_INVALID_ARGUMENT, "dynParam[0..1] = [pMin, pMax] must be ordered");
+		}
+		const int K = cfg->n_halfplanes;
+		e->nc = 2 * K; // rows of the reduced problem
+		e->n_diag = 5 * K;
+		RobustParams &p = e->rb;
+		memset(&p, 0, sizeof(p));
+		p.lb[0] = cfg->lb[0];
+		p.ub[0] = cfg->ub[0];
+		p.relaxLb = cfg->relaxLb;
+		p.relaxCost = cfg->relaxCost;
+		p.inf = cfg->inf;
+		p.gc = (cfg->dynParam[0] + cfg->dynParam[1]) / 2; // AAF(interval): centre, radius (aa_aafcommon.cpp:81-101)
+		p.gr = (cfg->dynParam[1] - cfg->dynParam[0]) / 2;
+		p.gi[0] = 0.5;
+		p.gih[0] = sqrt(0.5);
+		p.gi[1] = 1.0 / (2.0 * cfg->relaxCost);
+		p.gih[1] = sqrt(p.gi[1]);
+		p.n_halfplanes = K;
+		cudaError_t te = cudaMalloc(&e->d_table, sizeof(double) * 2 * K);
+		if (te == cudaSuccess) te = cudaMemcpy(e->d_table, cfg->halfplanes, sizeof(double) * 2 * K, cudaMemcpyHostToDevice);
+		if (te != cudaSuccess) {
+			cudaFree(e->d_table);
+			delete e;
+			return fail(ASIF_ERR_CUDA, "table upload failed: %s", cudaGetErrorString(te));
+		}
+		p.table = e->d_table;
+		e->cfg.halfplanes = nullptr; // borrowed pointer is not kept
+		break;
+	}
 	default:
 		delete e;
 		return fail(ASIF_ERR_UNSUPPORTED, "filter %d not implemented yet", cfg->filter);
@@ -425,6 +562,7 @@ int32_t asif_engine_destroy(asif_engine *e)
 		cudaStreamDestroy(e->stream);
 	}
 	cudaFree(e->d_counters);
+	cudaFree(e->d_table);
 	delete e;
 	return ASIF_OK;
 }

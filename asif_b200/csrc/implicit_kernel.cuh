@@ -1,0 +1,336 @@
+// implicit_kernel.cuh -- batched ASIFimplicit::filter, one state per thread.
+// Reference path replaced: src/asif_implicit.cpp:305-356 (filter), :403-611 (updateConstraints),
+// closed-loop rhs :751-827 (identical to the TB class), and the OSQP solve behind it.
+// Same design as tb_kernel.cuh: streaming selection of the NPBTSS smallest min-h points over the
+// WHOLE horizon (no hit test, :487), snapshots in shared memory, rows recomputed on demand, plus
+// NPBS backup-set rows taken at the end of the trajectory (:542-554) with their own relax variable.
+// QP in v = (u, delta_safe, delta_reach).
+#pragma once
+#include "filter_common.cuh"
+#include "qp_gi.cuh"
+
+namespace asifb {
+
+constexpr int IMP_THREADS = 128;
+
+// Options of ASIFimplicit (include/asif_implicit.h:20-34) + what initialize() derives (src/asif_implicit.cpp:211-254)
+struct ImplicitParams {
+	double lb[MAX_NU], ub[MAX_NU];
+	double relaxCost, relaxSafeLb, relaxReachLb;
+	double backTrajDt, inf;
+	int32_t npBT;
+	int32_t pad_;
+	SoftSat sat;
+	double gi[MAX_NV], gih[MAX_NV];
+};
+
+template <class M, int NPBTSS>
+__host__ __device__ constexpr int imp_smem_doubles_per_thread()
+{
+	return NPBTSS * (M::NX + M::NX * M::NX);
+}
+
+template <class M, int NPBTSS>
+struct ImpRows {
+	static constexpr int NX = M::NX, NU = M::NU, NPSS = M::NPSS, NPBS = M::NPBS, NS = NX + NX * NX;
+	static constexpr int NSAFE = NPBTSS * NPSS, NC = NSAFE + NPBS, NV = NU + 2;
+	const double *snap;
+	int T;
+	double f[NX], g[NX * NU];
+	int kslot[NPBTSS];
+	double lgB[NPBS][NU], hB[NPBS], rhsB[NPBS]; // backup rows
+	double lb[NV], ub[NV];
+
+	__device__ __forceinline__ void point_rows(const int slot, double (&n)[NPSS][NV], double (&rhs)[NPSS]) const
+	{
+		double xs[NS], hs[NPSS], Dhs[NPSS * NX];
+#pragma unroll
+		for (int e = 0; e < NS; e++) xs[e] = snap[(slot * NS + e) * T];
+		M::safety_set(xs, hs, Dhs);
+#pragma unroll
+		for (int j = 0; j < NPSS; j++) {
+			double dh[NX];
+#pragma unroll
+			for (int cc = 0; cc < NX; cc++) {
+				double acc = Dhs[j] * xs[NX + cc * NX];
+#pragma unroll
+				for (int m = 1; m < NX; m++) acc = acc + Dhs[j + m * NPSS] * xs[NX + m + cc * NX];
+				dh[cc] = acc;
+			}
+			double lf = dh[0] * f[0];
+#pragma unroll
+			for (int m = 1; m < NX; m++) lf = lf + dh[m] * f[m];
+#pragma unroll
+			for (int i = 0; i < NU; i++) {
+				double lg = dh[0] * g[i * NX];
+#pragma unroll
+				for (int m = 1; m < NX; m++) lg = lg + dh[m] * g[m + i * NX];
+				n[j][i] = lg;
+			}
+			n[j][NU] = hs[j];
+			n[j][NU + 1] = 0.0;
+			rhs[j] = -lf;
+		}
+	}
+	__device__ __forceinline__ void bound_row(const int k, double (&n)[NV], double &rhs) const
+	{
+		const int var = k >> 1;
+		const bool upper = k & 1;
+		double bnd = 0.0;
+#pragma unroll
+		for (int i = 0; i < NV; i++) {
+			n[i] = (i == var) ? (upper ? -1.0 : 1.0) : 0.0;
+			if (i == var) bnd = upper ? -ub[i] : lb[i];
+		}
+		rhs = bnd;
+	}
+	__device__ __forceinline__ void backup_row(const int r, double (&n)[NV], double &rhs) const
+	{
+#pragma unroll
+		for (int t = 0; t < NPBS; t++) {
+			if (t == r) {
+#pragma unroll
+				for (int i = 0; i < NU; i++) n[i] = lgB[t][i];
+				n[NU] = 0.0;
+				n[NU + 1] = hB[t];
+				rhs = rhsB[t];
+			}
+		}
+	}
+	template <class F>
+	__device__ __forceinline__ void scan(F &&fn) const
+	{
+#pragma unroll 1
+		for (int s = 0; s < NPBTSS; s++) {
+			int slot = 0;
+#pragma unroll
+			for (int t = 0; t < NPBTSS; t++) slot = (t == s) ? kslot[t] : slot;
+			double n[NPSS][NV], rhs[NPSS];
+			point_rows(slot, n, rhs);
+#pragma unroll
+			for (int j = 0; j < NPSS; j++) fn(s * NPSS + j, n[j], rhs[j]);
+		}
+#pragma unroll
+		for (int r = 0; r < NPBS; r++) {
+			double n[NV], rhs = 0.0;
+			backup_row(r, n, rhs);
+			fn(NSAFE + r, n, rhs);
+		}
+#pragma unroll
+		for (int k = 0; k < 2 * NV; k++) {
+			double n[NV], rhs;
+			bound_row(k, n, rhs);
+			fn(NC + k, n, rhs);
+		}
+	}
+	__device__ __forceinline__ void get(const int j, double (&n)[NV], double &rhs) const
+	{
+		if (j >= NC) {
+			bound_row(j - NC, n, rhs);
+		} else if (j >= NSAFE) {
+			backup_row(j - NSAFE, n, rhs);
+		} else {
+			const int s = j / NPSS, jj = j - s * NPSS;
+			int slot = 0;
+#pragma unroll
+			for (int t = 0; t < NPBTSS; t++) slot = (t == s) ? kslot[t] : slot;
+			double nn[NPSS][NV], rr[NPSS];
+			point_rows(slot, nn, rr);
+#pragma unroll
+			for (int t = 0; t < NPSS; t++) {
+				if (t == jj) {
+#pragma unroll
+					for (int i = 0; i < NV; i++) n[i] = nn[t][i];
+					rhs = rr[t];
+				}
+			}
+		}
+	}
+};
+
+template <class M, int NPBTSS, bool WITH_DIAG>
+__global__ void __launch_bounds__(IMP_THREADS, 3)
+implicit_filter_kernel(const ImplicitParams p, const int64_t n, const double *__restrict__ x_in,
+                       const double *__restrict__ u_des, double *__restrict__ u_act, double *__restrict__ relax_out,
+                       int32_t *__restrict__ rc_out, double *__restrict__ diag, unsigned long long *__restrict__ qp_iter_sum)
+{
+	constexpr int NX = M::NX, NU = M::NU, NPSS = M::NPSS, NPBS = M::NPBS;
+	constexpr int NS = NX + NX * NX;
+	constexpr int NSAFE = NPBTSS * NPSS, NC = NSAFE + NPBS, NV = NU + 2;
+	constexpr int NDIAG = 2 + NPBTSS + NC * NV + NC;
+
+	extern __shared__ double smem[];
+	const int T = blockDim.x;
+	double *snap = smem + threadIdx.x;
+	const int64_t k = (int64_t)blockIdx.x * T + threadIdx.x;
+	const bool live = k < n;
+	const int64_t kk = live ? k : (n - 1);
+	double x0[NX], ud[NU];
+#pragma unroll
+	for (int i = 0; i < NX; i++) x0[i] = x_in[kk * NX + i];
+#pragma unroll
+	for (int i = 0; i < NU; i++) ud[i] = u_des[kk * NU + i];
+
+	double hs[NPSS], Dhs[NPSS * NX];
+	M::safety_set(x0, hs, Dhs);
+	double hSafetyNow = hs[0];
+#pragma unroll
+	for (int j = 1; j < NPSS; j++) hSafetyNow = (hs[j] < hSafetyNow) ? hs[j] : hSafetyNow;
+
+	ImpRows<M, NPBTSS> R;
+	R.snap = snap;
+	R.T = T;
+	double X[NS];
+#pragma unroll
+	for (int i = 0; i < NS; i++) X[i] = 0.0;
+#pragma unroll
+	for (int i = 0; i < NX; i++) X[i] = x0[i];
+#pragma unroll
+	for (int i = 0; i < NX; i++) X[NX + i * (NX + 1)] = 1.0;
+	double key[NPBTSS];
+	int kidx[NPBTSS];
+#pragma unroll
+	for (int s = 0; s < NPBTSS; s++) {
+		key[s] = INFINITY;
+		kidx[s] = -1;
+		R.kslot[s] = s;
+	}
+	key[0] = hSafetyNow;
+	kidx[0] = 0;
+#pragma unroll
+	for (int e = 0; e < NS; e++) snap[(R.kslot[0] * NS + e) * T] = X[e];
+
+	const int N = p.npBT;
+	for (int i = 1; i < N; i++) {
+		double Xd[NS], DfCL[NX * NX];
+		backup_cl_dynamics<M>(p.sat, p.lb, p.ub, X, Xd, DfCL);
+		sensitivity_rhs<M>(DfCL, X + NX, Xd + NX);
+#pragma unroll
+		for (int e = 0; e < NS; e++) X[e] = Xd[e] * p.backTrajDt + X[e];
+		M::safety_set(X, hs, Dhs);
+		double hmin = hs[0];
+#pragma unroll
+		for (int j = 1; j < NPSS; j++) hmin = (hs[j] < hmin) ? hs[j] : hmin;
+		if (hmin < key[NPBTSS - 1]) {
+			const int slot = R.kslot[NPBTSS - 1];
+#pragma unroll
+			for (int e = 0; e < NS; e++) snap[(slot * NS + e) * T] = X[e];
+			double ck = hmin;
+			int ci = i, cs = slot;
+			bool ins = false;
+#pragma unroll
+			for (int s = 0; s < NPBTSS; s++) {
+				const bool sw = ins || (ck < key[s]);
+				ins = sw;
+				const double tk = key[s];
+				const int ti = kidx[s], ts = R.kslot[s];
+				key[s] = sw ? ck : tk;
+				kidx[s] = sw ? ci : ti;
+				R.kslot[s] = sw ? cs : ts;
+				ck = sw ? tk : ck;
+				ci = sw ? ti : ci;
+				cs = sw ? ts : cs;
+			}
+		}
+	}
+	// open-loop dynamics at the current state (:414-416) and the backup rows at the trajectory end (:542-554)
+	M::dynamics(x0, R.f, R.g);
+	double hBackupEnd;
+	{
+		double hB[NPBS], DhB[NPBS * NX];
+		M::backup_set_rows(X, hB, DhB);
+		hBackupEnd = hB[0];
+#pragma unroll
+		for (int r = 1; r < NPBS; r++) hBackupEnd = (hB[r] < hBackupEnd) ? hB[r] : hBackupEnd;
+#pragma unroll
+		for (int r = 0; r < NPBS; r++) {
+			double dh[NX];
+#pragma unroll
+			for (int cc = 0; cc < NX; cc++) {
+				double acc = DhB[r] * X[NX + cc * NX];
+#pragma unroll
+				for (int m = 1; m < NX; m++) acc = acc + DhB[r + m * NPBS] * X[NX + m + cc * NX];
+				dh[cc] = acc;
+			}
+			double lf = dh[0] * R.f[0];
+#pragma unroll
+			for (int m = 1; m < NX; m++) lf = lf + dh[m] * R.f[m];
+#pragma unroll
+			for (int i = 0; i < NU; i++) {
+				double lg = dh[0] * R.g[i * NX];
+#pragma unroll
+				for (int m = 1; m < NX; m++) lg = lg + dh[m] * R.g[m + i * NX];
+				R.lgB[r][i] = lg;
+			}
+			R.hB[r] = hB[r];
+			R.rhsB[r] = -lf;
+		}
+	}
+	// cost, bounds (:238-254), QP, post-solve (:334-353)
+	double c[NV], v[NV];
+	DiagMetric<NV> mt;
+#pragma unroll
+	for (int i = 0; i < NU; i++) {
+		c[i] = -2.0 * ud[i];
+		R.lb[i] = p.lb[i];
+		R.ub[i] = p.ub[i];
+	}
+	c[NU] = -2.0 * p.relaxCost * p.relaxSafeLb;
+	c[NU + 1] = -2.0 * p.relaxCost * p.relaxReachLb;
+	R.lb[NU] = p.relaxSafeLb;
+	R.lb[NU + 1] = p.relaxReachLb;
+	R.ub[NU] = p.inf;
+	R.ub[NU + 1] = p.inf;
+#pragma unroll
+	for (int i = 0; i < NV; i++) {
+		mt.gi[i] = p.gi[i];
+		mt.gih[i] = p.gih[i];
+	}
+	int iters = 0;
+	const int st = qp_gi_solve<NV>(mt, c, R, v, &iters);
+	double uo[NU], r0 = 0.0, r1 = 0.0;
+	int32_t rc;
+	if (st == QP_OK) {
+#pragma unroll
+		for (int i = 0; i < NU; i++) uo[i] = input_saturate(v[i], p.lb[i], p.ub[i]);
+		r0 = v[NU];
+		r1 = v[NU + 1];
+		rc = 1;
+	} else {
+		double Du[NU * NX];
+		M::backup_controller(x0, uo, Du);
+#pragma unroll
+		for (int i = 0; i < NU; i++) uo[i] = input_saturate(uo[i], p.lb[i], p.ub[i]);
+		rc = -1;
+	}
+	if (live) {
+#pragma unroll
+		for (int i = 0; i < NU; i++) u_act[k * NU + i] = uo[i];
+		relax_out[k * 2] = r0;
+		relax_out[k * 2 + 1] = r1;
+		rc_out[k] = rc;
+		if (WITH_DIAG) {
+			double *d = diag + k * NDIAG;
+			d[0] = hSafetyNow;
+			d[1] = hBackupEnd;
+#pragma unroll
+			for (int s = 0; s < NPBTSS; s++) d[2 + s] = (double)kidx[s];
+			double *A = d + 2 + NPBTSS, *b = A + NC * NV;
+			R.scan([&](const int j, const double(&nn)[NV], const double rhs) {
+				if (j < NC) {
+#pragma unroll
+					for (int i = 0; i < NV; i++) A[j + i * NC] = nn[i];
+					b[j] = rhs;
+				}
+			});
+		}
+	}
+	if (qp_iter_sum) {
+		unsigned int it = live ? (unsigned int)iters : 0u;
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) it += __shfl_xor_sync(0xffffffffu, it, o);
+		if ((threadIdx.x & 31) == 0 && it) atomicAdd(qp_iter_sum, (unsigned long long)it);
+	}
+}
+
+} // namespace asifb

@@ -277,4 +277,66 @@ struct SegwayTB {
 	__device__ static void dynamics_with_gradient(const double *, const double *, double *, double *, double *) {}
 };
 
+// ------------------------------------------------------------------ InvertedPendulum (implicit)
+// examples/InvertedPendulum_Implicit.cpp:13-80
+struct InvertedPendulumImplicit {
+	static constexpr int NX = 2, NU = 1, NPSS = 4, NPBS = 1;
+	static constexpr bool FUSED_GRADIENT = false;
+	// g = {0,1}; Df = {0, cos x0, 1, 0} column-major; Dg = 0
+	__host__ __device__ static constexpr int g_pat(int i)
+	{
+		constexpr int t[2] = {0, 1};
+		return t[i];
+	}
+	__host__ __device__ static constexpr int df_pat(int i)
+	{
+		constexpr int t[4] = {0, 2, 1, 0};
+		return t[i];
+	}
+	__host__ __device__ static constexpr int dg_pat(int i)
+	{
+		constexpr int t[4] = {0, 0, 0, 0};
+		return t[i];
+	}
+	__device__ static void safety_set(const double *x, double *h, double *Dh)
+	{
+		h[0] = -x[0] + M_PI;   Dh[0] = -1.0; Dh[4] = 0.0;
+		h[1] = x[0] - (-M_PI); Dh[1] = 1.0;  Dh[5] = 0.0;
+		h[2] = x[1] - (-M_PI); Dh[2] = 0.0;  Dh[6] = 1.0;
+		h[3] = -x[1] + M_PI;   Dh[3] = 0.0;  Dh[7] = -1.0;
+	}
+	// h = Pv - x'Px, P = {1.25,.25,.25,.25}, Pv = 0.05 (:39-52): the four products in loop order
+	__device__ static void backup_set_rows(const double *x, double *h, double *Dh)
+	{
+		double v = 0.05;
+		v -= 1.25 * x[0] * x[0];
+		v -= 0.25 * x[0] * x[1];
+		v -= 0.25 * x[1] * x[0];
+		v -= 0.25 * x[1] * x[1];
+		h[0] = v;
+		Dh[0] = (-2.5) * x[0] + (-0.5) * x[1];
+		Dh[1] = (-0.5) * x[0] + (-0.5) * x[1];
+	}
+	__device__ static void backup_controller(const double *x, double *u, double *Du)
+	{
+		u[0] = (-3.0) * x[0] + (-3.0) * x[1];
+		Du[0] = -3.0;
+		Du[1] = -3.0;
+	}
+	__device__ static void dynamics(const double *x, double *f, double *g)
+	{
+		f[0] = x[1];
+		f[1] = sin(x[0]);
+		g[0] = 0.;
+		g[1] = 1.;
+	}
+	__device__ static void dynamics_gradients(const double *x, double *Df, double *Dg)
+	{
+		Df[0] = 0.;        Df[2] = 1.;
+		Df[1] = cos(x[0]); Df[3] = 0.;
+		Dg[0] = Dg[1] = Dg[2] = Dg[3] = 0.0;
+	}
+	__device__ static void dynamics_with_gradient(const double *, const double *, double *, double *, double *) {}
+};
+
 } // namespace asifb

@@ -1,0 +1,161 @@
+// robust_kernel.cuh -- batched ASIFrobust::filter on a half-plane safety table, one state per thread.
+// Reference path replaced: src/asif_robust.cpp:218-252 (filter), :275-367 (updateConstraints) with
+// the interval Lie derivatives libaffa produces, and the 402-variable LP-dual QP behind it.
+//
+// The reference carries 2(nu+1) multipliers per safety function (nv = nu+1+2 npSS (nu+1), dense).
+// They have zero cost and can be eliminated exactly: row k holds for some lambda >= 0 iff
+//     h_k d + min(Lg-_k u, Lg+_k u) + Lf-_k >= 0     (nu = 1)
+// i.e. two ordinary rows in (u, d).  The optimum (u*, d*) is identical; the multipliers
+// are not outputs.  So per state: K half-planes -> 2K rows, nothing stored: the active-set solver's
+// scan recomputes each row from the table entry (shared memory, same address for all lanes ->
+// broadcast) and four per-state scalars.  HBM traffic stays 44 B per state; the table is read once
+// per CTA.
+//
+// Interval values for the InvertedPendulum dynamics on a point state (examples/InvertedPendulum_Robust.cpp:62-69):
+// f = [x1, sin x0] exact, g = [0, [pMin, pMax]] = centre (pMin+pMax)/2 +- (pMax-pMin)/2, hence
+// Lf_k = Dh_k0 f0 + Dh_k1 f1 (a point) and Lg_k = Dh_k1 gc +- |Dh_k1 gr|.
+#pragma once
+#include "filter_common.cuh"
+#include "qp_gi.cuh"
+
+namespace asifb {
+
+constexpr int ROB_THREADS = 128;
+
+struct RobustParams {
+	double lb[MAX_NU], ub[MAX_NU];
+	double relaxLb, relaxCost, inf;
+	double gc, gr; // centre and radius of the input-gain interval
+	double gi[MAX_NV], gih[MAX_NV];
+	int32_t n_halfplanes;
+	int32_t pad_;
+	const double *table; // device pointer, [n_halfplanes][2]
+};
+
+struct RobustRows {
+	static constexpr int NV = 2;
+	const double *tab; // shared memory
+	int K;
+	double x0, x1, f0, f1, gc, gr;
+	double lb[NV], ub[NV];
+	__device__ __forceinline__ void plane(const int k, double &h, double &lo, double &hi, double &lf) const
+	{
+		const double a0 = tab[2 * k], a1 = tab[2 * k + 1];
+		h = 1. - a0 * x0 - a1 * x1;
+		const double Dh0 = -a0, Dh1 = -a1;
+		lf = Dh0 * f0 + Dh1 * f1;
+		const double lgc = Dh1 * gc, lgr = fabs(Dh1 * gr);
+		lo = lgc - lgr;
+		hi = lgc + lgr;
+	}
+	__device__ __forceinline__ void bound_row(const int k, double (&n)[NV], double &rhs) const
+	{
+		const int var = k >> 1;
+		const bool upper = k & 1;
+		double bnd = 0.0;
+#pragma unroll
+		for (int i = 0; i < NV; i++) {
+			n[i] = (i == var) ? (upper ? -1.0 : 1.0) : 0.0;
+			if (i == var) bnd = upper ? -ub[i] : lb[i];
+		}
+		rhs = bnd;
+	}
+	template <class F>
+	__device__ __forceinline__ void scan(F &&fn) const
+	{
+		for (int k = 0; k < K; k++) {
+			double h, lo, hi, lf;
+			plane(k, h, lo, hi, lf);
+			double n[NV] = {lo, h};
+			fn(2 * k, n, -lf);
+			n[0] = hi;
+			fn(2 * k + 1, n, -lf);
+		}
+#pragma unroll
+		for (int k = 0; k < 2 * NV; k++) {
+			double n[NV], rhs;
+			bound_row(k, n, rhs);
+			fn(2 * K + k, n, rhs);
+		}
+	}
+	__device__ __forceinline__ void get(const int j, double (&n)[NV], double &rhs) const
+	{
+		if (j >= 2 * K) {
+			bound_row(j - 2 * K, n, rhs);
+		} else {
+			double h, lo, hi, lf;
+			plane(j >> 1, h, lo, hi, lf);
+			n[0] = (j & 1) ? hi : lo;
+			n[1] = h;
+			rhs = -lf;
+		}
+	}
+};
+
+template <bool WITH_DIAG>
+__global__ void __launch_bounds__(ROB_THREADS)
+robust_ip_filter_kernel(const RobustParams p, const int64_t n, const double *__restrict__ x_in,
+                        const double *__restrict__ u_des, double *__restrict__ u_act, double *__restrict__ relax_out,
+                        int32_t *__restrict__ rc_out, double *__restrict__ diag, unsigned long long *__restrict__ qp_iter_sum)
+{
+	extern __shared__ double tab[];
+	const int K = p.n_halfplanes;
+	for (int i = threadIdx.x; i < 2 * K; i += blockDim.x) tab[i] = p.table[i];
+	__syncthreads();
+	const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	const bool live = k < n;
+	const int64_t kk = live ? k : (n - 1);
+	RobustRows R;
+	R.tab = tab;
+	R.K = K;
+	R.x0 = x_in[kk * 2];
+	R.x1 = x_in[kk * 2 + 1];
+	R.f0 = R.x1;
+	R.f1 = sin(R.x0);
+	R.gc = p.gc;
+	R.gr = p.gr;
+	R.lb[0] = p.lb[0];
+	R.ub[0] = p.ub[0];
+	R.lb[1] = p.relaxLb;
+	R.ub[1] = p.inf;
+	double c[2] = {-2.0 * u_des[kk], -2.0 * p.relaxCost * p.relaxLb}, v[2];
+	DiagMetric<2> mt;
+#pragma unroll
+	for (int i = 0; i < 2; i++) {
+		mt.gi[i] = p.gi[i];
+		mt.gih[i] = p.gih[i];
+	}
+	int iters = 0;
+	const int st = qp_gi_solve<2>(mt, c, R, v, &iters);
+	if (live) {
+		if (st == QP_OK) {
+			u_act[k] = input_saturate(v[0], p.lb[0], p.ub[0]);
+			relax_out[k] = v[1];
+			rc_out[k] = 1;
+		} else { // the reference leaves uAct untouched (src/asif_robust.cpp:249-251); a batch defines it as 0
+			u_act[k] = 0.0;
+			relax_out[k] = 0.0;
+			rc_out[k] = -1;
+		}
+		if (WITH_DIAG) {
+			double *d = diag + k * (5 * (int64_t)K);
+			for (int j = 0; j < K; j++) {
+				double h, lo, hi, lf;
+				R.plane(j, h, lo, hi, lf);
+				d[5 * j] = h;
+				d[5 * j + 1] = lo;
+				d[5 * j + 2] = hi;
+				d[5 * j + 3] = lf;
+				d[5 * j + 4] = lf;
+			}
+		}
+	}
+	if (qp_iter_sum) {
+		unsigned int it = live ? (unsigned int)iters : 0u;
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) it += __shfl_xor_sync(0xffffffffu, it, o);
+		if ((threadIdx.x & 31) == 0 && it) atomicAdd(qp_iter_sum, (unsigned long long)it);
+	}
+}
+
+} // namespace asifb

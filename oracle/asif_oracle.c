@@ -485,13 +485,173 @@ static int32_t explicit_filter(const oracle_model *md, double relaxLb, double re
 	return -1;
 }
 
+
+/* ------------------------------------------------------------------------------------------
+ * ASIFimplicit, src/asif_implicit.cpp:194-266 (initialize), :305-356 (filter), :403-611 (updateConstraints)
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+	double relaxCost, relaxReachLb, relaxSafeLb, backTrajHorizon, backTrajDt, satSharpness, inf;
+	int npBTSS;
+} imp_options;
+
+static int32_t implicit_filter(const oracle_model *md, const imp_options *o, int N, const double *x, const double *uDes,
+                               double *uAct, double *relax, double *diag)
+{
+	const int nx = md->nx, nu = md->nu, npSS = md->npSS, npBS = md->npBS, npBTSS = o->npBTSS;
+	const int ns = nx + nx * nx, npTC = npBTSS * npSS + npBS, nv = nu + 2;
+	double f[NX], g[NX * NU];
+	md->dynamics(x, f, g); /* :414-416 */
+	double *traj = (double *)malloc(sizeof(double) * (size_t)N * ns);
+	double *t = (double *)malloc(sizeof(double) * N);
+	double *hFull = (double *)malloc(sizeof(double) * (size_t)N * npSS);
+	double *DhFull = (double *)malloc(sizeof(double) * (size_t)N * npSS * nx);
+	double *hFullMin = (double *)malloc(sizeof(double) * N);
+	integrate_backup_trajectory(md, o->satSharpness, o->backTrajDt, N, x, traj, t, hFull, DhFull, hFullMin);
+	int crit[64];
+	k_smallest(hFullMin, N, npBTSS, crit); /* std::sort over all N points, :487 */
+
+	double *h = (double *)calloc(npTC, sizeof(double));
+	double *Dh = (double *)calloc((size_t)npTC * nx, sizeof(double));
+	double DhSSDx[64];
+	for (int idx = 0; idx < npBTSS; idx++) { /* :518-540 */
+		int c = crit[idx];
+		memcpy(h + idx * npSS, hFull + (size_t)c * npSS, sizeof(double) * npSS);
+		mat_mul(DhFull + (size_t)c * npSS * nx, npSS, nx, traj + (size_t)c * ns + nx, nx, DhSSDx);
+		for (int i = 0; i < npSS; i++)
+			for (int j = 0; j < nx; j++) Dh[(idx * npSS + i) + j * npTC] = DhSSDx[i + j * npSS];
+	}
+	/* backup-set rows at the end of the trajectory, :542-554 */
+	const double *btX = traj + (size_t)(N - 1) * ns;
+	double DhBS[4 * NX], DhBSDx[4 * NX];
+	md->backup_set(btX, h + npBTSS * npSS, DhBS, 0);
+	double hBackupEnd = min_elem(h + npBTSS * npSS, npBS);
+	mat_mul(DhBS, npBS, nx, btX + nx, nx, DhBSDx);
+	for (int i = 0; i < npBS; i++)
+		for (int j = 0; j < nx; j++) Dh[(npBTSS * npSS + i) + j * npTC] = DhBSDx[i + j * npBS];
+
+	double *Lfh = (double *)malloc(sizeof(double) * npTC);
+	double *Lgh = (double *)malloc(sizeof(double) * (size_t)npTC * nu);
+	mat_vec(Dh, npTC, nx, f, Lfh);
+	mat_mul(Dh, npTC, nx, g, nu, Lgh);
+	double *A = (double *)calloc((size_t)npTC * nv, sizeof(double));
+	double *b = (double *)calloc(npTC, sizeof(double));
+	for (int i = 0; i < npTC; i++) /* :590-611 */
+		for (int j = 0; j < nu; j++) A[i + j * npTC] = Lgh[i + j * npTC];
+	for (int i = 0; i < npBTSS * npSS; i++) A[i + nu * npTC] = h[i];
+	for (int i = npBTSS * npSS; i < npTC; i++) A[i + (nu + 1) * npTC] = h[i];
+	for (int i = 0; i < npTC; i++) b[i] = -Lfh[i];
+
+	double H[ORACLE_QP_NVMAX * ORACLE_QP_NVMAX] = {0.0}, c[ORACLE_QP_NVMAX], lb[ORACLE_QP_NVMAX], ub[ORACLE_QP_NVMAX], sol[ORACLE_QP_NVMAX];
+	for (int i = 0; i < nu; i++) {
+		H[i + i * nv] = 1.0;
+		c[i] = -2.0 * uDes[i];
+		lb[i] = md->lb[i];
+		ub[i] = md->ub[i];
+	}
+	H[(nv - 2) + (nv - 2) * nv] = o->relaxCost; /* :238-254 */
+	H[(nv - 1) + (nv - 1) * nv] = o->relaxCost;
+	c[nv - 2] = -2.0 * o->relaxCost * o->relaxSafeLb;
+	c[nv - 1] = -2.0 * o->relaxCost * o->relaxReachLb;
+	lb[nv - 2] = o->relaxSafeLb;
+	lb[nv - 1] = o->relaxReachLb;
+	ub[nv - 2] = o->inf;
+	ub[nv - 1] = o->inf;
+	int st = oracle_qp_solve(nv, npTC, 1, H, c, A, b, lb, ub, 0, sol);
+	int32_t rc;
+	if (st == 1) {
+		memcpy(uAct, sol, sizeof(double) * nu);
+		input_saturate(md, uAct);
+		relax[0] = sol[nu];
+		relax[1] = sol[nu + 1];
+		rc = 1;
+	} else {
+		double Du[NU * NX];
+		md->backup_controller(x, uAct, Du);
+		input_saturate(md, uAct);
+		rc = -1;
+	}
+	if (diag) {
+		double hs[16], Dhs[16 * NX];
+		md->safety_set(x, hs, Dhs);
+		diag[0] = min_elem(hs, npSS);
+		diag[1] = hBackupEnd;
+		for (int i = 0; i < npBTSS; i++) diag[2 + i] = (double)crit[i];
+		memcpy(diag + 2 + npBTSS, A, sizeof(double) * npTC * nv);
+		memcpy(diag + 2 + npBTSS + npTC * nv, b, sizeof(double) * npTC);
+	}
+	free(traj); free(t); free(hFull); free(DhFull); free(hFullMin);
+	free(h); free(Dh); free(Lfh); free(Lgh); free(A); free(b);
+	return rc;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * ASIFrobust on the InvertedPendulum interval dynamics + half-plane table, in the REDUCED form.
+ *
+ * Reference: src/asif_robust.cpp:275-367 builds, per safety function k, the LP-dual rows
+ *     h_k d + [Lg-_k, Lf-_k].lam+_k - [Lg+_k, Lf+_k].lam-_k >= 0,  lam+_k0 - lam-_k0 = u,  lam+_k1 - lam-_k1 = 1,
+ * lam >= 0 with zero cost (:103-150,339-358).  For fixed (u, d) the best lam is lam+ = (u+, 1), lam- = (u-, 0),
+ * so row k holds iff  h_k d + min(Lg-_k u, Lg+_k u) + Lf-_k >= 0, i.e. the two ordinary rows
+ *     Lg-_k u + h_k d >= -Lf-_k   and   Lg+_k u + h_k d >= -Lf-_k          (SURVEY F8 / 8a-R),
+ * and (u*, d*) are identical.  The interval values follow libaffa on a point state:
+ * f = [x1, sin x0] has radius 0, g = [0, [pMin, pMax]] is centre (pMin+pMax)/2 with one noise term
+ * (pMax-pMin)/2 (lib/libaffa/src/aa_aafcommon.cpp:81-101), Lg_k = Dh_k1 * g1 (aa_aafapprox.cpp:34-101).
+ * Pinned against the reference build (402 variables, 300 rows, libaffa) by tests/test_oracle_vs_ref.py.
+ * ---------------------------------------------------------------------------------------- */
+#include "oracle_tables.h"
+
+static int32_t robust_ip_filter(double relaxLb, double relaxCost, double pMin, double pMax, double inf, const double *x,
+                                const double *uDes, double *uAct, double *relax, double *diag)
+{
+	const int npSS = ORACLE_N_HALFPLANES, nc = 2 * npSS, nv = 2;
+	const double *tab = oracle_halfplanes_70_135;
+	double *A = (double *)calloc((size_t)nc * nv, sizeof(double));
+	double *b = (double *)calloc(nc, sizeof(double));
+	const double f0 = x[1], f1 = sin(x[0]);
+	const double gc = (pMin + pMax) / 2, gr = (pMax - pMin) / 2; /* AAF(interval): centre and radius */
+	for (int k = 0; k < npSS; k++) {
+		const double a0 = tab[2 * k], a1 = tab[2 * k + 1];
+		const double h = 1. - a0 * x[0] - a1 * x[1]; /* examples/InvertedPendulum_Robust.cpp:53-60 */
+		const double Dh0 = -a0, Dh1 = -a1;
+		double lf = 0.0;
+		lf = lf + Dh0 * f0;
+		lf = lf + Dh1 * f1;
+		const double lgc = Dh1 * gc, lgr = fabs(Dh1 * gr); /* centre and radius of Dh1 * g1 */
+		const double lgLo = lgc - lgr, lgHi = lgc + lgr;
+		A[2 * k] = lgLo;
+		A[2 * k + 1] = lgHi;
+		A[2 * k + nc] = h;
+		A[2 * k + 1 + nc] = h;
+		b[2 * k] = -lf;
+		b[2 * k + 1] = -lf;
+		if (diag) {
+			diag[5 * k + 0] = h;
+			diag[5 * k + 1] = lgLo;
+			diag[5 * k + 2] = lgHi;
+			diag[5 * k + 3] = lf;
+			diag[5 * k + 4] = lf;
+		}
+	}
+	double H[4] = {1.0, 0.0, 0.0, relaxCost}, c[2] = {-2.0 * uDes[0], -2.0 * relaxCost * relaxLb};
+	double lb[2] = {-1.5, relaxLb}, ub[2] = {1.5, inf}, sol[2];
+	int st = oracle_qp_solve(nv, nc, 1, H, c, A, b, lb, ub, 0, sol);
+	free(A);
+	free(b);
+	if (st == 1) {
+		uAct[0] = sol[0] > 1.5 ? 1.5 : (sol[0] < -1.5 ? -1.5 : sol[0]);
+		*relax = sol[1];
+		return 1;
+	}
+	return -1; /* uAct untouched, src/asif_robust.cpp:249-251 */
+}
+
 /* ------------------------------------------------------------------------------------------ */
 typedef struct {
 	int cfg;
 	const oracle_model *md;
 	tb_options tb;
 	int N;
-	double relaxLb, relaxCost;
+	double relaxLb, relaxCost, pMin, pMax;
+	imp_options imp;
 	int nx, nu, n_relax, nc, nv, n_diag;
 } ctx_t;
 
@@ -527,6 +687,39 @@ static int make_ctx(int cfg, const double *opts, int n_opts, ctx_t *c)
 		c->n_diag = 4 + c->tb.npBTSS + c->nc * c->nv + c->nc;
 		break;
 	}
+	case ORACLE_CFG_IP_IMPLICIT: {
+		c->md = oracle_get_model(cfg, 0);
+		imp_options *o = &c->imp;
+		/* include/asif_implicit.h:20-34 + examples/InvertedPendulum_Implicit.cpp:93-97 */
+		o->relaxCost = 50.0; o->relaxReachLb = 5.0; o->relaxSafeLb = 10.0; o->backTrajHorizon = 5.0;
+		o->backTrajDt = 0.001; o->satSharpness = 0.1; o->inf = 1e20; o->npBTSS = 10;
+		if (opts && n_opts >= 6) {
+			o->relaxCost = opts[0]; o->relaxReachLb = opts[1]; o->relaxSafeLb = opts[2];
+			o->backTrajHorizon = opts[3]; o->backTrajDt = opts[4]; o->satSharpness = opts[5];
+		}
+		/* src/asif_implicit.cpp:211-216 (no backTrajExtend in this class) */
+		c->N = (int)round(o->backTrajHorizon / o->backTrajDt) + 1;
+		if (c->N < o->npBTSS) {
+			c->N = o->npBTSS;
+			o->backTrajDt = o->backTrajHorizon / (double)(c->N - 1);
+		}
+		c->n_relax = 2;
+		c->nc = o->npBTSS * c->md->npSS + c->md->npBS;
+		c->nv = c->md->nu + 2;
+		c->n_diag = 2 + o->npBTSS + c->nc * c->nv + c->nc;
+		break;
+	}
+	case ORACLE_CFG_IP_ROBUST:
+		c->md = oracle_get_model(ORACLE_CFG_IP_IMPLICIT, 0); /* dims + open-loop plant only */
+		c->relaxLb = 5.0; c->relaxCost = 50.0; c->pMin = 0.8; c->pMax = 1.2;
+		if (opts && n_opts >= 4) {
+			c->relaxLb = opts[0]; c->relaxCost = opts[1]; c->pMin = opts[2]; c->pMax = opts[3];
+		}
+		c->n_relax = 1;
+		c->nc = 2 * ORACLE_N_HALFPLANES;
+		c->nv = 2;
+		c->n_diag = 5 * ORACLE_N_HALFPLANES;
+		break;
 	default:
 		return -1;
 	}
@@ -544,6 +737,10 @@ static int32_t filter_one(const ctx_t *c, const double *x, const double *ud, dou
 	case ORACLE_CFG_DI_IMPLICIT_TB:
 	case ORACLE_CFG_SEGWAY_TB:
 		return tb_filter(c->md, &c->tb, c->N, x, ud, ua, relax, diag);
+	case ORACLE_CFG_IP_IMPLICIT:
+		return implicit_filter(c->md, &c->imp, c->N, x, ud, ua, relax, diag);
+	case ORACLE_CFG_IP_ROBUST:
+		return robust_ip_filter(c->relaxLb, c->relaxCost, c->pMin, c->pMax, 1e20, x, ud, ua, relax, diag);
 	}
 	return -100;
 }

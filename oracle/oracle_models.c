@@ -290,12 +290,71 @@ static const oracle_model k_segway_shipped = {
 	4, 1, 4, 1, {-20.0, 0.0}, {20.0, 0.0}, seg_safety, seg_backup_set_shipped, seg_dynamics,
 	seg_dynamics_gradients, 0, seg_backup_controller};
 
+
+/* ---------------------------------------------------------------- InvertedPendulum (implicit)
+ * examples/InvertedPendulum_Implicit.cpp:13-80 */
+static void ip_safety(const double *x, double *h, double *Dh)
+{
+	/* :31-37, xBound = vBound = {-pi, pi} */
+	h[0] = -x[0] + M_PI;    Dh[0] = -1.0; Dh[4] = 0.0;
+	h[1] = x[0] - (-M_PI);  Dh[1] = 1.0;  Dh[5] = 0.0;
+	h[2] = x[1] - (-M_PI);  Dh[2] = 0.0;  Dh[6] = 1.0;
+	h[3] = -x[1] + M_PI;    Dh[3] = 0.0;  Dh[7] = -1.0;
+}
+
+static void ip_backup_set(const double *x, double *h, double *Dh, double *DDh)
+{
+	/* :39-52, P = {1.25,.25,.25,.25}, mPpPt = {-2.5,-.5,-.5,-.5}, Pv = 0.05 (not squared) */
+	static const double P[4] = {1.25, 0.25, 0.25, 0.25};
+	static const double mPpPt[4] = {-2.5, -0.5, -0.5, -0.5};
+	(void)DDh;
+	h[0] = 0.05;
+	for (int i = 0; i < 2; i++)
+		for (int j = 0; j < 2; j++) h[0] -= P[i + j * 2] * x[i] * x[j];
+	for (int i = 0; i < 2; i++) {
+		Dh[i] = 0.0;
+		for (int k = 0; k < 2; k++) Dh[i] = Dh[i] + mPpPt[i + k * 2] * x[k];
+	}
+}
+
+static void ip_dynamics(const double *x, double *f, double *g)
+{
+	/* :55-62 */
+	f[0] = x[1];
+	f[1] = sin(x[0]);
+	g[0] = 0.;
+	g[1] = 1.;
+}
+
+static void ip_backup_controller(const double *x, double *u, double *Du)
+{
+	/* :64-71, K = {-3,-3} */
+	u[0] = 0.0;
+	u[0] = u[0] + (-3.0) * x[0];
+	u[0] = u[0] + (-3.0) * x[1];
+	Du[0] = -3.0;
+	Du[1] = -3.0;
+}
+
+static void ip_dynamics_gradients(const double *x, double *Df, double *Dg)
+{
+	/* :73-80 */
+	Df[0] = 0.;        Df[2] = 1.;
+	Df[1] = cos(x[0]); Df[3] = 0.;
+	for (int i = 0; i < 4; i++) Dg[i] = 0.0;
+}
+
+static const oracle_model k_ip_implicit = {
+	2, 1, 4, 1, {-1.5, 0.0}, {1.5, 0.0}, ip_safety, ip_backup_set, ip_dynamics, ip_dynamics_gradients, 0,
+	ip_backup_controller};
+
 const oracle_model *oracle_get_model(int cfg, int variant)
 {
 	switch (cfg) {
 	case ORACLE_CFG_DI_EXPLICIT: return &k_di_explicit;
 	case ORACLE_CFG_DI_IMPLICIT_TB: return variant ? &k_di_tb_split : &k_di_tb;
 	case ORACLE_CFG_SEGWAY_TB: return variant ? &k_segway_shipped : &k_segway_centred;
+	case ORACLE_CFG_IP_IMPLICIT: return &k_ip_implicit;
 	default: return 0;
 	}
 }

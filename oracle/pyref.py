@@ -36,6 +36,7 @@ class RefLib:
         L.ref_destroy.argtypes = [C.c_void_p]
         L.ref_dims.argtypes = [C.c_void_p, _ip]
         L.ref_filter_batch.argtypes = [C.c_void_p, C.c_int64, _dp, _dp, _dp, _dp, _ip, _dp]
+        L.ref_filter_batch_ex.argtypes = [C.c_void_p, C.c_int64, _dp, _dp, _dp, _dp, _ip, _dp, _ip, _ip]
         L.ref_rollout.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_double, _dp, _dp, _dp, _ip, C.POINTER(C.c_int64)]
 
     def set_qp_mode(self, eps=1e-8, polish=1, warm_start=0, max_iter=20000, polish_refine_iter=10):
@@ -74,6 +75,22 @@ class RefFilter:
         r = self.lib.lib.ref_filter_batch(self.h, n, _d(x), _d(u_des), _d(u), _d(relax), rc.ctypes.data_as(_ip), _d(diag))
         assert r == 0
         return (u, relax, rc, diag) if want_diag else (u, relax, rc)
+
+    def filter_batch_ex(self, x, u_des):
+        """(u, relax, rc, diag, raw OSQP status, ADMM iterations) - single-threaded use only."""
+        x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1, self.nx)
+        u_des = np.ascontiguousarray(u_des, dtype=np.float64).reshape(-1, self.nu)
+        n = x.shape[0]
+        u = np.zeros((n, self.nu))
+        relax = np.zeros((n, self.n_relax))
+        rc = np.zeros(n, dtype=np.int32)
+        diag = np.zeros((n, self.n_diag))
+        st = np.zeros(n, dtype=np.int32)
+        it = np.zeros(n, dtype=np.int32)
+        r = self.lib.lib.ref_filter_batch_ex(self.h, n, _d(x), _d(u_des), _d(u), _d(relax), rc.ctypes.data_as(_ip), _d(diag),
+                                             st.ctypes.data_as(_ip), it.ctypes.data_as(_ip))
+        assert r == 0
+        return u, relax, rc, diag, st, it
 
     def rollout(self, x0, u_des, steps, dt):
         x = np.array(x0, dtype=np.float64).reshape(-1, self.nx).copy()

@@ -112,6 +112,8 @@ void osqp_shim_configure(double eps_abs_rel, int polish, int warm_start, int max
  * second clause); observed |du| up to 2e-5 on the DoubleIntegrator TB config.  The oracle setting
  * therefore raises it (10) so that "OSQP with polish" means the converged KKT point. */
 void osqp_shim_configure_refine(int polish_refine_iter);
+/* raw status_val (and iteration count) of the most recent osqp_solve in this process */
+int osqp_shim_last_status(int *iters);
 /* cumulative ADMM iterations / solves since process start (for reporting K-bar) */
 void osqp_shim_stats(long long *n_solves, long long *n_iters, long long *n_polish_ok);
 

@@ -42,6 +42,7 @@ const double MIN_SCALING = 1e-4, MAX_SCALING = 1e4;
 double g_cfg_eps = -1.0;
 int g_cfg_polish = -1, g_cfg_warm = -1, g_cfg_max_iter = -1, g_cfg_refine = -1;
 long long g_n_solves = 0, g_n_iters = 0, g_n_polish_ok = 0;
+int g_last_status = 0, g_last_iter = 0;
 
 typedef std::vector<double> vec;
 
@@ -576,6 +577,8 @@ struct Solver {
 			if (ok) g_n_polish_ok++;
 		}
 		w->info->status_val = status;
+		g_last_status = status;
+		g_last_iter = iter;
 		w->info->pri_res = r.pri;
 		w->info->dua_res = r.dua;
 		w->info->obj_val = r.obj;
@@ -605,6 +608,12 @@ void osqp_shim_configure(double eps_abs_rel, int polish, int warm_start, int max
 	g_cfg_polish = polish;
 	g_cfg_warm = warm_start;
 	g_cfg_max_iter = max_iter;
+}
+
+int osqp_shim_last_status(int *iters)
+{
+	if (iters) *iters = g_last_iter;
+	return g_last_status;
 }
 
 void osqp_shim_stats(long long *n_solves, long long *n_iters, long long *n_polish_ok)

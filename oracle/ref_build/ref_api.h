@@ -40,6 +40,10 @@ int ref_dims(void *h, int32_t *dims);
  * diag (optional, n*n_diag doubles): config-specific diagnostics followed by A_ (nc*nv, col-major) and b_ (nc). */
 int ref_filter_batch(void *h, int64_t n, const double *x, const double *u_des,
                      double *u_act, double *relax, int32_t *rc, double *diag);
+/* same, also returning the raw OSQP status_val / iteration count of each state's QP (single-threaded use only;
+ * for calls that solve no QP the values are those of the previous solve) */
+int ref_filter_batch_ex(void *h, int64_t n, const double *x, const double *u_des, double *u_act, double *relax,
+                        int32_t *rc, double *diag, int32_t *qp_status, int32_t *qp_iters);
 /* closed-loop rollout exactly as the example main loops do (x += dt*(f+g*uAct)); x is updated in place */
 int ref_rollout(void *h, int64_t n, int32_t steps, double dt, double *x, const double *u_des,
                 double *u_act_last, int32_t *rc_last, int64_t *rc_hist /* [8] or NULL */);

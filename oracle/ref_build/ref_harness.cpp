@@ -54,6 +54,23 @@ int ref_filter_batch(void *h, int64_t n, const double *x, const double *u_des,
 	return 0;
 }
 
+int ref_filter_batch_ex(void *h, int64_t n, const double *x, const double *u_des, double *u_act, double *relax,
+                        int32_t *rc, double *diag, int32_t *qp_status, int32_t *qp_iters)
+{
+	RefFilter *f = (RefFilter *)h;
+	if (!f) return -1;
+	for (int64_t k = 0; k < n; k++) {
+		double r[2] = {0.0, 0.0};
+		rc[k] = f->filter(x + k * f->nx, u_des + k * f->nu, u_act + k * f->nu, r, diag ? diag + k * f->n_diag : 0);
+		for (int j = 0; j < f->n_relax; j++) relax[k * f->n_relax + j] = r[j];
+		int it = 0;
+		const int st = osqp_shim_last_status(&it); /* of the (last) QP this filter() call solved */
+		if (qp_status) qp_status[k] = st;
+		if (qp_iters) qp_iters[k] = it;
+	}
+	return 0;
+}
+
 int ref_rollout(void *h, int64_t n, int32_t steps, double dt, double *x, const double *u_des,
                 double *u_act_last, int32_t *rc_last, int64_t *rc_hist)
 {

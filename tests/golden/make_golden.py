@@ -31,10 +31,10 @@ def main():
         jobs.append(extra())
     for name, cfg, opts, (x, ud) in jobs:
         f = L.create(cfg, opts)
-        u, relax, rc, diag = f.filter_batch(x, ud, want_diag=True)
+        u, relax, rc, diag, qp_status, qp_iters = f.filter_batch_ex(x, ud)
         out = os.path.join(HERE, name + ".npz")
         np.savez_compressed(out, cfg=cfg, opts=np.asarray(opts, dtype=np.float64), x=x, u_des=ud, u_act=u, relax=relax,
-                            rc=rc, diag=diag)
+                            rc=rc, diag=diag, qp_status=qp_status, qp_iters=qp_iters)
         print(name, "n =", len(rc), "rc histogram", dict(zip(*np.unique(rc, return_counts=True))),
               "%.0f kB" % (os.path.getsize(out) / 1e3))
     # a closed-loop rollout (segway, 20 agents x 50 control steps) through the reference main-loop arithmetic

@@ -1,0 +1,42 @@
+"""Oracle restatement of ASIFimplicit / ASIFrobust (InvertedPendulum configs 3a, 3b) against golden
+vectors produced by the reference's own sources.  CPU only."""
+import os
+
+import numpy as np
+
+import conftest as cf
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def run(oracle, name):
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    cfg, opts = int(g["cfg"]), list(g["opts"])
+    u, relax, rc, diag = oracle.filter_batch(cfg, g["x"], g["u_des"], opts, want_diag=True)
+    unp = cf.unpinned_mask(g["rc"], rc, relax, g["qp_status"])
+    assert unp.mean() < 0.03, "%s: %d unpinned states" % (name, unp.sum())
+    k = ~unp
+    cf.assert_parity(name, (u[k], relax[k], rc[k]), (g["u_act"][k], g["relax"][k], g["rc"][k]))
+    return g, diag, k, rc
+
+
+def test_c3a_implicit_short_golden(oracle):
+    g, diag, k, rc = run(oracle, "c3a_ip_implicit_short")
+    m = k & (g["rc"] == 1)
+    assert np.array_equal(diag[m], g["diag"][m])  # hSafetyNow, hBackupEnd, critical indices, A_, b_: same bits
+    assert (g["rc"] == -1).sum() > 50 and (g["rc"] == 1).sum() > 50
+
+
+def test_c3a_implicit_example_options_golden(oracle):
+    """npBT = 5001 (the example's own horizon and step)."""
+    g, diag, k, rc = run(oracle, "c3a_ip_implicit")
+    m = k & (g["rc"] == 1)
+    assert np.array_equal(diag[m], g["diag"][m])
+
+
+def test_c3b_robust_golden(oracle):
+    """The reduced 2-variable problem against the reference's 402-variable LP-dual formulation (libaffa intervals)."""
+    g, diag, k, rc = run(oracle, "c3b_ip_robust")
+    # h_k, [Lg-, Lg+], [Lf-, Lf+] read back from the reference's A_ (all states: assembly does not depend on the QP)
+    assert np.abs(diag - g["diag"]).max() <= 1e-12
+    assert (g["rc"] == -1).sum() > 5

@@ -12,15 +12,16 @@ from oracle import pyref
     (pyref.CFG_DI_EXPLICIT, cf.C1_OPTS, cf.c1_inputs, 20000),
     (pyref.CFG_DI_IMPLICIT_TB, cf.C2_TB_OPTS, cf.c2_inputs, 6000),
     (pyref.CFG_SEGWAY_TB, cf.SEGWAY_TB_OPTS, cf.c5_inputs, 600),
+    (pyref.CFG_IP_IMPLICIT, cf.C3A_SHORT_OPTS, cf.c3a_inputs, 1500),
 ])
 def test_oracle_matches_reference(oracle, reflib, cfg, opts, gen, n):
     x, ud = gen(n, seed=cf.SEED + 100 + cfg)
     f = reflib.create(cfg, opts)
-    u0, relax0, rc0, diag0 = f.filter_batch(x, ud, want_diag=True)
+    u0, relax0, rc0, diag0, st0, it0 = f.filter_batch_ex(x, ud)
     u, relax, rc, diag = oracle.filter_batch(cfg, x, ud, opts, want_diag=True)
-    unpinned = np.isin(rc0, (-2, 3, 4)) | ((rc0 == -3) & (rc == 1) & (relax[:, 0] > 50.0))
+    unpinned = cf.unpinned_mask(rc0, rc, relax, st0)
     print("cfg", cfg, "rc", dict(zip(*np.unique(rc0, return_counts=True))), "unpinned", int(unpinned.sum()))
-    assert unpinned.mean() < 0.01
+    assert unpinned.mean() < 0.03
     k = ~unpinned
     cf.assert_parity("cfg%d" % cfg, (u[k], relax[k], rc[k]), (u0[k], relax0[k], rc0[k]))
     m = k & (rc0 == 1)
