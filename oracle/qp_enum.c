@@ -225,8 +225,13 @@ int oracle_qp_solve(int nv, int nc, int diagonal_cost, const double *H, const do
 		for (int j = 0; j < nv; j++) s += G[(size_t)i * nv + j] * G[(size_t)i * nv + j];
 		rown[i] = sqrt(s);
 		if (rown[i] > 0.0) {
-			cand[ncand++] = i;
-			if (eq[i]) neq++;
+			/* a right-hand side of magnitude >= 1e19 (options_.inf = 1e20: trivial rows, the open upper bound
+			 * of a relax variable) is a real number for feasibility but is never an active constraint: at
+			 * that scale the multiplier test is pure round-off */
+			if (fabs(r[i]) < 1e19 * rown[i]) {
+				cand[ncand++] = i;
+				if (eq[i]) neq++;
+			}
 		} else {
 			rown[i] = 1.0;
 			if (eq[i] ? (r[i] != 0.0) : (r[i] > 0.0)) infeasible = 1;
