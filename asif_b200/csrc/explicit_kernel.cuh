@@ -19,8 +19,8 @@ struct RegRows {
 	int stride;
 	double lb[NV], ub[NV];
 	__device__ __forceinline__ int count() const { return NC + 2 * NV; }
-	template <class F>
-	__device__ __forceinline__ void scan(F &&fn) const
+	template <class F, class FB>
+	__device__ __forceinline__ void scan(F &&fn, FB &&) const
 	{
 		const int m = count();
 		for (int j = 0; j < m; j++) {

@@ -97,8 +97,8 @@ struct ImpRows {
 			}
 		}
 	}
-	template <class F>
-	__device__ __forceinline__ void scan(F &&fn) const
+	template <class F, class FB>
+	__device__ __forceinline__ void scan(F &&fn, FB &&fb) const
 	{
 #pragma unroll 1
 		for (int s = 0; s < NPBTSS; s++) {
@@ -117,11 +117,7 @@ struct ImpRows {
 			fn(NSAFE + r, n, rhs);
 		}
 #pragma unroll
-		for (int k = 0; k < 2 * NV; k++) {
-			double n[NV], rhs;
-			bound_row(k, n, rhs);
-			fn(NC + k, n, rhs);
-		}
+		for (int k = 0; k < 2 * NV; k++) fb(NC + k, k >> 1, (k & 1) != 0, (k & 1) ? -ub[k >> 1] : lb[k >> 1]);
 	}
 	__device__ __forceinline__ void get(const int j, double (&n)[NV], double &rhs) const
 	{
@@ -316,13 +312,13 @@ implicit_filter_kernel(const ImplicitParams p, const int64_t n, const double *__
 #pragma unroll
 			for (int s = 0; s < NPBTSS; s++) d[2 + s] = (double)kidx[s];
 			double *A = d + 2 + NPBTSS, *b = A + NC * NV;
-			R.scan([&](const int j, const double(&nn)[NV], const double rhs) {
-				if (j < NC) {
+			R.scan(
+			    [&](const int j, const double(&nn)[NV], const double rhs) {
 #pragma unroll
-					for (int i = 0; i < NV; i++) A[j + i * NC] = nn[i];
-					b[j] = rhs;
-				}
-			});
+				    for (int i = 0; i < NV; i++) A[j + i * NC] = nn[i];
+				    b[j] = rhs;
+			    },
+			    [](const int, const int, const bool, const double) {});
 		}
 	}
 	if (qp_iter_sum) {

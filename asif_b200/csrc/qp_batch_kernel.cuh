@@ -22,8 +22,8 @@ struct BatchRows {
 	bool has_eq;
 	// rows: [0,nc) A rows; [nc, nc+2NV) bounds; [nc+2NV, 2nc+2NV) negated equality rows
 	__device__ __forceinline__ int count() const { return has_eq ? 2 * nc + 2 * NV : nc + 2 * NV; }
-	template <class F>
-	__device__ __forceinline__ void scan(F &&fn) const
+	template <class F, class FB>
+	__device__ __forceinline__ void scan(F &&fn, FB &&) const
 	{
 		const int m = count();
 		for (int j = 0; j < m; j++) {

@@ -9,8 +9,8 @@
 //
 // Everything is per thread and in registers: NV is a template constant, all loops over NV are
 // unrolled, the active set holds at most NV rows.  Rows are presented by a functor with two
-// members -- scan(f): call f(j, normal, rhs) for every row j in order; get(j, normal, rhs): one
-// row -- so that the caller decides where they live (shared memory for the implicit filters, computed on the fly
+// members -- scan(f, fb): call f(j, normal, rhs) for every general row j in order and
+// fb(j, var, upper, bound) for every variable-bound row; get(j, normal, rhs): one row -- so that the caller decides where they live (shared memory for the implicit filters, computed on the fly
 // from a table for the robust/realizable ones, global memory for the generic batch entry).
 // Work is done in the metric of the Hessian (v-hat = sqrt(2H) v) with every processed row
 // normalised to unit length, so the thresholds below are scale free.
@@ -203,27 +203,47 @@ __device__ __forceinline__ int qp_gi_solve(const Metric &mt, const double (&c)[N
 		// ---- most violated row that is not active (rows.scan visits every row once, in order)
 		int p = -1;
 		double sp = 0.0;
-		double np_[NV], rhs_p = 0.0;
+		double np_[NV];
 #pragma unroll
 		for (int i = 0; i < NV; i++) np_[i] = 0.0;
-		rows.scan([&](const int j, const double(&n)[NV], const double rhs) {
-			double s = -rhs, nmax = 1.0;
+		rows.scan(
+		    [&](const int j, const double(&n)[NV], const double rhs) {
+			    double s = -rhs;
 #pragma unroll
-			for (int i = 0; i < NV; i++) {
-				s += n[i] * w.v[i];
-				nmax = fmax(nmax, fabs(n[i]));
-			}
-			bool is_act = false;
+			    for (int i = 0; i < NV; i++) s += n[i] * w.v[i];
+			    if (s < -QP_FEAS_TOL && s < sp) { // rarely true: the expensive part of the test only runs then
+				    double nmax = 1.0;
 #pragma unroll
-			for (int a = 0; a < NV; a++) is_act |= (a < w.q) && (w.act[a] == j);
-			if (!is_act && s < -QP_FEAS_TOL * nmax && s < sp) {
-				sp = s;
-				p = j;
-				rhs_p = rhs;
+				    for (int i = 0; i < NV; i++) nmax = fmax(nmax, fabs(n[i]));
+				    bool is_act = false;
 #pragma unroll
-				for (int i = 0; i < NV; i++) np_[i] = n[i];
-			}
-		});
+				    for (int a = 0; a < NV; a++) is_act |= (a < w.q) && (w.act[a] == j);
+				    if (!is_act && s < -QP_FEAS_TOL * nmax) {
+					    sp = s;
+					    p = j;
+#pragma unroll
+					    for (int i = 0; i < NV; i++) np_[i] = n[i];
+				    }
+			    }
+		    },
+		    // variable bound: +v[var] >= bnd (lower) or -v[var] >= bnd (upper); same value as the generic row
+		    [&](const int j, const int var, const bool upper, const double bnd) {
+			    double vv = 0.0;
+#pragma unroll
+			    for (int i = 0; i < NV; i++) vv = (i == var) ? w.v[i] : vv;
+			    const double s = (upper ? -vv : vv) - bnd;
+			    if (s < -QP_FEAS_TOL && s < sp) {
+				    bool is_act = false;
+#pragma unroll
+				    for (int a = 0; a < NV; a++) is_act |= (a < w.q) && (w.act[a] == j);
+				    if (!is_act) {
+					    sp = s;
+					    p = j;
+#pragma unroll
+					    for (int i = 0; i < NV; i++) np_[i] = (i == var) ? (upper ? -1.0 : 1.0) : 0.0;
+				    }
+			    }
+		    });
 		if (p < 0) {
 			status = QP_OK;
 			break;

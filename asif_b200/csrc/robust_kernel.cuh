@@ -60,8 +60,8 @@ struct RobustRows {
 		}
 		rhs = bnd;
 	}
-	template <class F>
-	__device__ __forceinline__ void scan(F &&fn) const
+	template <class F, class FB>
+	__device__ __forceinline__ void scan(F &&fn, FB &&fb) const
 	{
 		for (int k = 0; k < K; k++) {
 			double h, lo, hi, lf;
@@ -72,11 +72,7 @@ struct RobustRows {
 			fn(2 * k + 1, n, -lf);
 		}
 #pragma unroll
-		for (int k = 0; k < 2 * NV; k++) {
-			double n[NV], rhs;
-			bound_row(k, n, rhs);
-			fn(2 * K + k, n, rhs);
-		}
+		for (int k = 0; k < 2 * NV; k++) fb(2 * K + k, k >> 1, (k & 1) != 0, (k & 1) ? -ub[k >> 1] : lb[k >> 1]);
 	}
 	__device__ __forceinline__ void get(const int j, double (&n)[NV], double &rhs) const
 	{
