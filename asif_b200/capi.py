@@ -8,6 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 FILTER_EXPLICIT, FILTER_IMPLICIT_TB, FILTER_IMPLICIT, FILTER_ROBUST, FILTER_REALIZABLE = 1, 2, 3, 4, 5
 MODEL_DOUBLE_INTEGRATOR, MODEL_DOUBLE_INTEGRATOR_TB, MODEL_INVERTED_PENDULUM, MODEL_INVERTED_PENDULUM_TABLE = 1, 2, 3, 4
+MODEL_INVERTED_PENDULUM_KERNEL = 5
 MODEL_SEGWAY, MODEL_SEGWAY_SHIPPED = 6, 7
 MEM_HOST, MEM_DEVICE = 0, 1
 QP_SHARED_H, QP_SHARED_BOUNDS = 1, 2
@@ -34,7 +35,7 @@ class EngineConfig(C.Structure):
         ("uncertaintyBounds", C.c_double * 4), ("dynParam", C.c_double * 4),
         ("halfplanes", _dp), ("n_halfplanes", C.c_int32),
         ("kernel_vertices", _dp), ("n_vertices", C.c_int32),
-        ("facet_normals", _dp), ("facet_vertices", _ip), ("facet_active", _ip),
+        ("facet_normals", _dp), ("facet_vertices", _ip), ("facet_active", _ip), ("facet_lie", _dp),
         ("n_facets", C.c_int32), ("max_critical_facets", C.c_int32), ("max_active_constraints", C.c_int32),
     ]
 
@@ -118,6 +119,20 @@ class Engine:
             if k in ("lb", "ub", "dynParam", "uncertaintyBounds"):
                 for i, vi in enumerate(np.atleast_1d(v)):
                     getattr(cfg, k)[i] = float(vi)
+            elif k == "kernel":
+                # polytope kernel of ASIFrealizable: dict with vertices, normals, facet_vertices, facet_active, facet_lie
+                kv = np.ascontiguousarray(v["vertices"], dtype=np.float64)
+                kn = np.ascontiguousarray(v["normals"], dtype=np.float64)
+                kfv = np.ascontiguousarray(v["facet_vertices"], dtype=np.int32)
+                kfa = np.ascontiguousarray(v["facet_active"], dtype=np.int32)
+                kl = np.ascontiguousarray(v["facet_lie"], dtype=np.float64)
+                self._keep += [kv, kn, kfv, kfa, kl]
+                cfg.kernel_vertices, cfg.n_vertices = kv.ctypes.data_as(_dp), kv.shape[0]
+                cfg.facet_normals, cfg.n_facets = kn.ctypes.data_as(_dp), kn.shape[0]
+                cfg.facet_vertices, cfg.facet_active = kfv.ctypes.data_as(_ip), kfa.ctypes.data_as(_ip)
+                cfg.facet_lie = kl.ctypes.data_as(_dp)
+                cfg.max_critical_facets = int(v["max_critical_facets"])
+                cfg.max_active_constraints = int(kfa.shape[1])
             elif k == "halfplanes":
                 t = np.ascontiguousarray(v, dtype=np.float64).reshape(-1, 2)
                 self._keep.append(t)

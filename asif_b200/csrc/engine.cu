@@ -8,6 +8,7 @@
 #include "filter_common.cuh"
 #include "implicit_kernel.cuh"
 #include "robust_kernel.cuh"
+#include "realizable_kernel.cuh"
 #include "models.cuh"
 #include "qp_batch_kernel.cuh"
 #include "tb_kernel.cuh"
@@ -60,6 +61,9 @@ struct asif_engine {
 	ExplicitParams ex;
 	ImplicitParams im;
 	RobustParams rb;
+	RealizableParams rz;
+	void *d_kernel = nullptr; // polytope kernel tables (realizable filter), one allocation
+	size_t rz_smem = 0;
 	double *d_table = nullptr; // half-plane table (robust filter)
 	Slot slot[N_SLOTS];
 	cudaStream_t stream = nullptr; // device-memory calls without a caller stream
@@ -194,6 +198,18 @@ int launch_robust(asif_engine *e, int64_t n, const double *x, const double *ud, 
 	return ASIF_OK;
 }
 
+int launch_realizable(asif_engine *e, int64_t n, const double *x, const double *ud, double *ua, double *relax, int32_t *rc,
+                      double *diag, cudaStream_t st)
+{
+	const unsigned blocks = (unsigned)((n + RZ_THREADS - 1) / RZ_THREADS);
+	if (diag)
+		realizable_ip_filter_kernel<true><<<blocks, RZ_THREADS, e->rz_smem, st>>>(e->rz, n, x, ud, ua, relax, rc, diag, e->d_counters);
+	else
+		realizable_ip_filter_kernel<false><<<blocks, RZ_THREADS, e->rz_smem, st>>>(e->rz, n, x, ud, ua, relax, rc, nullptr, e->d_counters);
+	CUDA_TRY(cudaGetLastError());
+	return ASIF_OK;
+}
+
 int launch_filter(asif_engine *e, int64_t n, const double *x, const double *ud, double *ua, double *relax, int32_t *rc,
                   double *diag, cudaStream_t st)
 {
@@ -214,6 +230,9 @@ int launch_filter(asif_engine *e, int64_t n, const double *x, const double *ud, 
 		break;
 	case ASIF_FILTER_ROBUST:
 		if (e->cfg.model == ASIF_MODEL_INVERTED_PENDULUM_TABLE) return launch_robust(e, n, x, ud, ua, relax, rc, diag, st);
+		break;
+	case ASIF_FILTER_REALIZABLE:
+		if (e->cfg.model == ASIF_MODEL_INVERTED_PENDULUM_KERNEL) return launch_realizable(e, n, x, ud, ua, relax, rc, diag, st);
 		break;
 	}
 	return fail(ASIF_ERR_UNSUPPORTED, "no kernel for filter %d / model %d", e->cfg.filter, e->cfg.model);
@@ -313,7 +332,8 @@ int32_t asif_engine_config_init(asif_engine_config *cfg, int32_t filter, int32_t
 		cfg->relaxLb = 5.0;
 		break;
 	case ASIF_FILTER_REALIZABLE: /* include/asif_realizable.h:14-20 */
-		cfg->relaxDes = 1.0;
+		cfg->relaxDes = 5.0;
+		cfg->relaxOffset = 5.0;
 		break;
 	default:
 		return fail(ASIF_ERR_INVALID_ARGUMENT, "unknown filter %d", filter);
@@ -322,6 +342,12 @@ int32_t asif_engine_config_init(asif_engine_config *cfg, int32_t filter, int32_t
 	case ASIF_MODEL_DOUBLE_INTEGRATOR:
 	case ASIF_MODEL_DOUBLE_INTEGRATOR_TB:
 		cfg->lb[0] = -1.0; cfg->ub[0] = 1.0; /* examples/DoubleIntegrator*.cpp: lb/ub */
+		break;
+	case ASIF_MODEL_INVERTED_PENDULUM_KERNEL:
+		cfg->lb[0] = -1.5; cfg->ub[0] = 1.5; /* examples/InvertedPendulum_RealizableSampled.cpp:19-20 */
+		cfg->dynParam[0] = 0.9; cfg->dynParam[1] = 1.1; /* :27-28 */
+		cfg->uncertaintyBounds[0] = 0.032; cfg->uncertaintyBounds[1] = 0.027; /* :23 */
+		cfg->npSSmax = 0; /* the default of the example's constructor call (:239) */
 		break;
 	case ASIF_MODEL_INVERTED_PENDULUM:
 	case ASIF_MODEL_INVERTED_PENDULUM_TABLE:
@@ -531,6 +557,94 @@ int32_t asif_engine_create(const asif_engine_config *cfg, asif_engine **out)
 		e->cfg.halfplanes = nullptr; // borrowed pointer is not kept
 		break;
 	}
+	case ASIF_FILTER_REALIZABLE: {
+		if (cfg->model != ASIF_MODEL_INVERTED_PENDULUM_KERNEL) {
+			delete e;
+			return fail(ASIF_ERR_UNSUPPORTED, "realizable filter: model %d not compiled in", cfg->model);
+		}
+		const int nV = cfg->n_vertices, nF = cfg->n_facets, mC = cfg->max_critical_facets, mA = cfg->max_active_constraints;
+		const int nb = cfg->npSSmax < 0 ? 0 : (cfg->npSSmax > nF ? nF : cfg->npSSmax); // src/asif_realizable.cpp:20
+		if (!cfg->kernel_vertices || !cfg->facet_normals || !cfg->facet_vertices || !cfg->facet_active || !cfg->facet_lie ||
+		    nV < 2 || nF < 1 || nV > 4096 || nF > 4096) {
+			delete e;
+			return fail(ASIF_ERR_INVALID_ARGUMENT, "realizable filter needs the polytope kernel tables (vertices, normals, "
+			                                       "facet_vertices, facet_active, facet_lie)");
+		}
+		if (mC < 1 || mC > RZ_MAX_CRIT || mA < 1 || mA > RZ_MAX_ACT || nb > RZ_MAX_BAR) {
+			delete e;
+			return fail(ASIF_ERR_UNSUPPORTED, "realizable filter: maxCriticalFacets <= %d, maxActiveConstraints <= %d, npSSmax <= %d",
+			            RZ_MAX_CRIT, RZ_MAX_ACT, RZ_MAX_BAR);
+		}
+		for (int i = 0; i < 2 * nF; i++)
+			if (cfg->facet_vertices[i] < 0 || cfg->facet_vertices[i] >= nV) {
+				delete e;
+				return fail(ASIF_ERR_INVALID_ARGUMENT, "facet_vertices[%d] out of range", i);
+			}
+		for (int i = 0; i < mA * nF; i++)
+			if (cfg->facet_active[i] >= nF) {
+				delete e;
+				return fail(ASIF_ERR_INVALID_ARGUMENT, "facet_active[%d] out of range", i);
+			}
+		e->n_relax = 2;
+		e->nv = 2;
+		e->nc = 2 * mC * mA + nb;
+		e->n_diag = 1 + mC + nb + 4 * mC * mA + 2 * nb;
+		RealizableParams &p = e->rz;
+		memset(&p, 0, sizeof(p));
+		p.lb = cfg->lb[0];
+		p.ub = cfg->ub[0];
+		p.relaxDes = cfg->relaxDes;
+		p.relaxOffset = cfg->relaxOffset;
+		p.relaxCost = cfg->relaxCost;
+		p.inf = cfg->inf;
+		p.unc[0] = cfg->uncertaintyBounds[0];
+		p.unc[1] = cfg->uncertaintyBounds[1];
+		{ // mid of AAF(interval(pMin, pMax)).convert()  (aa_aafcommon.cpp:81-101, 217-227)
+			const double gc = (cfg->dynParam[1] + cfg->dynParam[0]) / 2, gr = (cfg->dynParam[1] - cfg->dynParam[0]) / 2;
+			p.gmid = ((gc - gr) + (gc + gr)) / 2;
+		}
+		p.gi[0] = 0.5;
+		p.gih[0] = sqrt(0.5);
+		p.gi[1] = 1.0 / (2.0 * (nb > 0 ? cfg->relaxCost : 1.0)); // H(eps) = relaxCost only when npSSmax > 0 (:188-189)
+		p.gih[1] = sqrt(p.gi[1]);
+		p.n_vertices = nV;
+		p.n_facets = nF;
+		p.max_crit = mC;
+		p.max_act = mA;
+		p.npSSmax = nb;
+		const size_t bV = sizeof(double) * 2 * nV, bN = sizeof(double) * 2 * nF, bL = sizeof(double) * 4 * nF * mA;
+		const size_t bFV = sizeof(int32_t) * 2 * nF, bFA = sizeof(int32_t) * nF * mA;
+		e->rz_smem = bV + bN + bL + bFV + bFA;
+		if (e->rz_smem > 96 * 1024) {
+			delete e;
+			return fail(ASIF_ERR_UNSUPPORTED, "polytope kernel too large for the shared-memory staging (%zu B)", e->rz_smem);
+		}
+		cudaError_t te = cudaMalloc(&e->d_kernel, e->rz_smem);
+		char *base = (char *)e->d_kernel;
+		if (te == cudaSuccess) te = cudaMemcpy(base, cfg->kernel_vertices, bV, cudaMemcpyHostToDevice);
+		if (te == cudaSuccess) te = cudaMemcpy(base + bV, cfg->facet_normals, bN, cudaMemcpyHostToDevice);
+		if (te == cudaSuccess) te = cudaMemcpy(base + bV + bN, cfg->facet_lie, bL, cudaMemcpyHostToDevice);
+		if (te == cudaSuccess) te = cudaMemcpy(base + bV + bN + bL, cfg->facet_vertices, bFV, cudaMemcpyHostToDevice);
+		if (te == cudaSuccess) te = cudaMemcpy(base + bV + bN + bL + bFV, cfg->facet_active, bFA, cudaMemcpyHostToDevice);
+		if (te == cudaSuccess && e->rz_smem > 48 * 1024) {
+			te = cudaFuncSetAttribute(realizable_ip_filter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->rz_smem);
+			if (te == cudaSuccess)
+				te = cudaFuncSetAttribute(realizable_ip_filter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->rz_smem);
+		}
+		if (te != cudaSuccess) {
+			cudaFree(e->d_kernel);
+			delete e;
+			return fail(ASIF_ERR_CUDA, "kernel-table upload failed: %s", cudaGetErrorString(te));
+		}
+		p.vertices = (const double *)base;
+		p.normals = (const double *)(base + bV);
+		p.facet_lie = (const double *)(base + bV + bN);
+		p.facet_vertices = (const int32_t *)(base + bV + bN + bL);
+		p.facet_active = (const int32_t *)(base + bV + bN + bL + bFV);
+		e->cfg.kernel_vertices = e->cfg.facet_normals = e->cfg.facet_lie = nullptr; // borrowed pointers are not kept
+		e->cfg.facet_vertices = e->cfg.facet_active = nullptr;
+		break;
+	}
 	default:
 		delete e;
 		return fail(ASIF_ERR_UNSUPPORTED, "filter %d not implemented yet", cfg->filter);
@@ -563,6 +677,7 @@ int32_t asif_engine_destroy(asif_engine *e)
 	}
 	cudaFree(e->d_counters);
 	cudaFree(e->d_table);
+	cudaFree(e->d_kernel);
 	delete e;
 	return ASIF_OK;
 }

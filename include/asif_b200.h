@@ -46,6 +46,7 @@ extern "C" {
 #define ASIF_MODEL_DOUBLE_INTEGRATOR_TB 2 /* examples/DoubleIntegrator_implicit_tb.cpp:13-85  */
 #define ASIF_MODEL_INVERTED_PENDULUM 3    /* examples/InvertedPendulum_Implicit.cpp:13-80     */
 #define ASIF_MODEL_INVERTED_PENDULUM_TABLE 4 /* examples/InvertedPendulum_Robust.cpp:53-79 + half-plane table */
+#define ASIF_MODEL_INVERTED_PENDULUM_KERNEL 5 /* examples/InvertedPendulum_RealizableSampled.cpp:46-62 + polytope kernel table */
 #define ASIF_MODEL_SEGWAY 6               /* examples/segway_implicit_tb.cpp:13-212, backup set centred on the controller equilibrium */
 #define ASIF_MODEL_SEGWAY_SHIPPED 7       /* same, backup set exactly as shipped (:41-55)     */
 
@@ -89,7 +90,12 @@ typedef struct asif_engine_config {
 	int32_t n_vertices;
 	const double *facet_normals;   /* [nFacets][nx] */
 	const int32_t *facet_vertices; /* [nFacets][nx] vertex ids */
-	const int32_t *facet_active;   /* [nFacets][maxActiveConstraints] facet ids */
+	const int32_t *facet_active;   /* [nFacets][maxActiveConstraints] facet ids, -1 = absent */
+	/* [nFacets][maxActiveConstraints][4] = LfLo, LfHi, LgLo, LgHi: the interval Lie derivatives of the active
+	 * constraint over the facet, which src/asif_realizable.cpp:470-500 recomputes on every call although they do
+	 * not depend on x.  The caller evaluates its interval dynamics callback once per facet at initialize
+	 * (INTEGRATION.md shows the loop) and hands the numbers over. */
+	const double *facet_lie;
 	int32_t n_facets, max_critical_facets, max_active_constraints;
 } asif_engine_config;
 

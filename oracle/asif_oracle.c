@@ -644,6 +644,9 @@ static int32_t robust_ip_filter(double relaxLb, double relaxCost, double pMin, d
 	return -1; /* uAct untouched, src/asif_robust.cpp:249-251 */
 }
 
+int32_t oracle_realizable_filter(const double *opts, const double *x, const double *uDes, double *uAct, double *relax,
+                                 double *diag); /* realizable_oracle.c */
+
 /* ------------------------------------------------------------------------------------------ */
 typedef struct {
 	int cfg;
@@ -652,6 +655,7 @@ typedef struct {
 	int N;
 	double relaxLb, relaxCost, pMin, pMax;
 	imp_options imp;
+	double rz[8];
 	int nx, nu, n_relax, nc, nv, n_diag;
 } ctx_t;
 
@@ -720,6 +724,22 @@ static int make_ctx(int cfg, const double *opts, int n_opts, ctx_t *c)
 		c->nv = 2;
 		c->n_diag = 5 * ORACLE_N_HALFPLANES;
 		break;
+	case ORACLE_CFG_IP_REALIZABLE: {
+		c->md = oracle_get_model(ORACLE_CFG_IP_IMPLICIT, 0); /* dims only */
+		/* [relaxDes, relaxOffset, relaxCost, unc0, unc1, npSSmax, pMin, pMax]: Options of
+		 * examples/InvertedPendulum_RealizableSampled.cpp:232-233 (relaxOffset keeps its default 5, include/asif_realizable.h:16-19) */
+		const double d[8] = {1.0, 5.0, 50.0, 0.032, 0.027, 2.0, 0.9, 1.1};
+		memcpy(c->rz, d, sizeof(d));
+		if (opts && n_opts >= 6)
+			for (int i = 0; i < 6; i++) c->rz[i] = opts[i];
+		if (c->rz[5] < 0 || c->rz[5] > 8) return -1;
+		const int npSS = ORACLE_RZ_MAXCRIT * ORACLE_RZ_MAXACT, npSSmax = (int)c->rz[5];
+		c->n_relax = 2;
+		c->nc = 2 * npSS + npSSmax;
+		c->nv = 2;
+		c->n_diag = 1 + ORACLE_RZ_MAXCRIT + npSSmax + 4 * npSS + 2 * npSSmax;
+		break;
+	}
 	default:
 		return -1;
 	}
@@ -739,6 +759,8 @@ static int32_t filter_one(const ctx_t *c, const double *x, const double *ud, dou
 		return tb_filter(c->md, &c->tb, c->N, x, ud, ua, relax, diag);
 	case ORACLE_CFG_IP_IMPLICIT:
 		return implicit_filter(c->md, &c->imp, c->N, x, ud, ua, relax, diag);
+	case ORACLE_CFG_IP_REALIZABLE:
+		return oracle_realizable_filter(c->rz, x, ud, ua, relax, diag);
 	case ORACLE_CFG_IP_ROBUST:
 		return robust_ip_filter(c->relaxLb, c->relaxCost, c->pMin, c->pMax, 1e20, x, ud, ua, relax, diag);
 	}

@@ -182,3 +182,21 @@ class OracleLib:
         st = self.lib.oracle_qp_solve(nv, nc, int(diagonal_cost), Hf.ctypes.data_as(_dp), _d(c), Af.ctypes.data_as(_dp),
                                       _d(b), _d(lb), _d(ub), bep, _d(sol))
         return st, sol
+
+
+def realizable_export(ref_filter):
+    """Kernel geometry + the x-independent facet interval table from the reference build (config 4)."""
+    L = ref_filter.lib.lib
+    L.ref_realizable_export.argtypes = [C.c_void_p, _ip, _dp, _dp, _ip, _ip, _dp]
+    dims = np.zeros(4, dtype=np.int32)
+    assert L.ref_realizable_export(ref_filter.h, dims.ctypes.data_as(_ip), None, None, None, None, None) == 0
+    nV, nF, maxCrit, maxAct = (int(v) for v in dims)
+    vertices = np.zeros((nV, 2))
+    normals = np.zeros((nF, 2))
+    fv = np.zeros((nF, 2), dtype=np.int32)
+    fa = np.zeros((nF, maxAct), dtype=np.int32)
+    lie = np.zeros((nF, maxAct, 4))
+    assert L.ref_realizable_export(ref_filter.h, dims.ctypes.data_as(_ip), _d(vertices), _d(normals), fv.ctypes.data_as(_ip),
+                                   fa.ctypes.data_as(_ip), _d(lie)) == 0
+    return dict(vertices=vertices, normals=normals, facet_vertices=fv, facet_active=fa, facet_lie=lie,
+                max_critical_facets=maxCrit, max_active_constraints=maxAct)

@@ -114,6 +114,8 @@ void osqp_shim_configure(double eps_abs_rel, int polish, int warm_start, int max
 void osqp_shim_configure_refine(int polish_refine_iter);
 /* raw status_val (and iteration count) of the most recent osqp_solve in this process */
 int osqp_shim_last_status(int *iters);
+/* number of solves so far that ended at the iteration limit or with an 'inaccurate' verdict (-2, 2, 3, 4) */
+long long osqp_shim_inexact_count(void);
 /* cumulative ADMM iterations / solves since process start (for reporting K-bar) */
 void osqp_shim_stats(long long *n_solves, long long *n_iters, long long *n_polish_ok);
 

@@ -43,6 +43,7 @@ double g_cfg_eps = -1.0;
 int g_cfg_polish = -1, g_cfg_warm = -1, g_cfg_max_iter = -1, g_cfg_refine = -1;
 long long g_n_solves = 0, g_n_iters = 0, g_n_polish_ok = 0;
 int g_last_status = 0, g_last_iter = 0;
+long long g_n_inexact = 0; /* solves that ended in -2 / 2 / 3 / 4 (iteration limit or 'inaccurate' verdicts) */
 
 typedef std::vector<double> vec;
 
@@ -495,6 +496,15 @@ struct Solver {
 	int solve(OSQPWorkspace *w)
 	{
 		g_n_solves++;
+		if (getenv("OSQP_SHIM_TRACE") && n == 2 && atoi(getenv("OSQP_SHIM_TRACE")) > 1) {
+			fprintf(stderr, "  data: q0 %g %g rho %g\n", q0[0], q0[1], rho);
+			for (int i = 0; i < m; i++) {
+				double a0 = 0, a1 = 0;
+				for (c_int k = Ap[0]; k < Ap[1]; k++) if (Ai[k] == i) a0 = Ax[k];
+				for (c_int k = Ap[1]; k < Ap[2]; k++) if (Ai[k] == i) a1 = Ax[k];
+				fprintf(stderr, "  row %d: %.17g <= %.17g l0 + %.17g l1 <= %.17g\n", i, l0[i], a0, a1, u0[i]);
+			}
+		}
 		if (!factor_ok) {
 			w->info->status_val = OSQP_NON_CVX;
 			return 1;
@@ -578,7 +588,11 @@ struct Solver {
 		}
 		w->info->status_val = status;
 		g_last_status = status;
+		if (status == OSQP_MAX_ITER_REACHED || status == OSQP_SOLVED_INACCURATE || status == OSQP_PRIMAL_INFEASIBLE_INACCURATE ||
+		    status == OSQP_DUAL_INFEASIBLE_INACCURATE)
+			g_n_inexact++;
 		g_last_iter = iter;
+		if (getenv("OSQP_SHIM_TRACE")) fprintf(stderr, "osqp_solve n=%d m=%d status=%d iter=%d pri=%g dua=%g\n", n, m, status, iter, r.pri, r.dua);
 		w->info->pri_res = r.pri;
 		w->info->dua_res = r.dua;
 		w->info->obj_val = r.obj;
@@ -609,6 +623,8 @@ void osqp_shim_configure(double eps_abs_rel, int polish, int warm_start, int max
 	g_cfg_warm = warm_start;
 	g_cfg_max_iter = max_iter;
 }
+
+long long osqp_shim_inexact_count(void) { return g_n_inexact; }
 
 int osqp_shim_last_status(int *iters)
 {

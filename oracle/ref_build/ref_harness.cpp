@@ -61,10 +61,13 @@ int ref_filter_batch_ex(void *h, int64_t n, const double *x, const double *u_des
 	if (!f) return -1;
 	for (int64_t k = 0; k < n; k++) {
 		double r[2] = {0.0, 0.0};
+		const long long inexact0 = osqp_shim_inexact_count();
 		rc[k] = f->filter(x + k * f->nx, u_des + k * f->nu, u_act + k * f->nu, r, diag ? diag + k * f->n_diag : 0);
 		for (int j = 0; j < f->n_relax; j++) relax[k * f->n_relax + j] = r[j];
 		int it = 0;
-		const int st = osqp_shim_last_status(&it); /* of the (last) QP this filter() call solved */
+		int st = osqp_shim_last_status(&it); /* of the (last) QP this filter() call solved */
+		/* any QP of this call (e.g. a facet-feasibility solve of ASIFrealizable) that ended inexactly taints the state */
+		if (osqp_shim_inexact_count() != inexact0 && st != -2 && st != 2 && st != 3 && st != 4) st = -2;
 		if (qp_status) qp_status[k] = st;
 		if (qp_iters) qp_iters[k] = it;
 	}

@@ -11,6 +11,11 @@
 #include <vector>
 #include <algorithm>
 #include <chrono>
+#include <random>
+#include <functional>
+#include <utility>
+#include <cstring>
+#include <cstdint>
 #include <cmath>
 #include <stdio.h>
 #include <stdlib.h>

@@ -136,3 +136,34 @@ EXTRA_GOLDEN_JOBS = [
     lambda: ("c3a_ip_implicit", 3, C3A_OPTS, c3a_inputs(60, seed=SEED + 33)),
     lambda: ("c3b_ip_robust", 4, C3B_OPTS, c3b_inputs(160)),
 ]
+
+# ---- config 4 (ASIFrealizable, IP dynamics + RealizableKernelData_100Hz_50pt) -----------------------
+# [relaxDes, relaxOffset, relaxCost, unc0, unc1, npSSmax]
+C4_OPTS = [1.0, 5.0, 50.0, 0.032, 0.027, 2.0]
+
+
+def realizable_kernel():
+    return np.load(os.path.join(ROOT, "tests", "golden", "realizable_kernel_100hz_50pt.npz"))
+
+
+def c4_inputs(n, seed=SEED + 6):
+    """Half of the states uniform on [-3,3]^2, half scattered around the kernel boundary so that
+    the critical-facet machinery is exercised (uniform sampling alone makes a facet critical for < 2 % of states)."""
+    g = philox(seed)
+    k = realizable_kernel()
+    V = k["vertices"]
+    na = n // 2
+    xa = g.uniform(-3, 3, (na, 2))
+    idx = g.integers(0, len(V), n - na)
+    t = g.uniform(0, 1, (n - na, 1))
+    xb = V[idx] * t + V[(idx + 1) % len(V)] * (1 - t) + g.normal(0, 0.03, (n - na, 2))
+    return np.ascontiguousarray(np.vstack([xa, xb])), g.uniform(-1.5, 1.5, (n, 1))
+
+
+def realizable_engine_kwargs(opts, kernel=None):
+    k = realizable_kernel() if kernel is None else kernel
+    return dict(relaxDes=opts[0], relaxOffset=opts[1], relaxCost=opts[2], uncertaintyBounds=[opts[3], opts[4]],
+                npSSmax=int(opts[5]), dynParam=[0.9, 1.1], kernel=k)
+
+
+EXTRA_GOLDEN_JOBS.append(lambda: ("c4_ip_realizable", 5, C4_OPTS, c4_inputs(1200)))

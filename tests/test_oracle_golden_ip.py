@@ -40,3 +40,19 @@ def test_c3b_robust_golden(oracle):
     # h_k, [Lg-, Lg+], [Lf-, Lf+] read back from the reference's A_ (all states: assembly does not depend on the QP)
     assert np.abs(diag - g["diag"]).max() <= 1e-12
     assert (g["rc"] == -1).sum() > 5
+
+
+def test_c4_realizable_golden(oracle):
+    """Reduced 2-variable problem + exact segment/box test against the reference's 38-variable LP-dual QP with OSQP
+    facet-feasibility solves.  States where one of the reference's QPs did not converge are excluded (counted)."""
+    g = np.load(os.path.join(GOLD, "c4_ip_realizable.npz"))
+    u, relax, rc, diag = oracle.filter_batch(5, g["x"], g["u_des"], list(g["opts"]), want_diag=True)
+    tainted = np.isin(g["qp_status"], (-2, 2, 3, 4))
+    assert tainted.mean() < 0.03
+    k = ~tainted
+    assert np.array_equal(diag[k][:, :6], g["diag"][k][:, :6])
+    assert np.array_equal(diag[k], g["diag"][k])  # table gathers and barrier rows: same bits
+    r1, r0 = relax.copy(), g["relax"].copy()
+    r1[:, 0] = r0[:, 0] = 0.0
+    cf.assert_parity("C4", (u[k], r1[k], rc[k]), (g["u_act"][k], r0[k], g["rc"][k]))
+    assert (g["rc"] == -2).sum() > 50 and (g["diag"][:, 0] >= 1).sum() > 100
