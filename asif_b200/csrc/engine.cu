@@ -796,13 +796,18 @@ template <int NV>
 int launch_qp(int64_t n, int nc, int diag_cost, const double *H, const double *c, const double *A, const double *b,
               const double *lb, const double *ub, const uint8_t *be, double *sol, int32_t *status, int share, cudaStream_t st)
 {
-	const size_t smem = sizeof(double) * (size_t)(nc * NV + nc) * (QPB_THREADS + 1);
+	int threads = QPB_THREADS;
+	size_t smem = sizeof(double) * (size_t)(nc * NV + nc) * (threads + 1);
+	if (smem > 200 * 1024) { // fewer problems per CTA
+		threads = 32;
+		smem = sizeof(double) * (size_t)(nc * NV + nc) * (threads + 1);
+	}
 	if (smem > 200 * 1024) return fail(ASIF_ERR_UNSUPPORTED, "qp_solve_batch: nc = %d too large for the shared-memory slab", nc);
 	auto k = qp_batch_kernel<NV>;
 	int r = set_smem(k, smem);
 	if (r) return r;
-	const unsigned blocks = (unsigned)((n + QPB_THREADS - 1) / QPB_THREADS);
-	k<<<blocks, QPB_THREADS, smem, st>>>(n, nc, diag_cost, H, c, A, b, lb, ub, be, sol, status, share & ASIF_QP_SHARED_H,
+	const unsigned blocks = (unsigned)((n + threads - 1) / threads);
+	k<<<blocks, threads, smem, st>>>(n, nc, diag_cost, H, c, A, b, lb, ub, be, sol, status, share & ASIF_QP_SHARED_H,
 	                                      share & ASIF_QP_SHARED_BOUNDS);
 	CUDA_TRY(cudaGetLastError());
 	return ASIF_OK;

@@ -74,8 +74,8 @@ qp_batch_kernel(const int64_t n, const int nc, const int diagonal_cost, const do
                 double *__restrict__ sol, int32_t *__restrict__ status, const int shared_H, const int shared_bounds)
 {
 	extern __shared__ double smem[];
-	const int T = QPB_THREADS;
-	const int TS = QPB_THREADS + 1; // padded element stride: conflict-free transposing stores
+	const int T = blockDim.x;  // 64, or 32 when the slab of a 64-problem CTA would not fit in shared memory
+	const int TS = T + 1;      // padded element stride: conflict-free transposing stores
 	const int64_t base = (int64_t)blockIdx.x * T;
 	const int nprob = (int)((n - base) < T ? (n - base) : T);
 	const int ea = nc * NV;
