@@ -5,7 +5,8 @@
 //                                        declared here only when the reference header is absent
 //   * ASIF::QPWrapperB200                a QPWrapperAbstract backend on the B200 kernels, the
 //                                        sibling of QPWrapperOsqp (src/qpwrapper_osqp.cpp)
-//   * ASIF::FilterBatchImplicitTB / FilterBatchExplicit
+//   * ASIF::b200::FilterBatchImplicitTB / FilterBatchImplicit / FilterBatchExplicit / FilterBatchRobust /
+//     FilterBatchRealizable
 //                                        the batched counterparts of ASIFimplicitTB / ASIF with the
 //                                        same Options structs, initialize / updateOptions semantics
 //                                        and return codes, plus filterBatch(n, X, UDes, UAct, Relax, rc)
@@ -147,7 +148,9 @@ namespace ASIF
 			DoubleIntegratorTB = ASIF_MODEL_DOUBLE_INTEGRATOR_TB,
 			InvertedPendulum = ASIF_MODEL_INVERTED_PENDULUM,
 			Segway = ASIF_MODEL_SEGWAY,
-			SegwayShipped = ASIF_MODEL_SEGWAY_SHIPPED
+			SegwayShipped = ASIF_MODEL_SEGWAY_SHIPPED,
+			InvertedPendulumTable = ASIF_MODEL_INVERTED_PENDULUM_TABLE,
+			InvertedPendulumKernel = ASIF_MODEL_INVERTED_PENDULUM_KERNEL
 		};
 
 		inline std::string lastError(void) { return std::string(asif_last_error()); }
@@ -350,6 +353,216 @@ namespace ASIF
 			int32_t device_;
 			Options options_;
 			double lb_, ub_;
+		};
+
+		// Batched ASIF::ASIFimplicit (include/asif_implicit.h): relax is double[2] per state (safe, reach).
+		class FilterBatchImplicit : public FilterBatchBase
+		{
+		public:
+			typedef struct {
+				double relaxCost = 50.0;
+				double relaxReachLb = 5.0;
+				double relaxSafeLb = 5.0;
+				double backTrajHorizon = 1.0;
+				double backTrajDt = 0.01;
+				double backTrajAbsTol = 1.0e-6;
+				double backTrajRelTol = 1.0e-6;
+				double satSharpness = 0.1;
+				double inf = 1e20;
+			} Options; // include/asif_implicit.h:20-34 (x0 / n_debug / use_learning are not on the batched path)
+
+			FilterBatchImplicit(const Model model, const uint32_t npBTSS = 10, const int32_t device = 0)
+			    : model_(model), npBTSS_(npBTSS), device_(device)
+			{
+			}
+			int32_t initialize(const double lb[], const double ub[]) { return initialize(lb, ub, Options()); }
+			int32_t initialize(const double lb[], const double ub[], const Options &options)
+			{
+				options_ = options;
+				lb_ = lb[0];
+				ub_ = ub[0];
+				return build();
+			}
+			// src/asif_implicit.cpp:369-401: same satSharpness clamp and return codes as the TB class
+			int32_t updateOptions(const Options &options)
+			{
+				options_ = options;
+				int32_t code = 1;
+				if (options_.satSharpness > 2) {
+					options_.satSharpness = 2;
+					code = 2;
+				} else if (options_.satSharpness < 0.01) {
+					options_.satSharpness = 0.01;
+					code = 3;
+				}
+				const int32_t r = build();
+				return r == 1 ? code : r;
+			}
+			int32_t filter(const double x[], const double uDes[], double uAct[], double relax[2])
+			{
+				int32_t rc = 0;
+				const int32_t r = filterBatch(1, x, uDes, uAct, relax, &rc);
+				return r == ASIF_OK ? rc : r;
+			}
+
+		protected:
+			int32_t build(void)
+			{
+				asif_engine_config cfg;
+				int32_t r = asif_engine_config_init(&cfg, ASIF_FILTER_IMPLICIT, (int32_t)model_);
+				if (r != ASIF_OK) return r;
+				cfg.device = device_;
+				cfg.npBTSS = (int32_t)npBTSS_;
+				cfg.lb[0] = lb_;
+				cfg.ub[0] = ub_;
+				cfg.relaxCost = options_.relaxCost;
+				cfg.relaxLb = options_.relaxSafeLb;
+				cfg.relaxReachLb = options_.relaxReachLb;
+				cfg.backTrajHorizon = options_.backTrajHorizon;
+				cfg.backTrajDt = options_.backTrajDt;
+				cfg.satSharpness = options_.satSharpness;
+				cfg.inf = options_.inf;
+				return create(cfg);
+			}
+			Model model_;
+			uint32_t npBTSS_;
+			int32_t device_;
+			Options options_;
+			double lb_, ub_;
+		};
+
+		// Batched ASIF::ASIFrobust (include/asif_robust.h) on a table of half-planes h_k = 1 - a_k.x with the
+		// InvertedPendulum interval dynamics g1 in [pMin, pMax] (examples/InvertedPendulum_Robust.cpp:53-69).
+		class FilterBatchRobust : public FilterBatchBase
+		{
+		public:
+			typedef struct {
+				double relaxLb = 5.0;
+				double relaxCost = 50.0;
+				double inf = 1e20;
+			} Options; // include/asif_robust.h:14-19
+
+			// halfplanes: npSS rows {a0, a1}; the table is copied
+			FilterBatchRobust(const uint32_t npSS, const double halfplanes[], const double pMin, const double pMax,
+			                  const int32_t device = 0)
+			    : table_(halfplanes, halfplanes + 2 * npSS), pMin_(pMin), pMax_(pMax), device_(device)
+			{
+			}
+			int32_t initialize(const double lb[], const double ub[]) { return initialize(lb, ub, Options()); }
+			int32_t initialize(const double lb[], const double ub[], const Options &options)
+			{
+				asif_engine_config cfg;
+				int32_t r = asif_engine_config_init(&cfg, ASIF_FILTER_ROBUST, ASIF_MODEL_INVERTED_PENDULUM_TABLE);
+				if (r != ASIF_OK) return r;
+				cfg.device = device_;
+				cfg.lb[0] = lb[0];
+				cfg.ub[0] = ub[0];
+				cfg.relaxLb = options.relaxLb;
+				cfg.relaxCost = options.relaxCost;
+				cfg.inf = options.inf;
+				cfg.dynParam[0] = pMin_;
+				cfg.dynParam[1] = pMax_;
+				cfg.halfplanes = table_.data();
+				cfg.n_halfplanes = (int32_t)(table_.size() / 2);
+				return create(cfg);
+			}
+			int32_t filter(const double x[], const double uDes[], double uAct[], double &relax)
+			{
+				int32_t rc = 0;
+				double ua = uAct[0], rl = 0.0;
+				const int32_t r = filterBatch(1, x, uDes, &ua, &rl, &rc);
+				if (r != ASIF_OK) return r;
+				if (rc == 1) { // uAct / relax untouched on failure (src/asif_robust.cpp:249-251)
+					uAct[0] = ua;
+					relax = rl;
+				}
+				return rc;
+			}
+
+		protected:
+			std::vector<double> table_;
+			double pMin_, pMax_;
+			int32_t device_;
+		};
+
+		// Batched ASIF::ASIFrealizable (include/asif_realizable.h) for a 2-D polytope kernel.  The x-independent
+		// interval Lie derivatives over each facet (facetLie[facet][active][LfLo, LfHi, LgLo, LgHi]) are inputs:
+		// INTEGRATION.md shows the loop that evaluates them with the user's interval dynamics callback at initialize.
+		class FilterBatchRealizable : public FilterBatchBase
+		{
+		public:
+			typedef struct {
+				double relaxDes = 5.0;
+				double relaxOffset = 5.0;
+				double relaxCost = 50.0;
+				double inf = 1e20;
+			} Options; // include/asif_realizable.h:14-20
+
+			FilterBatchRealizable(const double uncertaintyBounds[2], const uint32_t nVertices, const double vertices[],
+			                      const uint32_t nFacets, const double normals[], const int32_t facetVertices[],
+			                      const int32_t facetActive[], const double facetLie[], const uint32_t maxCriticalFacets,
+			                      const uint32_t maxActiveConstraints, const double pMin, const double pMax,
+			                      const uint32_t npSSmax = 0, const int32_t device = 0)
+			    : v_(vertices, vertices + 2 * nVertices), n_(normals, normals + 2 * nFacets),
+			      fv_(facetVertices, facetVertices + 2 * nFacets), fa_(facetActive, facetActive + maxActiveConstraints * nFacets),
+			      lie_(facetLie, facetLie + 4 * maxActiveConstraints * nFacets), maxCrit_(maxCriticalFacets),
+			      maxAct_(maxActiveConstraints), npSSmax_(npSSmax), pMin_(pMin), pMax_(pMax), device_(device)
+			{
+				unc_[0] = uncertaintyBounds[0];
+				unc_[1] = uncertaintyBounds[1];
+			}
+			int32_t initialize(const double lb[], const double ub[]) { return initialize(lb, ub, Options()); }
+			int32_t initialize(const double lb[], const double ub[], const Options &options)
+			{
+				asif_engine_config cfg;
+				int32_t r = asif_engine_config_init(&cfg, ASIF_FILTER_REALIZABLE, ASIF_MODEL_INVERTED_PENDULUM_KERNEL);
+				if (r != ASIF_OK) return r;
+				cfg.device = device_;
+				cfg.lb[0] = lb[0];
+				cfg.ub[0] = ub[0];
+				cfg.relaxDes = options.relaxDes;
+				cfg.relaxOffset = options.relaxOffset;
+				cfg.relaxCost = options.relaxCost;
+				cfg.inf = options.inf;
+				cfg.npSSmax = (int32_t)npSSmax_;
+				cfg.uncertaintyBounds[0] = unc_[0];
+				cfg.uncertaintyBounds[1] = unc_[1];
+				cfg.dynParam[0] = pMin_;
+				cfg.dynParam[1] = pMax_;
+				cfg.kernel_vertices = v_.data();
+				cfg.n_vertices = (int32_t)(v_.size() / 2);
+				cfg.facet_normals = n_.data();
+				cfg.n_facets = (int32_t)(n_.size() / 2);
+				cfg.facet_vertices = fv_.data();
+				cfg.facet_active = fa_.data();
+				cfg.facet_lie = lie_.data();
+				cfg.max_critical_facets = (int32_t)maxCrit_;
+				cfg.max_active_constraints = (int32_t)maxAct_;
+				return create(cfg);
+			}
+			// relax[0] of the reference is a multiplier of its LP-dual formulation (not unique): reported as 0;
+			// relax[1] is the barrier relaxation eps.  rc: 1, -1 (QP infeasible), -2 (outside the kernel, no critical facet)
+			int32_t filter(const double x[], const double uDes[], double uAct[], double relax[2])
+			{
+				int32_t rc = 0;
+				double ua = uAct[0], rl[2] = {0.0, 0.0};
+				const int32_t r = filterBatch(1, x, uDes, &ua, rl, &rc);
+				if (r != ASIF_OK) return r;
+				if (rc == 1) {
+					uAct[0] = ua;
+					relax[0] = rl[0];
+					relax[1] = rl[1];
+				}
+				return rc;
+			}
+
+		protected:
+			std::vector<double> v_, n_;
+			std::vector<int32_t> fv_, fa_;
+			std::vector<double> lie_;
+			uint32_t maxCrit_, maxAct_, npSSmax_;
+			double pMin_, pMax_, unc_[2];
+			int32_t device_;
 		};
 	} // namespace b200
 } // namespace ASIF

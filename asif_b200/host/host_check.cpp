@@ -82,6 +82,25 @@ int main()
 		for (int i = 0; i < n; i++)
 			if (rc[i] == 1 && (UA[i] > 1.0 || UA[i] < -1.0)) return fail("uAct outside bounds");
 	}
+	// --- 4. implicit and robust classes compile against the same surface and run one batch each
+	{
+		b200::FilterBatchImplicit asif(b200::Model::InvertedPendulum, 10);
+		b200::FilterBatchImplicit::Options o;
+		o.backTrajHorizon = 5.0;
+		o.backTrajDt = 0.05;
+		o.relaxReachLb = 5.0;
+		o.relaxSafeLb = 10.0;
+		const double lb[1] = {-1.5}, ub[1] = {1.5};
+		if (asif.initialize(lb, ub, o) != 1) return fail("FilterBatchImplicit::initialize");
+		double x[2] = {0.2, -0.1}, uDes[1] = {0.4}, uAct[1] = {0.0}, relax[2] = {0.0, 0.0};
+		const int32_t rc = asif.filter(x, uDes, uAct, relax);
+		if (rc != 1 || relax[0] < 10.0 - 1e-9 || relax[1] < 5.0 - 1e-9) return fail("FilterBatchImplicit::filter");
+		const double planes[4] = {0.5, 0.0, -0.5, 0.0}; // |x0| <= 2
+		b200::FilterBatchRobust rob(2, planes, 0.8, 1.2);
+		if (rob.initialize(lb, ub) != 1) return fail("FilterBatchRobust::initialize");
+		double r1 = 0.0;
+		if (rob.filter(x, uDes, uAct, r1) != 1) return fail("FilterBatchRobust::filter");
+	}
 	std::printf("host_check ok\n");
 	return 0;
 }
