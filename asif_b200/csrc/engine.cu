@@ -62,6 +62,7 @@ struct asif_engine {
 	ImplicitParams im;
 	RobustParams rb;
 	RealizableParams rz;
+	double *d_ttable = nullptr; // t_i of the backup trajectory (TB filter)
 	void *d_kernel = nullptr; // polytope kernel tables (realizable filter), one allocation
 	size_t rz_smem = 0;
 	double *d_table = nullptr; // half-plane table (robust filter)
@@ -99,7 +100,7 @@ int ensure_slot(asif_engine *e, Slot &s, int64_t n, bool want_diag)
 }
 
 // ---- soft saturation constants, src/asif_implicit_tb.cpp:768-784 (host libm, same operations)
-void make_softsat(double r, const double *lb, const double *ub, int nu, SoftSat &s)
+int make_softsat(double r, const double *lb, const double *ub, int nu, SoftSat &s)
 {
 	const double alpha = M_PI / 8;
 	const double beta = M_PI / 4;
@@ -112,14 +113,19 @@ void make_softsat(double r, const double *lb, const double *ub, int nu, SoftSat 
 	for (int i = 0; i < MAX_NU; i++) {
 		s.range[i] = 1.0;
 		s.middle[i] = 0.0;
-		s.inv_range_exact[i] = 0.0;
+		s.uc_scale_exact[i] = 0.0;
 	}
+	int mode = SAT_IDENTITY;
 	for (int i = 0; i < nu; i++) {
 		s.range[i] = ub[i] - lb[i];
 		s.middle[i] = (ub[i] + lb[i]) / 2;
 		int ex;
-		if (frexp(s.range[i], &ex) == 0.5) s.inv_range_exact[i] = 1.0 / s.range[i]; // power of two: exact reciprocal
+		const bool pow2 = frexp(s.range[i], &ex) == 0.5;
+		if (pow2) s.uc_scale_exact[i] = 2.0 / s.range[i]; // exact: every operation of 2*(u-mid)/range is then exact
+		const int m = (pow2 && s.middle[i] == 0.0 && s.range[i] == 2.0) ? SAT_IDENTITY : (pow2 ? SAT_POW2 : SAT_GENERAL);
+		if (m < mode) mode = m;
 	}
+	return mode;
 }
 
 template <class K>
@@ -130,25 +136,35 @@ int set_smem(K kernel, size_t bytes)
 }
 
 // ---- kernel dispatch -------------------------------------------------------------------------
-template <class M, int NPBTSS>
-int launch_tb(asif_engine *e, int64_t n, const double *x, const double *ud, double *ua, double *relax, int32_t *rc,
-              double *diag, cudaStream_t st)
+template <class M, int NPBTSS, int SATMODE>
+int launch_tb_mode(asif_engine *e, int64_t n, const double *x, const double *ud, double *ua, double *relax, int32_t *rc,
+                   double *diag, cudaStream_t st)
 {
 	const size_t smem = sizeof(double) * tb_smem_doubles_per_thread<M, NPBTSS>() * TB_THREADS;
 	const unsigned blocks = (unsigned)((n + TB_THREADS - 1) / TB_THREADS);
 	if (diag) {
-		auto k = tb_filter_kernel<M, NPBTSS, true>;
+		auto k = tb_filter_kernel<M, NPBTSS, true, SATMODE>;
 		int r = set_smem(k, smem);
 		if (r) return r;
 		k<<<blocks, TB_THREADS, smem, st>>>(e->tb, n, x, ud, ua, relax, rc, diag, e->d_counters);
 	} else {
-		auto k = tb_filter_kernel<M, NPBTSS, false>;
+		auto k = tb_filter_kernel<M, NPBTSS, false, SATMODE>;
 		int r = set_smem(k, smem);
 		if (r) return r;
 		k<<<blocks, TB_THREADS, smem, st>>>(e->tb, n, x, ud, ua, relax, rc, nullptr, e->d_counters);
 	}
 	CUDA_TRY(cudaGetLastError());
 	return ASIF_OK;
+}
+
+// SAT_POW2 and SAT_IDENTITY are exact shortcuts of SAT_GENERAL; IDENTITY is only instantiated for the nx = 2 models
+template <class M, int NPBTSS>
+int launch_tb(asif_engine *e, int64_t n, const double *x, const double *ud, double *ua, double *relax, int32_t *rc,
+              double *diag, cudaStream_t st)
+{
+	if (e->tb.sat_mode == SAT_IDENTITY && M::NX <= 2) return launch_tb_mode<M, NPBTSS, SAT_IDENTITY>(e, n, x, ud, ua, relax, rc, diag, st);
+	if (e->tb.sat_mode >= SAT_POW2) return launch_tb_mode<M, NPBTSS, SAT_POW2>(e, n, x, ud, ua, relax, rc, diag, st);
+	return launch_tb_mode<M, NPBTSS, SAT_GENERAL>(e, n, x, ud, ua, relax, rc, diag, st);
 }
 
 template <class M>
@@ -170,13 +186,14 @@ int launch_implicit(asif_engine *e, int64_t n, const double *x, const double *ud
 {
 	const size_t smem = sizeof(double) * imp_smem_doubles_per_thread<M, NPBTSS>() * IMP_THREADS;
 	const unsigned blocks = (unsigned)((n + IMP_THREADS - 1) / IMP_THREADS);
+	const bool pow2 = e->im.sat_mode >= SAT_POW2;
 	if (diag) {
-		auto k = implicit_filter_kernel<M, NPBTSS, true>;
+		auto k = pow2 ? implicit_filter_kernel<M, NPBTSS, true, SAT_POW2> : implicit_filter_kernel<M, NPBTSS, true, SAT_GENERAL>;
 		int r = set_smem(k, smem);
 		if (r) return r;
 		k<<<blocks, IMP_THREADS, smem, st>>>(e->im, n, x, ud, ua, relax, rc, diag, e->d_counters);
 	} else {
-		auto k = implicit_filter_kernel<M, NPBTSS, false>;
+		auto k = pow2 ? implicit_filter_kernel<M, NPBTSS, false, SAT_POW2> : implicit_filter_kernel<M, NPBTSS, false, SAT_GENERAL>;
 		int r = set_smem(k, smem);
 		if (r) return r;
 		k<<<blocks, IMP_THREADS, smem, st>>>(e->im, n, x, ud, ua, relax, rc, nullptr, e->d_counters);
@@ -244,7 +261,7 @@ int launch_tb_rollout(asif_engine *e, int64_t n, int32_t steps, double dt, doubl
 {
 	const size_t smem = sizeof(double) * tb_smem_doubles_per_thread<M, NPBTSS>() * TB_THREADS;
 	const unsigned blocks = (unsigned)((n + TB_THREADS - 1) / TB_THREADS);
-	auto k = tb_rollout_kernel<M, NPBTSS>;
+	auto k = (e->tb.sat_mode >= SAT_POW2) ? tb_rollout_kernel<M, NPBTSS, SAT_POW2> : tb_rollout_kernel<M, NPBTSS, SAT_GENERAL>;
 	int r = set_smem(k, smem);
 	if (r) return r;
 	k<<<blocks, TB_THREADS, smem, st>>>(e->tb, n, steps, dt, x, ud, ua, rc, e->d_counters + 1, e->d_counters);
@@ -462,9 +479,25 @@ int32_t asif_engine_create(const asif_engine_config *cfg, asif_engine **out)
 		}
 		p.npBT = (int32_t)npBT;
 		// updateOptions() clamps satSharpness to [0.01, 2] (src/asif_implicit_tb.cpp:391-400); initialize() does not.
-		make_softsat(cfg->satSharpness, cfg->lb, cfg->ub, nu, p.sat);
+		p.sat_mode = make_softsat(cfg->satSharpness, cfg->lb, cfg->ub, nu, p.sat);
 		p.gi[nu] = 1.0 / (2.0 * cfg->relaxCost);
 		p.gih[nu] = sqrt(p.gi[nu]);
+		{ // t_i exactly as the reference accumulates it
+			double *tt = new (std::nothrow) double[npBT];
+			cudaError_t te = tt ? cudaMalloc(&e->d_ttable, sizeof(double) * npBT) : cudaErrorMemoryAllocation;
+			if (te == cudaSuccess) {
+				tt[0] = 0.0;
+				for (int64_t i = 1; i < npBT; i++) tt[i] = tt[i - 1] + p.backTrajDt;
+				te = cudaMemcpy(e->d_ttable, tt, sizeof(double) * npBT, cudaMemcpyHostToDevice);
+			}
+			delete[] tt;
+			if (te != cudaSuccess) {
+				cudaFree(e->d_ttable);
+				delete e;
+				return fail(ASIF_ERR_CUDA, "time table upload failed: %s", cudaGetErrorString(te));
+			}
+			p.t_of_index = e->d_ttable;
+		}
 		break;
 	}
 	case ASIF_FILTER_IMPLICIT: {
@@ -509,7 +542,7 @@ int32_t asif_engine_create(const asif_engine_config *cfg, asif_engine **out)
 			return fail(ASIF_ERR_INVALID_ARGUMENT, "backup trajectory of %lld points is not sensible", (long long)npBT);
 		}
 		p.npBT = (int32_t)npBT;
-		make_softsat(cfg->satSharpness, cfg->lb, cfg->ub, nu, p.sat);
+		p.sat_mode = make_softsat(cfg->satSharpness, cfg->lb, cfg->ub, nu, p.sat);
 		for (int i = nu; i < nu + 2; i++) {
 			p.gi[i] = 1.0 / (2.0 * cfg->relaxCost);
 			p.gih[i] = sqrt(p.gi[i]);
@@ -678,6 +711,7 @@ int32_t asif_engine_destroy(asif_engine *e)
 	cudaFree(e->d_counters);
 	cudaFree(e->d_table);
 	cudaFree(e->d_kernel);
+	cudaFree(e->d_ttable);
 	delete e;
 	return ASIF_OK;
 }

@@ -20,9 +20,17 @@ struct SoftSat {
 	double bevelYc;    // 1 - r
 	double range[MAX_NU];  // ub - lb
 	double middle[MAX_NU]; // (ub + lb)/2
-	// 1/range when range is a power of two (then x/range == x*(1/range) bit for bit and the FP64
-	// division, ~10 dependent DFMAs per Euler step, is not needed); 0 otherwise
-	double inv_range_exact[MAX_NU];
+	// 2/range when range is a power of two (then 2*(u-mid)/range == (u-mid)*(2/range) bit for bit and the
+	// FP64 division, ~10 dependent DFMAs per Euler step, is not needed); 0 otherwise
+	double uc_scale_exact[MAX_NU];
+};
+
+// How the normalised input uc = 2 (u - middle) / range is evaluated; chosen on the host from (lb, ub).
+// Every mode produces the same bits as the reference expression.
+enum : int {
+	SAT_GENERAL = 0,  // 2*(u-middle)/range
+	SAT_POW2 = 1,     // range is a power of two: (u-middle)*(2/range), all operations exact
+	SAT_IDENTITY = 2  // middle == 0 and range == 2 (e.g. u in [-1,1]): uc == u
 };
 
 // Structural patterns a model may declare for its callback outputs: an entry that is the literal
@@ -38,7 +46,8 @@ struct TbParams {
 	double relaxCost, relaxSafeLb, relaxTTS, relaxMinOrtho;
 	double backTrajHorizon, backTrajDt, backTrajMinOrtho, inf;
 	int32_t npBT; // trajectory points (npBT-1 Euler steps)
-	int32_t pad_;
+	int32_t sat_mode;
+	const double *t_of_index; // device: t_0 = 0, t_i = t_{i-1} + dt (src/asif_implicit_tb.cpp:465,475)
 	SoftSat sat;
 	// QP metric: gi = 1/(2 H_ii), gih = sqrt(gi) for v = (u, relax)
 	double gi[MAX_NV], gih[MAX_NV];
@@ -59,22 +68,24 @@ __device__ __forceinline__ double input_saturate(double u, double lb, double ub)
 	return u;
 }
 
-// src/asif_implicit_tb.cpp:764-819, one input.  Same branch order and operation order.
+// src/asif_implicit_tb.cpp:764-819, one input.  Same decisions and operation order; the five-way branch is
+// folded onto |uc| (two compares instead of four; a NaN input takes the pass-through leg as in the reference).
+template <int SATMODE>
 __device__ __forceinline__ void input_saturate_soft(const SoftSat &s, int i, double lb, double ub, double u, double &uSat,
                                                     double &DuSat)
 {
 	const double range = s.range[i], middle = s.middle[i];
-	const double inv = s.inv_range_exact[i];
-	const double uc = (inv != 0.0) ? (2 * (u - middle)) * inv : 2 * (u - middle) / range;
-	if (uc >= s.bevelStop) {
-		uSat = ub;
+	double uc;
+	if (SATMODE == SAT_IDENTITY) uc = u;
+	else if (SATMODE == SAT_POW2) uc = (u - middle) * s.uc_scale_exact[i];
+	else uc = 2 * (u - middle) / range;
+	const double a = fabs(uc);
+	uSat = u; // |uc| <= bevelStart (or NaN): pass through
+	DuSat = 1;
+	if (a >= s.bevelStop) {
+		uSat = (uc > 0) ? ub : lb;
 		DuSat = 0;
-	} else if (uc <= -s.bevelStop) {
-		uSat = lb;
-		DuSat = 0;
-	} else if (uc <= s.bevelStart && uc >= -s.bevelStart) {
-		uSat = u;
-		DuSat = 1;
+	} else if (a <= s.bevelStart || !(a > s.bevelStart)) {
 	} else if (uc > s.bevelStart) {
 		const double d = uc - s.bevelStop;
 		const double sq = sqrt(s.r2 - d * d);
@@ -87,9 +98,6 @@ __device__ __forceinline__ void input_saturate_soft(const SoftSat &s, int i, dou
 		uSat = -sq - s.bevelYc;
 		DuSat = (s.bevelStop + uc) / sq;
 		uSat = 0.5 * uSat * range + middle;
-	} else { // NaN input
-		DuSat = 1;
-		uSat = u;
 	}
 }
 
@@ -108,7 +116,8 @@ __host__ __device__ constexpr int dfcl_pattern(int i, int j)
 
 // Closed-loop backup dynamics and their Jacobian, src/asif_implicit_tb.cpp:833-897.
 // Entries of DfCL whose dfcl_pattern is PZ / P1 are not written (callers must not read them).
-template <class M>
+// f_pat(i) == PZ marks a drift component that is the literal 0.0 (then g uSat + 0.0 == g uSat).
+template <class M, int SATMODE>
 __device__ __forceinline__ void backup_cl_dynamics(const SoftSat &sat, const double *lb, const double *ub, const double *x,
                                                    double *fCL, double *DfCL)
 {
@@ -117,7 +126,7 @@ __device__ __forceinline__ void backup_cl_dynamics(const SoftSat &sat, const dou
 	double d[NX * NX], Dg[M::FUSED_GRADIENT ? 1 : NX * NU * NX];
 	M::backup_controller(x, u, Du);
 #pragma unroll
-	for (int k = 0; k < NU; k++) input_saturate_soft(sat, k, lb[k], ub[k], u[k], uSat[k], DuSat[k]);
+	for (int k = 0; k < NU; k++) input_saturate_soft<SATMODE>(sat, k, lb[k], ub[k], u[k], uSat[k], DuSat[k]);
 	if (M::FUSED_GRADIENT) {
 		M::dynamics_with_gradient(x, uSat, f, g, d);
 	} else {
@@ -170,7 +179,7 @@ __device__ __forceinline__ void backup_cl_dynamics(const SoftSat &sat, const dou
 			acc = have ? acc + t : t;
 			have = true;
 		}
-		fCL[i] = have ? acc + f[i] : f[i];
+		fCL[i] = have ? ((M::f_pat(i) == PZ) ? acc : acc + f[i]) : f[i];
 	}
 }
 

@@ -19,7 +19,7 @@ struct ImplicitParams {
 	double relaxCost, relaxSafeLb, relaxReachLb;
 	double backTrajDt, inf;
 	int32_t npBT;
-	int32_t pad_;
+	int32_t sat_mode;
 	SoftSat sat;
 	double gi[MAX_NV], gih[MAX_NV];
 };
@@ -144,7 +144,7 @@ struct ImpRows {
 	}
 };
 
-template <class M, int NPBTSS, bool WITH_DIAG>
+template <class M, int NPBTSS, bool WITH_DIAG, int SATMODE>
 __global__ void __launch_bounds__(IMP_THREADS, 3)
 implicit_filter_kernel(const ImplicitParams p, const int64_t n, const double *__restrict__ x_in,
                        const double *__restrict__ u_des, double *__restrict__ u_act, double *__restrict__ relax_out,
@@ -199,14 +199,19 @@ implicit_filter_kernel(const ImplicitParams p, const int64_t n, const double *__
 	const int N = p.npBT;
 	for (int i = 1; i < N; i++) {
 		double Xd[NS], DfCL[NX * NX];
-		backup_cl_dynamics<M>(p.sat, p.lb, p.ub, X, Xd, DfCL);
+		backup_cl_dynamics<M, SATMODE>(p.sat, p.lb, p.ub, X, Xd, DfCL);
 		sensitivity_rhs<M>(DfCL, X + NX, Xd + NX);
 #pragma unroll
 		for (int e = 0; e < NS; e++) X[e] = Xd[e] * p.backTrajDt + X[e];
-		M::safety_set(X, hs, Dhs);
-		double hmin = hs[0];
+		double hmin;
+		if (M::HAS_SAFETY_MIN) {
+			hmin = M::safety_min(X);
+		} else {
+			M::safety_set(X, hs, Dhs);
+			hmin = hs[0];
 #pragma unroll
-		for (int j = 1; j < NPSS; j++) hmin = (hs[j] < hmin) ? hs[j] : hmin;
+			for (int j = 1; j < NPSS; j++) hmin = (hs[j] < hmin) ? hs[j] : hmin;
+		}
 		if (hmin < key[NPBTSS - 1]) {
 			const int slot = R.kslot[NPBTSS - 1];
 #pragma unroll

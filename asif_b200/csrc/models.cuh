@@ -58,6 +58,15 @@ struct DoubleIntegratorTB {
 		constexpr int t[4] = {0, 0, 0, 0};
 		return t[i];
 	}
+	__host__ __device__ static constexpr int f_pat(int i)
+	{
+		constexpr int t[2] = {2, 0};
+		return t[i];
+	}
+	// min_j h_j(x) without forming the four values: min(1-x, x+1) = 1-|x| and rounding is monotone, so
+	// min_j h_j = 1 - max(|x0|, |x1|) with the same bits as the reference's min_element over h
+	static constexpr bool HAS_SAFETY_MIN = true;
+	__device__ static double safety_min(const double *x) { return 1.0 - fmax(fabs(x[0]), fabs(x[1])); }
 	__device__ static void safety_set(const double *x, double *h, double *Dh)
 	{
 		h[0] = -x[0] + 1.0;   Dh[0] = -1.0; Dh[4] = 0.0;
@@ -129,6 +138,13 @@ struct SegwayTB {
 		constexpr int t[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 2, 0, 2, 0, 0, 0, 0};
 		return t[i];
 	}
+	__host__ __device__ static constexpr int f_pat(int i)
+	{
+		constexpr int t[4] = {2, 2, 2, 2};
+		return t[i];
+	}
+	static constexpr bool HAS_SAFETY_MIN = false;
+	__device__ static double safety_min(const double *) { return 0.0; }
 	__device__ static double bound(int i)
 	{
 		return i == 0 ? 3.0 : (i == 1 ? 3.0 : (i == 2 ? (M_PI / 6) : M_PI));
@@ -298,6 +314,14 @@ struct InvertedPendulumImplicit {
 		constexpr int t[4] = {0, 0, 0, 0};
 		return t[i];
 	}
+	__host__ __device__ static constexpr int f_pat(int i)
+	{
+		constexpr int t[2] = {2, 2};
+		return t[i];
+	}
+	// box +-pi on both components: min_j h_j = pi - max(|x0|, |x1|), same bits as min_element over h
+	static constexpr bool HAS_SAFETY_MIN = true;
+	__device__ static double safety_min(const double *x) { return M_PI - fmax(fabs(x[0]), fabs(x[1])); }
 	__device__ static void safety_set(const double *x, double *h, double *Dh)
 	{
 		h[0] = -x[0] + M_PI;   Dh[0] = -1.0; Dh[4] = 0.0;

@@ -191,7 +191,7 @@ struct TbDiagRec {
 // thread's shared-memory view (already offset by threadIdx.x, element stride T).  Must be called
 // by all 32 lanes of a warp together (warp-uniform early exit from the trajectory loop).
 // R is left describing the state's QP rows (the diag writer re-scans them).
-template <class M, int NPBTSS, bool WITH_DIAG>
+template <class M, int NPBTSS, bool WITH_DIAG, int SATMODE>
 __device__ __forceinline__ int32_t tb_filter_one(const TbParams &p, const double (&x0)[M::NX], const double (&ud)[M::NU],
                                                  double *snap, const int T, double (&uo)[M::NU], double &relax,
                                                  int &qp_iters, TbDiagRec<NPBTSS> &dg, TbRows<M, NPBTSS> &R)
@@ -233,27 +233,30 @@ __device__ __forceinline__ int32_t tb_filter_one(const TbParams &p, const double
 	for (int e = 0; e < NS; e++) snap[(R.kslot[0] * NS + e) * T] = X[e];
 
 	bool hit = false;
-	double tHit = 0.0, tNow = 0.0;
+	int idxHit = 0;
 	double hBackupEnd = 0.0;
 	const int N = p.npBT;
-	const bool run = !inside;
+	bool active = !inside; // still selecting critical points and looking for the first hit
 	for (int i = 1; i < N; i++) {
 		if (!WITH_DIAG) {
-			if (__all_sync(0xffffffffu, hit || !run)) break;
+			if (__all_sync(0xffffffffu, !active)) break;
 		}
-		tNow = tNow + p.backTrajDt;
 		// rhs (:899-909) and Euler step: (rhs*dt) + prev, two roundings (:477-480)
 		double Xd[NS], DfCL[NX * NX];
-		backup_cl_dynamics<M>(p.sat, p.lb, p.ub, X, Xd, DfCL);
+		backup_cl_dynamics<M, SATMODE>(p.sat, p.lb, p.ub, X, Xd, DfCL);
 		sensitivity_rhs<M>(DfCL, X + NX, Xd + NX);
 #pragma unroll
 		for (int e = 0; e < NS; e++) X[e] = Xd[e] * p.backTrajDt + X[e];
 		// selection and hit scan are frozen after the first hit (:507,539)
-		const bool active = run && !hit;
-		M::safety_set(X, hs, Dhs);
-		double hmin = hs[0];
+		double hmin;
+		if (M::HAS_SAFETY_MIN) {
+			hmin = M::safety_min(X);
+		} else {
+			M::safety_set(X, hs, Dhs);
+			hmin = hs[0];
 #pragma unroll
-		for (int j = 1; j < NPSS; j++) hmin = (hs[j] < hmin) ? hs[j] : hmin;
+			for (int j = 1; j < NPSS; j++) hmin = (hs[j] < hmin) ? hs[j] : hmin;
+		}
 		if (active && hmin < key[NPBTSS - 1]) {
 			// evict the largest key, insert (hmin, i) keeping ascending order; ties keep the earlier index first
 			const int slot = R.kslot[NPBTSS - 1];
@@ -282,7 +285,8 @@ __device__ __forceinline__ int32_t tb_filter_one(const TbParams &p, const double
 		if (__any_sync(0xffffffffu, hit_now)) {
 			if (hit_now) {
 				hit = true;
-				tHit = tNow;
+				active = false;
+				idxHit = i;
 #pragma unroll
 				for (int e = 0; e < NS; e++) snap[(NPBTSS * NS + e) * T] = X[e];
 			}
@@ -345,7 +349,7 @@ __device__ __forceinline__ int32_t tb_filter_one(const TbParams &p, const double
 		for (int e = 0; e < NS; e++) xh[e] = snap[(NPBTSS * NS + e) * T];
 		double hBS, DhBS[NX], DDhBS[NX * NX], fCl[NX], DfCl[NX * NX];
 		M::backup_set(xh, hBS, DhBS, DDhBS);
-		backup_cl_dynamics<M>(p.sat, p.lb, p.ub, xh, fCl, DfCl);
+		backup_cl_dynamics<M, SATMODE>(p.sat, p.lb, p.ub, xh, fCl, DfCl);
 #pragma unroll
 		for (int r = 0; r < NX; r++)
 #pragma unroll
@@ -366,6 +370,8 @@ __device__ __forceinline__ int32_t tb_filter_one(const TbParams &p, const double
 		const double den1 = sqrt(n1), den2 = sqrt(n2);
 		const double den = den1 * den2;
 		ortho = cosT / den;
+		// t_i accumulates += dt in the reference (:475); it depends on i only, so the host tabulates it once
+		const double tHit = p.t_of_index[idxHit];
 		TTS = tHit;
 		const double hReach = p.backTrajHorizon - tHit;
 		double DhBSDx[NX];
@@ -464,7 +470,7 @@ __host__ __device__ constexpr int tb_min_blocks()
 	return M::NX <= 2 ? ASIF_TB_MINBLOCKS_NX2 : 2;
 }
 
-template <class M, int NPBTSS, bool WITH_DIAG>
+template <class M, int NPBTSS, bool WITH_DIAG, int SATMODE>
 __global__ void __launch_bounds__(TB_THREADS, tb_min_blocks<M>())
 tb_filter_kernel(const TbParams p, const int64_t n, const double *__restrict__ x_in, const double *__restrict__ u_des,
                  double *__restrict__ u_act, double *__restrict__ relax_out, int32_t *__restrict__ rc_out,
@@ -493,7 +499,7 @@ tb_filter_kernel(const TbParams p, const int64_t n, const double *__restrict__ x
 	int qp_iters;
 	TbDiagRec<NPBTSS> dg;
 	TbRows<M, NPBTSS> R;
-	const int32_t rc = tb_filter_one<M, NPBTSS, WITH_DIAG>(p, x0, ud, snap, T, uo, relax, qp_iters, dg, R);
+	const int32_t rc = tb_filter_one<M, NPBTSS, WITH_DIAG, SATMODE>(p, x0, ud, snap, T, uo, relax, qp_iters, dg, R);
 
 	if (live) {
 #pragma unroll
@@ -534,7 +540,7 @@ tb_filter_kernel(const TbParams p, const int64_t n, const double *__restrict__ x
 
 // Closed-loop rollout (examples/segway_implicit_tb.cpp:251-283): the state never leaves the
 // registers between control steps; one launch covers all steps of every agent.
-template <class M, int NPBTSS>
+template <class M, int NPBTSS, int SATMODE>
 __global__ void __launch_bounds__(TB_THREADS, tb_min_blocks<M>())
 tb_rollout_kernel(const TbParams p, const int64_t n, const int32_t steps, const double dt_plant, double *__restrict__ x_io,
                   const double *__restrict__ u_des, double *__restrict__ u_act_last, int32_t *__restrict__ rc_last,
@@ -565,7 +571,7 @@ tb_rollout_kernel(const TbParams p, const int64_t n, const int32_t steps, const 
 		int qp_iters;
 		TbDiagRec<NPBTSS> dg;
 		TbRows<M, NPBTSS> R;
-		rc = tb_filter_one<M, NPBTSS, false>(p, x, ud, snap, T, uo, relax, qp_iters, dg, R);
+		rc = tb_filter_one<M, NPBTSS, false, SATMODE>(p, x, ud, snap, T, uo, relax, qp_iters, dg, R);
 		iters += (unsigned long long)qp_iters;
 		const int slot = (rc >= -3 && rc <= 2) ? rc + 3 : 7;
 #pragma unroll

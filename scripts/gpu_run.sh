@@ -16,8 +16,8 @@ ncu-launches)
   ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches.csv \
       python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launches.log 2>&1; echo "ncu-launches rc=$?" ;;
 ncu-full)
-  python bench.py --steps 2 --warmup 3 --no-cpu-baseline --states 2000000 > gpurun_out/plain2.log 2>&1 &&
+  python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/plain2.log 2>&1 &&
   ncu --set full --clock-control none --import-source on -k regex:tb_filter_kernel -s 3 -c 2 -f -o gpurun_out/prof_tb \
-      python bench.py --steps 2 --warmup 3 --no-cpu-baseline --states 2000000 > gpurun_out/ncu_full.log 2>&1; echo "ncu-full rc=$?" ;;
+      python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1; echo "ncu-full rc=$?" ;;
 esac
 done
