@@ -237,10 +237,17 @@ __device__ __forceinline__ int32_t tb_filter_one(const TbParams &p, const double
 	double hBackupEnd = 0.0;
 	const int N = p.npBT;
 	bool active = !inside; // still selecting critical points and looking for the first hit
-	for (int i = 1; i < N; i++) {
+	// Two nested loops: the inner one is the per-step instruction stream and leaves as soon as ANY lane of the
+	// warp hits the backup set; the hit bookkeeping (once per state) lives between the loops, so it costs
+	// nothing per step.  (A plain `if (hit_now) {...}` in the step body is if-converted by ptxas into ~11
+	// predicated instructions that issue on every step.)
+	int i = 1;
+	while (i < N) {
 		if (!WITH_DIAG) {
 			if (__all_sync(0xffffffffu, !active)) break;
 		}
+		bool hit_now = false;
+		for (; i < N; i++) {
 		// rhs (:899-909) and Euler step: (rhs*dt) + prev, two roundings (:477-480)
 		double Xd[NS], DfCL[NX * NX];
 		backup_cl_dynamics<M, SATMODE>(p.sat, p.lb, p.ub, X, Xd, DfCL);
@@ -280,16 +287,18 @@ __device__ __forceinline__ int32_t tb_filter_one(const TbParams &p, const double
 			}
 			nkept = nkept < NPBTSS ? nkept + 1 : NPBTSS;
 		}
-		// the hit happens once per state: keep its bookkeeping out of the per-step instruction stream
-		const bool hit_now = active && (M::backup_set_value(X) >= 0.0);
+		hit_now = active && (M::backup_set_value(X) >= 0.0);
 		if (__any_sync(0xffffffffu, hit_now)) {
-			if (hit_now) {
-				hit = true;
-				active = false;
-				idxHit = i;
+			i++;
+			break;
+		}
+		}
+		if (hit_now) { // i was already advanced past the hit point
+			hit = true;
+			active = false;
+			idxHit = i - 1;
 #pragma unroll
-				for (int e = 0; e < NS; e++) snap[(NPBTSS * NS + e) * T] = X[e];
-			}
+			for (int e = 0; e < NS; e++) snap[(NPBTSS * NS + e) * T] = X[e];
 		}
 	}
 	if (WITH_DIAG) hBackupEnd = M::backup_set_value(X);
