@@ -1,0 +1,69 @@
+"""Closed-loop rollout on the device (config 5: fleet of independent agents, state resident across control steps)
+against the oracle's restatement of the example main loop and the reference-generated golden.  B200 box."""
+import os
+
+import numpy as np
+import pytest
+
+import conftest as cf
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ab():
+    import asif_b200
+    if asif_b200.device_count() < 1:
+        pytest.fail("no CUDA device: the engine has no CPU fallback")
+    return asif_b200
+
+
+def test_rollout_double_integrator_matches_oracle(ab, oracle):
+    n, steps, dt = 3000, 60, 1e-3
+    x0, ud = cf.c2_inputs(n, seed=91)
+    x0 *= 0.4
+    eng = ab.Engine(ab.FILTER_IMPLICIT_TB, ab.MODEL_DOUBLE_INTEGRATOR_TB, **cf.tb_engine_kwargs(cf.C2_TB_OPTS))
+    x, u, rc, hist = eng.rollout(x0, ud, steps, dt)
+    xo, uo, rco, histo = oracle.rollout(2, x0, ud, steps, dt, cf.C2_TB_OPTS)
+    assert np.array_equal(rc, rco) and np.array_equal(hist, histo)
+    assert hist.sum() == n * steps
+    # Same arithmetic on both sides except the QP step (dual active set vs KKT enumeration): per call u agrees to
+    # 1e-6 + 1e-5|u| (ill-conditioned active sets with a large relaxation lose digits), so after `steps` plant
+    # steps the states may differ by at most steps * dt * that.
+    assert np.abs(x - xo).max() < steps * dt * (1e-6 + 1e-5)
+    assert np.median(np.abs(x - xo)) < 1e-14
+    # the last input is the filter evaluated at slightly different states (closed loop): strict tolerance for
+    # almost all agents, and a bound that allows for the state difference times the loop gain for every agent
+    strict = np.abs(u - uo) <= 1e-6 + 1e-5 * np.abs(uo)
+    assert strict.mean() > 0.995
+    assert np.abs(u - uo).max() < 1e-3  # one agent in a few thousand sits on an ill-conditioned QP (du/dx ~ 1e3)
+    # a rollout of k steps equals k filter calls + plant steps done by hand (the example main loop)
+    xs = x0.copy()
+    for _ in range(5):
+        ua, _, _ = eng.filter_batch(xs, ud)
+        xs = xs + dt * np.stack([xs[:, 1], ua[:, 0]], axis=1)
+    x5, _, _, _ = eng.rollout(x0, ud, 5, dt)
+    assert np.abs(x5 - xs).max() < 1e-12
+
+
+def test_rollout_segway_golden(ab):
+    g = np.load(os.path.join(cf.ROOT, "tests", "golden", "c5_segway_rollout.npz"))
+    eng = ab.Engine(ab.FILTER_IMPLICIT_TB, ab.MODEL_SEGWAY, **cf.tb_engine_kwargs(list(g["opts"])))
+    x, u, rc, hist = eng.rollout(g["x0"], g["u_des"], int(g["steps"]), float(g["dt"]))
+    assert np.array_equal(rc, g["rc_last"])
+    assert np.array_equal(hist, g["rc_hist"])
+    assert np.abs(x - g["x_end"]).max() < 1e-9
+    assert np.all(np.abs(u - g["u_act_last"]) <= 1e-6 + 1e-5 * np.abs(g["u_act_last"]))
+
+
+def test_rollout_stays_safe_long_horizon(ab):
+    """Property at scale: agents that start inside the safe set and keep finding the backup set stay inside it."""
+    n, steps = 20000, 400
+    x0, ud = cf.c2_inputs(n, seed=17)
+    x0 *= 0.5
+    eng = ab.Engine(ab.FILTER_IMPLICIT_TB, ab.MODEL_DOUBLE_INTEGRATOR_TB, **cf.tb_engine_kwargs(cf.C2_TB_OPTS))
+    x, u, rc, hist = eng.rollout(x0, ud, steps, 1e-3)
+    assert np.isfinite(x).all()
+    assert hist.sum() == n * steps
+    assert np.abs(x).max() <= 1.0 + 1e-9
+    assert np.abs(u).max() <= 1.0
