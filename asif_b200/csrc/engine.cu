@@ -16,6 +16,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <new>
@@ -42,8 +43,19 @@ int fail(int code, const char *fmt, ...)
 			return fail(ASIF_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
 	} while (0)
 
-constexpr int N_SLOTS = 3;               // pipeline depth of the host-memory path
-constexpr int64_t CHUNK_STATES = 1 << 20; // states per pipeline chunk
+constexpr int N_SLOTS = 4;               // pipeline depth of the host-memory path
+constexpr int64_t CHUNK_STATES = 1 << 20; // states per pipeline chunk (env ASIF_B200_CHUNK_STATES overrides)
+
+int64_t chunk_states()
+{
+	static int64_t v = 0;
+	if (v == 0) {
+		const char *e = getenv("ASIF_B200_CHUNK_STATES");
+		const long long x = e ? atoll(e) : 0;
+		v = (x >= 1024) ? (int64_t)x : CHUNK_STATES;
+	}
+	return v;
+}
 
 struct Slot {
 	cudaStream_t stream = nullptr;
@@ -743,7 +755,7 @@ int32_t asif_engine_filter_batch(asif_engine *e, int64_t n, const double *x, con
 	// host memory: chunks rotate over N_SLOTS streams so that the H2D copy of chunk i+1, the kernel of
 	// chunk i and the D2H copy of chunk i-1 overlap (they do when the caller's buffers are pinned)
 	const int nx = e->nx, nu = e->nu, nr = e->n_relax, nd = e->n_diag;
-	const int64_t chunk = n < CHUNK_STATES ? n : CHUNK_STATES;
+	const int64_t chunk = n < chunk_states() ? n : chunk_states();
 	CUDA_TRY(cudaMemset(e->d_counters, 0, sizeof(unsigned long long)));
 	int si = 0;
 	for (int64_t off = 0; off < n; off += chunk, si = (si + 1) % N_SLOTS) {
