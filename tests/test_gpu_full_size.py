@@ -1,0 +1,96 @@
+"""BASELINE-size runs (1e7 states of config 2, 1e6 of the others) checked through size-independent properties:
+output invariants of the QP, determinism, slicing and permutation invariance, agreement of the host-memory and
+device-memory entry points.  B200 box."""
+import numpy as np
+import pytest
+
+import conftest as cf
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ab():
+    import asif_b200
+    if asif_b200.device_count() < 1:
+        pytest.fail("no CUDA device: the engine has no CPU fallback")
+    return asif_b200
+
+
+def test_c2_full_size_properties(ab, oracle):
+    n = 10_000_000
+    x, ud = cf.c2_inputs(n, seed=cf.SEED + 200)
+    o = cf.C2_TB_OPTS
+    eng = ab.Engine(ab.FILTER_IMPLICIT_TB, ab.MODEL_DOUBLE_INTEGRATOR_TB, **cf.tb_engine_kwargs(o))
+    u, relax, rc = eng.filter_batch(x, ud)
+    # return codes are the reference's, nothing else
+    assert set(np.unique(rc)) <= {1, 2, -1, -3}
+    hist = {int(k): int(v) for k, v in zip(*np.unique(rc, return_counts=True))}
+    print("C2 1e7 rc histogram", hist)
+    assert 0.80 < hist[1] / n < 0.86 and 0.14 < hist[-3] / n < 0.20
+    # invariants of the solution: input bounds, relaxation lower bound, pass-through inside the backup set
+    assert u.min() >= -1.0 and u.max() <= 1.0
+    ok = rc > 0
+    assert relax[ok].min() >= o[1] - 1e-9
+    inside = rc == 2
+    assert np.array_equal(u[inside, 0], np.clip(ud[inside, 0], -1, 1)) and np.all(relax[inside] == o[1])
+    # failure path: saturated backup controller K x
+    fail = rc < 0
+    assert np.array_equal(u[fail, 0], np.clip(-10.0 * x[fail, 0] + -20.0 * x[fail, 1], -1, 1))
+    # determinism and slicing invariance (each state is independent; no cross-state effects of chunking / tail CTAs)
+    u2, relax2, rc2 = eng.filter_batch(x, ud)
+    assert np.array_equal(u, u2) and np.array_equal(relax, relax2) and np.array_equal(rc, rc2)
+    for lo, hi in ((0, 1), (12345, 12345 + 1048577), (n - 777, n)):
+        us, rs, cs = eng.filter_batch(x[lo:hi], ud[lo:hi])
+        assert np.array_equal(us, u[lo:hi]) and np.array_equal(rs, relax[lo:hi]) and np.array_equal(cs, rc[lo:hi])
+    # permutation invariance on a sample
+    g = cf.philox(5)
+    idx = g.permutation(n)[:500_000]
+    up, rp, cp = eng.filter_batch(x[idx], ud[idx])
+    assert np.array_equal(up, u[idx]) and np.array_equal(cp, rc[idx])
+    # a seeded sub-sample against the oracle (the oracle finishes 2e4 states in seconds)
+    sub = g.permutation(n)[:20_000]
+    u0, relax0, rc0 = oracle.filter_batch(2, x[sub], ud[sub], o)
+    cf.assert_parity("C2 sub-sample of 1e7", (u[sub], relax[sub], rc[sub]), (u0, relax0, rc0))
+
+
+def test_device_pointer_entry_matches_host_entry(ab):
+    import torch
+    n = 300_001
+    x, ud = cf.c2_inputs(n, seed=3)
+    eng = ab.Engine(ab.FILTER_IMPLICIT_TB, ab.MODEL_DOUBLE_INTEGRATOR_TB, **cf.tb_engine_kwargs(cf.C2_TB_OPTS))
+    u, relax, rc = eng.filter_batch(x, ud)
+    dev = torch.device("cuda", 0)
+    xd, udd = torch.from_numpy(x).to(dev), torch.from_numpy(ud).to(dev)
+    ua = torch.empty((n, 1), dtype=torch.float64, device=dev)
+    rl = torch.empty((n, 1), dtype=torch.float64, device=dev)
+    rcd = torch.empty((n,), dtype=torch.int32, device=dev)
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        eng.filter_batch_into(n, xd, udd, ua, rl, rcd, stream=st.cuda_stream)
+    st.synchronize()
+    assert np.array_equal(ua.cpu().numpy(), u) and np.array_equal(rl.cpu().numpy(), relax) and np.array_equal(rcd.cpu().numpy(), rc)
+
+
+def test_other_configs_full_size_invariants(ab):
+    n = 1_000_000
+    # C1
+    x, ud = cf.c1_inputs(n)
+    u, relax, rc = ab.Engine(ab.FILTER_EXPLICIT, ab.MODEL_DOUBLE_INTEGRATOR).filter_batch(x, ud)
+    assert set(np.unique(rc)) <= {1, -1} and np.abs(u).max() <= 1.0 and np.all(relax[rc == 1] == 5.0)
+    # C3b
+    o = cf.C3B_OPTS
+    x, ud = cf.c3b_inputs(n)
+    u, relax, rc = ab.Engine(ab.FILTER_ROBUST, ab.MODEL_INVERTED_PENDULUM_TABLE, relaxLb=o[0], relaxCost=o[1],
+                             dynParam=[o[2], o[3]], halfplanes=cf.halfplane_table()).filter_batch(x, ud)
+    assert set(np.unique(rc)) <= {1, -1} and np.abs(u).max() <= 1.5 and relax[rc == 1].min() >= o[0] - 1e-9
+    # C4
+    x, ud = cf.c4_inputs(n)
+    u, relax, rc = ab.Engine(ab.FILTER_REALIZABLE, ab.MODEL_INVERTED_PENDULUM_KERNEL,
+                             **cf.realizable_engine_kwargs(cf.C4_OPTS)).filter_batch(x, ud)
+    assert set(np.unique(rc)) <= {1, -1, -2} and np.abs(u).max() <= 1.5 and relax[:, 1].min() >= -1e-12
+    # C5 filter call
+    x, ud = cf.c5_inputs(n)
+    u, relax, rc = ab.Engine(ab.FILTER_IMPLICIT_TB, ab.MODEL_SEGWAY, **cf.tb_engine_kwargs(cf.SEGWAY_TB_OPTS)).filter_batch(x, ud)
+    assert set(np.unique(rc)) <= {1, 2, -1, -2, -3} and np.abs(u).max() <= 20.0
+    assert (rc == -2).sum() <= 5  # iteration cap of the active-set solver: essentially never
