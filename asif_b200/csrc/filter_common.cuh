@@ -130,8 +130,12 @@ __device__ __forceinline__ void backup_cl_dynamics(const SoftSat &sat, const dou
 	if (M::FUSED_GRADIENT) {
 		M::dynamics_with_gradient(x, uSat, f, g, d);
 	} else {
-		M::dynamics(x, f, g);
-		M::dynamics_gradients(x, d, Dg);
+		if (M::HAS_DYNAMICS_ALL) {
+			M::dynamics_all(x, f, g, d, Dg); // shares sub-expressions (trig of the same argument) between f, g and Df, Dg
+		} else {
+			M::dynamics(x, f, g);
+			M::dynamics_gradients(x, d, Dg);
+		}
 	}
 #pragma unroll
 	for (int i = 0; i < NX; i++)

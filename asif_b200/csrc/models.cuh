@@ -112,6 +112,8 @@ struct DoubleIntegratorTB {
 		Df[0] = 0.0; Df[1] = 0.0; Df[2] = 1.0; Df[3] = 0.0;
 		Dg[0] = Dg[1] = Dg[2] = Dg[3] = 0.0;
 	}
+	static constexpr bool HAS_DYNAMICS_ALL = false;
+	__device__ static void dynamics_all(const double *, double *, double *, double *, double *) {}
 };
 
 // ------------------------------------------------------------------ Segway (implicit TB)
@@ -194,16 +196,31 @@ struct SegwayTB {
 #pragma unroll
 		for (int k = 0; k < 4; k++) Du[k] = K[k];
 	}
+	// sin/cos of theta and 2 theta are shared by f, g and their gradients: one sincos pair per evaluation point
+	static constexpr bool HAS_DYNAMICS_ALL = true;
+	__device__ static void dynamics_all(const double *x, double *f, double *g, double *Df, double *Dg)
+	{
+		double s1, c1, s2, c2;
+		sincos(x[2], &s1, &c1);
+		sincos(2.0 * x[2], &s2, &c2);
+		dynamics_core(x, s1, c1, s2, c2, f, g);
+		gradients_core(x, s1, c1, s2, c2, Df, Dg);
+	}
 	__device__ static void dynamics(const double *X, double *f, double *g)
+	{
+		double s1, c1, s2, c2;
+		sincos(X[2], &s1, &c1);
+		sincos(2.0 * X[2], &s2, &c2);
+		dynamics_core(X, s1, c1, s2, c2, f, g);
+	}
+	__device__ static void dynamics_core(const double *X, const double s1, const double c1, const double s2, const double c2,
+	                                     double *f, double *g)
 	{
 		// The friction term of the shipped model carries a literal factor 0.0 (:80), so every
 		// product with it is an exact zero; those terms are dropped (adding +-0.0 to a non-zero
 		// partial sum is the identity in IEEE arithmetic).
 		f[0] = X[1];
 		const double w2 = X[3] * X[3];
-		double s1, c1, s2, c2;
-		sincos(X[2], &s1, &c1);
-		sincos(2.0 * X[2], &s2, &c2);
 		const double den = 1.0 / ((14.553176960783997 + -2.0831375273848773 * c2) + -0.59146430898882 * s2);
 		f[1] = 0.0975 *
 		       (((((((44.798 *
@@ -237,6 +254,11 @@ struct SegwayTB {
 		double s1, c1, s2, c2;
 		sincos(x[2], &s1, &c1);
 		sincos(x[2] * 2.0, &s2, &c2);
+		gradients_core(x, s1, c1, s2, c2, Df, Dg);
+	}
+	__device__ static void gradients_core(const double *x, const double s1, const double c1, const double s2, const double c2,
+	                                      double *Df, double *Dg)
+	{
 		const double w2 = x[3] * x[3];
 		const double th = tanh(x[1] * 1000.0);
 		const double th2 = th * th;
@@ -358,6 +380,20 @@ struct InvertedPendulumImplicit {
 	{
 		Df[0] = 0.;        Df[2] = 1.;
 		Df[1] = cos(x[0]); Df[3] = 0.;
+		Dg[0] = Dg[1] = Dg[2] = Dg[3] = 0.0;
+	}
+	// sin x0 (drift) and cos x0 (its gradient) share one argument reduction
+	static constexpr bool HAS_DYNAMICS_ALL = true;
+	__device__ static void dynamics_all(const double *x, double *f, double *g, double *Df, double *Dg)
+	{
+		double s, c;
+		sincos(x[0], &s, &c);
+		f[0] = x[1];
+		f[1] = s;
+		g[0] = 0.;
+		g[1] = 1.;
+		Df[0] = 0.; Df[2] = 1.;
+		Df[1] = c;  Df[3] = 0.;
 		Dg[0] = Dg[1] = Dg[2] = Dg[3] = 0.0;
 	}
 	__device__ static void dynamics_with_gradient(const double *, const double *, double *, double *, double *) {}

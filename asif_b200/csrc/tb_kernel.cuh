@@ -27,6 +27,9 @@
 namespace asifb {
 
 constexpr int TB_THREADS = 128;
+#ifndef ASIF_TB_MINBLOCKS_NX4
+#define ASIF_TB_MINBLOCKS_NX4 2
+#endif
 #ifndef ASIF_TB_MINBLOCKS_NX2
 #define ASIF_TB_MINBLOCKS_NX2 6 // 80 registers: 24 warps/SM; measured 5.41 ms vs 6.23 ms at 4 (16 warps/SM) for 1e7 C2 states
 #endif
@@ -476,7 +479,7 @@ __device__ __forceinline__ int32_t tb_filter_one(const TbParams &p, const double
 template <class M>
 __host__ __device__ constexpr int tb_min_blocks()
 {
-	return M::NX <= 2 ? ASIF_TB_MINBLOCKS_NX2 : 2;
+	return M::NX <= 2 ? ASIF_TB_MINBLOCKS_NX2 : ASIF_TB_MINBLOCKS_NX4;
 }
 
 template <class M, int NPBTSS, bool WITH_DIAG, int SATMODE>
