@@ -651,6 +651,7 @@ int32_t oracle_realizable_filter(const double *opts, const double *x, const doub
 typedef struct {
 	int cfg;
 	const oracle_model *md;
+	oracle_model md_copy; /* model with overridden input bounds */
 	tb_options tb;
 	int N;
 	double relaxLb, relaxCost, pMin, pMax;
@@ -683,6 +684,12 @@ static int make_ctx(int cfg, const double *opts, int n_opts, ctx_t *c)
 		if (cfg == ORACLE_CFG_SEGWAY_TB && opts && n_opts >= 10) variant = (opts[9] == 0.0);
 		if (cfg == ORACLE_CFG_DI_IMPLICIT_TB && opts && n_opts >= 10) variant = (opts[9] != 0.0);
 		c->md = oracle_get_model(cfg, variant);
+		if (c->md && opts && n_opts >= 12) { /* initialize(lb, ub) with other bounds than the example's: opts[10], opts[11] */
+			c->md_copy = *c->md;
+			c->md_copy.lb[0] = opts[10];
+			c->md_copy.ub[0] = opts[11];
+			c->md = &c->md_copy;
+		}
 		tb_parse_options(cfg, opts, n_opts, &c->tb);
 		c->N = tb_npbt(&c->tb);
 		c->n_relax = 1;

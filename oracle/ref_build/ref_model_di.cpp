@@ -103,7 +103,12 @@ struct DiTb : RefFilter {
 		o.relaxTTS = 5.0;
 		o.relaxMinOrtho = 5.0;
 		ref_tb_options(opts, n_opts, o);
-		f.initialize(ex_di_tb::lb, ex_di_tb::ub, o);
+		double lb[1] = {ex_di_tb::lb[0]}, ub[1] = {ex_di_tb::ub[0]};
+		if (opts && n_opts >= 12) { /* initialize(lb, ub) with other input bounds: opts[10], opts[11] */
+			lb[0] = opts[10];
+			ub[0] = opts[11];
+		}
+		f.initialize(lb, ub, o);
 		nx = 2; nu = 1; n_relax = 1; nc = 18; nv = 2; n_diag = 4 + 4 + nc * nv + nc;
 	}
 	int32_t filter(const double *x, const double *u_des, double *u_act, double *relax, double *diag) override

@@ -1,0 +1,47 @@
+"""Option / bound variants of the TB filter that exercise every saturation mode of the kernel (identity, power-of-two
+scale, general division), wide bevels (satSharpness), horizons, dt, cost weights.  CUDA vs oracle; B200 box."""
+import numpy as np
+import pytest
+
+import conftest as cf
+
+pytestmark = pytest.mark.gpu
+
+VARIANTS = [
+    # (lb, ub, overrides of C2_TB_OPTS by index)
+    ((-1.0, 1.0), {}),                               # SAT_IDENTITY
+    ((-2.0, 2.0), {}),                               # SAT_POW2 (range 4)
+    ((-0.5, 0.5), {8: 0.5}),                         # SAT_POW2 (range 1), wider bevel
+    ((-0.7, 1.1), {8: 1.0}),                         # SAT_GENERAL, asymmetric bounds, bevel radius 1
+    ((-1.0, 1.0), {8: 1.7}),                         # bevel radius close to the clamp of updateOptions (2)
+    ((-1.0, 1.0), {4: 3.0, 6: 0.05, 5: 0.05}),       # horizon 3, dt 0.05, extend 5 %: npBT = 64
+    ((-3.0, 3.0), {0: 5.0, 1: 2.0, 2: 30.0, 3: 60.0, 7: 0.001}),  # segway-like weights on the double integrator
+]
+
+
+@pytest.fixture(scope="module")
+def ab():
+    import asif_b200
+    if asif_b200.device_count() < 1:
+        pytest.fail("no CUDA device: the engine has no CPU fallback")
+    return asif_b200
+
+
+@pytest.mark.parametrize("case", range(len(VARIANTS)))
+def test_tb_option_variants(ab, oracle, case):
+    (lb, ub), over = VARIANTS[case]
+    opts = list(cf.C2_TB_OPTS)
+    for k, v in over.items():
+        opts[k] = v
+    n = 30_000
+    x, ud = cf.c2_inputs(n, seed=500 + case)
+    ud = ud * 1.5 * max(abs(lb), abs(ub))
+    eng = ab.Engine(ab.FILTER_IMPLICIT_TB, ab.MODEL_DOUBLE_INTEGRATOR_TB, lb=[lb], ub=[ub], **cf.tb_engine_kwargs(opts))
+    u, relax, rc, diag = eng.filter_batch(x, ud, want_diag=True)
+    u0, relax0, rc0, diag0 = oracle.filter_batch(2, x, ud, opts + [0.0, lb, ub], want_diag=True)
+    print("variant", case, "rc", dict(zip(*np.unique(rc0, return_counts=True))))
+    cf.assert_parity("variant %d" % case, (u, relax, rc), (u0, relax0, rc0))
+    m = rc0 == 1
+    assert m.sum() > 200
+    assert np.array_equal(diag[m][:, :3], diag0[m][:, :3]) and np.array_equal(diag[m][:, 4:], diag0[m][:, 4:])
+    assert u.min() >= lb and u.max() <= ub

@@ -36,3 +36,20 @@ def test_rollout_matches_reference(oracle, reflib):
     xo, uo, rco, ho = oracle.rollout(pyref.CFG_DI_IMPLICIT_TB, x0, ud, 40, 1e-3, cf.C2_TB_OPTS)
     assert np.array_equal(rcr, rco)
     assert np.abs(xr - xo).max() < 1e-9
+
+
+@pytest.mark.parametrize("lb,ub,sat", [(-2.0, 2.0, 0.1), (-0.7, 1.1, 1.0), (-1.0, 1.0, 1.7)])
+def test_tb_other_bounds_and_sharpness(oracle, reflib, lb, ub, sat):
+    """initialize(lb, ub) with bounds other than the example's and wide saturation bevels."""
+    opts = list(cf.C2_TB_OPTS) + [0.0, lb, ub]
+    opts[8] = sat
+    x, ud = cf.c2_inputs(1200, seed=int(abs(lb) * 10))
+    ud = ud * 2
+    f = reflib.create(pyref.CFG_DI_IMPLICIT_TB, opts)
+    u0, relax0, rc0, diag0, st0, it0 = f.filter_batch_ex(x, ud)
+    u, relax, rc, diag = oracle.filter_batch(pyref.CFG_DI_IMPLICIT_TB, x, ud, opts, want_diag=True)
+    k = ~cf.unpinned_mask(rc0, rc, relax, st0)
+    assert k.mean() > 0.98
+    cf.assert_parity("bounds", (u[k], relax[k], rc[k]), (u0[k], relax0[k], rc0[k]))
+    m = k & (rc0 == 1)
+    assert np.array_equal(diag[m], diag0[m])
