@@ -37,7 +37,7 @@ enum : int {
 // 0.0 or 1.0 for every state.  The kernels skip the multiplications by such entries; for finite
 // operands this cannot change an IEEE result (x*0 = +-0, acc + +-0 = acc, 1*x = x) except for the
 // sign of an exact zero.  PG = general (no assumption).
-enum : int { PZ = 0, P1 = 1, PG = 2 };
+enum : int { PZ = 0, P1 = 1, PG = 2, PM1 = 3 }; // PM1: the literal -1.0 (only used for the safety-set Jacobian)
 
 // Options of ASIFimplicitTB (include/asif_implicit_tb.h:19-33) + what initialize() derives from them
 // (src/asif_implicit_tb.cpp:169-223).
@@ -208,6 +208,66 @@ __device__ __forceinline__ void sensitivity_rhs(const double *DfCL, const double
 			}
 			Qd[r + c * NX] = acc;
 		}
+}
+
+// Safety rows of one critical point (src/asif_implicit_tb.cpp:567-585, :643-653): h_j, Dh_row = DhSS(x_i) Q_i,
+// Lfh_j = Dh_row f, Lgh_j = Dh_row g.  xs = [x_i; Q_i] (column-major Q), f, g = open-loop dynamics at the CURRENT state.
+// Structural patterns of DhSS (dhs_pat), f (f_pat) and g (g_pat) remove the products with literal 0 / +-1 entries;
+// what remains is evaluated in the reference's order.
+template <class M>
+__device__ __forceinline__ void safety_point_rows(const double *xs, const double *f, const double *g, double *hs, double *lf,
+                                                  double *lg /* [NPSS][NU] */)
+{
+	constexpr int NX = M::NX, NU = M::NU, NPSS = M::NPSS;
+	double Dhs[NPSS * NX];
+	M::safety_set(xs, hs, Dhs);
+#pragma unroll
+	for (int j = 0; j < NPSS; j++) {
+		double dh[NX];
+		bool dhz[NX]; // structurally zero
+#pragma unroll
+		for (int cc = 0; cc < NX; cc++) {
+			bool have = false;
+			double acc = 0.0;
+#pragma unroll
+			for (int m = 0; m < NX; m++) {
+				const int pt = M::dhs_pat(j + m * NPSS);
+				if (pt == PZ) continue;
+				const double q = xs[NX + m + cc * NX];
+				const double t = (pt == P1) ? q : ((pt == PM1) ? -q : Dhs[j + m * NPSS] * q);
+				acc = have ? acc + t : t;
+				have = true;
+			}
+			dh[cc] = acc;
+			dhz[cc] = !have;
+		}
+		{
+			bool have = false;
+			double acc = 0.0;
+#pragma unroll
+			for (int m = 0; m < NX; m++) {
+				if (dhz[m] || M::f_pat(m) == PZ) continue;
+				const double t = dh[m] * f[m];
+				acc = have ? acc + t : t;
+				have = true;
+			}
+			lf[j] = acc;
+		}
+#pragma unroll
+		for (int i = 0; i < NU; i++) {
+			bool have = false;
+			double acc = 0.0;
+#pragma unroll
+			for (int m = 0; m < NX; m++) {
+				const int pg = M::g_pat(m + i * NX);
+				if (dhz[m] || pg == PZ) continue;
+				const double t = (pg == P1) ? dh[m] : dh[m] * g[m + i * NX];
+				acc = have ? acc + t : t;
+				have = true;
+			}
+			lg[j * NU + i] = acc;
+		}
+	}
 }
 
 } // namespace asifb

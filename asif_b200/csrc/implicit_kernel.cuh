@@ -43,33 +43,17 @@ struct ImpRows {
 
 	__device__ __forceinline__ void point_rows(const int slot, double (&n)[NPSS][NV], double (&rhs)[NPSS]) const
 	{
-		double xs[NS], hs[NPSS], Dhs[NPSS * NX];
+		double xs[NS], hs[NPSS], lf[NPSS], lg[NPSS * NU];
 #pragma unroll
 		for (int e = 0; e < NS; e++) xs[e] = snap[(slot * NS + e) * T];
-		M::safety_set(xs, hs, Dhs);
+		safety_point_rows<M>(xs, f, g, hs, lf, lg);
 #pragma unroll
 		for (int j = 0; j < NPSS; j++) {
-			double dh[NX];
 #pragma unroll
-			for (int cc = 0; cc < NX; cc++) {
-				double acc = Dhs[j] * xs[NX + cc * NX];
-#pragma unroll
-				for (int m = 1; m < NX; m++) acc = acc + Dhs[j + m * NPSS] * xs[NX + m + cc * NX];
-				dh[cc] = acc;
-			}
-			double lf = dh[0] * f[0];
-#pragma unroll
-			for (int m = 1; m < NX; m++) lf = lf + dh[m] * f[m];
-#pragma unroll
-			for (int i = 0; i < NU; i++) {
-				double lg = dh[0] * g[i * NX];
-#pragma unroll
-				for (int m = 1; m < NX; m++) lg = lg + dh[m] * g[m + i * NX];
-				n[j][i] = lg;
-			}
+			for (int i = 0; i < NU; i++) n[j][i] = lg[j * NU + i];
 			n[j][NU] = hs[j];
 			n[j][NU + 1] = 0.0;
-			rhs[j] = -lf;
+			rhs[j] = -lf[j];
 		}
 	}
 	__device__ __forceinline__ void bound_row(const int k, double (&n)[NV], double &rhs) const

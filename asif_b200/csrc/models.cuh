@@ -63,6 +63,12 @@ struct DoubleIntegratorTB {
 		constexpr int t[2] = {2, 0};
 		return t[i];
 	}
+	// DhSS column-major {-1,1,0,0 | 0,0,1,-1}
+	__host__ __device__ static constexpr int dhs_pat(int i)
+	{
+		constexpr int t[8] = {3, 1, 0, 0, 0, 0, 1, 3};
+		return t[i];
+	}
 	// min_j h_j(x) without forming the four values: min(1-x, x+1) = 1-|x| and rounding is monotone, so
 	// min_j h_j = 1 - max(|x0|, |x1|) with the same bits as the reference's min_element over h
 	static constexpr bool HAS_SAFETY_MIN = true;
@@ -143,6 +149,12 @@ struct SegwayTB {
 	__host__ __device__ static constexpr int f_pat(int i)
 	{
 		constexpr int t[4] = {2, 2, 2, 2};
+		return t[i];
+	}
+	// DhSS = diag(-2 x_i)
+	__host__ __device__ static constexpr int dhs_pat(int i)
+	{
+		constexpr int t[16] = {2, 0, 0, 0, 0, 2, 0, 0, 0, 0, 2, 0, 0, 0, 0, 2};
 		return t[i];
 	}
 	static constexpr bool HAS_SAFETY_MIN = false;
@@ -339,6 +351,12 @@ struct InvertedPendulumImplicit {
 	__host__ __device__ static constexpr int f_pat(int i)
 	{
 		constexpr int t[2] = {2, 2};
+		return t[i];
+	}
+	// DhSS column-major {-1,1,0,0 | 0,0,1,-1}
+	__host__ __device__ static constexpr int dhs_pat(int i)
+	{
+		constexpr int t[8] = {3, 1, 0, 0, 0, 0, 1, 3};
 		return t[i];
 	}
 	// box +-pi on both components: min_j h_j = pi - max(|x0|, |x1|), same bits as min_element over h
