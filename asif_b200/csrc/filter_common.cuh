@@ -80,24 +80,21 @@ __device__ __forceinline__ void input_saturate_soft(const SoftSat &s, int i, dou
 	else if (SATMODE == SAT_POW2) uc = (u - middle) * s.uc_scale_exact[i];
 	else uc = 2 * (u - middle) / range;
 	const double a = fabs(uc);
-	uSat = u; // |uc| <= bevelStart (or NaN): pass through
-	DuSat = 1;
-	if (a >= s.bevelStop) {
-		uSat = (uc > 0) ? ub : lb;
-		DuSat = 0;
-	} else if (a <= s.bevelStart || !(a > s.bevelStart)) {
-	} else if (uc > s.bevelStart) {
-		const double d = uc - s.bevelStop;
+	// clamp and pass-through legs as selects (no branch, no register shuffling between the legs) ...
+	const bool sat = a >= s.bevelStop;
+	const bool bevel = !sat && (a > s.bevelStart); // false for NaN: pass through, as the reference's last else
+	const double bound = (uc > 0) ? ub : lb;
+	uSat = sat ? bound : u;
+	DuSat = sat ? 0.0 : 1.0;
+	// ... the circular bevel (sqrt + division) is rare: a real branch, entered only by the lanes that need it
+	if (bevel) {
+		// uc > bevelStart: d = uc - Xc ; uc < -bevelStart: d = uc + Xc.  (uc -+ Xc)^2 is even in the sign flip,
+		// so both legs of the reference share sq; the signs below reproduce each leg's expressions exactly.
+		const double d = (uc > 0) ? (uc - s.bevelStop) : (uc + s.bevelStop);
 		const double sq = sqrt(s.r2 - d * d);
-		uSat = sq + s.bevelYc;
-		DuSat = (s.bevelStop - uc) / sq;
-		uSat = 0.5 * uSat * range + middle;
-	} else if (uc < -s.bevelStart) {
-		const double d = uc + s.bevelStop;
-		const double sq = sqrt(s.r2 - d * d);
-		uSat = -sq - s.bevelYc;
-		DuSat = (s.bevelStop + uc) / sq;
-		uSat = 0.5 * uSat * range + middle;
+		const double y = (uc > 0) ? (sq + s.bevelYc) : (-sq - s.bevelYc);
+		DuSat = ((uc > 0) ? (s.bevelStop - uc) : (s.bevelStop + uc)) / sq;
+		uSat = 0.5 * y * range + middle;
 	}
 }
 
