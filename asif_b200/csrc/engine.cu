@@ -879,13 +879,77 @@ extern "C" int32_t asif_qp_solve_batch(int32_t device, int32_t nv, int32_t nc, i
 	double *dsol = sol;
 	int32_t *dstatus = status;
 	void *scratch = nullptr;
+	if (mem == ASIF_MEM_HOST && n <= 8) {
+		// Latency path (the QPWrapper interface solves ONE problem per call): the problem is packed into a
+		// pinned, device-mapped buffer which the kernel reads and writes directly - one launch and one
+		// synchronisation, no cudaMemcpy at all.
+		static thread_local void *tl_pin = nullptr;
+		static thread_local size_t tl_pin_cap = 0;
+		const size_t sH = (shH ? 1 : n) * (size_t)nv * nv, sc = (size_t)n * nv, sA = (size_t)n * nc * nv, sb = (size_t)n * nc;
+		const size_t sB = (shB ? 1 : n) * (size_t)nv, ssol = (size_t)n * nv;
+		const size_t bytes = (sH + sc + sA + sb + 2 * sB + ssol) * sizeof(double) + (size_t)n * sizeof(int32_t) + (be ? (size_t)nc : 0) + 64;
+		if (bytes > tl_pin_cap) {
+			if (tl_pin) cudaFreeHost(tl_pin);
+			tl_pin = nullptr;
+			tl_pin_cap = 0;
+			const size_t want = bytes < (1u << 16) ? (1u << 16) : bytes;
+			CUDA_TRY(cudaHostAlloc(&tl_pin, want, cudaHostAllocMapped | cudaHostAllocPortable));
+			tl_pin_cap = want;
+		}
+		double *p = (double *)tl_pin;
+		double *hH = p; p += sH;
+		double *hc = p; p += sc;
+		double *hA = p; p += sA;
+		double *hb = p; p += sb;
+		double *hlb = p; p += sB;
+		double *hub = p; p += sB;
+		double *hsol = p; p += ssol;
+		int32_t *hst = (int32_t *)p;
+		uint8_t *hbe = (uint8_t *)(hst + n);
+		memcpy(hH, H, sH * 8);
+		memcpy(hc, c, sc * 8);
+		if (nc) {
+			memcpy(hA, A, sA * 8);
+			memcpy(hb, b, sb * 8);
+		}
+		memcpy(hlb, lb, sB * 8);
+		memcpy(hub, ub, sB * 8);
+		if (be) memcpy(hbe, be, nc);
+		int r;
+		switch (nv) { // unified addressing: the mapped host pointers are valid device pointers
+		case 1: r = launch_qp<1>(n, nc, diagonal_cost, hH, hc, hA, hb, hlb, hub, be ? hbe : nullptr, hsol, hst, share_flags, st); break;
+		case 2: r = launch_qp<2>(n, nc, diagonal_cost, hH, hc, hA, hb, hlb, hub, be ? hbe : nullptr, hsol, hst, share_flags, st); break;
+		case 3: r = launch_qp<3>(n, nc, diagonal_cost, hH, hc, hA, hb, hlb, hub, be ? hbe : nullptr, hsol, hst, share_flags, st); break;
+		default: r = launch_qp<4>(n, nc, diagonal_cost, hH, hc, hA, hb, hlb, hub, be ? hbe : nullptr, hsol, hst, share_flags, st); break;
+		}
+		if (r) return r;
+		CUDA_TRY(cudaStreamSynchronize(st));
+		memcpy(sol, hsol, ssol * 8);
+		memcpy(status, hst, (size_t)n * sizeof(int32_t));
+		return ASIF_OK;
+	}
 	if (mem == ASIF_MEM_HOST) {
 		// one allocation, carved up; sizes in doubles
 		const size_t sH = (shH ? 1 : n) * (size_t)nv * nv, sc = (size_t)n * nv, sA = (size_t)n * nc * nv, sb = (size_t)n * nc;
 		const size_t sB = (shB ? 1 : n) * (size_t)nv, ssol = (size_t)n * nv;
 		const size_t nd = sH + sc + sA + sb + 2 * sB + ssol;
 		const size_t bytes = nd * sizeof(double) + (size_t)n * sizeof(int32_t) + (be ? (size_t)nc : 0) + 64;
-		CUDA_TRY(cudaMalloc(&scratch, bytes));
+		// per-thread, per-device scratch that only grows: the single-problem QPWrapper path (n = 1, one call per
+		// filter() of an unmodified reference user) must not pay a cudaMalloc / cudaFree per solve
+		{
+			static thread_local void *tl_buf[16] = {nullptr};
+			static thread_local size_t tl_cap[16] = {0};
+			const int slot = device & 15;
+			if (bytes > tl_cap[slot]) {
+				if (tl_buf[slot]) cudaFree(tl_buf[slot]);
+				tl_buf[slot] = nullptr;
+				tl_cap[slot] = 0;
+				const size_t want = bytes < (1u << 16) ? (1u << 16) : bytes;
+				CUDA_TRY(cudaMalloc(&tl_buf[slot], want));
+				tl_cap[slot] = want;
+			}
+			scratch = tl_buf[slot];
+		}
 		double *p = (double *)scratch;
 		double *hH = p; p += sH;
 		double *hc = p; p += sc;
@@ -904,7 +968,6 @@ extern "C" int32_t asif_qp_solve_batch(int32_t device, int32_t nv, int32_t nc, i
 		if (err == cudaSuccess) err = cudaMemcpyAsync(hub, ub, sB * 8, cudaMemcpyHostToDevice, st);
 		if (err == cudaSuccess && be) err = cudaMemcpyAsync(hbe, be, nc, cudaMemcpyHostToDevice, st);
 		if (err != cudaSuccess) {
-			cudaFree(scratch);
 			return fail(ASIF_ERR_CUDA, "qp_solve_batch H2D: %s", cudaGetErrorString(err));
 		}
 		dH = hH; dc = hc; dA = hA; db = hb; dlb = hlb; dub = hub;
@@ -926,7 +989,6 @@ extern "C" int32_t asif_qp_solve_batch(int32_t device, int32_t nv, int32_t nc, i
 			if (err == cudaSuccess) err = cudaMemcpyAsync(status, dstatus, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st);
 		}
 		cudaError_t e2 = cudaStreamSynchronize(st);
-		cudaFree(scratch);
 		if (r) return r;
 		if (err != cudaSuccess || e2 != cudaSuccess)
 			return fail(ASIF_ERR_CUDA, "qp_solve_batch D2H: %s", cudaGetErrorString(err != cudaSuccess ? err : e2));
