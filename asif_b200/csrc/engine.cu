@@ -431,10 +431,11 @@ int32_t asif_engine_create(const asif_engine_config *cfg, asif_engine **out)
 			delete e;
 			return fail(ASIF_ERR_UNSUPPORTED, "explicit filter: model %d not compiled in", cfg->model);
 		}
-		e->nc = npSS;
+		e->nc = (cfg->npSSmax > 0 && cfg->npSSmax < npSS) ? cfg->npSSmax : npSS; // npSSmax_ = min(npSSmax, npSS), nc_ = npSSmax_
 		e->n_diag = e->nc * e->nv + e->nc;
 		ExplicitParams &p = e->ex;
 		memset(&p, 0, sizeof(p));
+		p.npSSmax = e->nc;
 		for (int i = 0; i < nu; i++) {
 			p.lb[i] = cfg->lb[i];
 			p.ub[i] = cfg->ub[i];

@@ -17,8 +17,9 @@ struct RegRows {
 	// rows in shared memory [(NC)*(NV+1)][T]; bounds appended
 	const double *rows;
 	int stride;
+	int nc; // rows in use (npSSmax <= NC)
 	double lb[NV], ub[NV];
-	__device__ __forceinline__ int count() const { return NC + 2 * NV; }
+	__device__ __forceinline__ int count() const { return nc + 2 * NV; }
 	template <class F, class FB>
 	__device__ __forceinline__ void scan(F &&fn, FB &&) const
 	{
@@ -31,12 +32,12 @@ struct RegRows {
 	}
 	__device__ __forceinline__ void get(int j, double (&n)[NV], double &rhs) const
 	{
-		if (j < NC) {
+		if (j < nc) {
 #pragma unroll
 			for (int i = 0; i < NV; i++) n[i] = rows[(j * (NV + 1) + i) * stride];
 			rhs = rows[(j * (NV + 1) + NV) * stride];
 		} else {
-			const int k = j - NC;
+			const int k = j - nc;
 			const int var = k >> 1;
 			const bool upper = k & 1;
 			double bnd = 0.0;
@@ -73,8 +74,21 @@ explicit_filter_kernel(const ExplicitParams p, const int64_t n, const double *__
 	double h[NPSS], Dh[NPSS * NX], f[NX], g[NX * NU];
 	M::safety_set(x, h, Dh);
 	M::dynamics(x, f, g);
+	// optional row selection: the npSSmax smallest h, ascending, ties keep the lower index (src/asif.cpp:250-268;
+	// std::sort leaves tie order unspecified).  pos[j] = rank of safety function j.
+	const int ncUse = p.npSSmax;
+	int pos[NPSS];
 #pragma unroll
 	for (int j = 0; j < NPSS; j++) {
+		int r = 0;
+#pragma unroll
+		for (int q = 0; q < NPSS; q++) r += (h[q] < h[j] || (h[q] == h[j] && q < j)) ? 1 : 0;
+		pos[j] = (ncUse < NPSS) ? r : j;
+	}
+#pragma unroll
+	for (int jj = 0; jj < NPSS; jj++) {
+		const int j = jj; // safety function jj lands in row pos[jj] when it is among the selected ones
+		if (pos[jj] >= ncUse) continue;
 		// Lfh = Dh f, Lgh = Dh g (src/asif.cpp:276-285), A = [Lgh | h], b = -Lfh (:295-303)
 		double lf = Dh[j] * f[0];
 #pragma unroll
@@ -84,14 +98,15 @@ explicit_filter_kernel(const ExplicitParams p, const int64_t n, const double *__
 			double lg = Dh[j] * g[i * NX];
 #pragma unroll
 			for (int m = 1; m < NX; m++) lg = lg + Dh[j + m * NPSS] * g[m + i * NX];
-			rows[(j * (NV + 1) + i) * T] = lg;
+			rows[(pos[jj] * (NV + 1) + i) * T] = lg;
 		}
-		rows[(j * (NV + 1) + NU) * T] = h[j];
-		rows[(j * (NV + 1) + NV) * T] = -lf;
+		rows[(pos[jj] * (NV + 1) + NU) * T] = h[j];
+		rows[(pos[jj] * (NV + 1) + NV) * T] = -lf;
 	}
 	RegRows<NV, NC> R;
 	R.rows = rows;
 	R.stride = T;
+	R.nc = ncUse;
 	double c[NV], v[NV];
 	DiagMetric<NV> mt;
 #pragma unroll
@@ -125,11 +140,11 @@ explicit_filter_kernel(const ExplicitParams p, const int64_t n, const double *__
 			rc_out[k] = -1;
 		}
 		if (WITH_DIAG) {
-			constexpr int NDIAG = NC * NV + NC;
+			const int NDIAG = ncUse * NV + ncUse; // A_[nc*nv] column-major, b_[nc] with nc = npSSmax
 			double *d = diag + k * NDIAG;
-			for (int j = 0; j < NC; j++) {
-				for (int i = 0; i < NV; i++) d[j + i * NC] = rows[(j * (NV + 1) + i) * T];
-				d[NC * NV + j] = rows[(j * (NV + 1) + NV) * T];
+			for (int j = 0; j < ncUse; j++) {
+				for (int i = 0; i < NV; i++) d[j + i * ncUse] = rows[(j * (NV + 1) + i) * T];
+				d[ncUse * NV + j] = rows[(j * (NV + 1) + NV) * T];
 			}
 		}
 	}

@@ -58,6 +58,8 @@ struct ExplicitParams {
 	double lb[MAX_NU], ub[MAX_NU];
 	double relaxLb, relaxCost;
 	double gi[MAX_NV], gih[MAX_NV];
+	int32_t npSSmax; // rows kept (min(npSSmax, npSS), src/asif.cpp:21-22)
+	int32_t pad_;
 };
 
 // src/asif_implicit_tb.cpp:821-830

@@ -206,7 +206,11 @@ namespace ASIF
 				double inf = 1e20;
 			} Options; // include/asif.h:11-17
 
-			explicit FilterBatchExplicit(const Model model, const int32_t device = 0) : model_(model), device_(device) {}
+			// npSSmax as in the ASIF::ASIF constructor (include/asif.h:39-44): rows kept after sorting by h, default all
+			explicit FilterBatchExplicit(const Model model, const int32_t device = 0, const uint32_t npSSmax = (uint32_t)-1)
+			    : model_(model), device_(device), npSSmax_(npSSmax)
+			{
+			}
 			int32_t initialize(const double lb[], const double ub[]) { return initialize(lb, ub, Options()); }
 			int32_t initialize(const double lb[], const double ub[], const Options &options)
 			{
@@ -222,6 +226,7 @@ namespace ASIF
 				cfg.relaxLb = options.relaxLb;
 				cfg.relaxCost = options.relaxCost;
 				cfg.inf = options.inf;
+				cfg.npSSmax = (npSSmax_ > 0x7fffffffu) ? 0 : (int32_t)npSSmax_;
 				return create(cfg);
 			}
 			// src/asif.cpp:213-231 moves only the LOWER bound of the relax variable and leaves the upper
@@ -250,6 +255,7 @@ namespace ASIF
 		protected:
 			Model model_;
 			int32_t device_;
+			uint32_t npSSmax_;
 			Options options_;
 			double lb_, ub_;
 		};

@@ -445,18 +445,30 @@ static int32_t tb_filter(const oracle_model *md, const tb_options *o, int N, con
  * ASIF (explicit), src/asif.cpp:64-110 (initialize), :176-210 (filter), :233-312 (updateConstraints)
  * npSSmax = npSS (the default of every named config)
  * ---------------------------------------------------------------------------------------- */
-static int32_t explicit_filter(const oracle_model *md, double relaxLb, double relaxCost, const double *x,
+static int32_t explicit_filter(const oracle_model *md, double relaxLb, double relaxCost, int npSSmax, const double *x,
                                const double *uDes, double *uAct, double *relax, double *diag)
 {
-	const int nx = md->nx, nu = md->nu, npSS = md->npSS, nv = nu + 1, nc = npSS;
-	double h[16], Dh[16 * NX], f[NX], g[NX * NU], Lfh[16], Lgh[16 * NU];
-	md->safety_set(x, h, Dh);
+	const int nx = md->nx, nu = md->nu, npSS = md->npSS, nv = nu + 1;
+	const int nsel = (npSSmax > 0 && npSSmax < npSS) ? npSSmax : npSS, nc = nsel;
+	double hFull[16], DhFull[16 * NX], h[16], Dh[16 * NX], f[NX], g[NX * NU], Lfh[16], Lgh[16 * NU];
+	md->safety_set(x, hFull, DhFull);
 	md->dynamics(x, f, g);
-	mat_vec(Dh, npSS, nx, f, Lfh);
-	mat_mul(Dh, npSS, nx, g, nu, Lgh);
+	if (nsel < npSS) { /* :250-268: the npSSmax smallest h (std::sort; ties: lower index first here) */
+		int idx[16];
+		k_smallest(hFull, npSS, nsel, idx);
+		for (int i = 0; i < nsel; i++) {
+			h[i] = hFull[idx[i]];
+			for (int j = 0; j < nx; j++) Dh[i + j * nsel] = DhFull[idx[i] + j * npSS];
+		}
+	} else {
+		memcpy(h, hFull, sizeof(double) * npSS);
+		memcpy(Dh, DhFull, sizeof(double) * npSS * nx);
+	}
+	mat_vec(Dh, nsel, nx, f, Lfh);
+	mat_mul(Dh, nsel, nx, g, nu, Lgh);
 	double A[16 * ORACLE_QP_NVMAX], b[16];
-	for (int i = 0; i < npSS; i++) {
-		for (int j = 0; j < nu; j++) A[i + j * nc] = Lgh[i + j * npSS];
+	for (int i = 0; i < nsel; i++) {
+		for (int j = 0; j < nu; j++) A[i + j * nc] = Lgh[i + j * nsel];
 		A[i + nu * nc] = h[i];
 		b[i] = -Lfh[i];
 	}
@@ -484,7 +496,6 @@ static int32_t explicit_filter(const oracle_model *md, double relaxLb, double re
 	}
 	return -1;
 }
-
 
 /* ------------------------------------------------------------------------------------------
  * ASIFimplicit, src/asif_implicit.cpp:194-266 (initialize), :305-356 (filter), :403-611 (updateConstraints)
@@ -655,6 +666,7 @@ typedef struct {
 	tb_options tb;
 	int N;
 	double relaxLb, relaxCost, pMin, pMax;
+	int npSSmax;
 	imp_options imp;
 	double rz[8];
 	int nx, nu, n_relax, nc, nv, n_diag;
@@ -673,8 +685,9 @@ static int make_ctx(int cfg, const double *opts, int n_opts, ctx_t *c)
 			c->relaxLb = opts[0];
 			c->relaxCost = opts[1];
 		}
+		c->npSSmax = (opts && n_opts >= 3 && opts[2] > 0 && opts[2] < c->md->npSS) ? (int)opts[2] : c->md->npSS;
 		c->n_relax = 1;
-		c->nc = c->md->npSS;
+		c->nc = c->npSSmax;
 		c->nv = c->md->nu + 1;
 		c->n_diag = c->nc * c->nv + c->nc;
 		break;
@@ -760,7 +773,7 @@ static int32_t filter_one(const ctx_t *c, const double *x, const double *ud, dou
 {
 	switch (c->cfg) {
 	case ORACLE_CFG_DI_EXPLICIT:
-		return explicit_filter(c->md, c->relaxLb, c->relaxCost, x, ud, ua, relax, diag);
+		return explicit_filter(c->md, c->relaxLb, c->relaxCost, c->npSSmax, x, ud, ua, relax, diag);
 	case ORACLE_CFG_DI_IMPLICIT_TB:
 	case ORACLE_CFG_SEGWAY_TB:
 		return tb_filter(c->md, &c->tb, c->N, x, ud, ua, relax, diag);

@@ -20,7 +20,9 @@ struct AsifAccess : ASIF::ASIF {
 
 struct DiExplicit : RefFilter {
 	AsifAccess f;
-	DiExplicit(const double *opts, int n_opts) : f(ex_di::nx, ex_di::nu, ex_di::npSS, ex_di::safetySet, ex_di::dynamics)
+	static uint32_t sel(const double *opts, int n_opts) { return (opts && n_opts >= 3 && opts[2] > 0) ? (uint32_t)opts[2] : (uint32_t)-1; }
+	DiExplicit(const double *opts, int n_opts)
+	    : f(ex_di::nx, ex_di::nu, ex_di::npSS, ex_di::safetySet, ex_di::dynamics, sel(opts, n_opts)) /* opts[2] = npSSmax */
 	{
 		ASIF::ASIF::Options o; /* defaults: relaxLb 5, relaxCost 50 (include/asif.h:11-17) */
 		if (opts && n_opts >= 2) {
@@ -28,7 +30,9 @@ struct DiExplicit : RefFilter {
 			o.relaxCost = opts[1];
 		}
 		f.initialize(ex_di::lb, ex_di::ub, o);
-		nx = 2; nu = 1; n_relax = 1; nc = 4; nv = 2; n_diag = nc * nv + nc;
+		nx = 2; nu = 1; n_relax = 1; nv = 2;
+		nc = (sel(opts, n_opts) < 4) ? (int)sel(opts, n_opts) : 4;
+		n_diag = nc * nv + nc;
 	}
 	int32_t filter(const double *x, const double *u_des, double *u_act, double *relax, double *diag) override
 	{

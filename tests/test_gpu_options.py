@@ -45,3 +45,22 @@ def test_tb_option_variants(ab, oracle, case):
     assert m.sum() > 200
     assert np.array_equal(diag[m][:, :3], diag0[m][:, :3]) and np.array_equal(diag[m][:, 4:], diag0[m][:, 4:])
     assert u.min() >= lb and u.max() <= ub
+
+
+@pytest.mark.parametrize("npSSmax", [1, 2, 3, 7])
+def test_explicit_row_selection(ab, oracle, npSSmax):
+    """npSSmax < npSS: the npSSmax smallest-h rows, ascending (src/asif.cpp:250-268)."""
+    n = 50_000
+    x, ud = cf.c1_inputs(n, seed=90 + npSSmax)
+    x[: n // 10, 0] = np.round(x[: n // 10, 0], 1)  # exact ties between safety functions
+    x[: n // 10, 1] = x[: n // 10, 0]
+    opts = list(cf.C1_OPTS[:2]) + [float(npSSmax)]
+    eng = ab.Engine(ab.FILTER_EXPLICIT, ab.MODEL_DOUBLE_INTEGRATOR, relaxLb=opts[0], relaxCost=opts[1], npSSmax=npSSmax)
+    nc = min(npSSmax, 4)
+    assert eng.nc == nc and eng.n_diag == 3 * nc
+    u, relax, rc, diag = eng.filter_batch(x, ud, want_diag=True)
+    u0, relax0, rc0, diag0 = oracle.filter_batch(1, x, ud, opts, want_diag=True)
+    assert np.array_equal(diag, diag0)
+    cf.assert_parity("npSSmax", (u, relax, rc), (u0, relax0, rc0))
+    u2, relax2, rc2, _ = eng.filter_batch(x, ud)
+    assert np.array_equal(u2, u) and np.array_equal(rc2, rc)

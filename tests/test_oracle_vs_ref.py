@@ -53,3 +53,20 @@ def test_tb_other_bounds_and_sharpness(oracle, reflib, lb, ub, sat):
     cf.assert_parity("bounds", (u[k], relax[k], rc[k]), (u0[k], relax0[k], rc0[k]))
     m = k & (rc0 == 1)
     assert np.array_equal(diag[m], diag0[m])
+
+
+@pytest.mark.parametrize("npSSmax", [1, 2, 3, 9])
+def test_explicit_row_selection(oracle, reflib, npSSmax):
+    """ASIF::ASIF with npSSmax < npSS keeps the npSSmax smallest-h rows in ascending order (src/asif.cpp:21-22,250-268)."""
+    opts = list(cf.C1_OPTS[:2]) + [float(npSSmax)]
+    x, ud = cf.c1_inputs(2500, seed=70 + npSSmax)
+    f = reflib.create(pyref.CFG_DI_EXPLICIT, opts)
+    u0, relax0, rc0, diag0, st0, it0 = f.filter_batch_ex(x, ud)
+    u, relax, rc, diag = oracle.filter_batch(pyref.CFG_DI_EXPLICIT, x, ud, opts, want_diag=True)
+    nc = min(npSSmax, 4)
+    assert diag.shape[1] == nc * 2 + nc and diag0.shape == diag.shape
+    assert np.array_equal(diag, diag0)
+    cf.assert_parity("npSSmax", (u, relax, rc), (u0, relax0, rc0))
+    if nc < 4:  # selected h values (column 1 of A_) ascend
+        hsel = diag[:, nc:2 * nc]
+        assert np.all(np.diff(hsel, axis=1) >= 0)
