@@ -57,6 +57,8 @@ int64_t chunk_states()
 	return v;
 }
 
+constexpr int N_SNAP_BUFS = 6;
+
 struct Slot {
 	cudaStream_t stream = nullptr;
 	double *x = nullptr, *ud = nullptr, *ua = nullptr, *relax = nullptr, *diag = nullptr;
@@ -82,6 +84,17 @@ struct asif_engine {
 	cudaStream_t stream = nullptr; // device-memory calls without a caller stream
 	unsigned long long *d_counters = nullptr; // [0] qp rows processed, [1..8] rc histogram
 	uint64_t last_qp_rows = 0;
+	int num_sms = 148;
+	// snapshot scratch of the persistent nx = 4 kernels: a ring, so that launches on different streams never share
+	// a buffer that may still be in use (the next user waits on the previous user's event)
+	struct SnapBuf {
+		double *p = nullptr;
+		size_t cap = 0;
+		cudaEvent_t ev = nullptr;
+		cudaStream_t last = nullptr;
+		bool used = false;
+	} snapbuf[N_SNAP_BUFS];
+	int snap_next = 0;
 };
 
 namespace {
@@ -148,25 +161,97 @@ int set_smem(K kernel, size_t bytes)
 }
 
 // ---- kernel dispatch -------------------------------------------------------------------------
+// Launch geometry of the TB kernels.  nx = 2: one CTA per tile of TB_THREADS states, snapshots in shared memory.
+// nx = 4: persistent grid over a global snapshot scratch; the grid is the largest one that fits the SMs, shrunk so
+// that every CTA runs the same number of tiles (no ragged last wave).
+template <class M, int NPBTSS>
+int tb_geometry(asif_engine *e, int64_t n, cudaStream_t st, unsigned &blocks, size_t &smem, double *&gsnap, int &buf)
+{
+	const int64_t tiles = (n + TB_THREADS - 1) / TB_THREADS;
+	const size_t per_cta = sizeof(double) * tb_smem_doubles_per_thread<M, NPBTSS>() * TB_THREADS;
+	gsnap = nullptr;
+	buf = -1;
+	if (!tb_global_snapshots<M>()) {
+		blocks = (unsigned)tiles;
+		smem = per_cta;
+		return ASIF_OK;
+	}
+	const int64_t resident = (int64_t)e->num_sms * tb_min_blocks<M>();
+	const int64_t rounds = (tiles + resident - 1) / resident;
+	blocks = (unsigned)((tiles + rounds - 1) / rounds);
+	if (blocks < 1) blocks = 1;
+	smem = 0;
+	const size_t need = sizeof(double) * TB_SCRATCH_HEADER + per_cta * (size_t)resident;
+	// pick a scratch buffer: one last used on this same stream (stream order protects it), else an idle one, else an
+	// unallocated one, else the next in the ring after waiting for its last user
+	int pick = -1;
+	for (int i = 0; i < N_SNAP_BUFS && pick < 0; i++) {
+		asif_engine::SnapBuf &c = e->snapbuf[i];
+		if (c.p && c.cap >= need && c.used && c.last == st) pick = i;
+	}
+	for (int i = 0; i < N_SNAP_BUFS && pick < 0; i++) {
+		asif_engine::SnapBuf &c = e->snapbuf[i];
+		if (c.p && c.cap >= need && (!c.used || cudaEventQuery(c.ev) == cudaSuccess)) {
+			c.used = false;
+			pick = i;
+		}
+	}
+	for (int i = 0; i < N_SNAP_BUFS && pick < 0; i++)
+		if (!e->snapbuf[i].p) pick = i;
+	if (pick < 0) {
+		pick = e->snap_next;
+		e->snap_next = (e->snap_next + 1) % N_SNAP_BUFS;
+	}
+	buf = pick;
+	asif_engine::SnapBuf &b = e->snapbuf[buf];
+	if (b.cap < need) {
+		if (b.p) CUDA_TRY(cudaFree(b.p)); // synchronises with any kernel still using it
+		b.p = nullptr;
+		b.cap = 0;
+		b.used = false;
+		CUDA_TRY(cudaMalloc(&b.p, need));
+		b.cap = need;
+	}
+	if (!b.ev) CUDA_TRY(cudaEventCreateWithFlags(&b.ev, cudaEventDisableTiming));
+	if (b.used && b.last != st) CUDA_TRY(cudaStreamWaitEvent(st, b.ev, 0));
+	CUDA_TRY(cudaMemsetAsync(b.p, 0, sizeof(double) * TB_SCRATCH_HEADER, st)); // tile counter
+	gsnap = b.p;
+	return ASIF_OK;
+}
+
+int tb_release(asif_engine *e, int buf, cudaStream_t st)
+{
+	if (buf >= 0) {
+		CUDA_TRY(cudaEventRecord(e->snapbuf[buf].ev, st));
+		e->snapbuf[buf].used = true;
+		e->snapbuf[buf].last = st;
+	}
+	return ASIF_OK;
+}
+
 template <class M, int NPBTSS, int SATMODE>
 int launch_tb_mode(asif_engine *e, int64_t n, const double *x, const double *ud, double *ua, double *relax, int32_t *rc,
                    double *diag, cudaStream_t st)
 {
-	const size_t smem = sizeof(double) * tb_smem_doubles_per_thread<M, NPBTSS>() * TB_THREADS;
-	const unsigned blocks = (unsigned)((n + TB_THREADS - 1) / TB_THREADS);
+	unsigned blocks;
+	size_t smem;
+	double *gsnap;
+	int buf;
+	int r = tb_geometry<M, NPBTSS>(e, n, st, blocks, smem, gsnap, buf);
+	if (r) return r;
 	if (diag) {
 		auto k = tb_filter_kernel<M, NPBTSS, true, SATMODE>;
-		int r = set_smem(k, smem);
+		r = set_smem(k, smem);
 		if (r) return r;
-		k<<<blocks, TB_THREADS, smem, st>>>(e->tb, n, x, ud, ua, relax, rc, diag, e->d_counters);
+		k<<<blocks, TB_THREADS, smem, st>>>(e->tb, n, x, ud, ua, relax, rc, diag, e->d_counters, gsnap);
 	} else {
 		auto k = tb_filter_kernel<M, NPBTSS, false, SATMODE>;
-		int r = set_smem(k, smem);
+		r = set_smem(k, smem);
 		if (r) return r;
-		k<<<blocks, TB_THREADS, smem, st>>>(e->tb, n, x, ud, ua, relax, rc, nullptr, e->d_counters);
+		k<<<blocks, TB_THREADS, smem, st>>>(e->tb, n, x, ud, ua, relax, rc, nullptr, e->d_counters, gsnap);
 	}
 	CUDA_TRY(cudaGetLastError());
-	return ASIF_OK;
+	return tb_release(e, buf, st);
 }
 
 // SAT_POW2 and SAT_IDENTITY are exact shortcuts of SAT_GENERAL; IDENTITY is only instantiated for the nx = 2 models
@@ -271,14 +356,18 @@ template <class M, int NPBTSS>
 int launch_tb_rollout(asif_engine *e, int64_t n, int32_t steps, double dt, double *x, const double *ud, double *ua,
                       int32_t *rc, cudaStream_t st)
 {
-	const size_t smem = sizeof(double) * tb_smem_doubles_per_thread<M, NPBTSS>() * TB_THREADS;
-	const unsigned blocks = (unsigned)((n + TB_THREADS - 1) / TB_THREADS);
-	auto k = (e->tb.sat_mode >= SAT_POW2) ? tb_rollout_kernel<M, NPBTSS, SAT_POW2> : tb_rollout_kernel<M, NPBTSS, SAT_GENERAL>;
-	int r = set_smem(k, smem);
+	unsigned blocks;
+	size_t smem;
+	double *gsnap;
+	int buf;
+	int r = tb_geometry<M, NPBTSS>(e, n, st, blocks, smem, gsnap, buf);
 	if (r) return r;
-	k<<<blocks, TB_THREADS, smem, st>>>(e->tb, n, steps, dt, x, ud, ua, rc, e->d_counters + 1, e->d_counters);
+	auto k = (e->tb.sat_mode >= SAT_POW2) ? tb_rollout_kernel<M, NPBTSS, SAT_POW2> : tb_rollout_kernel<M, NPBTSS, SAT_GENERAL>;
+	r = set_smem(k, smem);
+	if (r) return r;
+	k<<<blocks, TB_THREADS, smem, st>>>(e->tb, n, steps, dt, x, ud, ua, rc, e->d_counters + 1, e->d_counters, gsnap);
 	CUDA_TRY(cudaGetLastError());
-	return ASIF_OK;
+	return tb_release(e, buf, st);
 }
 
 int launch_rollout(asif_engine *e, int64_t n, int32_t steps, double dt, double *x, const double *ud, double *ua,
@@ -411,6 +500,7 @@ int32_t asif_engine_create(const asif_engine_config *cfg, asif_engine **out)
 	asif_engine *e = new (std::nothrow) asif_engine();
 	if (!e) return fail(ASIF_ERR_INVALID_ARGUMENT, "out of host memory");
 	e->cfg = *cfg;
+	if (cudaDeviceGetAttribute(&e->num_sms, cudaDevAttrMultiProcessorCount, cfg->device) != cudaSuccess || e->num_sms <= 0) e->num_sms = 148;
 	int npSS;
 	model_dims(cfg->model, e->nx, e->nu, npSS);
 	e->nv = e->nu + 1;
@@ -722,6 +812,10 @@ int32_t asif_engine_destroy(asif_engine *e)
 		cudaStreamDestroy(e->stream);
 	}
 	cudaFree(e->d_counters);
+	for (auto &b : e->snapbuf) {
+		if (b.p) cudaFree(b.p);
+		if (b.ev) cudaEventDestroy(b.ev);
+	}
 	cudaFree(e->d_table);
 	cudaFree(e->d_kernel);
 	cudaFree(e->d_ttable);

@@ -28,7 +28,7 @@ namespace asifb {
 
 constexpr int TB_THREADS = 128;
 #ifndef ASIF_TB_MINBLOCKS_NX4
-#define ASIF_TB_MINBLOCKS_NX4 2
+#define ASIF_TB_MINBLOCKS_NX4 4 // 128 registers, 16 warps/SM (snapshots in global scratch); 13.2 ms vs 16.5 ms at 2 for 1e6 C5 states
 #endif
 #ifndef ASIF_TB_MINBLOCKS_NX2
 #define ASIF_TB_MINBLOCKS_NX2 6 // 80 registers: 24 warps/SM; measured 5.41 ms vs 6.23 ms at 4 (16 warps/SM) for 1e7 C2 states
@@ -466,22 +466,31 @@ __host__ __device__ constexpr int tb_min_blocks()
 	return M::NX <= 2 ? ASIF_TB_MINBLOCKS_NX2 : ASIF_TB_MINBLOCKS_NX4;
 }
 
+// Where the critical-point snapshots live.  nx = 2: shared memory (30 doubles per thread).  nx = 4: 100 doubles per
+// thread would cap the SM at 8 warps, and the FP64 pipe then idles on dependent-issue latency (ncu: issue slots 54 %
+// busy); the snapshots are written only when a point enters the running k-smallest list and read only by the QP, so
+// they go to a global scratch sized for the resident grid (L2 resident) and the kernel becomes persistent:
+// 16 warps/SM, measured 16.5 -> 13.2 ms for 1e6 segway states.
+constexpr int TB_SCRATCH_HEADER = 16; // doubles in front of the snapshot scratch: [0] = tile counter (zeroed per launch)
+
+template <class M>
+__host__ __device__ constexpr bool tb_global_snapshots()
+{
+	return M::NX > 2;
+}
+
 template <class M, int NPBTSS, bool WITH_DIAG, int SATMODE>
-__global__ void __launch_bounds__(TB_THREADS, tb_min_blocks<M>())
-tb_filter_kernel(const TbParams p, const int64_t n, const double *__restrict__ x_in, const double *__restrict__ u_des,
-                 double *__restrict__ u_act, double *__restrict__ relax_out, int32_t *__restrict__ rc_out,
-                 double *__restrict__ diag, unsigned long long *__restrict__ qp_iter_sum)
+__device__ __forceinline__ void tb_filter_tile(const TbParams &p, const int64_t n, const int64_t k, double *snap, const int T,
+                                               const double *__restrict__ x_in, const double *__restrict__ u_des,
+                                               double *__restrict__ u_act, double *__restrict__ relax_out,
+                                               int32_t *__restrict__ rc_out, double *__restrict__ diag,
+                                               unsigned long long *__restrict__ qp_iter_sum)
 {
 	constexpr int NX = M::NX, NU = M::NU, NPSS = M::NPSS;
 	constexpr int NC = NPBTSS * NPSS + 2;
 	constexpr int NV = NU + 1;
 	constexpr int NDIAG = TbDiagLayout<NPBTSS>::HEAD + NC * NV + NC;
 
-	extern __shared__ double smem[];
-	const int T = blockDim.x;
-	double *snap = smem + threadIdx.x; // [(NPBTSS+1)*NS][T]
-
-	const int64_t k = (int64_t)blockIdx.x * T + threadIdx.x;
 	const bool live = k < n;
 	const int64_t kk = live ? k : (n - 1); // tail lanes redo the last state and do not store
 
@@ -534,19 +543,65 @@ tb_filter_kernel(const TbParams p, const int64_t n, const double *__restrict__ x
 	}
 }
 
+// gsnap: global snapshot scratch, gridDim.x * tb_smem_doubles_per_thread * blockDim.x doubles (nx = 4 models), else unused
+template <class M, int NPBTSS, bool WITH_DIAG, int SATMODE>
+__global__ void __launch_bounds__(TB_THREADS, tb_min_blocks<M>())
+tb_filter_kernel(const TbParams p, const int64_t n, const double *__restrict__ x_in, const double *__restrict__ u_des,
+                 double *__restrict__ u_act, double *__restrict__ relax_out, int32_t *__restrict__ rc_out,
+                 double *__restrict__ diag, unsigned long long *__restrict__ qp_iter_sum, double *__restrict__ gsnap)
+{
+	const int T = blockDim.x;
+	if (tb_global_snapshots<M>()) {
+		// persistent: every warp pulls tiles of 32 states from a counter that lives in front of the scratch
+		unsigned long long *next_tile = reinterpret_cast<unsigned long long *>(gsnap);
+		double *snap = gsnap + TB_SCRATCH_HEADER + (int64_t)blockIdx.x * tb_smem_doubles_per_thread<M, NPBTSS>() * T + threadIdx.x;
+		for (;;) {
+			unsigned long long tile = 0;
+			if ((threadIdx.x & 31) == 0) tile = atomicAdd(next_tile, 1ull);
+			tile = __shfl_sync(0xffffffffu, tile, 0);
+			if ((int64_t)tile * 32 >= n) break;
+			tb_filter_tile<M, NPBTSS, WITH_DIAG, SATMODE>(p, n, (int64_t)tile * 32 + (threadIdx.x & 31), snap, T, x_in, u_des, u_act,
+			                                              relax_out, rc_out, diag, qp_iter_sum);
+		}
+	} else {
+		extern __shared__ double smem[];
+		double *snap = smem + threadIdx.x; // [(NPBTSS+1)*NS][T]
+		tb_filter_tile<M, NPBTSS, WITH_DIAG, SATMODE>(p, n, (int64_t)blockIdx.x * T + threadIdx.x, snap, T, x_in, u_des, u_act,
+		                                              relax_out, rc_out, diag, qp_iter_sum);
+	}
+}
+
 // Closed-loop rollout (examples/segway_implicit_tb.cpp:251-283): the state never leaves the
 // registers between control steps; one launch covers all steps of every agent.
 template <class M, int NPBTSS, int SATMODE>
 __global__ void __launch_bounds__(TB_THREADS, tb_min_blocks<M>())
 tb_rollout_kernel(const TbParams p, const int64_t n, const int32_t steps, const double dt_plant, double *__restrict__ x_io,
                   const double *__restrict__ u_des, double *__restrict__ u_act_last, int32_t *__restrict__ rc_last,
-                  unsigned long long *__restrict__ rc_hist, unsigned long long *__restrict__ qp_iter_sum)
+                  unsigned long long *__restrict__ rc_hist, unsigned long long *__restrict__ qp_iter_sum, double *__restrict__ gsnap)
 {
 	constexpr int NX = M::NX, NU = M::NU;
 	extern __shared__ double smem[];
 	const int T = blockDim.x;
-	double *snap = smem + threadIdx.x;
-	const int64_t k = (int64_t)blockIdx.x * T + threadIdx.x;
+	constexpr bool GS = tb_global_snapshots<M>();
+	double *snap = GS ? gsnap + TB_SCRATCH_HEADER + (int64_t)blockIdx.x * tb_smem_doubles_per_thread<M, NPBTSS>() * T + threadIdx.x
+	                  : smem + threadIdx.x;
+	unsigned long long *next_tile = reinterpret_cast<unsigned long long *>(gsnap);
+	unsigned int hist[8];
+#pragma unroll
+	for (int i = 0; i < 8; i++) hist[i] = 0;
+	unsigned long long iters = 0;
+	for (bool first = true;; first = false) { // nx = 4: warps pull tiles of 32 agents; nx = 2: one tile per CTA
+	int64_t k;
+	if (GS) {
+		unsigned long long tile = 0;
+		if ((threadIdx.x & 31) == 0) tile = atomicAdd(next_tile, 1ull);
+		tile = __shfl_sync(0xffffffffu, tile, 0);
+		if ((int64_t)tile * 32 >= n) break;
+		k = (int64_t)tile * 32 + (threadIdx.x & 31);
+	} else {
+		if (!first) break;
+		k = (int64_t)blockIdx.x * T + threadIdx.x;
+	}
 	const bool live = k < n;
 	const int64_t kk = live ? k : (n - 1);
 	double x[NX], ud[NU], uo[NU];
@@ -558,20 +613,16 @@ tb_rollout_kernel(const TbParams p, const int64_t n, const int32_t steps, const 
 		uo[i] = 0.0;
 	}
 	int32_t rc = 0;
-	unsigned int hist[8];
-#pragma unroll
-	for (int i = 0; i < 8; i++) hist[i] = 0;
-	unsigned long long iters = 0;
 	for (int32_t s = 0; s < steps; s++) {
 		double relax;
 		int qp_iters;
 		TbDiagRec<NPBTSS> dg;
 		TbRows<M, NPBTSS> R;
 		rc = tb_filter_one<M, NPBTSS, false, SATMODE>(p, x, ud, snap, T, uo, relax, qp_iters, dg, R);
-		iters += (unsigned long long)qp_iters;
+		iters += live ? (unsigned long long)qp_iters : 0ull;
 		const int slot = (rc >= -3 && rc <= 2) ? rc + 3 : 7;
 #pragma unroll
-		for (int i = 0; i < 8; i++) hist[i] += (i == slot) ? 1u : 0u;
+		for (int i = 0; i < 8; i++) hist[i] += (live && i == slot) ? 1u : 0u;
 		// plant step: fCl = f + g uAct ; x += dt*fCl  (:265-283)
 		double f[NX], g[NX * NU];
 		M::dynamics(x, f, g);
@@ -590,17 +641,18 @@ tb_rollout_kernel(const TbParams p, const int64_t n, const int32_t steps, const 
 		for (int i = 0; i < NU; i++) u_act_last[k * NU + i] = uo[i];
 		rc_last[k] = rc;
 	}
+	} // tiles
 	if (rc_hist) {
 #pragma unroll
 		for (int i = 0; i < 8; i++) {
-			unsigned int c = live ? hist[i] : 0u;
+			unsigned int c = hist[i];
 #pragma unroll
 			for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
 			if ((threadIdx.x & 31) == 0 && c) atomicAdd(rc_hist + i, (unsigned long long)c);
 		}
 	}
 	if (qp_iter_sum) {
-		unsigned long long it = live ? iters : 0ull;
+		unsigned long long it = iters;
 #pragma unroll
 		for (int o = 16; o > 0; o >>= 1) it += __shfl_xor_sync(0xffffffffu, it, o);
 		if ((threadIdx.x & 31) == 0 && it) atomicAdd(qp_iter_sum, it);
