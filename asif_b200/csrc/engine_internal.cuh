@@ -1,0 +1,228 @@
+// engine_internal.cuh -- what the translation units of libasif_b200.so share: the engine object, error plumbing and the
+// launch helpers of the TB kernels.  engine.cu holds the C ABI and every kernel whose arithmetic is bit-identical to
+// the reference build (compiled with -fmad=false); kernels_contract.cu holds the kernels of the models that call
+// libm-class functions (sin, cos, tanh), compiled with FMA contraction (see the note there).
+#pragma once
+#include "../../include/asif_b200.h"
+
+#include "explicit_kernel.cuh"
+#include "filter_common.cuh"
+#include "implicit_kernel.cuh"
+#include "robust_kernel.cuh"
+#include "realizable_kernel.cuh"
+#include "models.cuh"
+#include "tb_kernel.cuh"
+
+#include <cstdint>
+
+using namespace asifb;
+
+namespace asifb {
+// records the message asif_last_error() returns (thread local) and hands the code back; defined in engine.cu
+int fail(int code, const char *fmt, ...);
+}
+using asifb::fail;
+
+namespace {
+
+#define CUDA_TRY(expr)                                                                                         \
+	do {                                                                                                       \
+		cudaError_t e__ = (expr);                                                                              \
+		if (e__ != cudaSuccess)                                                                                \
+			return fail(ASIF_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+	} while (0)
+
+constexpr int N_SLOTS = 4;               // pipeline depth of the host-memory path
+constexpr int64_t CHUNK_STATES = 1 << 19; // states per pipeline chunk (env ASIF_B200_CHUNK_STATES overrides); measured
+                                          // e2e for 1e7 C2 states: 2^17 6.7 ms, 2^18 6.1, 2^19 5.7, 2^20 6.1, 2^21 6.3
+
+inline int64_t chunk_states()
+{
+	static int64_t v = 0;
+	if (v == 0) {
+		const char *e = getenv("ASIF_B200_CHUNK_STATES");
+		const long long x = e ? atoll(e) : 0;
+		v = (x >= 1024) ? (int64_t)x : CHUNK_STATES;
+	}
+	return v;
+}
+
+constexpr int N_SNAP_BUFS = 6;
+
+struct Slot {
+	cudaStream_t stream = nullptr;
+	double *x = nullptr, *ud = nullptr, *ua = nullptr, *relax = nullptr, *diag = nullptr;
+	int32_t *rc = nullptr;
+	int64_t cap = 0, cap_diag = 0;
+};
+
+} // namespace
+
+struct asif_engine {
+	asif_engine_config cfg;
+	int nx, nu, n_relax, nc, nv, n_diag;
+	TbParams tb;
+	ExplicitParams ex;
+	ImplicitParams im;
+	RobustParams rb;
+	RealizableParams rz;
+	double *d_ttable = nullptr; // t_i of the backup trajectory (TB filter)
+	void *d_kernel = nullptr; // polytope kernel tables (realizable filter), one allocation
+	size_t rz_smem = 0;
+	double *d_table = nullptr; // half-plane table (robust filter)
+	Slot slot[N_SLOTS];
+	cudaStream_t stream = nullptr; // device-memory calls without a caller stream
+	unsigned long long *d_counters = nullptr; // [0] qp rows processed, [1..8] rc histogram
+	uint64_t last_qp_rows = 0;
+	int num_sms = 148;
+	// snapshot scratch of the persistent nx = 4 kernels: a ring, so that launches on different streams never share
+	// a buffer that may still be in use (the next user waits on the previous user's event)
+	struct SnapBuf {
+		double *p = nullptr;
+		size_t cap = 0;
+		cudaEvent_t ev = nullptr;
+		cudaStream_t last = nullptr;
+		bool used = false;
+	} snapbuf[N_SNAP_BUFS];
+	int snap_next = 0;
+};
+
+
+template <class K>
+int set_smem(K kernel, size_t bytes)
+{
+	if (bytes > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+	return ASIF_OK;
+}
+
+// ---- kernel dispatch -------------------------------------------------------------------------
+// Launch geometry of the TB kernels.  nx = 2: one CTA per tile of TB_THREADS states, snapshots in shared memory.
+// nx = 4: persistent grid over a global snapshot scratch; the grid is the largest one that fits the SMs, shrunk so
+// that every CTA runs the same number of tiles (no ragged last wave).
+template <class M, int NPBTSS>
+int tb_geometry(asif_engine *e, int64_t n, cudaStream_t st, unsigned &blocks, size_t &smem, double *&gsnap, int &buf)
+{
+	const int64_t tiles = (n + TB_THREADS - 1) / TB_THREADS;
+	const size_t per_cta = sizeof(double) * tb_smem_doubles_per_thread<M, NPBTSS>() * TB_THREADS;
+	gsnap = nullptr;
+	buf = -1;
+	if (!tb_global_snapshots<M>()) {
+		blocks = (unsigned)tiles;
+		smem = per_cta;
+		return ASIF_OK;
+	}
+	const int64_t resident = (int64_t)e->num_sms * tb_min_blocks<M>();
+	const int64_t rounds = (tiles + resident - 1) / resident;
+	blocks = (unsigned)((tiles + rounds - 1) / rounds);
+	if (blocks < 1) blocks = 1;
+	smem = 0;
+	const size_t need = sizeof(double) * TB_SCRATCH_HEADER + per_cta * (size_t)resident;
+	// pick a scratch buffer: one last used on this same stream (stream order protects it), else an idle one, else an
+	// unallocated one, else the next in the ring after waiting for its last user
+	int pick = -1;
+	for (int i = 0; i < N_SNAP_BUFS && pick < 0; i++) {
+		asif_engine::SnapBuf &c = e->snapbuf[i];
+		if (c.p && c.cap >= need && c.used && c.last == st) pick = i;
+	}
+	for (int i = 0; i < N_SNAP_BUFS && pick < 0; i++) {
+		asif_engine::SnapBuf &c = e->snapbuf[i];
+		if (c.p && c.cap >= need && (!c.used || cudaEventQuery(c.ev) == cudaSuccess)) {
+			c.used = false;
+			pick = i;
+		}
+	}
+	for (int i = 0; i < N_SNAP_BUFS && pick < 0; i++)
+		if (!e->snapbuf[i].p) pick = i;
+	if (pick < 0) {
+		pick = e->snap_next;
+		e->snap_next = (e->snap_next + 1) % N_SNAP_BUFS;
+	}
+	buf = pick;
+	asif_engine::SnapBuf &b = e->snapbuf[buf];
+	if (b.cap < need) {
+		if (b.p) CUDA_TRY(cudaFree(b.p)); // synchronises with any kernel still using it
+		b.p = nullptr;
+		b.cap = 0;
+		b.used = false;
+		CUDA_TRY(cudaMalloc(&b.p, need));
+		b.cap = need;
+	}
+	if (!b.ev) CUDA_TRY(cudaEventCreateWithFlags(&b.ev, cudaEventDisableTiming));
+	if (b.used && b.last != st) CUDA_TRY(cudaStreamWaitEvent(st, b.ev, 0));
+	CUDA_TRY(cudaMemsetAsync(b.p, 0, sizeof(double) * TB_SCRATCH_HEADER, st)); // tile counter
+	gsnap = b.p;
+	return ASIF_OK;
+}
+
+inline int tb_release(asif_engine *e, int buf, cudaStream_t st)
+{
+	if (buf >= 0) {
+		CUDA_TRY(cudaEventRecord(e->snapbuf[buf].ev, st));
+		e->snapbuf[buf].used = true;
+		e->snapbuf[buf].last = st;
+	}
+	return ASIF_OK;
+}
+
+template <class M, int NPBTSS, int SATMODE>
+int launch_tb_mode(asif_engine *e, int64_t n, const double *x, const double *ud, double *ua, double *relax, int32_t *rc,
+                   double *diag, cudaStream_t st)
+{
+	unsigned blocks;
+	size_t smem;
+	double *gsnap;
+	int buf;
+	int r = tb_geometry<M, NPBTSS>(e, n, st, blocks, smem, gsnap, buf);
+	if (r) return r;
+	if (diag) {
+		auto k = tb_filter_kernel<M, NPBTSS, true, SATMODE>;
+		r = set_smem(k, smem);
+		if (r) return r;
+		k<<<blocks, TB_THREADS, smem, st>>>(e->tb, n, x, ud, ua, relax, rc, diag, e->d_counters, gsnap);
+	} else {
+		auto k = tb_filter_kernel<M, NPBTSS, false, SATMODE>;
+		r = set_smem(k, smem);
+		if (r) return r;
+		k<<<blocks, TB_THREADS, smem, st>>>(e->tb, n, x, ud, ua, relax, rc, nullptr, e->d_counters, gsnap);
+	}
+	CUDA_TRY(cudaGetLastError());
+	return tb_release(e, buf, st);
+}
+
+// SAT_POW2 and SAT_IDENTITY are exact shortcuts of SAT_GENERAL; IDENTITY is only instantiated for the nx = 2 models
+template <class M, int NPBTSS>
+int launch_tb(asif_engine *e, int64_t n, const double *x, const double *ud, double *ua, double *relax, int32_t *rc,
+              double *diag, cudaStream_t st)
+{
+	if (e->tb.sat_mode == SAT_IDENTITY && M::NX <= 2) return launch_tb_mode<M, NPBTSS, SAT_IDENTITY>(e, n, x, ud, ua, relax, rc, diag, st);
+	if (e->tb.sat_mode >= SAT_POW2) return launch_tb_mode<M, NPBTSS, SAT_POW2>(e, n, x, ud, ua, relax, rc, diag, st);
+	return launch_tb_mode<M, NPBTSS, SAT_GENERAL>(e, n, x, ud, ua, relax, rc, diag, st);
+}
+
+
+template <class M, int NPBTSS>
+int launch_tb_rollout(asif_engine *e, int64_t n, int32_t steps, double dt, double *x, const double *ud, double *ua,
+                      int32_t *rc, cudaStream_t st)
+{
+	unsigned blocks;
+	size_t smem;
+	double *gsnap;
+	int buf;
+	int r = tb_geometry<M, NPBTSS>(e, n, st, blocks, smem, gsnap, buf);
+	if (r) return r;
+	auto k = (e->tb.sat_mode >= SAT_POW2) ? tb_rollout_kernel<M, NPBTSS, SAT_POW2> : tb_rollout_kernel<M, NPBTSS, SAT_GENERAL>;
+	r = set_smem(k, smem);
+	if (r) return r;
+	k<<<blocks, TB_THREADS, smem, st>>>(e->tb, n, steps, dt, x, ud, ua, rc, e->d_counters + 1, e->d_counters, gsnap);
+	CUDA_TRY(cudaGetLastError());
+	return tb_release(e, buf, st);
+}
+
+
+// defined in kernels_contract.cu
+namespace asifb {
+int launch_tb_segway(asif_engine *e, bool shipped, int64_t n, const double *x, const double *ud, double *ua, double *relax,
+                     int32_t *rc, double *diag, cudaStream_t st);
+int launch_tb_rollout_segway(asif_engine *e, bool shipped, int64_t n, int32_t steps, double dt, double *x, const double *ud,
+                             double *ua, int32_t *rc, cudaStream_t st);
+} // namespace asifb

@@ -1,0 +1,29 @@
+// kernels_contract.cu -- TB kernels of the segway model, compiled WITH FMA contraction (-fmad=true).
+//
+// The double-integrator kernels (engine.cu) are compiled with -fmad=false so that every multiply and add rounds as in
+// the reference's GCC x86-64 build; their trajectories, critical indices and constraint rows are bit-identical to that
+// build.  The segway callbacks (examples/segway_implicit_tb.cpp:69-212) call sin, cos and tanh on every Euler step:
+// CUDA's and glibc's implementations differ in the last bit, so bit identity with the reference is unattainable for
+// this model whatever the contraction setting, and parity is judged by the tolerances of BASELINE.json (u within
+// 1e-6 + 1e-5|u|, identical return codes, barrier values within 1e-9; tests/test_gpu_parity.py, test_gpu_rollout.py).
+// Contraction perturbs results by the same last-bit amount and removes a quarter of the FP64 instructions:
+// C5 filter 13.6 -> 12.1 ms per 1e6 states, fleet rollout 1.72 -> 1.53 s (B200, profiles/).
+#include "engine_internal.cuh"
+
+namespace asifb {
+
+int launch_tb_segway(asif_engine *e, bool shipped, int64_t n, const double *x, const double *ud, double *ua, double *relax,
+                     int32_t *rc, double *diag, cudaStream_t st)
+{
+	return shipped ? launch_tb<SegwayTB<false>, 4>(e, n, x, ud, ua, relax, rc, diag, st)
+	               : launch_tb<SegwayTB<true>, 4>(e, n, x, ud, ua, relax, rc, diag, st);
+}
+
+int launch_tb_rollout_segway(asif_engine *e, bool shipped, int64_t n, int32_t steps, double dt, double *x, const double *ud,
+                             double *ua, int32_t *rc, cudaStream_t st)
+{
+	return shipped ? launch_tb_rollout<SegwayTB<false>, 4>(e, n, steps, dt, x, ud, ua, rc, st)
+	               : launch_tb_rollout<SegwayTB<true>, 4>(e, n, steps, dt, x, ud, ua, rc, st);
+}
+
+} // namespace asifb
