@@ -82,11 +82,13 @@ int make_softsat(double r, const double *lb, const double *ub, int nu, SoftSat &
 		s.range[i] = 1.0;
 		s.middle[i] = 0.0;
 		s.uc_scale_exact[i] = 0.0;
+		s.uc_scale[i] = 2.0;
 	}
 	int mode = SAT_IDENTITY;
 	for (int i = 0; i < nu; i++) {
 		s.range[i] = ub[i] - lb[i];
 		s.middle[i] = (ub[i] + lb[i]) / 2;
+		s.uc_scale[i] = 2.0 / s.range[i];
 		int ex;
 		const bool pow2 = frexp(s.range[i], &ex) == 0.5;
 		if (pow2) s.uc_scale_exact[i] = 2.0 / s.range[i]; // exact: every operation of 2*(u-mid)/range is then exact
@@ -105,28 +107,6 @@ int launch_explicit(asif_engine *e, int64_t n, const double *x, const double *ud
 		explicit_filter_kernel<M, true><<<blocks, EXPL_THREADS, 0, st>>>(e->ex, n, x, ud, ua, relax, rc, diag, e->d_counters);
 	else
 		explicit_filter_kernel<M, false><<<blocks, EXPL_THREADS, 0, st>>>(e->ex, n, x, ud, ua, relax, rc, nullptr, e->d_counters);
-	CUDA_TRY(cudaGetLastError());
-	return ASIF_OK;
-}
-
-template <class M, int NPBTSS>
-int launch_implicit(asif_engine *e, int64_t n, const double *x, const double *ud, double *ua, double *relax, int32_t *rc,
-                    double *diag, cudaStream_t st)
-{
-	const size_t smem = sizeof(double) * imp_smem_doubles_per_thread<M, NPBTSS>() * IMP_THREADS;
-	const unsigned blocks = (unsigned)((n + IMP_THREADS - 1) / IMP_THREADS);
-	const bool pow2 = e->im.sat_mode >= SAT_POW2;
-	if (diag) {
-		auto k = pow2 ? implicit_filter_kernel<M, NPBTSS, true, SAT_POW2> : implicit_filter_kernel<M, NPBTSS, true, SAT_GENERAL>;
-		int r = set_smem(k, smem);
-		if (r) return r;
-		k<<<blocks, IMP_THREADS, smem, st>>>(e->im, n, x, ud, ua, relax, rc, diag, e->d_counters);
-	} else {
-		auto k = pow2 ? implicit_filter_kernel<M, NPBTSS, false, SAT_POW2> : implicit_filter_kernel<M, NPBTSS, false, SAT_GENERAL>;
-		int r = set_smem(k, smem);
-		if (r) return r;
-		k<<<blocks, IMP_THREADS, smem, st>>>(e->im, n, x, ud, ua, relax, rc, nullptr, e->d_counters);
-	}
 	CUDA_TRY(cudaGetLastError());
 	return ASIF_OK;
 }
@@ -172,7 +152,7 @@ int launch_filter(asif_engine *e, int64_t n, const double *x, const double *ud, 
 		break;
 	case ASIF_FILTER_IMPLICIT:
 		if (e->cfg.model == ASIF_MODEL_INVERTED_PENDULUM)
-			return launch_implicit<InvertedPendulumImplicit, 10>(e, n, x, ud, ua, relax, rc, diag, st);
+			return launch_implicit_ip(e, n, x, ud, ua, relax, rc, diag, st);
 		break;
 	case ASIF_FILTER_ROBUST:
 		if (e->cfg.model == ASIF_MODEL_INVERTED_PENDULUM_TABLE) return launch_robust(e, n, x, ud, ua, relax, rc, diag, st);

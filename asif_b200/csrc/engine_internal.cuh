@@ -225,4 +225,6 @@ int launch_tb_segway(asif_engine *e, bool shipped, int64_t n, const double *x, c
                      int32_t *rc, double *diag, cudaStream_t st);
 int launch_tb_rollout_segway(asif_engine *e, bool shipped, int64_t n, int32_t steps, double dt, double *x, const double *ud,
                              double *ua, int32_t *rc, cudaStream_t st);
+int launch_implicit_ip(asif_engine *e, int64_t n, const double *x, const double *ud, double *ua, double *relax, int32_t *rc,
+                       double *diag, cudaStream_t st);
 } // namespace asifb

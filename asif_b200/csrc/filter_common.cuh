@@ -23,14 +23,16 @@ struct SoftSat {
 	// 2/range when range is a power of two (then 2*(u-mid)/range == (u-mid)*(2/range) bit for bit and the
 	// FP64 division, ~10 dependent DFMAs per Euler step, is not needed); 0 otherwise
 	double uc_scale_exact[MAX_NU];
+	double uc_scale[MAX_NU]; // 2/range rounded (SAT_RECIP)
 };
 
 // How the normalised input uc = 2 (u - middle) / range is evaluated; chosen on the host from (lb, ub).
-// Every mode produces the same bits as the reference expression.
+// The first three modes produce the same bits as the reference expression.
 enum : int {
 	SAT_GENERAL = 0,  // 2*(u-middle)/range
 	SAT_POW2 = 1,     // range is a power of two: (u-middle)*(2/range), all operations exact
-	SAT_IDENTITY = 2  // middle == 0 and range == 2 (e.g. u in [-1,1]): uc == u
+	SAT_IDENTITY = 2, // middle == 0 and range == 2 (e.g. u in [-1,1]): uc == u
+	SAT_RECIP = 3     // (u-middle)*fl(2/range): last-bit differences; only for models without bit parity (kernels_contract.cu)
 };
 
 // Structural patterns a model may declare for its callback outputs: an entry that is the literal
@@ -80,6 +82,7 @@ __device__ __forceinline__ void input_saturate_soft(const SoftSat &s, int i, dou
 	double uc;
 	if (SATMODE == SAT_IDENTITY) uc = u;
 	else if (SATMODE == SAT_POW2) uc = (u - middle) * s.uc_scale_exact[i];
+	else if (SATMODE == SAT_RECIP) uc = (u - middle) * s.uc_scale[i];
 	else uc = 2 * (u - middle) / range;
 	const double a = fabs(uc);
 	// clamp and pass-through legs as selects (no branch, no register shuffling between the legs) ...

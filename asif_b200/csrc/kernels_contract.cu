@@ -1,4 +1,4 @@
-// kernels_contract.cu -- TB kernels of the segway model, compiled WITH FMA contraction (-fmad=true).
+// kernels_contract.cu -- kernels of the segway and inverted-pendulum models, compiled WITH FMA contraction (-fmad=true).
 //
 // The double-integrator kernels (engine.cu) are compiled with -fmad=false so that every multiply and add rounds as in
 // the reference's GCC x86-64 build; their trajectories, critical indices and constraint rows are bit-identical to that
@@ -7,7 +7,10 @@
 // this model whatever the contraction setting, and parity is judged by the tolerances of BASELINE.json (u within
 // 1e-6 + 1e-5|u|, identical return codes, barrier values within 1e-9; tests/test_gpu_parity.py, test_gpu_rollout.py).
 // Contraction perturbs results by the same last-bit amount and removes a quarter of the FP64 instructions:
-// C5 filter 13.6 -> 12.1 ms per 1e6 states, fleet rollout 1.72 -> 1.53 s (B200, profiles/).
+// C5 filter 13.6 -> 12.1 ms per 1e6 states, fleet rollout 1.72 -> 1.53 s (B200, profiles/).  The same holds for the
+// inverted pendulum of the implicit filter (examples/InvertedPendulum_Implicit.cpp:27-46, sin and cos per step); there
+// the normalisation of the soft saturation also multiplies by 1/range instead of dividing (SAT_RECIP: the quotient
+// only feeds two comparisons and the rare bevel leg, and the FP64 division was 14 % of the kernel's stall samples).
 #include "engine_internal.cuh"
 
 namespace asifb {
@@ -24,6 +27,29 @@ int launch_tb_rollout_segway(asif_engine *e, bool shipped, int64_t n, int32_t st
 {
 	return shipped ? launch_tb_rollout<SegwayTB<false>, 4>(e, n, steps, dt, x, ud, ua, rc, st)
 	               : launch_tb_rollout<SegwayTB<true>, 4>(e, n, steps, dt, x, ud, ua, rc, st);
+}
+
+int launch_implicit_ip(asif_engine *e, int64_t n, const double *x, const double *ud, double *ua, double *relax, int32_t *rc,
+                       double *diag, cudaStream_t st)
+{
+	using M = InvertedPendulumImplicit;
+	constexpr int NPBTSS = 10;
+	const size_t smem = sizeof(double) * imp_smem_doubles_per_thread<M, NPBTSS>() * IMP_THREADS;
+	const unsigned blocks = (unsigned)((n + IMP_THREADS - 1) / IMP_THREADS);
+	const bool pow2 = e->im.sat_mode >= SAT_POW2;
+	if (diag) {
+		auto k = pow2 ? implicit_filter_kernel<M, NPBTSS, true, SAT_POW2> : implicit_filter_kernel<M, NPBTSS, true, SAT_RECIP>;
+		int r = set_smem(k, smem);
+		if (r) return r;
+		k<<<blocks, IMP_THREADS, smem, st>>>(e->im, n, x, ud, ua, relax, rc, diag, e->d_counters);
+	} else {
+		auto k = pow2 ? implicit_filter_kernel<M, NPBTSS, false, SAT_POW2> : implicit_filter_kernel<M, NPBTSS, false, SAT_RECIP>;
+		int r = set_smem(k, smem);
+		if (r) return r;
+		k<<<blocks, IMP_THREADS, smem, st>>>(e->im, n, x, ud, ua, relax, rc, nullptr, e->d_counters);
+	}
+	CUDA_TRY(cudaGetLastError());
+	return ASIF_OK;
 }
 
 } // namespace asifb

@@ -27,6 +27,10 @@
 namespace asifb {
 
 constexpr int TB_THREADS = 128;
+#ifndef ASIF_TB_STEP_UNROLL
+#define ASIF_TB_STEP_UNROLL 1
+#endif
+constexpr int TB_STEP_UNROLL = ASIF_TB_STEP_UNROLL;
 #ifndef ASIF_TB_MINBLOCKS_NX4
 #define ASIF_TB_MINBLOCKS_NX4 4 // 128 registers, 16 warps/SM (snapshots in global scratch); 13.2 ms vs 16.5 ms at 2 for 1e6 C5 states
 #endif
@@ -234,6 +238,7 @@ __device__ __forceinline__ int32_t tb_filter_one(const TbParams &p, const double
 			if (__all_sync(0xffffffffu, !active)) break;
 		}
 		bool hit_now = false;
+#pragma unroll TB_STEP_UNROLL
 		for (; i < N; i++) {
 		// rhs (:899-909) and Euler step: (rhs*dt) + prev, two roundings (:477-480)
 		double Xd[NS], DfCL[NX * NX];
