@@ -40,6 +40,23 @@ class EngineConfig(C.Structure):
     ]
 
 
+class LoopConfig(C.Structure):
+    """Mirror of struct asif_loop_config (include/asif_b200.h)."""
+    _fields_ = [
+        ("struct_size", C.c_uint32), ("steps", C.c_int32), ("dt", C.c_double), ("steps_per_sample", C.c_int32),
+        ("smooth_bounds", C.c_int32), ("smooth_lb", C.c_double), ("smooth_ub", C.c_double), ("smooth_rate", C.c_double),
+        ("plant_gain", C.c_double), ("log_stride", C.c_int32), ("log_after_step", C.c_int32), ("log_agents", C.c_int64),
+    ]
+
+
+# field offsets inside one closed-loop log record, by name
+def loop_log_fields(nx, nu, n_relax):
+    names = ["t"] + ["x%d" % i for i in range(nx)] + ["xEstim%d" % i for i in range(nx)] + ["uDes%d" % i for i in range(nu)] + \
+        ["uFilter%d" % i for i in range(nu)] + ["uAct%d" % i for i in range(nu)] + ["relax%d" % i for i in range(n_relax)] + \
+        ["rc", "smoothLo", "smoothHi", "TTS", "BTorthoBS", "critIdx0"]
+    return {k: i for i, k in enumerate(names)}
+
+
 _lib = None
 
 
@@ -69,6 +86,10 @@ def load_library():
     L.asif_engine_rollout.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_double, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.c_int32, C.c_void_p]
     L.asif_engine_last_qp_iterations.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+    L.asif_loop_config_init.argtypes = [C.POINTER(LoopConfig)]
+    L.asif_engine_loop_log_dims.argtypes = [C.c_void_p, C.POINTER(LoopConfig), C.POINTER(C.c_int64)]
+    L.asif_engine_closed_loop.argtypes = [C.c_void_p, C.c_int64, C.POINTER(LoopConfig)] + [C.c_void_p] * 5 + \
+        [C.POINTER(C.c_int64), C.c_void_p, C.c_int32, C.c_void_p]
     L.asif_qp_solve_batch.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int32] + [C.c_void_p] * 9 + \
                                      [C.c_int32, C.c_int32, C.c_void_p]
     L.asif_measure_fp64_peak.argtypes = [C.c_int32, _dp, _dp]
@@ -204,6 +225,34 @@ class Engine:
         _check(load_library().asif_engine_rollout(self._h, n, steps, dt, ptrs[0][0], ptrs[1][0], ptrs[2][0], ptrs[3][0],
                                                   hist, mem, stream))
         return np.array(list(hist), dtype=np.int64) if want_hist else None
+
+    def closed_loop(self, x0, u_des, steps, dt=1e-3, steps_per_sample=1, smooth=None, plant_gain=1.0, log_stride=0,
+                    log_agents=0, log_after_step=True):
+        """The example main loop for a fleet (asif_engine_closed_loop).  smooth = (lb, ub, rate) enables the smoothBounds
+        rate limiter.  Returns a dict: x, u_act, relax, rc (last filter call), rc_hist, log (agents, records, fields)."""
+        L = load_library()
+        cfg = LoopConfig()
+        _check(L.asif_loop_config_init(C.byref(cfg)))
+        cfg.steps, cfg.dt, cfg.steps_per_sample, cfg.plant_gain = int(steps), float(dt), int(steps_per_sample), float(plant_gain)
+        cfg.log_stride, cfg.log_agents, cfg.log_after_step = int(log_stride), int(log_agents), int(bool(log_after_step))
+        if smooth is not None:
+            cfg.smooth_bounds = 1
+            cfg.smooth_lb, cfg.smooth_ub, cfg.smooth_rate = (float(v) for v in smooth)
+        x = np.array(x0, dtype=np.float64).reshape(-1, self.nx).copy()
+        u_des = np.ascontiguousarray(u_des, dtype=np.float64).reshape(-1, self.nu)
+        n = x.shape[0]
+        u = np.empty((n, self.nu))
+        relax = np.empty((n, self.n_relax))
+        rc = np.empty(n, dtype=np.int32)
+        hist = (C.c_int64 * 8)()
+        dims = (C.c_int64 * 2)()
+        _check(L.asif_engine_loop_log_dims(self._h, C.byref(cfg), dims))
+        nlog = min(int(log_agents), n) if log_stride > 0 else 0
+        log = np.zeros((nlog, int(dims[1]), int(dims[0]))) if nlog else None
+        _check(L.asif_engine_closed_loop(self._h, n, C.byref(cfg), x.ctypes.data, u_des.ctypes.data, u.ctypes.data,
+                                         relax.ctypes.data, rc.ctypes.data, hist, log.ctypes.data if nlog else None, MEM_HOST, None))
+        return dict(x=x, u_act=u, relax=relax, rc=rc, rc_hist=np.array(list(hist), dtype=np.int64), log=log,
+                    fields=loop_log_fields(self.nx, self.nu, self.n_relax))
 
     def last_qp_iterations(self):
         v = C.c_uint64()

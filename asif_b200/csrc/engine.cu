@@ -164,6 +164,18 @@ int launch_filter(asif_engine *e, int64_t n, const double *x, const double *ud, 
 	return fail(ASIF_ERR_UNSUPPORTED, "no kernel for filter %d / model %d", e->cfg.filter, e->cfg.model);
 }
 
+} // namespace
+
+namespace asifb {
+int launch_filter_any(asif_engine *e, int64_t n, const double *x, const double *ud, double *ua, double *relax, int32_t *rc,
+                      double *diag, cudaStream_t st)
+{
+	return launch_filter(e, n, x, ud, ua, relax, rc, diag, st);
+}
+} // namespace asifb
+
+namespace {
+
 int launch_rollout(asif_engine *e, int64_t n, int32_t steps, double dt, double *x, const double *ud, double *ua,
                    int32_t *rc, cudaStream_t st)
 {

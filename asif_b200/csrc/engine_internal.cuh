@@ -219,6 +219,12 @@ int launch_tb_rollout(asif_engine *e, int64_t n, int32_t steps, double dt, doubl
 }
 
 
+// defined in engine.cu: dispatch of one filter launch on device pointers
+namespace asifb {
+int launch_filter_any(asif_engine *e, int64_t n, const double *x, const double *ud, double *ua, double *relax, int32_t *rc,
+                      double *diag, cudaStream_t st);
+}
+
 // defined in kernels_contract.cu
 namespace asifb {
 int launch_tb_segway(asif_engine *e, bool shipped, int64_t n, const double *x, const double *ud, double *ua, double *relax,

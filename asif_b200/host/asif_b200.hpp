@@ -175,8 +175,38 @@ namespace ASIF
 				if (engine_ == nullptr) return ASIF_ERR_INVALID_ARGUMENT;
 				return asif_engine_filter_batch(engine_, n, X, UDes, UAct, Relax, rc, diag, ASIF_MEM_DEVICE, stream);
 			}
+			// The loop around filter() of the example programs for n agents (asif_engine_closed_loop): X is advanced in
+			// place by loop.steps plant steps; see asif_loop_config for sampling, rate limiter and log options.
+			// log: logRecordWidth() * logRecords(loop) doubles per recorded agent, or nullptr when loop.log_stride == 0.
+			int32_t closedLoop(const int64_t n, const asif_loop_config &loop, double X[], const double UDes[], double UActLast[],
+			                   double RelaxLast[], int32_t rcLast[], int64_t rcHist[8] = nullptr, double log[] = nullptr)
+			{
+				if (engine_ == nullptr) return ASIF_ERR_INVALID_ARGUMENT;
+				return asif_engine_closed_loop(engine_, n, &loop, X, UDes, UActLast, RelaxLast, rcLast, rcHist, log, ASIF_MEM_HOST,
+				                               nullptr);
+			}
+			static asif_loop_config loopDefaults(void)
+			{
+				asif_loop_config c;
+				asif_loop_config_init(&c);
+				return c;
+			}
+			int64_t logRecordWidth(void) const
+			{
+				asif_loop_config c = loopDefaults();
+				int64_t d[2] = {0, 0};
+				asif_engine_loop_log_dims(engine_, &c, d);
+				return d[0];
+			}
+			int64_t logRecords(const asif_loop_config &loop) const
+			{
+				int64_t d[2] = {0, 0};
+				asif_engine_loop_log_dims(engine_, &loop, d);
+				return d[1];
+			}
 			uint32_t nx(void) const { return dims_[0]; }
 			uint32_t nu(void) const { return dims_[1]; }
+			uint32_t nRelax(void) const { return dims_[2]; }
 			uint32_t nDiag(void) const { return dims_[5]; }
 
 		protected:

@@ -4,6 +4,9 @@
 // abstract interface, and a filterBatch call.  Prints "host_check ok" and returns 0 on success.
 // Needs a GPU at run time; build() only checks that it compiles and links.
 #include "asif_b200.hpp"
+#include "loop_log.hpp"
+#include <fstream>
+#include <string>
 
 #include <cstdio>
 #include <memory>
@@ -100,6 +103,39 @@ int main()
 		if (rob.initialize(lb, ub) != 1) return fail("FilterBatchRobust::initialize");
 		double r1 = 0.0;
 		if (rob.filter(x, uDes, uAct, r1) != 1) return fail("FilterBatchRobust::filter");
+		// --- 5. the example main loop for a small fleet, logged in the example's CSV layout
+		// (examples/InvertedPendulum_Implicit.cpp:84-150: ten start points, dt 1e-3)
+		const int n = 10;
+		asif_loop_config loop = b200::FilterBatchBase::loopDefaults();
+		loop.steps = 40;
+		loop.dt = 0.001;
+		loop.log_stride = 1;
+		loop.log_agents = n;
+		std::vector<double> X(2 * n), U(n, 0.0), UA(n), R(2 * n);
+		std::vector<int32_t> rcs(n);
+		for (int i = 0; i < n; i++) {
+			X[2 * i] = 0.1 + double(i) * 0.29;
+			X[2 * i + 1] = 0.0;
+		}
+		const int64_t W = asif.logRecordWidth(), NR = asif.logRecords(loop);
+		std::vector<double> log((size_t)(n * NR * W));
+		int64_t hist[8];
+		if (asif.closedLoop(n, loop, X.data(), U.data(), UA.data(), R.data(), rcs.data(), hist, log.data()) != 0)
+			return fail("closedLoop");
+		int64_t calls = 0;
+		for (int i = 0; i < 8; i++) calls += hist[i];
+		if (calls != (int64_t)n * loop.steps || NR != loop.steps) return fail("closedLoop: return-code histogram / record count");
+		const b200::LogLayout L(asif.nx(), asif.nu(), asif.nRelax());
+		if ((int64_t)L.width() != W) return fail("LogLayout width differs from the library's");
+		if (b200::writeLoopCsv("/tmp/asif_b200_host_check_0.csv", b200::LogSchema::ImplicitPendulum, L, log.data(), NR) != 0)
+			return fail("writeLoopCsv");
+		std::ifstream chk("/tmp/asif_b200_host_check_0.csv");
+		std::string header, first;
+		std::getline(chk, header);
+		std::getline(chk, first);
+		if (header != "tNow,x,v,uDes,uAct,gammaSafe,gammaReach,rc") return fail("CSV header");
+		if (first.compare(0, 13, "0.0010000000,") != 0) return fail("CSV first record (tNow after the first step, 10 digits)");
+		std::printf("closedLoop + CSV: %lld records per agent, first line %s\n", (long long)NR, first.c_str());
 	}
 	std::printf("host_check ok\n");
 	return 0;

@@ -138,6 +138,39 @@ int32_t asif_engine_filter_batch(asif_engine *e, int64_t n, const double *x, con
 int32_t asif_engine_rollout(asif_engine *e, int64_t n, int32_t steps, double dt, double *x, const double *u_des,
                             double *u_act_last, int32_t *rc_last, int64_t *rc_hist, int32_t mem, void *stream);
 
+/*
+ * The loop around filter() in the example programs, for a fleet of n independent agents with the state resident on
+ * the device: every steps_per_sample plant steps the state is sampled (xEstim), filtered, optionally passed through
+ * the smoothBounds rate limiter, and held while the plant  x += dt (f(x) + g(x) uAct)  advances
+ * (examples/InvertedPendulum_Implicit.cpp:113-147, examples/InvertedPendulum_RealizableSampled.cpp:258-304 `dtPerSample`,
+ * examples/DoubleIntegrator_RealizableSampled.cpp:110-205 `smoothBounds`, examples/segway_implicit_tb.cpp:251-283).
+ * Works for every filter class; asif_engine_rollout is the fused fast path for ASIFimplicitTB without sampling or log.
+ */
+typedef struct asif_loop_config {
+	uint32_t struct_size;     /* set by asif_loop_config_init */
+	int32_t steps;            /* plant steps */
+	double dt;                /* plant Euler step (examples: 1e-3) */
+	int32_t steps_per_sample; /* dtPerSample >= 1 */
+	int32_t smooth_bounds;    /* 1: rate limiter on input 0 */
+	double smooth_lb, smooth_ub, smooth_rate; /* examples: -20, 20, 20*dtPerSample*0.001 */
+	double plant_gain;        /* input gain p of dynamicsExact for the pendulum table/kernel models */
+	int32_t log_stride;       /* record every log_stride-th plant step; 0: no log */
+	int32_t log_after_step;   /* 1: record (t+dt, x after the step) as the segway/implicit examples do; 0: (t, x before) */
+	int64_t log_agents;       /* agents [0, log_agents) are recorded */
+} asif_loop_config;
+
+int32_t asif_loop_config_init(asif_loop_config *cfg);
+/* dims[0] = doubles per log record, dims[1] = records per agent for this config.  Record layout:
+ * t, x[nx], xEstim[nx], uDes[nu], uFilter[nu], uAct[nu], relax[n_relax], rc, smoothLo, smoothHi, TTS, BTorthoBS, critIdx0
+ * (the last three are filled for ASIFimplicitTB, 0 otherwise); log[agent][record][field]. */
+int32_t asif_engine_loop_log_dims(const asif_engine *e, const asif_loop_config *cfg, int64_t dims[2]);
+/* x is updated in place; u_act_last / relax_last / rc_last receive the last filter call's outputs; rc_hist[8] (host,
+ * optional) counts return codes over all filter calls as asif_engine_rollout does; log may be NULL when log_stride is 0.
+ * All batch pointers and log live in the memory space `mem`. */
+int32_t asif_engine_closed_loop(asif_engine *e, int64_t n, const asif_loop_config *cfg, double *x, const double *u_des,
+                                double *u_act_last, double *relax_last, int32_t *rc_last, int64_t *rc_hist, double *log,
+                                int32_t mem, void *stream);
+
 /* mean QP work of the last filter_batch/rollout call: rows processed by the active-set solver,
  * summed over states (the "K-bar" of SURVEY 8d is this / states) */
 int32_t asif_engine_last_qp_iterations(asif_engine *e, uint64_t *rows_processed);
