@@ -56,6 +56,30 @@ def make_inputs(n, seed):
     return g.uniform(-1, 1, (n, 2)), g.uniform(-1, 1, (n, 1))
 
 
+def bind_to_gpu_numa_node(dev_index):
+    """Run this rank (and place its pinned staging buffers: first touch) on the CPU socket the GPU hangs off.
+    With several ranks per box the host<->device legs of `e2e` otherwise cross the socket interconnect.
+    Returns a short description for the JSON line; never fails the run."""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(dev_index)
+        bdf = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read())
+        if node < 0:
+            return "numa node unknown for %s" % bdf
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return "numa node %d has no allowed cpus" % node
+        os.sched_setaffinity(0, cpus)
+        return "gpu %s -> numa node %d (%d cpus)" % (bdf, node, len(cpus))
+    except Exception as e:  # sysfs layout differs, containers without the node files, ...
+        return "not bound (%s)" % type(e).__name__
+
+
 class ClockSampler:
     """nvidia-smi clock / throttle-reason samples during the timed region."""
 
@@ -206,6 +230,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
     n = args.states
+    all_cpus = os.sched_getaffinity(0)
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else "single rank: not bound"
 
     eng = ab.Engine(ab.FILTER_IMPLICIT_TB, ab.MODEL_DOUBLE_INTEGRATOR_TB, device=local_rank,
                     relaxCost=C2_OPTS[0], relaxLb=C2_OPTS[1], relaxTTS=C2_OPTS[2], relaxMinOrtho=C2_OPTS[3],
@@ -304,7 +330,7 @@ def main():
         "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(world),
         "e2e": {"value": e2e_value, "unit": "states/s", "h2d_bytes_per_step": 24 * n, "d2h_bytes_per_step": 20 * n,
-                "ms_per_step": 1e3 * e2e_s / args.steps, "matches_device_resident": same},
+                "ms_per_step": 1e3 * e2e_s / args.steps, "matches_device_resident": same, "host_binding": numa},
         "gpu_launches": args.steps,
         "roofline": {"bound": "fp64", "achieved": ach_tf, "peak": p64_tflops, "unit": "TFLOP/s", "frac": ach_tf / p64_tflops,
                      "traffic": traffic, "kernel": "tb_filter_kernel<DoubleIntegratorTB,4,false>",
@@ -316,6 +342,7 @@ def main():
     }
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        os.sched_setaffinity(0, all_cpus)
         try:
             cores = os.cpu_count() or 1
             w, _ = cpu_reference_run(100 * cores, cores, False)

@@ -92,3 +92,18 @@ def test_host_layer_compiles():
     """The C++ host layer (QPWrapperB200, FilterBatch*) builds against the C ABI with a plain C++11 compiler."""
     subprocess.check_call(["make", "-C", os.path.join(ROOT, "asif_b200", "host"), "-s"])
     assert os.path.exists(os.path.join(ROOT, "asif_b200", "host", "host_check"))
+
+
+def test_loop_config_defaults_and_argument_checks(lib):
+    """asif_loop_config mirrors the example main loops' constants; argument errors are reported without a device."""
+    from asif_b200 import capi
+    L = lib
+    c = capi.LoopConfig()
+    assert L.asif_loop_config_init(C.byref(c)) == 0
+    assert c.struct_size == C.sizeof(capi.LoopConfig)
+    assert c.dt == 1e-3 and c.steps_per_sample == 1 and c.smooth_bounds == 0 and c.log_after_step == 1
+    assert (c.smooth_lb, c.smooth_ub) == (-20.0, 20.0) and c.plant_gain == 1.0
+    assert L.asif_engine_closed_loop(None, 1, C.byref(c), None, None, None, None, None, None, None, 0, None) == -1
+    assert b"NULL" in L.asif_last_error()
+    f = capi.loop_log_fields(2, 1, 2)
+    assert f["t"] == 0 and f["x0"] == 1 and f["xEstim0"] == 3 and f["relax1"] == f["rc"] - 1 and len(f) == 16
