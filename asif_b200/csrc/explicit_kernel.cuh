@@ -85,46 +85,101 @@ explicit_filter_kernel(const ExplicitParams p, const int64_t n, const double *__
 		for (int q = 0; q < NPSS; q++) r += (h[q] < h[j] || (h[q] == h[j] && q < j)) ? 1 : 0;
 		pos[j] = (ncUse < NPSS) ? r : j;
 	}
+	// Lfh = Dh f, Lgh = Dh g (src/asif.cpp:276-285), A = [Lgh | h], b = -Lfh (:295-303); safety function j lands in row
+	// pos[j] when it is among the selected ones
+	double lgv[NPSS][NU], rhsv[NPSS];
 #pragma unroll
-	for (int jj = 0; jj < NPSS; jj++) {
-		const int j = jj; // safety function jj lands in row pos[jj] when it is among the selected ones
-		if (pos[jj] >= ncUse) continue;
-		// Lfh = Dh f, Lgh = Dh g (src/asif.cpp:276-285), A = [Lgh | h], b = -Lfh (:295-303)
+	for (int j = 0; j < NPSS; j++) {
 		double lf = Dh[j] * f[0];
 #pragma unroll
 		for (int m = 1; m < NX; m++) lf = lf + Dh[j + m * NPSS] * f[m];
+		rhsv[j] = -lf;
 #pragma unroll
 		for (int i = 0; i < NU; i++) {
 			double lg = Dh[j] * g[i * NX];
 #pragma unroll
 			for (int m = 1; m < NX; m++) lg = lg + Dh[j + m * NPSS] * g[m + i * NX];
-			rows[(pos[jj] * (NV + 1) + i) * T] = lg;
+			lgv[j][i] = lg;
 		}
-		rows[(pos[jj] * (NV + 1) + NU) * T] = h[j];
-		rows[(pos[jj] * (NV + 1) + NV) * T] = -lf;
 	}
-	RegRows<NV, NC> R;
-	R.rows = rows;
-	R.stride = T;
-	R.nc = ncUse;
-	double c[NV], v[NV];
-	DiagMetric<NV> mt;
+	constexpr bool CLOSED_FORM = (NU == 1); // one input, relax variable fixed: the QP is an interval intersection
+	if (!CLOSED_FORM || WITH_DIAG) {
 #pragma unroll
-	for (int i = 0; i < NU; i++) {
-		c[i] = -2.0 * ud[i];
-		R.lb[i] = p.lb[i];
-		R.ub[i] = p.ub[i];
-	}
-	c[NU] = -2.0 * p.relaxCost * p.relaxLb;
-	R.lb[NU] = p.relaxLb; // both bounds pinned (src/asif.cpp:88-91)
-	R.ub[NU] = p.relaxLb;
+		for (int j = 0; j < NPSS; j++) {
+			if (pos[j] >= ncUse) continue;
 #pragma unroll
-	for (int i = 0; i < NV; i++) {
-		mt.gi[i] = p.gi[i];
-		mt.gih[i] = p.gih[i];
+			for (int i = 0; i < NU; i++) rows[(pos[j] * (NV + 1) + i) * T] = lgv[j][i];
+			rows[(pos[j] * (NV + 1) + NU) * T] = h[j];
+			rows[(pos[j] * (NV + 1) + NV) * T] = rhsv[j];
+		}
 	}
-	int iters = 0;
-	const int st = qp_gi_solve<NV>(mt, c, R, v, &iters);
+	double v[NV];
+	int iters = 0, st;
+	if (CLOSED_FORM) {
+		// delta is pinned to relaxLb by both bounds (src/asif.cpp:88-91), so row j reads  Lgh_j u >= -Lfh_j - h_j relaxLb:
+		// a lower bound on u when Lgh_j > 0, an upper bound when < 0, a feasibility condition when == 0, and
+		// u* = clamp(uDes) onto the intersection with [lb, ub] -- the exact optimum of the QP the reference hands to OSQP
+		// (SURVEY 8c known-answer anchor ii).  Bounds are kept as fractions r/a and compared by cross-multiplication:
+		// one division per state.
+		double alo = 1.0, rlo = p.lb[0], ahi = -1.0, rhi = -p.ub[0];
+		bool feasible = true;
+		bool row_lo = false, row_hi = false;
+#pragma unroll
+		for (int j = 0; j < NPSS; j++) {
+			if (pos[j] >= ncUse) continue;
+			const double a = lgv[j][0];
+			const double r = rhsv[j] - h[j] * p.relaxLb;
+			if (a > 0.0) {
+				if (r * alo > rlo * a) {
+					alo = a;
+					rlo = r;
+					row_lo = true;
+				}
+			} else if (a < 0.0) {
+				if (r * ahi < rhi * a) {
+					ahi = a;
+					rhi = r;
+					row_hi = true;
+				}
+			} else {
+				feasible = feasible && !(r > 0.0);
+			}
+		}
+		feasible = feasible && (rlo * ahi >= rhi * alo);
+		double u = ud[0];
+		if (u * alo < rlo) {
+			u = rlo / alo;
+			iters = row_lo ? 1 : 0;
+		} else if (u * ahi < rhi) {
+			u = rhi / ahi;
+			iters = row_hi ? 1 : 0;
+		}
+		v[0] = u;
+		v[NU] = p.relaxLb;
+		st = feasible ? QP_OK : QP_PRIMAL_INFEASIBLE;
+	} else {
+		RegRows<NV, NC> R;
+		R.rows = rows;
+		R.stride = T;
+		R.nc = ncUse;
+		double c[NV];
+		DiagMetric<NV> mt;
+#pragma unroll
+		for (int i = 0; i < NU; i++) {
+			c[i] = -2.0 * ud[i];
+			R.lb[i] = p.lb[i];
+			R.ub[i] = p.ub[i];
+		}
+		c[NU] = -2.0 * p.relaxCost * p.relaxLb;
+		R.lb[NU] = p.relaxLb; // both bounds pinned (src/asif.cpp:88-91)
+		R.ub[NU] = p.relaxLb;
+#pragma unroll
+		for (int i = 0; i < NV; i++) {
+			mt.gi[i] = p.gi[i];
+			mt.gih[i] = p.gih[i];
+		}
+		st = qp_gi_solve<NV>(mt, c, R, v, &iters);
+	}
 	if (live) {
 		if (st == QP_OK) {
 #pragma unroll
