@@ -145,7 +145,9 @@ int launch_filter(asif_engine *e, int64_t n, const double *x, const double *ud, 
 		return launch_explicit<DoubleIntegratorExplicit>(e, n, x, ud, ua, relax, rc, diag, st);
 	case ASIF_FILTER_IMPLICIT_TB:
 		switch (e->cfg.model) {
-		case ASIF_MODEL_DOUBLE_INTEGRATOR_TB: return launch_tb<DoubleIntegratorTB, 4>(e, n, x, ud, ua, relax, rc, diag, st);
+		case ASIF_MODEL_DOUBLE_INTEGRATOR_TB:
+			if (e->cfg.npBTSS != 4) return launch_tb<DoubleIntegratorTB, TB_NPBTSS_RUNTIME>(e, n, x, ud, ua, relax, rc, diag, st);
+			return launch_tb<DoubleIntegratorTB, 4>(e, n, x, ud, ua, relax, rc, diag, st);
 		case ASIF_MODEL_SEGWAY: return launch_tb_segway(e, false, n, x, ud, ua, relax, rc, diag, st);
 		case ASIF_MODEL_SEGWAY_SHIPPED: return launch_tb_segway(e, true, n, x, ud, ua, relax, rc, diag, st);
 		}
@@ -182,7 +184,9 @@ int launch_rollout(asif_engine *e, int64_t n, int32_t steps, double dt, double *
 	if (n <= 0) return ASIF_OK;
 	if (e->cfg.filter == ASIF_FILTER_IMPLICIT_TB) {
 		switch (e->cfg.model) {
-		case ASIF_MODEL_DOUBLE_INTEGRATOR_TB: return launch_tb_rollout<DoubleIntegratorTB, 4>(e, n, steps, dt, x, ud, ua, rc, st);
+		case ASIF_MODEL_DOUBLE_INTEGRATOR_TB:
+			if (e->cfg.npBTSS != 4) return launch_tb_rollout<DoubleIntegratorTB, TB_NPBTSS_RUNTIME>(e, n, steps, dt, x, ud, ua, rc, st);
+			return launch_tb_rollout<DoubleIntegratorTB, 4>(e, n, steps, dt, x, ud, ua, rc, st);
 		case ASIF_MODEL_SEGWAY: return launch_tb_rollout_segway(e, false, n, steps, dt, x, ud, ua, rc, st);
 		case ASIF_MODEL_SEGWAY_SHIPPED: return launch_tb_rollout_segway(e, true, n, steps, dt, x, ud, ua, rc, st);
 		}
@@ -350,9 +354,9 @@ int32_t asif_engine_create(const asif_engine_config *cfg, asif_engine **out)
 			delete e;
 			return fail(ASIF_ERR_UNSUPPORTED, "implicit-TB filter: model %d not compiled in", cfg->model);
 		}
-		if (cfg->npBTSS != 4) {
+		if (cfg->npBTSS < 1 || cfg->npBTSS > np_capacity(TB_NPBTSS_RUNTIME)) {
 			delete e;
-			return fail(ASIF_ERR_UNSUPPORTED, "implicit-TB filter: npBTSS = %d not compiled in (4 is)", cfg->npBTSS);
+			return fail(ASIF_ERR_UNSUPPORTED, "implicit-TB filter: npBTSS = %d outside 1..%d", cfg->npBTSS, np_capacity(TB_NPBTSS_RUNTIME));
 		}
 		if (!(cfg->backTrajDt > 0) || !(cfg->backTrajHorizon > 0)) {
 			delete e;
@@ -387,6 +391,7 @@ int32_t asif_engine_create(const asif_engine_config *cfg, asif_engine **out)
 			return fail(ASIF_ERR_INVALID_ARGUMENT, "backup trajectory of %lld points is not sensible", (long long)npBT);
 		}
 		p.npBT = (int32_t)npBT;
+		p.npBTSS = cfg->npBTSS;
 		// updateOptions() clamps satSharpness to [0.01, 2] (src/asif_implicit_tb.cpp:391-400); initialize() does not.
 		p.sat_mode = make_softsat(cfg->satSharpness, cfg->lb, cfg->ub, nu, p.sat);
 		p.gi[nu] = 1.0 / (2.0 * cfg->relaxCost);
@@ -414,9 +419,9 @@ int32_t asif_engine_create(const asif_engine_config *cfg, asif_engine **out)
 			delete e;
 			return fail(ASIF_ERR_UNSUPPORTED, "implicit filter: model %d not compiled in", cfg->model);
 		}
-		if (cfg->npBTSS != 10) {
+		if (cfg->npBTSS < 1 || cfg->npBTSS > np_capacity(IMP_NPBTSS_RUNTIME)) {
 			delete e;
-			return fail(ASIF_ERR_UNSUPPORTED, "implicit filter: npBTSS = %d not compiled in (10 is)", cfg->npBTSS);
+			return fail(ASIF_ERR_UNSUPPORTED, "implicit filter: npBTSS = %d outside 1..%d", cfg->npBTSS, np_capacity(IMP_NPBTSS_RUNTIME));
 		}
 		if (!(cfg->backTrajDt > 0) || !(cfg->backTrajHorizon > 0)) {
 			delete e;
@@ -451,6 +456,7 @@ int32_t asif_engine_create(const asif_engine_config *cfg, asif_engine **out)
 			return fail(ASIF_ERR_INVALID_ARGUMENT, "backup trajectory of %lld points is not sensible", (long long)npBT);
 		}
 		p.npBT = (int32_t)npBT;
+		p.npBTSS = cfg->npBTSS;
 		p.sat_mode = make_softsat(cfg->satSharpness, cfg->lb, cfg->ub, nu, p.sat);
 		for (int i = nu; i < nu + 2; i++) {
 			p.gi[i] = 1.0 / (2.0 * cfg->relaxCost);

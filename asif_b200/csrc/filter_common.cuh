@@ -41,6 +41,13 @@ enum : int {
 // sign of an exact zero.  PG = general (no assumption).
 enum : int { PZ = 0, P1 = 1, PG = 2, PM1 = 3 }; // PM1: the literal -1.0 (only used for the safety-set Jacobian)
 
+// npBTSS as a template value: N > 0 is the count itself (everything unrolled: the tuned instantiations, 4 for the TB
+// examples, 10 for the implicit one); N < 0 is a list CAPACITY of -N with the count taken from the options at run time (1 <= npBTSS <= -N).  The
+// first npBTSS entries of an ascending list of the -N smallest points are the npBTSS smallest points in the same
+// order and with the same tie handling, so the run-time variant only has to look at fewer entries when it builds rows.
+__host__ __device__ constexpr int np_capacity(const int n) { return n > 0 ? n : -n; }
+__host__ __device__ constexpr bool np_runtime(const int n) { return n < 0; }
+
 // Options of ASIFimplicitTB (include/asif_implicit_tb.h:19-33) + what initialize() derives from them
 // (src/asif_implicit_tb.cpp:169-223).
 struct TbParams {
@@ -49,6 +56,8 @@ struct TbParams {
 	double backTrajHorizon, backTrajDt, backTrajMinOrtho, inf;
 	int32_t npBT; // trajectory points (npBT-1 Euler steps)
 	int32_t sat_mode;
+	int32_t npBTSS; // critical trajectory points (read by the run-time-count instantiations only)
+	int32_t pad_;
 	const double *t_of_index; // device: t_0 = 0, t_i = t_{i-1} + dt (src/asif_implicit_tb.cpp:465,475)
 	SoftSat sat;
 	// QP metric: gi = 1/(2 H_ii), gih = sqrt(gi) for v = (u, relax)

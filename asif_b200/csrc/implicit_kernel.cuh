@@ -20,24 +20,32 @@ struct ImplicitParams {
 	double backTrajDt, inf;
 	int32_t npBT;
 	int32_t sat_mode;
+	int32_t npBTSS; // critical trajectory points (read by the run-time-count instantiation only)
+	int32_t pad_;
 	SoftSat sat;
 	double gi[MAX_NV], gih[MAX_NV];
 };
 
+constexpr int IMP_NPBTSS_RUNTIME = -16; // generic instantiation: any npBTSS in 1..16 (see np_capacity in tb_kernel.cuh)
+
 template <class M, int NPBTSS>
 __host__ __device__ constexpr int imp_smem_doubles_per_thread()
 {
-	return NPBTSS * (M::NX + M::NX * M::NX);
+	return np_capacity(NPBTSS) * (M::NX + M::NX * M::NX);
 }
 
 template <class M, int NPBTSS>
 struct ImpRows {
 	static constexpr int NX = M::NX, NU = M::NU, NPSS = M::NPSS, NPBS = M::NPBS, NS = NX + NX * NX;
-	static constexpr int NSAFE = NPBTSS * NPSS, NC = NSAFE + NPBS, NV = NU + 2;
+	static constexpr int CAP = np_capacity(NPBTSS), NV = NU + 2;
+	int np; // critical points in use (== NPBTSS when that is a compile-time count)
+	__device__ __forceinline__ int count_np() const { return np_runtime(NPBTSS) ? np : NPBTSS; }
+	__device__ __forceinline__ int nsafe() const { return count_np() * NPSS; }
+	__device__ __forceinline__ int nc() const { return count_np() * NPSS + NPBS; }
 	const double *snap;
 	int T;
 	double f[NX], g[NX * NU];
-	int kslot[NPBTSS];
+	int kslot[CAP];
 	double lgB[NPBS][NU], hB[NPBS], rhsB[NPBS]; // backup rows
 	double lb[NV], ub[NV];
 
@@ -84,11 +92,12 @@ struct ImpRows {
 	template <class F, class FB>
 	__device__ __forceinline__ void scan(F &&fn, FB &&fb) const
 	{
+		const int NSAFE = nsafe(), NC = nc();
 #pragma unroll 1
-		for (int s = 0; s < NPBTSS; s++) {
+		for (int s = 0; s < count_np(); s++) {
 			int slot = 0;
 #pragma unroll
-			for (int t = 0; t < NPBTSS; t++) slot = (t == s) ? kslot[t] : slot;
+			for (int t = 0; t < CAP; t++) slot = (t == s) ? kslot[t] : slot;
 			double n[NPSS][NV], rhs[NPSS];
 			point_rows(slot, n, rhs);
 #pragma unroll
@@ -105,6 +114,7 @@ struct ImpRows {
 	}
 	__device__ __forceinline__ void get(const int j, double (&n)[NV], double &rhs) const
 	{
+		const int NSAFE = nsafe(), NC = nc();
 		if (j >= NC) {
 			bound_row(j - NC, n, rhs);
 		} else if (j >= NSAFE) {
@@ -113,7 +123,7 @@ struct ImpRows {
 			const int s = j / NPSS, jj = j - s * NPSS;
 			int slot = 0;
 #pragma unroll
-			for (int t = 0; t < NPBTSS; t++) slot = (t == s) ? kslot[t] : slot;
+			for (int t = 0; t < CAP; t++) slot = (t == s) ? kslot[t] : slot;
 			double nn[NPSS][NV], rr[NPSS];
 			point_rows(slot, nn, rr);
 #pragma unroll
@@ -136,8 +146,10 @@ implicit_filter_kernel(const ImplicitParams p, const int64_t n, const double *__
 {
 	constexpr int NX = M::NX, NU = M::NU, NPSS = M::NPSS, NPBS = M::NPBS;
 	constexpr int NS = NX + NX * NX;
-	constexpr int NSAFE = NPBTSS * NPSS, NC = NSAFE + NPBS, NV = NU + 2;
-	constexpr int NDIAG = 2 + NPBTSS + NC * NV + NC;
+	constexpr int NV = NU + 2, CAP = np_capacity(NPBTSS);
+	const int np = np_runtime(NPBTSS) ? p.npBTSS : NPBTSS;
+	const int NC = np * NPSS + NPBS;
+	const int NDIAG = 2 + np + NC * NV + NC;
 
 	extern __shared__ double smem[];
 	const int T = blockDim.x;
@@ -158,6 +170,7 @@ implicit_filter_kernel(const ImplicitParams p, const int64_t n, const double *__
 	for (int j = 1; j < NPSS; j++) hSafetyNow = (hs[j] < hSafetyNow) ? hs[j] : hSafetyNow;
 
 	ImpRows<M, NPBTSS> R;
+	R.np = np;
 	R.snap = snap;
 	R.T = T;
 	double X[NS];
@@ -167,10 +180,10 @@ implicit_filter_kernel(const ImplicitParams p, const int64_t n, const double *__
 	for (int i = 0; i < NX; i++) X[i] = x0[i];
 #pragma unroll
 	for (int i = 0; i < NX; i++) X[NX + i * (NX + 1)] = 1.0;
-	double key[NPBTSS];
-	int kidx[NPBTSS];
+	double key[CAP];
+	int kidx[CAP];
 #pragma unroll
-	for (int s = 0; s < NPBTSS; s++) {
+	for (int s = 0; s < CAP; s++) {
 		key[s] = INFINITY;
 		kidx[s] = -1;
 		R.kslot[s] = s;
@@ -196,15 +209,15 @@ implicit_filter_kernel(const ImplicitParams p, const int64_t n, const double *__
 #pragma unroll
 			for (int j = 1; j < NPSS; j++) hmin = (hs[j] < hmin) ? hs[j] : hmin;
 		}
-		if (hmin < key[NPBTSS - 1]) {
-			const int slot = R.kslot[NPBTSS - 1];
+		if (hmin < key[CAP - 1]) {
+			const int slot = R.kslot[CAP - 1];
 #pragma unroll
 			for (int e = 0; e < NS; e++) snap[(slot * NS + e) * T] = X[e];
 			double ck = hmin;
 			int ci = i, cs = slot;
 			bool ins = false;
 #pragma unroll
-			for (int s = 0; s < NPBTSS; s++) {
+			for (int s = 0; s < CAP; s++) {
 				const bool sw = ins || (ck < key[s]);
 				ins = sw;
 				const double tk = key[s];
@@ -299,8 +312,9 @@ implicit_filter_kernel(const ImplicitParams p, const int64_t n, const double *__
 			d[0] = hSafetyNow;
 			d[1] = hBackupEnd;
 #pragma unroll
-			for (int s = 0; s < NPBTSS; s++) d[2 + s] = (double)kidx[s];
-			double *A = d + 2 + NPBTSS, *b = A + NC * NV;
+			for (int s = 0; s < CAP; s++)
+				if (s < np) d[2 + s] = (double)kidx[s];
+			double *A = d + 2 + np, *b = A + NC * NV;
 			R.scan(
 			    [&](const int j, const double(&nn)[NV], const double rhs) {
 #pragma unroll

@@ -18,6 +18,9 @@ namespace asifb {
 int launch_tb_segway(asif_engine *e, bool shipped, int64_t n, const double *x, const double *ud, double *ua, double *relax,
                      int32_t *rc, double *diag, cudaStream_t st)
 {
+	if (e->cfg.npBTSS != 4) // any other count: the run-time-count instantiation (centred and shipped backup sets)
+		return shipped ? launch_tb<SegwayTB<false>, TB_NPBTSS_RUNTIME>(e, n, x, ud, ua, relax, rc, diag, st)
+		               : launch_tb<SegwayTB<true>, TB_NPBTSS_RUNTIME>(e, n, x, ud, ua, relax, rc, diag, st);
 	return shipped ? launch_tb<SegwayTB<false>, 4>(e, n, x, ud, ua, relax, rc, diag, st)
 	               : launch_tb<SegwayTB<true>, 4>(e, n, x, ud, ua, relax, rc, diag, st);
 }
@@ -25,15 +28,18 @@ int launch_tb_segway(asif_engine *e, bool shipped, int64_t n, const double *x, c
 int launch_tb_rollout_segway(asif_engine *e, bool shipped, int64_t n, int32_t steps, double dt, double *x, const double *ud,
                              double *ua, int32_t *rc, cudaStream_t st)
 {
+	if (e->cfg.npBTSS != 4)
+		return shipped ? launch_tb_rollout<SegwayTB<false>, TB_NPBTSS_RUNTIME>(e, n, steps, dt, x, ud, ua, rc, st)
+		               : launch_tb_rollout<SegwayTB<true>, TB_NPBTSS_RUNTIME>(e, n, steps, dt, x, ud, ua, rc, st);
 	return shipped ? launch_tb_rollout<SegwayTB<false>, 4>(e, n, steps, dt, x, ud, ua, rc, st)
 	               : launch_tb_rollout<SegwayTB<true>, 4>(e, n, steps, dt, x, ud, ua, rc, st);
 }
 
-int launch_implicit_ip(asif_engine *e, int64_t n, const double *x, const double *ud, double *ua, double *relax, int32_t *rc,
-                       double *diag, cudaStream_t st)
+template <int NPBTSS>
+static int launch_implicit_ip_np(asif_engine *e, int64_t n, const double *x, const double *ud, double *ua, double *relax,
+                                 int32_t *rc, double *diag, cudaStream_t st)
 {
 	using M = InvertedPendulumImplicit;
-	constexpr int NPBTSS = 10;
 	const size_t smem = sizeof(double) * imp_smem_doubles_per_thread<M, NPBTSS>() * IMP_THREADS;
 	const unsigned blocks = (unsigned)((n + IMP_THREADS - 1) / IMP_THREADS);
 	const bool pow2 = e->im.sat_mode >= SAT_POW2;
@@ -50,6 +56,13 @@ int launch_implicit_ip(asif_engine *e, int64_t n, const double *x, const double 
 	}
 	CUDA_TRY(cudaGetLastError());
 	return ASIF_OK;
+}
+
+int launch_implicit_ip(asif_engine *e, int64_t n, const double *x, const double *ud, double *ua, double *relax, int32_t *rc,
+                       double *diag, cudaStream_t st)
+{
+	if (e->cfg.npBTSS != 10) return launch_implicit_ip_np<IMP_NPBTSS_RUNTIME>(e, n, x, ud, ua, relax, rc, diag, st);
+	return launch_implicit_ip_np<10>(e, n, x, ud, ua, relax, rc, diag, st);
 }
 
 } // namespace asifb

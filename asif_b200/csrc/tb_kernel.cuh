@@ -38,34 +38,36 @@ constexpr int TB_STEP_UNROLL = ASIF_TB_STEP_UNROLL;
 #define ASIF_TB_MINBLOCKS_NX2 6 // 80 registers: 24 warps/SM; measured 5.41 ms vs 6.23 ms at 4 (16 warps/SM) for 1e7 C2 states
 #endif
 
-template <int NPBTSS>
-struct TbDiagLayout {
-	// [TTS, BTorthoBS, hSafetyNow, hBackupEnd, critIdx[NPBTSS], A (nc*nv col-major), b (nc)]
-	static constexpr int HEAD = 4 + NPBTSS;
-};
+constexpr int TB_NPBTSS_RUNTIME = -8; // generic TB instantiation: any npBTSS in 1..8
+
+// diag record: [TTS, BTorthoBS, hSafetyNow, hBackupEnd, critIdx[npBTSS], A (nc*nv col-major), b (nc)]
+__host__ __device__ constexpr int tb_diag_head(const int np) { return 4 + np; }
 
 // shared memory doubles per thread: NPBTSS critical-point snapshots + the hit point
 template <class M, int NPBTSS>
 __host__ __device__ constexpr int tb_smem_doubles_per_thread()
 {
-	return (NPBTSS + 1) * (M::NX + M::NX * M::NX);
+	return (np_capacity(NPBTSS) + 1) * (M::NX + M::NX * M::NX);
 }
 
 // Rows of the TB QP (src/asif_implicit_tb.cpp:554-674), computed on demand.
 template <class M, int NPBTSS>
 struct TbRows {
 	static constexpr int NX = M::NX, NU = M::NU, NPSS = M::NPSS, NS = NX + NX * NX;
-	static constexpr int NC = NPBTSS * NPSS + 2, NV = NU + 1;
+	static constexpr int CAP = np_capacity(NPBTSS), NV = NU + 1;
+	__device__ __forceinline__ int count_np() const { return np_runtime(NPBTSS) ? np : NPBTSS; }
+	__device__ __forceinline__ int nc() const { return count_np() * NPSS + 2; }
 	const double *snap; // this thread's view, element stride T
 	int T;
 	double f[NX], g[NX * NU]; // open-loop dynamics at the current state (:416-418)
-	int kslot[NPBTSS];
+	int kslot[CAP];
 	int nkept;
 	bool trivial;         // inside the backup set: A = 0, b = -inf (:716-733)
 	double lgT[NU], rhsT; // time-to-safety row
 	double lgO[NU], rhsO; // orthogonality row
 	double lb[NV], ub[NV];
 	double neg_inf;
+	int np; // critical points in use, set for the run-time-count instantiations only
 
 	// the NPSS safety rows of the critical point stored in `slot` (:567-585, :643-674)
 	__device__ __forceinline__ void point_rows(const int slot, double (&n)[NPSS][NV], double (&rhs)[NPSS]) const
@@ -99,13 +101,14 @@ struct TbRows {
 	__device__ __forceinline__ void scan(F &&fn, FB &&fb) const
 	{
 		if (!trivial) {
+			const int NC = nc();
 #pragma unroll 1
-			for (int s = 0; s < NPBTSS; s++) { // not unrolled: one copy of point_rows keeps registers down
+			for (int s = 0; s < count_np(); s++) { // not unrolled: one copy of point_rows keeps registers down
 				double n[NPSS][NV], rhs[NPSS];
 				if (s < nkept) {
 					int slot = 0;
 #pragma unroll
-					for (int t = 0; t < NPBTSS; t++) slot = (t == s) ? kslot[t] : slot;
+					for (int t = 0; t < CAP; t++) slot = (t == s) ? kslot[t] : slot;
 					point_rows(slot, n, rhs);
 				} else { // h = 1, Dh = 0 (:556-566)
 #pragma unroll
@@ -129,10 +132,11 @@ struct TbRows {
 			fn(NC - 1, n, rhsO);
 		}
 #pragma unroll
-		for (int k = 0; k < 2 * NV; k++) fb(NC + k, k >> 1, (k & 1) != 0, (k & 1) ? -ub[k >> 1] : lb[k >> 1]);
+		for (int k = 0; k < 2 * NV; k++) fb(nc() + k, k >> 1, (k & 1) != 0, (k & 1) ? -ub[k >> 1] : lb[k >> 1]);
 	}
 	__device__ __forceinline__ void get(const int j, double (&n)[NV], double &rhs) const
 	{
+		const int NC = nc();
 		if (j >= NC) {
 			bound_row(j - NC, n, rhs);
 		} else if (trivial) {
@@ -150,7 +154,7 @@ struct TbRows {
 			if (s < nkept) {
 				int slot = 0;
 #pragma unroll
-				for (int t = 0; t < NPBTSS; t++) slot = (t == s) ? kslot[t] : slot;
+				for (int t = 0; t < CAP; t++) slot = (t == s) ? kslot[t] : slot;
 				double nn[NPSS][NV], rr[NPSS];
 				point_rows(slot, nn, rr);
 #pragma unroll
@@ -174,7 +178,7 @@ struct TbRows {
 template <int NPBTSS>
 struct TbDiagRec {
 	double TTS, ortho, hSafetyNow, hBackupEnd;
-	int critIdx[NPBTSS];
+	int critIdx[np_capacity(NPBTSS)];
 	bool have_rows;
 };
 
@@ -190,6 +194,9 @@ __device__ __forceinline__ int32_t tb_filter_one(const TbParams &p, const double
 	constexpr int NX = M::NX, NU = M::NU, NPSS = M::NPSS;
 	constexpr int NS = NX + NX * NX;
 	constexpr int NV = NU + 1;
+	constexpr int CAP = np_capacity(NPBTSS);
+	const int np = np_runtime(NPBTSS) ? p.npBTSS : NPBTSS;
+	if (np_runtime(NPBTSS)) R.np = np;
 
 	// ---- filter(): h_BS(x), hSafetyNow (:278-283)
 	double hs[NPSS], Dhs[NPSS * NX];
@@ -208,10 +215,10 @@ __device__ __forceinline__ int32_t tb_filter_one(const TbParams &p, const double
 #pragma unroll
 	for (int i = 0; i < NX; i++) X[NX + i * (NX + 1)] = 1.0;
 
-	double key[NPBTSS]; // ascending; +inf = empty
-	int kidx[NPBTSS];
+	double key[CAP]; // ascending; +inf = empty
+	int kidx[CAP];
 #pragma unroll
-	for (int s = 0; s < NPBTSS; s++) {
+	for (int s = 0; s < CAP; s++) {
 		key[s] = INFINITY;
 		kidx[s] = -1;
 		R.kslot[s] = s;
@@ -256,16 +263,16 @@ __device__ __forceinline__ int32_t tb_filter_one(const TbParams &p, const double
 #pragma unroll
 			for (int j = 1; j < NPSS; j++) hmin = (hs[j] < hmin) ? hs[j] : hmin;
 		}
-		if (active && hmin < key[NPBTSS - 1]) {
+		if (active && hmin < key[CAP - 1]) {
 			// evict the largest key, insert (hmin, i) keeping ascending order; ties keep the earlier index first
-			const int slot = R.kslot[NPBTSS - 1];
+			const int slot = R.kslot[CAP - 1];
 #pragma unroll
 			for (int e = 0; e < NS; e++) snap[(slot * NS + e) * T] = X[e];
 			double ck = hmin;
 			int ci = i, cs = slot;
 			bool ins = false; // once placed, everything behind shifts by one
 #pragma unroll
-			for (int s = 0; s < NPBTSS; s++) {
+			for (int s = 0; s < CAP; s++) {
 				const bool sw = ins || (ck < key[s]);
 				ins = sw;
 				const double tk = key[s];
@@ -277,7 +284,7 @@ __device__ __forceinline__ int32_t tb_filter_one(const TbParams &p, const double
 				ci = sw ? ti : ci;
 				cs = sw ? ts : cs;
 			}
-			nkept = nkept < NPBTSS ? nkept + 1 : NPBTSS;
+			nkept = nkept < CAP ? nkept + 1 : CAP;
 		}
 		hit_now = active && (M::backup_set_value(X) >= 0.0);
 		if (__any_sync(0xffffffffu, hit_now)) {
@@ -290,7 +297,7 @@ __device__ __forceinline__ int32_t tb_filter_one(const TbParams &p, const double
 			active = false;
 			idxHit = i - 1;
 #pragma unroll
-			for (int e = 0; e < NS; e++) snap[(NPBTSS * NS + e) * T] = X[e];
+			for (int e = 0; e < NS; e++) snap[(CAP * NS + e) * T] = X[e];
 		}
 	}
 	if (WITH_DIAG) hBackupEnd = M::backup_set_value(X);
@@ -300,7 +307,7 @@ __device__ __forceinline__ int32_t tb_filter_one(const TbParams &p, const double
 	DiagMetric<NV> mt;
 	R.snap = snap;
 	R.T = T;
-	R.nkept = nkept;
+	R.nkept = (np_runtime(NPBTSS) && nkept > np) ? np : nkept;
 	R.trivial = inside;
 	R.neg_inf = -p.inf;
 #pragma unroll
@@ -347,7 +354,7 @@ __device__ __forceinline__ int32_t tb_filter_one(const TbParams &p, const double
 		// time-to-safety and orthogonality rows (:588-641)
 		double xh[NS];
 #pragma unroll
-		for (int e = 0; e < NS; e++) xh[e] = snap[(NPBTSS * NS + e) * T];
+		for (int e = 0; e < NS; e++) xh[e] = snap[(CAP * NS + e) * T];
 		double hBS, DhBS[NX], DDhBS[NX * NX], fCl[NX], DfCl[NX * NX];
 		M::backup_set(xh, hBS, DhBS, DDhBS);
 		backup_cl_dynamics<M, SATMODE>(p.sat, p.lb, p.ub, xh, fCl, DfCl);
@@ -458,7 +465,7 @@ __device__ __forceinline__ int32_t tb_filter_one(const TbParams &p, const double
 		dg.hSafetyNow = hSafetyNow;
 		dg.hBackupEnd = hBackupEnd;
 #pragma unroll
-		for (int s = 0; s < NPBTSS; s++) dg.critIdx[s] = (!inside && hit && s < nkept) ? kidx[s] : -1;
+		for (int s = 0; s < CAP; s++) dg.critIdx[s] = (!inside && hit && s < nkept) ? kidx[s] : -1;
 		dg.have_rows = inside || hit;
 	}
 	return rc;
@@ -492,9 +499,10 @@ __device__ __forceinline__ void tb_filter_tile(const TbParams &p, const int64_t 
                                                unsigned long long *__restrict__ qp_iter_sum)
 {
 	constexpr int NX = M::NX, NU = M::NU, NPSS = M::NPSS;
-	constexpr int NC = NPBTSS * NPSS + 2;
 	constexpr int NV = NU + 1;
-	constexpr int NDIAG = TbDiagLayout<NPBTSS>::HEAD + NC * NV + NC;
+	const int np = np_runtime(NPBTSS) ? p.npBTSS : NPBTSS;
+	const int NC = np * NPSS + 2;
+	const int NDIAG = tb_diag_head(np) + NC * NV + NC;
 
 	const bool live = k < n;
 	const int64_t kk = live ? k : (n - 1); // tail lanes redo the last state and do not store
@@ -523,8 +531,9 @@ __device__ __forceinline__ void tb_filter_tile(const TbParams &p, const int64_t 
 			d[2] = dg.hSafetyNow;
 			d[3] = dg.hBackupEnd;
 #pragma unroll
-			for (int s = 0; s < NPBTSS; s++) d[4 + s] = (double)dg.critIdx[s];
-			double *A = d + 4 + NPBTSS, *b = A + NC * NV;
+			for (int s = 0; s < np_capacity(NPBTSS); s++)
+				if (s < np) d[4 + s] = (double)dg.critIdx[s];
+			double *A = d + 4 + np, *b = A + NC * NV;
 			for (int j = 0; j < NC; j++) {
 				for (int i = 0; i < NV; i++) A[j + i * NC] = 0.0;
 				b[j] = (dg.have_rows && R.trivial) ? -p.inf : 0.0;

@@ -221,6 +221,7 @@ static void tb_parse_options(int cfg, const double *v, int n, tb_options *o)
 	o->relaxCost = v[0]; o->relaxSafeLb = v[1]; o->relaxTTS = v[2]; o->relaxMinOrtho = v[3];
 	o->backTrajHorizon = v[4]; o->backTrajExtend = v[5]; o->backTrajDt = v[6]; o->backTrajMinOrtho = v[7];
 	o->satSharpness = v[8];
+	if (n >= 13 && v[12] >= 1.0 && v[12] <= 16.0) o->npBTSS = (int)v[12]; /* constructor argument npBTSS */
 }
 
 /* src/asif_implicit_tb.cpp:177-182 */
@@ -721,6 +722,7 @@ static int make_ctx(int cfg, const double *opts, int n_opts, ctx_t *c)
 			o->relaxCost = opts[0]; o->relaxReachLb = opts[1]; o->relaxSafeLb = opts[2];
 			o->backTrajHorizon = opts[3]; o->backTrajDt = opts[4]; o->satSharpness = opts[5];
 		}
+		if (opts && n_opts >= 7 && opts[6] >= 1.0 && opts[6] <= 16.0) o->npBTSS = (int)opts[6]; /* constructor argument */
 		/* src/asif_implicit.cpp:211-216 (no backTrajExtend in this class) */
 		c->N = (int)round(o->backTrajHorizon / o->backTrajDt) + 1;
 		if (c->N < o->npBTSS) {

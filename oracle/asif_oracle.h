@@ -56,7 +56,7 @@ const oracle_model *oracle_get_model(int cfg, int variant);
 /* option vectors are the same plain-double arrays oracle/ref_build/ref_api.h takes:
  * explicit: [relaxLb, relaxCost]
  * TB      : [relaxCost, relaxSafeLb, relaxTTS, relaxMinOrtho, backTrajHorizon, backTrajExtend,
- *            backTrajDt, backTrajMinOrtho, satSharpness, (segway) centred]
+ *            backTrajDt, backTrajMinOrtho, satSharpness, (segway) centred, lb, ub, npBTSS]
  * implicit: [relaxCost, relaxReachLb, relaxSafeLb, backTrajHorizon, backTrajDt, satSharpness, npBTSS]
  */
 /* dims[0..5] = nx, nu, n_relax, nc, nv, n_diag ; returns 0 or -1 */

@@ -92,11 +92,18 @@ void ref_tb_options(const double *opts, int n_opts, ASIF::ASIFimplicitTB::Option
 	o.satSharpness = opts[8];
 }
 
+/* opts[12]: the constructor argument npBTSS (default: the example's) */
+uint32_t ref_tb_npbtss(const double *opts, int n_opts, uint32_t dflt)
+{
+	return (opts && n_opts >= 13 && opts[12] >= 1.0 && opts[12] <= 16.0) ? (uint32_t)opts[12] : dflt;
+}
+
 namespace {
 struct DiTb : RefFilter {
 	TbAccess f;
+	int npBTSS;
 	DiTb(const double *opts, int n_opts)
-	    : f(ex_di_tb::nx, ex_di_tb::nu, ex_di_tb::npSS, ex_di_tb::npBTSS, ex_di_tb::safetySet, di_tb_backup_set_fixed,
+	    : f(ex_di_tb::nx, ex_di_tb::nu, ex_di_tb::npSS, ref_tb_npbtss(opts, n_opts, ex_di_tb::npBTSS), ex_di_tb::safetySet, di_tb_backup_set_fixed,
 	        ex_di_tb::dynamicsWithGradient, ex_di_tb::backupController)
 	{
 		ASIF::ASIFimplicitTB::Options o;
@@ -113,12 +120,13 @@ struct DiTb : RefFilter {
 			ub[0] = opts[11];
 		}
 		f.initialize(lb, ub, o);
-		nx = 2; nu = 1; n_relax = 1; nc = 18; nv = 2; n_diag = 4 + 4 + nc * nv + nc;
+		npBTSS = (int)ref_tb_npbtss(opts, n_opts, ex_di_tb::npBTSS);
+		nx = 2; nu = 1; n_relax = 1; nc = npBTSS * 4 + 2; nv = 2; n_diag = 4 + npBTSS + nc * nv + nc;
 	}
 	int32_t filter(const double *x, const double *u_des, double *u_act, double *relax, double *diag) override
 	{
 		int32_t rc = f.filter(x, u_des, u_act, relax[0]);
-		if (diag) ref_tb_fill_diag(f, f.A(), f.b(), 4, nc, nv, diag);
+		if (diag) ref_tb_fill_diag(f, f.A(), f.b(), npBTSS, nc, nv, diag);
 		return rc;
 	}
 	void plant(const double *x, double *fo, double *go) override { ex_di_tb::dynamics(x, fo, go); }

@@ -25,8 +25,12 @@ struct ImplicitAccess : ASIF::ASIFimplicit {
 struct IpImplicit : RefFilter {
 	ImplicitAccess f;
 	int npBTSS;
+	static uint32_t np(const double *opts, int n_opts) /* opts[6]: the constructor argument npBTSS */
+	{
+		return (opts && n_opts >= 7 && opts[6] >= 1.0 && opts[6] <= 16.0) ? (uint32_t)opts[6] : ex_ip_implicit::npBTSS;
+	}
 	IpImplicit(const double *opts, int n_opts)
-	    : f(ex_ip_implicit::nx, ex_ip_implicit::nu, ex_ip_implicit::npSS, ex_ip_implicit::npBS, ex_ip_implicit::npBTSS,
+	    : f(ex_ip_implicit::nx, ex_ip_implicit::nu, ex_ip_implicit::npSS, ex_ip_implicit::npBS, np(opts, n_opts),
 	        ex_ip_implicit::safetySet, ex_ip_implicit::backupSet, ex_ip_implicit::dynamics,
 	        ex_ip_implicit::dynamicsGradients, ex_ip_implicit::backupController)
 	{
@@ -45,7 +49,7 @@ struct IpImplicit : RefFilter {
 			o.satSharpness = opts[5];
 		}
 		f.initialize(ex_ip_implicit::lb, ex_ip_implicit::ub, o);
-		npBTSS = ex_ip_implicit::npBTSS;
+		npBTSS = (int)np(opts, n_opts);
 		nx = 2; nu = 1; n_relax = 2; nc = npBTSS * 4 + 1; nv = 3; n_diag = 2 + npBTSS + nc * nv + nc;
 	}
 	int32_t filter(const double *x, const double *u_des, double *u_act, double *relax, double *diag) override

@@ -6,6 +6,7 @@ namespace ex_segway {
 }
 
 void ref_tb_fill_diag(const ASIF::ASIFimplicitTB &f, const double *A, const double *b, int npBTSS, int nc, int nv, double *diag);
+uint32_t ref_tb_npbtss(const double *opts, int n_opts, uint32_t dflt);
 void ref_tb_options(const double *opts, int n_opts, ASIF::ASIFimplicitTB::Options &o);
 
 namespace {
@@ -30,11 +31,13 @@ void segway_backup_set_centred(const double *x, double *h, double *Dh, double *D
 
 struct SegwayTb : RefFilter {
 	TbAccess *f;
+	int npBTSS;
 	SegwayTb(const double *opts, int n_opts)
 	{
 		bool centred = true;
 		if (opts && n_opts >= 10) centred = opts[9] != 0.0;
-		f = new TbAccess(ex_segway::nx, ex_segway::nu, ex_segway::npSS, ex_segway::npBTSS, ex_segway::safetySet,
+		npBTSS = (int)ref_tb_npbtss(opts, n_opts, ex_segway::npBTSS);
+		f = new TbAccess(ex_segway::nx, ex_segway::nu, ex_segway::npSS, (uint32_t)npBTSS, ex_segway::safetySet,
 		                 centred ? segway_backup_set_centred : ex_segway::backupSet, ex_segway::dynamics,
 		                 ex_segway::dynamicsGradients, ex_segway::backupController);
 		ASIF::ASIFimplicitTB::Options o;
@@ -48,13 +51,13 @@ struct SegwayTb : RefFilter {
 		o.backTrajMinOrtho = 0.001;
 		ref_tb_options(opts, n_opts, o);
 		f->initialize(ex_segway::lb, ex_segway::ub, o);
-		nx = 4; nu = 1; n_relax = 1; nc = 18; nv = 2; n_diag = 4 + 4 + nc * nv + nc;
+		nx = 4; nu = 1; n_relax = 1; nc = npBTSS * 4 + 2; nv = 2; n_diag = 4 + npBTSS + nc * nv + nc;
 	}
 	~SegwayTb() { delete f; }
 	int32_t filter(const double *x, const double *u_des, double *u_act, double *relax, double *diag) override
 	{
 		int32_t rc = f->filter(x, u_des, u_act, relax[0]);
-		if (diag) ref_tb_fill_diag(*f, f->A(), f->b(), 4, nc, nv, diag);
+		if (diag) ref_tb_fill_diag(*f, f->A(), f->b(), npBTSS, nc, nv, diag);
 		return rc;
 	}
 	void plant(const double *x, double *fo, double *go) override { ex_segway::dynamics(x, fo, go); }

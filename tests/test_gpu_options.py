@@ -64,3 +64,55 @@ def test_explicit_row_selection(ab, oracle, npSSmax):
     cf.assert_parity("npSSmax", (u, relax, rc), (u0, relax0, rc0))
     out2 = eng.filter_batch(x, ud)
     assert np.array_equal(out2[0], u) and np.array_equal(out2[2], rc)
+
+
+@pytest.mark.parametrize("model,npBTSS", [("di", 1), ("di", 3), ("di", 8), ("segway", 2), ("segway", 6), ("ip", 4), ("ip", 16)])
+def test_other_critical_point_counts(ab, oracle, model, npBTSS):
+    """npBTSS other than the examples' 4 / 10 runs the run-time-count instantiation (capacity 8 / 16)."""
+    if model == "di":
+        n, cfg = 30_000, 2
+        opts = list(cf.C2_TB_OPTS) + [0.0, -1.0, 1.0, float(npBTSS)]
+        x, ud = cf.c2_inputs(n, seed=700 + npBTSS)
+        eng = ab.Engine(ab.FILTER_IMPLICIT_TB, ab.MODEL_DOUBLE_INTEGRATOR_TB, npBTSS=npBTSS, **cf.tb_engine_kwargs(cf.C2_TB_OPTS))
+        head, nc = 4 + npBTSS, npBTSS * 4 + 2
+    elif model == "segway":
+        n, cfg = 4_000, 6
+        opts = list(cf.SEGWAY_TB_OPTS) + [-20.0, 20.0, float(npBTSS)]
+        x, ud = cf.c5_inputs(n, seed=700 + npBTSS)
+        eng = ab.Engine(ab.FILTER_IMPLICIT_TB, ab.MODEL_SEGWAY, npBTSS=npBTSS, **cf.tb_engine_kwargs(cf.SEGWAY_TB_OPTS))
+        head, nc = 4 + npBTSS, npBTSS * 4 + 2
+    else:
+        n, cfg = 20_000, 3
+        opts = list(cf.C3A_SHORT_OPTS) + [float(npBTSS)]
+        x, ud = cf.c3a_inputs(n, seed=700 + npBTSS)
+        eng = ab.Engine(ab.FILTER_IMPLICIT, ab.MODEL_INVERTED_PENDULUM, npBTSS=npBTSS, **cf.implicit_engine_kwargs(cf.C3A_SHORT_OPTS))
+        head, nc = 2 + npBTSS, npBTSS * 4 + 1
+    assert eng.nc == nc and eng.n_diag == head + nc * eng.nv + nc
+    u, relax, rc, diag = eng.filter_batch(x, ud, want_diag=True)
+    u0, relax0, rc0, diag0 = oracle.filter_batch(cfg, x, ud, opts, want_diag=True)
+    flips = int((rc != rc0).sum())
+    assert flips <= (0 if model == "di" else 2)
+    keep = rc == rc0
+    cf.assert_parity("npBTSS %s %d" % (model, npBTSS), (u[keep], relax[keep], rc[keep]), (u0[keep], relax0[keep], rc0[keep]))
+    lo = 4 if model != "ip" else 2
+    m = keep & (rc0 == 1) & np.all(diag[:, lo:lo + npBTSS] == diag0[:, lo:lo + npBTSS], axis=1)
+    assert m.sum() > 0.95 * (keep & (rc0 == 1)).sum()
+    cols = [c for c in range(diag.shape[1]) if not (model != "ip" and c == 3)]  # hBackupEnd_ is a previous-call diagnostic
+    d = np.abs(diag[m][:, cols] - diag0[m][:, cols]) / (1.0 + np.abs(diag0[m][:, cols]))
+    assert d.max() <= (0.0 if model == "di" else 1e-9)
+    out2 = eng.filter_batch(x, ud)
+    assert np.array_equal(out2[0], u) and np.array_equal(out2[2], rc)
+    if model == "di":  # the fused rollout uses the same instantiation
+        xr, ur, rcr, hist = eng.rollout(x[:2000], ud[:2000], 3, 1e-3)
+        xs = x[:2000].copy()
+        for _ in range(3):
+            ua = eng.filter_batch(xs, ud[:2000])[0]
+            xs = xs + 1e-3 * np.stack([xs[:, 1], ua[:, 0]], axis=1)
+        assert np.abs(xr - xs).max() < 1e-12
+
+
+def test_critical_point_count_limits(ab):
+    with pytest.raises(ab.AsifError):
+        ab.Engine(ab.FILTER_IMPLICIT_TB, ab.MODEL_DOUBLE_INTEGRATOR_TB, npBTSS=9)
+    with pytest.raises(ab.AsifError):
+        ab.Engine(ab.FILTER_IMPLICIT, ab.MODEL_INVERTED_PENDULUM, npBTSS=17)

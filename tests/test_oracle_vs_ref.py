@@ -70,3 +70,27 @@ def test_explicit_row_selection(oracle, reflib, npSSmax):
     if nc < 4:  # selected h values (column 1 of A_) ascend
         hsel = diag[:, nc:2 * nc]
         assert np.all(np.diff(hsel, axis=1) >= 0)
+
+
+@pytest.mark.parametrize("cfg,npBTSS", [(pyref.CFG_DI_IMPLICIT_TB, 1), (pyref.CFG_DI_IMPLICIT_TB, 3), (pyref.CFG_DI_IMPLICIT_TB, 8),
+                                        (pyref.CFG_IP_IMPLICIT, 4), (pyref.CFG_IP_IMPLICIT, 16), (pyref.CFG_SEGWAY_TB, 2)])
+def test_other_critical_point_counts(oracle, reflib, cfg, npBTSS):
+    """npBTSS is a constructor argument of the implicit classes (include/asif_implicit_tb.h:36-48): other values than the
+    examples' 4 / 10 change the number of rows, the padding and the diag layout."""
+    if cfg == pyref.CFG_DI_IMPLICIT_TB:
+        opts, (x, ud) = list(cf.C2_TB_OPTS) + [0.0, -1.0, 1.0, float(npBTSS)], cf.c2_inputs(600, seed=40 + npBTSS)
+    elif cfg == pyref.CFG_SEGWAY_TB:
+        opts, (x, ud) = list(cf.SEGWAY_TB_OPTS) + [-20.0, 20.0, float(npBTSS)], cf.c5_inputs(150, seed=40 + npBTSS)
+    else:
+        opts, (x, ud) = list(cf.C3A_SHORT_OPTS) + [float(npBTSS)], cf.c3a_inputs(600, seed=40 + npBTSS)
+    f = reflib.create(cfg, opts)
+    u0, relax0, rc0, diag0, st0, it0 = f.filter_batch_ex(x, ud)
+    u, relax, rc, diag = oracle.filter_batch(cfg, x, ud, opts, want_diag=True)
+    npss = 4
+    nc = npBTSS * npss + (1 if cfg == pyref.CFG_IP_IMPLICIT else 2)
+    assert f.nc == nc and diag.shape == diag0.shape
+    k = ~cf.unpinned_mask(rc0, rc, relax, st0)
+    assert k.mean() > 0.9
+    cf.assert_parity("npBTSS", (u[k], relax[k], rc[k]), (u0[k], relax0[k], rc0[k]))
+    m = k & (rc0 == 1)
+    assert m.sum() > 20 and np.array_equal(diag[m], diag0[m])
