@@ -114,8 +114,11 @@ int launch_explicit(asif_engine *e, int64_t n, const double *x, const double *ud
 int launch_robust(asif_engine *e, int64_t n, const double *x, const double *ud, double *ua, double *relax, int32_t *rc,
                   double *diag, cudaStream_t st)
 {
-	const size_t smem = sizeof(double) * 2 * (size_t)e->rb.n_halfplanes;
+	const size_t smem = sizeof(double) * 4 * (size_t)e->rb.n_halfplanes;
 	const unsigned blocks = (unsigned)((n + ROB_THREADS - 1) / ROB_THREADS);
+	int r = set_smem(robust_ip_filter_kernel<true>, smem); // tables beyond 1536 half-planes need the opt-in shared-memory size
+	if (!r) r = set_smem(robust_ip_filter_kernel<false>, smem);
+	if (r) return r;
 	if (diag)
 		robust_ip_filter_kernel<true><<<blocks, ROB_THREADS, smem, st>>>(e->rb, n, x, ud, ua, relax, rc, diag, e->d_counters);
 	else

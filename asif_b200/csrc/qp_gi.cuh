@@ -182,6 +182,14 @@ __device__ __forceinline__ void qp_rebuild(QpWork<NV> &w, const Rows &rows, cons
 	}
 }
 
+// Row scan at the current iterate.  The default ignores the iterate; a row functor whose rows come in families of which
+// only one member can be the most violated at a given point overloads this (found by ADL) to present that member only.
+template <int NV, class Rows, class F, class FB>
+__device__ __forceinline__ void qp_scan_rows(const Rows &rows, const double (&)[NV], F &&fn, FB &&fb)
+{
+	rows.scan(fn, fb);
+}
+
 // v returns the minimiser when the result is QP_OK.
 // iters (optional) returns the number of rows processed (for the K-bar statistic).
 template <int NV, class Rows, class Metric>
@@ -206,7 +214,8 @@ __device__ __forceinline__ int qp_gi_solve(const Metric &mt, const double (&c)[N
 		double np_[NV];
 #pragma unroll
 		for (int i = 0; i < NV; i++) np_[i] = 0.0;
-		rows.scan(
+		qp_scan_rows(
+		    rows, w.v,
 		    [&](const int j, const double(&n)[NV], const double rhs) {
 			    double s = -rhs;
 #pragma unroll

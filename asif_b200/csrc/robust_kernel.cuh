@@ -34,19 +34,18 @@ struct RobustParams {
 
 struct RobustRows {
 	static constexpr int NV = 2;
-	const double *tab; // shared memory
+	const double *tab; // shared memory, [K][4] = a0, a1, Lg- / Dh-independent part, Lg+ (the last two staged per CTA)
 	int K;
-	double x0, x1, f0, f1, gc, gr;
+	double x0, x1, f0, f1;
 	double lb[NV], ub[NV];
 	__device__ __forceinline__ void plane(const int k, double &h, double &lo, double &hi, double &lf) const
 	{
-		const double a0 = tab[2 * k], a1 = tab[2 * k + 1];
+		const double a0 = tab[4 * k], a1 = tab[4 * k + 1];
 		h = 1. - a0 * x0 - a1 * x1;
 		const double Dh0 = -a0, Dh1 = -a1;
 		lf = Dh0 * f0 + Dh1 * f1;
-		const double lgc = Dh1 * gc, lgr = fabs(Dh1 * gr);
-		lo = lgc - lgr;
-		hi = lgc + lgr;
+		lo = tab[4 * k + 2]; // Lg = Dh1 * [gc - gr, gc + gr] does not depend on the state
+		hi = tab[4 * k + 3];
 	}
 	__device__ __forceinline__ void bound_row(const int k, double (&n)[NV], double &rhs) const
 	{
@@ -74,6 +73,22 @@ struct RobustRows {
 #pragma unroll
 		for (int k = 0; k < 2 * NV; k++) fb(2 * K + k, k >> 1, (k & 1) != 0, (k & 1) ? -ub[k >> 1] : lb[k >> 1]);
 	}
+	// The two rows of a half-plane differ only in the u coefficient (Lg- <= Lg+): at an iterate with u >= 0 the Lg- row
+	// has the smaller residual, with u < 0 the Lg+ row.  The other one can be neither the most violated row nor
+	// violated at all when its sibling is active, so the solver's scan evaluates one row per half-plane.
+	template <class F, class FB>
+	__device__ __forceinline__ void scan_at(const double (&v)[NV], F &&fn, FB &&fb) const
+	{
+		const bool lower = v[0] >= 0.0;
+		for (int k = 0; k < K; k++) {
+			double h, lo, hi, lf;
+			plane(k, h, lo, hi, lf);
+			const double n[NV] = {lower ? lo : hi, h};
+			fn(2 * k + (lower ? 0 : 1), n, -lf);
+		}
+#pragma unroll
+		for (int k = 0; k < 2 * NV; k++) fb(2 * K + k, k >> 1, (k & 1) != 0, (k & 1) ? -ub[k >> 1] : lb[k >> 1]);
+	}
 	__device__ __forceinline__ void get(const int j, double (&n)[NV], double &rhs) const
 	{
 		if (j >= 2 * K) {
@@ -88,6 +103,12 @@ struct RobustRows {
 	}
 };
 
+template <class F, class FB>
+__device__ __forceinline__ void qp_scan_rows(const RobustRows &rows, const double (&v)[2], F &&fn, FB &&fb)
+{
+	rows.scan_at(v, fn, fb);
+}
+
 template <bool WITH_DIAG>
 __global__ void __launch_bounds__(ROB_THREADS)
 robust_ip_filter_kernel(const RobustParams p, const int64_t n, const double *__restrict__ x_in,
@@ -96,7 +117,15 @@ robust_ip_filter_kernel(const RobustParams p, const int64_t n, const double *__r
 {
 	extern __shared__ double tab[];
 	const int K = p.n_halfplanes;
-	for (int i = threadIdx.x; i < 2 * K; i += blockDim.x) tab[i] = p.table[i];
+	for (int i = threadIdx.x; i < K; i += blockDim.x) {
+		const double a0 = p.table[2 * i], a1 = p.table[2 * i + 1];
+		const double Dh1 = -a1;
+		const double lgc = Dh1 * p.gc, lgr = fabs(Dh1 * p.gr);
+		tab[4 * i] = a0;
+		tab[4 * i + 1] = a1;
+		tab[4 * i + 2] = lgc - lgr;
+		tab[4 * i + 3] = lgc + lgr;
+	}
 	__syncthreads();
 	const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	const bool live = k < n;
@@ -108,8 +137,6 @@ robust_ip_filter_kernel(const RobustParams p, const int64_t n, const double *__r
 	R.x1 = x_in[kk * 2 + 1];
 	R.f0 = R.x1;
 	R.f1 = sin(R.x0);
-	R.gc = p.gc;
-	R.gr = p.gr;
 	R.lb[0] = p.lb[0];
 	R.ub[0] = p.ub[0];
 	R.lb[1] = p.relaxLb;

@@ -83,3 +83,19 @@ def test_golden_on_gpu(ab):
     unp = cf.unpinned_mask(g["rc"], rc, relax, g["qp_status"])
     k = ~unp
     cf.assert_parity("golden C3b", (u[k], relax[k], rc[k]), (g["u_act"][k], g["relax"][k], g["rc"][k]))
+
+
+def test_robust_large_table(ab):
+    """A table of 4000 half-planes (the 100 of the example, each 40 times): shared memory beyond the 48 KB default, and the
+    same optimum as with the 100 distinct ones (duplicate rows do not move it)."""
+    n = 20_000
+    x, ud = cf.c3b_inputs(n, seed=77)
+    o = cf.C3B_OPTS
+    t100 = cf.halfplane_table()
+    t4000 = np.ascontiguousarray(np.tile(t100, (40, 1)))
+    kw = dict(relaxLb=o[0], relaxCost=o[1], dynParam=[o[2], o[3]])
+    u1, r1, rc1 = ab.Engine(ab.FILTER_ROBUST, ab.MODEL_INVERTED_PENDULUM_TABLE, halfplanes=t100, **kw).filter_batch(x, ud)
+    u2, r2, rc2 = ab.Engine(ab.FILTER_ROBUST, ab.MODEL_INVERTED_PENDULUM_TABLE, halfplanes=t4000, **kw).filter_batch(x, ud)
+    assert np.array_equal(rc1, rc2)
+    m = rc1 == 1
+    assert np.abs(u1[m] - u2[m]).max() < 1e-9 and np.abs(r1[m] - r2[m]).max() < 1e-6
