@@ -64,6 +64,23 @@ struct RealizableRows {
 #pragma unroll
 		for (int k = 0; k < 2 * NV; k++) fb(base + k, k >> 1, (k & 1) != 0, (k & 1) ? -ub[k >> 1] : lb[k >> 1]);
 	}
+	// the two rows of a facet slot differ only in the u coefficient (Lg- <= Lg+): one of them per scan, as in robust_kernel.cuh
+	template <class F, class FB>
+	__device__ __forceinline__ void scan_at(const double (&v)[NV], F &&fn, FB &&fb) const
+	{
+		const bool lower = v[0] >= 0.0;
+		for (int s = 0; s < nslots; s++) {
+			const double n[NV] = {lower ? lgLo[s] : lgHi[s], 0.0};
+			fn(2 * s + (lower ? 0 : 1), n, rhs[s]);
+		}
+		for (int i = 0; i < nbar; i++) {
+			const double n[NV] = {barL[i], 1.0};
+			fn(2 * nslots + i, n, barB[i]);
+		}
+		const int base = 2 * nslots + nbar;
+#pragma unroll
+		for (int k = 0; k < 2 * NV; k++) fb(base + k, k >> 1, (k & 1) != 0, (k & 1) ? -ub[k >> 1] : lb[k >> 1]);
+	}
 	__device__ __forceinline__ void get(const int j, double (&n)[NV], double &r) const
 	{
 		const int base = 2 * nslots + nbar;
@@ -85,6 +102,12 @@ struct RealizableRows {
 		}
 	}
 };
+
+template <class F, class FB>
+__device__ __forceinline__ void qp_scan_rows(const RealizableRows &rows, const double (&v)[2], F &&fn, FB &&fb)
+{
+	rows.scan_at(v, fn, fb);
+}
 
 // diag: [nCrit, critFacet[max_crit] (-1 absent), barrierFacet[npSSmax], per slot LgLo, LgHi, LfLo, LfHi, per barrier row Lgh, b]
 template <bool WITH_DIAG>

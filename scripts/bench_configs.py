@@ -56,6 +56,9 @@ def main():
     run("C3b ASIFrobust / InvertedPendulum + 100 half-planes, 1e6 states",
         ab.Engine(ab.FILTER_ROBUST, ab.MODEL_INVERTED_PENDULUM_TABLE, relaxLb=o[0], relaxCost=o[1], dynParam=[o[2], o[3]],
                   halfplanes=cf.halfplane_table()), x, ud, reps=10)
+    x, ud = cf.c4_inputs(1_000_000)
+    run("C4 ASIFrealizable / InvertedPendulum + 100Hz_50pt polytope kernel, 1e6 states",
+        ab.Engine(ab.FILTER_REALIZABLE, ab.MODEL_INVERTED_PENDULUM_KERNEL, **cf.realizable_engine_kwargs(cf.C4_OPTS)), x, ud, reps=10)
     x, ud = cf.c5_inputs(1_000_000)
     run("C5-filter ASIFimplicitTB / segway npBT=316, 1e6 states (one control step)",
         ab.Engine(ab.FILTER_IMPLICIT_TB, ab.MODEL_SEGWAY, **cf.tb_engine_kwargs(cf.SEGWAY_TB_OPTS)), x, ud, reps=3)
