@@ -6,7 +6,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 
-FILTER_EXPLICIT, FILTER_IMPLICIT_TB, FILTER_IMPLICIT, FILTER_ROBUST, FILTER_REALIZABLE = 1, 2, 3, 4, 5
+FILTER_EXPLICIT, FILTER_IMPLICIT_TB, FILTER_IMPLICIT, FILTER_ROBUST, FILTER_REALIZABLE, FILTER_IMPLICIT_RB = 1, 2, 3, 4, 5, 6
 MODEL_DOUBLE_INTEGRATOR, MODEL_DOUBLE_INTEGRATOR_TB, MODEL_INVERTED_PENDULUM, MODEL_INVERTED_PENDULUM_TABLE = 1, 2, 3, 4
 MODEL_INVERTED_PENDULUM_KERNEL = 5
 MODEL_SEGWAY, MODEL_SEGWAY_SHIPPED = 6, 7
@@ -37,6 +37,7 @@ class EngineConfig(C.Structure):
         ("kernel_vertices", _dp), ("n_vertices", C.c_int32),
         ("facet_normals", _dp), ("facet_vertices", _ip), ("facet_active", _ip), ("facet_lie", _dp),
         ("n_facets", C.c_int32), ("max_critical_facets", C.c_int32), ("max_active_constraints", C.c_int32),
+        ("backContDt", C.c_double), ("x_unc", C.c_double * 4),
     ]
 
 
@@ -137,7 +138,7 @@ class Engine:
         cfg.device = device
         self._keep = []
         for k, v in options.items():
-            if k in ("lb", "ub", "dynParam", "uncertaintyBounds"):
+            if k in ("lb", "ub", "dynParam", "uncertaintyBounds", "x_unc"):
                 for i, vi in enumerate(np.atleast_1d(v)):
                     getattr(cfg, k)[i] = float(vi)
             elif k == "kernel":

@@ -159,6 +159,14 @@ int launch_filter(asif_engine *e, int64_t n, const double *x, const double *ud, 
 		if (e->cfg.model == ASIF_MODEL_INVERTED_PENDULUM)
 			return launch_implicit_ip(e, n, x, ud, ua, relax, rc, diag, st);
 		break;
+	case ASIF_FILTER_IMPLICIT_RB:
+		if (e->cfg.model == ASIF_MODEL_INVERTED_PENDULUM) return launch_implicit_rb_ip(e, n, x, ud, ua, relax, rc, diag, st);
+		if (e->cfg.model == ASIF_MODEL_DOUBLE_INTEGRATOR_TB) { // fused-gradient constructor; bit-exact unit
+			using M = DoubleIntegratorTB;
+			if (e->cfg.npBTSS != 10) return launch_implicit_t<M, IMP_NPBTSS_RUNTIME, true, SAT_GENERAL>(e, n, x, ud, ua, relax, rc, diag, st);
+			return launch_implicit_t<M, 10, true, SAT_GENERAL>(e, n, x, ud, ua, relax, rc, diag, st);
+		}
+		break;
 	case ASIF_FILTER_ROBUST:
 		if (e->cfg.model == ASIF_MODEL_INVERTED_PENDULUM_TABLE) return launch_robust(e, n, x, ud, ua, relax, rc, diag, st);
 		break;
@@ -256,6 +264,15 @@ int32_t asif_engine_config_init(asif_engine_config *cfg, int32_t filter, int32_t
 		cfg->relaxReachLb = 5.0;
 		cfg->backTrajHorizon = 1.0;
 		cfg->backTrajDt = 0.01;
+		cfg->satSharpness = 0.1;
+		cfg->npBTSS = 10;
+		break;
+	case ASIF_FILTER_IMPLICIT_RB: /* include/asif_implicit_robust.h:22-38 */
+		cfg->relaxLb = 5.0;
+		cfg->relaxReachLb = 5.0;
+		cfg->backTrajHorizon = 1.0;
+		cfg->backTrajDt = 0.01;
+		cfg->backContDt = 0.01;
 		cfg->satSharpness = 0.1;
 		cfg->npBTSS = 10;
 		break;
@@ -417,8 +434,26 @@ int32_t asif_engine_create(const asif_engine_config *cfg, asif_engine **out)
 		}
 		break;
 	}
+	case ASIF_FILTER_IMPLICIT_RB:
+		if (cfg->model != ASIF_MODEL_INVERTED_PENDULUM && cfg->model != ASIF_MODEL_DOUBLE_INTEGRATOR_TB) {
+			delete e;
+			return fail(ASIF_ERR_UNSUPPORTED, "implicit-RB filter: model %d not compiled in", cfg->model);
+		}
+		// the hold is re-armed on the first Euler step of every trajectory only while backContDt - 0.0001 <= 1 + dt
+		// (src/asif_implicit_robust.cpp:895-903); beyond that the reference would carry the held input from one
+		// filter() call into the next, which a batch of independent states cannot reproduce
+		if (!(cfg->backContDt > 0) || !(cfg->backContDt < 1.0)) {
+			delete e;
+			return fail(ASIF_ERR_INVALID_ARGUMENT, "implicit-RB filter: backContDt must be in (0, 1)");
+		}
+		for (int i = 0; i < e->nx; i++)
+			if (!(cfg->x_unc[i] >= 0)) {
+				delete e;
+				return fail(ASIF_ERR_INVALID_ARGUMENT, "implicit-RB filter: x_unc[%d] must be >= 0", i);
+			}
+		/* fall through: the rest is ASIFimplicit's initialize (src/asif_implicit_robust.cpp:264-344 == src/asif_implicit.cpp:194-266) */
 	case ASIF_FILTER_IMPLICIT: {
-		if (cfg->model != ASIF_MODEL_INVERTED_PENDULUM) {
+		if (cfg->filter == ASIF_FILTER_IMPLICIT && cfg->model != ASIF_MODEL_INVERTED_PENDULUM) {
 			delete e;
 			return fail(ASIF_ERR_UNSUPPORTED, "implicit filter: model %d not compiled in", cfg->model);
 		}
@@ -460,6 +495,8 @@ int32_t asif_engine_create(const asif_engine_config *cfg, asif_engine **out)
 		}
 		p.npBT = (int32_t)npBT;
 		p.npBTSS = cfg->npBTSS;
+		p.backContDt = cfg->backContDt;
+		for (int i = 0; i < 4; i++) p.x_unc[i] = (i < e->nx) ? cfg->x_unc[i] : 0.0;
 		p.sat_mode = make_softsat(cfg->satSharpness, cfg->lb, cfg->ub, nu, p.sat);
 		for (int i = nu; i < nu + 2; i++) {
 			p.gi[i] = 1.0 / (2.0 * cfg->relaxCost);

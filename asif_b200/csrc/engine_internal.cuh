@@ -218,6 +218,30 @@ int launch_tb_rollout(asif_engine *e, int64_t n, int32_t steps, double dt, doubl
 	return tb_release(e, buf, st);
 }
 
+// ASIFimplicit / ASIFimplicitRB launch for one model.  SAT_LO is the saturation mode used when the input range is not a
+// power of two: SAT_GENERAL in the bit-exact unit (engine.cu), SAT_RECIP in the contracted one (kernels_contract.cu).
+template <class M, int NPBTSS, bool RB, int SAT_LO>
+int launch_implicit_t(asif_engine *e, int64_t n, const double *x, const double *ud, double *ua, double *relax, int32_t *rc,
+                      double *diag, cudaStream_t st)
+{
+	const size_t smem = sizeof(double) * imp_smem_doubles_per_thread<M, NPBTSS>() * IMP_THREADS;
+	const unsigned blocks = (unsigned)((n + IMP_THREADS - 1) / IMP_THREADS);
+	const bool pow2 = e->im.sat_mode >= SAT_POW2;
+	if (diag) {
+		auto k = pow2 ? implicit_filter_kernel<M, NPBTSS, true, SAT_POW2, RB> : implicit_filter_kernel<M, NPBTSS, true, SAT_LO, RB>;
+		int r = set_smem(k, smem);
+		if (r) return r;
+		k<<<blocks, IMP_THREADS, smem, st>>>(e->im, n, x, ud, ua, relax, rc, diag, e->d_counters);
+	} else {
+		auto k = pow2 ? implicit_filter_kernel<M, NPBTSS, false, SAT_POW2, RB> : implicit_filter_kernel<M, NPBTSS, false, SAT_LO, RB>;
+		int r = set_smem(k, smem);
+		if (r) return r;
+		k<<<blocks, IMP_THREADS, smem, st>>>(e->im, n, x, ud, ua, relax, rc, nullptr, e->d_counters);
+	}
+	CUDA_TRY(cudaGetLastError());
+	return ASIF_OK;
+}
+
 
 // defined in engine.cu: dispatch of one filter launch on device pointers
 namespace asifb {
@@ -233,4 +257,6 @@ int launch_tb_rollout_segway(asif_engine *e, bool shipped, int64_t n, int32_t st
                              double *ua, int32_t *rc, cudaStream_t st);
 int launch_implicit_ip(asif_engine *e, int64_t n, const double *x, const double *ud, double *ua, double *relax, int32_t *rc,
                        double *diag, cudaStream_t st);
+int launch_implicit_rb_ip(asif_engine *e, int64_t n, const double *x, const double *ud, double *ua, double *relax, int32_t *rc,
+                          double *diag, cudaStream_t st);
 } // namespace asifb

@@ -128,14 +128,15 @@ __host__ __device__ constexpr int dfcl_pattern(int i, int j)
 // Closed-loop backup dynamics and their Jacobian, src/asif_implicit_tb.cpp:833-897.
 // Entries of DfCL whose dfcl_pattern is PZ / P1 are not written (callers must not read them).
 // f_pat(i) == PZ marks a drift component that is the literal 0.0 (then g uSat + 0.0 == g uSat).
+// The part after the backup controller: u is the input handed to the saturation, Du the controller Jacobian that
+// enters DfCL (for ASIFimplicitRB these can be the zero-order-held values, see backup_cl_dynamics_zoh).
 template <class M, int SATMODE>
-__device__ __forceinline__ void backup_cl_dynamics(const SoftSat &sat, const double *lb, const double *ub, const double *x,
-                                                   double *fCL, double *DfCL)
+__device__ __forceinline__ void backup_cl_from_input(const SoftSat &sat, const double *lb, const double *ub, const double *x,
+                                                     const double *u, const double *Du, double *fCL, double *DfCL)
 {
 	constexpr int NX = M::NX, NU = M::NU;
-	double f[NX], g[NX * NU], u[NU], Du[NU * NX], uSat[NU], DuSat[NU];
+	double f[NX], g[NX * NU], uSat[NU], DuSat[NU];
 	double d[NX * NX], Dg[M::FUSED_GRADIENT ? 1 : NX * NU * NX];
-	M::backup_controller(x, u, Du);
 #pragma unroll
 	for (int k = 0; k < NU; k++) input_saturate_soft<SATMODE>(sat, k, lb[k], ub[k], u[k], uSat[k], DuSat[k]);
 	if (M::FUSED_GRADIENT) {
@@ -196,6 +197,46 @@ __device__ __forceinline__ void backup_cl_dynamics(const SoftSat &sat, const dou
 		}
 		fCL[i] = have ? ((M::f_pat(i) == PZ) ? acc : acc + f[i]) : f[i];
 	}
+}
+
+template <class M, int SATMODE>
+__device__ __forceinline__ void backup_cl_dynamics(const SoftSat &sat, const double *lb, const double *ub, const double *x,
+                                                   double *fCL, double *DfCL)
+{
+	double u[M::NU], Du[M::NU * M::NX];
+	M::backup_controller(x, u, Du);
+	backup_cl_from_input<M, SATMODE>(sat, lb, ub, x, u, Du, fCL, DfCL);
+}
+
+// Zero-order-hold backup controller of ASIFimplicitRB (src/asif_implicit_robust.cpp:878-903): the controller is
+// evaluated at every rhs call, but the input that is saturated and applied is refreshed only when
+// t >= t_last + backContDt - 0.0001; t_last is reset to -1 while t <= backTrajDt, i.e. on the first Euler step of
+// every trajectory, so the hold carries no state from one filter() call to the next as long as backContDt < 1
+// (enforced at engine creation).  Quirk kept: the fused-gradient branch builds DfCL from the HELD Du (:921), the
+// split branch from the CURRENT one (:939).
+template <class M>
+struct ZohState {
+	double u[M::NU], Du[M::NU * M::NX];
+	double t_last;
+};
+
+template <class M, int SATMODE>
+__device__ __forceinline__ void backup_cl_dynamics_zoh(const SoftSat &sat, const double *lb, const double *ub, const double *x,
+                                                       const double t, const double backTrajDt, const double backContDt,
+                                                       ZohState<M> &z, double *fCL, double *DfCL)
+{
+	constexpr int NX = M::NX, NU = M::NU;
+	double u[NU], Du[NU * NX];
+	M::backup_controller(x, u, Du);
+	if (t <= backTrajDt) z.t_last = -1.;
+	if (t >= (z.t_last + backContDt - 0.0001)) {
+#pragma unroll
+		for (int i = 0; i < NU; i++) z.u[i] = u[i];
+#pragma unroll
+		for (int i = 0; i < NU * NX; i++) z.Du[i] = Du[i];
+		z.t_last = t;
+	}
+	backup_cl_from_input<M, SATMODE>(sat, lb, ub, x, z.u, M::FUSED_GRADIENT ? z.Du : Du, fCL, DfCL);
 }
 
 // Q-dot = DfCL Q (src/asif_implicit_tb.cpp:906-908) with the structural pattern of DfCL

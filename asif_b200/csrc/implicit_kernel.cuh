@@ -5,6 +5,12 @@
 // WHOLE horizon (no hit test, :487), snapshots in shared memory, rows recomputed on demand, plus
 // NPBS backup-set rows taken at the end of the trajectory (:542-554) with their own relax variable.
 // QP in v = (u, delta_safe, delta_reach).
+//
+// RB = true selects ASIFimplicitRB (src/asif_implicit_robust.cpp:363-441 filter, :481-778 updateConstraints,
+// :878-965 closed-loop rhs): the same filter with (a) the backup input under a zero-order hold of backContDt
+// (backup_cl_dynamics_zoh) and (b) the h entries of the safety rows replaced by the lower bound of the interval
+// safety set over x_i +- x_unc (:636-647; the Dh rows stay nominal, and the interval Lfh / Lgh the reference also
+// computes are never used, :689-738).  Selection of the critical points still uses the nominal min h (:572).
 #pragma once
 #include "filter_common.cuh"
 #include "qp_gi.cuh"
@@ -24,6 +30,9 @@ struct ImplicitParams {
 	int32_t pad_;
 	SoftSat sat;
 	double gi[MAX_NV], gih[MAX_NV];
+	// ASIFimplicitRB only (include/asif_implicit_robust.h:22-38)
+	double backContDt;
+	double x_unc[4];
 };
 
 constexpr int IMP_NPBTSS_RUNTIME = -16; // generic instantiation: any npBTSS in 1..16 (see np_capacity in tb_kernel.cuh)
@@ -34,7 +43,7 @@ __host__ __device__ constexpr int imp_smem_doubles_per_thread()
 	return np_capacity(NPBTSS) * (M::NX + M::NX * M::NX);
 }
 
-template <class M, int NPBTSS>
+template <class M, int NPBTSS, bool RB = false>
 struct ImpRows {
 	static constexpr int NX = M::NX, NU = M::NU, NPSS = M::NPSS, NPBS = M::NPBS, NS = NX + NX * NX;
 	static constexpr int CAP = np_capacity(NPBTSS), NV = NU + 2;
@@ -48,6 +57,7 @@ struct ImpRows {
 	int kslot[CAP];
 	double lgB[NPBS][NU], hB[NPBS], rhsB[NPBS]; // backup rows
 	double lb[NV], ub[NV];
+	double x_unc[RB ? NX : 1];
 
 	__device__ __forceinline__ void point_rows(const int slot, double (&n)[NPSS][NV], double (&rhs)[NPSS]) const
 	{
@@ -55,6 +65,7 @@ struct ImpRows {
 #pragma unroll
 		for (int e = 0; e < NS; e++) xs[e] = snap[(slot * NS + e) * T];
 		safety_point_rows<M>(xs, f, g, hs, lf, lg);
+		if (RB) M::safety_set_lower(xs, x_unc, hs);
 #pragma unroll
 		for (int j = 0; j < NPSS; j++) {
 #pragma unroll
@@ -138,7 +149,7 @@ struct ImpRows {
 	}
 };
 
-template <class M, int NPBTSS, bool WITH_DIAG, int SATMODE>
+template <class M, int NPBTSS, bool WITH_DIAG, int SATMODE, bool RB = false>
 __global__ void __launch_bounds__(IMP_THREADS, 3)
 implicit_filter_kernel(const ImplicitParams p, const int64_t n, const double *__restrict__ x_in,
                        const double *__restrict__ u_des, double *__restrict__ u_act, double *__restrict__ relax_out,
@@ -169,7 +180,11 @@ implicit_filter_kernel(const ImplicitParams p, const int64_t n, const double *__
 #pragma unroll
 	for (int j = 1; j < NPSS; j++) hSafetyNow = (hs[j] < hSafetyNow) ? hs[j] : hSafetyNow;
 
-	ImpRows<M, NPBTSS> R;
+	ImpRows<M, NPBTSS, RB> R;
+	if (RB) {
+#pragma unroll
+		for (int i = 0; i < NX; i++) R.x_unc[i] = p.x_unc[i];
+	}
 	R.np = np;
 	R.snap = snap;
 	R.T = T;
@@ -194,9 +209,21 @@ implicit_filter_kernel(const ImplicitParams p, const int64_t n, const double *__
 	for (int e = 0; e < NS; e++) snap[(R.kslot[0] * NS + e) * T] = X[e];
 
 	const int N = p.npBT;
+	ZohState<M> zoh;
+	if (RB) {
+#pragma unroll
+		for (int i = 0; i < NU; i++) zoh.u[i] = 0.0;
+#pragma unroll
+		for (int i = 0; i < NU * NX; i++) zoh.Du[i] = 0.0;
+		zoh.t_last = -1.;
+	}
 	for (int i = 1; i < N; i++) {
 		double Xd[NS], DfCL[NX * NX];
-		backup_cl_dynamics<M, SATMODE>(p.sat, p.lb, p.ub, X, Xd, DfCL);
+		if (RB) // the reference hands t = i*backTrajDt to the rhs (src/asif_implicit_robust.cpp:550)
+			backup_cl_dynamics_zoh<M, SATMODE>(p.sat, p.lb, p.ub, X, (double)(unsigned)i * p.backTrajDt, p.backTrajDt,
+			                                   p.backContDt, zoh, Xd, DfCL);
+		else
+			backup_cl_dynamics<M, SATMODE>(p.sat, p.lb, p.ub, X, Xd, DfCL);
 		sensitivity_rhs<M>(DfCL, X + NX, Xd + NX);
 #pragma unroll
 		for (int e = 0; e < NS; e++) X[e] = Xd[e] * p.backTrajDt + X[e];

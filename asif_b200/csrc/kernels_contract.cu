@@ -35,34 +35,21 @@ int launch_tb_rollout_segway(asif_engine *e, bool shipped, int64_t n, int32_t st
 	               : launch_tb_rollout<SegwayTB<true>, 4>(e, n, steps, dt, x, ud, ua, rc, st);
 }
 
-template <int NPBTSS>
-static int launch_implicit_ip_np(asif_engine *e, int64_t n, const double *x, const double *ud, double *ua, double *relax,
-                                 int32_t *rc, double *diag, cudaStream_t st)
-{
-	using M = InvertedPendulumImplicit;
-	const size_t smem = sizeof(double) * imp_smem_doubles_per_thread<M, NPBTSS>() * IMP_THREADS;
-	const unsigned blocks = (unsigned)((n + IMP_THREADS - 1) / IMP_THREADS);
-	const bool pow2 = e->im.sat_mode >= SAT_POW2;
-	if (diag) {
-		auto k = pow2 ? implicit_filter_kernel<M, NPBTSS, true, SAT_POW2> : implicit_filter_kernel<M, NPBTSS, true, SAT_RECIP>;
-		int r = set_smem(k, smem);
-		if (r) return r;
-		k<<<blocks, IMP_THREADS, smem, st>>>(e->im, n, x, ud, ua, relax, rc, diag, e->d_counters);
-	} else {
-		auto k = pow2 ? implicit_filter_kernel<M, NPBTSS, false, SAT_POW2> : implicit_filter_kernel<M, NPBTSS, false, SAT_RECIP>;
-		int r = set_smem(k, smem);
-		if (r) return r;
-		k<<<blocks, IMP_THREADS, smem, st>>>(e->im, n, x, ud, ua, relax, rc, nullptr, e->d_counters);
-	}
-	CUDA_TRY(cudaGetLastError());
-	return ASIF_OK;
-}
-
 int launch_implicit_ip(asif_engine *e, int64_t n, const double *x, const double *ud, double *ua, double *relax, int32_t *rc,
                        double *diag, cudaStream_t st)
 {
-	if (e->cfg.npBTSS != 10) return launch_implicit_ip_np<IMP_NPBTSS_RUNTIME>(e, n, x, ud, ua, relax, rc, diag, st);
-	return launch_implicit_ip_np<10>(e, n, x, ud, ua, relax, rc, diag, st);
+	using M = InvertedPendulumImplicit;
+	if (e->cfg.npBTSS != 10) return launch_implicit_t<M, IMP_NPBTSS_RUNTIME, false, SAT_RECIP>(e, n, x, ud, ua, relax, rc, diag, st);
+	return launch_implicit_t<M, 10, false, SAT_RECIP>(e, n, x, ud, ua, relax, rc, diag, st);
+}
+
+// ASIFimplicitRB on the same callbacks (zero-order-hold backup input, interval lower bound of the safety rows)
+int launch_implicit_rb_ip(asif_engine *e, int64_t n, const double *x, const double *ud, double *ua, double *relax, int32_t *rc,
+                          double *diag, cudaStream_t st)
+{
+	using M = InvertedPendulumImplicit;
+	if (e->cfg.npBTSS != 10) return launch_implicit_t<M, IMP_NPBTSS_RUNTIME, true, SAT_RECIP>(e, n, x, ud, ua, relax, rc, diag, st);
+	return launch_implicit_t<M, 10, true, SAT_RECIP>(e, n, x, ud, ua, relax, rc, diag, st);
 }
 
 } // namespace asifb

@@ -12,6 +12,22 @@
 
 namespace asifb {
 
+// Lower bound of an affine box safety set {-x_i + hi, x_i - lo} over the box [x - unc, x + unc] exactly as libaffa
+// produces it for ASIFimplicitRB (src/asif_implicit_robust.cpp:636-647: safetySet_int, then h_int.convert().left()):
+//   AAF(interval(l, r)): centre (r + l)/2, one noise coefficient (r - l)/2   (lib/libaffa/src/aa_aafcommon.cpp:80-101)
+//   negation / adding a constant: centre negated / shifted, coefficient negated / kept (aa_aafarithm.cpp:35-98,103-184)
+//   convert().left() = centre - rad(), rad() = 0 + |coefficient|                (aa_aafcommon.cpp:217-245)
+__device__ __forceinline__ void box_safety_lower(const double *x, const double *unc, const double lo, const double hi, double *hl)
+{
+	const double l0 = x[0] - unc[0], r0 = x[0] + unc[0], l1 = x[1] - unc[1], r1 = x[1] + unc[1];
+	const double c0 = (r0 + l0) / 2, c1 = (r1 + l1) / 2;
+	const double d0 = fabs((r0 - l0) / 2), d1 = fabs((r1 - l1) / 2);
+	hl[0] = (-c0 + hi) - d0;
+	hl[1] = (c0 - lo) - d0;
+	hl[2] = (c1 - lo) - d1;
+	hl[3] = (-c1 + hi) - d1;
+}
+
 // ------------------------------------------------------------------ DoubleIntegrator (explicit)
 // examples/DoubleIntegrator.cpp:12-61
 struct DoubleIntegratorExplicit {
@@ -40,7 +56,7 @@ struct DoubleIntegratorExplicit {
 // ------------------------------------------------------------------ DoubleIntegrator (implicit TB)
 // examples/DoubleIntegrator_implicit_tb.cpp:13-85 ; backup-set Hessian completed
 struct DoubleIntegratorTB {
-	static constexpr int NX = 2, NU = 1, NPSS = 4;
+	static constexpr int NX = 2, NU = 1, NPSS = 4, NPBS = 1;
 	static constexpr bool FUSED_GRADIENT = true; // DYNAMICS_WITH_GRADIENT, :9
 	// structural patterns (filter_common.cuh): B = {0,1}; d_fcl_dx = A = {0,0,1,0} column-major
 	__host__ __device__ static constexpr int g_pat(int i)
@@ -95,6 +111,14 @@ struct DoubleIntegratorTB {
 		Dh[1] = -2.0 * x[1];
 		DDh[0] = -2.0; DDh[1] = 0.0; DDh[2] = 0.0; DDh[3] = -2.0;
 	}
+	// the 3-argument backup set of the non-TB implicit classes (h, Dh only)
+	__device__ static void backup_set_rows(const double *x, double *h, double *Dh)
+	{
+		h[0] = backup_set_value(x);
+		Dh[0] = -2.0 * x[0];
+		Dh[1] = -2.0 * x[1];
+	}
+	__device__ static void safety_set_lower(const double *x, const double *unc, double *hl) { box_safety_lower(x, unc, -1.0, 1.0, hl); }
 	__device__ static void backup_controller(const double *x, double *u, double *Du)
 	{
 		u[0] = (-10.0) * x[0] + (-20.0) * x[1];
@@ -369,6 +393,7 @@ struct InvertedPendulumImplicit {
 		h[2] = x[1] - (-M_PI); Dh[2] = 0.0;  Dh[6] = 1.0;
 		h[3] = -x[1] + M_PI;   Dh[3] = 0.0;  Dh[7] = -1.0;
 	}
+	__device__ static void safety_set_lower(const double *x, const double *unc, double *hl) { box_safety_lower(x, unc, -M_PI, M_PI, hl); }
 	// h = Pv - x'Px, P = {1.25,.25,.25,.25}, Pv = 0.05 (:39-52): the four products in loop order
 	__device__ static void backup_set_rows(const double *x, double *h, double *Dh)
 	{

@@ -467,6 +467,94 @@ namespace ASIF
 			double lb_, ub_;
 		};
 
+		// Batched ASIF::ASIFimplicitRB (include/asif_implicit_robust.h:19-160, src/asif_implicit_robust.cpp): ASIFimplicit with
+		// a zero-order-hold backup controller (Options.backContDt) and the h entries of the safety rows replaced by the
+		// lower bound of the interval safety set over x_i +- x_unc.  The interval callbacks of the reference constructor
+		// (safetySet_int ...) are compiled into the device model functor (safety_set_lower, asif_b200/csrc/models.cuh).
+		class FilterBatchImplicitRB : public FilterBatchBase
+		{
+		public:
+			typedef struct {
+				double *x0 = nullptr;    // unused on the batched path (the reference uses it for the set-up solve only)
+				double *x_unc = nullptr; // [nx] state uncertainty box; nullptr = zeros, as in the reference (:276-279)
+				int n_debug = -1;        // diagnostics of the single-state class; not on the batched path
+				double relaxCost = 50.0;
+				double relaxReachLb = 5.0;
+				double relaxSafeLb = 5.0;
+				double backTrajHorizon = 1.0;
+				double backContDt = 0.01;
+				double backTrajDt = 0.01;
+				double backTrajAbsTol = 1.0e-6;
+				double backTrajRelTol = 1.0e-6;
+				double satSharpness = 0.1;
+				double inf = 1e20;
+				bool use_learning = false; // the learned residual is not built: true is refused
+			} Options; // include/asif_implicit_robust.h:22-38
+
+			FilterBatchImplicitRB(const Model model, const uint32_t npBTSS = 10, const int32_t device = 0)
+			    : model_(model), npBTSS_(npBTSS), device_(device)
+			{
+			}
+			int32_t initialize(const double lb[], const double ub[]) { return initialize(lb, ub, Options()); }
+			int32_t initialize(const double lb[], const double ub[], const Options &options)
+			{
+				options_ = options;
+				lb_ = lb[0];
+				ub_ = ub[0];
+				return build();
+			}
+			// src/asif_implicit_robust.cpp:443-479: satSharpness clamp with return codes 2 / 3
+			int32_t updateOptions(const Options &options)
+			{
+				options_ = options;
+				int32_t code = 1;
+				if (options_.satSharpness > 2) {
+					options_.satSharpness = 2;
+					code = 2;
+				} else if (options_.satSharpness < 0.01) {
+					options_.satSharpness = 0.01;
+					code = 3;
+				}
+				const int32_t r = build();
+				return r == 1 ? code : r;
+			}
+			int32_t filter(const double x[], const double uDes[], double uAct[], double relax[2])
+			{
+				int32_t rc = 0;
+				const int32_t r = filterBatch(1, x, uDes, uAct, relax, &rc);
+				return r == ASIF_OK ? rc : r;
+			}
+
+		protected:
+			int32_t build(void)
+			{
+				if (options_.use_learning) return ASIF_ERR_UNSUPPORTED;
+				asif_engine_config cfg;
+				int32_t r = asif_engine_config_init(&cfg, ASIF_FILTER_IMPLICIT_RB, (int32_t)model_);
+				if (r != ASIF_OK) return r;
+				cfg.device = device_;
+				cfg.npBTSS = (int32_t)npBTSS_;
+				cfg.lb[0] = lb_;
+				cfg.ub[0] = ub_;
+				cfg.relaxCost = options_.relaxCost;
+				cfg.relaxLb = options_.relaxSafeLb;
+				cfg.relaxReachLb = options_.relaxReachLb;
+				cfg.backTrajHorizon = options_.backTrajHorizon;
+				cfg.backTrajDt = options_.backTrajDt;
+				cfg.backContDt = options_.backContDt;
+				cfg.satSharpness = options_.satSharpness;
+				cfg.inf = options_.inf;
+				const int nx = (model_ == Model::Segway || model_ == Model::SegwayShipped) ? 4 : 2;
+				for (int i = 0; i < nx; i++) cfg.x_unc[i] = options_.x_unc ? options_.x_unc[i] : 0.0;
+				return create(cfg);
+			}
+			Model model_;
+			uint32_t npBTSS_;
+			int32_t device_;
+			Options options_;
+			double lb_, ub_;
+		};
+
 		// Batched ASIF::ASIFrobust (include/asif_robust.h) on a table of half-planes h_k = 1 - a_k.x with the
 		// InvertedPendulum interval dynamics g1 in [pMin, pMax] (examples/InvertedPendulum_Robust.cpp:53-69).
 		class FilterBatchRobust : public FilterBatchBase

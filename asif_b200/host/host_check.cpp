@@ -98,6 +98,24 @@ int main()
 		double x[2] = {0.2, -0.1}, uDes[1] = {0.4}, uAct[1] = {0.0}, relax[2] = {0.0, 0.0};
 		const int32_t rc = asif.filter(x, uDes, uAct, relax);
 		if (rc != 1 || relax[0] < 10.0 - 1e-9 || relax[1] < 5.0 - 1e-9) return fail("FilterBatchImplicit::filter");
+		{ // ASIFimplicitRB: with x_unc = 0 and a hold of one Euler step it must return what ASIFimplicit returned
+			b200::FilterBatchImplicitRB rb(b200::Model::InvertedPendulum, 10);
+			b200::FilterBatchImplicitRB::Options ro;
+			ro.backTrajHorizon = 5.0;
+			ro.backTrajDt = 0.05;
+			ro.backContDt = 0.05;
+			ro.relaxReachLb = 5.0;
+			ro.relaxSafeLb = 10.0;
+			if (rb.initialize(lb, ub, ro) != 1) return fail("FilterBatchImplicitRB::initialize");
+			double uRb[1] = {0.0}, relaxRb[2] = {0.0, 0.0};
+			if (rb.filter(x, uDes, uRb, relaxRb) != rc || uRb[0] != uAct[0] || relaxRb[0] != relax[0]) return fail("FilterBatchImplicitRB::filter");
+			double unc[2] = {0.05, 0.08};
+			ro.x_unc = unc;
+			ro.backContDt = 0.2;
+			ro.satSharpness = 5.0;
+			if (rb.updateOptions(ro) != 2) return fail("FilterBatchImplicitRB::updateOptions clamp code");
+			if (rb.filter(x, uDes, uRb, relaxRb) != 1) return fail("FilterBatchImplicitRB::filter with x_unc");
+		}
 		const double planes[4] = {0.5, 0.0, -0.5, 0.0}; // |x0| <= 2
 		b200::FilterBatchRobust rob(2, planes, 0.8, 1.2);
 		if (rob.initialize(lb, ub) != 1) return fail("FilterBatchRobust::initialize");

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define ASIF_B200_ABI_VERSION 1
+#define ASIF_B200_ABI_VERSION 2
 
 /* error codes (function return values) */
 #define ASIF_OK 0
@@ -39,6 +39,7 @@ extern "C" {
 #define ASIF_FILTER_IMPLICIT 3    /* ASIF::ASIFimplicit    include/asif_implicit.h:96-113 */
 #define ASIF_FILTER_ROBUST 4      /* ASIF::ASIFrobust      include/asif_robust.h:41-59    */
 #define ASIF_FILTER_REALIZABLE 5  /* ASIF::ASIFrealizable  include/asif_realizable.h:58-76 */
+#define ASIF_FILTER_IMPLICIT_RB 6 /* ASIF::ASIFimplicitRB  include/asif_implicit_robust.h:124-146 */
 
 /* models: the reference passes std::function callbacks; on the device a model is a compiled-in
  * functor with the same five callback signatures (asif_b200/csrc/models.cuh). */
@@ -97,6 +98,12 @@ typedef struct asif_engine_config {
 	 * (INTEGRATION.md shows the loop) and hands the numbers over. */
 	const double *facet_lie;
 	int32_t n_facets, max_critical_facets, max_active_constraints;
+	/* ASIFimplicitRB (include/asif_implicit_robust.h:22-38): zero-order-hold period of the backup controller and the
+	 * state-uncertainty box x_unc[nx] (Options.x_unc; the reference borrows the pointer, here the values are copied).
+	 * The interval safety set the class evaluates on x +- x_unc is compiled into the model functor
+	 * (safety_set_lower in asif_b200/csrc/models.cuh). */
+	double backContDt;
+	double x_unc[4];
 } asif_engine_config;
 
 int32_t asif_b200_abi_version(void);

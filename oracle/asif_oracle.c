@@ -139,6 +139,53 @@ static void ode_rhs(const oracle_model *md, double sat_sharpness, const double *
 	mat_mul(DfCL, md->nx, md->nx, X + md->nx, md->nx, Xdot + md->nx);
 }
 
+/* ASIFimplicitRB: zero-order-hold backup controller, src/asif_implicit_robust.cpp:878-952.  The hold is refreshed
+ * when t >= t_last + backContDt - 0.0001 (and t_last is reset to -1 while t <= backTrajDt, i.e. on the first
+ * step of every trajectory); the saturation acts on the HELD input.  Quirk kept: the fused-gradient branch uses
+ * the held Du (:921), the split branch the CURRENT Du (:939). */
+typedef struct {
+	double backContDt, backTrajDt, t_last;
+	double u[NU], Du[NU * NX];
+} zoh_state;
+
+static void backup_cl_dynamics_zoh(const oracle_model *md, double sat_sharpness, const double *x, double t, zoh_state *z,
+                                   double *fCL, double *DfCL)
+{
+	const int nx = md->nx, nu = md->nu;
+	double f[NX], g[NX * NU], u[NU], Du[NU * NX], uSat[NU], DuSat[NU];
+	md->backup_controller(x, u, Du);
+	if (t <= z->backTrajDt) z->t_last = -1.;
+	if (t >= (z->t_last + z->backContDt - 0.0001)) {
+		for (int i = 0; i < nu; i++) z->u[i] = u[i];
+		for (int i = 0; i < nu * nx; i++) z->Du[i] = Du[i];
+		z->t_last = t;
+	}
+	input_saturate_soft(md, sat_sharpness, z->u, uSat, DuSat);
+	if (md->dynamics_with_gradient) {
+		double d[NX * NX];
+		md->dynamics_with_gradient(x, uSat, f, g, d);
+		for (int i = 0; i < nx; i++)
+			for (int j = 0; j < nx; j++) {
+				int idx = i + j * nx;
+				DfCL[idx] = d[idx];
+				for (int k = 0; k < nu; k++) DfCL[idx] += g[i + k * nx] * DuSat[k] * z->Du[k + j * nu];
+			}
+	} else {
+		double Df[NX * NX], Dg[NX * NU * NX];
+		md->dynamics(x, f, g);
+		md->dynamics_gradients(x, Df, Dg);
+		for (int i = 0; i < nx; i++)
+			for (int j = 0; j < nx; j++) {
+				int idx = i + j * nx;
+				DfCL[idx] = Df[idx];
+				for (int k = 0; k < nu; k++)
+					DfCL[idx] += Dg[i + k * nx + j * nx * nu] * uSat[k] + g[i + k * nx] * DuSat[k] * Du[k + j * nu];
+			}
+	}
+	mat_vec(g, nx, nu, uSat, fCL);
+	for (int i = 0; i < nx; i++) fCL[i] += f[i];
+}
+
 /* open-loop f,g at the current state as the filter sees them: for the fused-gradient
  * constructor the library wraps dynamicsWithGradient(x, u = 0) (src/asif_implicit_tb.cpp:79-86) */
 static void open_loop_dynamics(const oracle_model *md, const double *x, double *f, double *g)
@@ -152,8 +199,19 @@ static void open_loop_dynamics(const oracle_model *md, const double *x, double *
 
 /* Euler trajectory with sensitivities, src/asif_implicit_tb.cpp:421-429,464-487.
  * traj: N x (nx+nx*nx), hFull: N x npSS, DhFull: N x npSS*nx, hFullMin: N, t: N */
+static void integrate_backup_trajectory_z(const oracle_model *md, double sat_sharpness, double dt, int N, const double *x,
+                                          double *traj, double *t, double *hFull, double *DhFull, double *hFullMin,
+                                          zoh_state *z);
 static void integrate_backup_trajectory(const oracle_model *md, double sat_sharpness, double dt, int N, const double *x,
                                         double *traj, double *t, double *hFull, double *DhFull, double *hFullMin)
+{
+	integrate_backup_trajectory_z(md, sat_sharpness, dt, N, x, traj, t, hFull, DhFull, hFullMin, 0);
+}
+
+/* z != NULL: ASIFimplicitRB's loop (src/asif_implicit_robust.cpp:547-570), whose rhs receives t = i*backTrajDt (:550) */
+static void integrate_backup_trajectory_z(const oracle_model *md, double sat_sharpness, double dt, int N, const double *x,
+                                          double *traj, double *t, double *hFull, double *DhFull, double *hFullMin,
+                                          zoh_state *z)
 {
 	const int nx = md->nx, ns = nx + nx * nx, npSS = md->npSS;
 	double *X0 = traj;
@@ -166,7 +224,12 @@ static void integrate_backup_trajectory(const oracle_model *md, double sat_sharp
 	for (int i = 1; i < N; i++) {
 		double *Xp = traj + (size_t)(i - 1) * ns, *Xi = traj + (size_t)i * ns;
 		t[i] = t[i - 1] + dt;
-		ode_rhs(md, sat_sharpness, Xp, Xi);
+		if (z) {
+			double DfCL[NX * NX];
+			backup_cl_dynamics_zoh(md, sat_sharpness, Xp, (double)(uint32_t)i * dt, z, Xi, DfCL);
+			mat_mul(DfCL, md->nx, md->nx, Xp + md->nx, md->nx, Xi + md->nx);
+		} else
+			ode_rhs(md, sat_sharpness, Xp, Xi);
 		for (int k = 0; k < ns; k++) Xi[k] = Xi[k] * dt;
 		for (int k = 0; k < ns; k++) Xi[k] = Xi[k] + Xp[k];
 		md->safety_set(Xi, hFull + (size_t)i * npSS, DhFull + (size_t)i * npSS * nx);
@@ -504,6 +567,9 @@ static int32_t explicit_filter(const oracle_model *md, double relaxLb, double re
 typedef struct {
 	double relaxCost, relaxReachLb, relaxSafeLb, backTrajHorizon, backTrajDt, satSharpness, inf;
 	int npBTSS;
+	/* ASIFimplicitRB (include/asif_implicit_robust.h:22-38): rb != 0 selects that class */
+	int rb;
+	double backContDt, x_unc[NX];
 } imp_options;
 
 static int32_t implicit_filter(const oracle_model *md, const imp_options *o, int N, const double *x, const double *uDes,
@@ -518,7 +584,12 @@ static int32_t implicit_filter(const oracle_model *md, const imp_options *o, int
 	double *hFull = (double *)malloc(sizeof(double) * (size_t)N * npSS);
 	double *DhFull = (double *)malloc(sizeof(double) * (size_t)N * npSS * nx);
 	double *hFullMin = (double *)malloc(sizeof(double) * N);
-	integrate_backup_trajectory(md, o->satSharpness, o->backTrajDt, N, x, traj, t, hFull, DhFull, hFullMin);
+	zoh_state z;
+	memset(&z, 0, sizeof(z));
+	z.backContDt = o->backContDt;
+	z.backTrajDt = o->backTrajDt;
+	z.t_last = -1.;
+	integrate_backup_trajectory_z(md, o->satSharpness, o->backTrajDt, N, x, traj, t, hFull, DhFull, hFullMin, o->rb ? &z : 0);
 	int crit[64];
 	k_smallest(hFullMin, N, npBTSS, crit); /* std::sort over all N points, :487 */
 
@@ -528,6 +599,8 @@ static int32_t implicit_filter(const oracle_model *md, const imp_options *o, int
 	for (int idx = 0; idx < npBTSS; idx++) { /* :518-540 */
 		int c = crit[idx];
 		memcpy(h + idx * npSS, hFull + (size_t)c * npSS, sizeof(double) * npSS);
+		/* RB: h <- lower bound of safetySet_int over x_c +- x_unc (src/asif_implicit_robust.cpp:636-647); Dh stays nominal */
+		if (o->rb) md->safety_set_lower(traj + (size_t)c * ns, o->x_unc, h + idx * npSS);
 		mat_mul(DhFull + (size_t)c * npSS * nx, npSS, nx, traj + (size_t)c * ns + nx, nx, DhSSDx);
 		for (int i = 0; i < npSS; i++)
 			for (int j = 0; j < nx; j++) Dh[(idx * npSS + i) + j * npTC] = DhSSDx[i + j * npSS];
@@ -712,6 +785,8 @@ static int make_ctx(int cfg, const double *opts, int n_opts, ctx_t *c)
 		c->n_diag = 4 + c->tb.npBTSS + c->nc * c->nv + c->nc;
 		break;
 	}
+	case ORACLE_CFG_IP_IMPLICIT_RB:
+	case ORACLE_CFG_DI_IMPLICIT_RB:
 	case ORACLE_CFG_IP_IMPLICIT: {
 		c->md = oracle_get_model(cfg, 0);
 		imp_options *o = &c->imp;
@@ -723,6 +798,13 @@ static int make_ctx(int cfg, const double *opts, int n_opts, ctx_t *c)
 			o->backTrajHorizon = opts[3]; o->backTrajDt = opts[4]; o->satSharpness = opts[5];
 		}
 		if (opts && n_opts >= 7 && opts[6] >= 1.0 && opts[6] <= 16.0) o->npBTSS = (int)opts[6]; /* constructor argument */
+		if (cfg != ORACLE_CFG_IP_IMPLICIT) { /* include/asif_implicit_robust.h:22-38 */
+			o->rb = 1;
+			if (!(opts && n_opts >= 6)) { o->relaxSafeLb = 5.0; o->backTrajHorizon = 1.0; o->backTrajDt = 0.01; }
+			o->backContDt = 0.01;
+			if (opts && n_opts >= 8) o->backContDt = opts[7];
+			for (int i = 0; i < c->md->nx; i++) o->x_unc[i] = (opts && n_opts >= 8 + c->md->nx) ? opts[8 + i] : 0.0;
+		}
 		/* src/asif_implicit.cpp:211-216 (no backTrajExtend in this class) */
 		c->N = (int)round(o->backTrajHorizon / o->backTrajDt) + 1;
 		if (c->N < o->npBTSS) {
@@ -780,6 +862,8 @@ static int32_t filter_one(const ctx_t *c, const double *x, const double *ud, dou
 	case ORACLE_CFG_SEGWAY_TB:
 		return tb_filter(c->md, &c->tb, c->N, x, ud, ua, relax, diag);
 	case ORACLE_CFG_IP_IMPLICIT:
+	case ORACLE_CFG_IP_IMPLICIT_RB:
+	case ORACLE_CFG_DI_IMPLICIT_RB:
 		return implicit_filter(c->md, &c->imp, c->N, x, ud, ua, relax, diag);
 	case ORACLE_CFG_IP_REALIZABLE:
 		return oracle_realizable_filter(c->rz, x, ud, ua, relax, diag);

@@ -30,7 +30,9 @@ enum {
 	ORACLE_CFG_IP_IMPLICIT = 3,
 	ORACLE_CFG_IP_ROBUST = 4,
 	ORACLE_CFG_IP_REALIZABLE = 5,
-	ORACLE_CFG_SEGWAY_TB = 6
+	ORACLE_CFG_SEGWAY_TB = 6,
+	ORACLE_CFG_IP_IMPLICIT_RB = 7, /* ASIFimplicitRB, InvertedPendulum callbacks (split gradients) */
+	ORACLE_CFG_DI_IMPLICIT_RB = 8  /* ASIFimplicitRB, DoubleIntegrator_implicit_tb callbacks (fused gradient) */
 };
 
 /* exact QP by active-set enumeration (qp_enum.c).  Returns 1 or -3. */
@@ -49,6 +51,9 @@ typedef struct oracle_model {
 	void (*dynamics_gradients)(const double *x, double *Df, double *Dg);     /* NULL when fused */
 	void (*dynamics_with_gradient)(const double *x, const double *u, double *f, double *g, double *d_fcl_dx); /* or NULL */
 	void (*backup_controller)(const double *x, double *u, double *Du);
+	/* ASIFimplicitRB only: h_int[j].convert().left() of safetySet_int over the box [x - x_unc, x + x_unc]
+	 * (src/asif_implicit_robust.cpp:640-647), restating the libaffa operations the interval callback performs */
+	void (*safety_set_lower)(const double *x, const double *x_unc, double *h_lo);
 } oracle_model;
 
 const oracle_model *oracle_get_model(int cfg, int variant);
@@ -58,6 +63,7 @@ const oracle_model *oracle_get_model(int cfg, int variant);
  * TB      : [relaxCost, relaxSafeLb, relaxTTS, relaxMinOrtho, backTrajHorizon, backTrajExtend,
  *            backTrajDt, backTrajMinOrtho, satSharpness, (segway) centred, lb, ub, npBTSS]
  * implicit: [relaxCost, relaxReachLb, relaxSafeLb, backTrajHorizon, backTrajDt, satSharpness, npBTSS]
+ * implicitRB: the same seven, then [backContDt, x_unc[0..nx-1]]
  */
 /* dims[0..5] = nx, nu, n_relax, nc, nv, n_diag ; returns 0 or -1 */
 int oracle_dims(int cfg, const double *opts, int n_opts, int32_t *dims);

@@ -348,6 +348,40 @@ static const oracle_model k_ip_implicit = {
 	2, 1, 4, 1, {-1.5, 0.0}, {1.5, 0.0}, ip_safety, ip_backup_set, ip_dynamics, ip_dynamics_gradients, 0,
 	ip_backup_controller};
 
+/* ---------------------------------------------------------------- interval lower bounds for ASIFimplicitRB
+ * safetySet_int on a box safety set {-x_i + hi_i, x_i - lo_i} evaluated in libaffa, then .convert().left():
+ *   x_i   = AAF(interval(x_i - unc_i, x_i + unc_i)):  centre (right + left)/2, one noise term (right - left)/2
+ *           (lib/libaffa/src/aa_aafcommon.cpp:80-101)
+ *   -x_i  : centre and coefficient negated (aa_aafarithm.cpp:173-184);  (+-x_i) +- AAF(constant): centres added /
+ *           subtracted, the coefficient carried over (aa_aafarithm.cpp:35-98, :103-163)
+ *   left  = centre - rad, rad = 0 + |coefficient| (aa_aafcommon.cpp:217-245) */
+static double aa_centre(double lo, double hi) { return (hi + lo) / 2; }
+static double aa_radius(double lo, double hi)
+{
+	double coef = (hi - lo) / 2, sum = 0;
+	if (coef >= 0.0) sum += coef;
+	else sum += -coef;
+	return sum;
+}
+static void box_safety_lower(const double *x, const double *unc, double lo0, double hi0, double lo1, double hi1, double *hl)
+{
+	const double c0 = aa_centre(x[0] - unc[0], x[0] + unc[0]), r0 = aa_radius(x[0] - unc[0], x[0] + unc[0]);
+	const double c1 = aa_centre(x[1] - unc[1], x[1] + unc[1]), r1 = aa_radius(x[1] - unc[1], x[1] + unc[1]);
+	hl[0] = (-c0 + hi0) - r0;
+	hl[1] = (c0 - lo0) - r0;
+	hl[2] = (c1 - lo1) - r1;
+	hl[3] = (-c1 + hi1) - r1;
+}
+static void ip_safety_lower(const double *x, const double *unc, double *hl) { box_safety_lower(x, unc, -M_PI, M_PI, -M_PI, M_PI, hl); }
+static void ditb_safety_lower(const double *x, const double *unc, double *hl) { box_safety_lower(x, unc, -1.0, 1.0, -1.0, 1.0, hl); }
+
+static const oracle_model k_ip_implicit_rb = {
+	2, 1, 4, 1, {-1.5, 0.0}, {1.5, 0.0}, ip_safety, ip_backup_set, ip_dynamics, ip_dynamics_gradients, 0,
+	ip_backup_controller, ip_safety_lower};
+static const oracle_model k_di_implicit_rb = {
+	2, 1, 4, 1, {-1.0, 0.0}, {1.0, 0.0}, ditb_safety, ditb_backup_set, ditb_dynamics, 0,
+	ditb_dynamics_with_gradient, ditb_backup_controller, ditb_safety_lower};
+
 const oracle_model *oracle_get_model(int cfg, int variant)
 {
 	switch (cfg) {
@@ -355,6 +389,8 @@ const oracle_model *oracle_get_model(int cfg, int variant)
 	case ORACLE_CFG_DI_IMPLICIT_TB: return variant ? &k_di_tb_split : &k_di_tb;
 	case ORACLE_CFG_SEGWAY_TB: return variant ? &k_segway_shipped : &k_segway_centred;
 	case ORACLE_CFG_IP_IMPLICIT: return &k_ip_implicit;
+	case ORACLE_CFG_IP_IMPLICIT_RB: return &k_ip_implicit_rb;
+	case ORACLE_CFG_DI_IMPLICIT_RB: return &k_di_implicit_rb;
 	default: return 0;
 	}
 }

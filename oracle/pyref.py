@@ -13,6 +13,7 @@ REF_SO = os.path.join(HERE, "_ref", "libasif_ref.so")
 ORACLE_SO = os.path.join(HERE, "liboracle.so")
 
 CFG_DI_EXPLICIT, CFG_DI_IMPLICIT_TB, CFG_IP_IMPLICIT, CFG_IP_ROBUST, CFG_IP_REALIZABLE, CFG_SEGWAY_TB = 1, 2, 3, 4, 5, 6
+CFG_IP_IMPLICIT_RB, CFG_DI_IMPLICIT_RB = 7, 8  # ASIFimplicitRB on the pendulum (split gradients) / double-integrator (fused) callbacks
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)

@@ -20,7 +20,9 @@ enum {
 	REF_CFG_IP_IMPLICIT = 3,    /* ASIFimplicit   + examples/InvertedPendulum_Implicit.cpp    */
 	REF_CFG_IP_ROBUST = 4,      /* ASIFrobust     + examples/InvertedPendulum_Robust.cpp + KernelData_70-135kg.h */
 	REF_CFG_IP_REALIZABLE = 5,  /* ASIFrealizable + IP dynamics + RealizableKernelData_100Hz_50pt.h */
-	REF_CFG_SEGWAY_TB = 6       /* ASIFimplicitTB + examples/segway_implicit_tb.cpp           */
+	REF_CFG_SEGWAY_TB = 6,      /* ASIFimplicitTB + examples/segway_implicit_tb.cpp           */
+	REF_CFG_IP_IMPLICIT_RB = 7, /* ASIFimplicitRB + examples/InvertedPendulum_Implicit.cpp callbacks (split gradients) */
+	REF_CFG_DI_IMPLICIT_RB = 8  /* ASIFimplicitRB + examples/DoubleIntegrator_implicit_tb.cpp callbacks (fused gradient) */
 };
 
 /* QP mode for every filter created afterwards:

@@ -19,4 +19,6 @@ RefFilter *make_ip_implicit(const double *opts, int n_opts);
 RefFilter *make_ip_robust(const double *opts, int n_opts);
 RefFilter *make_ip_realizable(const double *opts, int n_opts);
 RefFilter *make_segway_tb(const double *opts, int n_opts);
+RefFilter *make_ip_implicit_rb(const double *opts, int n_opts);
+RefFilter *make_di_implicit_rb(const double *opts, int n_opts);
 #endif

@@ -27,6 +27,8 @@ void *ref_create(int cfg, const double *opts, int n_opts)
 	case REF_CFG_IP_ROBUST: return make_ip_robust(opts, n_opts);
 	case REF_CFG_IP_REALIZABLE: return make_ip_realizable(opts, n_opts);
 	case REF_CFG_SEGWAY_TB: return make_segway_tb(opts, n_opts);
+	case REF_CFG_IP_IMPLICIT_RB: return make_ip_implicit_rb(opts, n_opts);
+	case REF_CFG_DI_IMPLICIT_RB: return make_di_implicit_rb(opts, n_opts);
 	default: return 0;
 	}
 }

@@ -133,5 +133,106 @@ struct DiTb : RefFilter {
 };
 } // namespace
 
+
+namespace {
+/* ------------------------------------------------------------------------------------------------
+ * ASIFimplicitRB (src/asif_implicit_robust.cpp), fused-gradient constructor, on the
+ * DoubleIntegrator_implicit_tb callbacks (no example of this class is shipped).  Interval callbacks: the
+ * example's expressions (examples/DoubleIntegrator_implicit_tb.cpp:30-36,55-85) re-typed on interval_t.
+ * ---------------------------------------------------------------------------------------------- */
+void di_safety_set_int(const interval_t *x, interval_t *h, interval_t *Dh)
+{
+	using namespace ex_di_tb;
+	h[0] = -x[0] + xBound[1]; Dh[0] = -1.0; Dh[4] =  0.0;
+	h[1] =  x[0] - xBound[0]; Dh[1] =  1.0; Dh[5] =  0.0;
+	h[2] =  x[1] - vBound[0]; Dh[2] =  0.0; Dh[6] =  1.0;
+	h[3] = -x[1] + vBound[1]; Dh[3] =  0.0; Dh[7] = -1.0;
+}
+void di_backup_set3(const double *x, double *h, double *Dh)
+{
+	double DDh[4];
+	ex_di_tb::backupSet(x, h, Dh, DDh);
+}
+void di_backup_set_int(const interval_t *x, interval_t *h, interval_t *Dh)
+{
+	using namespace ex_di_tb;
+	h[0] = Pv * Pv;
+	for (uint32_t i = 0; i < nx; i++)
+		for (uint32_t j = 0; j < nx; j++) h[0] = h[0] - P[i + j * nx] * x[i] * x[j];
+	for (uint32_t i = 0; i < nx; i++) {
+		Dh[i] = 0.0;
+		for (uint32_t k = 0; k < nx; k++) Dh[i] = Dh[i] + mPpPt[i + k * nx] * x[k];
+	}
+}
+void di_dynamics_with_gradient_int(const interval_t *x, const double *u, interval_t *f, interval_t *g, interval_t *d)
+{
+	using namespace ex_di_tb;
+	for (uint32_t i = 0; i < nx; i++) { /* matrixVectorMultiply(A, x) on interval_t: accumulate from 0, k ascending */
+		f[i] = 0.0;
+		for (uint32_t k = 0; k < nx; k++) f[i] = f[i] + A[i + k * nx] * x[k];
+	}
+	for (uint32_t i = 0; i < nx * nu; i++) g[i] = B[i];
+	for (uint32_t i = 0; i < nx * nx; i++) d[i] = A[i];
+}
+
+struct RbAccessDi : ASIF::ASIFimplicitRB {
+	using ASIF::ASIFimplicitRB::ASIFimplicitRB;
+	const double *A() const { return A_; }
+	const double *b() const { return b_; }
+};
+
+/* opts: [relaxCost, relaxReachLb, relaxSafeLb, backTrajHorizon, backTrajDt, satSharpness, npBTSS, backContDt, x_unc0, x_unc1]
+ * diag: [hSafetyNow, hBackupEnd (this call's trajectory), critIdx[npBTSS], A_[nc*nv], b_[nc]] */
+struct DiImplicitRB : RefFilter {
+	RbAccessDi f;
+	int npBTSS;
+	double xunc[2];
+	static uint32_t np(const double *opts, int n_opts)
+	{
+		return (opts && n_opts >= 7 && opts[6] >= 1.0 && opts[6] <= 16.0) ? (uint32_t)opts[6] : 10u;
+	}
+	DiImplicitRB(const double *opts, int n_opts)
+	    : f(ex_di_tb::nx, ex_di_tb::nu, ex_di_tb::npSS, 1, np(opts, n_opts), ex_di_tb::safetySet, di_safety_set_int,
+	        di_backup_set3, di_backup_set_int, ex_di_tb::dynamicsWithGradient, di_dynamics_with_gradient_int,
+	        ex_di_tb::backupController)
+	{
+		ASIF::ASIFimplicitRB::Options o; /* defaults: include/asif_implicit_robust.h:22-38 */
+		xunc[0] = xunc[1] = 0.0;
+		if (opts && n_opts >= 10) {
+			o.relaxCost = opts[0];
+			o.relaxReachLb = opts[1];
+			o.relaxSafeLb = opts[2];
+			o.backTrajHorizon = opts[3];
+			o.backTrajDt = opts[4];
+			o.satSharpness = opts[5];
+			o.backContDt = opts[7];
+			xunc[0] = opts[8];
+			xunc[1] = opts[9];
+		}
+		o.x_unc = xunc;
+		f.initialize(ex_di_tb::lb, ex_di_tb::ub, o);
+		npBTSS = (int)np(opts, n_opts);
+		nx = 2; nu = 1; n_relax = 2; nc = npBTSS * 4 + 1; nv = 3; n_diag = 2 + npBTSS + nc * nv + nc;
+	}
+	int32_t filter(const double *x, const double *u_des, double *u_act, double *relax, double *diag) override
+	{
+		AAF::set_default(0);
+		int32_t rc = f.filter(x, u_des, u_act, relax);
+		if (diag) {
+			double h[1], Dh[2];
+			diag[0] = f.hSafetyNow_;
+			di_backup_set3(f.backTraj_.back().second.data(), h, Dh);
+			diag[1] = h[0];
+			for (int i = 0; i < npBTSS; i++) diag[2 + i] = (double)f.backTrajCritIdx_[i];
+			memcpy(diag + 2 + npBTSS, f.A(), sizeof(double) * nc * nv);
+			memcpy(diag + 2 + npBTSS + nc * nv, f.b(), sizeof(double) * nc);
+		}
+		return rc;
+	}
+	void plant(const double *x, double *fo, double *go) override { ex_di_tb::dynamics(x, fo, go); }
+};
+} // namespace
+
+RefFilter *make_di_implicit_rb(const double *opts, int n_opts) { return new DiImplicitRB(opts, n_opts); }
 RefFilter *make_di_explicit(const double *opts, int n_opts) { return new DiExplicit(opts, n_opts); }
 RefFilter *make_di_implicit_tb(const double *opts, int n_opts) { return new DiTb(opts, n_opts); }

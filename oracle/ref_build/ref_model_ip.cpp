@@ -69,6 +69,104 @@ struct IpImplicit : RefFilter {
 	void plant(const double *x, double *fo, double *go) override { ex_ip_implicit::dynamics(x, fo, go); }
 };
 
+
+/* ------------------------------------------------------------------------------------------------
+ * ASIFimplicitRB (src/asif_implicit_robust.cpp) on the InvertedPendulum_Implicit callbacks.
+ * The reference ships no example of this class; the interval callbacks below are the example's own
+ * expressions (examples/InvertedPendulum_Implicit.cpp:27-59) re-typed on interval_t, operator for operator.
+ * Only safetySet_int and dynamics_int are ever called by the class (src/asif_implicit_robust.cpp:500,643).
+ * ---------------------------------------------------------------------------------------------- */
+void ip_safety_set_int(const interval_t *x, interval_t *h, interval_t *Dh)
+{
+	using namespace ex_ip_implicit;
+	h[0] = -x[0] + xBound[1]; Dh[0] = -1.0; Dh[4] =  0.0;
+	h[1] =  x[0] - xBound[0]; Dh[1] =  1.0; Dh[5] =  0.0;
+	h[2] =  x[1] - vBound[0]; Dh[2] =  0.0; Dh[6] =  1.0;
+	h[3] = -x[1] + vBound[1]; Dh[3] =  0.0; Dh[7] = -1.0;
+}
+void ip_backup_set_int(const interval_t *x, interval_t *h, interval_t *Dh)
+{
+	using namespace ex_ip_implicit;
+	h[0] = Pv;
+	for (uint32_t i = 0; i < nx; i++)
+		for (uint32_t j = 0; j < nx; j++) h[0] = h[0] - P[i + j * nx] * x[i] * x[j];
+	for (uint32_t i = 0; i < nx; i++) {
+		Dh[i] = 0.0;
+		for (uint32_t k = 0; k < nx; k++) Dh[i] = Dh[i] + mPpPt[i + k * nx] * x[k];
+	}
+}
+void ip_dynamics_int(const interval_t *x, interval_t *f, interval_t *g)
+{
+	f[0] = x[1];
+	f[1] = sin(x[0]);
+	g[0] = 0.;
+	g[1] = 1.;
+}
+void ip_dynamics_gradients_int(const interval_t *x, interval_t *Df, interval_t *Dg)
+{
+	Df[0] = 0.;        Df[2] = 1.;
+	Df[1] = cos(x[0]); Df[3] = 0.;
+	for (uint32_t i = 0; i < 4; i++) Dg[i] = 0.0;
+}
+
+struct RbAccess : ASIF::ASIFimplicitRB {
+	using ASIF::ASIFimplicitRB::ASIFimplicitRB;
+	const double *A() const { return A_; }
+	const double *b() const { return b_; }
+};
+
+/* opts: [relaxCost, relaxReachLb, relaxSafeLb, backTrajHorizon, backTrajDt, satSharpness, npBTSS, backContDt, x_unc0, x_unc1]
+ * diag: as IpImplicit */
+struct IpImplicitRB : RefFilter {
+	RbAccess f;
+	int npBTSS;
+	double xunc[2];
+	static uint32_t np(const double *opts, int n_opts)
+	{
+		return (opts && n_opts >= 7 && opts[6] >= 1.0 && opts[6] <= 16.0) ? (uint32_t)opts[6] : ex_ip_implicit::npBTSS;
+	}
+	IpImplicitRB(const double *opts, int n_opts)
+	    : f(ex_ip_implicit::nx, ex_ip_implicit::nu, ex_ip_implicit::npSS, ex_ip_implicit::npBS, np(opts, n_opts),
+	        ex_ip_implicit::safetySet, ip_safety_set_int, ex_ip_implicit::backupSet, ip_backup_set_int,
+	        ex_ip_implicit::dynamics, ip_dynamics_int, ex_ip_implicit::dynamicsGradients, ip_dynamics_gradients_int,
+	        ex_ip_implicit::backupController)
+	{
+		ASIF::ASIFimplicitRB::Options o; /* defaults: include/asif_implicit_robust.h:22-38 */
+		xunc[0] = xunc[1] = 0.0;
+		if (opts && n_opts >= 10) {
+			o.relaxCost = opts[0];
+			o.relaxReachLb = opts[1];
+			o.relaxSafeLb = opts[2];
+			o.backTrajHorizon = opts[3];
+			o.backTrajDt = opts[4];
+			o.satSharpness = opts[5];
+			o.backContDt = opts[7];
+			xunc[0] = opts[8];
+			xunc[1] = opts[9];
+		}
+		o.x_unc = xunc; /* borrowed pointer (src/asif_implicit_robust.cpp:276-279) */
+		f.initialize(ex_ip_implicit::lb, ex_ip_implicit::ub, o);
+		npBTSS = (int)np(opts, n_opts);
+		nx = 2; nu = 1; n_relax = 2; nc = npBTSS * 4 + 1; nv = 3; n_diag = 2 + npBTSS + nc * nv + nc;
+	}
+	int32_t filter(const double *x, const double *u_des, double *u_act, double *relax, double *diag) override
+	{
+		AAF::set_default(0); /* libaffa's global noise-symbol counter (F12) */
+		int32_t rc = f.filter(x, u_des, u_act, relax);
+		if (diag) {
+			double h[1], Dh[2];
+			diag[0] = f.hSafetyNow_;
+			ex_ip_implicit::backupSet(f.backTraj_.back().second.data(), h, Dh);
+			diag[1] = h[0];
+			for (int i = 0; i < npBTSS; i++) diag[2 + i] = (double)f.backTrajCritIdx_[i];
+			memcpy(diag + 2 + npBTSS, f.A(), sizeof(double) * nc * nv);
+			memcpy(diag + 2 + npBTSS + nc * nv, f.b(), sizeof(double) * nc);
+		}
+		return rc;
+	}
+	void plant(const double *x, double *fo, double *go) override { ex_ip_implicit::dynamics(x, fo, go); }
+};
+
 /* Config 3b.  The shipped example compiles its STANDARD block (pMin = pMax = 1, :12,30-33) and never fills
  * SafetySetData (:51).  Deviation D5: the table comes from include/KernelData_70-135kg.h and the interval
  * dynamics callback below is the example's (:62-69) with [pMin, pMax] as a parameter (the ROBUST block's
@@ -145,3 +243,4 @@ struct IpRobust : RefFilter {
 
 RefFilter *make_ip_implicit(const double *opts, int n_opts) { return new IpImplicit(opts, n_opts); }
 RefFilter *make_ip_robust(const double *opts, int n_opts) { return new IpRobust(opts, n_opts); }
+RefFilter *make_ip_implicit_rb(const double *opts, int n_opts) { return new IpImplicitRB(opts, n_opts); }

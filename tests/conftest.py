@@ -167,3 +167,22 @@ def realizable_engine_kwargs(opts, kernel=None):
 
 
 EXTRA_GOLDEN_JOBS.append(lambda: ("c4_ip_realizable", 5, C4_OPTS, c4_inputs(1200)))
+
+
+# ---- ASIFimplicitRB (no example ships): pendulum callbacks (split gradients, cfg 7) and
+# DoubleIntegrator_implicit_tb callbacks (fused gradient, cfg 8) ---------------------------------------
+# [relaxCost, relaxReachLb, relaxSafeLb, backTrajHorizon, backTrajDt, satSharpness, npBTSS, backContDt, x_unc0, x_unc1]
+RB_IP_OPTS = [50.0, 5.0, 10.0, 5.0, 0.05, 0.1, 10.0, 0.2, 0.05, 0.08]   # npBT 101, hold refreshed every 4th step
+RB_DI_OPTS = [20.0, 1.0, 2.0, 3.0, 0.02, 0.5, 6.0, 0.1, 0.05, 0.01]     # npBT 151, 6 critical points, hold refreshed every 5th step
+RB_DI_NP10_OPTS = [50.0, 5.0, 10.0, 2.0, 0.01, 0.1, 10.0, 0.05, 0.02, 0.03]  # npBT 201, 10 critical points (unrolled kernel)
+# (a hold of 0.3 s at dt 0.1 drives this loop into an exactly periodic orbit: tied min-h keys, whose order std::sort leaves open)
+RB_IP_NP4_OPTS = [50.0, 5.0, 10.0, 2.0, 0.01, 0.5, 4.0, 0.033, 0.1, 0.0]  # 4 critical points, odd hold period, wide bevel
+
+
+def rb_engine_kwargs(opts):
+    return dict(relaxCost=opts[0], relaxReachLb=opts[1], relaxLb=opts[2], backTrajHorizon=opts[3], backTrajDt=opts[4],
+                satSharpness=opts[5], npBTSS=int(opts[6]), backContDt=opts[7], x_unc=[opts[8], opts[9]])
+
+
+EXTRA_GOLDEN_JOBS.append(lambda: ("rb_ip_implicit", 7, RB_IP_OPTS, c3a_inputs(800, seed=SEED + 71)))
+EXTRA_GOLDEN_JOBS.append(lambda: ("rb_di_implicit", 8, RB_DI_OPTS, c2_inputs(800, seed=SEED + 72)))

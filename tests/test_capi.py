@@ -32,7 +32,7 @@ def test_exports_every_declared_symbol(lib):
     assert len(names) >= 11
     for n in names:
         assert hasattr(lib, n), "libasif_b200.so does not export %s" % n
-    assert lib.asif_b200_abi_version() == 1
+    assert lib.asif_b200_abi_version() == 2
 
 
 def test_struct_layout_matches(lib):

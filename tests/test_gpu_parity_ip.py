@@ -99,3 +99,62 @@ def test_robust_large_table(ab):
     assert np.array_equal(rc1, rc2)
     m = rc1 == 1
     assert np.abs(u1[m] - u2[m]).max() < 1e-9 and np.abs(r1[m] - r2[m]).max() < 1e-6
+
+
+@pytest.mark.parametrize("cfg,model,opts,gen,bit_exact", [
+    (7, "MODEL_INVERTED_PENDULUM", cf.RB_IP_OPTS, cf.c3a_inputs, False),
+    (7, "MODEL_INVERTED_PENDULUM", cf.RB_IP_NP4_OPTS, cf.c3a_inputs, False),
+    (8, "MODEL_DOUBLE_INTEGRATOR_TB", cf.RB_DI_OPTS, cf.c2_inputs, True),
+    (8, "MODEL_DOUBLE_INTEGRATOR_TB", cf.RB_DI_NP10_OPTS, cf.c2_inputs, True),
+])
+def test_implicit_rb(ab, oracle, cfg, model, opts, gen, bit_exact):
+    """ASIFimplicitRB on the GPU vs the oracle: zero-order-hold backup input + interval lower bound of the safety rows.
+    DoubleIntegrator (no libm calls, -fmad=false): rows bit-identical.  Pendulum (CUDA sincos): 1e-9."""
+    n = 20_000
+    x, ud = gen(n, seed=cf.SEED + 300 + cfg)
+    eng = ab.Engine(ab.FILTER_IMPLICIT_RB, getattr(ab, model), **cf.rb_engine_kwargs(opts))
+    u, relax, rc, diag = eng.filter_batch(x, ud, want_diag=True)
+    u0, relax0, rc0, diag0 = oracle.filter_batch(cfg, x, ud, opts, want_diag=True)
+    flips = np.nonzero(rc != rc0)[0]
+    print("implicitRB cfg", cfg, "rc", dict(zip(*np.unique(rc0, return_counts=True))), "flips", flips.size,
+          "QP rows/state", eng.last_qp_iterations() / n)
+    assert flips.size <= (0 if bit_exact else max(2, n // 2000))
+    keep = rc == rc0
+    cf.assert_parity("implicitRB", (u[keep], relax[keep], rc[keep]), (u0[keep], relax0[keep], rc0[keep]))
+    if bit_exact:
+        assert np.array_equal(diag, diag0)
+    else:
+        nb = int(opts[6])
+        same = keep & np.all(diag[:, 2:2 + nb] == diag0[:, 2:2 + nb], axis=1)
+        assert same[keep].mean() > 0.995
+        assert (np.abs(diag[same] - diag0[same]) / (1.0 + np.abs(diag0[same]))).max() <= 1e-9
+    u2, relax2, rc2 = eng.filter_batch(x, ud)
+    assert np.array_equal(rc, rc2) and np.array_equal(u, u2) and np.array_equal(relax, relax2)
+
+
+def test_implicit_rb_reduces_to_implicit(ab):
+    """x_unc = 0, hold period = Euler step: the RB kernel returns what the implicit kernel returns."""
+    x, ud = cf.c3a_inputs(5000, seed=9)
+    o = cf.C3A_SHORT_OPTS
+    a = ab.Engine(ab.FILTER_IMPLICIT, ab.MODEL_INVERTED_PENDULUM, **cf.implicit_engine_kwargs(o)).filter_batch(x, ud, want_diag=True)
+    b = ab.Engine(ab.FILTER_IMPLICIT_RB, ab.MODEL_INVERTED_PENDULUM, backContDt=o[4], x_unc=[0.0, 0.0],
+                  **cf.implicit_engine_kwargs(o)).filter_batch(x, ud, want_diag=True)
+    for p, q in zip(a, b):
+        assert np.array_equal(p, q)
+
+
+def test_implicit_rb_golden_on_gpu(ab):
+    import os
+    gold = os.path.join(cf.ROOT, "tests", "golden")
+    for name, model in (("rb_ip_implicit", ab.MODEL_INVERTED_PENDULUM), ("rb_di_implicit", ab.MODEL_DOUBLE_INTEGRATOR_TB)):
+        g = np.load(os.path.join(gold, name + ".npz"))
+        eng = ab.Engine(ab.FILTER_IMPLICIT_RB, model, **cf.rb_engine_kwargs(list(g["opts"])))
+        u, relax, rc, diag = eng.filter_batch(g["x"], g["u_des"], want_diag=True)
+        unp = cf.unpinned_mask(g["rc"], rc, relax, g["qp_status"])
+        assert unp.mean() < 0.03
+        k = ~unp
+        cf.assert_parity("golden " + name, (u[k], relax[k], rc[k]), (g["u_act"][k], g["relax"][k], g["rc"][k]))
+        if name == "rb_di_implicit":
+            assert np.array_equal(diag, g["diag"])
+        else:
+            assert (np.abs(diag - g["diag"]) / (1.0 + np.abs(g["diag"]))).max() <= 1e-9

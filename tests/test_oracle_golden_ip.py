@@ -3,6 +3,7 @@ vectors produced by the reference's own sources.  CPU only."""
 import os
 
 import numpy as np
+import pytest
 
 import conftest as cf
 
@@ -56,3 +57,11 @@ def test_c4_realizable_golden(oracle):
     r1[:, 0] = r0[:, 0] = 0.0
     cf.assert_parity("C4", (u[k], r1[k], rc[k]), (g["u_act"][k], r0[k], g["rc"][k]))
     assert (g["rc"] == -2).sum() > 50 and (g["diag"][:, 0] >= 1).sum() > 100
+
+
+@pytest.mark.parametrize("name", ["rb_ip_implicit", "rb_di_implicit"])
+def test_implicit_rb_golden(oracle, name):
+    """ASIFimplicitRB fixtures from the reference build (libaffa interval safety set, zero-order-hold backup input)."""
+    g, diag, k, rc = run(oracle, name)
+    assert np.array_equal(diag, g["diag"])  # every state: rows do not depend on the QP
+    assert (g["rc"] == -1).sum() > 50 and (g["rc"] == 1).sum() > 50

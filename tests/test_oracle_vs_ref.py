@@ -94,3 +94,40 @@ def test_other_critical_point_counts(oracle, reflib, cfg, npBTSS):
     cf.assert_parity("npBTSS", (u[k], relax[k], rc[k]), (u0[k], relax0[k], rc0[k]))
     m = k & (rc0 == 1)
     assert m.sum() > 20 and np.array_equal(diag[m], diag0[m])
+
+
+@pytest.mark.parametrize("cfg,opts,gen,n", [
+    (pyref.CFG_IP_IMPLICIT_RB, cf.RB_IP_OPTS, cf.c3a_inputs, 1500),
+    (pyref.CFG_IP_IMPLICIT_RB, cf.RB_IP_NP4_OPTS, cf.c3a_inputs, 800),
+    (pyref.CFG_DI_IMPLICIT_RB, cf.RB_DI_OPTS, cf.c2_inputs, 1500),
+    (pyref.CFG_DI_IMPLICIT_RB, cf.RB_DI_NP10_OPTS, cf.c2_inputs, 800),
+    (pyref.CFG_IP_IMPLICIT_RB, None, cf.c3a_inputs, 500),  # Options() defaults of the class
+])
+def test_implicit_rb_matches_reference(oracle, reflib, cfg, opts, gen, n):
+    """ASIFimplicitRB (src/asif_implicit_robust.cpp): zero-order-hold backup input, interval lower bound of h through
+    libaffa.  Every row of A_, b_ and the critical indices must carry the reference's bits for every state (the
+    assembly does not depend on the QP); u / relax / rc within tolerance wherever the OSQP stand-in converged."""
+    x, ud = gen(n, seed=cf.SEED + 200 + cfg)
+    f = reflib.create(cfg, opts)
+    u0, relax0, rc0, diag0, st0, it0 = f.filter_batch_ex(x, ud)
+    u, relax, rc, diag = oracle.filter_batch(cfg, x, ud, opts, want_diag=True)
+    assert np.array_equal(diag, diag0)
+    unpinned = cf.unpinned_mask(rc0, rc, relax, st0)
+    print("cfg", cfg, "rc", dict(zip(*np.unique(rc0, return_counts=True))), "unpinned", int(unpinned.sum()))
+    assert unpinned.mean() < 0.03
+    k = ~unpinned
+    cf.assert_parity("rb cfg%d" % cfg, (u[k], relax[k], rc[k]), (u0[k], relax0[k], rc0[k]))
+    assert (rc0 == 1).sum() > 50 and (rc0 == -1).sum() > 50
+
+
+def test_implicit_rb_reduces_to_implicit(oracle, reflib):
+    """x_unc = 0 and a hold period equal to the Euler step: ASIFimplicitRB is ASIFimplicit (reference vs reference, and
+    oracle vs oracle), bit for bit."""
+    x, ud = cf.c3a_inputs(300, seed=5)
+    o = list(cf.C3A_SHORT_OPTS) + [10.0]
+    f3, f7 = reflib.create(pyref.CFG_IP_IMPLICIT, o), reflib.create(pyref.CFG_IP_IMPLICIT_RB, o + [o[4], 0.0, 0.0])
+    d3, d7 = f3.filter_batch(x, ud, True)[3], f7.filter_batch(x, ud, True)[3]
+    assert np.array_equal(d3, d7)
+    e3 = oracle.filter_batch(pyref.CFG_IP_IMPLICIT, x, ud, o, want_diag=True)[3]
+    e7 = oracle.filter_batch(pyref.CFG_IP_IMPLICIT_RB, x, ud, o + [o[4], 0.0, 0.0], want_diag=True)[3]
+    assert np.array_equal(e3, e7) and np.array_equal(e3, d3)
