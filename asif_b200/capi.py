@@ -41,6 +41,14 @@ class EngineConfig(C.Structure):
     ]
 
 
+class LearningData(C.Structure):
+    """Mirror of struct asif_learning_data = ASIF::LearningData (include/asif_learning_utils.h:8-32)."""
+    _fields_ = [(k, C.c_uint32) for k in ("d_drift_in", "d_act_in", "d_drift_hidden", "d_act_hidden", "d_drift_hidden_2",
+                                          "d_act_hidden_2", "d_drift_out", "d_act_out")] + \
+               [(k, _dp) for k in ("w_1_drift", "w_2_drift", "w_3_drift", "b_1_drift", "b_2_drift", "b_3_drift",
+                                   "w_1_act", "w_2_act", "w_3_act", "b_1_act", "b_2_act", "b_3_act")]
+
+
 class LoopConfig(C.Structure):
     """Mirror of struct asif_loop_config (include/asif_b200.h)."""
     _fields_ = [
@@ -87,6 +95,7 @@ def load_library():
     L.asif_engine_rollout.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_double, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.c_int32, C.c_void_p]
     L.asif_engine_last_qp_iterations.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+    L.asif_engine_set_learning.argtypes = [C.c_void_p, C.POINTER(LearningData)]
     L.asif_loop_config_init.argtypes = [C.POINTER(LoopConfig)]
     L.asif_engine_loop_log_dims.argtypes = [C.c_void_p, C.POINTER(LoopConfig), C.POINTER(C.c_int64)]
     L.asif_engine_closed_loop.argtypes = [C.c_void_p, C.c_int64, C.POINTER(LoopConfig)] + [C.c_void_p] * 5 + \
@@ -254,6 +263,25 @@ class Engine:
                                          relax.ctypes.data, rc.ctypes.data, hist, log.ctypes.data if nlog else None, MEM_HOST, None))
         return dict(x=x, u_act=u, relax=relax, rc=rc, rc_hist=np.array(list(hist), dtype=np.int64), log=log,
                     fields=loop_log_fields(self.nx, self.nu, self.n_relax))
+
+    def set_learning(self, dims=None, blob=None):
+        """Options.use_learning: dims = (d_drift_in, d_act_in, d_drift_hidden, d_act_hidden, d_drift_hidden_2,
+        d_act_hidden_2, d_drift_out, d_act_out); blob = drift net (w1, b1, w2, b2, w3, b3; weights column-major) then the
+        actuation net.  set_learning() switches the residual off."""
+        L = load_library()
+        if dims is None:
+            _check(L.asif_engine_set_learning(self._h, None))
+            return
+        b = np.ascontiguousarray(blob, dtype=np.float64)
+        din, ain, dh1, ah1, dh2, ah2, dout, aout = (int(v) for v in dims)
+        ld = LearningData(din, ain, dh1, ah1, dh2, ah2, dout, aout)
+        pos = 0
+        for (i, h1, h2, o, tag) in ((din, dh1, dh2, dout, "drift"), (ain, ah1, ah2, aout, "act")):
+            for name, ln in (("w_1", h1 * i), ("b_1", h1), ("w_2", h2 * h1), ("b_2", h2), ("w_3", o * h2), ("b_3", o)):
+                setattr(ld, "%s_%s" % (name, tag), C.cast(b.ctypes.data + 8 * pos, _dp))
+                pos += ln
+        assert pos == b.size, "blob length does not match the layer widths"
+        _check(L.asif_engine_set_learning(self._h, C.byref(ld)))
 
     def last_qp_iterations(self):
         v = C.c_uint64()

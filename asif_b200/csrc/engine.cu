@@ -669,6 +669,7 @@ int32_t asif_engine_destroy(asif_engine *e)
 		if (b.ev) cudaEventDestroy(b.ev);
 	}
 	cudaFree(e->d_table);
+	cudaFree(e->d_learn);
 	cudaFree(e->d_kernel);
 	cudaFree(e->d_ttable);
 	delete e;
@@ -767,6 +768,61 @@ int32_t asif_engine_rollout(asif_engine *e, int64_t n, int32_t steps, double dt,
 		CUDA_TRY(cudaMemcpy(h, e->d_counters, sizeof(h), cudaMemcpyDeviceToHost));
 		for (int i = 0; i < 8; i++) rc_hist[i] = (int64_t)h[1 + i];
 	}
+	return ASIF_OK;
+}
+
+int32_t asif_engine_set_learning(asif_engine *e, const asif_learning_data *d)
+{
+	if (!e) return fail(ASIF_ERR_INVALID_ARGUMENT, "engine is NULL");
+	if (e->cfg.filter != ASIF_FILTER_IMPLICIT && e->cfg.filter != ASIF_FILTER_IMPLICIT_RB)
+		return fail(ASIF_ERR_UNSUPPORTED, "the learned residual exists in ASIFimplicit and ASIFimplicitRB only (filter %d given)", e->cfg.filter);
+	CUDA_TRY(cudaSetDevice(e->cfg.device));
+	CUDA_TRY(cudaDeviceSynchronize()); // no launch may still read the previous networks
+	cudaFree(e->d_learn);
+	e->d_learn = nullptr;
+	memset(&e->im.learn, 0, sizeof(e->im.learn));
+	if (!d) return ASIF_OK;
+	const uint32_t din[2] = {d->d_drift_in, d->d_act_in}, dh1[2] = {d->d_drift_hidden, d->d_act_hidden};
+	const uint32_t dh2[2] = {d->d_drift_hidden_2, d->d_act_hidden_2}, dout[2] = {d->d_drift_out, d->d_act_out};
+	const double *w[2][6] = {{d->w_1_drift, d->b_1_drift, d->w_2_drift, d->b_2_drift, d->w_3_drift, d->b_3_drift},
+	                         {d->w_1_act, d->b_1_act, d->w_2_act, d->b_2_act, d->w_3_act, d->b_3_act}};
+	size_t len[2][6], total = 0;
+	for (int t = 0; t < 2; t++) {
+		if (din[t] < 2u * (uint32_t)e->nx || din[t] > (uint32_t)LEARN_MAX_WIDTH || dh1[t] < 1 || dh1[t] > (uint32_t)LEARN_MAX_WIDTH ||
+		    dh2[t] < 1 || dh2[t] > (uint32_t)LEARN_MAX_WIDTH || dout[t] < (t == 0 ? 1u : (uint32_t)e->nu) || dout[t] > (uint32_t)LEARN_MAX_WIDTH)
+			return fail(ASIF_ERR_INVALID_ARGUMENT, "learning data: net %d has widths in %u, hidden %u / %u, out %u (need in >= 2 nx, all <= %d)",
+			            t, din[t], dh1[t], dh2[t], dout[t], LEARN_MAX_WIDTH);
+		len[t][0] = (size_t)dh1[t] * din[t]; len[t][1] = dh1[t];
+		len[t][2] = (size_t)dh2[t] * dh1[t]; len[t][3] = dh2[t];
+		len[t][4] = (size_t)dout[t] * dh2[t]; len[t][5] = dout[t];
+		for (int k = 0; k < 6; k++) {
+			if (!w[t][k]) return fail(ASIF_ERR_INVALID_ARGUMENT, "learning data: a weight or bias pointer is NULL");
+			total += len[t][k];
+		}
+	}
+	double *host = new (std::nothrow) double[total];
+	if (!host) return fail(ASIF_ERR_INVALID_ARGUMENT, "out of host memory");
+	size_t pos = 0;
+	LearnNets L;
+	memset(&L, 0, sizeof(L));
+	for (int t = 0; t < 2; t++) {
+		L.off[t] = (int32_t)pos;
+		L.d_in[t] = (int32_t)din[t]; L.d_h1[t] = (int32_t)dh1[t]; L.d_h2[t] = (int32_t)dh2[t]; L.d_out[t] = (int32_t)dout[t];
+		for (int k = 0; k < 6; k++) {
+			memcpy(host + pos, w[t][k], sizeof(double) * len[t][k]);
+			pos += len[t][k];
+		}
+	}
+	cudaError_t ce = cudaMalloc(&e->d_learn, sizeof(double) * total);
+	if (ce == cudaSuccess) ce = cudaMemcpy(e->d_learn, host, sizeof(double) * total, cudaMemcpyHostToDevice);
+	delete[] host;
+	if (ce != cudaSuccess) {
+		cudaFree(e->d_learn);
+		e->d_learn = nullptr;
+		return fail(ASIF_ERR_CUDA, "learning data upload failed: %s", cudaGetErrorString(ce));
+	}
+	L.blob = e->d_learn;
+	e->im.learn = L;
 	return ASIF_OK;
 }
 

@@ -70,6 +70,7 @@ struct asif_engine {
 	void *d_kernel = nullptr; // polytope kernel tables (realizable filter), one allocation
 	size_t rz_smem = 0;
 	double *d_table = nullptr; // half-plane table (robust filter)
+	double *d_learn = nullptr; // learned-residual networks (implicit filters)
 	Slot slot[N_SLOTS];
 	cudaStream_t stream = nullptr; // device-memory calls without a caller stream
 	unsigned long long *d_counters = nullptr; // [0] qp rows processed, [1..8] rc histogram

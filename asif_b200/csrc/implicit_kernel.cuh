@@ -19,6 +19,59 @@ namespace asifb {
 
 constexpr int IMP_THREADS = 128;
 
+// The two residual networks of include/asif_learning_utils.h:8-32 on the device: weights column-major [rows x cols]
+// as matrixVectorMultiply reads them, in one blob: drift net (w1, b1, w2, b2, w3, b3) then actuation net.
+constexpr int LEARN_MAX_WIDTH = 64; // widest input / hidden layer accepted
+struct LearnNets {
+	const double *blob; // nullptr: use_learning == false
+	int32_t d_in[2], d_h1[2], d_h2[2], d_out[2]; // [0] drift net, [1] actuation net
+	int32_t off[2];                              // offset of each net inside the blob
+};
+
+// driftNN / actNN (include/asif_learning_utils.h:34-119): out = W3 relu(W2 relu(W1 in + b1) + b2) + b3, every product
+// accumulated from 0.0 with k ascending (include/asif_utils.h:46-62).  Only the first n_out outputs are formed (the
+// reference forms all and uses the first / the first nu).  Kept out of line: it runs once per state.
+static __device__ __noinline__ void learn_mlp(const double *__restrict__ w, const int din, const int dh1, const int dh2, const int dout,
+                                       const double *in, const int n_out, double *out)
+{
+	double o1[LEARN_MAX_WIDTH], o2[LEARN_MAX_WIDTH];
+	const double *w1 = w, *b1 = w1 + dh1 * din, *w2 = b1 + dh1, *b2 = w2 + dh2 * dh1, *w3 = b2 + dh2, *b3 = w3 + dout * dh2;
+	for (int i = 0; i < dh1; i++) {
+		double acc = 0.0;
+		for (int k = 0; k < din; k++) acc = acc + __ldg(w1 + i + k * dh1) * in[k];
+		o1[i] = fmax(0., acc + __ldg(b1 + i));
+	}
+	for (int i = 0; i < dh2; i++) {
+		double acc = 0.0;
+		for (int k = 0; k < dh1; k++) acc = acc + __ldg(w2 + i + k * dh2) * o1[k];
+		o2[i] = fmax(0., acc + __ldg(b2 + i));
+	}
+	for (int i = 0; i < n_out; i++) {
+		double acc = 0.0;
+		for (int k = 0; k < dh2; k++) acc = acc + __ldg(w3 + i + k * dout) * o2[k];
+		out[i] = acc + __ldg(b3 + i);
+	}
+}
+
+// update_weights (include/asif_learning_utils.h:121-155): input [x ; Dh_index_[0..nx-1] ; 0 ...] for both nets
+template <int NX, int NU>
+__device__ __forceinline__ void learned_residual(const LearnNets &L, const double *x, const double *dh_index, double &dLf,
+                                                 double (&dLg)[NU])
+{
+	double in[LEARN_MAX_WIDTH];
+#pragma unroll 1
+	for (int i = 0; i < LEARN_MAX_WIDTH; i++) in[i] = 0.0;
+#pragma unroll
+	for (int i = 0; i < NX; i++) {
+		in[i] = x[i];
+		in[i + NX] = dh_index[i];
+	}
+	double od[1];
+	learn_mlp(L.blob + L.off[0], L.d_in[0], L.d_h1[0], L.d_h2[0], L.d_out[0], in, 1, od);
+	dLf = od[0];
+	learn_mlp(L.blob + L.off[1], L.d_in[1], L.d_h1[1], L.d_h2[1], L.d_out[1], in, NU, dLg);
+}
+
 // Options of ASIFimplicit (include/asif_implicit.h:20-34) + what initialize() derives (src/asif_implicit.cpp:211-254)
 struct ImplicitParams {
 	double lb[MAX_NU], ub[MAX_NU];
@@ -33,6 +86,8 @@ struct ImplicitParams {
 	// ASIFimplicitRB only (include/asif_implicit_robust.h:22-38)
 	double backContDt;
 	double x_unc[4];
+	// learned residual (Options.use_learning, include/asif_learning_utils.h): device blob or nullptr
+	LearnNets learn;
 };
 
 constexpr int IMP_NPBTSS_RUNTIME = -16; // generic instantiation: any npBTSS in 1..16 (see np_capacity in tb_kernel.cuh)
@@ -58,14 +113,21 @@ struct ImpRows {
 	double lgB[NPBS][NU], hB[NPBS], rhsB[NPBS]; // backup rows
 	double lb[NV], ub[NV];
 	double x_unc[RB ? NX : 1];
+	bool learn;           // Options.use_learning
+	double dLf, dLg[NU];  // residual on Lfh[0] / Lgh[0..nu-1] (flat, column-major npTC x nu: rows 0..nu-1 of column 0)
 
-	__device__ __forceinline__ void point_rows(const int slot, double (&n)[NPSS][NV], double (&rhs)[NPSS]) const
+	__device__ __forceinline__ void point_rows(const int slot, double (&n)[NPSS][NV], double (&rhs)[NPSS], const bool first = false) const
 	{
 		double xs[NS], hs[NPSS], lf[NPSS], lg[NPSS * NU];
 #pragma unroll
 		for (int e = 0; e < NS; e++) xs[e] = snap[(slot * NS + e) * T];
 		safety_point_rows<M>(xs, f, g, hs, lf, lg);
 		if (RB) M::safety_set_lower(xs, x_unc, hs);
+		if (learn && first) { // Lfh[0] += ..., Lgh[i] += ... before A_ and b_ are filled (src/asif_implicit.cpp:585-611)
+			lf[0] += dLf;
+#pragma unroll
+			for (int i = 0; i < NU; i++) lg[i * NU] += dLg[i];
+		}
 #pragma unroll
 		for (int j = 0; j < NPSS; j++) {
 #pragma unroll
@@ -110,7 +172,7 @@ struct ImpRows {
 #pragma unroll
 			for (int t = 0; t < CAP; t++) slot = (t == s) ? kslot[t] : slot;
 			double n[NPSS][NV], rhs[NPSS];
-			point_rows(slot, n, rhs);
+			point_rows(slot, n, rhs, s == 0);
 #pragma unroll
 			for (int j = 0; j < NPSS; j++) fn(s * NPSS + j, n[j], rhs[j]);
 		}
@@ -136,7 +198,7 @@ struct ImpRows {
 #pragma unroll
 			for (int t = 0; t < CAP; t++) slot = (t == s) ? kslot[t] : slot;
 			double nn[NPSS][NV], rr[NPSS];
-			point_rows(slot, nn, rr);
+			point_rows(slot, nn, rr, s == 0);
 #pragma unroll
 			for (int t = 0; t < NPSS; t++) {
 				if (t == jj) {
@@ -260,6 +322,27 @@ implicit_filter_kernel(const ImplicitParams p, const int64_t n, const double *__
 	}
 	// open-loop dynamics at the current state (:414-416) and the backup rows at the trajectory end (:542-554)
 	M::dynamics(x0, R.f, R.g);
+	R.learn = p.learn.blob != nullptr;
+	R.dLf = 0.0;
+#pragma unroll
+	for (int i = 0; i < NU; i++) R.dLg[i] = 0.0;
+	if (R.learn) {
+		// Dh_index_ = DhSS(x_c) Q_c of the first critical point, npSS x nx column-major; its first nx entries
+		// (src/asif_implicit.cpp:533-537, include/asif_learning_utils.h:127-129)
+		double xs[NS], hq[NPSS], Dq[NPSS * NX], dhi[NX];
+#pragma unroll
+		for (int e = 0; e < NS; e++) xs[e] = snap[(R.kslot[0] * NS + e) * T];
+		M::safety_set(xs, hq, Dq);
+#pragma unroll
+		for (int i = 0; i < NX; i++) {
+			const int row = i % NPSS, col = i / NPSS;
+			double acc = 0.0;
+#pragma unroll
+			for (int m = 0; m < NX; m++) acc = acc + Dq[row + m * NPSS] * xs[NX + m + col * NX];
+			dhi[i] = acc;
+		}
+		learned_residual<NX, NU>(p.learn, x0, dhi, R.dLf, R.dLg);
+	}
 	double hBackupEnd;
 	{
 		double hB[NPBS], DhB[NPBS * NX];

@@ -155,6 +155,10 @@ namespace ASIF
 
 		inline std::string lastError(void) { return std::string(asif_last_error()); }
 
+		// ASIF::LearningData (include/asif_learning_utils.h:8-32): same fields (without the two output pointers Lfh_diff /
+		// Lgh_diff, which the reference allocates anew on every call and never frees, :145-146)
+		typedef asif_learning_data LearningData;
+
 		// common plumbing of the batched filters
 		class FilterBatchBase
 		{
@@ -405,7 +409,9 @@ namespace ASIF
 				double backTrajRelTol = 1.0e-6;
 				double satSharpness = 0.1;
 				double inf = 1e20;
-			} Options; // include/asif_implicit.h:20-34 (x0 / n_debug / use_learning are not on the batched path)
+				bool use_learning = false; // adds the residual of learning_data_ to Lfh[0] / Lgh[0..nu-1] (src/asif_implicit.cpp:585-588)
+			} Options; // include/asif_implicit.h:20-34 (x0 / n_debug are not on the batched path)
+			LearningData learning_data_ = LearningData(); // public member as in the reference (include/asif_implicit.h:125); read at initialize / updateOptions
 
 			FilterBatchImplicit(const Model model, const uint32_t npBTSS = 10, const int32_t device = 0)
 			    : model_(model), npBTSS_(npBTSS), device_(device)
@@ -458,7 +464,12 @@ namespace ASIF
 				cfg.backTrajDt = options_.backTrajDt;
 				cfg.satSharpness = options_.satSharpness;
 				cfg.inf = options_.inf;
-				return create(cfg);
+				r = create(cfg);
+				if (r == 1 && options_.use_learning) {
+					const int32_t rl = asif_engine_set_learning(engine_, &learning_data_);
+					if (rl != ASIF_OK) return rl;
+				}
+				return r;
 			}
 			Model model_;
 			uint32_t npBTSS_;
@@ -488,8 +499,9 @@ namespace ASIF
 				double backTrajRelTol = 1.0e-6;
 				double satSharpness = 0.1;
 				double inf = 1e20;
-				bool use_learning = false; // the learned residual is not built: true is refused
+				bool use_learning = false; // adds the residual of learning_data_ (src/asif_implicit_robust.cpp:705-708)
 			} Options; // include/asif_implicit_robust.h:22-38
+			LearningData learning_data_ = LearningData(); // include/asif_implicit_robust.h:149
 
 			FilterBatchImplicitRB(const Model model, const uint32_t npBTSS = 10, const int32_t device = 0)
 			    : model_(model), npBTSS_(npBTSS), device_(device)
@@ -528,7 +540,6 @@ namespace ASIF
 		protected:
 			int32_t build(void)
 			{
-				if (options_.use_learning) return ASIF_ERR_UNSUPPORTED;
 				asif_engine_config cfg;
 				int32_t r = asif_engine_config_init(&cfg, ASIF_FILTER_IMPLICIT_RB, (int32_t)model_);
 				if (r != ASIF_OK) return r;
@@ -546,7 +557,12 @@ namespace ASIF
 				cfg.inf = options_.inf;
 				const int nx = (model_ == Model::Segway || model_ == Model::SegwayShipped) ? 4 : 2;
 				for (int i = 0; i < nx; i++) cfg.x_unc[i] = options_.x_unc ? options_.x_unc[i] : 0.0;
-				return create(cfg);
+				r = create(cfg);
+				if (r == 1 && options_.use_learning) {
+					const int32_t rl = asif_engine_set_learning(engine_, &learning_data_);
+					if (rl != ASIF_OK) return rl;
+				}
+				return r;
 			}
 			Model model_;
 			uint32_t npBTSS_;

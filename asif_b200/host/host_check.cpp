@@ -115,6 +115,21 @@ int main()
 			ro.satSharpness = 5.0;
 			if (rb.updateOptions(ro) != 2) return fail("FilterBatchImplicitRB::updateOptions clamp code");
 			if (rb.filter(x, uDes, uRb, relaxRb) != 1) return fail("FilterBatchImplicitRB::filter with x_unc");
+			// learned residual: networks whose last layer is all zero except the bias: Lfh[0] += 0.25, Lgh[0] += 0 -> rows move, call succeeds
+			const double w1[4 * 3] = {0.1, -0.2, 0.3, 0.0, 0.2, 0.1, -0.1, 0.3, 0.0, 0.1, 0.2, -0.3}, b1[3] = {0.1, 0.0, -0.1};
+			const double w2[3 * 2] = {0.5, -0.5, 0.25, 0.1, -0.2, 0.3}, b2[2] = {0.0, 0.1};
+			const double w3[2 * 1] = {0.0, 0.0}, b3d[1] = {0.25}, b3a[1] = {0.0};
+			b200::LearningData &L = rb.learning_data_;
+			L.d_drift_in = L.d_act_in = 4; L.d_drift_hidden = L.d_act_hidden = 3; L.d_drift_hidden_2 = L.d_act_hidden_2 = 2;
+			L.d_drift_out = L.d_act_out = 1;
+			L.w_1_drift = L.w_1_act = w1; L.b_1_drift = L.b_1_act = b1; L.w_2_drift = L.w_2_act = w2; L.b_2_drift = L.b_2_act = b2;
+			L.w_3_drift = L.w_3_act = w3; L.b_3_drift = b3d; L.b_3_act = b3a;
+			ro.use_learning = true;
+			ro.satSharpness = 0.1;
+			if (rb.updateOptions(ro) != 1) return fail("FilterBatchImplicitRB::updateOptions with use_learning");
+			double uL[1] = {0.0}, relaxL[2] = {0.0, 0.0};
+			const int32_t rcL = rb.filter(x, uDes, uL, relaxL);
+			if (rcL != 1 && rcL != -1) return fail("FilterBatchImplicitRB::filter with use_learning");
 		}
 		const double planes[4] = {0.5, 0.0, -0.5, 0.0}; // |x0| <= 2
 		b200::FilterBatchRobust rob(2, planes, 0.8, 1.2);

@@ -178,6 +178,22 @@ int32_t asif_engine_closed_loop(asif_engine *e, int64_t n, const asif_loop_confi
                                 double *u_act_last, double *relax_last, int32_t *rc_last, int64_t *rc_hist, double *log,
                                 int32_t mem, void *stream);
 
+/*
+ * Learned residual of the implicit classes (Options.use_learning + the public member learning_data_,
+ * include/asif_implicit.h:33,125, include/asif_implicit_robust.h:37,149; arithmetic include/asif_learning_utils.h:34-155):
+ * two MLPs with two ReLU hidden layers on [x ; Dh_index_[0..nx-1] ; 0...]; the drift net's first output is added to
+ * Lfh[0], the actuation net's first nu outputs to Lgh[0..nu-1], before A_ and b_ are filled.  The struct mirrors
+ * ASIF::LearningData field for field (weights are column-major [rows x cols], as matrixVectorMultiply reads them);
+ * the arrays are host memory and are copied.  data == NULL switches the residual off.  Every layer width <= 64.
+ * ASIF_FILTER_IMPLICIT and ASIF_FILTER_IMPLICIT_RB engines only.
+ */
+typedef struct asif_learning_data {
+	uint32_t d_drift_in, d_act_in, d_drift_hidden, d_act_hidden, d_drift_hidden_2, d_act_hidden_2, d_drift_out, d_act_out;
+	const double *w_1_drift, *w_2_drift, *w_3_drift, *b_1_drift, *b_2_drift, *b_3_drift;
+	const double *w_1_act, *w_2_act, *w_3_act, *b_1_act, *b_2_act, *b_3_act;
+} asif_learning_data;
+int32_t asif_engine_set_learning(asif_engine *e, const asif_learning_data *data);
+
 /* mean QP work of the last filter_batch/rollout call: rows processed by the active-set solver,
  * summed over states (the "K-bar" of SURVEY 8d is this / states) */
 int32_t asif_engine_last_qp_iterations(asif_engine *e, uint64_t *rows_processed);

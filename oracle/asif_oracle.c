@@ -572,6 +572,76 @@ typedef struct {
 	double backContDt, x_unc[NX];
 } imp_options;
 
+/* Learned residual, include/asif_learning_utils.h:34-155: two MLPs (two ReLU hidden layers each) on the input
+ * [x ; Dh_index_[0..nx-1] ; 0...]; the drift net's first output is added to Lfh[0], the actuation net's first nu
+ * outputs to Lgh[0..nu-1] (:148-154).  Dh_index_ holds DhSS(x_c) Q_c (npSS x nx, column-major) of the FIRST critical
+ * point (src/asif_implicit.cpp:533-537), so its first nx entries are column 0 of rows 0..nx-1 - a quirk that is kept.
+ * Weights are column-major [rows x cols] as matrixVectorMultiply reads them (include/asif_utils.h:46-62). */
+static struct {
+	int on;
+	uint32_t d[8];
+	double *blob;
+	const double *w1d, *b1d, *w2d, *b2d, *w3d, *b3d, *w1a, *b1a, *w2a, *b2a, *w3a, *b3a;
+} g_learn;
+
+int oracle_set_learning(const uint32_t *dims, const double *blob)
+{
+	free(g_learn.blob);
+	memset(&g_learn, 0, sizeof(g_learn));
+	if (!dims || !blob) return 0;
+	memcpy(g_learn.d, dims, sizeof(g_learn.d));
+	const uint32_t *d = dims;
+	const size_t nd = (size_t)d[2] * d[0] + d[2] + (size_t)d[4] * d[2] + d[4] + (size_t)d[6] * d[4] + d[6];
+	const size_t na = (size_t)d[3] * d[1] + d[3] + (size_t)d[5] * d[3] + d[5] + (size_t)d[7] * d[5] + d[7];
+	g_learn.blob = (double *)malloc(sizeof(double) * (nd + na));
+	memcpy(g_learn.blob, blob, sizeof(double) * (nd + na));
+	const double *p = g_learn.blob;
+	g_learn.w1d = p; p += (size_t)d[2] * d[0];
+	g_learn.b1d = p; p += d[2];
+	g_learn.w2d = p; p += (size_t)d[4] * d[2];
+	g_learn.b2d = p; p += d[4];
+	g_learn.w3d = p; p += (size_t)d[6] * d[4];
+	g_learn.b3d = p; p += d[6];
+	g_learn.w1a = p; p += (size_t)d[3] * d[1];
+	g_learn.b1a = p; p += d[3];
+	g_learn.w2a = p; p += (size_t)d[5] * d[3];
+	g_learn.b2a = p; p += d[5];
+	g_learn.w3a = p; p += (size_t)d[7] * d[5];
+	g_learn.b3a = p; p += d[7];
+	g_learn.on = 1;
+	return 0;
+}
+
+/* driftNN / actNN, include/asif_learning_utils.h:34-119 */
+static void mlp3(const double *w1, const double *b1, const double *w2, const double *b2, const double *w3, const double *b3,
+                 int din, int dh1, int dh2, int dout, const double *in, double *out)
+{
+	double *o1 = (double *)malloc(sizeof(double) * (dh1 + 1)), *o2 = (double *)malloc(sizeof(double) * (dh2 + 1));
+	double *o3 = (double *)malloc(sizeof(double) * (dout + 1));
+	mat_vec(w1, dh1, din, in, o1);
+	for (int i = 0; i < dh1; i++) o1[i] = fmax(0., o1[i] + b1[i]);
+	mat_vec(w2, dh2, dh1, o1, o2);
+	for (int i = 0; i < dh2; i++) o2[i] = fmax(0., o2[i] + b2[i]);
+	mat_vec(w3, dout, dh2, o2, o3);
+	for (int i = 0; i < dout; i++) out[i] = o3[i] + b3[i];
+	free(o1); free(o2); free(o3);
+}
+
+/* update_weights, include/asif_learning_utils.h:121-155 */
+static void learned_residual(const double *x, int nx, const double *DhIndex, double *Lfh, double *Lgh, int nu)
+{
+	const uint32_t *d = g_learn.d;
+	double *din = (double *)calloc(d[0] + 1, sizeof(double)), *ain = (double *)calloc(d[1] + 1, sizeof(double));
+	double *dout = (double *)calloc(d[6] + 1, sizeof(double)), *aout = (double *)calloc(d[7] + 1, sizeof(double));
+	for (int i = 0; i < nx; i++) din[i] = ain[i] = x[i];
+	for (int i = 0; i < nx; i++) din[i + nx] = ain[i + nx] = DhIndex[i];
+	mlp3(g_learn.w1d, g_learn.b1d, g_learn.w2d, g_learn.b2d, g_learn.w3d, g_learn.b3d, d[0], d[2], d[4], d[6], din, dout);
+	mlp3(g_learn.w1a, g_learn.b1a, g_learn.w2a, g_learn.b2a, g_learn.w3a, g_learn.b3a, d[1], d[3], d[5], d[7], ain, aout);
+	Lfh[0] += dout[0];
+	for (int i = 0; i < nu; i++) Lgh[i] += aout[i];
+	free(din); free(ain); free(dout); free(aout);
+}
+
 static int32_t implicit_filter(const oracle_model *md, const imp_options *o, int N, const double *x, const double *uDes,
                                double *uAct, double *relax, double *diag)
 {
@@ -595,7 +665,7 @@ static int32_t implicit_filter(const oracle_model *md, const imp_options *o, int
 
 	double *h = (double *)calloc(npTC, sizeof(double));
 	double *Dh = (double *)calloc((size_t)npTC * nx, sizeof(double));
-	double DhSSDx[64];
+	double DhSSDx[64], DhIndex[64] = {0.0};
 	for (int idx = 0; idx < npBTSS; idx++) { /* :518-540 */
 		int c = crit[idx];
 		memcpy(h + idx * npSS, hFull + (size_t)c * npSS, sizeof(double) * npSS);
@@ -604,6 +674,7 @@ static int32_t implicit_filter(const oracle_model *md, const imp_options *o, int
 		mat_mul(DhFull + (size_t)c * npSS * nx, npSS, nx, traj + (size_t)c * ns + nx, nx, DhSSDx);
 		for (int i = 0; i < npSS; i++)
 			for (int j = 0; j < nx; j++) Dh[(idx * npSS + i) + j * npTC] = DhSSDx[i + j * npSS];
+		if (idx == 0) memcpy(DhIndex, DhSSDx, sizeof(double) * npSS * nx); /* Dh_index_, :533-537 (n_debug == -1) */
 	}
 	/* backup-set rows at the end of the trajectory, :542-554 */
 	const double *btX = traj + (size_t)(N - 1) * ns;
@@ -618,6 +689,7 @@ static int32_t implicit_filter(const oracle_model *md, const imp_options *o, int
 	double *Lgh = (double *)malloc(sizeof(double) * (size_t)npTC * nu);
 	mat_vec(Dh, npTC, nx, f, Lfh);
 	mat_mul(Dh, npTC, nx, g, nu, Lgh);
+	if (g_learn.on) learned_residual(x, nx, DhIndex, Lfh, Lgh, nu); /* :585-588 */
 	double *A = (double *)calloc((size_t)npTC * nv, sizeof(double));
 	double *b = (double *)calloc(npTC, sizeof(double));
 	for (int i = 0; i < npTC; i++) /* :590-611 */

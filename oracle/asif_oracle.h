@@ -70,6 +70,9 @@ int oracle_dims(int cfg, const double *opts, int n_opts, int32_t *dims);
 /* one call = the reference's filter(x, uDes, uAct, relax) on each of the n states, stateless */
 int oracle_filter_batch(int cfg, const double *opts, int n_opts, int64_t n, const double *x, const double *u_des,
                         double *u_act, double *relax, int32_t *rc, double *diag);
+/* learned residual of the implicit classes (cfg 3, 7, 8), include/asif_learning_utils.h: process-wide switch, NULL = off.
+ * dims[8] / blob as ref_set_learning (oracle/ref_build/ref_api.h) */
+int oracle_set_learning(const uint32_t *dims, const double *blob);
 /* closed-loop rollout (example main loops): x += dt*(f + g*uAct), in place */
 int oracle_rollout(int cfg, const double *opts, int n_opts, int64_t n, int32_t steps, double dt, double *x,
                    const double *u_des, double *u_act_last, int32_t *rc_last, int64_t *rc_hist);

@@ -65,6 +65,13 @@ class RefFilter:
         lib.lib.ref_dims(h, dims.ctypes.data_as(_ip))
         self.nx, self.nu, self.n_relax, self.nc, self.nv, self.n_diag = (int(v) for v in dims)
 
+    def set_learning(self, dims, blob):
+        """Options.use_learning = true with these networks (implicit classes only)."""
+        d = np.ascontiguousarray(dims, dtype=np.uint32)
+        b = np.ascontiguousarray(blob, dtype=np.float64)
+        self.lib.lib.ref_set_learning.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), _dp]
+        assert self.lib.lib.ref_set_learning(self.h, d.ctypes.data_as(C.POINTER(C.c_uint32)), _d(b)) == 0
+
     def filter_batch(self, x, u_des, want_diag=False):
         x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1, self.nx)
         u_des = np.ascontiguousarray(u_des, dtype=np.float64).reshape(-1, self.nu)
@@ -130,6 +137,16 @@ class OracleLib:
                                      C.POINTER(C.c_int64)]
         L.oracle_qp_solve.argtypes = [C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp,
                                       C.POINTER(C.c_ubyte), _dp]
+
+    def set_learning(self, dims=None, blob=None):
+        """Process-wide learned-residual switch of the implicit classes; set_learning() turns it off."""
+        self.lib.oracle_set_learning.argtypes = [C.POINTER(C.c_uint32), _dp]
+        if dims is None:
+            assert self.lib.oracle_set_learning(None, None) == 0
+            return
+        d = np.ascontiguousarray(dims, dtype=np.uint32)
+        b = np.ascontiguousarray(blob, dtype=np.float64)
+        assert self.lib.oracle_set_learning(d.ctypes.data_as(C.POINTER(C.c_uint32)), _d(b)) == 0
 
     def dims(self, cfg, opts=None):
         o = None if opts is None else np.ascontiguousarray(opts, dtype=np.float64)
@@ -201,3 +218,16 @@ def realizable_export(ref_filter):
                                    fa.ctypes.data_as(_ip), _d(lie)) == 0
     return dict(vertices=vertices, normals=normals, facet_vertices=fv, facet_active=fa, facet_lie=lie,
                 max_critical_facets=maxCrit, max_active_constraints=maxAct)
+
+
+def learning_blob(dims, seed=7, scale=0.3):
+    """Random networks for the learned residual in the blob layout ref_set_learning / oracle_set_learning /
+    asif_engine_set_learning share: drift net (w1 [hidden x in] column-major, b1, w2, b2, w3, b3), then the actuation net."""
+    g = np.random.Generator(np.random.Philox(key=seed))
+    din, ain, dh1, ah1, dh2, ah2, dout, aout = (int(v) for v in dims)
+    parts = []
+    for (i, h1, h2, o) in ((din, dh1, dh2, dout), (ain, ah1, ah2, aout)):
+        for (r, c) in ((h1, i), (h2, h1), (o, h2)):
+            parts.append(g.normal(0, scale, r * c))
+            parts.append(g.normal(0, scale, r))
+    return np.concatenate(parts)

@@ -38,6 +38,10 @@ void *ref_create(int cfg, const double *opts, int n_opts);
 void ref_destroy(void *h);
 /* dims[0..5] = nx, nu, n_relax, nc (rows of A_), nv, n_diag */
 int ref_dims(void *h, int32_t *dims);
+/* implicit classes (cfg 3, 7, 8): switch on Options.use_learning with these networks (include/asif_learning_utils.h:8-32).
+ * dims[8] = d_drift_in, d_act_in, d_drift_hidden, d_act_hidden, d_drift_hidden_2, d_act_hidden_2, d_drift_out, d_act_out;
+ * blob = drift net (w1 [hidden x in] column-major, b1, w2, b2, w3, b3) followed by the actuation net, same order */
+int ref_set_learning(void *h, const uint32_t *dims, const double *blob);
 /* x[n*nx], u_des[n*nu] row-major per state; outputs u_act[n*nu], relax[n*n_relax], rc[n];
  * diag (optional, n*n_diag doubles): config-specific diagnostics followed by A_ (nc*nv, col-major) and b_ (nc). */
 int ref_filter_batch(void *h, int64_t n, const double *x, const double *u_des,

@@ -35,6 +35,12 @@ void *ref_create(int cfg, const double *opts, int n_opts)
 
 void ref_destroy(void *h) { delete (RefFilter *)h; }
 
+int ref_set_learning(void *h, const uint32_t *dims, const double *blob)
+{
+	RefFilter *f = (RefFilter *)h;
+	return f ? f->set_learning(dims, blob) : -1;
+}
+
 int ref_dims(void *h, int32_t *dims)
 {
 	RefFilter *f = (RefFilter *)h;

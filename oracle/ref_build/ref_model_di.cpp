@@ -187,6 +187,15 @@ struct DiImplicitRB : RefFilter {
 	RbAccessDi f;
 	int npBTSS;
 	double xunc[2];
+	ASIF::ASIFimplicitRB::Options o_;
+	LearnStore learn_;
+	int set_learning(const uint32_t *dims, const double *blob) override
+	{
+		learn_.fill(f.learning_data_, dims, blob);
+		o_.use_learning = true;
+		f.updateOptions(o_);
+		return 0;
+	}
 	static uint32_t np(const double *opts, int n_opts)
 	{
 		return (opts && n_opts >= 7 && opts[6] >= 1.0 && opts[6] <= 16.0) ? (uint32_t)opts[6] : 10u;
@@ -211,6 +220,7 @@ struct DiImplicitRB : RefFilter {
 		}
 		o.x_unc = xunc;
 		f.initialize(ex_di_tb::lb, ex_di_tb::ub, o);
+		o_ = o;
 		npBTSS = (int)np(opts, n_opts);
 		nx = 2; nu = 1; n_relax = 2; nc = npBTSS * 4 + 1; nv = 3; n_diag = 2 + npBTSS + nc * nv + nc;
 	}

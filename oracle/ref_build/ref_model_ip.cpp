@@ -25,6 +25,15 @@ struct ImplicitAccess : ASIF::ASIFimplicit {
 struct IpImplicit : RefFilter {
 	ImplicitAccess f;
 	int npBTSS;
+	ASIF::ASIFimplicit::Options o_;
+	LearnStore learn_;
+	int set_learning(const uint32_t *dims, const double *blob) override
+	{
+		learn_.fill(f.learning_data_, dims, blob);
+		o_.use_learning = true;
+		f.updateOptions(o_);
+		return 0;
+	}
 	static uint32_t np(const double *opts, int n_opts) /* opts[6]: the constructor argument npBTSS */
 	{
 		return (opts && n_opts >= 7 && opts[6] >= 1.0 && opts[6] <= 16.0) ? (uint32_t)opts[6] : ex_ip_implicit::npBTSS;
@@ -49,6 +58,7 @@ struct IpImplicit : RefFilter {
 			o.satSharpness = opts[5];
 		}
 		f.initialize(ex_ip_implicit::lb, ex_ip_implicit::ub, o);
+		o_ = o;
 		npBTSS = (int)np(opts, n_opts);
 		nx = 2; nu = 1; n_relax = 2; nc = npBTSS * 4 + 1; nv = 3; n_diag = 2 + npBTSS + nc * nv + nc;
 	}
@@ -121,6 +131,15 @@ struct IpImplicitRB : RefFilter {
 	RbAccess f;
 	int npBTSS;
 	double xunc[2];
+	ASIF::ASIFimplicitRB::Options o_;
+	LearnStore learn_;
+	int set_learning(const uint32_t *dims, const double *blob) override
+	{
+		learn_.fill(f.learning_data_, dims, blob);
+		o_.use_learning = true;
+		f.updateOptions(o_);
+		return 0;
+	}
 	static uint32_t np(const double *opts, int n_opts)
 	{
 		return (opts && n_opts >= 7 && opts[6] >= 1.0 && opts[6] <= 16.0) ? (uint32_t)opts[6] : ex_ip_implicit::npBTSS;
@@ -146,6 +165,7 @@ struct IpImplicitRB : RefFilter {
 		}
 		o.x_unc = xunc; /* borrowed pointer (src/asif_implicit_robust.cpp:276-279) */
 		f.initialize(ex_ip_implicit::lb, ex_ip_implicit::ub, o);
+		o_ = o;
 		npBTSS = (int)np(opts, n_opts);
 		nx = 2; nu = 1; n_relax = 2; nc = npBTSS * 4 + 1; nv = 3; n_diag = 2 + npBTSS + nc * nv + nc;
 	}

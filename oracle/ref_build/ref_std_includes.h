@@ -23,5 +23,6 @@
 #include <asif++.h>
 #include "CyberTimer.hpp"
 #include "customTimer.h"
+#define ASIF_REF_WITH_LEARNING_HELPER 1
 #include "ref_common.h"
 #endif

@@ -186,3 +186,13 @@ def rb_engine_kwargs(opts):
 
 EXTRA_GOLDEN_JOBS.append(lambda: ("rb_ip_implicit", 7, RB_IP_OPTS, c3a_inputs(800, seed=SEED + 71)))
 EXTRA_GOLDEN_JOBS.append(lambda: ("rb_di_implicit", 8, RB_DI_OPTS, c2_inputs(800, seed=SEED + 72)))
+
+
+# ---- learned residual of the implicit classes (Options.use_learning, include/asif_learning_utils.h) -------------
+# (d_drift_in, d_act_in, d_drift_hidden, d_act_hidden, d_drift_hidden_2, d_act_hidden_2, d_drift_out, d_act_out)
+LEARN_DIMS = [6, 5, 16, 12, 8, 10, 2, 1]
+
+
+def learning_blob(dims=LEARN_DIMS, seed=7, scale=0.3):
+    from oracle import pyref
+    return pyref.learning_blob(dims, seed=seed, scale=scale)

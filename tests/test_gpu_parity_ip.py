@@ -158,3 +158,50 @@ def test_implicit_rb_golden_on_gpu(ab):
             assert np.array_equal(diag, g["diag"])
         else:
             assert (np.abs(diag - g["diag"]) / (1.0 + np.abs(g["diag"]))).max() <= 1e-9
+
+
+@pytest.mark.parametrize("cfg,filt,model,opts,gen,bit_exact", [
+    (3, "FILTER_IMPLICIT", "MODEL_INVERTED_PENDULUM", cf.C3A_SHORT_OPTS, cf.c3a_inputs, False),
+    (7, "FILTER_IMPLICIT_RB", "MODEL_INVERTED_PENDULUM", cf.RB_IP_NP4_OPTS, cf.c3a_inputs, False),
+    (8, "FILTER_IMPLICIT_RB", "MODEL_DOUBLE_INTEGRATOR_TB", cf.RB_DI_OPTS, cf.c2_inputs, True),
+])
+def test_learned_residual(ab, oracle, cfg, filt, model, opts, gen, bit_exact):
+    """Options.use_learning on the GPU (asif_engine_set_learning) against the oracle, then switched off again."""
+    n = 10_000
+    x, ud = gen(n, seed=cf.SEED + 500 + cfg)
+    kw = cf.implicit_engine_kwargs(opts) if cfg == 3 else cf.rb_engine_kwargs(opts)
+    eng = ab.Engine(getattr(ab, filt), getattr(ab, model), **kw)
+    base = eng.filter_batch(x, ud, want_diag=True)
+    blob = cf.learning_blob()
+    eng.set_learning(cf.LEARN_DIMS, blob)
+    u, relax, rc, diag = eng.filter_batch(x, ud, want_diag=True)
+    oracle.set_learning(cf.LEARN_DIMS, blob)
+    try:
+        u0, relax0, rc0, diag0 = oracle.filter_batch(cfg, x, ud, opts, want_diag=True)
+    finally:
+        oracle.set_learning()
+    flips = np.nonzero(rc != rc0)[0]
+    print("learned residual cfg", cfg, "rc", dict(zip(*np.unique(rc0, return_counts=True))), "flips", flips.size)
+    assert flips.size <= (0 if bit_exact else max(2, n // 2000))
+    keep = rc == rc0
+    cf.assert_parity("learning", (u[keep], relax[keep], rc[keep]), (u0[keep], relax0[keep], rc0[keep]))
+    if bit_exact:
+        assert np.array_equal(diag, diag0)
+    else:
+        nb = 10 if cfg == 3 else int(opts[6])
+        same = keep & np.all(diag[:, 2:2 + nb] == diag0[:, 2:2 + nb], axis=1)
+        assert same[keep].mean() > 0.995
+        assert (np.abs(diag[same] - diag0[same]) / (1.0 + np.abs(diag0[same]))).max() <= 1e-9
+    assert (diag != base[3]).any()
+    u2, relax2, rc2 = eng.filter_batch(x, ud)  # non-diag kernel
+    assert np.array_equal(rc, rc2) and np.array_equal(u, u2)
+    eng.set_learning()
+    off = eng.filter_batch(x, ud, want_diag=True)
+    for p, q in zip(base, off):
+        assert np.array_equal(p, q)
+
+
+def test_learning_refused_elsewhere(ab):
+    eng = ab.Engine(ab.FILTER_IMPLICIT_TB, ab.MODEL_DOUBLE_INTEGRATOR_TB, **cf.tb_engine_kwargs(cf.C2_TB_OPTS))
+    with pytest.raises(ab.AsifError):
+        eng.set_learning(cf.LEARN_DIMS, cf.learning_blob())

@@ -131,3 +131,34 @@ def test_implicit_rb_reduces_to_implicit(oracle, reflib):
     e3 = oracle.filter_batch(pyref.CFG_IP_IMPLICIT, x, ud, o, want_diag=True)[3]
     e7 = oracle.filter_batch(pyref.CFG_IP_IMPLICIT_RB, x, ud, o + [o[4], 0.0, 0.0], want_diag=True)[3]
     assert np.array_equal(e3, e7) and np.array_equal(e3, d3)
+
+
+@pytest.mark.parametrize("cfg,opts,gen", [
+    (pyref.CFG_IP_IMPLICIT, cf.C3A_SHORT_OPTS, cf.c3a_inputs),
+    (pyref.CFG_IP_IMPLICIT_RB, cf.RB_IP_OPTS, cf.c3a_inputs),
+    (pyref.CFG_DI_IMPLICIT_RB, cf.RB_DI_OPTS, cf.c2_inputs),
+])
+def test_learned_residual_matches_reference(oracle, reflib, cfg, opts, gen):
+    """Options.use_learning with random networks in learning_data_ (include/asif_learning_utils.h:121-155): Lfh[0] and
+    Lgh[0] move by the two MLP outputs; rows bit-identical to the reference build for every state."""
+    n = 1000
+    x, ud = gen(n, seed=cf.SEED + 400 + cfg)
+    blob = cf.learning_blob()
+    f = reflib.create(cfg, opts)
+    d_off = f.filter_batch(x, ud, want_diag=True)[3]
+    f.set_learning(cf.LEARN_DIMS, blob)
+    u0, relax0, rc0, diag0, st0, it0 = f.filter_batch_ex(x, ud)
+    oracle.set_learning(cf.LEARN_DIMS, blob)
+    try:
+        u, relax, rc, diag = oracle.filter_batch(cfg, x, ud, opts, want_diag=True)
+    finally:
+        oracle.set_learning()
+    assert np.array_equal(diag, diag0)
+    changed = diag0 != d_off
+    nb, nc = int(round(f.n_diag)) and (f.nc - 1) // 4, f.nc
+    # exactly two entries per state differ from the run without the residual: A_[0,0] and b_[0]
+    A0, b0 = 2 + nb, 2 + nb + nc * f.nv
+    assert changed[:, A0].all() and changed[:, b0].all() and changed.sum() == 2 * n
+    k = ~cf.unpinned_mask(rc0, rc, relax, st0)
+    assert k.mean() > 0.95
+    cf.assert_parity("learning cfg%d" % cfg, (u[k], relax[k], rc[k]), (u0[k], relax0[k], rc0[k]))
