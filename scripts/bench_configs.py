@@ -51,6 +51,13 @@ def main():
     x, ud = cf.c3a_inputs(1_000_000)
     run("C3a ASIFimplicit / InvertedPendulum npBT=5001, 1e6 states",
         ab.Engine(ab.FILTER_IMPLICIT, ab.MODEL_INVERTED_PENDULUM, **cf.implicit_engine_kwargs(cf.C3A_OPTS)), x, ud, reps=2)
+    # ASIFimplicitRB (no config of BASELINE.json names it): pendulum callbacks at the example's
+    # horizon (5000 Euler steps), hold period 10 ms, x_unc = (0.05, 0.08); and with the learned residual switched on
+    rb_opts = [50.0, 5.0, 10.0, 5.0, 0.001, 0.1, 10.0, 0.01, 0.05, 0.08]
+    eng = ab.Engine(ab.FILTER_IMPLICIT_RB, ab.MODEL_INVERTED_PENDULUM, **cf.rb_engine_kwargs(rb_opts))
+    run("RB ASIFimplicitRB / InvertedPendulum npBT=5001, hold 10 ms, 1e6 states", eng, x, ud, reps=2)
+    eng.set_learning(cf.LEARN_DIMS, cf.learning_blob())
+    run("RB + learned residual (16/8 and 12/10 hidden units), 1e6 states", eng, x, ud, reps=2)
     x, ud = cf.c3b_inputs(1_000_000)
     o = cf.C3B_OPTS
     run("C3b ASIFrobust / InvertedPendulum + 100 half-planes, 1e6 states",
