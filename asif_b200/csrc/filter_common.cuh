@@ -97,7 +97,8 @@ __device__ __forceinline__ void input_saturate_soft(const SoftSat &s, int i, dou
 	// clamp and pass-through legs as selects (no branch, no register shuffling between the legs) ...
 	const bool sat = a >= s.bevelStop;
 	const bool bevel = !sat && (a > s.bevelStart); // false for NaN: pass through, as the reference's last else
-	const double bound = (uc > 0) ? ub : lb;
+	// SAT_IDENTITY means lb = -1, ub = 1: the bound is the sign of uc on 1.0 (uc = 0 never saturates)
+	const double bound = (SATMODE == SAT_IDENTITY) ? copysign(1.0, uc) : ((uc > 0) ? ub : lb);
 	uSat = sat ? bound : u;
 	DuSat = sat ? 0.0 : 1.0;
 	// ... the circular bevel (sqrt + division) is rare: a real branch, entered only by the lanes that need it

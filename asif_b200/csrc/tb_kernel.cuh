@@ -204,7 +204,7 @@ __device__ __forceinline__ int32_t tb_filter_one(const TbParams &p, const double
 	double hSafetyNow = hs[0];
 #pragma unroll
 	for (int j = 1; j < NPSS; j++) hSafetyNow = (hs[j] < hSafetyNow) ? hs[j] : hSafetyNow;
-	const bool inside = M::backup_set_value(x0) >= 0;
+	const bool inside = M::backup_set_reached(x0);
 
 	// ---- backup trajectory (Euler, :464-487) with streaming selection and hit detection (:505-528)
 	double X[NS];
@@ -286,7 +286,7 @@ __device__ __forceinline__ int32_t tb_filter_one(const TbParams &p, const double
 			}
 			nkept = nkept < CAP ? nkept + 1 : CAP;
 		}
-		hit_now = active && (M::backup_set_value(X) >= 0.0);
+		hit_now = active && M::backup_set_reached(X);
 		if (__any_sync(0xffffffffu, hit_now)) {
 			i++;
 			break;
