@@ -112,12 +112,15 @@ struct DoubleIntegratorTB {
 	// backup_set_value(x) >= 0 without the last subtraction: an IEEE difference p - q has exactly the sign of the real
 	// p - q and is zero only for p == q (gradual underflow), so ((c - x0^2) - x1^2) >= 0  <=>  (c - x0^2) >= x1^2
 	static constexpr bool HAS_BACKUP_SET_REACHED = true;
-	__device__ static bool backup_set_reached(const double *x)
+	__device__ static double backup_set_level() { return 0.01 * 0.01; }
+	// level = backup_set_level(), or -inf for a lane that must never report a hit (then the test is false by itself)
+	__device__ static bool backup_set_reached(const double *x, const double level)
 	{
-		double h = 0.01 * 0.01;
+		double h = level;
 		h -= x[0] * x[0];
 		return h >= x[1] * x[1];
 	}
+	__device__ static bool backup_set_reached(const double *x) { return backup_set_reached(x, backup_set_level()); }
 	__device__ static void backup_set(const double *x, double &h, double *Dh, double *DDh)
 	{
 		h = backup_set_value(x);
@@ -223,6 +226,8 @@ struct SegwayTB {
 	}
 	static constexpr bool HAS_BACKUP_SET_REACHED = false;
 	__device__ static bool backup_set_reached(const double *x) { return backup_set_value(x) >= 0.0; }
+	__device__ static double backup_set_level() { return 0.0; }
+	__device__ static bool backup_set_reached(const double *x, const double) { return backup_set_reached(x); }
 	__device__ static void backup_set(const double *xin, double &h, double *Dh, double *DDh)
 	{
 		h = backup_set_value(xin);

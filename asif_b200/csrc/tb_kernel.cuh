@@ -235,6 +235,8 @@ __device__ __forceinline__ int32_t tb_filter_one(const TbParams &p, const double
 	double hBackupEnd = 0.0;
 	const int N = p.npBT;
 	bool active = !inside; // still selecting critical points and looking for the first hit
+	if (inside) key[CAP - 1] = -INFINITY; // trivial rows: the list is never read
+	double bs_level = active ? M::backup_set_level() : -INFINITY;
 	// Two nested loops: the inner one is the per-step instruction stream and leaves as soon as ANY lane of the
 	// warp hits the backup set; the hit bookkeeping (once per state) lives between the loops, so it costs
 	// nothing per step.  (A plain `if (hit_now) {...}` in the step body is if-converted by ptxas into ~11
@@ -263,7 +265,7 @@ __device__ __forceinline__ int32_t tb_filter_one(const TbParams &p, const double
 #pragma unroll
 			for (int j = 1; j < NPSS; j++) hmin = (hs[j] < hmin) ? hs[j] : hmin;
 		}
-		if (active && hmin < key[CAP - 1]) {
+		if (hmin < key[CAP - 1]) { // lanes that are no longer selecting hold key[CAP-1] = -inf
 			// evict the largest key, insert (hmin, i) keeping ascending order; ties keep the earlier index first
 			const int slot = R.kslot[CAP - 1];
 #pragma unroll
@@ -286,7 +288,8 @@ __device__ __forceinline__ int32_t tb_filter_one(const TbParams &p, const double
 			}
 			nkept = nkept < CAP ? nkept + 1 : CAP;
 		}
-		hit_now = active && M::backup_set_reached(X);
+		// models with a level form fold `active` into the level (-inf once the lane stopped looking: never reached)
+		hit_now = M::HAS_BACKUP_SET_REACHED ? M::backup_set_reached(X, bs_level) : (active && M::backup_set_reached(X));
 		if (__any_sync(0xffffffffu, hit_now)) {
 			i++;
 			break;
@@ -295,6 +298,8 @@ __device__ __forceinline__ int32_t tb_filter_one(const TbParams &p, const double
 		if (hit_now) { // i was already advanced past the hit point
 			hit = true;
 			active = false;
+			key[CAP - 1] = -INFINITY; // freezes the selection (:507,539): no later point can enter the list
+			bs_level = -INFINITY;
 			idxHit = i - 1;
 #pragma unroll
 			for (int e = 0; e < NS; e++) snap[(CAP * NS + e) * T] = X[e];
