@@ -28,6 +28,53 @@ __device__ __forceinline__ void box_safety_lower(const double *x, const double *
 	hl[3] = (-c1 + hi) - d1;
 }
 
+// sin and cos of one argument for the per-step dynamics of the pendulum and segway models.
+// CUDA's sincos() is accurate but, inlined, materialises each of its ~17 polynomial / reduction constants with two
+// UMOV instructions on every call (~34 issue slots per Euler step in ncu's source view); here the constants sit in
+// constant memory and are read as FMA operands.  Argument reduction: k = rint(x * 2/pi), r = x - k*pi/2 with pi/2
+// split into three doubles (Cody-Waite, FMA); polynomials: the fdlibm kernels (public domain) on [-pi/4, pi/4],
+// evaluated with FMA.  Error <= ~1 ulp for |x| <= 1e5 (k is exact and the three-term reduction holds); beyond
+// that the library routine is used.  These models have no bit parity with the reference anyway (CUDA's sin/cos
+// differ from glibc's in the last bit): their parity is the 1e-9 / 1e-6 tolerance, which this keeps (tests).
+static __constant__ double kSinCosC[18] = {
+    6.36619772367581382433e-01,                                                                   // 2/pi
+    1.57079632679489655800e+00, 6.12323399573676603587e-17, -1.49738490485916983294e-33,          // pi/2 = hi + mid + lo
+    -1.66666666666666324348e-01, 8.33333333332248946124e-03, -1.98412698298579493134e-04,         // S1..S3
+    2.75573137070700676789e-06, -2.50507602534068634195e-08, 1.58969099521155010221e-10,          // S4..S6
+    4.16666666666666019037e-02, -1.38888888888741095749e-03, 2.48015872894767294178e-05,          // C1..C3
+    -2.75573143513906633035e-07, 2.08757232129817482790e-09, -1.13596475577881948265e-11,         // C4..C6
+    1.0e5, 0.0};
+
+__device__ __forceinline__ void sincos_model(const double x, double *sp, double *cp)
+{
+	if (!(fabs(x) <= kSinCosC[16])) { // huge or NaN: the library path (never on a sane trajectory)
+		sincos(x, sp, cp);
+		return;
+	}
+	const int k = __double2int_rn(x * kSinCosC[0]);
+	const double kd = (double)k;
+	double r = fma(-kd, kSinCosC[1], x);
+	r = fma(-kd, kSinCosC[2], r);
+	r = fma(-kd, kSinCosC[3], r);
+	const double z = r * r;
+	double ps = fma(z, kSinCosC[9], kSinCosC[8]);
+	double pc = fma(z, kSinCosC[15], kSinCosC[14]);
+	ps = fma(z, ps, kSinCosC[7]);
+	pc = fma(z, pc, kSinCosC[13]);
+	ps = fma(z, ps, kSinCosC[6]);
+	pc = fma(z, pc, kSinCosC[12]);
+	ps = fma(z, ps, kSinCosC[5]);
+	pc = fma(z, pc, kSinCosC[11]);
+	ps = fma(z, ps, kSinCosC[4]);
+	pc = fma(z, pc, kSinCosC[10]);
+	const double s = fma(r * z, ps, r);          // r + r z (S1 + z (...))
+	const double c = fma(z, fma(z, pc, -0.5), 1.0); // 1 - z/2 + z^2 (C1 + z (...))
+	const double a = (k & 1) ? c : s, b = (k & 1) ? s : c; // odd quadrant: sin <- cos, cos <- sin
+	// quadrants 2,3 negate the sine, quadrants 1,2 the cosine: flip the sign bit with integer logic (one LOP3 each)
+	*sp = __hiloint2double(__double2hiint(a) ^ ((k & 2) << 30), __double2loint(a));
+	*cp = __hiloint2double(__double2hiint(b) ^ (((k + 1) & 2) << 30), __double2loint(b));
+}
+
 // ------------------------------------------------------------------ DoubleIntegrator (explicit)
 // examples/DoubleIntegrator.cpp:12-61
 struct DoubleIntegratorExplicit {
@@ -258,8 +305,8 @@ struct SegwayTB {
 	__device__ static void dynamics_all(const double *x, double *f, double *g, double *Df, double *Dg)
 	{
 		double s1, c1, s2, c2;
-		sincos(x[2], &s1, &c1);
-		sincos(2.0 * x[2], &s2, &c2);
+		sincos_model(x[2], &s1, &c1);
+		sincos_model(2.0 * x[2], &s2, &c2);
 		dynamics_core(x, s1, c1, s2, c2, f, g);
 		gradients_core(x, s1, c1, s2, c2, Df, Dg);
 	}
@@ -455,7 +502,7 @@ struct InvertedPendulumImplicit {
 	__device__ static void dynamics_all(const double *x, double *f, double *g, double *Df, double *Dg)
 	{
 		double s, c;
-		sincos(x[0], &s, &c);
+		sincos_model(x[0], &s, &c);
 		f[0] = x[1];
 		f[1] = s;
 		g[0] = 0.;
