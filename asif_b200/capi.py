@@ -92,6 +92,9 @@ def load_library():
     L.asif_engine_dims.argtypes = [C.c_void_p, _ip]
     L.asif_engine_filter_batch.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                            C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+    L.asif_engine_filter_batch_cost.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+    L.asif_engine_set_input_cost.argtypes = [C.c_void_p, C.c_void_p]
     L.asif_engine_rollout.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_double, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.c_int32, C.c_void_p]
     L.asif_engine_last_qp_iterations.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
@@ -214,6 +217,29 @@ class Engine:
         dptr = _ptr(diag)[0] if diag is not None else None
         _check(load_library().asif_engine_filter_batch(self._h, n, ptrs[0][0], ptrs[1][0], ptrs[2][0], ptrs[3][0],
                                                        ptrs[4][0], dptr, mem, stream))
+
+    def filter_batch_cost(self, x, c, H=None, want_diag=False):
+        """filter(x, H, c, uAct, relax) on a batch: c is (n, nv), H (nu, nu) or None (keep the current input Hessian)."""
+        x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1, self.nx)
+        c = np.ascontiguousarray(c, dtype=np.float64).reshape(-1, self.nv)
+        n = x.shape[0]
+        assert c.shape[0] == n
+        Hp = None
+        if H is not None:
+            Hc = np.asfortranarray(np.asarray(H, dtype=np.float64).reshape(self.nu, self.nu))
+            Hp = Hc.ctypes.data
+        u = np.empty((n, self.nu))
+        relax = np.empty((n, self.n_relax))
+        rc = np.empty(n, dtype=np.int32)
+        diag = np.empty((n, self.n_diag)) if want_diag else None
+        _check(load_library().asif_engine_filter_batch_cost(self._h, n, x.ctypes.data, Hp, c.ctypes.data, u.ctypes.data,
+                                                            relax.ctypes.data, rc.ctypes.data,
+                                                            diag.ctypes.data if want_diag else None, MEM_HOST, None))
+        return (u, relax, rc, diag) if want_diag else (u, relax, rc)
+
+    def set_input_cost(self, H):
+        Hc = np.asfortranarray(np.asarray(H, dtype=np.float64).reshape(self.nu, self.nu))
+        _check(load_library().asif_engine_set_input_cost(self._h, Hc.ctypes.data))
 
     def rollout(self, x0, u_des, steps, dt):
         x = np.array(x0, dtype=np.float64).reshape(-1, self.nx).copy()

@@ -51,7 +51,7 @@ int ensure_slot(asif_engine *e, Slot &s, int64_t n, bool want_diag)
 		s.rc = nullptr;
 		s.cap = 0;
 		CUDA_TRY(cudaMalloc(&s.x, sizeof(double) * n * e->nx));
-		CUDA_TRY(cudaMalloc(&s.ud, sizeof(double) * n * e->nu));
+		CUDA_TRY(cudaMalloc(&s.ud, sizeof(double) * n * e->nv)); // uDes[n][nu] or, for the (H, c) overloads, c[n][nv]
 		CUDA_TRY(cudaMalloc(&s.ua, sizeof(double) * n * e->nu));
 		CUDA_TRY(cudaMalloc(&s.relax, sizeof(double) * n * e->n_relax));
 		CUDA_TRY(cudaMalloc(&s.rc, sizeof(int32_t) * n));
@@ -683,8 +683,20 @@ int32_t asif_engine_dims(const asif_engine *e, int32_t dims[6])
 	return ASIF_OK;
 }
 
-int32_t asif_engine_filter_batch(asif_engine *e, int64_t n, const double *x, const double *u_des, double *u_act,
-                                 double *relax, int32_t *rc, double *diag, int32_t mem, void *stream)
+} // extern "C"
+
+namespace {
+// switches the kernels of this engine between updateCost(uDes) and the caller's linear cost (filter(x, H, c, ...))
+void set_custom_cost(asif_engine *e, int on)
+{
+	e->tb.custom_cost = on;
+	e->im.custom_cost = on;
+	e->ex.custom_cost = on;
+}
+
+// filter_batch proper; cw = doubles per state of the cost argument (nu for uDes, nv for c)
+int32_t filter_batch_impl(asif_engine *e, int64_t n, const double *x, const double *u_des, const int cw, double *u_act,
+                          double *relax, int32_t *rc, double *diag, int32_t mem, void *stream)
 {
 	if (!e) return fail(ASIF_ERR_INVALID_ARGUMENT, "engine is NULL");
 	if (n < 0) return fail(ASIF_ERR_INVALID_ARGUMENT, "n < 0");
@@ -713,7 +725,7 @@ int32_t asif_engine_filter_batch(asif_engine *e, int64_t n, const double *x, con
 		int r = ensure_slot(e, s, chunk, diag != nullptr);
 		if (r) return r;
 		CUDA_TRY(cudaMemcpyAsync(s.x, x + off * nx, sizeof(double) * m * nx, cudaMemcpyHostToDevice, s.stream));
-		CUDA_TRY(cudaMemcpyAsync(s.ud, u_des + off * nu, sizeof(double) * m * nu, cudaMemcpyHostToDevice, s.stream));
+		CUDA_TRY(cudaMemcpyAsync(s.ud, u_des + off * cw, sizeof(double) * m * cw, cudaMemcpyHostToDevice, s.stream));
 		r = launch_filter(e, m, s.x, s.ud, s.ua, s.relax, s.rc, diag ? s.diag : nullptr, s.stream);
 		if (r) return r;
 		CUDA_TRY(cudaMemcpyAsync(u_act + off * nu, s.ua, sizeof(double) * m * nu, cudaMemcpyDeviceToHost, s.stream));
@@ -724,6 +736,52 @@ int32_t asif_engine_filter_batch(asif_engine *e, int64_t n, const double *x, con
 	for (Slot &s : e->slot)
 		if (s.stream) CUDA_TRY(cudaStreamSynchronize(s.stream));
 	return ASIF_OK;
+}
+} // namespace
+
+extern "C" {
+
+int32_t asif_engine_filter_batch(asif_engine *e, int64_t n, const double *x, const double *u_des, double *u_act,
+                                 double *relax, int32_t *rc, double *diag, int32_t mem, void *stream)
+{
+	if (!e) return fail(ASIF_ERR_INVALID_ARGUMENT, "engine is NULL");
+	set_custom_cost(e, 0);
+	return filter_batch_impl(e, n, x, u_des, e->nu, u_act, relax, rc, diag, mem, stream);
+}
+
+int32_t asif_engine_set_input_cost(asif_engine *e, const double *H)
+{
+	if (!e || !H) return fail(ASIF_ERR_INVALID_ARGUMENT, "NULL argument");
+	const int nu = e->nu;
+	for (int i = 0; i < nu; i++)
+		if (!(H[i + i * nu] > 0.0)) return fail(ASIF_ERR_INVALID_ARGUMENT, "H[%d][%d] must be > 0", i, i);
+	// updateH (src/asif_implicit_tb.cpp:748-762): the nu x nu block of H_; with diagonalCost = true (the constructors'
+	// default, the only mode built here) the QP wrapper reads its diagonal only (src/qpwrapper_osqp.cpp:267-283)
+	double *gis[] = {e->tb.gi, e->im.gi, e->ex.gi, e->rb.gi, e->rz.gi};
+	double *gihs[] = {e->tb.gih, e->im.gih, e->ex.gih, e->rb.gih, e->rz.gih};
+	for (int t = 0; t < 5; t++)
+		for (int i = 0; i < nu; i++) {
+			gis[t][i] = 1.0 / (2.0 * H[i + i * nu]);
+			gihs[t][i] = sqrt(gis[t][i]);
+		}
+	return ASIF_OK;
+}
+
+int32_t asif_engine_filter_batch_cost(asif_engine *e, int64_t n, const double *x, const double *H, const double *c,
+                                      double *u_act, double *relax, int32_t *rc, double *diag, int32_t mem, void *stream)
+{
+	if (!e) return fail(ASIF_ERR_INVALID_ARGUMENT, "engine is NULL");
+	if (e->cfg.filter == ASIF_FILTER_ROBUST || e->cfg.filter == ASIF_FILTER_REALIZABLE)
+		return fail(ASIF_ERR_UNSUPPORTED, "filter(x, H, c, ...) of ASIFrobust / ASIFrealizable takes a cost over the LP-dual multipliers "
+		            "(nv = 402 / 38), which the reduced formulation solved here does not carry");
+	if (H) {
+		const int r = asif_engine_set_input_cost(e, H);
+		if (r) return r;
+	}
+	set_custom_cost(e, 1);
+	const int32_t r = filter_batch_impl(e, n, x, c, e->nv, u_act, relax, rc, diag, mem, stream);
+	set_custom_cost(e, 0);
+	return r;
 }
 
 int32_t asif_engine_rollout(asif_engine *e, int64_t n, int32_t steps, double dt, double *x, const double *u_des,

@@ -65,11 +65,17 @@ explicit_filter_kernel(const ExplicitParams p, const int64_t n, const double *__
 	const int64_t k = (int64_t)blockIdx.x * T + threadIdx.x;
 	const bool live = k < n;
 	const int64_t kk = live ? k : (n - 1);
-	double x[NX], ud[NU];
+	double x[NX], c[NU + 1];
 #pragma unroll
 	for (int i = 0; i < NX; i++) x[i] = x_in[kk * NX + i];
+	if (p.custom_cost) { // filter(x, H, c, ...) (src/asif.cpp:153-174): the caller's c, all nv entries
 #pragma unroll
-	for (int i = 0; i < NU; i++) ud[i] = u_des[kk * NU + i];
+		for (int i = 0; i < NU + 1; i++) c[i] = u_des[kk * (NU + 1) + i];
+	} else { // updateCost(uDes) (src/asif.cpp:314-323) + the relax entry of initialize() (:93-98)
+#pragma unroll
+		for (int i = 0; i < NU; i++) c[i] = -2.0 * u_des[kk * NU + i];
+		c[NU] = -2.0 * p.relaxCost * p.relaxLb;
+	}
 
 	double h[NPSS], Dh[NPSS * NX], f[NX], g[NX * NU];
 	M::safety_set(x, h, Dh);
@@ -146,7 +152,8 @@ explicit_filter_kernel(const ExplicitParams p, const int64_t n, const double *__
 			}
 		}
 		feasible = feasible && (rlo * ahi >= rhi * alo);
-		double u = ud[0];
+		// unconstrained minimiser of H00 u^2 + c0 u; with the default cost (H00 = 1, c0 = -2 uDes) this is uDes bit for bit
+		double u = -(p.gi[0] * c[0]);
 		if (u * alo < rlo) {
 			u = rlo / alo;
 			iters = row_lo ? 1 : 0;
@@ -162,15 +169,12 @@ explicit_filter_kernel(const ExplicitParams p, const int64_t n, const double *__
 		R.rows = rows;
 		R.stride = T;
 		R.nc = ncUse;
-		double c[NV];
 		DiagMetric<NV> mt;
 #pragma unroll
 		for (int i = 0; i < NU; i++) {
-			c[i] = -2.0 * ud[i];
 			R.lb[i] = p.lb[i];
 			R.ub[i] = p.ub[i];
 		}
-		c[NU] = -2.0 * p.relaxCost * p.relaxLb;
 		R.lb[NU] = p.relaxLb; // both bounds pinned (src/asif.cpp:88-91)
 		R.ub[NU] = p.relaxLb;
 #pragma unroll

@@ -57,7 +57,9 @@ struct TbParams {
 	int32_t npBT; // trajectory points (npBT-1 Euler steps)
 	int32_t sat_mode;
 	int32_t npBTSS; // critical trajectory points (read by the run-time-count instantiations only)
-	int32_t pad_;
+	// filter(x, H, c, ...) overloads (src/asif_implicit_tb.cpp:252-259): != 0 means the u_des argument of the kernel
+	// holds the caller's linear cost c[n][nv] instead of uDes[n][nu] (H enters through gi / gih)
+	int32_t custom_cost;
 	const double *t_of_index; // device: t_0 = 0, t_i = t_{i-1} + dt (src/asif_implicit_tb.cpp:465,475)
 	SoftSat sat;
 	// QP metric: gi = 1/(2 H_ii), gih = sqrt(gi) for v = (u, relax)
@@ -70,7 +72,7 @@ struct ExplicitParams {
 	double relaxLb, relaxCost;
 	double gi[MAX_NV], gih[MAX_NV];
 	int32_t npSSmax; // rows kept (min(npSSmax, npSS), src/asif.cpp:21-22)
-	int32_t pad_;
+	int32_t custom_cost; // filter(x, H, c, ...) (src/asif.cpp:153-174): u_des holds c[n][nv]
 };
 
 // src/asif_implicit_tb.cpp:821-830

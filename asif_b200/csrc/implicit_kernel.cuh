@@ -80,7 +80,7 @@ struct ImplicitParams {
 	int32_t npBT;
 	int32_t sat_mode;
 	int32_t npBTSS; // critical trajectory points (read by the run-time-count instantiation only)
-	int32_t pad_;
+	int32_t custom_cost; // filter(x, H, c, ...) (src/asif_implicit.cpp:296-303): u_des holds c[n][nv]
 	SoftSat sat;
 	double gi[MAX_NV], gih[MAX_NV];
 	// ASIFimplicitRB only (include/asif_implicit_robust.h:22-38)
@@ -230,11 +230,18 @@ implicit_filter_kernel(const ImplicitParams p, const int64_t n, const double *__
 	const int64_t k = (int64_t)blockIdx.x * T + threadIdx.x;
 	const bool live = k < n;
 	const int64_t kk = live ? k : (n - 1);
-	double x0[NX], ud[NU];
+	double x0[NX], c[NU + 2];
 #pragma unroll
 	for (int i = 0; i < NX; i++) x0[i] = x_in[kk * NX + i];
+	if (p.custom_cost) { // the caller's c, all nv entries
 #pragma unroll
-	for (int i = 0; i < NU; i++) ud[i] = u_des[kk * NU + i];
+		for (int i = 0; i < NU + 2; i++) c[i] = u_des[kk * (NU + 2) + i];
+	} else { // updateCost(uDes) + the relax entries of initialize() (:238-254, :653-664)
+#pragma unroll
+		for (int i = 0; i < NU; i++) c[i] = -2.0 * u_des[kk * NU + i];
+		c[NU] = -2.0 * p.relaxCost * p.relaxSafeLb;
+		c[NU + 1] = -2.0 * p.relaxCost * p.relaxReachLb;
+	}
 
 	double hs[NPSS], Dhs[NPSS * NX];
 	M::safety_set(x0, hs, Dhs);
@@ -375,16 +382,13 @@ implicit_filter_kernel(const ImplicitParams p, const int64_t n, const double *__
 		}
 	}
 	// cost, bounds (:238-254), QP, post-solve (:334-353)
-	double c[NV], v[NV];
+	double v[NV];
 	DiagMetric<NV> mt;
 #pragma unroll
 	for (int i = 0; i < NU; i++) {
-		c[i] = -2.0 * ud[i];
 		R.lb[i] = p.lb[i];
 		R.ub[i] = p.ub[i];
 	}
-	c[NU] = -2.0 * p.relaxCost * p.relaxSafeLb;
-	c[NU + 1] = -2.0 * p.relaxCost * p.relaxReachLb;
 	R.lb[NU] = p.relaxSafeLb;
 	R.lb[NU + 1] = p.relaxReachLb;
 	R.ub[NU] = p.inf;

@@ -175,6 +175,22 @@ struct TbRows {
 	}
 };
 
+// Linear cost of one state: updateCost(uDes) plus the relax entry of initialize() (src/asif_implicit_tb.cpp:206-212,
+// 735-746), or the caller's c of the filter(x, H, c, ...) overloads (:252-259) when p.custom_cost is set.
+template <int NU>
+__device__ __forceinline__ void tb_cost_vector(const TbParams &p, const double *__restrict__ u_des, const int64_t kk,
+                                               double (&cin)[NU + 1])
+{
+	if (p.custom_cost) {
+#pragma unroll
+		for (int i = 0; i < NU + 1; i++) cin[i] = u_des[kk * (NU + 1) + i];
+	} else {
+#pragma unroll
+		for (int i = 0; i < NU; i++) cin[i] = -2.0 * u_des[kk * NU + i];
+		cin[NU] = -2.0 * p.relaxCost * p.relaxSafeLb;
+	}
+}
+
 template <int NPBTSS>
 struct TbDiagRec {
 	double TTS, ortho, hSafetyNow, hBackupEnd;
@@ -187,7 +203,7 @@ struct TbDiagRec {
 // by all 32 lanes of a warp together (warp-uniform early exit from the trajectory loop).
 // R is left describing the state's QP rows (the diag writer re-scans them).
 template <class M, int NPBTSS, bool WITH_DIAG, int SATMODE>
-__device__ __forceinline__ int32_t tb_filter_one(const TbParams &p, const double (&x0)[M::NX], const double (&ud)[M::NU],
+__device__ __forceinline__ int32_t tb_filter_one(const TbParams &p, const double (&x0)[M::NX], const double (&cin)[M::NU + 1],
                                                  double *snap, const int T, double (&uo)[M::NU], double &relax,
                                                  int &qp_iters, TbDiagRec<NPBTSS> &dg, TbRows<M, NPBTSS> &R)
 {
@@ -317,18 +333,18 @@ __device__ __forceinline__ int32_t tb_filter_one(const TbParams &p, const double
 	R.neg_inf = -p.inf;
 #pragma unroll
 	for (int i = 0; i < NU; i++) {
-		c[i] = -2.0 * ud[i];
 		R.lb[i] = p.lb[i];
 		R.ub[i] = p.ub[i];
 		R.lgT[i] = 0.0;
 		R.lgO[i] = 0.0;
 	}
 #pragma unroll
+	for (int i = 0; i < NV; i++) c[i] = cin[i]; // linear cost: from uDes (tb_cost_vector) or the caller's c
+#pragma unroll
 	for (int i = 0; i < NX; i++) R.f[i] = 0.0;
 #pragma unroll
 	for (int i = 0; i < NX * NU; i++) R.g[i] = 0.0;
 	R.rhsT = R.rhsO = -p.inf;
-	c[NU] = -2.0 * p.relaxCost * p.relaxSafeLb;
 	R.lb[NU] = p.relaxSafeLb;
 	R.ub[NU] = p.inf;
 #pragma unroll
@@ -512,17 +528,16 @@ __device__ __forceinline__ void tb_filter_tile(const TbParams &p, const int64_t 
 	const bool live = k < n;
 	const int64_t kk = live ? k : (n - 1); // tail lanes redo the last state and do not store
 
-	double x0[NX], ud[NU];
+	double x0[NX], cin[NU + 1];
 #pragma unroll
 	for (int i = 0; i < NX; i++) x0[i] = x_in[kk * NX + i];
-#pragma unroll
-	for (int i = 0; i < NU; i++) ud[i] = u_des[kk * NU + i];
+	tb_cost_vector<NU>(p, u_des, kk, cin);
 
 	double uo[NU], relax;
 	int qp_iters;
 	TbDiagRec<NPBTSS> dg;
 	TbRows<M, NPBTSS> R;
-	const int32_t rc = tb_filter_one<M, NPBTSS, WITH_DIAG, SATMODE>(p, x0, ud, snap, T, uo, relax, qp_iters, dg, R);
+	const int32_t rc = tb_filter_one<M, NPBTSS, WITH_DIAG, SATMODE>(p, x0, cin, snap, T, uo, relax, qp_iters, dg, R);
 
 	if (live) {
 #pragma unroll
@@ -623,14 +638,12 @@ tb_rollout_kernel(const TbParams p, const int64_t n, const int32_t steps, const 
 	}
 	const bool live = k < n;
 	const int64_t kk = live ? k : (n - 1);
-	double x[NX], ud[NU], uo[NU];
+	double x[NX], ud[NU + 1], uo[NU];
 #pragma unroll
 	for (int i = 0; i < NX; i++) x[i] = x_io[kk * NX + i];
+	tb_cost_vector<NU>(p, u_des, kk, ud); // the rollout holds uDes per agent; ud is its cost vector
 #pragma unroll
-	for (int i = 0; i < NU; i++) {
-		ud[i] = u_des[kk * NU + i];
-		uo[i] = 0.0;
-	}
+	for (int i = 0; i < NU; i++) uo[i] = 0.0;
 	int32_t rc = 0;
 	for (int32_t s = 0; s < steps; s++) {
 		double relax;

@@ -172,6 +172,21 @@ namespace ASIF
 				if (engine_ == nullptr) return ASIF_ERR_INVALID_ARGUMENT;
 				return asif_engine_filter_batch(engine_, n, X, UDes, UAct, Relax, rc, diag, ASIF_MEM_HOST, nullptr);
 			}
+			// the filter(x, H, c, uAct, relax) overloads on n states: C[n*nv] is the caller's linear cost of the whole decision
+			// vector, H (nu x nu, column-major) replaces the input block of the Hessian and stays in force (updateH), or nullptr
+			int32_t filterBatch(const int64_t n, const double X[], const double H[], const double C[], double UAct[], double Relax[],
+			                    int32_t rc[], double diag[] = nullptr)
+			{
+				if (engine_ == nullptr) return ASIF_ERR_INVALID_ARGUMENT;
+				return asif_engine_filter_batch_cost(engine_, n, X, H, C, UAct, Relax, rc, diag, ASIF_MEM_HOST, nullptr);
+			}
+			// single state, as every reference class declares it (e.g. include/asif_implicit_tb.h:103-110); relax has nRelax() entries
+			int32_t filter(const double x[], const double H[], const double c[], double uAct[], double relax[])
+			{
+				int32_t rc = 0;
+				const int32_t r = filterBatch(1, x, H, c, uAct, relax, &rc);
+				return r == ASIF_OK ? rc : r;
+			}
 			// same with device pointers on the caller's CUDA stream (cudaStream_t); returns without synchronising
 			int32_t filterBatchDevice(const int64_t n, const double *X, const double *UDes, double *UAct, double *Relax,
 			                          int32_t *rc, void *stream, double *diag = nullptr)
@@ -233,6 +248,7 @@ namespace ASIF
 		class FilterBatchExplicit : public FilterBatchBase
 		{
 		public:
+			using FilterBatchBase::filter; // filter(x, H, c, uAct, relax)
 			typedef struct {
 				double relaxLb = 5.0;
 				double relaxCost = 50.0;
@@ -298,6 +314,7 @@ namespace ASIF
 		class FilterBatchImplicitTB : public FilterBatchBase
 		{
 		public:
+			using FilterBatchBase::filter; // filter(x, H, c, uAct, relax)
 			typedef struct {
 				double relaxCost = 50.0;
 				double relaxSafeLb = 5.0;
@@ -399,6 +416,7 @@ namespace ASIF
 		class FilterBatchImplicit : public FilterBatchBase
 		{
 		public:
+			using FilterBatchBase::filter; // filter(x, H, c, uAct, relax)
 			typedef struct {
 				double relaxCost = 50.0;
 				double relaxReachLb = 5.0;
@@ -485,6 +503,7 @@ namespace ASIF
 		class FilterBatchImplicitRB : public FilterBatchBase
 		{
 		public:
+			using FilterBatchBase::filter; // filter(x, H, c, uAct, relax)
 			typedef struct {
 				double *x0 = nullptr;    // unused on the batched path (the reference uses it for the set-up solve only)
 				double *x_unc = nullptr; // [nx] state uncertainty box; nullptr = zeros, as in the reference (:276-279)
@@ -576,6 +595,7 @@ namespace ASIF
 		class FilterBatchRobust : public FilterBatchBase
 		{
 		public:
+			using FilterBatchBase::filter; // filter(x, H, c, uAct, relax)
 			typedef struct {
 				double relaxLb = 5.0;
 				double relaxCost = 50.0;
@@ -631,6 +651,7 @@ namespace ASIF
 		class FilterBatchRealizable : public FilterBatchBase
 		{
 		public:
+			using FilterBatchBase::filter; // filter(x, H, c, uAct, relax)
 			typedef struct {
 				double relaxDes = 5.0;
 				double relaxOffset = 5.0;

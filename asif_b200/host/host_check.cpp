@@ -109,6 +109,10 @@ int main()
 			if (rb.initialize(lb, ub, ro) != 1) return fail("FilterBatchImplicitRB::initialize");
 			double uRb[1] = {0.0}, relaxRb[2] = {0.0, 0.0};
 			if (rb.filter(x, uDes, uRb, relaxRb) != rc || uRb[0] != uAct[0] || relaxRb[0] != relax[0]) return fail("FilterBatchImplicitRB::filter");
+			// filter(x, H, c, ...) with H = 1 and c = [-2 uDes, -2 relaxCost relaxSafeLb, -2 relaxCost relaxReachLb] is filter(x, uDes, ...)
+			const double Hone[1] = {1.0}, cvec[3] = {-2.0 * uDes[0], -2.0 * 50.0 * 10.0, -2.0 * 50.0 * 5.0};
+			double uC[1] = {0.0}, relaxC[2] = {0.0, 0.0};
+			if (rb.filter(x, Hone, cvec, uC, relaxC) != rc || uC[0] != uAct[0] || relaxC[1] != relax[1]) return fail("FilterBatchImplicitRB::filter(x, H, c)");
 			double unc[2] = {0.05, 0.08};
 			ro.x_unc = unc;
 			ro.backContDt = 0.2;

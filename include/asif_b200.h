@@ -137,6 +137,20 @@ int32_t asif_engine_filter_batch(asif_engine *e, int64_t n, const double *x, con
                                  double *relax, int32_t *rc, double *diag, int32_t mem, void *stream);
 
 /*
+ * The filter(x, H, c, uAct[, relax]) overloads (src/asif_implicit_tb.cpp:252-363, src/asif.cpp:153-210,
+ * src/asif_implicit.cpp:296-356, src/asif_implicit_robust.cpp:384-441): the caller supplies the linear cost c of the
+ * whole decision vector, c[n][nv] per state (the input part AND the relax entries, which updateCost(uDes) would
+ * leave at -2 relaxCost relaxLb), and optionally the nu x nu input block H of the Hessian (column-major, host
+ * memory; NULL keeps the current one).  As in the reference (updateH) a given H stays in force for later calls,
+ * including filter_batch(uDes).  Only the diagonal of H is used: diagonalCost = true, the constructors' default.
+ * Classes: ASIF, ASIFimplicitTB, ASIFimplicit, ASIFimplicitRB.
+ */
+int32_t asif_engine_filter_batch_cost(asif_engine *e, int64_t n, const double *x, const double *H, const double *c,
+                                      double *u_act, double *relax, int32_t *rc, double *diag, int32_t mem, void *stream);
+/* updateH alone (host pointer, nu x nu column-major) */
+int32_t asif_engine_set_input_cost(asif_engine *e, const double *H);
+
+/*
  * Closed-loop rollout as in the example main loops (examples/segway_implicit_tb.cpp:251-283):
  * steps x { filter ; x += dt*(f(x) + g(x) uAct) } with the state resident on the device.
  * x is updated in place; u_des is held per state.  rc_hist[8] (host memory, optional) counts

@@ -51,6 +51,23 @@ static double min_elem(const double *v, int n)
 	return m;
 }
 
+/* The filter(x, H, c, ...) overloads (src/asif_implicit_tb.cpp:252-363, src/asif.cpp:153-210, src/asif_implicit.cpp:296-356):
+ * updateH copies the caller's nu x nu block into H_ (:748-762) and the caller's c replaces c_ entirely.  The batch
+ * entry below sets this per state; the filters apply it right before the solve. */
+static struct {
+	const double *H; /* nu x nu column-major or NULL */
+	const double *c; /* nv entries or NULL */
+} g_cost;
+
+static void apply_cost_override(int nv, int nu, double *H, double *c)
+{
+	if (g_cost.H)
+		for (int j = 0; j < nu; j++)
+			for (int i = 0; i < nu; i++) H[i + j * nv] = g_cost.H[i + j * nu];
+	if (g_cost.c)
+		for (int i = 0; i < nv; i++) c[i] = g_cost.c[i];
+}
+
 /* src/asif_implicit_tb.cpp:821-830 (same in every class) */
 static void input_saturate(const oracle_model *md, double *u)
 {
@@ -458,6 +475,7 @@ static int32_t tb_filter(const oracle_model *md, const tb_options *o, int N, con
 		for (int i = 0; i < npTC; i++) b[i] = -o->inf;
 		dg.TTS = 0.0;
 		dg.BTorthoBS = 1.0;
+		apply_cost_override(nv, nu, H, c);
 		int st = oracle_qp_solve(nv, npTC, 1, H, c, A, b, lb, ub, 0, sol);
 		if (st == 1) {
 			memcpy(uAct, sol, sizeof(double) * nu);
@@ -474,6 +492,7 @@ static int32_t tb_filter(const oracle_model *md, const tb_options *o, int N, con
 		if (tb_update_constraints(md, o, N, x, A, b, &dg, xe) == 1) {
 			md->backup_set(xe, hb, Dhb, DDhb);
 			dg.hBackupEnd = hb[0];
+			apply_cost_override(nv, nu, H, c);
 			int st = oracle_qp_solve(nv, npTC, 1, H, c, A, b, lb, ub, 0, sol);
 			if (st == 1) {
 				memcpy(uAct, sol, sizeof(double) * nu);
@@ -547,6 +566,7 @@ static int32_t explicit_filter(const oracle_model *md, double relaxLb, double re
 	c[nu] = -2.0 * relaxCost * relaxLb;
 	lb[nu] = relaxLb; /* :88-91 both bounds pinned to relaxLb */
 	ub[nu] = relaxLb;
+	apply_cost_override(nv, nu, H, c);
 	int st = oracle_qp_solve(nv, nc, 1, H, c, A, b, lb, ub, 0, sol);
 	if (diag) {
 		memcpy(diag, A, sizeof(double) * nc * nv);
@@ -713,6 +733,7 @@ static int32_t implicit_filter(const oracle_model *md, const imp_options *o, int
 	lb[nv - 1] = o->relaxReachLb;
 	ub[nv - 2] = o->inf;
 	ub[nv - 1] = o->inf;
+	apply_cost_override(nv, nu, H, c);
 	int st = oracle_qp_solve(nv, npTC, 1, H, c, A, b, lb, ub, 0, sol);
 	int32_t rc;
 	if (st == 1) {
@@ -962,6 +983,26 @@ int oracle_filter_batch(int cfg, const double *opts, int n_opts, int64_t n, cons
 		double r[2] = {0.0, 0.0};
 		for (int j = 0; j < c.nu; j++) u_act[k * c.nu + j] = 0.0;
 		rc[k] = filter_one(&c, x + k * c.nx, u_des + k * c.nu, u_act + k * c.nu, r, diag ? diag + k * c.n_diag : 0);
+		for (int j = 0; j < c.n_relax; j++) relax[k * c.n_relax + j] = r[j];
+	}
+	return 0;
+}
+
+int oracle_filter_batch_cost(int cfg, const double *opts, int n_opts, int64_t n, const double *x, const double *H,
+                             const double *cvec, double *u_act, double *relax, int32_t *rc, double *diag)
+{
+	ctx_t c;
+	if (make_ctx(cfg, opts, n_opts, &c)) return -1;
+	if (cfg == ORACLE_CFG_IP_ROBUST || cfg == ORACLE_CFG_IP_REALIZABLE) return -2; /* reduced formulations: no LP-dual cost */
+	double ud0[NU] = {0.0};
+	for (int64_t k = 0; k < n; k++) {
+		double r[2] = {0.0, 0.0};
+		for (int j = 0; j < c.nu; j++) u_act[k * c.nu + j] = 0.0;
+		g_cost.H = H;
+		g_cost.c = cvec + k * c.nv;
+		rc[k] = filter_one(&c, x + k * c.nx, ud0, u_act + k * c.nu, r, diag ? diag + k * c.n_diag : 0);
+		g_cost.H = 0;
+		g_cost.c = 0;
 		for (int j = 0; j < c.n_relax; j++) relax[k * c.n_relax + j] = r[j];
 	}
 	return 0;

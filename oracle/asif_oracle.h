@@ -70,6 +70,10 @@ int oracle_dims(int cfg, const double *opts, int n_opts, int32_t *dims);
 /* one call = the reference's filter(x, uDes, uAct, relax) on each of the n states, stateless */
 int oracle_filter_batch(int cfg, const double *opts, int n_opts, int64_t n, const double *x, const double *u_des,
                         double *u_act, double *relax, int32_t *rc, double *diag);
+/* the filter(x, H, c, uAct, relax) overloads on each of the n states: H nu x nu column-major (or NULL = identity
+ * block), cvec[n*nv].  Classes ASIF, ASIFimplicitTB, ASIFimplicit, ASIFimplicitRB. */
+int oracle_filter_batch_cost(int cfg, const double *opts, int n_opts, int64_t n, const double *x, const double *H,
+                             const double *cvec, double *u_act, double *relax, int32_t *rc, double *diag);
 /* learned residual of the implicit classes (cfg 3, 7, 8), include/asif_learning_utils.h: process-wide switch, NULL = off.
  * dims[8] / blob as ref_set_learning (oracle/ref_build/ref_api.h) */
 int oracle_set_learning(const uint32_t *dims, const double *blob);

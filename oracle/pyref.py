@@ -84,6 +84,24 @@ class RefFilter:
         assert r == 0
         return (u, relax, rc, diag) if want_diag else (u, relax, rc)
 
+    def filter_batch_cost(self, x, c, H=None):
+        """The reference's filter(x, H, c, uAct, relax) per state -> (u, relax, rc, diag, qp_status)."""
+        L = self.lib.lib
+        L.ref_filter_batch_cost.argtypes = [C.c_void_p, C.c_int64, _dp, _dp, _dp, _dp, _dp, _ip, _dp, _ip]
+        x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1, self.nx)
+        c = np.ascontiguousarray(c, dtype=np.float64).reshape(-1, self.nv)
+        Hf = None if H is None else np.asfortranarray(np.asarray(H, dtype=np.float64).reshape(self.nu, self.nu))
+        n = x.shape[0]
+        u = np.zeros((n, self.nu))
+        relax = np.zeros((n, self.n_relax))
+        rc = np.zeros(n, dtype=np.int32)
+        diag = np.zeros((n, self.n_diag))
+        st = np.zeros(n, dtype=np.int32)
+        r = L.ref_filter_batch_cost(self.h, n, _d(x), None if Hf is None else Hf.ctypes.data_as(_dp), _d(c), _d(u), _d(relax),
+                                    rc.ctypes.data_as(_ip), _d(diag), st.ctypes.data_as(_ip))
+        assert r == 0
+        return u, relax, rc, diag, st
+
     def filter_batch_ex(self, x, u_des):
         """(u, relax, rc, diag, raw OSQP status, ADMM iterations) - single-threaded use only."""
         x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1, self.nx)
@@ -168,6 +186,25 @@ class OracleLib:
         diag = np.zeros((n, n_diag)) if want_diag else None
         r = self.lib.oracle_filter_batch(cfg, _d(o), 0 if o is None else o.size, n, _d(x), _d(u_des), _d(u), _d(relax),
                                          rc.ctypes.data_as(_ip), _d(diag))
+        assert r == 0
+        return (u, relax, rc, diag) if want_diag else (u, relax, rc)
+
+    def filter_batch_cost(self, cfg, x, c, H=None, opts=None, want_diag=False):
+        """filter(x, H, c, uAct, relax) per state: c (n, nv), H (nu, nu) or None."""
+        self.lib.oracle_filter_batch_cost.argtypes = [C.c_int, _dp, C.c_int, C.c_int64, _dp, _dp, _dp, _dp, _dp, _ip, _dp]
+        o = None if opts is None else np.ascontiguousarray(opts, dtype=np.float64)
+        nx, nu, n_relax, nc, nv, n_diag = self.dims(cfg, opts)
+        x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1, nx)
+        c = np.ascontiguousarray(c, dtype=np.float64).reshape(-1, nv)
+        Hf = None if H is None else np.asfortranarray(np.asarray(H, dtype=np.float64).reshape(nu, nu))
+        n = x.shape[0]
+        u = np.zeros((n, nu))
+        relax = np.zeros((n, n_relax))
+        rc = np.zeros(n, dtype=np.int32)
+        diag = np.zeros((n, n_diag)) if want_diag else None
+        r = self.lib.oracle_filter_batch_cost(cfg, _d(o), 0 if o is None else o.size, n, _d(x),
+                                              None if Hf is None else Hf.ctypes.data_as(_dp), _d(c), _d(u), _d(relax),
+                                              rc.ctypes.data_as(_ip), _d(diag))
         assert r == 0
         return (u, relax, rc, diag) if want_diag else (u, relax, rc)
 

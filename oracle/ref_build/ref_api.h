@@ -50,6 +50,10 @@ int ref_filter_batch(void *h, int64_t n, const double *x, const double *u_des,
  * for calls that solve no QP the values are those of the previous solve) */
 int ref_filter_batch_ex(void *h, int64_t n, const double *x, const double *u_des, double *u_act, double *relax,
                         int32_t *rc, double *diag, int32_t *qp_status, int32_t *qp_iters);
+/* the classes' filter(x, H, c, uAct, relax) overloads per state (cfg 1, 2, 3, 6, 7, 8): H nu x nu column-major or NULL
+ * (the class then keeps its current H_), c[n*nv]; qp_status as ref_filter_batch_ex */
+int ref_filter_batch_cost(void *h, int64_t n, const double *x, const double *H, const double *c, double *u_act, double *relax,
+                          int32_t *rc, double *diag, int32_t *qp_status);
 /* closed-loop rollout exactly as the example main loops do (x += dt*(f+g*uAct)); x is updated in place */
 int ref_rollout(void *h, int64_t n, int32_t steps, double dt, double *x, const double *u_des,
                 double *u_act_last, int32_t *rc_last, int64_t *rc_hist /* [8] or NULL */);

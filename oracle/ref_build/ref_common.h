@@ -6,6 +6,8 @@
 
 struct RefFilter {
 	int nx, nu, n_relax, nc, nv, n_diag;
+	/* when costC is set, filter() calls the class's filter(x, H, c, uAct, relax) overload with these instead of uDes */
+	const double *costH = 0, *costC = 0;
 	virtual ~RefFilter() {}
 	/* one reference filter() call; diag may be NULL */
 	virtual int32_t filter(const double *x, const double *u_des, double *u_act, double *relax, double *diag) = 0;

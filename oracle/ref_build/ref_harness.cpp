@@ -82,6 +82,29 @@ int ref_filter_batch_ex(void *h, int64_t n, const double *x, const double *u_des
 	return 0;
 }
 
+int ref_filter_batch_cost(void *h, int64_t n, const double *x, const double *H, const double *c, double *u_act, double *relax,
+                          int32_t *rc, double *diag, int32_t *qp_status)
+{
+	RefFilter *f = (RefFilter *)h;
+	if (!f) return -1;
+	std::vector<double> ud0(f->nu, 0.0);
+	for (int64_t k = 0; k < n; k++) {
+		double r[2] = {0.0, 0.0};
+		const long long inexact0 = osqp_shim_inexact_count();
+		f->costH = H;
+		f->costC = c + k * f->nv;
+		rc[k] = f->filter(x + k * f->nx, ud0.data(), u_act + k * f->nu, r, diag ? diag + k * f->n_diag : 0);
+		f->costH = 0;
+		f->costC = 0;
+		for (int j = 0; j < f->n_relax; j++) relax[k * f->n_relax + j] = r[j];
+		int it = 0;
+		int st = osqp_shim_last_status(&it);
+		if (osqp_shim_inexact_count() != inexact0 && st != -2 && st != 2 && st != 3 && st != 4) st = -2;
+		if (qp_status) qp_status[k] = st;
+	}
+	return 0;
+}
+
 int ref_rollout(void *h, int64_t n, int32_t steps, double dt, double *x, const double *u_des,
                 double *u_act_last, int32_t *rc_last, int64_t *rc_hist)
 {

@@ -36,7 +36,7 @@ struct DiExplicit : RefFilter {
 	}
 	int32_t filter(const double *x, const double *u_des, double *u_act, double *relax, double *diag) override
 	{
-		int32_t rc = f.filter(x, u_des, u_act, relax[0]);
+		int32_t rc = costC ? f.filter(x, costH, costC, u_act, relax[0]) : f.filter(x, u_des, u_act, relax[0]);
 		if (diag) {
 			memcpy(diag, f.A(), sizeof(double) * nc * nv);
 			memcpy(diag + nc * nv, f.b(), sizeof(double) * nc);
@@ -125,7 +125,7 @@ struct DiTb : RefFilter {
 	}
 	int32_t filter(const double *x, const double *u_des, double *u_act, double *relax, double *diag) override
 	{
-		int32_t rc = f.filter(x, u_des, u_act, relax[0]);
+		int32_t rc = costC ? f.filter(x, costH, costC, u_act, relax[0]) : f.filter(x, u_des, u_act, relax[0]);
 		if (diag) ref_tb_fill_diag(f, f.A(), f.b(), npBTSS, nc, nv, diag);
 		return rc;
 	}
@@ -227,7 +227,7 @@ struct DiImplicitRB : RefFilter {
 	int32_t filter(const double *x, const double *u_des, double *u_act, double *relax, double *diag) override
 	{
 		AAF::set_default(0);
-		int32_t rc = f.filter(x, u_des, u_act, relax);
+		int32_t rc = costC ? f.filter(x, costH, costC, u_act, relax) : f.filter(x, u_des, u_act, relax);
 		if (diag) {
 			double h[1], Dh[2];
 			diag[0] = f.hSafetyNow_;

@@ -64,7 +64,7 @@ struct IpImplicit : RefFilter {
 	}
 	int32_t filter(const double *x, const double *u_des, double *u_act, double *relax, double *diag) override
 	{
-		int32_t rc = f.filter(x, u_des, u_act, relax);
+		int32_t rc = costC ? f.filter(x, costH, costC, u_act, relax) : f.filter(x, u_des, u_act, relax);
 		if (diag) {
 			double h[1], Dh[2];
 			diag[0] = f.hSafetyNow_;
@@ -172,7 +172,7 @@ struct IpImplicitRB : RefFilter {
 	int32_t filter(const double *x, const double *u_des, double *u_act, double *relax, double *diag) override
 	{
 		AAF::set_default(0); /* libaffa's global noise-symbol counter (F12) */
-		int32_t rc = f.filter(x, u_des, u_act, relax);
+		int32_t rc = costC ? f.filter(x, costH, costC, u_act, relax) : f.filter(x, u_des, u_act, relax);
 		if (diag) {
 			double h[1], Dh[2];
 			diag[0] = f.hSafetyNow_;

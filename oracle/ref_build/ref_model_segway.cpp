@@ -56,7 +56,7 @@ struct SegwayTb : RefFilter {
 	~SegwayTb() { delete f; }
 	int32_t filter(const double *x, const double *u_des, double *u_act, double *relax, double *diag) override
 	{
-		int32_t rc = f->filter(x, u_des, u_act, relax[0]);
+		int32_t rc = costC ? f->filter(x, costH, costC, u_act, relax[0]) : f->filter(x, u_des, u_act, relax[0]);
 		if (diag) ref_tb_fill_diag(*f, f->A(), f->b(), npBTSS, nc, nv, diag);
 		return rc;
 	}

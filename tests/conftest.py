@@ -196,3 +196,13 @@ LEARN_DIMS = [6, 5, 16, 12, 8, 10, 2, 1]
 def learning_blob(dims=LEARN_DIMS, seed=7, scale=0.3):
     from oracle import pyref
     return pyref.learning_blob(dims, seed=seed, scale=scale)
+
+
+# ---- filter(x, H, c, uAct, relax) overloads: a caller-supplied input Hessian block and full linear cost ------------
+def custom_cost(ud, nv, seed, relax_c=(-2 * 50 * 7.0, -2 * 50 * 4.0), h00=2.5):
+    """H = [h00]; c = [-2 h00 uDes * U(0.5,1.5), relax entries * U(0.8,1.2)] per state."""
+    g = philox(seed)
+    n = ud.shape[0]
+    c = np.concatenate([-2 * h00 * ud * g.uniform(0.5, 1.5, (n, 1)),
+                        np.tile(np.asarray(relax_c[:nv - 1]), (n, 1)) * g.uniform(0.8, 1.2, (n, nv - 1))], axis=1)
+    return np.array([[h00]]), np.ascontiguousarray(c)

@@ -116,3 +116,53 @@ def test_critical_point_count_limits(ab):
         ab.Engine(ab.FILTER_IMPLICIT_TB, ab.MODEL_DOUBLE_INTEGRATOR_TB, npBTSS=9)
     with pytest.raises(ab.AsifError):
         ab.Engine(ab.FILTER_IMPLICIT, ab.MODEL_INVERTED_PENDULUM, npBTSS=17)
+
+
+@pytest.mark.parametrize("cfg,filt,model,opts,gen,kw", [
+    (1, "FILTER_EXPLICIT", "MODEL_DOUBLE_INTEGRATOR", cf.C1_OPTS, cf.c1_inputs, lambda o: dict(relaxLb=o[0], relaxCost=o[1])),
+    (2, "FILTER_IMPLICIT_TB", "MODEL_DOUBLE_INTEGRATOR_TB", cf.C2_TB_OPTS, cf.c2_inputs, cf.tb_engine_kwargs),
+    (3, "FILTER_IMPLICIT", "MODEL_INVERTED_PENDULUM", cf.C3A_SHORT_OPTS, cf.c3a_inputs, cf.implicit_engine_kwargs),
+    (7, "FILTER_IMPLICIT_RB", "MODEL_INVERTED_PENDULUM", cf.RB_IP_OPTS, cf.c3a_inputs, cf.rb_engine_kwargs),
+    (6, "FILTER_IMPLICIT_TB", "MODEL_SEGWAY", cf.SEGWAY_TB_OPTS, cf.c5_inputs, cf.tb_engine_kwargs),
+])
+def test_custom_cost(oracle, cfg, filt, model, opts, gen, kw):
+    """asif_engine_filter_batch_cost = the filter(x, H, c, uAct, relax) overloads, against the oracle; H stays in force
+    for later uDes calls (updateH), and H = I with the default c reproduces filter(x, uDes) bit for bit."""
+    import asif_b200 as ab
+    n = 20_000 if cfg != 6 else 4000
+    x, ud = gen(n, seed=cf.SEED + 700 + cfg)
+    eng = ab.Engine(getattr(ab, filt), getattr(ab, model), **kw(opts))
+    base = eng.filter_batch(x, ud, want_diag=True)
+    H, c = cf.custom_cost(ud, eng.nv, seed=cfg)
+    u, relax, rc, diag = eng.filter_batch_cost(x, c, H, want_diag=True)
+    u0, relax0, rc0, diag0 = oracle.filter_batch_cost(cfg, x, c, H, opts, want_diag=True)
+    flips = np.nonzero(rc != rc0)[0]
+    print("custom cost cfg", cfg, "rc", dict(zip(*np.unique(rc0, return_counts=True))), "flips", flips.size)
+    assert flips.size <= (0 if cfg in (1, 2) else max(2, n // 2000))
+    keep = rc == rc0
+    cf.assert_parity("custom cost", (u[keep], relax[keep], rc[keep]), (u0[keep], relax0[keep], rc0[keep]))
+    if cfg in (1, 2):
+        assert np.array_equal(diag, diag0)
+    # sticky H: filter(x, uDes) now minimises 2.5 (u - uDes)^2 + ..., i.e. c = [-2 uDes, defaults] with H = 2.5
+    u1, relax1, rc1 = eng.filter_batch(x, ud)
+    relax_defaults = {1: [-2 * opts[1] * opts[0]], 2: [-2 * opts[0] * opts[1]], 6: [-2 * opts[0] * opts[1]],
+                      3: [-2 * opts[0] * opts[2], -2 * opts[0] * opts[1]], 7: [-2 * opts[0] * opts[2], -2 * opts[0] * opts[1]]}[cfg]
+    cdef = np.concatenate([-2.0 * ud, np.tile(relax_defaults, (n, 1))], axis=1)
+    u2, relax2, rc2 = eng.filter_batch_cost(x, cdef, None)
+    assert np.array_equal(rc1, rc2) and np.array_equal(u1, u2) and np.array_equal(relax1, relax2)
+    # back to the identity block: the very first results return
+    eng.set_input_cost(np.eye(1))
+    again = eng.filter_batch(x, ud, want_diag=True)
+    for p, q in zip(base, again):
+        assert np.array_equal(p, q)
+    u3, relax3, rc3 = eng.filter_batch_cost(x, cdef, np.eye(1))
+    assert np.array_equal(base[2], rc3) and np.array_equal(base[0], u3) and np.array_equal(base[1], relax3)
+
+
+def test_custom_cost_refused_for_lp_dual_classes():
+    import asif_b200 as ab
+    o = cf.C3B_OPTS
+    eng = ab.Engine(ab.FILTER_ROBUST, ab.MODEL_INVERTED_PENDULUM_TABLE, relaxLb=o[0], relaxCost=o[1], dynParam=[o[2], o[3]],
+                    halfplanes=cf.halfplane_table())
+    with pytest.raises(ab.AsifError):
+        eng.filter_batch_cost(np.zeros((4, 2)), np.zeros((4, 2)), None)
