@@ -141,12 +141,19 @@ def test_custom_cost(oracle, cfg, filt, model, opts, gen, kw):
     assert flips.size <= (0 if cfg in (1, 2) else max(2, n // 2000))
     keep = rc == rc0
     cf.assert_parity("custom cost", (u[keep], relax[keep], rc[keep]), (u0[keep], relax0[keep], rc0[keep]))
-    if cfg in (1, 2):
+    if cfg == 1:
         assert np.array_equal(diag, diag0)
+    if cfg == 2:  # rows of the states that build rows (rc 1); column 3 is hBackupEnd, which the kernel leaves unset without a hit
+        m = rc0 == 1
+        assert np.array_equal(diag[m][:, :3], diag0[m][:, :3]) and np.array_equal(diag[m][:, 4:], diag0[m][:, 4:])
     # sticky H: filter(x, uDes) now minimises 2.5 (u - uDes)^2 + ..., i.e. c = [-2 uDes, defaults] with H = 2.5
     u1, relax1, rc1 = eng.filter_batch(x, ud)
-    relax_defaults = {1: [-2 * opts[1] * opts[0]], 2: [-2 * opts[0] * opts[1]], 6: [-2 * opts[0] * opts[1]],
-                      3: [-2 * opts[0] * opts[2], -2 * opts[0] * opts[1]], 7: [-2 * opts[0] * opts[2], -2 * opts[0] * opts[1]]}[cfg]
+    if cfg == 1:      # explicit: [relaxLb, relaxCost]
+        relax_defaults = [-2 * opts[1] * opts[0]]
+    elif cfg in (2, 6):  # TB: [relaxCost, relaxSafeLb, ...]
+        relax_defaults = [-2 * opts[0] * opts[1]]
+    else:             # implicit / RB: [relaxCost, relaxReachLb, relaxSafeLb, ...]; v = (u, delta_safe, delta_reach)
+        relax_defaults = [-2 * opts[0] * opts[2], -2 * opts[0] * opts[1]]
     cdef = np.concatenate([-2.0 * ud, np.tile(relax_defaults, (n, 1))], axis=1)
     u2, relax2, rc2 = eng.filter_batch_cost(x, cdef, None)
     assert np.array_equal(rc1, rc2) and np.array_equal(u1, u2) and np.array_equal(relax1, relax2)
