@@ -95,6 +95,7 @@ def load_library():
     L.asif_engine_filter_batch_cost.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
     L.asif_engine_set_input_cost.argtypes = [C.c_void_p, C.c_void_p]
+    L.asif_engine_filter_batch_lie.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 8 + [C.c_int32, C.c_void_p]
     L.asif_engine_rollout.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_double, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.c_int32, C.c_void_p]
     L.asif_engine_last_qp_iterations.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
@@ -235,6 +236,20 @@ class Engine:
         _check(load_library().asif_engine_filter_batch_cost(self._h, n, x.ctypes.data, Hp, c.ctypes.data, u.ctypes.data,
                                                             relax.ctypes.data, rc.ctypes.data,
                                                             diag.ctypes.data if want_diag else None, MEM_HOST, None))
+        return (u, relax, rc, diag) if want_diag else (u, relax, rc)
+
+    def filter_batch_lie(self, x, u_des, Lfh, Lgh, want_diag=False):
+        """ASIF::filter(x, uDes, uAct, Lfh, Lgh, relax) on a batch: Lfh (n, nc), Lgh (n, nc*nu) per state column-major."""
+        x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1, self.nx)
+        u_des = np.ascontiguousarray(u_des, dtype=np.float64).reshape(-1, self.nu)
+        n = x.shape[0]
+        Lfh = np.ascontiguousarray(Lfh, dtype=np.float64).reshape(n, self.nc)
+        Lgh = np.ascontiguousarray(Lgh, dtype=np.float64).reshape(n, self.nc * self.nu)
+        u, relax, rc = np.empty((n, self.nu)), np.empty((n, self.n_relax)), np.empty(n, dtype=np.int32)
+        diag = np.empty((n, self.n_diag)) if want_diag else None
+        _check(load_library().asif_engine_filter_batch_lie(self._h, n, x.ctypes.data, u_des.ctypes.data, Lfh.ctypes.data,
+                                                           Lgh.ctypes.data, u.ctypes.data, relax.ctypes.data, rc.ctypes.data,
+                                                           diag.ctypes.data if want_diag else None, MEM_HOST, None))
         return (u, relax, rc, diag) if want_diag else (u, relax, rc)
 
     def set_input_cost(self, H):

@@ -706,6 +706,8 @@ int32_t filter_batch_impl(asif_engine *e, int64_t n, const double *x, const doub
 	if (mem == ASIF_MEM_DEVICE) {
 		cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
 		CUDA_TRY(cudaMemsetAsync(e->d_counters, 0, sizeof(unsigned long long), st));
+		e->ex.lfh = e->lie_lfh;
+		e->ex.lgh = e->lie_lgh;
 		int r = launch_filter(e, n, x, u_des, u_act, relax, rc, diag, st);
 		if (r) return r;
 		if (!stream) CUDA_TRY(cudaStreamSynchronize(st));
@@ -726,6 +728,8 @@ int32_t filter_batch_impl(asif_engine *e, int64_t n, const double *x, const doub
 		if (r) return r;
 		CUDA_TRY(cudaMemcpyAsync(s.x, x + off * nx, sizeof(double) * m * nx, cudaMemcpyHostToDevice, s.stream));
 		CUDA_TRY(cudaMemcpyAsync(s.ud, u_des + off * cw, sizeof(double) * m * cw, cudaMemcpyHostToDevice, s.stream));
+		e->ex.lfh = e->lie_lfh ? e->lie_lfh + off * e->nc : nullptr; // device copies of the whole batch (filter_batch_lie)
+		e->ex.lgh = e->lie_lgh ? e->lie_lgh + off * e->nc * e->nu : nullptr;
 		r = launch_filter(e, m, s.x, s.ud, s.ua, s.relax, s.rc, diag ? s.diag : nullptr, s.stream);
 		if (r) return r;
 		CUDA_TRY(cudaMemcpyAsync(u_act + off * nu, s.ua, sizeof(double) * m * nu, cudaMemcpyDeviceToHost, s.stream));
@@ -781,6 +785,46 @@ int32_t asif_engine_filter_batch_cost(asif_engine *e, int64_t n, const double *x
 	set_custom_cost(e, 1);
 	const int32_t r = filter_batch_impl(e, n, x, c, e->nv, u_act, relax, rc, diag, mem, stream);
 	set_custom_cost(e, 0);
+	return r;
+}
+
+int32_t asif_engine_filter_batch_lie(asif_engine *e, int64_t n, const double *x, const double *u_des, const double *Lfh,
+                                     const double *Lgh, double *u_act, double *relax, int32_t *rc, double *diag, int32_t mem,
+                                     void *stream)
+{
+	if (!e) return fail(ASIF_ERR_INVALID_ARGUMENT, "engine is NULL");
+	if (e->cfg.filter != ASIF_FILTER_EXPLICIT)
+		return fail(ASIF_ERR_UNSUPPORTED, "filter(x, uDes, uAct, Lfh, Lgh, relax) exists in ASIF::ASIF only (filter %d given)", e->cfg.filter);
+	if (!Lfh || !Lgh) return fail(ASIF_ERR_INVALID_ARGUMENT, "Lfh / Lgh is NULL");
+	if (n <= 0) return n < 0 ? fail(ASIF_ERR_INVALID_ARGUMENT, "n < 0") : ASIF_OK;
+	CUDA_TRY(cudaSetDevice(e->cfg.device));
+	set_custom_cost(e, 0);
+	double *dl = nullptr, *dg = nullptr;
+	if (mem == ASIF_MEM_DEVICE) {
+		e->lie_lfh = Lfh;
+		e->lie_lgh = Lgh;
+	} else { // host arrays: one device copy of the whole batch (8 (nc + nc nu) bytes per state), chunks index into it
+		const size_t bl = sizeof(double) * (size_t)n * e->nc, bg = bl * e->nu;
+		cudaError_t ce = cudaMalloc(&dl, bl);
+		if (ce == cudaSuccess) ce = cudaMalloc(&dg, bg);
+		if (ce == cudaSuccess) ce = cudaMemcpy(dl, Lfh, bl, cudaMemcpyHostToDevice);
+		if (ce == cudaSuccess) ce = cudaMemcpy(dg, Lgh, bg, cudaMemcpyHostToDevice);
+		if (ce != cudaSuccess) {
+			cudaFree(dl);
+			cudaFree(dg);
+			return fail(ASIF_ERR_CUDA, "Lfh / Lgh upload failed: %s", cudaGetErrorString(ce));
+		}
+		e->lie_lfh = dl;
+		e->lie_lgh = dg;
+	}
+	const int32_t r = filter_batch_impl(e, n, x, u_des, e->nu, u_act, relax, rc, diag, mem, stream);
+	e->lie_lfh = e->lie_lgh = nullptr;
+	e->ex.lfh = e->ex.lgh = nullptr;
+	if (dl || dg) {
+		cudaDeviceSynchronize();
+		cudaFree(dl);
+		cudaFree(dg);
+	}
 	return r;
 }
 

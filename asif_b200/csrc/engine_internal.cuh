@@ -71,6 +71,7 @@ struct asif_engine {
 	size_t rz_smem = 0;
 	double *d_table = nullptr; // half-plane table (robust filter)
 	double *d_learn = nullptr; // learned-residual networks (implicit filters)
+	const double *lie_lfh = nullptr, *lie_lgh = nullptr; // device arrays of the current filter_batch_lie call (explicit filter)
 	Slot slot[N_SLOTS];
 	cudaStream_t stream = nullptr; // device-memory calls without a caller stream
 	unsigned long long *d_counters = nullptr; // [0] qp rows processed, [1..8] rc histogram

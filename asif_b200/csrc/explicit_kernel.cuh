@@ -108,6 +108,15 @@ explicit_filter_kernel(const ExplicitParams p, const int64_t n, const double *__
 			lgv[j][i] = lg;
 		}
 	}
+	if (p.lfh != nullptr) { // use_custom_ineq_: row pos[j] takes the caller's values (src/asif.cpp:287-292)
+#pragma unroll
+		for (int j = 0; j < NPSS; j++) {
+			if (pos[j] >= ncUse) continue;
+			rhsv[j] = -p.lfh[kk * ncUse + pos[j]];
+#pragma unroll
+			for (int i = 0; i < NU; i++) lgv[j][i] = p.lgh[kk * ncUse * NU + pos[j] + i * ncUse];
+		}
+	}
 	constexpr bool CLOSED_FORM = (NU == 1); // one input, relax variable fixed: the QP is an interval intersection
 	if (!CLOSED_FORM || WITH_DIAG) {
 #pragma unroll

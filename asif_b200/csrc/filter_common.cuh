@@ -73,6 +73,9 @@ struct ExplicitParams {
 	double gi[MAX_NV], gih[MAX_NV];
 	int32_t npSSmax; // rows kept (min(npSSmax, npSS), src/asif.cpp:21-22)
 	int32_t custom_cost; // filter(x, H, c, ...) (src/asif.cpp:153-174): u_des holds c[n][nv]
+	// filter(x, uDes, uAct, Lfh, Lgh[, relax]) (src/asif.cpp:125-141, 287-292): caller-supplied Lie derivatives per state,
+	// Lfh[n][nc], Lgh[n][nc x nu column-major], replacing the computed ones row for row; nullptr = computed
+	const double *lfh, *lgh;
 };
 
 // src/asif_implicit_tb.cpp:821-830

@@ -289,6 +289,20 @@ namespace ASIF
 				const double lb[1] = {lb_}, ub[1] = {ub_};
 				return initialize(lb, ub, options);
 			}
+			// filter(x, uDes, uAct, Lfh, Lgh, relax) (include/asif.h:43-58): caller-supplied Lie derivatives; for this call only
+			int32_t filter(const double x[], const double uDes[], double uAct[], double Lfh[], double Lgh[], double &relax)
+			{
+				int32_t rc = 0;
+				if (engine_ == nullptr) return ASIF_ERR_INVALID_ARGUMENT;
+				const int32_t r = asif_engine_filter_batch_lie(engine_, 1, x, uDes, Lfh, Lgh, uAct, &relax, &rc, nullptr, ASIF_MEM_HOST, nullptr);
+				return r == ASIF_OK ? rc : r;
+			}
+			int32_t filterBatchLie(const int64_t n, const double X[], const double UDes[], const double Lfh[], const double Lgh[],
+			                       double UAct[], double Relax[], int32_t rc[], double diag[] = nullptr)
+			{
+				if (engine_ == nullptr) return ASIF_ERR_INVALID_ARGUMENT;
+				return asif_engine_filter_batch_lie(engine_, n, X, UDes, Lfh, Lgh, UAct, Relax, rc, diag, ASIF_MEM_HOST, nullptr);
+			}
 			int32_t filter(const double x[], const double uDes[], double uAct[], double &relax)
 			{
 				int32_t rc = 0;

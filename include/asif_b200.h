@@ -147,6 +147,15 @@ int32_t asif_engine_filter_batch(asif_engine *e, int64_t n, const double *x, con
  */
 int32_t asif_engine_filter_batch_cost(asif_engine *e, int64_t n, const double *x, const double *H, const double *c,
                                       double *u_act, double *relax, int32_t *rc, double *diag, int32_t mem, void *stream);
+/*
+ * ASIF::filter(x, uDes, uAct, Lfh, Lgh[, relax]) (include/asif.h:43-58, src/asif.cpp:125-141, 287-292): the caller supplies
+ * the Lie derivatives of the nc = min(npSSmax, npSS) selected safety functions, Lfh[n][nc] and Lgh[n][nc x nu] (per state
+ * column-major), in place of Dh f and Dh g; h still comes from the safety set.  Unlike the reference (which keeps the
+ * caller's pointers and stays in this mode for every later call) the arrays apply to this call only.  Explicit filter only.
+ */
+int32_t asif_engine_filter_batch_lie(asif_engine *e, int64_t n, const double *x, const double *u_des, const double *Lfh,
+                                     const double *Lgh, double *u_act, double *relax, int32_t *rc, double *diag, int32_t mem,
+                                     void *stream);
 /* updateH alone (host pointer, nu x nu column-major) */
 int32_t asif_engine_set_input_cost(asif_engine *e, const double *H);
 

@@ -57,6 +57,9 @@ static double min_elem(const double *v, int n)
 static struct {
 	const double *H; /* nu x nu column-major or NULL */
 	const double *c; /* nv entries or NULL */
+	/* ASIF::filter(x, uDes, uAct, Lfh, Lgh[, relax]) (src/asif.cpp:125-141,287-292): caller-supplied Lie derivatives,
+	 * npSSmax entries / npSSmax x nu column-major, replacing the computed ones row for row */
+	const double *Lfh, *Lgh;
 } g_cost;
 
 static void apply_cost_override(int nv, int nu, double *H, double *c)
@@ -549,6 +552,10 @@ static int32_t explicit_filter(const oracle_model *md, double relaxLb, double re
 	}
 	mat_vec(Dh, nsel, nx, f, Lfh);
 	mat_mul(Dh, nsel, nx, g, nu, Lgh);
+	if (g_cost.Lfh && g_cost.Lgh) { /* use_custom_ineq_, :287-292 */
+		for (int i = 0; i < nsel; i++) Lfh[i] = g_cost.Lfh[i];
+		for (int i = 0; i < nsel * nu; i++) Lgh[i] = g_cost.Lgh[i];
+	}
 	double A[16 * ORACLE_QP_NVMAX], b[16];
 	for (int i = 0; i < nsel; i++) {
 		for (int j = 0; j < nu; j++) A[i + j * nc] = Lgh[i + j * nsel];
@@ -1004,6 +1011,23 @@ int oracle_filter_batch_cost(int cfg, const double *opts, int n_opts, int64_t n,
 		g_cost.H = 0;
 		g_cost.c = 0;
 		for (int j = 0; j < c.n_relax; j++) relax[k * c.n_relax + j] = r[j];
+	}
+	return 0;
+}
+
+int oracle_filter_batch_lie(const double *opts, int n_opts, int64_t n, const double *x, const double *u_des, const double *Lfh,
+                            const double *Lgh, double *u_act, double *relax, int32_t *rc, double *diag)
+{
+	ctx_t c;
+	if (make_ctx(ORACLE_CFG_DI_EXPLICIT, opts, n_opts, &c)) return -1;
+	for (int64_t k = 0; k < n; k++) {
+		double r[2] = {0.0, 0.0};
+		for (int j = 0; j < c.nu; j++) u_act[k * c.nu + j] = 0.0;
+		g_cost.Lfh = Lfh + k * c.nc;
+		g_cost.Lgh = Lgh + k * c.nc * c.nu;
+		rc[k] = filter_one(&c, x + k * c.nx, u_des + k * c.nu, u_act + k * c.nu, r, diag ? diag + k * c.n_diag : 0);
+		g_cost.Lfh = g_cost.Lgh = 0;
+		relax[k] = r[0];
 	}
 	return 0;
 }

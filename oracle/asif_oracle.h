@@ -74,6 +74,9 @@ int oracle_filter_batch(int cfg, const double *opts, int n_opts, int64_t n, cons
  * block), cvec[n*nv].  Classes ASIF, ASIFimplicitTB, ASIFimplicit, ASIFimplicitRB. */
 int oracle_filter_batch_cost(int cfg, const double *opts, int n_opts, int64_t n, const double *x, const double *H,
                              const double *cvec, double *u_act, double *relax, int32_t *rc, double *diag);
+/* ASIF::filter(x, uDes, uAct, Lfh, Lgh, relax) per state (cfg 1): Lfh[n*nc], Lgh[n*nc*nu] (per state column-major nc x nu) */
+int oracle_filter_batch_lie(const double *opts, int n_opts, int64_t n, const double *x, const double *u_des, const double *Lfh,
+                            const double *Lgh, double *u_act, double *relax, int32_t *rc, double *diag);
 /* learned residual of the implicit classes (cfg 3, 7, 8), include/asif_learning_utils.h: process-wide switch, NULL = off.
  * dims[8] / blob as ref_set_learning (oracle/ref_build/ref_api.h) */
 int oracle_set_learning(const uint32_t *dims, const double *blob);

@@ -102,6 +102,20 @@ class RefFilter:
         assert r == 0
         return u, relax, rc, diag, st
 
+    def filter_batch_lie(self, x, u_des, Lfh, Lgh):
+        """ASIF::filter(x, uDes, uAct, Lfh, Lgh, relax) per state (cfg 1) -> (u, relax, rc, diag)."""
+        L = self.lib.lib
+        L.ref_filter_batch_lie.argtypes = [C.c_void_p, C.c_int64, _dp, _dp, _dp, _dp, _dp, _dp, _ip, _dp]
+        x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1, self.nx)
+        u_des = np.ascontiguousarray(u_des, dtype=np.float64).reshape(-1, self.nu)
+        Lfh = np.ascontiguousarray(Lfh, dtype=np.float64)
+        Lgh = np.ascontiguousarray(Lgh, dtype=np.float64)
+        n = x.shape[0]
+        u, relax, rc, diag = np.zeros((n, self.nu)), np.zeros((n, 1)), np.zeros(n, dtype=np.int32), np.zeros((n, self.n_diag))
+        assert L.ref_filter_batch_lie(self.h, n, _d(x), _d(u_des), _d(Lfh), _d(Lgh), _d(u), _d(relax), rc.ctypes.data_as(_ip),
+                                      _d(diag)) == 0
+        return u, relax, rc, diag
+
     def filter_batch_ex(self, x, u_des):
         """(u, relax, rc, diag, raw OSQP status, ADMM iterations) - single-threaded use only."""
         x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1, self.nx)
@@ -207,6 +221,21 @@ class OracleLib:
                                               rc.ctypes.data_as(_ip), _d(diag))
         assert r == 0
         return (u, relax, rc, diag) if want_diag else (u, relax, rc)
+
+    def filter_batch_lie(self, x, u_des, Lfh, Lgh, opts=None):
+        """ASIF::filter(x, uDes, uAct, Lfh, Lgh, relax) per state (cfg 1)."""
+        self.lib.oracle_filter_batch_lie.argtypes = [_dp, C.c_int, C.c_int64, _dp, _dp, _dp, _dp, _dp, _dp, _ip, _dp]
+        o = None if opts is None else np.ascontiguousarray(opts, dtype=np.float64)
+        nx, nu, n_relax, nc, nv, n_diag = self.dims(CFG_DI_EXPLICIT, opts)
+        x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1, nx)
+        u_des = np.ascontiguousarray(u_des, dtype=np.float64).reshape(-1, nu)
+        Lfh = np.ascontiguousarray(Lfh, dtype=np.float64)
+        Lgh = np.ascontiguousarray(Lgh, dtype=np.float64)
+        n = x.shape[0]
+        u, relax, rc, diag = np.zeros((n, nu)), np.zeros((n, 1)), np.zeros(n, dtype=np.int32), np.zeros((n, n_diag))
+        assert self.lib.oracle_filter_batch_lie(_d(o), 0 if o is None else o.size, n, _d(x), _d(u_des), _d(Lfh), _d(Lgh), _d(u),
+                                                _d(relax), rc.ctypes.data_as(_ip), _d(diag)) == 0
+        return u, relax, rc, diag
 
     def rollout(self, cfg, x0, u_des, steps, dt, opts=None):
         o = None if opts is None else np.ascontiguousarray(opts, dtype=np.float64)

@@ -54,6 +54,10 @@ int ref_filter_batch_ex(void *h, int64_t n, const double *x, const double *u_des
  * (the class then keeps its current H_), c[n*nv]; qp_status as ref_filter_batch_ex */
 int ref_filter_batch_cost(void *h, int64_t n, const double *x, const double *H, const double *c, double *u_act, double *relax,
                           int32_t *rc, double *diag, int32_t *qp_status);
+/* cfg 1 only: ASIF::filter(x, uDes, uAct, Lfh, Lgh, relax) per state with Lfh[n*nc], Lgh[n*nc*nu].  The reference keeps
+ * the caller's pointers and the custom mode for good (src/asif.cpp:137-139): use a filter object created for this purpose */
+int ref_filter_batch_lie(void *h, int64_t n, const double *x, const double *u_des, const double *Lfh, const double *Lgh,
+                         double *u_act, double *relax, int32_t *rc, double *diag);
 /* closed-loop rollout exactly as the example main loops do (x += dt*(f+g*uAct)); x is updated in place */
 int ref_rollout(void *h, int64_t n, int32_t steps, double dt, double *x, const double *u_des,
                 double *u_act_last, int32_t *rc_last, int64_t *rc_hist /* [8] or NULL */);

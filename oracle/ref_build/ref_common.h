@@ -8,6 +8,8 @@ struct RefFilter {
 	int nx, nu, n_relax, nc, nv, n_diag;
 	/* when costC is set, filter() calls the class's filter(x, H, c, uAct, relax) overload with these instead of uDes */
 	const double *costH = 0, *costC = 0;
+	/* ASIF only: when set, filter() calls filter(x, uDes, uAct, Lfh, Lgh, relax) (sticky in the reference: use a fresh object) */
+	double *lieLfh = 0, *lieLgh = 0;
 	virtual ~RefFilter() {}
 	/* one reference filter() call; diag may be NULL */
 	virtual int32_t filter(const double *x, const double *u_des, double *u_act, double *relax, double *diag) = 0;

@@ -105,6 +105,24 @@ int ref_filter_batch_cost(void *h, int64_t n, const double *x, const double *H, 
 	return 0;
 }
 
+int ref_filter_batch_lie(void *h, int64_t n, const double *x, const double *u_des, const double *Lfh, const double *Lgh,
+                         double *u_act, double *relax, int32_t *rc, double *diag)
+{
+	RefFilter *f = (RefFilter *)h;
+	if (!f) return -1;
+	std::vector<double> lf(f->nc), lg(f->nc * f->nu);
+	for (int64_t k = 0; k < n; k++) {
+		double r[2] = {0.0, 0.0};
+		for (int i = 0; i < f->nc; i++) lf[i] = Lfh[k * f->nc + i];
+		for (int i = 0; i < f->nc * f->nu; i++) lg[i] = Lgh[k * f->nc * f->nu + i];
+		f->lieLfh = lf.data();
+		f->lieLgh = lg.data();
+		rc[k] = f->filter(x + k * f->nx, u_des + k * f->nu, u_act + k * f->nu, r, diag ? diag + k * f->n_diag : 0);
+		relax[k] = r[0];
+	}
+	return 0;
+}
+
 int ref_rollout(void *h, int64_t n, int32_t steps, double dt, double *x, const double *u_des,
                 double *u_act_last, int32_t *rc_last, int64_t *rc_hist)
 {

@@ -36,7 +36,8 @@ struct DiExplicit : RefFilter {
 	}
 	int32_t filter(const double *x, const double *u_des, double *u_act, double *relax, double *diag) override
 	{
-		int32_t rc = costC ? f.filter(x, costH, costC, u_act, relax[0]) : f.filter(x, u_des, u_act, relax[0]);
+		int32_t rc = costC ? f.filter(x, costH, costC, u_act, relax[0])
+		                   : (lieLfh ? f.filter(x, u_des, u_act, lieLfh, lieLgh, relax[0]) : f.filter(x, u_des, u_act, relax[0]));
 		if (diag) {
 			memcpy(diag, f.A(), sizeof(double) * nc * nv);
 			memcpy(diag + nc * nv, f.b(), sizeof(double) * nc);

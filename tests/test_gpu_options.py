@@ -173,3 +173,23 @@ def test_custom_cost_refused_for_lp_dual_classes():
                     halfplanes=cf.halfplane_table())
     with pytest.raises(ab.AsifError):
         eng.filter_batch_cost(np.zeros((4, 2)), np.zeros((4, 2)), None)
+
+
+@pytest.mark.parametrize("npSSmax", [0, 2])
+def test_explicit_custom_lie_derivatives(oracle, npSSmax):
+    """asif_engine_filter_batch_lie: caller-supplied Lfh / Lgh for the explicit filter; this call only (not sticky)."""
+    import asif_b200 as ab
+    n = 50_000
+    opts = list(cf.C1_OPTS) + ([float(npSSmax)] if npSSmax else [])
+    x, ud = cf.c1_inputs(n, seed=cf.SEED + 810 + npSSmax)
+    eng = ab.Engine(ab.FILTER_EXPLICIT, ab.MODEL_DOUBLE_INTEGRATOR, relaxLb=opts[0], relaxCost=opts[1], npSSmax=npSSmax or -1)
+    base = eng.filter_batch(x, ud, want_diag=True)
+    g = cf.philox(6)
+    Lfh, Lgh = g.normal(0, 1, (n, eng.nc)), g.normal(0, 1, (n, eng.nc))
+    u, relax, rc, diag = eng.filter_batch_lie(x, ud, Lfh, Lgh, want_diag=True)
+    u0, relax0, rc0, diag0 = oracle.filter_batch_lie(x, ud, Lfh, Lgh, opts)
+    assert np.array_equal(diag, diag0)
+    cf.assert_parity("lie", (u, relax, rc), (u0, relax0, rc0))
+    again = eng.filter_batch(x, ud, want_diag=True)
+    for p, q in zip(base, again):
+        assert np.array_equal(p, q)

@@ -192,3 +192,18 @@ def test_custom_cost_matches_reference(oracle, reflib, cfg, opts, gen, n):
     # the cost matters: the same states through filter(x, uDes) give other inputs
     u1 = oracle.filter_batch(cfg, x, ud, opts)[0]
     assert np.abs(u1 - u)[rc == 1].max() > 1e-3
+
+
+@pytest.mark.parametrize("npSSmax", [0, 2])
+def test_explicit_custom_lie_derivatives(oracle, reflib, npSSmax):
+    """ASIF::filter(x, uDes, uAct, Lfh, Lgh, relax) (src/asif.cpp:125-141,287-292): caller-supplied Lfh / Lgh rows."""
+    opts = list(cf.C1_OPTS) + ([float(npSSmax)] if npSSmax else [])
+    x, ud = cf.c1_inputs(3000, seed=cf.SEED + 800 + npSSmax)
+    f = reflib.create(pyref.CFG_DI_EXPLICIT, opts)
+    g = cf.philox(5)
+    Lfh, Lgh = g.normal(0, 1, (3000, f.nc)), g.normal(0, 1, (3000, f.nc))
+    u0, relax0, rc0, diag0 = f.filter_batch_lie(x, ud, Lfh, Lgh)
+    u, relax, rc, diag = oracle.filter_batch_lie(x, ud, Lfh, Lgh, opts)
+    assert np.array_equal(diag, diag0)
+    cf.assert_parity("lie", (u, relax, rc), (u0, relax0, rc0))
+    assert (rc0 == -1).sum() > 50
