@@ -479,6 +479,15 @@ namespace ASIF
 				return r == ASIF_OK ? rc : r;
 			}
 
+			// src/asif_implicit.cpp:829-842 (same in src/asif_implicit_robust.cpp:967-980)
+			static std::string filterErrorMsgString(const int32_t rc)
+			{
+				switch (rc) {
+				case 1: return "Success";
+				case -1: return "QP failed";
+				default: return "Unkown";
+				}
+			}
 		protected:
 			int32_t build(void)
 			{
@@ -570,6 +579,15 @@ namespace ASIF
 				return r == ASIF_OK ? rc : r;
 			}
 
+			// src/asif_implicit.cpp:829-842 (same in src/asif_implicit_robust.cpp:967-980)
+			static std::string filterErrorMsgString(const int32_t rc)
+			{
+				switch (rc) {
+				case 1: return "Success";
+				case -1: return "QP failed";
+				default: return "Unkown";
+				}
+			}
 		protected:
 			int32_t build(void)
 			{
