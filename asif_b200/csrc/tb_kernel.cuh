@@ -58,7 +58,7 @@ struct TbRows {
 	__device__ __forceinline__ int count_np() const { return np_runtime(NPBTSS) ? np : NPBTSS; }
 	__device__ __forceinline__ int nc() const { return count_np() * NPSS + 2; }
 	const double *snap; // this thread's view, element stride T
-	int T;
+	static constexpr int T = TB_THREADS;
 	double f[NX], g[NX * NU]; // open-loop dynamics at the current state (:416-418)
 	int kslot[CAP];
 	int nkept;
@@ -96,31 +96,63 @@ struct TbRows {
 		}
 		rhs = bnd;
 	}
+	// the slots of the kept points, 4 bits each (CAP <= 8): looked up by shift and mask in the row loops, where the
+	// loop index is not a compile-time constant (an array would live in local memory)
+	unsigned kpack;
+	__device__ __forceinline__ void pack_slots()
+	{
+		kpack = 0u;
+#pragma unroll
+		for (int t = 0; t < CAP; t++) kpack |= (unsigned)kslot[t] << (4 * t);
+	}
+	__device__ __forceinline__ int slot_of(const int s) const { return (int)((kpack >> (4 * s)) & 15u); }
 	// every row once, in the reference's row order, then the 2*NV variable bounds
 	template <class F, class FB>
 	__device__ __forceinline__ void scan(F &&fn, FB &&fb) const
 	{
+		double v0[NV];
+#pragma unroll
+		for (int i = 0; i < NV; i++) v0[i] = 0.0;
+		scan_at<false>(v0, fn, fb);
+	}
+	// PREFILTER: rows are presented at the iterate v; the four rows of a critical point are handed to fn only when
+	// the smallest of their residuals is below -QP_FEAS_TOL, which is the first thing fn tests for each of them
+	// (qp_gi.cuh), so the solver's decisions are unchanged while the common case costs one branch per point
+	template <bool PREFILTER, class F, class FB>
+	__device__ __forceinline__ void scan_at(const double (&v)[NV], F &&fn, FB &&fb) const
+	{
 		if (!trivial) {
 			const int NC = nc();
+			const int nk = nkept < count_np() ? nkept : count_np();
 #pragma unroll 1
-			for (int s = 0; s < count_np(); s++) { // not unrolled: one copy of point_rows keeps registers down
+			for (int s = 0; s < nk; s++) { // not unrolled: one copy of point_rows keeps registers down
 				double n[NPSS][NV], rhs[NPSS];
-				if (s < nkept) {
-					int slot = 0;
-#pragma unroll
-					for (int t = 0; t < CAP; t++) slot = (t == s) ? kslot[t] : slot;
-					point_rows(slot, n, rhs);
-				} else { // h = 1, Dh = 0 (:556-566)
+				point_rows(slot_of(s), n, rhs);
+				bool any = true;
+				if (PREFILTER) {
+					double smin = 0.0;
 #pragma unroll
 					for (int j = 0; j < NPSS; j++) {
+						double r = -rhs[j]; // same expression as the solver's residual
 #pragma unroll
-						for (int i = 0; i < NU; i++) n[j][i] = 0.0;
-						n[j][NU] = 1.0;
-						rhs[j] = -0.0;
+						for (int i = 0; i < NV; i++) r += n[j][i] * v[i];
+						smin = (j == 0 || r < smin) ? r : smin;
 					}
+					any = smin < -QP_FEAS_TOL;
 				}
+				if (any) {
 #pragma unroll
-				for (int j = 0; j < NPSS; j++) fn(s * NPSS + j, n[j], rhs[j]);
+					for (int j = 0; j < NPSS; j++) fn(s * NPSS + j, n[j], rhs[j]);
+				}
+			}
+#pragma unroll 1
+			for (int s = nk; s < count_np(); s++) { // missing points: h = 1, Dh = 0 (:556-566)
+				double n[NV];
+#pragma unroll
+				for (int i = 0; i < NU; i++) n[i] = 0.0;
+				n[NU] = 1.0;
+#pragma unroll
+				for (int j = 0; j < NPSS; j++) fn(s * NPSS + j, n, -0.0);
 			}
 			double n[NV];
 #pragma unroll
@@ -152,11 +184,8 @@ struct TbRows {
 		} else {
 			const int s = j / NPSS, jj = j - s * NPSS;
 			if (s < nkept) {
-				int slot = 0;
-#pragma unroll
-				for (int t = 0; t < CAP; t++) slot = (t == s) ? kslot[t] : slot;
 				double nn[NPSS][NV], rr[NPSS];
-				point_rows(slot, nn, rr);
+				point_rows(slot_of(s), nn, rr);
 #pragma unroll
 				for (int t = 0; t < NPSS; t++) {
 					if (t == jj) {
@@ -189,6 +218,14 @@ __device__ __forceinline__ void tb_cost_vector(const TbParams &p, const double *
 		for (int i = 0; i < NU; i++) cin[i] = -2.0 * u_des[kk * NU + i];
 		cin[NU] = -2.0 * p.relaxCost * p.relaxSafeLb;
 	}
+}
+
+// the solver's row scan for the TB rows (found by ADL, see qp_scan_rows in qp_gi.cuh): scan at the iterate with the
+// per-point pre-filter
+template <class M, int NPBTSS, class F, class FB>
+__device__ __forceinline__ void qp_scan_rows(const TbRows<M, NPBTSS> &rows, const double (&v)[M::NU + 1], F &&fn, FB &&fb)
+{
+	rows.template scan_at<true>(v, fn, fb);
 }
 
 template <int NPBTSS>
@@ -327,8 +364,8 @@ __device__ __forceinline__ int32_t tb_filter_one(const TbParams &p, const double
 	double c[NV];
 	DiagMetric<NV> mt;
 	R.snap = snap;
-	R.T = T;
 	R.nkept = (np_runtime(NPBTSS) && nkept > np) ? np : nkept;
+	R.pack_slots();
 	R.trivial = inside;
 	R.neg_inf = -p.inf;
 #pragma unroll
@@ -584,7 +621,7 @@ tb_filter_kernel(const TbParams p, const int64_t n, const double *__restrict__ x
                  double *__restrict__ u_act, double *__restrict__ relax_out, int32_t *__restrict__ rc_out,
                  double *__restrict__ diag, unsigned long long *__restrict__ qp_iter_sum, double *__restrict__ gsnap)
 {
-	const int T = blockDim.x;
+	constexpr int T = TB_THREADS; // every launch uses TB_THREADS threads (engine_internal.cuh): compile-time strides
 	if (tb_global_snapshots<M>()) {
 		// persistent: every warp pulls tiles of 32 states from a counter that lives in front of the scratch
 		unsigned long long *next_tile = reinterpret_cast<unsigned long long *>(gsnap);
@@ -615,7 +652,7 @@ tb_rollout_kernel(const TbParams p, const int64_t n, const int32_t steps, const 
 {
 	constexpr int NX = M::NX, NU = M::NU;
 	extern __shared__ double smem[];
-	const int T = blockDim.x;
+	constexpr int T = TB_THREADS;
 	constexpr bool GS = tb_global_snapshots<M>();
 	double *snap = GS ? gsnap + TB_SCRATCH_HEADER + (int64_t)blockIdx.x * tb_smem_doubles_per_thread<M, NPBTSS>() * T + threadIdx.x
 	                  : smem + threadIdx.x;
