@@ -221,9 +221,9 @@ __device__ __forceinline__ int qp_gi_solve(const Metric &mt, const double (&c)[N
 #pragma unroll
 			    for (int i = 0; i < NV; i++) s += n[i] * w.v[i];
 			    if (s < -QP_FEAS_TOL && s < sp) { // rarely true: the expensive part of the test only runs then
-				    double nmax = 1.0;
+				    double nmax = 1.0; // max(1, |n|_inf) by compare and select (fmax would add NaN handling to every term)
 #pragma unroll
-				    for (int i = 0; i < NV; i++) nmax = fmax(nmax, fabs(n[i]));
+				    for (int i = 0; i < NV; i++) nmax = (fabs(n[i]) > nmax) ? fabs(n[i]) : nmax;
 				    bool is_act = false;
 #pragma unroll
 				    for (int a = 0; a < NV; a++) is_act |= (a < w.q) && (w.act[a] == j);

@@ -99,6 +99,25 @@ def main():
     cols = [0, 1, 2] + list(range(4, eng.n_diag))
     report("C5 ASIFimplicitTB / segway npBT 316", n5, eng.filter_batch(x, ud, want_diag=True), oracle_batch(6, x, ud, cf.SEGWAY_TB_OPTS),
            cols, note="CUDA sincos/tanh vs glibc, FMA contraction on: tolerance parity", crit_cols=slice(4, 8))
+    # ASIFimplicitRB: pendulum callbacks (split gradients, tolerance parity) and double-integrator callbacks
+    # (fused gradient, bit parity)
+    nr = max(5000, N // 5)
+    x, ud = cf.c3a_inputs(nr, seed=cf.SEED + 91)
+    eng = ab.Engine(ab.FILTER_IMPLICIT_RB, ab.MODEL_INVERTED_PENDULUM, **cf.rb_engine_kwargs(cf.RB_IP_OPTS))
+    report("RB ASIFimplicitRB / InvertedPendulum npBT 101, hold 0.2 s, x_unc (0.05, 0.08)", nr, eng.filter_batch(x, ud, want_diag=True),
+           oracle_batch(7, x, ud, cf.RB_IP_OPTS), slice(None), crit_cols=slice(2, 12))
+    x, ud = cf.c2_inputs(nr, seed=cf.SEED + 92)
+    eng = ab.Engine(ab.FILTER_IMPLICIT_RB, ab.MODEL_DOUBLE_INTEGRATOR_TB, **cf.rb_engine_kwargs(cf.RB_DI_OPTS))
+    report("RB ASIFimplicitRB / DoubleIntegrator npBT 151, hold 0.1 s, x_unc (0.05, 0.01)", nr, eng.filter_batch(x, ud, want_diag=True),
+           oracle_batch(8, x, ud, cf.RB_DI_OPTS), slice(None), crit_cols=slice(2, 8))
+    # the filter(x, H, c, ...) overloads on the headline config
+    x, ud = cf.c2_inputs(N, seed=cf.SEED + 93)
+    eng = ab.Engine(ab.FILTER_IMPLICIT_TB, ab.MODEL_DOUBLE_INTEGRATOR_TB, **cf.tb_engine_kwargs(cf.C2_TB_OPTS))
+    H, c = cf.custom_cost(ud, eng.nv, seed=2)
+    want = O.filter_batch_cost(2, x, c, H, cf.C2_TB_OPTS, True)  # single thread: the oracle's cost override is a process-wide switch
+    cols = [0, 1, 2] + list(range(4, eng.n_diag))
+    report("C2 through filter(x, H, c): H = 2.5, c random", N, eng.filter_batch_cost(x, c, H, want_diag=True), want, cols,
+           crit_cols=slice(4, 8))
 
 
 if __name__ == "__main__":
