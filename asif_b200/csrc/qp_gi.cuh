@@ -304,7 +304,9 @@ __device__ __forceinline__ int qp_gi_solve(const Metric &mt, const double (&c)[N
 #pragma unroll
 					for (int b = a + 1; b < NV; b++)
 						if (b < w.q) t -= w.R[a][b] * r[b];
-					r[a] = t / w.R[a][a];
+					// a new row orthogonal to an active one (a variable bound against a row without that variable) gives an
+					// exact 0 here, and a zero numerator sends CUDA's division through its slow-path subroutine
+					r[a] = (t == 0.0) ? t : t / w.R[a][a];
 				}
 			}
 			double t1 = INFINITY;
