@@ -720,8 +720,27 @@ int32_t filter_batch_impl(asif_engine *e, int64_t n, const double *x, const doub
 	const int64_t chunk = n < chunk_states() ? n : chunk_states();
 	CUDA_TRY(cudaMemset(e->d_counters, 0, sizeof(unsigned long long)));
 	int si = 0;
-	for (int64_t off = 0; off < n; off += chunk, si = (si + 1) % N_SLOTS) {
-		const int64_t m = (n - off) < chunk ? (n - off) : chunk;
+	// Chunk schedule: the pipeline's fill (first H2D + first kernel) and drain (last kernel + last D2H) are not overlapped
+	// with anything, so the first two and the last two chunks are a quarter and a half of the steady-state size
+	// (env ASIF_B200_CHUNK_RAMP=0 switches the ramp off).
+	static const bool ramp = []() {
+		const char *v = getenv("ASIF_B200_CHUNK_RAMP");
+		return !(v && v[0] == '0');
+	}();
+	const int64_t small_ = chunk / 4 > 0 ? chunk / 4 : 1, mid_ = chunk / 2 > 0 ? chunk / 2 : 1;
+	const bool use_ramp = ramp && n >= 4 * chunk;
+	int64_t m = 0;
+	int idx = 0;
+	for (int64_t off = 0; off < n; off += m, si = (si + 1) % N_SLOTS, idx++) {
+		const int64_t left = n - off;
+		m = chunk;
+		if (use_ramp) {
+			if (idx == 0) m = small_;
+			else if (idx == 1) m = mid_;
+			else if (left <= small_ + mid_) m = left > small_ ? left - small_ : left; // the last two: about a half, then a quarter
+			else if (left < chunk + small_ + mid_) m = left - (small_ + mid_);        // what remains before them
+		}
+		if (m > left) m = left;
 		Slot &s = e->slot[si];
 		if (s.stream) CUDA_TRY(cudaStreamSynchronize(s.stream)); // slot buffers free again
 		int r = ensure_slot(e, s, chunk, diag != nullptr);
