@@ -686,6 +686,45 @@ int32_t asif_engine_dims(const asif_engine *e, int32_t dims[6])
 } // extern "C"
 
 namespace {
+// Device alias of a caller's host range when the device can address it (cudaHostAlloc'ed memory, or memory registered
+// with cudaHostRegisterMapped; under unified addressing both report a device pointer), else nullptr.
+template <class T>
+T *mapped_alias(const T *p, size_t count)
+{
+	if (!p || !count) return nullptr;
+	cudaPointerAttributes a0, a1;
+	const char *last = reinterpret_cast<const char *>(p) + count * sizeof(T) - 1;
+	if (cudaPointerGetAttributes(&a0, p) != cudaSuccess || cudaPointerGetAttributes(&a1, last) != cudaSuccess) {
+		cudaGetLastError();
+		return nullptr;
+	}
+	if (a0.type != cudaMemoryTypeHost || a1.type != cudaMemoryTypeHost || !a0.devicePointer || !a1.devicePointer) return nullptr;
+	if (reinterpret_cast<const char *>(a1.devicePointer) - reinterpret_cast<const char *>(a0.devicePointer) != last - reinterpret_cast<const char *>(p))
+		return nullptr; // first and last byte are not in one mapping
+	return reinterpret_cast<T *>(a0.devicePointer);
+}
+
+// ASIF_B200_HOST_IO: how a host-memory batch reaches the kernels.
+//   "staged"  H2D copy, kernel, D2H copy per chunk (the only mode for pageable memory)
+//   "out"     the kernels store uAct / relax / rc straight into the caller's pinned arrays over PCIe (posted writes,
+//             whole 128 / 256 B lines per warp): no D2H copies, no drain; inputs still arrive by chunked H2D copies
+//   "inout"   one launch over the caller's pinned arrays, inputs read over PCIe by the kernel as well
+//   "auto"    (default) "inout" for the trajectory-integrating and realizable filters, whose kernel time per state is
+//             at least the link time per state (loads and stores of one warp hide behind the arithmetic of the others;
+//             no pipeline fill or drain), "staged" for the explicit and robust filters, whose kernels are much shorter
+//             than their copies, so the copy engines' larger PCIe payloads win.  Measured on B200, ms per batch as
+//             staged / out / inout: C1 0.73 / 1.02 / 0.89, C2 (1e7) 6.06 / 5.97 / 5.27, C3a 32.1 / 31.8 / 32.5,
+//             C3b 1.02 / 1.30 / 1.43, C4 1.40 / 1.15 / 1.00, C5-filter 12.7 / 12.5 / 12.1 (gpurun_out/configs_e2e.jsonl).
+// Every mode falls back to "staged" when an array it needs is not device-addressable.
+int host_io_mode(const asif_engine *e)
+{
+	const char *v = getenv("ASIF_B200_HOST_IO"); // read per call: a test or a caller may switch it between batches
+	if (v && !strcmp(v, "staged")) return 0;
+	if (v && !strcmp(v, "out")) return 1;
+	if (v && !strcmp(v, "inout")) return 2;
+	return (e->cfg.filter == ASIF_FILTER_EXPLICIT || e->cfg.filter == ASIF_FILTER_ROBUST) ? 0 : 2;
+}
+
 // switches the kernels of this engine between updateCost(uDes) and the caller's linear cost (filter(x, H, c, ...))
 void set_custom_cost(asif_engine *e, int on)
 {
@@ -719,6 +758,29 @@ int32_t filter_batch_impl(asif_engine *e, int64_t n, const double *x, const doub
 	const int nx = e->nx, nu = e->nu, nr = e->n_relax, nd = e->n_diag;
 	const int64_t chunk = n < chunk_states() ? n : chunk_states();
 	CUDA_TRY(cudaMemset(e->d_counters, 0, sizeof(unsigned long long)));
+	// device aliases of the caller's output arrays (nullptr: pageable or unmapped memory, staged copies then)
+	double *m_ua = nullptr, *m_relax = nullptr, *m_diag = nullptr;
+	int32_t *m_rc = nullptr;
+	const int io = host_io_mode(e);
+	if (io >= 1) {
+		m_ua = mapped_alias(u_act, (size_t)n * nu);
+		m_relax = mapped_alias(relax, (size_t)n * nr);
+		m_rc = mapped_alias(rc, (size_t)n);
+		m_diag = diag ? mapped_alias(diag, (size_t)n * nd) : nullptr;
+	}
+	const bool direct_out = m_ua && m_relax && m_rc && (!diag || m_diag);
+	if (io == 2 && direct_out) {
+		const double *m_x = mapped_alias(x, (size_t)n * nx), *m_ud = mapped_alias(u_des, (size_t)n * cw);
+		if (m_x && m_ud) {
+			if (!e->slot[0].stream) CUDA_TRY(cudaStreamCreateWithFlags(&e->slot[0].stream, cudaStreamNonBlocking));
+			e->ex.lfh = e->lie_lfh;
+			e->ex.lgh = e->lie_lgh;
+			const int r = launch_filter(e, n, m_x, m_ud, m_ua, m_relax, m_rc, m_diag, e->slot[0].stream);
+			if (r) return r;
+			CUDA_TRY(cudaStreamSynchronize(e->slot[0].stream));
+			return ASIF_OK;
+		}
+	}
 	int si = 0;
 	// Chunk schedule: the pipeline's fill (first H2D + first kernel) and drain (last kernel + last D2H) are not overlapped
 	// with anything, so the first two and the last two chunks are a quarter and a half of the steady-state size
@@ -743,12 +805,17 @@ int32_t filter_batch_impl(asif_engine *e, int64_t n, const double *x, const doub
 		if (m > left) m = left;
 		Slot &s = e->slot[si];
 		if (s.stream) CUDA_TRY(cudaStreamSynchronize(s.stream)); // slot buffers free again
-		int r = ensure_slot(e, s, chunk, diag != nullptr);
+		int r = ensure_slot(e, s, chunk, diag != nullptr && !direct_out);
 		if (r) return r;
 		CUDA_TRY(cudaMemcpyAsync(s.x, x + off * nx, sizeof(double) * m * nx, cudaMemcpyHostToDevice, s.stream));
 		CUDA_TRY(cudaMemcpyAsync(s.ud, u_des + off * cw, sizeof(double) * m * cw, cudaMemcpyHostToDevice, s.stream));
 		e->ex.lfh = e->lie_lfh ? e->lie_lfh + off * e->nc : nullptr; // device copies of the whole batch (filter_batch_lie)
 		e->ex.lgh = e->lie_lgh ? e->lie_lgh + off * e->nc * e->nu : nullptr;
+		if (direct_out) {
+			r = launch_filter(e, m, s.x, s.ud, m_ua + off * nu, m_relax + off * nr, m_rc + off, diag ? m_diag + off * nd : nullptr, s.stream);
+			if (r) return r;
+			continue;
+		}
 		r = launch_filter(e, m, s.x, s.ud, s.ua, s.relax, s.rc, diag ? s.diag : nullptr, s.stream);
 		if (r) return r;
 		CUDA_TRY(cudaMemcpyAsync(u_act + off * nu, s.ua, sizeof(double) * m * nu, cudaMemcpyDeviceToHost, s.stream));

@@ -52,7 +52,11 @@ extern "C" {
 #define ASIF_MODEL_SEGWAY_SHIPPED 7       /* same, backup set exactly as shipped (:41-55)     */
 
 /* memory-space flags for the batch calls */
-#define ASIF_MEM_HOST 0   /* all batch pointers are host memory (pinned memory overlaps copies with compute) */
+#define ASIF_MEM_HOST 0   /* all batch pointers are host memory.  Pageable arrays are staged through chunked copies; pinned
+                           * (cudaHostAlloc / cudaHostRegisterMapped) arrays overlap the copies with the kernels and, for
+                           * the filter classes whose kernels outlast their transfers, are read and written by the kernel
+                           * directly over PCIe (env ASIF_B200_HOST_IO = staged | out | inout | auto; results are the same
+                           * bits in every mode) */
 #define ASIF_MEM_DEVICE 1 /* all batch pointers are device memory on the engine's device; nothing is copied */
 
 typedef struct asif_engine asif_engine;

@@ -41,7 +41,31 @@ def run(name, eng, x, ud, reps=5):
     print(json.dumps(out), flush=True)
 
 
+def run_e2e(name, eng, x, ud, reps=5):
+    """Host leg: pinned arrays through the C ABI, once per ASIF_B200_HOST_IO mode (wall clock around the calls)."""
+    n = x.shape[0]
+    xp, up = torch.from_numpy(x).pin_memory(), torch.from_numpy(ud).pin_memory()
+    ua = torch.empty((n, eng.nu), dtype=torch.float64).pin_memory()
+    rl = torch.empty((n, eng.n_relax), dtype=torch.float64).pin_memory()
+    rc = torch.empty((n,), dtype=torch.int32).pin_memory()
+    out = {"config": name, "states": n, "leg": "e2e (pinned host arrays, wall clock)",
+           "bytes_per_state": 8 * (eng.nx + 2 * eng.nu + eng.n_relax) + 4}
+    for mode in ("staged", "out", "inout"):
+        os.environ["ASIF_B200_HOST_IO"] = mode
+        for _ in range(2):
+            eng.filter_batch_into(n, xp, up, ua, rl, rc)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            eng.filter_batch_into(n, xp, up, ua, rl, rc)
+        out[mode + "_ms"] = 1e3 * (time.perf_counter() - t0) / reps
+    os.environ.pop("ASIF_B200_HOST_IO", None)
+    print(json.dumps(out), flush=True)
+
+
 def main():
+    global run
+    if "--e2e" in sys.argv:
+        run = run_e2e
     x, ud = cf.c1_inputs(1_000_000)
     run("C1 ASIF explicit / DoubleIntegrator, 1e6 states",
         ab.Engine(ab.FILTER_EXPLICIT, ab.MODEL_DOUBLE_INTEGRATOR, relaxLb=cf.C1_OPTS[0], relaxCost=cf.C1_OPTS[1]), x, ud, reps=20)
@@ -69,6 +93,8 @@ def main():
     x, ud = cf.c5_inputs(1_000_000)
     run("C5-filter ASIFimplicitTB / segway npBT=316, 1e6 states (one control step)",
         ab.Engine(ab.FILTER_IMPLICIT_TB, ab.MODEL_SEGWAY, **cf.tb_engine_kwargs(cf.SEGWAY_TB_OPTS)), x, ud, reps=3)
+    if "--e2e" in sys.argv:
+        return
     # C5 proper: fleet rollout, 1e5 agents x 1000 control steps, state resident on the device
     n, steps = 100_000, 1000
     x, ud = cf.c5_inputs(n)

@@ -94,3 +94,47 @@ def test_other_configs_full_size_invariants(ab):
     u, relax, rc = ab.Engine(ab.FILTER_IMPLICIT_TB, ab.MODEL_SEGWAY, **cf.tb_engine_kwargs(cf.SEGWAY_TB_OPTS)).filter_batch(x, ud)
     assert set(np.unique(rc)) <= {1, 2, -1, -2, -3} and np.abs(u).max() <= 20.0
     assert (rc == -2).sum() <= 5  # iteration cap of the active-set solver: essentially never
+
+
+@pytest.mark.parametrize("mode", ["staged", "out", "inout", "auto"])
+def test_pinned_host_io_modes_match_pageable(ab, mode, monkeypatch):
+    """ASIF_B200_HOST_IO: with pinned (device-addressable) arrays the kernels may store results straight into the
+    caller's memory ("out", the default) or also read the inputs from it ("inout"); every mode returns the bits of
+    the staged pageable path, over a size that spans the chunk ramp and ends in a ragged chunk."""
+    import torch
+    n = 4 * (1 << 19) + 12_345
+    x, ud = cf.c2_inputs(n, seed=11)
+    eng = ab.Engine(ab.FILTER_IMPLICIT_TB, ab.MODEL_DOUBLE_INTEGRATOR_TB, **cf.tb_engine_kwargs(cf.C2_TB_OPTS))
+    monkeypatch.setenv("ASIF_B200_HOST_IO", "staged")
+    u, relax, rc, diag = eng.filter_batch(x, ud, want_diag=True)
+    monkeypatch.setenv("ASIF_B200_HOST_IO", mode)
+    xp, up = torch.from_numpy(x).pin_memory(), torch.from_numpy(ud).pin_memory()
+    ua = torch.full((n, eng.nu), np.nan, dtype=torch.float64).pin_memory()
+    rl = torch.full((n, eng.n_relax), np.nan, dtype=torch.float64).pin_memory()
+    rcp = torch.full((n,), -99, dtype=torch.int32).pin_memory()
+    dg = torch.full((n, eng.n_diag), np.nan, dtype=torch.float64).pin_memory()
+    for with_diag in (False, True):
+        ua.fill_(np.nan), rl.fill_(np.nan), rcp.fill_(-99)
+        eng.filter_batch_into(n, xp, up, ua, rl, rcp, dg if with_diag else None)
+        assert np.array_equal(ua.numpy(), u) and np.array_equal(rl.numpy(), relax) and np.array_equal(rcp.numpy(), rc)
+        if with_diag:
+            assert np.array_equal(dg.numpy(), diag, equal_nan=True)
+    # a sub-range of the pinned arrays (alias arithmetic with an offset) and a mix of pinned inputs / pageable outputs
+    lo, hi = 1001, 1001 + 700_001
+    ua.fill_(np.nan)
+    eng.filter_batch_into(hi - lo, xp[lo:hi], up[lo:hi], ua[lo:hi], rl[lo:hi], rcp[lo:hi])
+    assert np.array_equal(ua.numpy()[lo:hi], u[lo:hi]) and np.isnan(ua.numpy()[:lo]).all() and np.isnan(ua.numpy()[hi:]).all()
+    u2, r2, c2 = np.empty_like(u), np.empty_like(relax), np.empty_like(rc)
+    eng.filter_batch_into(n, xp, up, u2, r2, c2)
+    assert np.array_equal(u2, u) and np.array_equal(r2, relax) and np.array_equal(c2, rc)
+    # another filter class through the same entry point
+    x4, ud4 = cf.c4_inputs(300_001)
+    e4 = ab.Engine(ab.FILTER_REALIZABLE, ab.MODEL_INVERTED_PENDULUM_KERNEL, **cf.realizable_engine_kwargs(cf.C4_OPTS))
+    monkeypatch.setenv("ASIF_B200_HOST_IO", "staged")
+    u4, r4, c4 = e4.filter_batch(x4, ud4)
+    monkeypatch.setenv("ASIF_B200_HOST_IO", mode)
+    a4 = torch.empty(u4.shape, dtype=torch.float64).pin_memory()
+    b4 = torch.empty(r4.shape, dtype=torch.float64).pin_memory()
+    d4 = torch.empty(c4.shape, dtype=torch.int32).pin_memory()
+    e4.filter_batch_into(x4.shape[0], torch.from_numpy(x4).pin_memory(), torch.from_numpy(ud4).pin_memory(), a4, b4, d4)
+    assert np.array_equal(a4.numpy(), u4) and np.array_equal(b4.numpy(), r4) and np.array_equal(d4.numpy(), c4)
