@@ -99,6 +99,11 @@ def load_library():
     L.asif_engine_rollout.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_double, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.c_int32, C.c_void_p]
     L.asif_engine_last_qp_iterations.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+    L.asif_engine_last_host_io.argtypes = [C.c_void_p, C.POINTER(C.c_int32)]
+    L.asif_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_uint64]
+    L.asif_host_free.argtypes = [C.c_void_p]
+    L.asif_host_register.argtypes = [C.c_void_p, C.c_uint64]
+    L.asif_host_unregister.argtypes = [C.c_void_p]
     L.asif_engine_set_learning.argtypes = [C.c_void_p, C.POINTER(LearningData)]
     L.asif_loop_config_init.argtypes = [C.POINTER(LoopConfig)]
     L.asif_engine_loop_log_dims.argtypes = [C.c_void_p, C.POINTER(LoopConfig), C.POINTER(C.c_int64)]
@@ -324,10 +329,45 @@ class Engine:
         assert pos == b.size, "blob length does not match the layer widths"
         _check(L.asif_engine_set_learning(self._h, C.byref(ld)))
 
+    def last_host_io(self):
+        """HOST_IO_STAGED / HOST_IO_OUT / HOST_IO_INOUT of the last host-memory batch, -1 before the first one."""
+        v = C.c_int32()
+        _check(load_library().asif_engine_last_host_io(self._h, C.byref(v)))
+        return int(v.value)
+
     def last_qp_iterations(self):
         v = C.c_uint64()
         _check(load_library().asif_engine_last_qp_iterations(self._h, C.byref(v)))
         return int(v.value)
+
+
+HOST_IO_STAGED, HOST_IO_OUT, HOST_IO_INOUT = 0, 1, 2
+
+
+class PinnedArray:
+    """numpy view of memory from asif_host_alloc (pinned, device-addressable); free() or the destructor releases it."""
+
+    def __init__(self, shape, dtype=np.float64):
+        shape = (shape,) if np.isscalar(shape) else tuple(shape)
+        dt = np.dtype(dtype)
+        nbytes = int(np.prod(shape, dtype=np.int64)) * dt.itemsize
+        p = C.c_void_p()
+        _check(load_library().asif_host_alloc(C.byref(p), nbytes))
+        self._p = p.value
+        buf = (C.c_char * nbytes).from_address(self._p) if nbytes else b""
+        self.array = np.frombuffer(buf, dtype=dt).reshape(shape)
+
+    def free(self):
+        if getattr(self, "_p", None):
+            self.array = None
+            load_library().asif_host_free(self._p)
+            self._p = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
 
 
 def qp_solve_batch(H, c, A, b, lb, ub, be=None, diagonal_cost=True, device=0):

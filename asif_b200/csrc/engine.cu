@@ -769,12 +769,14 @@ int32_t filter_batch_impl(asif_engine *e, int64_t n, const double *x, const doub
 		m_diag = diag ? mapped_alias(diag, (size_t)n * nd) : nullptr;
 	}
 	const bool direct_out = m_ua && m_relax && m_rc && (!diag || m_diag);
+	e->last_host_io = direct_out ? ASIF_HOST_IO_OUT : ASIF_HOST_IO_STAGED;
 	if (io == 2 && direct_out) {
 		const double *m_x = mapped_alias(x, (size_t)n * nx), *m_ud = mapped_alias(u_des, (size_t)n * cw);
 		if (m_x && m_ud) {
 			if (!e->slot[0].stream) CUDA_TRY(cudaStreamCreateWithFlags(&e->slot[0].stream, cudaStreamNonBlocking));
 			e->ex.lfh = e->lie_lfh;
 			e->ex.lgh = e->lie_lgh;
+			e->last_host_io = ASIF_HOST_IO_INOUT;
 			const int r = launch_filter(e, n, m_x, m_ud, m_ua, m_relax, m_rc, m_diag, e->slot[0].stream);
 			if (r) return r;
 			CUDA_TRY(cudaStreamSynchronize(e->slot[0].stream));
@@ -1011,6 +1013,42 @@ int32_t asif_engine_set_learning(asif_engine *e, const asif_learning_data *d)
 	}
 	L.blob = e->d_learn;
 	e->im.learn = L;
+	return ASIF_OK;
+}
+
+int32_t asif_engine_last_host_io(const asif_engine *e, int32_t *mode)
+{
+	if (!e || !mode) return fail(ASIF_ERR_INVALID_ARGUMENT, "NULL argument");
+	*mode = e->last_host_io;
+	return ASIF_OK;
+}
+
+int32_t asif_host_alloc(void **p, uint64_t bytes)
+{
+	if (!p) return fail(ASIF_ERR_INVALID_ARGUMENT, "NULL argument");
+	*p = nullptr;
+	if (!bytes) return ASIF_OK;
+	CUDA_TRY(cudaHostAlloc(p, (size_t)bytes, cudaHostAllocPortable | cudaHostAllocMapped));
+	return ASIF_OK;
+}
+
+int32_t asif_host_free(void *p)
+{
+	if (p) CUDA_TRY(cudaFreeHost(p));
+	return ASIF_OK;
+}
+
+int32_t asif_host_register(void *p, uint64_t bytes)
+{
+	if (!p || !bytes) return fail(ASIF_ERR_INVALID_ARGUMENT, "NULL or empty range");
+	CUDA_TRY(cudaHostRegister(p, (size_t)bytes, cudaHostRegisterPortable | cudaHostRegisterMapped));
+	return ASIF_OK;
+}
+
+int32_t asif_host_unregister(void *p)
+{
+	if (!p) return fail(ASIF_ERR_INVALID_ARGUMENT, "NULL argument");
+	CUDA_TRY(cudaHostUnregister(p));
 	return ASIF_OK;
 }
 

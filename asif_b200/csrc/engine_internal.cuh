@@ -76,6 +76,7 @@ struct asif_engine {
 	cudaStream_t stream = nullptr; // device-memory calls without a caller stream
 	unsigned long long *d_counters = nullptr; // [0] qp rows processed, [1..8] rc histogram
 	uint64_t last_qp_rows = 0;
+	int last_host_io = -1; // ASIF_HOST_IO_* actually used by the last host-memory batch (-1: none yet)
 	int num_sms = 148;
 	// snapshot scratch of the persistent nx = 4 kernels: a ring, so that launches on different streams never share
 	// a buffer that may still be in use (the next user waits on the previous user's event)

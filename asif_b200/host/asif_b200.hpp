@@ -61,6 +61,55 @@ namespace ASIF
 	};
 #endif
 
+	namespace b200
+	{
+		// Pinned, device-addressable host array for the filterBatch arguments (asif_host_alloc): with such arrays the
+		// engine overlaps transfers with the kernels or lets the kernels read and write them in place.  Move-only.
+		template <class T>
+		class PinnedBuffer
+		{
+		public:
+			PinnedBuffer(void) : p_(nullptr), n_(0) {}
+			explicit PinnedBuffer(const size_t n) : p_(nullptr), n_(0) { resize(n); }
+			PinnedBuffer(const PinnedBuffer &) = delete;
+			PinnedBuffer &operator=(const PinnedBuffer &) = delete;
+			PinnedBuffer(PinnedBuffer &&o) noexcept : p_(o.p_), n_(o.n_) { o.p_ = nullptr, o.n_ = 0; }
+			PinnedBuffer &operator=(PinnedBuffer &&o) noexcept
+			{
+				if (this != &o) {
+					release();
+					p_ = o.p_, n_ = o.n_;
+					o.p_ = nullptr, o.n_ = 0;
+				}
+				return *this;
+			}
+			~PinnedBuffer(void) { release(); }
+			// returns 0, or the negative code of asif_host_alloc (contents are not kept)
+			int32_t resize(const size_t n)
+			{
+				release();
+				void *q = nullptr;
+				const int32_t r = asif_host_alloc(&q, (uint64_t)n * sizeof(T));
+				if (r == 0) p_ = static_cast<T *>(q), n_ = n;
+				return r;
+			}
+			T *data(void) { return p_; }
+			const T *data(void) const { return p_; }
+			size_t size(void) const { return n_; }
+			T &operator[](const size_t i) { return p_[i]; }
+			const T &operator[](const size_t i) const { return p_[i]; }
+
+		private:
+			void release(void)
+			{
+				if (p_) asif_host_free(p_);
+				p_ = nullptr, n_ = 0;
+			}
+			T *p_;
+			size_t n_;
+		};
+	} // namespace b200
+
 	// A QPWrapperAbstract whose solve() runs on the B200 (asif_qp_solve_batch with n = 1).
 	// Argument meaning, copies and return values follow QPWrapperOsqp (src/qpwrapper_osqp.cpp:55-261):
 	// initialize() returns 0 on success (the polarity of osqp_setup, :121), the update*() calls return 1,

@@ -9,6 +9,7 @@
 #include <string>
 
 #include <cstdio>
+#include <cstring>
 #include <memory>
 
 static int fail(const char *what)
@@ -84,6 +85,16 @@ int main()
 		if (asif.filterBatch(n, X.data(), U.data(), UA.data(), R.data(), rc.data()) != 0) return fail("filterBatch");
 		for (int i = 0; i < n; i++)
 			if (rc[i] == 1 && (UA[i] > 1.0 || UA[i] < -1.0)) return fail("uAct outside bounds");
+		// the same batch from pinned buffers (asif_host_alloc): the same bits
+		b200::PinnedBuffer<double> Xp(2 * n), Up(n), UAp(n), Rp(n);
+		b200::PinnedBuffer<int32_t> rcp(n);
+		if (!Xp.data() || !rcp.data()) return fail("PinnedBuffer");
+		std::memcpy(Xp.data(), X.data(), sizeof(double) * 2 * n);
+		std::memcpy(Up.data(), U.data(), sizeof(double) * n);
+		if (asif.filterBatch(n, Xp.data(), Up.data(), UAp.data(), Rp.data(), rcp.data()) != 0) return fail("filterBatch (pinned)");
+		if (std::memcmp(UAp.data(), UA.data(), sizeof(double) * n) || std::memcmp(Rp.data(), R.data(), sizeof(double) * n) ||
+		    std::memcmp(rcp.data(), rc.data(), sizeof(int32_t) * n))
+			return fail("pinned and pageable batches differ");
 	}
 	// --- 4. implicit and robust classes compile against the same surface and run one batch each
 	{

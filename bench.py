@@ -331,7 +331,7 @@ def main():
         "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(world),
         "e2e": {"value": e2e_value, "unit": "states/s", "h2d_bytes_per_step": 24 * n, "d2h_bytes_per_step": 20 * n,
                 "ms_per_step": 1e3 * e2e_s / args.steps, "matches_device_resident": same, "host_binding": numa,
-                "host_io": os.environ.get("ASIF_B200_HOST_IO", "auto (inout for this filter class)")},
+                "host_io": {0: "staged", 1: "out", 2: "inout"}.get(eng.last_host_io(), "?") + " (ASIF_B200_HOST_IO=%s)" % os.environ.get("ASIF_B200_HOST_IO", "auto")},
         "gpu_launches": args.steps,
         "roofline": {"bound": "fp64", "achieved": ach_tf, "peak": p64_tflops, "unit": "TFLOP/s", "frac": ach_tf / p64_tflops,
                      "traffic": traffic, "kernel": "tb_filter_kernel<DoubleIntegratorTB,4,false>",

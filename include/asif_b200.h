@@ -59,6 +59,11 @@ extern "C" {
                            * bits in every mode) */
 #define ASIF_MEM_DEVICE 1 /* all batch pointers are device memory on the engine's device; nothing is copied */
 
+/* how a host-memory batch reached the kernels (asif_engine_last_host_io) */
+#define ASIF_HOST_IO_STAGED 0 /* chunked H2D copy, kernel, D2H copy */
+#define ASIF_HOST_IO_OUT 1    /* chunked H2D copies; the kernels store into the caller's pinned output arrays */
+#define ASIF_HOST_IO_INOUT 2  /* one launch reading and writing the caller's pinned arrays over PCIe */
+
 typedef struct asif_engine asif_engine;
 
 /*
@@ -139,6 +144,21 @@ int32_t asif_engine_dims(const asif_engine *e, int32_t dims[6]);
  */
 int32_t asif_engine_filter_batch(asif_engine *e, int64_t n, const double *x, const double *u_des, double *u_act,
                                  double *relax, int32_t *rc, double *diag, int32_t mem, void *stream);
+
+/*
+ * Pinned host memory for the batch arrays of ASIF_MEM_HOST calls.  The reference copies caller arrays into its own
+ * new[] buffers (src/asif.cpp:27-34, src/qpwrapper_osqp.cpp:14-29); a batch of 1e7 states is 440 MB per call, so the
+ * caller's arrays are used in place instead, and they are fastest when the device can address them:
+ * asif_host_alloc returns such memory (cudaHostAlloc, portable + mapped), asif_host_register pins and maps a range the
+ * caller already owns (page-aligned ranges register fastest; unregister before freeing it).  Pageable arrays work too,
+ * through staged copies.  asif_engine_last_host_io reports which ASIF_HOST_IO_* path the last host batch took
+ * (-1 before the first one).
+ */
+int32_t asif_host_alloc(void **p, uint64_t bytes);
+int32_t asif_host_free(void *p);
+int32_t asif_host_register(void *p, uint64_t bytes);
+int32_t asif_host_unregister(void *p);
+int32_t asif_engine_last_host_io(const asif_engine *e, int32_t *mode);
 
 /*
  * The filter(x, H, c, uAct[, relax]) overloads (src/asif_implicit_tb.cpp:252-363, src/asif.cpp:153-210,

@@ -138,3 +138,49 @@ def test_pinned_host_io_modes_match_pageable(ab, mode, monkeypatch):
     d4 = torch.empty(c4.shape, dtype=torch.int32).pin_memory()
     e4.filter_batch_into(x4.shape[0], torch.from_numpy(x4).pin_memory(), torch.from_numpy(ud4).pin_memory(), a4, b4, d4)
     assert np.array_equal(a4.numpy(), u4) and np.array_equal(b4.numpy(), r4) and np.array_equal(d4.numpy(), c4)
+
+
+def test_pinned_arrays_of_the_c_abi_take_the_direct_path(ab, monkeypatch):
+    """asif_host_alloc memory is device-addressable: the TB filter reads and writes it in place (auto -> inout), the
+    explicit filter stages it (auto -> staged), pageable numpy arrays are always staged; a range pinned with
+    asif_host_register behaves like allocated memory.  Same bits every way."""
+    monkeypatch.delenv("ASIF_B200_HOST_IO", raising=False)
+    import ctypes as C
+    L = ab.load_library()
+    n = 200_003
+    x, ud = cf.c2_inputs(n, seed=21)
+    eng = ab.Engine(ab.FILTER_IMPLICIT_TB, ab.MODEL_DOUBLE_INTEGRATOR_TB, **cf.tb_engine_kwargs(cf.C2_TB_OPTS))
+    assert eng.last_host_io() == -1
+    u, relax, rc = eng.filter_batch(x, ud)
+    assert eng.last_host_io() == ab.HOST_IO_STAGED
+    bufs = [ab.PinnedArray((n, 2)), ab.PinnedArray((n, 1)), ab.PinnedArray((n, 1)), ab.PinnedArray((n, 1)), ab.PinnedArray(n, np.int32)]
+    xp, up, ua, rl, rcp = (b.array for b in bufs)
+    xp[:], up[:] = x, ud
+    eng.filter_batch_into(n, xp, up, ua, rl, rcp)
+    assert eng.last_host_io() == ab.HOST_IO_INOUT
+    assert np.array_equal(ua, u) and np.array_equal(rl, relax) and np.array_equal(rcp, rc)
+    # pinned outputs, pageable inputs: the kernels still store in place, the inputs are copied
+    ua[:], rcp[:] = np.nan, -99
+    eng.filter_batch_into(n, x, ud, ua, rl, rcp)
+    assert eng.last_host_io() == ab.HOST_IO_OUT
+    assert np.array_equal(ua, u) and np.array_equal(rcp, rc)
+    # explicit filter: staged by default even with pinned arrays
+    e1 = ab.Engine(ab.FILTER_EXPLICIT, ab.MODEL_DOUBLE_INTEGRATOR)
+    u1, r1, c1 = e1.filter_batch(x, ud)
+    e1.filter_batch_into(n, xp, up, ua, rl, rcp)
+    assert e1.last_host_io() == ab.HOST_IO_STAGED
+    assert np.array_equal(ua, u1) and np.array_equal(rl, r1) and np.array_equal(rcp, c1)
+    # registering a caller-owned range
+    own = [np.zeros((n, 2)), np.zeros((n, 1)), np.zeros((n, 1)), np.zeros((n, 1)), np.zeros(n, dtype=np.int32)]
+    own[0][:], own[1][:] = x, ud
+    for a in own:
+        ab.capi._check(L.asif_host_register(a.ctypes.data, a.nbytes))
+    try:
+        eng.filter_batch_into(n, *own)
+        assert eng.last_host_io() == ab.HOST_IO_INOUT
+        assert np.array_equal(own[2], u) and np.array_equal(own[3], relax) and np.array_equal(own[4], rc)
+    finally:
+        for a in own:
+            assert L.asif_host_unregister(a.ctypes.data) == 0
+    for b in bufs:
+        b.free()
