@@ -658,6 +658,7 @@ int32_t asif_engine_destroy(asif_engine *e)
 			cudaStreamDestroy(s.stream);
 		}
 		cudaFree(s.x); cudaFree(s.ud); cudaFree(s.ua); cudaFree(s.relax); cudaFree(s.rc); cudaFree(s.diag);
+		if (s.h) cudaFreeHost(s.h);
 	}
 	if (e->stream) {
 		cudaStreamSynchronize(e->stream);
@@ -672,6 +673,7 @@ int32_t asif_engine_destroy(asif_engine *e)
 	cudaFree(e->d_learn);
 	cudaFree(e->d_kernel);
 	cudaFree(e->d_ttable);
+	delete e->copier;
 	delete e;
 	return ASIF_OK;
 }
@@ -702,6 +704,23 @@ T *mapped_alias(const T *p, size_t count)
 	if (reinterpret_cast<const char *>(a1.devicePointer) - reinterpret_cast<const char *>(a0.devicePointer) != last - reinterpret_cast<const char *>(p))
 		return nullptr; // first and last byte are not in one mapping
 	return reinterpret_cast<T *>(a0.devicePointer);
+}
+
+// plain (unregistered) host memory: what cudaMemcpyAsync would stage through the driver's own bounce buffer
+bool is_pageable(const void *p)
+{
+	cudaPointerAttributes a;
+	if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+		cudaGetLastError();
+		return false;
+	}
+	return a.type == cudaMemoryTypeUnregistered;
+}
+
+bool bounce_enabled()
+{
+	const char *v = getenv("ASIF_B200_BOUNCE");
+	return !(v && v[0] == '0');
 }
 
 // ASIF_B200_HOST_IO: how a host-memory batch reaches the kernels.
@@ -783,6 +802,30 @@ int32_t filter_batch_impl(asif_engine *e, int64_t n, const double *x, const doub
 			return ASIF_OK;
 		}
 	}
+	// Pageable caller arrays (plain new[] / std::vector / numpy memory): a pageable cudaMemcpyAsync is staged by the
+	// driver on the calling thread (measured 11 GB/s), so large batches bounce through pinned staging buffers of the
+	// slots instead, filled and drained by a few host threads (host_copier.hpp); ASIF_B200_BOUNCE=0 switches it off.
+	const size_t out_row = sizeof(double) * (nu + nr + (diag ? nd : 0)) + sizeof(int32_t), in_row = sizeof(double) * (nx + cw);
+	bool bounce_in = false, bounce_out = false;
+	if ((size_t)n * (in_row + out_row) >= ((size_t)8 << 20) && bounce_enabled()) {
+		bounce_in = is_pageable(x) && is_pageable(u_des);
+		bounce_out = !direct_out && is_pageable(u_act) && is_pageable(relax) && is_pageable(rc) && (!diag || is_pageable(diag));
+		if ((bounce_in || bounce_out) && !e->copier) e->copier = new HostCopier(HostCopier::default_threads());
+	}
+	const size_t h_x = 0, h_ud = h_x + sizeof(double) * chunk * nx, h_ua = h_ud + sizeof(double) * chunk * e->nv,
+	             h_relax = h_ua + sizeof(double) * chunk * nu, h_diag = h_relax + sizeof(double) * chunk * nr,
+	             h_rc = h_diag + (diag ? sizeof(double) * chunk * nd : 0), h_bytes = h_rc + sizeof(int32_t) * chunk;
+	auto copy_out = [&](Slot &s) { // results of the slot's last chunk: staging -> caller arrays
+		if (!s.pend_m) return;
+		const int64_t o = s.pend_off, c = s.pend_m;
+		HostCopier::Piece jobs[4] = {{u_act + o * nu, s.h + h_ua, sizeof(double) * c * nu},
+		                             {relax + o * nr, s.h + h_relax, sizeof(double) * c * nr},
+		                             {rc + o, s.h + h_rc, sizeof(int32_t) * c},
+		                             {diag ? diag + o * nd : nullptr, s.h + h_diag, diag ? sizeof(double) * c * nd : 0}};
+		e->copier->copy(jobs, diag ? 4 : 3);
+		s.pend_m = 0;
+	};
+	for (Slot &s : e->slot) s.pend_m = 0;
 	int si = 0;
 	// Chunk schedule: the pipeline's fill (first H2D + first kernel) and drain (last kernel + last D2H) are not overlapped
 	// with anything, so the first two and the last two chunks are a quarter and a half of the steady-state size
@@ -807,10 +850,24 @@ int32_t filter_batch_impl(asif_engine *e, int64_t n, const double *x, const doub
 		if (m > left) m = left;
 		Slot &s = e->slot[si];
 		if (s.stream) CUDA_TRY(cudaStreamSynchronize(s.stream)); // slot buffers free again
+		if (bounce_out) copy_out(s);
 		int r = ensure_slot(e, s, chunk, diag != nullptr && !direct_out);
 		if (r) return r;
-		CUDA_TRY(cudaMemcpyAsync(s.x, x + off * nx, sizeof(double) * m * nx, cudaMemcpyHostToDevice, s.stream));
-		CUDA_TRY(cudaMemcpyAsync(s.ud, u_des + off * cw, sizeof(double) * m * cw, cudaMemcpyHostToDevice, s.stream));
+		if ((bounce_in || bounce_out) && s.h_cap < h_bytes) {
+			if (s.h) cudaFreeHost(s.h);
+			s.h = nullptr, s.h_cap = 0;
+			CUDA_TRY(cudaHostAlloc((void **)&s.h, h_bytes, cudaHostAllocDefault));
+			s.h_cap = h_bytes;
+		}
+		const double *src_x = x + off * nx, *src_ud = u_des + off * cw;
+		if (bounce_in) {
+			HostCopier::Piece jobs[2] = {{s.h + h_x, src_x, sizeof(double) * m * nx}, {s.h + h_ud, src_ud, sizeof(double) * m * cw}};
+			e->copier->copy(jobs, 2);
+			src_x = reinterpret_cast<const double *>(s.h + h_x);
+			src_ud = reinterpret_cast<const double *>(s.h + h_ud);
+		}
+		CUDA_TRY(cudaMemcpyAsync(s.x, src_x, sizeof(double) * m * nx, cudaMemcpyHostToDevice, s.stream));
+		CUDA_TRY(cudaMemcpyAsync(s.ud, src_ud, sizeof(double) * m * cw, cudaMemcpyHostToDevice, s.stream));
 		e->ex.lfh = e->lie_lfh ? e->lie_lfh + off * e->nc : nullptr; // device copies of the whole batch (filter_batch_lie)
 		e->ex.lgh = e->lie_lgh ? e->lie_lgh + off * e->nc * e->nu : nullptr;
 		if (direct_out) {
@@ -820,13 +877,24 @@ int32_t filter_batch_impl(asif_engine *e, int64_t n, const double *x, const doub
 		}
 		r = launch_filter(e, m, s.x, s.ud, s.ua, s.relax, s.rc, diag ? s.diag : nullptr, s.stream);
 		if (r) return r;
+		if (bounce_out) {
+			CUDA_TRY(cudaMemcpyAsync(s.h + h_ua, s.ua, sizeof(double) * m * nu, cudaMemcpyDeviceToHost, s.stream));
+			CUDA_TRY(cudaMemcpyAsync(s.h + h_relax, s.relax, sizeof(double) * m * nr, cudaMemcpyDeviceToHost, s.stream));
+			CUDA_TRY(cudaMemcpyAsync(s.h + h_rc, s.rc, sizeof(int32_t) * m, cudaMemcpyDeviceToHost, s.stream));
+			if (diag) CUDA_TRY(cudaMemcpyAsync(s.h + h_diag, s.diag, sizeof(double) * m * nd, cudaMemcpyDeviceToHost, s.stream));
+			s.pend_off = off, s.pend_m = m;
+			continue;
+		}
 		CUDA_TRY(cudaMemcpyAsync(u_act + off * nu, s.ua, sizeof(double) * m * nu, cudaMemcpyDeviceToHost, s.stream));
 		CUDA_TRY(cudaMemcpyAsync(relax + off * nr, s.relax, sizeof(double) * m * nr, cudaMemcpyDeviceToHost, s.stream));
 		CUDA_TRY(cudaMemcpyAsync(rc + off, s.rc, sizeof(int32_t) * m, cudaMemcpyDeviceToHost, s.stream));
 		if (diag) CUDA_TRY(cudaMemcpyAsync(diag + off * nd, s.diag, sizeof(double) * m * nd, cudaMemcpyDeviceToHost, s.stream));
 	}
-	for (Slot &s : e->slot)
+	for (int k = 0; k < N_SLOTS; k++, si = (si + 1) % N_SLOTS) { // oldest chunk first
+		Slot &s = e->slot[si];
 		if (s.stream) CUDA_TRY(cudaStreamSynchronize(s.stream));
+		if (bounce_out) copy_out(s);
+	}
 	return ASIF_OK;
 }
 } // namespace

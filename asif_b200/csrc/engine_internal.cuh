@@ -23,6 +23,8 @@ int fail(int code, const char *fmt, ...);
 }
 using asifb::fail;
 
+#include "host_copier.hpp"
+
 namespace {
 
 #define CUDA_TRY(expr)                                                                                         \
@@ -54,6 +56,11 @@ struct Slot {
 	double *x = nullptr, *ud = nullptr, *ua = nullptr, *relax = nullptr, *diag = nullptr;
 	int32_t *rc = nullptr;
 	int64_t cap = 0, cap_diag = 0;
+	// pinned staging for pageable caller arrays (bounce path): [x | ud | ua | relax | diag | rc], and the chunk whose
+	// results sit in it waiting to be copied out
+	char *h = nullptr;
+	size_t h_cap = 0;
+	int64_t pend_off = 0, pend_m = 0;
 };
 
 } // namespace
@@ -76,6 +83,7 @@ struct asif_engine {
 	cudaStream_t stream = nullptr; // device-memory calls without a caller stream
 	unsigned long long *d_counters = nullptr; // [0] qp rows processed, [1..8] rc histogram
 	uint64_t last_qp_rows = 0;
+	HostCopier *copier = nullptr; // created by the first large pageable batch
 	int last_host_io = -1; // ASIF_HOST_IO_* actually used by the last host-memory batch (-1: none yet)
 	int num_sms = 148;
 	// snapshot scratch of the persistent nx = 4 kernels: a ring, so that launches on different streams never share

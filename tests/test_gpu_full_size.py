@@ -184,3 +184,35 @@ def test_pinned_arrays_of_the_c_abi_take_the_direct_path(ab, monkeypatch):
             assert L.asif_host_unregister(a.ctypes.data) == 0
     for b in bufs:
         b.free()
+
+
+def test_pageable_bounce_path_matches_driver_staging(ab, monkeypatch):
+    """Large pageable batches go through the slots' pinned staging buffers, filled and drained by host threads
+    (csrc/host_copier.hpp); ASIF_B200_BOUNCE=0 leaves the staging to the driver.  Same bits, with and without the diag
+    record, with pinned inputs and pageable outputs, and for the (x, c) overload whose second array is nv wide."""
+    monkeypatch.delenv("ASIF_B200_HOST_IO", raising=False)
+    n = 4 * (1 << 19) + 54_321
+    x, ud = cf.c2_inputs(n, seed=31)
+    eng = ab.Engine(ab.FILTER_IMPLICIT_TB, ab.MODEL_DOUBLE_INTEGRATOR_TB, **cf.tb_engine_kwargs(cf.C2_TB_OPTS))
+    monkeypatch.setenv("ASIF_B200_BOUNCE", "0")
+    ref = eng.filter_batch(x, ud, want_diag=True)
+    c = np.concatenate([-2.0 * ud, np.full((n, 1), -2.0 * cf.C2_TB_OPTS[0] * cf.C2_TB_OPTS[1])], axis=1)
+    ref_c = eng.filter_batch_cost(x, c)
+    monkeypatch.delenv("ASIF_B200_BOUNCE")
+    for want_diag in (True, False):
+        out = eng.filter_batch(x, ud, want_diag=want_diag)
+        assert eng.last_host_io() == ab.HOST_IO_STAGED
+        for a, b in zip(out, ref):
+            assert np.array_equal(a, b, equal_nan=True)
+    out_c = eng.filter_batch_cost(x, c)
+    for a, b in zip(out_c, ref_c):
+        assert np.array_equal(a, b)
+    for a, b in zip(ref_c, ref[:3]):  # the (x, c) overload with updateCost's own c is filter(x, uDes)
+        assert np.array_equal(a, b)
+    # pinned inputs, pageable outputs
+    xp, up = ab.PinnedArray((n, 2)), ab.PinnedArray((n, 1))
+    xp.array[:], up.array[:] = x, ud
+    u, relax, rc = np.empty((n, 1)), np.empty((n, 1)), np.empty(n, dtype=np.int32)
+    eng.filter_batch_into(n, xp.array, up.array, u, relax, rc)
+    assert np.array_equal(u, ref[0]) and np.array_equal(relax, ref[1]) and np.array_equal(rc, ref[2])
+    xp.free(), up.free()

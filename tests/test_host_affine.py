@@ -35,3 +35,12 @@ def test_facet_table_matches_libaffa(tmp_path):
     assert np.abs(table - ref).max() <= 1e-15, np.abs(table - ref).max()
     # the intervals are not degenerate: the least-squares sine and the gain interval both contribute
     assert np.median(ref[:, :, 1] - ref[:, :, 0]) > 1e-2 and np.median(ref[:, :, 3] - ref[:, :, 2]) > 1e-2
+
+
+def test_host_copier_threads_copy_every_byte():
+    """csrc/host_copier.hpp (the pool that moves pageable caller arrays through pinned staging): 1200 copy() calls of
+    random shapes with 1 / 2 / 5 / 8 threads, compared byte for byte (asif_b200/host/host_copier_check.cpp)."""
+    host = os.path.join(cf.ROOT, "asif_b200", "host")
+    subprocess.check_call(["make", "-C", host, "-s", "host_copier_check"])
+    r = subprocess.run([os.path.join(host, "host_copier_check")], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "host_copier ok" in r.stdout, r.stdout + r.stderr
