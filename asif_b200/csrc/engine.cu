@@ -673,6 +673,7 @@ int32_t asif_engine_destroy(asif_engine *e)
 	cudaFree(e->d_learn);
 	cudaFree(e->d_kernel);
 	cudaFree(e->d_ttable);
+	if (e->small_h) cudaFreeHost(e->small_h);
 	delete e->copier;
 	delete e;
 	return ASIF_OK;
@@ -715,6 +716,12 @@ bool is_pageable(const void *p)
 		return false;
 	}
 	return a.type == cudaMemoryTypeUnregistered;
+}
+
+bool small_inplace_enabled()
+{
+	const char *v = getenv("ASIF_B200_SMALL_INPLACE");
+	return !(v && v[0] == '0');
 }
 
 bool bounce_enabled()
@@ -775,6 +782,36 @@ int32_t filter_batch_impl(asif_engine *e, int64_t n, const double *x, const doub
 	// host memory: chunks rotate over N_SLOTS streams so that the H2D copy of chunk i+1, the kernel of
 	// chunk i and the D2H copy of chunk i-1 overlap (they do when the caller's buffers are pinned)
 	const int nx = e->nx, nu = e->nu, nr = e->n_relax, nd = e->n_diag;
+	// Small batches (the single-state filter() of the host classes above all): five pageable copies and a kernel cost six
+	// driver calls that each wait for the one before.  Instead the arrays are copied by the CPU into a pinned scratch the
+	// device can address, one launch reads and writes it over PCIe, one synchronise, and the results are copied back.
+	// ASIF_B200_SMALL_INPLACE=0 switches it off.
+	{
+		const size_t o_x = 0, o_ud = o_x + sizeof(double) * n * nx, o_ua = o_ud + sizeof(double) * n * cw,
+		             o_relax = o_ua + sizeof(double) * n * nu, o_diag = o_relax + sizeof(double) * n * nr,
+		             o_rc = o_diag + (diag ? sizeof(double) * n * nd : 0), total = o_rc + sizeof(int32_t) * n;
+		if (total <= SMALL_BATCH_BYTES && small_inplace_enabled()) {
+			if (!e->small_h) CUDA_TRY(cudaHostAlloc((void **)&e->small_h, SMALL_BATCH_BYTES, cudaHostAllocMapped));
+			if (!e->slot[0].stream) CUDA_TRY(cudaStreamCreateWithFlags(&e->slot[0].stream, cudaStreamNonBlocking));
+			cudaStream_t st = e->slot[0].stream;
+			char *h = e->small_h;
+			memcpy(h + o_x, x, sizeof(double) * n * nx);
+			memcpy(h + o_ud, u_des, sizeof(double) * n * cw);
+			CUDA_TRY(cudaMemsetAsync(e->d_counters, 0, sizeof(unsigned long long), st));
+			e->ex.lfh = e->lie_lfh;
+			e->ex.lgh = e->lie_lgh;
+			e->last_host_io = ASIF_HOST_IO_INOUT;
+			const int r = launch_filter(e, n, (const double *)(h + o_x), (const double *)(h + o_ud), (double *)(h + o_ua),
+			                            (double *)(h + o_relax), (int32_t *)(h + o_rc), diag ? (double *)(h + o_diag) : nullptr, st);
+			if (r) return r;
+			CUDA_TRY(cudaStreamSynchronize(st));
+			memcpy(u_act, h + o_ua, sizeof(double) * n * nu);
+			memcpy(relax, h + o_relax, sizeof(double) * n * nr);
+			memcpy(rc, h + o_rc, sizeof(int32_t) * n);
+			if (diag) memcpy(diag, h + o_diag, sizeof(double) * n * nd);
+			return ASIF_OK;
+		}
+	}
 	// batches under four full chunks are cut in four (not below 2^16 states), so that their copies overlap too:
 	// 1e6 states, staged, 2^19 -> 2^18: C1 0.73 -> 0.68 ms, C3b 1.02 -> 0.81 ms, C4 1.40 -> 1.19 ms
 	int64_t chunk = chunk_states();

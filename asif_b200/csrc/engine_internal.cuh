@@ -34,6 +34,7 @@ namespace {
 			return fail(ASIF_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
 	} while (0)
 
+constexpr size_t SMALL_BATCH_BYTES = 64 << 10; // host batches up to this size run in place on the engine's mapped scratch
 constexpr int N_SLOTS = 4;               // pipeline depth of the host-memory path
 constexpr int64_t CHUNK_STATES = 1 << 19; // states per pipeline chunk (env ASIF_B200_CHUNK_STATES overrides); measured
                                           // e2e for 1e7 C2 states: 2^17 6.7 ms, 2^18 6.1, 2^19 5.7, 2^20 6.1, 2^21 6.3
@@ -84,6 +85,7 @@ struct asif_engine {
 	unsigned long long *d_counters = nullptr; // [0] qp rows processed, [1..8] rc histogram
 	uint64_t last_qp_rows = 0;
 	HostCopier *copier = nullptr; // created by the first large pageable batch
+	char *small_h = nullptr;      // pinned, device-addressable scratch of the small-batch path (SMALL_BATCH_BYTES)
 	int last_host_io = -1; // ASIF_HOST_IO_* actually used by the last host-memory batch (-1: none yet)
 	int num_sms = 148;
 	// snapshot scratch of the persistent nx = 4 kernels: a ring, so that launches on different streams never share

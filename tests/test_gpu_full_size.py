@@ -216,3 +216,23 @@ def test_pageable_bounce_path_matches_driver_staging(ab, monkeypatch):
     eng.filter_batch_into(n, xp.array, up.array, u, relax, rc)
     assert np.array_equal(u, ref[0]) and np.array_equal(relax, ref[1]) and np.array_equal(rc, ref[2])
     xp.free(), up.free()
+
+
+def test_small_batches_in_place_match_the_copy_path(ab, monkeypatch):
+    """Host batches up to 64 KB (the single-state filter() calls above all) run in place on the engine's mapped scratch:
+    same bits as the copy path, with and without the diag record, at the size limit and just past it."""
+    monkeypatch.delenv("ASIF_B200_HOST_IO", raising=False)
+    x, ud = cf.c2_inputs(3000, seed=41)
+    eng = ab.Engine(ab.FILTER_IMPLICIT_TB, ab.MODEL_DOUBLE_INTEGRATOR_TB, **cf.tb_engine_kwargs(cf.C2_TB_OPTS))
+    row = 44
+    for n in (1, 2, 31, 33, 1000, (64 << 10) // row, (64 << 10) // row + 1, 3000):
+        for want_diag in (False, True):
+            monkeypatch.setenv("ASIF_B200_SMALL_INPLACE", "0")
+            ref = eng.filter_batch(x[:n], ud[:n], want_diag=want_diag)
+            assert eng.last_host_io() == ab.HOST_IO_STAGED
+            monkeypatch.setenv("ASIF_B200_SMALL_INPLACE", "1")
+            out = eng.filter_batch(x[:n], ud[:n], want_diag=want_diag)
+            small = n * (row + (8 * eng.n_diag if want_diag else 0)) <= (64 << 10)
+            assert eng.last_host_io() == (ab.HOST_IO_INOUT if small else ab.HOST_IO_STAGED)
+            for a, b in zip(out, ref):
+                assert np.array_equal(a, b, equal_nan=True)
