@@ -274,6 +274,11 @@ implicit_filter_kernel(const ImplicitParams p, const int64_t n, const double *__
 	}
 	key[0] = hSafetyNow;
 	kidx[0] = 0;
+	int pk[CAP]; // (trajectory index << 4) | snapshot slot of the sorted entries; -1 index = empty
+#pragma unroll
+	for (int s = 0; s < CAP; s++) pk[s] = (int)(0xFFFFFFF0u | (unsigned)s);
+	pk[0] = 0;
+	static_assert(CAP <= 16, "snapshot slot is packed in four bits");
 #pragma unroll
 	for (int e = 0; e < NS; e++) snap[(R.kslot[0] * NS + e) * T] = X[e];
 
@@ -306,26 +311,28 @@ implicit_filter_kernel(const ImplicitParams p, const int64_t n, const double *__
 			for (int j = 1; j < NPSS; j++) hmin = (hs[j] < hmin) ? hs[j] : hmin;
 		}
 		if (hmin < key[CAP - 1]) {
-			const int slot = R.kslot[CAP - 1];
+			const int slot = pk[CAP - 1] & 15;
 #pragma unroll
 			for (int e = 0; e < NS; e++) snap[(slot * NS + e) * T] = X[e];
-			double ck = hmin;
-			int ci = i, cs = slot;
-			bool ins = false;
+			// keys are sorted, so "hmin < key[s]" is monotone in s: entries above the insertion point move up by
+			// one, the entry at it takes the new point (before later equal keys, as a stable sort leaves them)
+			const int npk = (i << 4) | slot;
 #pragma unroll
-			for (int s = 0; s < CAP; s++) {
-				const bool sw = ins || (ck < key[s]);
-				ins = sw;
-				const double tk = key[s];
-				const int ti = kidx[s], ts = R.kslot[s];
-				key[s] = sw ? ck : tk;
-				kidx[s] = sw ? ci : ti;
-				R.kslot[s] = sw ? cs : ts;
-				ck = sw ? tk : ck;
-				ci = sw ? ti : ci;
-				cs = sw ? ts : cs;
+			for (int s = CAP - 1; s >= 1; s--) {
+				const bool here = hmin < key[s], up = hmin < key[s - 1];
+				key[s] = up ? key[s - 1] : (here ? hmin : key[s]);
+				pk[s] = up ? pk[s - 1] : (here ? npk : pk[s]);
+			}
+			if (hmin < key[0]) {
+				key[0] = hmin;
+				pk[0] = npk;
 			}
 		}
+	}
+#pragma unroll
+	for (int s = 0; s < CAP; s++) {
+		kidx[s] = pk[s] >> 4;
+		R.kslot[s] = pk[s] & 15;
 	}
 	// open-loop dynamics at the current state (:414-416) and the backup rows at the trajectory end (:542-554)
 	M::dynamics(x0, R.f, R.g);
