@@ -115,6 +115,31 @@ static int try_set(const qp_t *q, const int *S, int k, double *v_out, const doub
 	double v[NVMAX];
 	if (k == 0) {
 		memcpy(v, q->v0, sizeof(double) * nv);
+	} else if (k == nv) {
+		/* a vertex: v is fixed by the rows alone (N' v = r_S), the multipliers follow from 2Hv + c = N mu.  Two
+		 * k x k solves instead of the (nv+k) KKT system, whose Schur complement N'(2H)^-1 N squares the sine of
+		 * the angle between near-parallel rows: a row pair at 1.7e-6 rad (a safety row with h = 1.7e-6 against the
+		 * orthogonality row; relax = 1.8e4 at the optimum) put its pivot at 2.8e-14, under the round-off of the
+		 * elimination, and the optimum was reported as "no KKT point" (found by the round-2 parity run). */
+		double M[NVMAX][NVMAX], rr[NVMAX];
+		for (int a = 0; a < k; a++) {
+			const double *na = q->G + (size_t)S[a] * nv;
+			const double sc = 1.0 / rown[S[a]];
+			for (int i = 0; i < nv; i++) M[a][i] = na[i] * sc;
+			rr[a] = q->r[S[a]] * sc;
+		}
+		if (!solve_small(k, M, rr)) return 0;
+		for (int i = 0; i < nv; i++) v[i] = rr[i];
+		double mu[NVMAX];
+		for (int i = 0; i < nv; i++) {
+			double t = q->c[i];
+			for (int j = 0; j < nv; j++) t += q->G2[i][j] * v[j];
+			mu[i] = t;
+			for (int a = 0; a < k; a++) M[i][a] = q->G[(size_t)S[a] * nv + i] / rown[S[a]];
+		}
+		if (!solve_small(k, M, mu)) return 0;
+		for (int a = 0; a < k; a++)
+			if (!q->eq[S[a]] && mu[a] < 0.0) return 0;
 	} else {
 		/* KKT system of the equality-constrained problem on S, rows scaled to unit length:
 		 *   [ 2H  -N ] [v ]   [ -c  ]

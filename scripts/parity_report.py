@@ -56,6 +56,7 @@ def report(name, n, got, want, diag_cols=None, note="", crit_cols=None):
         rec["rows_outside_1e-9"] = int((d.max(axis=1) > 1e-9).sum())
     if note:
         rec["note"] = note
+    rec["git_head"] = os.environ.get("ASIF_GIT_HEAD", "unknown")  # the box has no .git: the caller passes the commit it snapshots
     print(json.dumps(rec), flush=True)
 
 

@@ -193,3 +193,36 @@ def test_explicit_custom_lie_derivatives(oracle, npSSmax):
     again = eng.filter_batch(x, ud, want_diag=True)
     for p, q in zip(base, again):
         assert np.array_equal(p, q)
+
+
+@pytest.mark.parametrize("mem", ["pageable", "pinned", "device"])
+def test_custom_cost_first_call_on_fresh_engine(ab, oracle, mem):
+    """The call pattern of scripts/parity_report.py's last record: a fresh engine whose FIRST call
+    is asif_engine_filter_batch_cost, n = 1e5 (several pipeline chunks), diagnostics on; through pageable numpy arrays,
+    pinned arrays and device pointers.  filter(x, H, c, ...) = src/asif_implicit_tb.cpp:252-259, updateH :748-762."""
+    n = 100_000
+    x, ud = cf.c2_inputs(n, seed=cf.SEED + 93)
+    eng = ab.Engine(ab.FILTER_IMPLICIT_TB, ab.MODEL_DOUBLE_INTEGRATOR_TB, **cf.tb_engine_kwargs(cf.C2_TB_OPTS))
+    H, c = cf.custom_cost(ud, eng.nv, seed=2)
+    want = oracle.filter_batch_cost(2, x, c, H, cf.C2_TB_OPTS, True)
+    if mem == "pageable":
+        u, relax, rc, diag = eng.filter_batch_cost(x, c, H, want_diag=True)
+    else:
+        import ctypes as C
+        import torch
+        L = ab.load_library()
+        Hc = np.asfortranarray(H)
+        t = {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in dict(x=x, c=c).items()}
+        t.update(u=torch.empty((n, eng.nu), dtype=torch.float64), relax=torch.empty((n, eng.n_relax), dtype=torch.float64),
+                 rc=torch.empty(n, dtype=torch.int32), diag=torch.empty((n, eng.n_diag), dtype=torch.float64))
+        t = {k: (v.pin_memory() if mem == "pinned" else v.cuda()) for k, v in t.items()}
+        r = L.asif_engine_filter_batch_cost(eng._h, n, t["x"].data_ptr(), Hc.ctypes.data, t["c"].data_ptr(), t["u"].data_ptr(),
+                                            t["relax"].data_ptr(), t["rc"].data_ptr(), t["diag"].data_ptr(),
+                                            ab.MEM_DEVICE if mem == "device" else ab.MEM_HOST, None)
+        assert r == 0, L.asif_last_error()
+        u, relax, rc, diag = (t[k].cpu().numpy() for k in ("u", "relax", "rc", "diag"))
+    u0, relax0, rc0, diag0 = want
+    print("first-call custom cost", mem, "rc", dict(zip(*np.unique(rc0, return_counts=True))), "flips", int((rc != rc0).sum()))
+    cf.assert_parity("first-call custom cost / " + mem, (u, relax, rc), (u0, relax0, rc0))
+    m = rc0 == 1
+    assert np.array_equal(diag[m][:, :3], diag0[m][:, :3]) and np.array_equal(diag[m][:, 4:], diag0[m][:, 4:])
