@@ -9,5 +9,5 @@ from .capi import (  # noqa: F401
     FILTER_EXPLICIT, FILTER_IMPLICIT_TB, FILTER_IMPLICIT, FILTER_ROBUST, FILTER_REALIZABLE, FILTER_IMPLICIT_RB,
     MODEL_DOUBLE_INTEGRATOR, MODEL_DOUBLE_INTEGRATOR_TB, MODEL_INVERTED_PENDULUM, MODEL_INVERTED_PENDULUM_TABLE, MODEL_INVERTED_PENDULUM_KERNEL,
     MODEL_SEGWAY, MODEL_SEGWAY_SHIPPED, MEM_HOST, MEM_DEVICE,
-    AsifError, Engine, PinnedArray, HOST_IO_STAGED, HOST_IO_OUT, HOST_IO_INOUT, EngineConfig, LoopConfig, loop_log_fields, device_count, lib_path, load_library, measure_fp64_peak, qp_solve_batch,
+    AsifError, Engine, EngineGroup, PinnedArray, HOST_IO_STAGED, HOST_IO_OUT, HOST_IO_INOUT, EngineConfig, LoopConfig, loop_log_fields, device_count, lib_path, load_library, measure_fp64_peak, qp_solve_batch,
 )

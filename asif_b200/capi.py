@@ -112,6 +112,16 @@ def load_library():
     L.asif_qp_solve_batch.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int32] + [C.c_void_p] * 9 + \
                                      [C.c_int32, C.c_int32, C.c_void_p]
     L.asif_measure_fp64_peak.argtypes = [C.c_int32, _dp, _dp]
+    L.asif_engine_group_create.argtypes = [C.POINTER(EngineConfig), _ip, C.c_int32, C.POINTER(C.c_void_p)]
+    L.asif_engine_group_destroy.argtypes = [C.c_void_p]
+    L.asif_engine_group_size.argtypes = [C.c_void_p]
+    L.asif_engine_group_engine.argtypes = [C.c_void_p, C.c_int32]
+    L.asif_engine_group_engine.restype = C.c_void_p
+    L.asif_engine_group_slice.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.POINTER(C.c_int64)]
+    L.asif_engine_group_filter_batch.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 6
+    L.asif_engine_group_filter_batch_cost.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 7
+    L.asif_engine_group_rollout.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
+                                            C.c_void_p, C.POINTER(C.c_int64)]
     _lib = L
     return L
 
@@ -151,6 +161,21 @@ class Engine:
 
     def __init__(self, filter, model, device=0, **options):
         L = load_library()
+        cfg = self._config(filter, model, device, options)
+        self.cfg = cfg
+        h = C.c_void_p()
+        _check(L.asif_engine_create(C.byref(cfg), C.byref(h)))
+        self._h = h
+        self._read_dims(h)
+        self.device = device
+
+    def _read_dims(self, h):
+        dims = (C.c_int32 * 6)()
+        _check(load_library().asif_engine_dims(h, dims))
+        self.nx, self.nu, self.n_relax, self.nc, self.nv, self.n_diag = (int(v) for v in dims)
+
+    def _config(self, filter, model, device, options):
+        L = load_library()
         cfg = EngineConfig()
         _check(L.asif_engine_config_init(C.byref(cfg), filter, model))
         cfg.device = device
@@ -182,14 +207,7 @@ class Engine:
                 raise AsifError("unknown option %r" % k)
             else:
                 setattr(cfg, k, v)
-        self.cfg = cfg
-        h = C.c_void_p()
-        _check(L.asif_engine_create(C.byref(cfg), C.byref(h)))
-        self._h = h
-        dims = (C.c_int32 * 6)()
-        _check(L.asif_engine_dims(h, dims))
-        self.nx, self.nu, self.n_relax, self.nc, self.nv, self.n_diag = (int(v) for v in dims)
-        self.device = device
+        return cfg
 
     def close(self):
         if getattr(self, "_h", None):
@@ -342,6 +360,72 @@ class Engine:
 
 
 HOST_IO_STAGED, HOST_IO_OUT, HOST_IO_INOUT = 0, 1, 2
+
+
+class EngineGroup(Engine):
+    """One filter object replicated on several GPUs (asif_engine_group_*): a host batch is cut into contiguous slices,
+    one per device, and the results land in the caller's arrays.  devices=None takes every visible device."""
+
+    def __init__(self, filter, model, devices=None, **options):
+        L = load_library()
+        cfg = self._config(filter, model, 0, options)
+        self.cfg = cfg
+        g = C.c_void_p()
+        if devices is None:
+            _check(L.asif_engine_group_create(C.byref(cfg), None, 0, C.byref(g)))
+        else:
+            d = (C.c_int32 * len(devices))(*devices)
+            _check(L.asif_engine_group_create(C.byref(cfg), d, len(devices), C.byref(g)))
+        self._g = g
+        self._h = None
+        self.size = int(L.asif_engine_group_size(g))
+        self._read_dims(L.asif_engine_group_engine(g, 0))
+
+    def close(self):
+        if getattr(self, "_g", None):
+            load_library().asif_engine_group_destroy(self._g)
+            self._g = None
+
+    def slice(self, n, i):
+        b = (C.c_int64 * 2)()
+        _check(load_library().asif_engine_group_slice(self._g, n, i, b))
+        return int(b[0]), int(b[1])
+
+    def member_host_io(self, i):
+        v = C.c_int32()
+        L = load_library()
+        _check(L.asif_engine_last_host_io(L.asif_engine_group_engine(self._g, i), C.byref(v)))
+        return int(v.value)
+
+    def filter_batch_into(self, n, x, u_des, u_act, relax, rc, diag=None, stream=None):
+        ptrs = [_ptr(a) for a in (x, u_des, u_act, relax, rc)]
+        assert not any(d for _, d in ptrs), "group batches are host arrays"
+        dptr = _ptr(diag)[0] if diag is not None else None
+        _check(load_library().asif_engine_group_filter_batch(self._g, n, ptrs[0][0], ptrs[1][0], ptrs[2][0], ptrs[3][0], ptrs[4][0], dptr))
+
+    def filter_batch_cost(self, x, c, H=None, want_diag=False):
+        x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1, self.nx)
+        c = np.ascontiguousarray(c, dtype=np.float64).reshape(-1, self.nv)
+        n = x.shape[0]
+        Hp = None
+        if H is not None:
+            Hc = np.asfortranarray(np.asarray(H, dtype=np.float64).reshape(self.nu, self.nu))
+            Hp = Hc.ctypes.data
+        u, relax, rc = np.empty((n, self.nu)), np.empty((n, self.n_relax)), np.empty(n, dtype=np.int32)
+        diag = np.empty((n, self.n_diag)) if want_diag else None
+        _check(load_library().asif_engine_group_filter_batch_cost(self._g, n, x.ctypes.data, Hp, c.ctypes.data, u.ctypes.data,
+                                                                  relax.ctypes.data, rc.ctypes.data, diag.ctypes.data if want_diag else None))
+        return (u, relax, rc, diag) if want_diag else (u, relax, rc)
+
+    def rollout(self, x0, u_des, steps, dt):
+        x = np.array(x0, dtype=np.float64).reshape(-1, self.nx).copy()
+        u_des = np.ascontiguousarray(u_des, dtype=np.float64).reshape(-1, self.nu)
+        n = x.shape[0]
+        u, rc = np.empty((n, self.nu)), np.empty(n, dtype=np.int32)
+        hist = (C.c_int64 * 8)()
+        _check(load_library().asif_engine_group_rollout(self._g, n, steps, dt, x.ctypes.data, u_des.ctypes.data, u.ctypes.data,
+                                                        rc.ctypes.data, hist))
+        return x, u, rc, np.array(list(hist), dtype=np.int64)
 
 
 class PinnedArray:

@@ -20,6 +20,7 @@
 #include <cstring>
 #include <limits>
 #include <new>
+#include <stdexcept>
 
 using namespace asifb;
 
@@ -820,7 +821,10 @@ int32_t filter_batch_impl(asif_engine *e, int64_t n, const double *x, const doub
 		chunk = quarter > floor_ ? quarter : (n < floor_ ? n : floor_);
 		if (chunk > chunk_states()) chunk = chunk_states();
 	}
-	CUDA_TRY(cudaMemset(e->d_counters, 0, sizeof(unsigned long long)));
+	// the QP-work counter is zeroed on the engine's own stream and waited for: the slot streams are non-blocking and
+	// do not order against the legacy default stream a plain cudaMemset would run on
+	CUDA_TRY(cudaMemsetAsync(e->d_counters, 0, sizeof(unsigned long long), e->stream));
+	CUDA_TRY(cudaStreamSynchronize(e->stream));
 	// device aliases of the caller's output arrays (nullptr: pageable or unmapped memory, staged copies then)
 	double *m_ua = nullptr, *m_relax = nullptr, *m_diag = nullptr;
 	int32_t *m_rc = nullptr;
@@ -854,7 +858,13 @@ int32_t filter_batch_impl(asif_engine *e, int64_t n, const double *x, const doub
 	if ((size_t)n * (in_row + out_row) >= ((size_t)8 << 20) && bounce_enabled()) {
 		bounce_in = is_pageable(x) && is_pageable(u_des);
 		bounce_out = !direct_out && is_pageable(u_act) && is_pageable(relax) && is_pageable(rc) && (!diag || is_pageable(diag));
-		if ((bounce_in || bounce_out) && !e->copier) e->copier = new HostCopier(HostCopier::default_threads());
+		if ((bounce_in || bounce_out) && !e->copier) {
+			try { // nothing may throw through the C boundary
+				e->copier = new HostCopier(e->copy_threads > 0 ? e->copy_threads : HostCopier::default_threads());
+			} catch (const std::exception &ex) {
+				return fail(ASIF_ERR_INTERNAL, "host copier threads: %s", ex.what());
+			}
+		}
 	}
 	const size_t h_x = 0, h_ud = h_x + sizeof(double) * chunk * nx, h_ua = h_ud + sizeof(double) * chunk * e->nv,
 	             h_relax = h_ua + sizeof(double) * chunk * nu, h_diag = h_relax + sizeof(double) * chunk * nr,
@@ -1212,6 +1222,7 @@ extern "C" int32_t asif_qp_solve_batch(int32_t device, int32_t nv, int32_t nc, i
 	int ndev = 0;
 	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
 		return fail(ASIF_ERR_NO_DEVICE, "no CUDA device; this engine has no CPU fallback");
+	if (device < 0 || device >= ndev) return fail(ASIF_ERR_INVALID_ARGUMENT, "device %d out of range [0,%d)", device, ndev);
 	CUDA_TRY(cudaSetDevice(device));
 	cudaStream_t st = (cudaStream_t)stream;
 	const bool shH = share_flags & ASIF_QP_SHARED_H, shB = share_flags & ASIF_QP_SHARED_BOUNDS;
@@ -1280,7 +1291,16 @@ extern "C" int32_t asif_qp_solve_batch(int32_t device, int32_t nv, int32_t nc, i
 		{
 			static thread_local void *tl_buf[16] = {nullptr};
 			static thread_local size_t tl_cap[16] = {0};
+			static thread_local int tl_dev[16] = {0};
 			const int slot = device & 15;
+			if (tl_buf[slot] && tl_dev[slot] != device) { // an ordinal >= 16 shares the slot of another device: never its memory
+				cudaSetDevice(tl_dev[slot]);
+				cudaFree(tl_buf[slot]);
+				cudaSetDevice(device);
+				tl_buf[slot] = nullptr;
+				tl_cap[slot] = 0;
+			}
+			tl_dev[slot] = device;
 			if (bytes > tl_cap[slot]) {
 				if (tl_buf[slot]) cudaFree(tl_buf[slot]);
 				tl_buf[slot] = nullptr;

@@ -85,6 +85,7 @@ struct asif_engine {
 	unsigned long long *d_counters = nullptr; // [0] qp rows processed, [1..8] rc histogram
 	uint64_t last_qp_rows = 0;
 	HostCopier *copier = nullptr; // created by the first large pageable batch
+	int copy_threads = 0;         // its thread count; 0 = HostCopier::default_threads() (a group shares the cores out)
 	char *small_h = nullptr;      // pinned, device-addressable scratch of the small-batch path (SMALL_BATCH_BYTES)
 	int last_host_io = -1; // ASIF_HOST_IO_* actually used by the last host-memory batch (-1: none yet)
 	int num_sms = 148;
@@ -237,7 +238,7 @@ template <class M, int NPBTSS, bool RB, int SAT_LO>
 int launch_implicit_t(asif_engine *e, int64_t n, const double *x, const double *ud, double *ua, double *relax, int32_t *rc,
                       double *diag, cudaStream_t st)
 {
-	const size_t smem = sizeof(double) * imp_smem_doubles_per_thread<M, NPBTSS>() * IMP_THREADS;
+	const size_t smem = sizeof(double) * (diag ? imp_smem_doubles_per_thread<M, NPBTSS, true>() : imp_smem_doubles_per_thread<M, NPBTSS, false>()) * IMP_THREADS;
 	const unsigned blocks = (unsigned)((n + IMP_THREADS - 1) / IMP_THREADS);
 	const bool pow2 = e->im.sat_mode >= SAT_POW2;
 	if (diag) {

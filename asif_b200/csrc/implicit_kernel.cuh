@@ -92,11 +92,43 @@ struct ImplicitParams {
 
 constexpr int IMP_NPBTSS_RUNTIME = -16; // generic instantiation: any npBTSS in 1..16 (see np_capacity in tb_kernel.cuh)
 
-template <class M, int NPBTSS>
+// Shared memory per thread: CAP snapshot slots of (x_i, Q_i), the CAP min-h keys of those slots and (diagnostic kernel
+// only) their trajectory indices.  The ORDER of the slots lives in one 64-bit register (ImpOrder below).
+template <class M, int NPBTSS, bool WITH_IDX = false>
 __host__ __device__ constexpr int imp_smem_doubles_per_thread()
 {
-	return np_capacity(NPBTSS) * (M::NX + M::NX * M::NX);
+	return np_capacity(NPBTSS) * (M::NX + M::NX * M::NX + 1) + (WITH_IDX ? (np_capacity(NPBTSS) + 1) / 2 : 0);
 }
+
+// The running list of the CAP smallest min-h points, ascending.  Keys and snapshots sit in shared memory at fixed
+// physical slots; the sorted order is a permutation packed four bits per entry: nibble s = slot of the s-th smallest.
+// A new point always takes the slot of the entry it evicts (the largest), so an insert is one snapshot store, one key
+// store and a few 64-bit shifts - no data moves.  The common cases are O(1): a new overall minimum (every step of a
+// trajectory whose min h is still falling, e.g. a pendulum that the saturated backup input cannot catch) shifts the
+// whole word by one nibble; anything else searches its place among the stored keys (rare: at most CAP - 1 appends
+// while the list fills, then only when the trajectory comes back below an earlier excursion).
+// Ties keep the earlier trajectory index first (a new key goes behind equal ones), as before.
+template <int CAP>
+struct ImpOrder {
+	static_assert(CAP >= 1 && CAP <= 16, "slot numbers are packed in four bits, sixteen to a word");
+	static constexpr unsigned long long MASK = (CAP == 16) ? ~0ull : ((1ull << (4 * (CAP % 16))) - 1ull);
+	unsigned long long perm;
+	__device__ __forceinline__ void init()
+	{
+		unsigned long long v = 0;
+#pragma unroll
+		for (int s = 0; s < CAP; s++) v |= (unsigned long long)s << (4 * s);
+		perm = v;
+	}
+	__device__ __forceinline__ int slot(const int s) const { return (int)(perm >> (4 * s)) & 15; }
+	__device__ __forceinline__ int last() const { return (int)(perm >> (4 * (CAP - 1))) & 15; }
+	__device__ __forceinline__ void push_front(const int sl) { perm = ((perm << 4) | (unsigned long long)sl) & MASK; }
+	__device__ __forceinline__ void insert_at(const int p, const int sl)
+	{
+		const unsigned long long low = (1ull << (4 * p)) - 1ull;
+		perm = ((perm & low) | ((unsigned long long)sl << (4 * p)) | ((perm & ~low) << 4)) & MASK;
+	}
+};
 
 template <class M, int NPBTSS, bool RB = false>
 struct ImpRows {
@@ -109,7 +141,7 @@ struct ImpRows {
 	const double *snap;
 	int T;
 	double f[NX], g[NX * NU];
-	int kslot[CAP];
+	ImpOrder<CAP> order; // slot of the s-th smallest point
 	double lgB[NPBS][NU], hB[NPBS], rhsB[NPBS]; // backup rows
 	double lb[NV], ub[NV];
 	double x_unc[RB ? NX : 1];
@@ -168,9 +200,7 @@ struct ImpRows {
 		const int NSAFE = nsafe(), NC = nc();
 #pragma unroll 1
 		for (int s = 0; s < count_np(); s++) {
-			int slot = 0;
-#pragma unroll
-			for (int t = 0; t < CAP; t++) slot = (t == s) ? kslot[t] : slot;
+			const int slot = order.slot(s);
 			double n[NPSS][NV], rhs[NPSS];
 			point_rows(slot, n, rhs, s == 0);
 #pragma unroll
@@ -194,9 +224,7 @@ struct ImpRows {
 			backup_row(j - NSAFE, n, rhs);
 		} else {
 			const int s = j / NPSS, jj = j - s * NPSS;
-			int slot = 0;
-#pragma unroll
-			for (int t = 0; t < CAP; t++) slot = (t == s) ? kslot[t] : slot;
+			const int slot = order.slot(s);
 			double nn[NPSS][NV], rr[NPSS];
 			point_rows(slot, nn, rr, s == 0);
 #pragma unroll
@@ -264,23 +292,21 @@ implicit_filter_kernel(const ImplicitParams p, const int64_t n, const double *__
 	for (int i = 0; i < NX; i++) X[i] = x0[i];
 #pragma unroll
 	for (int i = 0; i < NX; i++) X[NX + i * (NX + 1)] = 1.0;
-	double key[CAP];
-	int kidx[CAP];
+	// keys by physical slot (shared memory), trajectory indices likewise (diagnostic kernel only)
+	double *keys = snap + CAP * NS * T;
+	int *kidx_s = reinterpret_cast<int *>(smem + CAP * (NS + 1) * T) + threadIdx.x;
 #pragma unroll
-	for (int s = 0; s < CAP; s++) {
-		key[s] = INFINITY;
-		kidx[s] = -1;
-		R.kslot[s] = s;
+	for (int s = 1; s < CAP; s++) keys[s * T] = INFINITY;
+	keys[0] = hSafetyNow;
+	if (WITH_DIAG) {
+#pragma unroll
+		for (int s = 1; s < CAP; s++) kidx_s[s * T] = -1;
+		kidx_s[0] = 0;
 	}
-	key[0] = hSafetyNow;
-	kidx[0] = 0;
-	int pk[CAP]; // (trajectory index << 4) | snapshot slot of the sorted entries; -1 index = empty
+	R.order.init();
+	double kmin = hSafetyNow, kmax = (CAP > 1) ? INFINITY : hSafetyNow; // smallest / largest key in the list
 #pragma unroll
-	for (int s = 0; s < CAP; s++) pk[s] = (int)(0xFFFFFFF0u | (unsigned)s);
-	pk[0] = 0;
-	static_assert(CAP <= 16, "snapshot slot is packed in four bits");
-#pragma unroll
-	for (int e = 0; e < NS; e++) snap[(R.kslot[0] * NS + e) * T] = X[e];
+	for (int e = 0; e < NS; e++) snap[e * T] = X[e]; // slot 0
 
 	const int N = p.npBT;
 	ZohState<M> zoh;
@@ -310,29 +336,23 @@ implicit_filter_kernel(const ImplicitParams p, const int64_t n, const double *__
 #pragma unroll
 			for (int j = 1; j < NPSS; j++) hmin = (hs[j] < hmin) ? hs[j] : hmin;
 		}
-		if (hmin < key[CAP - 1]) {
-			const int slot = pk[CAP - 1] & 15;
+		if (hmin < kmax) {
+			const int slot = R.order.last(); // the evicted (largest) entry's slot takes the new point
 #pragma unroll
 			for (int e = 0; e < NS; e++) snap[(slot * NS + e) * T] = X[e];
-			// keys are sorted, so "hmin < key[s]" is monotone in s: entries above the insertion point move up by
-			// one, the entry at it takes the new point (before later equal keys, as a stable sort leaves them)
-			const int npk = (i << 4) | slot;
-#pragma unroll
-			for (int s = CAP - 1; s >= 1; s--) {
-				const bool here = hmin < key[s], up = hmin < key[s - 1];
-				key[s] = up ? key[s - 1] : (here ? hmin : key[s]);
-				pk[s] = up ? pk[s - 1] : (here ? npk : pk[s]);
+			if (hmin < kmin) {
+				R.order.push_front(slot);
+				kmin = hmin;
+			} else {
+				// first place whose key is larger (hmin >= key of place 0 and hmin < key of place CAP-1 are known)
+				int pl = 1;
+				while (pl < CAP - 1 && !(hmin < keys[R.order.slot(pl) * T])) pl++;
+				R.order.insert_at(pl, slot);
 			}
-			if (hmin < key[0]) {
-				key[0] = hmin;
-				pk[0] = npk;
-			}
+			keys[slot * T] = hmin;
+			if (WITH_DIAG) kidx_s[slot * T] = i;
+			kmax = keys[R.order.last() * T];
 		}
-	}
-#pragma unroll
-	for (int s = 0; s < CAP; s++) {
-		kidx[s] = pk[s] >> 4;
-		R.kslot[s] = pk[s] & 15;
 	}
 	// open-loop dynamics at the current state (:414-416) and the backup rows at the trajectory end (:542-554)
 	M::dynamics(x0, R.f, R.g);
@@ -345,7 +365,7 @@ implicit_filter_kernel(const ImplicitParams p, const int64_t n, const double *__
 		// (src/asif_implicit.cpp:533-537, include/asif_learning_utils.h:127-129)
 		double xs[NS], hq[NPSS], Dq[NPSS * NX], dhi[NX];
 #pragma unroll
-		for (int e = 0; e < NS; e++) xs[e] = snap[(R.kslot[0] * NS + e) * T];
+		for (int e = 0; e < NS; e++) xs[e] = snap[(R.order.slot(0) * NS + e) * T];
 		M::safety_set(xs, hq, Dq);
 #pragma unroll
 		for (int i = 0; i < NX; i++) {
@@ -434,7 +454,7 @@ implicit_filter_kernel(const ImplicitParams p, const int64_t n, const double *__
 			d[1] = hBackupEnd;
 #pragma unroll
 			for (int s = 0; s < CAP; s++)
-				if (s < np) d[2 + s] = (double)kidx[s];
+				if (s < np) d[2 + s] = (double)kidx_s[R.order.slot(s) * T];
 			double *A = d + 2 + np, *b = A + NC * NV;
 			R.scan(
 			    [&](const int j, const double(&nn)[NV], const double rhs) {

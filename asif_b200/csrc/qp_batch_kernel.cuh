@@ -111,6 +111,7 @@ qp_batch_kernel(const int64_t n, const int nc, const int diagonal_cost, const do
 	double c[NV], v[NV];
 #pragma unroll
 	for (int i = 0; i < NV; i++) {
+		v[i] = 0.0; // what getSolution() returns when H is rejected (-7) and the solver never runs
 		R.lb[i] = lbk[i];
 		R.ub[i] = ubk[i];
 		c[i] = c_in[k * NV + i];
@@ -123,7 +124,7 @@ qp_batch_kernel(const int64_t n, const int nc, const int diagonal_cost, const do
 		for (int i = 0; i < NV; i++) {
 			const double h2 = 2.0 * Hk[i + i * NV];
 			ok = ok && (h2 > 0.0);
-			mt.gi[i] = 1.0 / h2;
+			mt.gi[i] = (h2 > 0.0) ? 1.0 / h2 : 1.0;
 			mt.gih[i] = sqrt(mt.gi[i]);
 		}
 		st = ok ? qp_gi_solve<NV>(mt, c, R, v) : -7; // OSQP_NON_CVX

@@ -190,6 +190,71 @@ __device__ __forceinline__ void qp_scan_rows(const Rows &rows, const double (&)[
 	rows.scan(fn, fb);
 }
 
+// Vertex polish.  At a vertex (NV active rows) the minimiser is fixed by the rows alone: N v = rhs.  The dual method reaches
+// it by steps along directions orthogonalised in hat space, whose error is eps / sin(angle between active rows) times the
+// length of the step - for a safety row with h ~ 1e-6 against the orthogonality row (3.7e-7 rad apart in hat space, the
+// relax variable at 1.8e4) that was 6e-5 in u, found against an exact rational solve in the round-2 parity run (3 states
+// in 2.7e6).  Such vertices are re-solved from the original rows by Gaussian elimination with partial pivoting, whose error
+// is eps times the condition number of N only; the result replaces v when it satisfies the active rows at least as well.
+// Rare (a few states in 1e4), so it is kept out of line and works on local arrays.
+constexpr double QP_POLISH_SIN = 1e-2; // polish when some R[a][a] (sine of the angle to the earlier active rows) is below this
+
+template <int NV>
+static __device__ __noinline__ bool qp_vertex_solve(double (&M)[NV][NV + 1], double (&out)[NV])
+{
+	for (int c = 0; c < NV; c++) {
+		int piv = c;
+		double best = fabs(M[c][c]);
+		for (int i = c + 1; i < NV; i++)
+			if (fabs(M[i][c]) > best) {
+				best = fabs(M[i][c]);
+				piv = i;
+			}
+		if (!(best > 0.0)) return false;
+		if (piv != c)
+			for (int j = 0; j <= NV; j++) {
+				const double t = M[c][j];
+				M[c][j] = M[piv][j];
+				M[piv][j] = t;
+			}
+		for (int i = c + 1; i < NV; i++) {
+			const double f = M[i][c] / M[c][c];
+			for (int j = c; j <= NV; j++) M[i][j] -= f * M[c][j];
+		}
+	}
+	for (int i = NV - 1; i >= 0; i--) {
+		double t = M[i][NV];
+		for (int j = i + 1; j < NV; j++) t -= M[i][j] * out[j];
+		out[i] = t / M[i][i];
+	}
+	bool fin = true;
+	for (int i = 0; i < NV; i++) fin = fin && (fabs(out[i]) < INFINITY);
+	return fin;
+}
+
+// N = the active rows [normal | rhs]; v is replaced by the direct solve when that satisfies the rows at least as well
+template <int NV>
+static __device__ __noinline__ void qp_vertex_polish(const double (&N)[NV][NV + 1], double (&v)[NV])
+{
+	double M[NV][NV + 1], vp[NV];
+	for (int a = 0; a < NV; a++)
+		for (int i = 0; i <= NV; i++) M[a][i] = N[a][i];
+	if (!qp_vertex_solve<NV>(M, vp)) return;
+	double r_old = 0.0, r_new = 0.0; // worst active-row residual, relative to max(1, |row|_inf)
+	for (int a = 0; a < NV; a++) {
+		double so = -N[a][NV], sn = -N[a][NV], nmax = 1.0;
+		for (int i = 0; i < NV; i++) {
+			so += N[a][i] * v[i];
+			sn += N[a][i] * vp[i];
+			nmax = fabs(N[a][i]) > nmax ? fabs(N[a][i]) : nmax;
+		}
+		r_old = fabs(so) / nmax > r_old ? fabs(so) / nmax : r_old;
+		r_new = fabs(sn) / nmax > r_new ? fabs(sn) / nmax : r_new;
+	}
+	if (r_new <= r_old)
+		for (int i = 0; i < NV; i++) v[i] = vp[i];
+}
+
 // v returns the minimiser when the result is QP_OK.
 // iters (optional) returns the number of rows processed (for the K-bar statistic).
 template <int NV, class Rows, class Metric>
@@ -382,6 +447,30 @@ __device__ __forceinline__ int qp_gi_solve(const Metric &mt, const double (&c)[N
 		}
 	}
 	if (iters) *iters = it;
+	if (status == QP_OK && w.q == NV) {
+		double rmin = w.R[0][0];
+#pragma unroll
+		for (int a = 1; a < NV; a++) rmin = (w.R[a][a] < rmin) ? w.R[a][a] : rmin;
+		if (rmin < QP_POLISH_SIN) { // rare; only plain arrays go out of line (the row functor stays in registers)
+			double N[NV][NV + 1], vv[NV];
+#pragma unroll 1
+			for (int a = 0; a < NV; a++) {
+				double n[NV], rhs = 0.0;
+				int ja = 0;
+#pragma unroll
+				for (int t = 0; t < NV; t++) ja = (t == a) ? w.act[t] : ja;
+				rows.get(ja, n, rhs);
+#pragma unroll
+				for (int i = 0; i < NV; i++) N[a][i] = n[i];
+				N[a][NV] = rhs;
+			}
+#pragma unroll
+			for (int i = 0; i < NV; i++) vv[i] = w.v[i];
+			qp_vertex_polish<NV>(N, vv);
+#pragma unroll
+			for (int i = 0; i < NV; i++) w.v[i] = vv[i];
+		}
+	}
 #pragma unroll
 	for (int i = 0; i < NV; i++) v[i] = w.v[i];
 	return status;

@@ -128,6 +128,10 @@ namespace ASIF
 		virtual int32_t initialize(const double H[], const double c[], const double A[], const double b[],
 		                           const double lb[], const double ub[], const bool be[] = nullptr)
 		{
+			// nv > 4 (the LP-dual formulations of ASIFrobust / ASIFrealizable: nv = 402 / 38) is not a problem this backend
+			// solves - those classes run on the B200 through FilterBatchRobust / FilterBatchRealizable, which eliminate the
+			// multipliers.  Every reference caller ignores initialize()'s return value (src/asif.cpp:102), so solve() fails
+			// loudly as well: it returns ASIF_ERR_UNSUPPORTED (-102), a value no OSQP status and no filter code uses.
 			if (nv_ < 1 || nv_ > 4) return ASIF_ERR_UNSUPPORTED;
 			if (be != nullptr) {
 				for (uint32_t i = 0; i < nc_; i++) {
@@ -212,13 +216,23 @@ namespace ASIF
 		class FilterBatchBase
 		{
 		public:
-			virtual ~FilterBatchBase(void) { asif_engine_destroy(engine_); }
+			virtual ~FilterBatchBase(void) { release(); }
+			// Device list: call before initialize().  With more than one device every host batch is cut into
+			// contiguous slices, one per GPU (asif_engine_group_*), and the results land in the caller's arrays; an empty
+			// list means "every visible device".  Without this call the filter runs on the constructor's single device.
+			void setDevices(const std::vector<int32_t> &devices)
+			{
+				devices_ = devices;
+				useGroup_ = true;
+			}
+			uint32_t nDevices(void) const { return group_ ? (uint32_t)asif_engine_group_size(group_) : (engine_ ? 1u : 0u); }
 			// filter(x, uDes, uAct, relax) of the reference class on n states; host arrays
-			// X[n*nx], UDes[n*nu], UAct[n*nu], Relax[n*nRelax], rc[n]; returns 0 or a negative ASIF_ERR_*
+			// X[n*nx], UDes[n*nu], UAct[n*nu], Relax[n*nRelax], rc[n]; returns 0 or a negative ASIF_ERR_* (<= -101)
 			int32_t filterBatch(const int64_t n, const double X[], const double UDes[], double UAct[], double Relax[],
 			                    int32_t rc[], double diag[] = nullptr)
 			{
 				if (engine_ == nullptr) return ASIF_ERR_INVALID_ARGUMENT;
+				if (group_) return asif_engine_group_filter_batch(group_, n, X, UDes, UAct, Relax, rc, diag);
 				return asif_engine_filter_batch(engine_, n, X, UDes, UAct, Relax, rc, diag, ASIF_MEM_HOST, nullptr);
 			}
 			// the filter(x, H, c, uAct, relax) overloads on n states: C[n*nv] is the caller's linear cost of the whole decision
@@ -227,14 +241,24 @@ namespace ASIF
 			                    int32_t rc[], double diag[] = nullptr)
 			{
 				if (engine_ == nullptr) return ASIF_ERR_INVALID_ARGUMENT;
+				if (group_) return asif_engine_group_filter_batch_cost(group_, n, X, H, C, UAct, Relax, rc, diag);
 				return asif_engine_filter_batch_cost(engine_, n, X, H, C, UAct, Relax, rc, diag, ASIF_MEM_HOST, nullptr);
 			}
-			// single state, as every reference class declares it (e.g. include/asif_implicit_tb.h:103-110); relax has nRelax() entries
+			// single state, as every reference class declares it (e.g. include/asif_implicit_tb.h:103-110); relax has nRelax() entries.
+			// Returns the reference's code, or an ASIF_ERR_* (<= -101, outside the reference's range) when the engine itself
+			// failed - uAct and relax are then left untouched.  The classes that leave uAct untouched when the QP fails
+			// (ASIF, ASIFrobust, ASIFrealizable: src/asif.cpp:207-209) do so here too.
 			int32_t filter(const double x[], const double H[], const double c[], double uAct[], double relax[])
 			{
 				int32_t rc = 0;
-				const int32_t r = filterBatch(1, x, H, c, uAct, relax, &rc);
-				return r == ASIF_OK ? rc : r;
+				double ua[2] = {0.0, 0.0}, rl[2] = {0.0, 0.0};
+				const int32_t r = filterBatch(1, x, H, c, ua, rl, &rc);
+				if (r != ASIF_OK) return r;
+				if (rc == 1 || !keepOnFailure_) {
+					for (uint32_t i = 0; i < nu(); i++) uAct[i] = ua[i];
+					for (uint32_t i = 0; i < nRelax(); i++) relax[i] = rl[i];
+				}
+				return rc;
 			}
 			// same with device pointers on the caller's CUDA stream (cudaStream_t); returns without synchronising
 			int32_t filterBatchDevice(const int64_t n, const double *X, const double *UDes, double *UAct, double *Relax,
@@ -278,18 +302,52 @@ namespace ASIF
 			uint32_t nDiag(void) const { return dims_[5]; }
 
 		protected:
-			FilterBatchBase(void) : engine_(nullptr) { std::memset(dims_, 0, sizeof(dims_)); }
+			FilterBatchBase(void) : engine_(nullptr), group_(nullptr), useGroup_(false), keepOnFailure_(false) { std::memset(dims_, 0, sizeof(dims_)); }
+			void release(void)
+			{
+				if (group_) asif_engine_group_destroy(group_); // owns its engines
+				else asif_engine_destroy(engine_);
+				group_ = nullptr;
+				engine_ = nullptr;
+			}
 			int32_t create(const asif_engine_config &cfg)
 			{
-				asif_engine *e = nullptr;
-				const int32_t r = asif_engine_create(&cfg, &e);
-				if (r != ASIF_OK) return r;
-				asif_engine_destroy(engine_);
-				engine_ = e;
+				if (useGroup_) {
+					asif_engine_group *g = nullptr;
+					const int32_t r = asif_engine_group_create(&cfg, devices_.empty() ? nullptr : devices_.data(), (int32_t)devices_.size(), &g);
+					if (r != ASIF_OK) return r;
+					release();
+					group_ = g;
+					engine_ = asif_engine_group_engine(group_, 0); // borrowed: dims, single-state calls, device-pointer calls
+				} else {
+					asif_engine *e = nullptr;
+					const int32_t r = asif_engine_create(&cfg, &e);
+					if (r != ASIF_OK) return r;
+					release();
+					engine_ = e;
+				}
 				asif_engine_dims(engine_, dims_);
 				return 1;
 			}
+			// single-state filter(x, uDes, ...) shared by the classes: locals first, so that an engine error leaves the caller's
+			// uAct / relax untouched (an ASIF_ERR_* must not read as "backup action is in uAct")
+			int32_t filterOne(const double x[], const double uDes[], double uAct[], double relax[])
+			{
+				int32_t rc = 0;
+				double ua[2] = {0.0, 0.0}, rl[2] = {0.0, 0.0};
+				const int32_t r = filterBatch(1, x, uDes, ua, rl, &rc);
+				if (r != ASIF_OK) return r;
+				if (rc == 1 || !keepOnFailure_) {
+					for (uint32_t i = 0; i < nu(); i++) uAct[i] = ua[i];
+					for (uint32_t i = 0; i < nRelax(); i++) relax[i] = rl[i];
+				}
+				return rc;
+			}
 			asif_engine *engine_;
+			asif_engine_group *group_;
+			std::vector<int32_t> devices_;
+			bool useGroup_;
+			bool keepOnFailure_; // ASIF / ASIFrobust / ASIFrealizable: uAct, relax untouched unless rc == 1
 			int32_t dims_[6];
 		};
 
@@ -309,6 +367,7 @@ namespace ASIF
 			explicit FilterBatchExplicit(const Model model, const int32_t device = 0, const uint32_t npSSmax = (uint32_t)-1)
 			    : model_(model), device_(device), npSSmax_(npSSmax)
 			{
+				keepOnFailure_ = true;
 			}
 			int32_t initialize(const double lb[], const double ub[]) { return initialize(lb, ub, Options()); }
 			int32_t initialize(const double lb[], const double ub[], const Options &options)
@@ -343,8 +402,14 @@ namespace ASIF
 			{
 				int32_t rc = 0;
 				if (engine_ == nullptr) return ASIF_ERR_INVALID_ARGUMENT;
-				const int32_t r = asif_engine_filter_batch_lie(engine_, 1, x, uDes, Lfh, Lgh, uAct, &relax, &rc, nullptr, ASIF_MEM_HOST, nullptr);
-				return r == ASIF_OK ? rc : r;
+				double ua[2] = {0.0, 0.0}, rl = 0.0;
+				const int32_t r = asif_engine_filter_batch_lie(engine_, 1, x, uDes, Lfh, Lgh, ua, &rl, &rc, nullptr, ASIF_MEM_HOST, nullptr);
+				if (r != ASIF_OK) return r;
+				if (rc == 1) { // untouched on failure (src/asif.cpp:207-209)
+					for (uint32_t i = 0; i < nu(); i++) uAct[i] = ua[i];
+					relax = rl;
+				}
+				return rc;
 			}
 			int32_t filterBatchLie(const int64_t n, const double X[], const double UDes[], const double Lfh[], const double Lgh[],
 			                       double UAct[], double Relax[], int32_t rc[], double diag[] = nullptr)
@@ -352,18 +417,8 @@ namespace ASIF
 				if (engine_ == nullptr) return ASIF_ERR_INVALID_ARGUMENT;
 				return asif_engine_filter_batch_lie(engine_, n, X, UDes, Lfh, Lgh, UAct, Relax, rc, diag, ASIF_MEM_HOST, nullptr);
 			}
-			int32_t filter(const double x[], const double uDes[], double uAct[], double &relax)
-			{
-				int32_t rc = 0;
-				double ua = uAct[0], rl = 0.0;
-				const int32_t r = filterBatch(1, x, uDes, &ua, &rl, &rc);
-				if (r != ASIF_OK) return r;
-				if (rc == 1) { // the reference leaves uAct/relax untouched on failure (src/asif.cpp:207-209)
-					uAct[0] = ua;
-					relax = rl;
-				}
-				return rc;
-			}
+			// the reference leaves uAct / relax untouched on failure (src/asif.cpp:207-209)
+			int32_t filter(const double x[], const double uDes[], double uAct[], double &relax) { return filterOne(x, uDes, uAct, &relax); }
 
 		protected:
 			Model model_;
@@ -421,16 +476,13 @@ namespace ASIF
 				const int32_t r = build(options_, 0.0);
 				return r == 1 ? code : r;
 			}
-			int32_t filter(const double x[], const double uDes[], double uAct[], double &relax)
-			{
-				int32_t rc = 0;
-				const int32_t r = filterBatch(1, x, uDes, uAct, &relax, &rc);
-				return r == ASIF_OK ? rc : r;
-			}
-			// closed-loop rollout of n independent agents (example main loops), state resident on the device
+			int32_t filter(const double x[], const double uDes[], double uAct[], double &relax) { return filterOne(x, uDes, uAct, &relax); }
+			// closed-loop rollout of n independent agents (example main loops), state resident on the device(s)
 			int32_t rollout(const int64_t n, const int32_t steps, const double dt, double X[], const double UDes[],
 			                double UActLast[], int32_t rcLast[], int64_t rcHist[8] = nullptr)
 			{
+				if (engine_ == nullptr) return ASIF_ERR_INVALID_ARGUMENT;
+				if (group_) return asif_engine_group_rollout(group_, n, steps, dt, X, UDes, UActLast, rcLast, rcHist);
 				return asif_engine_rollout(engine_, n, steps, dt, X, UDes, UActLast, rcLast, rcHist, ASIF_MEM_HOST, nullptr);
 			}
 			// src/asif_implicit_tb.cpp:911-933
@@ -521,12 +573,7 @@ namespace ASIF
 				const int32_t r = build();
 				return r == 1 ? code : r;
 			}
-			int32_t filter(const double x[], const double uDes[], double uAct[], double relax[2])
-			{
-				int32_t rc = 0;
-				const int32_t r = filterBatch(1, x, uDes, uAct, relax, &rc);
-				return r == ASIF_OK ? rc : r;
-			}
+			int32_t filter(const double x[], const double uDes[], double uAct[], double relax[2]) { return filterOne(x, uDes, uAct, relax); }
 
 			// src/asif_implicit.cpp:829-842 (same in src/asif_implicit_robust.cpp:967-980)
 			static std::string filterErrorMsgString(const int32_t rc)
@@ -621,12 +668,7 @@ namespace ASIF
 				const int32_t r = build();
 				return r == 1 ? code : r;
 			}
-			int32_t filter(const double x[], const double uDes[], double uAct[], double relax[2])
-			{
-				int32_t rc = 0;
-				const int32_t r = filterBatch(1, x, uDes, uAct, relax, &rc);
-				return r == ASIF_OK ? rc : r;
-			}
+			int32_t filter(const double x[], const double uDes[], double uAct[], double relax[2]) { return filterOne(x, uDes, uAct, relax); }
 
 			// src/asif_implicit.cpp:829-842 (same in src/asif_implicit_robust.cpp:967-980)
 			static std::string filterErrorMsgString(const int32_t rc)
@@ -688,6 +730,7 @@ namespace ASIF
 			                  const int32_t device = 0)
 			    : table_(halfplanes, halfplanes + 2 * npSS), pMin_(pMin), pMax_(pMax), device_(device)
 			{
+				keepOnFailure_ = true;
 			}
 			int32_t initialize(const double lb[], const double ub[]) { return initialize(lb, ub, Options()); }
 			int32_t initialize(const double lb[], const double ub[], const Options &options)
@@ -707,18 +750,8 @@ namespace ASIF
 				cfg.n_halfplanes = (int32_t)(table_.size() / 2);
 				return create(cfg);
 			}
-			int32_t filter(const double x[], const double uDes[], double uAct[], double &relax)
-			{
-				int32_t rc = 0;
-				double ua = uAct[0], rl = 0.0;
-				const int32_t r = filterBatch(1, x, uDes, &ua, &rl, &rc);
-				if (r != ASIF_OK) return r;
-				if (rc == 1) { // uAct / relax untouched on failure (src/asif_robust.cpp:249-251)
-					uAct[0] = ua;
-					relax = rl;
-				}
-				return rc;
-			}
+			// uAct / relax untouched on failure (src/asif_robust.cpp:249-251)
+			int32_t filter(const double x[], const double uDes[], double uAct[], double &relax) { return filterOne(x, uDes, uAct, &relax); }
 
 		protected:
 			std::vector<double> table_;
@@ -752,6 +785,7 @@ namespace ASIF
 			{
 				unc_[0] = uncertaintyBounds[0];
 				unc_[1] = uncertaintyBounds[1];
+				keepOnFailure_ = true;
 			}
 			int32_t initialize(const double lb[], const double ub[]) { return initialize(lb, ub, Options()); }
 			int32_t initialize(const double lb[], const double ub[], const Options &options)
@@ -784,19 +818,7 @@ namespace ASIF
 			}
 			// relax[0] of the reference is a multiplier of its LP-dual formulation (not unique): reported as 0;
 			// relax[1] is the barrier relaxation eps.  rc: 1, -1 (QP infeasible), -2 (outside the kernel, no critical facet)
-			int32_t filter(const double x[], const double uDes[], double uAct[], double relax[2])
-			{
-				int32_t rc = 0;
-				double ua = uAct[0], rl[2] = {0.0, 0.0};
-				const int32_t r = filterBatch(1, x, uDes, &ua, rl, &rc);
-				if (r != ASIF_OK) return r;
-				if (rc == 1) {
-					uAct[0] = ua;
-					relax[0] = rl[0];
-					relax[1] = rl[1];
-				}
-				return rc;
-			}
+			int32_t filter(const double x[], const double uDes[], double uAct[], double relax[2]) { return filterOne(x, uDes, uAct, relax); }
 
 		protected:
 			std::vector<double> v_, n_;

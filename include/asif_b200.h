@@ -24,14 +24,19 @@
 extern "C" {
 #endif
 
-#define ASIF_B200_ABI_VERSION 2
+#define ASIF_B200_ABI_VERSION 3
 
-/* error codes (function return values) */
+/* error codes (function return values).  They start at -101 so that a wrapper which hands a function's failure on in place
+ * of a per-state return code (the single-state filter() of the host classes, QPWrapperB200::solve) can never be mistaken
+ * for one of the reference's own codes: -1 QP failed / backup input applied, -2 OSQP iteration limit, -3 backup set not
+ * reached or primal infeasible, -4 dual infeasible, -7 non-convex, -10 unsolved (src/asif_implicit_tb.cpp:300-361,
+ * OSQP 0.6 constants.h). */
 #define ASIF_OK 0
-#define ASIF_ERR_INVALID_ARGUMENT (-1)
-#define ASIF_ERR_UNSUPPORTED (-2)
-#define ASIF_ERR_CUDA (-3)
-#define ASIF_ERR_NO_DEVICE (-4)
+#define ASIF_ERR_INVALID_ARGUMENT (-101)
+#define ASIF_ERR_UNSUPPORTED (-102)
+#define ASIF_ERR_CUDA (-103)
+#define ASIF_ERR_NO_DEVICE (-104)
+#define ASIF_ERR_INTERNAL (-105) /* host-side failure (allocation, thread creation) caught at the C boundary */
 
 /* filter classes of the reference */
 #define ASIF_FILTER_EXPLICIT 1    /* ASIF::ASIF            include/asif.h:39-65           */
@@ -126,6 +131,8 @@ int32_t asif_engine_config_init(asif_engine_config *cfg, int32_t filter, int32_t
 /* constructor + initialize(lb, ub, options) of the filter classes
  * (e.g. src/asif_implicit_tb.cpp:89-154,169-232) */
 int32_t asif_engine_create(const asif_engine_config *cfg, asif_engine **out);
+/* An engine is NOT re-entrant: like the reference's filter objects (member scratch, SURVEY 8b "Threading") it keeps
+ * per-call state (staging slots, the cost mode of the running call), so use one engine per host thread, or a group. */
 int32_t asif_engine_destroy(asif_engine *e);
 
 /* dims[0..5] = nx, nu, n_relax, nc (rows of A), nv, n_diag (doubles per state of the diag record) */
@@ -182,6 +189,33 @@ int32_t asif_engine_filter_batch_lie(asif_engine *e, int64_t n, const double *x,
                                      void *stream);
 /* updateH alone (host pointer, nu x nu column-major) */
 int32_t asif_engine_set_input_cost(asif_engine *e, const double *H);
+
+/*
+ * Engine groups: ONE caller batch over several GPUs of one box (SURVEY 8b "device list", 8e).  States are independent, so
+ * the batch is cut into contiguous slices [g*ceil(n/G), (g+1)*ceil(n/G)), one per device, and there is no collective: each
+ * device has its own engine (options and tables replicated), host worker thread and streams, and runs the single-device
+ * host-memory path on its slice of the CALLER's arrays - results land in the caller's u_act / relax / rc, nothing is
+ * gathered afterwards.  devices = NULL (or n_devices <= 0) takes every visible device; cfg->device is ignored.
+ * All batch pointers are host memory (pinned arrays from asif_host_alloc are fastest, as for a single engine).
+ * A group runs one batch at a time; calls from several threads are serialised.  asif_engine_group_engine returns a
+ * borrowed handle of member i for the per-engine queries (asif_engine_dims, asif_engine_last_host_io, ...).
+ * Replaces, for the batched surface, the loop over filter() a multi-GPU caller of the reference API would write
+ * (include/asif_implicit_tb.h:93-110 and siblings).
+ */
+typedef struct asif_engine_group asif_engine_group;
+int32_t asif_engine_group_create(const asif_engine_config *cfg, const int32_t *devices, int32_t n_devices, asif_engine_group **out);
+int32_t asif_engine_group_destroy(asif_engine_group *g);
+int32_t asif_engine_group_size(const asif_engine_group *g); /* devices in the group, or a negative error */
+asif_engine *asif_engine_group_engine(asif_engine_group *g, int32_t i);
+/* bounds[0..1] = the slice [lo, hi) of an n-state batch that member i processes */
+int32_t asif_engine_group_slice(const asif_engine_group *g, int64_t n, int32_t i, int64_t bounds[2]);
+int32_t asif_engine_group_filter_batch(asif_engine_group *g, int64_t n, const double *x, const double *u_des, double *u_act,
+                                       double *relax, int32_t *rc, double *diag);
+int32_t asif_engine_group_filter_batch_cost(asif_engine_group *g, int64_t n, const double *x, const double *H, const double *c,
+                                            double *u_act, double *relax, int32_t *rc, double *diag);
+/* rc_hist[8] is summed over the members */
+int32_t asif_engine_group_rollout(asif_engine_group *g, int64_t n, int32_t steps, double dt, double *x, const double *u_des,
+                                  double *u_act_last, int32_t *rc_last, int64_t *rc_hist);
 
 /*
  * Closed-loop rollout as in the example main loops (examples/segway_implicit_tb.cpp:251-283):

@@ -144,6 +144,34 @@ class RefFilter:
         assert r == 0
         return x, u, rc, hist
 
+    def rollout_ex(self, x0, u_des, steps, dt):
+        """rollout + per agent the number of control steps whose QP ended in an inexact ADMM exit."""
+        x = np.array(x0, dtype=np.float64).reshape(-1, self.nx).copy()
+        u_des = np.ascontiguousarray(u_des, dtype=np.float64).reshape(-1, self.nu)
+        n = x.shape[0]
+        u, rc, hist, bad = np.zeros((n, self.nu)), np.zeros(n, dtype=np.int32), np.zeros(8, dtype=np.int64), np.zeros(n, dtype=np.int32)
+        L = self.lib.lib
+        L.ref_rollout_ex.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_double, _dp, _dp, _dp, _ip, C.POINTER(C.c_int64), _ip]
+        assert L.ref_rollout_ex(self.h, n, steps, dt, _d(x), _d(u_des), _d(u), rc.ctypes.data_as(_ip),
+                                hist.ctypes.data_as(C.POINTER(C.c_int64)), bad.ctypes.data_as(_ip)) == 0
+        return x, u, rc, hist, bad
+
+    def rollout_log(self, x0, u_des, steps, dt):
+        """rollout_ex + the state, output and return code of every filter() call: (x, u, rc, hist, bad, x_log, u_log, rc_log, st_log)."""
+        x = np.array(x0, dtype=np.float64).reshape(-1, self.nx).copy()
+        u_des = np.ascontiguousarray(u_des, dtype=np.float64).reshape(-1, self.nu)
+        n = x.shape[0]
+        u, rc, hist, bad = np.zeros((n, self.nu)), np.zeros(n, dtype=np.int32), np.zeros(8, dtype=np.int64), np.zeros(n, dtype=np.int32)
+        xl, ul = np.zeros((n, steps, self.nx)), np.zeros((n, steps, self.nu))
+        rl, sl = np.zeros((n, steps), dtype=np.int32), np.zeros((n, steps), dtype=np.int32)
+        L = self.lib.lib
+        L.ref_rollout_log.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_double, _dp, _dp, _dp, _ip, C.POINTER(C.c_int64), _ip,
+                                      _dp, _dp, _ip, _ip]
+        assert L.ref_rollout_log(self.h, n, steps, dt, _d(x), _d(u_des), _d(u), rc.ctypes.data_as(_ip),
+                                 hist.ctypes.data_as(C.POINTER(C.c_int64)), bad.ctypes.data_as(_ip), _d(xl), _d(ul),
+                                 rl.ctypes.data_as(_ip), sl.ctypes.data_as(_ip)) == 0
+        return x, u, rc, hist, bad, xl, ul, rl, sl
+
     def close(self):
         if self.h:
             self.lib.lib.ref_destroy(self.h)

@@ -123,8 +123,33 @@ int ref_filter_batch_lie(void *h, int64_t n, const double *x, const double *u_de
 	return 0;
 }
 
+/* inexact_steps (optional, per agent): control steps of that agent whose QP ended in one of the ADMM stand-in's inexact
+ * exits (iteration limit, "inaccurate" thresholds) - after such a step the agent's trajectory is no longer pinned */
+int ref_rollout_ex(void *h, int64_t n, int32_t steps, double dt, double *x, const double *u_des,
+                   double *u_act_last, int32_t *rc_last, int64_t *rc_hist, int32_t *inexact_steps);
+
 int ref_rollout(void *h, int64_t n, int32_t steps, double dt, double *x, const double *u_des,
                 double *u_act_last, int32_t *rc_last, int64_t *rc_hist)
+{
+	return ref_rollout_ex(h, n, steps, dt, x, u_des, u_act_last, rc_last, rc_hist, 0);
+}
+
+/* x_log[n][steps][nx], u_log[n][steps][nu], rc_log[n][steps], st_log[n][steps] (optional): the state every filter() call of the
+ * loop saw, what it returned, and whether that call's QP took an inexact ADMM exit (0/1) - "teacher forcing" data: the CUDA
+ * path is then evaluated call by call on exactly the states the reference's closed loop visited */
+int ref_rollout_log(void *h, int64_t n, int32_t steps, double dt, double *x, const double *u_des, double *u_act_last,
+                    int32_t *rc_last, int64_t *rc_hist, int32_t *inexact_steps, double *x_log, double *u_log, int32_t *rc_log,
+                    int32_t *st_log);
+
+int ref_rollout_ex(void *h, int64_t n, int32_t steps, double dt, double *x, const double *u_des,
+                   double *u_act_last, int32_t *rc_last, int64_t *rc_hist, int32_t *inexact_steps)
+{
+	return ref_rollout_log(h, n, steps, dt, x, u_des, u_act_last, rc_last, rc_hist, inexact_steps, 0, 0, 0, 0);
+}
+
+int ref_rollout_log(void *h, int64_t n, int32_t steps, double dt, double *x, const double *u_des, double *u_act_last,
+                    int32_t *rc_last, int64_t *rc_hist, int32_t *inexact_steps, double *x_log, double *u_log, int32_t *rc_log,
+                    int32_t *st_log)
 {
 	RefFilter *f = (RefFilter *)h;
 	if (!f) return -1;
@@ -135,9 +160,17 @@ int ref_rollout(void *h, int64_t n, int32_t steps, double dt, double *x, const d
 		double *xk = x + k * nx;
 		int32_t rc = 0;
 		for (int j = 0; j < nu; j++) ua[j] = 0.0;
+		int32_t inexact = 0;
 		for (int32_t s = 0; s < steps; s++) {
 			double r[2];
+			const long long inexact0 = osqp_shim_inexact_count();
+			if (x_log) for (int i = 0; i < nx; i++) x_log[(k * steps + s) * nx + i] = xk[i];
 			rc = f->filter(xk, u_des + k * nu, ua.data(), r, 0);
+			const int bad = osqp_shim_inexact_count() != inexact0;
+			if (bad) inexact++;
+			if (u_log) for (int j = 0; j < nu; j++) u_log[(k * steps + s) * nu + j] = ua[j];
+			if (rc_log) rc_log[k * steps + s] = rc;
+			if (st_log) st_log[k * steps + s] = bad;
 			if (rc_hist) rc_hist[(rc >= -3 && rc <= 2) ? rc + 3 : 7]++;
 			/* plant step exactly as the example mains: fCl = 0; fCl += f; fCl += g*uAct; x += dt*fCl
 			   (examples/segway_implicit_tb.cpp:265-283) */
@@ -151,6 +184,7 @@ int ref_rollout(void *h, int64_t n, int32_t steps, double dt, double *x, const d
 		}
 		for (int j = 0; j < nu; j++) u_act_last[k * nu + j] = ua[j];
 		rc_last[k] = rc;
+		if (inexact_steps) inexact_steps[k] = inexact;
 	}
 	return 0;
 }

@@ -131,6 +131,40 @@ def unpinned_mask(rc_ref, rc_exact, relax_exact, qp_status=None):
     return m
 
 
+# Disagreements of the committed reference vectors with an EXACT solver, counted with the oracle in this container (round 2):
+# every one of them is a state where the reference build's ADMM stand-in left its loop inexactly (unpinned_mask).  The
+# golden tests compare EVERY state, require that each disagreement is such a state, and bound their number by these
+# measured counts (no percentage masks).
+GOLDEN_UNPINNED = {"c1_di_explicit": 0, "c2_di_implicit_tb": 2, "c3a_ip_implicit_short": 15, "c3a_ip_implicit": 0, "c3b_ip_robust": 3,
+                   "c4_ip_realizable": 7, "c5_segway_tb": 0, "rb_ip_implicit": 6, "rb_di_implicit": 5}
+
+
+def disagree(got, want):
+    """states on which two result sets differ by the north-star bar (rc; u or relax outside 1e-6 + 1e-5 |.|)"""
+    u, relax, rc = got
+    u0, relax0, rc0 = want
+    du = np.abs(u - u0).max(axis=1) > 1e-6 + 1e-5 * np.abs(u0).max(axis=1)
+    dr = np.abs(relax - relax0).max(axis=1) > 1e-6 + 1e-5 * np.abs(relax0).max(axis=1)
+    return (rc != rc0) | du | (dr & (rc0 == 1))
+
+
+def assert_golden_parity(name, got, g, relax_cols=None, knife_edge=0):
+    """got = (u, relax, rc) against the golden record g (u_act, relax, rc, qp_status).  All states are compared; a
+    disagreement must lie in the unpinned class and there may be at most GOLDEN_UNPINNED[name] (+ knife_edge flips for
+    the models whose device libm differs from glibc in the last bit) of them."""
+    u, relax, rc = got
+    rl, rl0 = relax, g["relax"]
+    if relax_cols is not None:
+        rl, rl0 = relax[:, relax_cols], g["relax"][:, relax_cols]
+    D = disagree((u, rl, rc), (g["u_act"], rl0, g["rc"]))
+    unp = unpinned_mask(g["rc"], rc, relax, g["qp_status"] if "qp_status" in g.files else None)
+    print("golden %s: %d states, %d disagree with the reference build, %d of them unpinned (budget %d)" % (
+        name, len(rc), D.sum(), (D & unp).sum(), GOLDEN_UNPINNED[name]))
+    assert (D & ~unp).sum() <= knife_edge, "%s: unexplained disagreements at %s" % (name, np.nonzero(D & ~unp)[0][:10])
+    assert (D & unp).sum() <= GOLDEN_UNPINNED[name] + knife_edge
+    return ~D
+
+
 EXTRA_GOLDEN_JOBS = [
     lambda: ("c3a_ip_implicit_short", 3, C3A_SHORT_OPTS, c3a_inputs(1200)),
     lambda: ("c3a_ip_implicit", 3, C3A_OPTS, c3a_inputs(60, seed=SEED + 33)),

@@ -32,7 +32,7 @@ def test_exports_every_declared_symbol(lib):
     assert len(names) >= 11
     for n in names:
         assert hasattr(lib, n), "libasif_b200.so does not export %s" % n
-    assert lib.asif_b200_abi_version() == 2
+    assert lib.asif_b200_abi_version() == 3
 
 
 def test_struct_layout_matches(lib):
@@ -57,14 +57,14 @@ def test_argument_validation_and_no_fallback(lib):
     lib.asif_engine_config_init(C.byref(cfg), asif_b200.FILTER_IMPLICIT_TB, asif_b200.MODEL_DOUBLE_INTEGRATOR_TB)
     h = C.c_void_p()
     cfg.struct_size = 12
-    assert lib.asif_engine_create(C.byref(cfg), C.byref(h)) == -1  # ASIF_ERR_INVALID_ARGUMENT
-    assert lib.asif_engine_create(None, C.byref(h)) == -1
-    assert lib.asif_engine_filter_batch(None, 1, None, None, None, None, None, None, 0, None) == -1
+    assert lib.asif_engine_create(C.byref(cfg), C.byref(h)) == -101  # ASIF_ERR_INVALID_ARGUMENT
+    assert lib.asif_engine_create(None, C.byref(h)) == -101
+    assert lib.asif_engine_filter_batch(None, 1, None, None, None, None, None, None, 0, None) == -101
     n_dev = lib.asif_device_count()
     if n_dev <= 0:
         # without a device nothing computes: create fails with ASIF_ERR_NO_DEVICE and says why
         lib.asif_engine_config_init(C.byref(cfg), asif_b200.FILTER_IMPLICIT_TB, asif_b200.MODEL_DOUBLE_INTEGRATOR_TB)
-        assert lib.asif_engine_create(C.byref(cfg), C.byref(h)) == -4
+        assert lib.asif_engine_create(C.byref(cfg), C.byref(h)) == -104
         assert b"no CPU fallback" in lib.asif_last_error()
         with pytest.raises(asif_b200.AsifError):
             asif_b200.Engine(asif_b200.FILTER_EXPLICIT, asif_b200.MODEL_DOUBLE_INTEGRATOR)
@@ -103,7 +103,7 @@ def test_loop_config_defaults_and_argument_checks(lib):
     assert c.struct_size == C.sizeof(capi.LoopConfig)
     assert c.dt == 1e-3 and c.steps_per_sample == 1 and c.smooth_bounds == 0 and c.log_after_step == 1
     assert (c.smooth_lb, c.smooth_ub) == (-20.0, 20.0) and c.plant_gain == 1.0
-    assert L.asif_engine_closed_loop(None, 1, C.byref(c), None, None, None, None, None, None, None, 0, None) == -1
+    assert L.asif_engine_closed_loop(None, 1, C.byref(c), None, None, None, None, None, None, None, 0, None) == -101
     assert b"NULL" in L.asif_last_error()
     f = capi.loop_log_fields(2, 1, 2)
     assert f["t"] == 0 and f["x0"] == 1 and f["xEstim0"] == 3 and f["relax1"] == f["rc"] - 1 and len(f) == 16

@@ -68,10 +68,7 @@ def test_golden_on_gpu(ab):
     g = np.load(os.path.join(gold, "c2_di_implicit_tb.npz"))
     eng = ab.Engine(ab.FILTER_IMPLICIT_TB, ab.MODEL_DOUBLE_INTEGRATOR_TB, **cf.tb_engine_kwargs(list(g["opts"])))
     u, relax, rc, diag = eng.filter_batch(g["x"], g["u_des"], want_diag=True)
-    unp = cf.unpinned_mask(g["rc"], rc, relax, g["qp_status"])
-    assert unp.mean() < 0.01
-    k = ~unp
-    cf.assert_parity("golden C2", (u[k], relax[k], rc[k]), (g["u_act"][k], g["relax"][k], g["rc"][k]))
+    k = cf.assert_golden_parity("c2_di_implicit_tb", (u, relax, rc), g)
     m = k & (g["rc"] == 1)
     d0 = g["diag"]
     assert np.array_equal(diag[m][:, :3], d0[m][:, :3]) and np.array_equal(diag[m][:, 4:], d0[m][:, 4:])
@@ -80,9 +77,7 @@ def test_golden_on_gpu(ab):
     eng = ab.Engine(ab.FILTER_ROBUST, ab.MODEL_INVERTED_PENDULUM_TABLE, relaxLb=o[0], relaxCost=o[1], dynParam=[o[2], o[3]],
                     halfplanes=cf.halfplane_table())
     u, relax, rc = eng.filter_batch(g["x"], g["u_des"])
-    unp = cf.unpinned_mask(g["rc"], rc, relax, g["qp_status"])
-    k = ~unp
-    cf.assert_parity("golden C3b", (u[k], relax[k], rc[k]), (g["u_act"][k], g["relax"][k], g["rc"][k]))
+    cf.assert_golden_parity("c3b_ip_robust", (u, relax, rc), g)
 
 
 def test_robust_large_table(ab):
@@ -150,10 +145,7 @@ def test_implicit_rb_golden_on_gpu(ab):
         g = np.load(os.path.join(gold, name + ".npz"))
         eng = ab.Engine(ab.FILTER_IMPLICIT_RB, model, **cf.rb_engine_kwargs(list(g["opts"])))
         u, relax, rc, diag = eng.filter_batch(g["x"], g["u_des"], want_diag=True)
-        unp = cf.unpinned_mask(g["rc"], rc, relax, g["qp_status"])
-        assert unp.mean() < 0.03
-        k = ~unp
-        cf.assert_parity("golden " + name, (u[k], relax[k], rc[k]), (g["u_act"][k], g["relax"][k], g["rc"][k]))
+        cf.assert_golden_parity(name, (u, relax, rc), g, knife_edge=0 if name == "rb_di_implicit" else 1)
         if name == "rb_di_implicit":
             assert np.array_equal(diag, g["diag"])
         else:

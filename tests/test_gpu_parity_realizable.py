@@ -43,7 +43,5 @@ def test_c4_realizable_golden(ab):
     k = ~tainted
     assert np.array_equal(diag[k][:, :6], g["diag"][k][:, :6])  # critical facets and barrier facets
     assert np.abs(diag[k] - g["diag"][k]).max() <= 1e-12
-    r1 = relax.copy()
-    r0 = g["relax"].copy()
-    r1[:, 0] = r0[:, 0] = 0.0  # relax[0] of the reference is a non-unique LP-dual multiplier
-    cf.assert_parity("golden C4", (u[k], r1[k], rc[k]), (g["u_act"][k], r0[k], g["rc"][k]))
+    # relax[0] of the reference is a non-unique LP-dual multiplier: relax[1] is compared, on EVERY state
+    cf.assert_golden_parity("c4_ip_realizable", (u, relax, rc), g, relax_cols=[1])

@@ -14,10 +14,7 @@ def run(oracle, name):
     g = np.load(os.path.join(GOLD, name + ".npz"))
     cfg, opts = int(g["cfg"]), list(g["opts"])
     u, relax, rc, diag = oracle.filter_batch(cfg, g["x"], g["u_des"], opts, want_diag=True)
-    unp = cf.unpinned_mask(g["rc"], rc, relax, g["qp_status"])
-    assert unp.mean() < 0.03, "%s: %d unpinned states" % (name, unp.sum())
-    k = ~unp
-    cf.assert_parity(name, (u[k], relax[k], rc[k]), (g["u_act"][k], g["relax"][k], g["rc"][k]))
+    k = cf.assert_golden_parity(name, (u, relax, rc), g)  # every state compared; disagreements counted against the measured budget
     return g, diag, k, rc
 
 
@@ -53,9 +50,8 @@ def test_c4_realizable_golden(oracle):
     k = ~tainted
     assert np.array_equal(diag[k][:, :6], g["diag"][k][:, :6])
     assert np.array_equal(diag[k], g["diag"][k])  # table gathers and barrier rows: same bits
-    r1, r0 = relax.copy(), g["relax"].copy()
-    r1[:, 0] = r0[:, 0] = 0.0
-    cf.assert_parity("C4", (u[k], r1[k], rc[k]), (g["u_act"][k], r0[k], g["rc"][k]))
+    # relax[0] of the reference is a non-unique LP-dual multiplier: relax[1] (eps) is compared, on EVERY state
+    cf.assert_golden_parity("c4_ip_realizable", (u, relax, rc), g, relax_cols=[1])
     assert (g["rc"] == -2).sum() > 50 and (g["diag"][:, 0] >= 1).sum() > 100
 
 
