@@ -100,6 +100,7 @@ def load_library():
                                       C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.c_int32, C.c_void_p]
     L.asif_engine_last_qp_iterations.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
     L.asif_engine_last_host_io.argtypes = [C.c_void_p, C.POINTER(C.c_int32)]
+    L.asif_engine_host_io_stats.argtypes = [C.c_void_p, _dp, _ip]
     L.asif_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_uint64]
     L.asif_host_free.argtypes = [C.c_void_p]
     L.asif_host_register.argtypes = [C.c_void_p, C.c_uint64]
@@ -352,6 +353,12 @@ class Engine:
         v = C.c_int32()
         _check(load_library().asif_engine_last_host_io(self._h, C.byref(v)))
         return int(v.value)
+
+    def host_io_stats(self):
+        """{mode name: (ms per 1e6 states, batches measured)} of the "auto" host-IO policy"""
+        ms, k = (C.c_double * 3)(), (C.c_int32 * 3)()
+        _check(load_library().asif_engine_host_io_stats(self._h, ms, k))
+        return {nm: (float(ms[i]), int(k[i])) for i, nm in enumerate(("staged", "out", "inout"))}
 
     def last_qp_iterations(self):
         v = C.c_uint64()

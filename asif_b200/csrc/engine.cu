@@ -13,6 +13,7 @@
 #include "qp_batch_kernel.cuh"
 #include "tb_kernel.cuh"
 
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -736,20 +737,55 @@ bool bounce_enabled()
 //   "out"     the kernels store uAct / relax / rc straight into the caller's pinned arrays over PCIe (posted writes,
 //             whole 128 / 256 B lines per warp): no D2H copies, no drain; inputs still arrive by chunked H2D copies
 //   "inout"   one launch over the caller's pinned arrays, inputs read over PCIe by the kernel as well
-//   "auto"    (default) "inout" for the trajectory-integrating and realizable filters, whose kernel time per state is
-//             at least the link time per state (loads and stores of one warp hide behind the arithmetic of the others;
-//             no pipeline fill or drain), "staged" for the explicit and robust filters, whose kernels are much shorter
-//             than their copies, so the copy engines' larger PCIe payloads win.  Measured on B200, ms per batch as
-//             staged / out / inout: C1 0.73 / 1.02 / 0.89, C2 (1e7) 6.06 / 5.97 / 5.27, C3a 32.1 / 31.8 / 32.5,
-//             C3b 1.02 / 1.30 / 1.43, C4 1.40 / 1.15 / 1.00, C5-filter 12.7 / 12.5 / 12.1 (gpurun_out/configs_e2e.jsonl).
+//   "auto"    (default) MEASURED per engine: which of "staged" and "inout" is faster depends on the filter class (kernel
+//             time per state against link time per state) AND on what else uses the box's host side - with one GPU the
+//             in-place launch wins for the trajectory-integrating classes (C2 5.27 vs 6.06 ms per 1e7 states), with four
+//             GPUs sharing the host bridge the copy engines' larger PCIe payloads won (round 1, SCALE N = 4).  So the
+//             first large batch runs the class default (below), the second the other mode, later ones the faster of the
+//             two (wall clock per state, exponentially averaged), and every 32nd batch re-tries the slower one.  Results
+//             are the same bits in every mode, so the choice is free.  asif_engine_host_io_stats reports the averages.
+//             Small batches (< 2^18 states) keep the class default: "inout" for the trajectory-integrating and realizable
+//             filters, "staged" for the explicit and robust ones (ms per batch staged / out / inout, one GPU: C1 0.73 /
+//             1.02 / 0.89, C2 6.06 / 5.97 / 5.27, C3a 32.1 / 31.8 / 32.5, C3b 1.02 / 1.30 / 1.43, C4 1.40 / 1.15 / 1.00,
+//             C5-filter 12.7 / 12.5 / 12.1; profiles/r01_config_e2e_host_io.jsonl).
 // Every mode falls back to "staged" when an array it needs is not device-addressable.
-int host_io_mode(const asif_engine *e)
+constexpr int64_t HOST_IO_PROBE_MIN_STATES = (int64_t)1 << 18;
+
+int host_io_forced()
 {
 	const char *v = getenv("ASIF_B200_HOST_IO"); // read per call: a test or a caller may switch it between batches
 	if (v && !strcmp(v, "staged")) return 0;
 	if (v && !strcmp(v, "out")) return 1;
 	if (v && !strcmp(v, "inout")) return 2;
+	return -1;
+}
+
+int host_io_class_default(const asif_engine *e)
+{
 	return (e->cfg.filter == ASIF_FILTER_EXPLICIT || e->cfg.filter == ASIF_FILTER_ROBUST) ? 0 : 2;
+}
+
+// the mode this batch runs in; *probe says whether its wall time is to be recorded
+int host_io_mode(asif_engine *e, int64_t n, bool *probe)
+{
+	*probe = false;
+	const int forced = host_io_forced();
+	if (forced >= 0) return forced;
+	const int dflt = host_io_class_default(e), other = dflt == 2 ? 0 : 2;
+	if (n < HOST_IO_PROBE_MIN_STATES) return dflt;
+	*probe = true;
+	if (e->io_samples[dflt] == 0) return dflt;
+	if (e->io_samples[other] == 0) return other;
+	const int best = e->io_ms_per_state[other] < e->io_ms_per_state[dflt] ? other : dflt;
+	if (++e->io_calls % 32 == 0) return best == dflt ? other : dflt; // conditions change (other ranks start or stop): look again
+	return best;
+}
+
+void host_io_record(asif_engine *e, int mode, int64_t n, double ms)
+{
+	const double per = ms / (double)n;
+	e->io_ms_per_state[mode] = e->io_samples[mode] ? 0.5 * e->io_ms_per_state[mode] + 0.5 * per : per;
+	e->io_samples[mode]++;
 }
 
 // switches the kernels of this engine between updateCost(uDes) and the caller's linear cost (filter(x, H, c, ...))
@@ -828,7 +864,13 @@ int32_t filter_batch_impl(asif_engine *e, int64_t n, const double *x, const doub
 	// device aliases of the caller's output arrays (nullptr: pageable or unmapped memory, staged copies then)
 	double *m_ua = nullptr, *m_relax = nullptr, *m_diag = nullptr;
 	int32_t *m_rc = nullptr;
-	const int io = host_io_mode(e);
+	bool probe = false;
+	const int io = host_io_mode(e, n, &probe);
+	const auto t_io0 = std::chrono::steady_clock::now();
+	auto record = [&](int mode) { // wall time of this batch into the engine's per-mode average ("auto" policy)
+		if (probe && mode == io)
+			host_io_record(e, mode, n, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_io0).count());
+	};
 	if (io >= 1) {
 		m_ua = mapped_alias(u_act, (size_t)n * nu);
 		m_relax = mapped_alias(relax, (size_t)n * nr);
@@ -847,6 +889,7 @@ int32_t filter_batch_impl(asif_engine *e, int64_t n, const double *x, const doub
 			const int r = launch_filter(e, n, m_x, m_ud, m_ua, m_relax, m_rc, m_diag, e->slot[0].stream);
 			if (r) return r;
 			CUDA_TRY(cudaStreamSynchronize(e->slot[0].stream));
+			record(2);
 			return ASIF_OK;
 		}
 	}
@@ -949,6 +992,7 @@ int32_t filter_batch_impl(asif_engine *e, int64_t n, const double *x, const doub
 		if (s.stream) CUDA_TRY(cudaStreamSynchronize(s.stream));
 		if (bounce_out) copy_out(s);
 	}
+	if (!bounce_in && !bounce_out) record(direct_out ? 1 : 0); // pinned arrays only: pageable batches say nothing about the link
 	return ASIF_OK;
 }
 } // namespace
@@ -1142,6 +1186,16 @@ int32_t asif_engine_last_host_io(const asif_engine *e, int32_t *mode)
 {
 	if (!e || !mode) return fail(ASIF_ERR_INVALID_ARGUMENT, "NULL argument");
 	*mode = e->last_host_io;
+	return ASIF_OK;
+}
+
+int32_t asif_engine_host_io_stats(const asif_engine *e, double ms_per_1e6_states[3], int32_t samples[3])
+{
+	if (!e || !ms_per_1e6_states || !samples) return fail(ASIF_ERR_INVALID_ARGUMENT, "NULL argument");
+	for (int i = 0; i < 3; i++) {
+		ms_per_1e6_states[i] = e->io_ms_per_state[i] * 1e6;
+		samples[i] = e->io_samples[i];
+	}
 	return ASIF_OK;
 }
 

@@ -88,6 +88,10 @@ struct asif_engine {
 	int copy_threads = 0;         // its thread count; 0 = HostCopier::default_threads() (a group shares the cores out)
 	char *small_h = nullptr;      // pinned, device-addressable scratch of the small-batch path (SMALL_BATCH_BYTES)
 	int last_host_io = -1; // ASIF_HOST_IO_* actually used by the last host-memory batch (-1: none yet)
+	// "auto" host-IO policy: wall time per state of large pinned batches per mode (exponential average), batches seen
+	double io_ms_per_state[3] = {0.0, 0.0, 0.0};
+	int io_samples[3] = {0, 0, 0};
+	unsigned io_calls = 0;
 	int num_sms = 148;
 	// snapshot scratch of the persistent nx = 4 kernels: a ring, so that launches on different streams never share
 	// a buffer that may still be in use (the next user waits on the previous user's event)

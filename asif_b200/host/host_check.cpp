@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstring>
 #include <memory>
+#include <vector>
 
 static int fail(const char *what)
 {
@@ -18,9 +19,56 @@ static int fail(const char *what)
 	return 1;
 }
 
-int main()
+// host_check --update-options <in.bin> <out.bin>: the sequence initialize(opts1) -> filterBatch -> updateOptions(opts2) ->
+// filterBatch of FilterBatchImplicitTB on caller-given states, written out for tests/test_gpu_dropin.py, which runs the same
+// sequence through the reference build's ASIFimplicitTB (src/asif_implicit_tb.cpp:169-232, 365-405).
+// in.bin:  int64 n, double opts1[9], double opts2[9], double x[n][2], double uDes[n]   (option order of the reference harness)
+// out.bin: int32 code of updateOptions, then twice { double u[n], double relax[n], int32 rc[n] }
+static int update_options_mode(const char *in_path, const char *out_path)
 {
 	using namespace ASIF;
+	std::ifstream in(in_path, std::ios::binary);
+	int64_t n = 0;
+	double o1[9], o2[9];
+	in.read((char *)&n, sizeof(n));
+	in.read((char *)o1, sizeof(o1));
+	in.read((char *)o2, sizeof(o2));
+	if (!in || n <= 0) return fail("update-options: bad input file");
+	std::vector<double> X(2 * n), U(n), UA(n), R(n);
+	std::vector<int32_t> rc(n);
+	in.read((char *)X.data(), sizeof(double) * 2 * n);
+	in.read((char *)U.data(), sizeof(double) * n);
+	if (!in) return fail("update-options: short input file");
+	auto to_opts = [](const double *o) {
+		b200::FilterBatchImplicitTB::Options t;
+		t.relaxCost = o[0]; t.relaxSafeLb = o[1]; t.relaxTTS = o[2]; t.relaxMinOrtho = o[3]; t.backTrajHorizon = o[4];
+		t.backTrajExtend = o[5]; t.backTrajDt = o[6]; t.backTrajMinOrtho = o[7]; t.satSharpness = o[8];
+		return t;
+	};
+	b200::FilterBatchImplicitTB asif(b200::Model::DoubleIntegratorTB, 4);
+	const double lb[1] = {-1.0}, ub[1] = {1.0};
+	if (asif.initialize(lb, ub, to_opts(o1)) != 1) return fail("update-options: initialize");
+	std::ofstream out(out_path, std::ios::binary);
+	if (asif.filterBatch(n, X.data(), U.data(), UA.data(), R.data(), rc.data()) != 0) return fail("update-options: filterBatch 1");
+	std::vector<double> UA1 = UA, R1 = R;
+	std::vector<int32_t> rc1 = rc;
+	const int32_t code = asif.updateOptions(to_opts(o2));
+	if (asif.filterBatch(n, X.data(), U.data(), UA.data(), R.data(), rc.data()) != 0) return fail("update-options: filterBatch 2");
+	out.write((const char *)&code, sizeof(code));
+	out.write((const char *)UA1.data(), sizeof(double) * n);
+	out.write((const char *)R1.data(), sizeof(double) * n);
+	out.write((const char *)rc1.data(), sizeof(int32_t) * n);
+	out.write((const char *)UA.data(), sizeof(double) * n);
+	out.write((const char *)R.data(), sizeof(double) * n);
+	out.write((const char *)rc.data(), sizeof(int32_t) * n);
+	std::printf("update-options ok: code %d\n", code);
+	return out ? 0 : fail("update-options: write");
+}
+
+int main(int argc, char **argv)
+{
+	using namespace ASIF;
+	if (argc == 4 && std::string(argv[1]) == "--update-options") return update_options_mode(argv[2], argv[3]);
 	// --- 1. the QP backend behind the abstract interface: min (v0-2)^2 + 50 (v1-10)^2, v0 + v1 >= 13, 0<=v0<=1
 	{
 		std::unique_ptr<QPWrapperAbstract> qp(new QPWrapperB200(2, 1, true));

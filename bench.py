@@ -13,6 +13,11 @@ its own 10^7-state slice, no collective on the data path).
   cpu_baseline  the reference's own filter() loop (oracle/_ref = reference sources + OSQP stand-in)
              on the host cores, bounded sample
 
+  extra_keys  per-config device-resident numbers with a roofline each (C1 at 1e6 and 1e8 states, C3a, C3b, C4, C5 filter,
+             C5 fleet rollout), a >= 2 s sustained leg of the headline kernel, the strong-scaling split of 1e7 states
+             over the N ranks (BASELINE configs[1] as worded), the copy-only H2D+D2H ceiling of the box at this N,
+             the pageable-caller leg and - with several visible GPUs in one process - the engine-group leg
+
 `--impl reference` times that CPU loop alone (all host threads) and prints the same JSON shape.
 Only the cpu_baseline leg and --impl reference touch oracle/; the GPU path is the C ABI of
 asif_b200/libasif_b200.so and fails loudly if the library or the device is missing.
@@ -201,6 +206,132 @@ def workload_config(n_gpus):
             "no collective)" % n_gpus, "l2": "inputs larger than L2 (240 MB in, 200 MB out per step)"}
 
 
+# ---- per-config legs (extra_keys): workloads of SURVEY 8d, algorithmic work per state as DESIGN.md section 4 states it ----
+def _wl():
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import conftest as cf  # the named workloads (inputs, option vectors, tables) live with the parity tests
+    return cf
+
+
+def qp_flops(rows_per_state, m, nv):
+    """direct dual active-set method ("use that method's operation count"): one violation scan of the m rows per
+    processed row + 1, (2 nv + 1) flops per row, and ~30 nv flops per active-set step"""
+    return (rows_per_state + 1.0) * m * (2 * nv + 1) + rows_per_state * 30.0 * nv
+
+
+def config_leg(torch, ab, dev, name, eng, x, ud, reps, flops_fn, bytes_per_state, p64, hbm_peak, note=""):
+    n = x.shape[0]
+    xd, udd = torch.from_numpy(x).to(dev), torch.from_numpy(ud).to(dev)
+    ua = torch.empty((n, eng.nu), dtype=torch.float64, device=dev)
+    rl = torch.empty((n, eng.n_relax), dtype=torch.float64, device=dev)
+    rc = torch.empty((n,), dtype=torch.int32, device=dev)
+    st = torch.cuda.current_stream()
+    for _ in range(3):
+        eng.filter_batch_into(n, xd, udd, ua, rl, rc, stream=st.cuda_stream)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(st)
+    for _ in range(reps):
+        eng.filter_batch_into(n, xd, udd, ua, rl, rc, stream=st.cuda_stream)
+    e1.record(st)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    rows = eng.last_qp_iterations() / n
+    fl = flops_fn(rows)
+    tf, gbs = fl * n / (ms * 1e-3) / 1e12, bytes_per_state * n / (ms * 1e-3) / 1e9
+    f64, fhbm = tf / p64, gbs / hbm_peak
+    hist = {int(k): int(v) for k, v in zip(*np.unique(rc.cpu().numpy(), return_counts=True))}
+    out = {"config": name, "states": n, "ms": ms, "states_per_s": n / (ms * 1e-3), "launches_timed": reps,
+           "rc_histogram": hist, "qp_rows_per_state": rows,
+           "roofline": {"bound": "fp64" if f64 >= fhbm else "hbm", "flops_per_state": fl, "bytes_per_state": bytes_per_state,
+                        "achieved_tflops": tf, "frac_fp64": f64, "achieved_gbs": gbs, "frac_hbm": fhbm,
+                        "frac": max(f64, fhbm)}}
+    if note:
+        out["note"] = note
+    del xd, udd, ua, rl, rc
+    return out
+
+
+def all_config_legs(torch, ab, dev, device_index, p64, hbm_peak):
+    cf = _wl()
+    legs = []
+    mk = lambda *a, **k: ab.Engine(*a, device=device_index, **k)  # noqa: E731
+    # C1: the one HBM-bound config; 1e6 states is launch/tail bound (40 us), 1e8 shows the asymptote
+    e = mk(ab.FILTER_EXPLICIT, ab.MODEL_DOUBLE_INTEGRATOR, relaxLb=cf.C1_OPTS[0], relaxCost=cf.C1_OPTS[1])
+    for n, reps in ((1_000_000, 50), (100_000_000, 5)):
+        x, ud = cf.c1_inputs(n)
+        legs.append(config_leg(torch, ab, dev, "C1 ASIF explicit / DoubleIntegrator, %.0e states" % n, e, x, ud, reps,
+                               lambda r: 2 * 4 * 2 * 2 + 4 * 6 + 20.0, 44, p64, hbm_peak,
+                               "closed-form 1-D QP (relax pinned): 2 npSS nx (1+nu) assembly flops + interval intersection"))
+        del x, ud
+    e.close()
+    # C3a: (N-1) (70 + sincos) + assembly + QP; transcendental calls are not counted as flops (SURVEY 8d)
+    x, ud = cf.c3a_inputs(1_000_000)
+    e = mk(ab.FILTER_IMPLICIT, ab.MODEL_INVERTED_PENDULUM, **cf.implicit_engine_kwargs(cf.C3A_OPTS))
+    legs.append(config_leg(torch, ab, dev, "C3a ASIFimplicit / InvertedPendulum npBT 5001, 1e6 states", e, x, ud, 3,
+                           lambda r: 5000 * 70.0 + (2 * 10 * 4 * 4 + 2 * 41 * 2 * 2) + qp_flops(r, 41 + 6, 3), 52, p64, hbm_peak,
+                           "5000 sincos calls per state are NOT credited as flops (they execute ~33 FP64 instructions each)"))
+    e.close()
+    x, ud = cf.c3b_inputs(1_000_000)
+    o = cf.C3B_OPTS
+    e = mk(ab.FILTER_ROBUST, ab.MODEL_INVERTED_PENDULUM_TABLE, relaxLb=o[0], relaxCost=o[1], dynParam=[o[2], o[3]],
+           halfplanes=cf.halfplane_table())
+    legs.append(config_leg(torch, ab, dev, "C3b ASIFrobust / InvertedPendulum + 100 half-planes, 1e6 states", e, x, ud, 20,
+                           lambda r: 100 * 10.0 + qp_flops(r, 200 + 4, 2), 44, p64, hbm_peak,
+                           "rows are recomputed from the table on every solver scan; credited once"))
+    e.close()
+    x, ud = cf.c4_inputs(1_000_000)
+    e = mk(ab.FILTER_REALIZABLE, ab.MODEL_INVERTED_PENDULUM_KERNEL, **cf.realizable_engine_kwargs(cf.C4_OPTS))
+    legs.append(config_leg(torch, ab, dev, "C4 ASIFrealizable / InvertedPendulum + 100Hz_50pt kernel, 1e6 states", e, x, ud, 20,
+                           lambda r: 50 * (4 + 8 + 12.0) + 2 * 20.0 + qp_flops(r, 18 + 2 + 4, 2), 52, p64, hbm_peak,
+                           "per facet: h (4), bounding-box test (8), exact segment/box test (12, credited for every facet)"))
+    e.close()
+    x, ud = cf.c5_inputs(1_000_000)
+    e = mk(ab.FILTER_IMPLICIT_TB, ab.MODEL_SEGWAY, **cf.tb_engine_kwargs(cf.SEGWAY_TB_OPTS))
+    leg = config_leg(torch, ab, dev, "C5 filter: ASIFimplicitTB / segway npBT 316, 1e6 states (one control step)", e, x, ud, 3,
+                     lambda r: 315 * 580.0 + 1500.0 + qp_flops(r, 18 + 4, 2), 60, p64, hbm_peak,
+                     "4 trig + tanh per Euler step not credited; lanes stop at their first hit, credited for the full horizon")
+    legs.append(leg)
+    # C5 proper: fleet rollout, state resident on the device
+    n, steps = 100_000, 1000
+    xd, udd = torch.from_numpy(x[:n].copy()).to(dev), torch.from_numpy(ud[:n].copy()).to(dev)
+    ua = torch.empty((n, 1), dtype=torch.float64, device=dev)
+    rc = torch.empty((n,), dtype=torch.int32, device=dev)
+    xw = xd.clone()
+    e.rollout_into(n, 10, 1e-3, xw, udd, ua, rc)  # warm-up on a copy
+    torch.cuda.synchronize()
+    st = torch.cuda.current_stream()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(st)
+    hist = e.rollout_into(n, steps, 1e-3, xd, udd, ua, rc, want_hist=True, stream=st.cuda_stream)
+    e1.record(st)
+    torch.cuda.synchronize()
+    sec = e0.elapsed_time(e1) * 1e-3
+    fl = leg["roofline"]["flops_per_state"]
+    legs.append({"config": "C5 segway fleet rollout: 1e5 agents x 1000 control steps, state resident on the device", "agents": n,
+                 "steps": steps, "seconds": sec, "state_steps_per_s": n * steps / sec, "rc_histogram_index_rc_plus_3": hist.tolist(),
+                 "x_finite": bool(torch.isfinite(xd).all().item()),
+                 "roofline": {"bound": "fp64", "flops_per_state": fl, "achieved_tflops": fl * n * steps / sec / 1e12,
+                              "frac": fl * n * steps / sec / 1e12 / p64}})
+    e.close()
+    return legs
+
+
+def copy_ceiling(torch, dev, n):
+    """H2D of one step's inputs and D2H of one step's outputs at the same time, nothing else: what the link allows"""
+    hx = torch.empty(n * 3, dtype=torch.float64).pin_memory()
+    ho = torch.empty(n * 5 // 2, dtype=torch.float64).pin_memory()
+    dx, do = torch.empty_like(hx, device=dev), torch.empty_like(ho, device=dev)
+    s1, s2 = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+
+    def both():
+        with torch.cuda.stream(s1):
+            dx.copy_(hx, non_blocking=True)
+        with torch.cuda.stream(s2):
+            ho.copy_(do, non_blocking=True)
+    return both, (hx, ho, dx, do)
+
+
 # =================================================================================================
 def main():
     ap = argparse.ArgumentParser()
@@ -210,6 +341,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--states", type=int, default=STATES_PER_GPU, help=argparse.SUPPRESS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra_keys legs (profiling runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
@@ -304,8 +436,97 @@ def main():
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     t_wall2 = time.time()
+    rc_h_np_first = rc_h.numpy().copy()
+    ua_h_np_first = ua_h.numpy().copy()
     clocks = sampler.stop(t_wall0, t_wall2)
-    same = bool(np.array_equal(rc_h.numpy(), rc_np) and np.array_equal(ua_h.numpy(), ua_d.cpu().numpy()))
+    same = bool(np.array_equal(rc_h_np_first, rc_np) and np.array_equal(ua_h_np_first, ua_d.cpu().numpy()))
+
+    host_io_used = eng.last_host_io()
+    extra = {}
+    if not args.no_extra:
+        # ---- (1) sustained: the headline kernel back to back for >= 2 s of device time, clocks sampled throughout
+        k_sus = max(args.steps, int(2200.0 / kern_ms) + 1)
+        s2 = ClockSampler(local_rank)
+        s2.start()
+        time.sleep(0.25)
+        barrier()
+        tw0 = time.time()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(k_sus):
+            eng.filter_batch_into(n, xd, ud, ua_d, rl_d, rc_d, stream=sp)
+        b.record(stream)
+        barrier()
+        tw1 = time.time()
+        sus_ms = max_over_ranks(a.elapsed_time(b))
+        extra["sustained"] = {"launches": k_sus, "seconds": sus_ms * 1e-3, "ms_per_step": sus_ms / k_sus,
+                              "states_per_s": n * world * k_sus / (sus_ms * 1e-3), "clocks": s2.stop(tw0, tw1),
+                              "vs_short_run_ms_per_step": (sus_ms / k_sus) / (ms_total / args.steps)}
+        # ---- (2) strong scaling: BASELINE configs[1] as worded - 1e7 states TOTAL, sharded over the N ranks
+        n_s = STATES_PER_GPU // world
+        for _ in range(2):
+            eng.filter_batch_into(n_s, xd[:n_s], ud[:n_s], ua_d[:n_s], rl_d[:n_s], rc_d[:n_s], stream=sp)
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(args.steps):
+            eng.filter_batch_into(n_s, xd[:n_s], ud[:n_s], ua_d[:n_s], rl_d[:n_s], rc_d[:n_s], stream=sp)
+        b.record(stream)
+        barrier()
+        st_ms = max_over_ranks(a.elapsed_time(b))
+        for _ in range(2):
+            eng.filter_batch_into(n_s, xh[:n_s], uh[:n_s], ua_h[:n_s], rl_h[:n_s], rc_h[:n_s])
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            eng.filter_batch_into(n_s, xh[:n_s], uh[:n_s], ua_h[:n_s], rl_h[:n_s], rc_h[:n_s])
+        torch.cuda.synchronize()
+        st_e2e = max_over_ranks(time.perf_counter() - t0)
+        extra["strong_scaling"] = {"total_states": n_s * world, "states_per_rank": n_s, "scaling": "strong",
+                                   "value": n_s * world * args.steps / (st_ms * 1e-3), "ms_per_step": st_ms / args.steps,
+                                   "e2e_value": n_s * world * args.steps / st_e2e, "e2e_ms_per_step": 1e3 * st_e2e / args.steps,
+                                   "unit": "states/s"}
+        # ---- (3) copy-only ceiling of the box at this N: every rank moves one step's inputs H2D and outputs D2H at once
+        both, keep = copy_ceiling(torch, dev, n)
+        for _ in range(2):
+            both()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            both()
+        torch.cuda.synchronize()
+        cp_s = max_over_ranks(time.perf_counter() - t0)
+        del keep
+        extra["copy_ceiling"] = {"ms_per_step": 1e3 * cp_s / args.steps, "aggregate_GB_per_s": BYTES_PER_STATE * n * world * args.steps / cp_s / 1e9,
+                                 "states_per_s_if_copies_were_everything": n * world * args.steps / cp_s,
+                                 "e2e_fraction_of_ceiling": (n * world * args.steps / e2e_s) / (n * world * args.steps / cp_s),
+                                 "what": "H2D 24 B/state + D2H 20 B/state concurrently on two streams per rank, all ranks at once, pinned buffers"}
+        # ---- (4) a caller with plain (pageable) arrays: std::vector / numpy memory, bounced through pinned staging
+        ua_p, rl_p, rc_p = np.empty((n, 1)), np.empty((n, 1)), np.empty(n, dtype=np.int32)
+        eng.filter_batch_into(n, xh_np, uh_np, ua_p, rl_p, rc_p)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            eng.filter_batch_into(n, xh_np, uh_np, ua_p, rl_p, rc_p)
+        pg_s = max_over_ranks(time.perf_counter() - t0)
+        extra["e2e_pageable_caller"] = {"value": n * world * 3 / pg_s, "unit": "states/s", "ms_per_step": 1e3 * pg_s / 3,
+                                        "matches": bool(np.array_equal(rc_p, rc_np))}
+        del ua_p, rl_p, rc_p
+        extra["host_io_auto_policy_ms_per_1e6_states"] = eng.host_io_stats()
+        # ---- (5) one process, one host batch, every visible GPU: the engine-group entry (asif_engine_group_*)
+        if world == 1 and ab.device_count() > 1:
+            grp = ab.EngineGroup(ab.FILTER_IMPLICIT_TB, ab.MODEL_DOUBLE_INTEGRATOR_TB, relaxCost=C2_OPTS[0], relaxLb=C2_OPTS[1],
+                                 relaxTTS=C2_OPTS[2], relaxMinOrtho=C2_OPTS[3], backTrajHorizon=C2_OPTS[4], backTrajExtend=C2_OPTS[5],
+                                 backTrajDt=C2_OPTS[6], backTrajMinOrtho=C2_OPTS[7], satSharpness=C2_OPTS[8])
+            for _ in range(3):
+                grp.filter_batch_into(n, xh, uh, ua_h, rl_h, rc_h)
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                grp.filter_batch_into(n, xh, uh, ua_h, rl_h, rc_h)
+            g_s = time.perf_counter() - t0
+            extra["engine_group_e2e"] = {"devices": grp.size, "states": n, "value": n * args.steps / g_s, "unit": "states/s",
+                                         "ms_per_step": 1e3 * g_s / args.steps, "matches_device_resident": bool(np.array_equal(rc_h.numpy(), rc_np))}
+            grp.close()
 
     value = n * world * args.steps / (ms_total * 1e-3)
     e2e_value = n * world * args.steps / e2e_s
@@ -331,7 +552,7 @@ def main():
         "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(world),
         "e2e": {"value": e2e_value, "unit": "states/s", "h2d_bytes_per_step": 24 * n, "d2h_bytes_per_step": 20 * n,
                 "ms_per_step": 1e3 * e2e_s / args.steps, "matches_device_resident": same, "host_binding": numa,
-                "host_io": {0: "staged", 1: "out", 2: "inout"}.get(eng.last_host_io(), "?") + " (ASIF_B200_HOST_IO=%s)" % os.environ.get("ASIF_B200_HOST_IO", "auto")},
+                "host_io": {0: "staged", 1: "out", 2: "inout"}.get(host_io_used, "?") + " (ASIF_B200_HOST_IO=%s)" % os.environ.get("ASIF_B200_HOST_IO", "auto")},
         "gpu_launches": args.steps,
         "roofline": {"bound": "fp64", "achieved": ach_tf, "peak": p64_tflops, "unit": "TFLOP/s", "frac": ach_tf / p64_tflops,
                      "traffic": traffic, "kernel": "tb_filter_kernel<DoubleIntegratorTB,4,false>",
@@ -341,6 +562,19 @@ def main():
                          "bytes_per_state": BYTES_PER_STATE, "peak_source": hbm_src},
         "rc_histogram": hist, "qp_rows_per_state": qp_rows, "clocks": clocks,
     }
+    line["roofline"]["credited_vs_executed"] = (
+        "credited %.0f flop/state (SURVEY 8d: 88 per Euler step + assembly + QP); the kernel executes ~33 FP64 instructions per "
+        "Euler step with FMA contraction off and structural zeros skipped, i.e. credited/executed ~ 2.1: the hardware-side view "
+        "is ncu's FP64-pipe utilisation in profiles/ (r01: 70 %% busy, 72 %% issue slots)" % fl)
+    if traffic is not None:
+        line["roofline"]["traffic_source"] = "profiles/traffic.json (one ncu --set full capture; see its 'source' field for the build)"
+    if extra:
+        line["extra_keys"] = extra
+    if rank == 0 and world == 1 and not args.no_extra:
+        try:
+            line.setdefault("extra_keys", {})["configs"] = all_config_legs(torch, ab, dev, local_rank, p64_tflops, hbm_peak)
+        except Exception as ex:  # a missing fixture must not lose the headline line
+            line.setdefault("extra_keys", {})["configs"] = {"error": repr(ex)}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         os.sched_setaffinity(0, all_cpus)

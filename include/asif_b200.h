@@ -61,7 +61,8 @@ extern "C" {
                            * (cudaHostAlloc / cudaHostRegisterMapped) arrays overlap the copies with the kernels and, for
                            * the filter classes whose kernels outlast their transfers, are read and written by the kernel
                            * directly over PCIe (env ASIF_B200_HOST_IO = staged | out | inout | auto; results are the same
-                           * bits in every mode) */
+                           * bits in every mode; "auto" measures staged against in-place on the first large batches of
+                           * an engine and keeps the faster, see asif_engine_host_io_stats) */
 #define ASIF_MEM_DEVICE 1 /* all batch pointers are device memory on the engine's device; nothing is copied */
 
 /* how a host-memory batch reached the kernels (asif_engine_last_host_io) */
@@ -166,6 +167,9 @@ int32_t asif_host_free(void *p);
 int32_t asif_host_register(void *p, uint64_t bytes);
 int32_t asif_host_unregister(void *p);
 int32_t asif_engine_last_host_io(const asif_engine *e, int32_t *mode);
+/* what the "auto" policy has measured on this engine: wall time per 1e6 states of large pinned batches in each
+ * ASIF_HOST_IO_* mode (exponential average; 0 with samples 0 = not tried yet) */
+int32_t asif_engine_host_io_stats(const asif_engine *e, double ms_per_1e6_states[3], int32_t samples[3]);
 
 /*
  * The filter(x, H, c, uAct[, relax]) overloads (src/asif_implicit_tb.cpp:252-363, src/asif.cpp:153-210,

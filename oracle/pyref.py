@@ -10,6 +10,8 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF_SO = os.path.join(HERE, "_ref", "libasif_ref.so")
+# the same reference sources with their filter classes constructible on ASIF::QPWrapperB200 (oracle/ref_build/qp_select_shim.h)
+REF_B200_SO = os.path.join(HERE, "_ref", "libasif_ref_b200.so")
 ORACLE_SO = os.path.join(HERE, "liboracle.so")
 
 CFG_DI_EXPLICIT, CFG_DI_IMPLICIT_TB, CFG_IP_IMPLICIT, CFG_IP_ROBUST, CFG_IP_REALIZABLE, CFG_SEGWAY_TB = 1, 2, 3, 4, 5, 6
@@ -45,6 +47,11 @@ class RefLib:
         self.lib.ref_set_qp_mode(eps, polish, warm_start, max_iter)
         self.lib.ref_set_polish_refine(polish_refine_iter)
 
+    def select_backend(self, backend):
+        """libasif_ref_b200.so only: 0 = OSQP stand-in, 1 = ASIF::QPWrapperB200, for filters created afterwards"""
+        self.lib.ref_select_backend.argtypes = [C.c_int]
+        self.lib.ref_select_backend(backend)
+
     def qp_stats(self):
         a, b, c = C.c_longlong(), C.c_longlong(), C.c_longlong()
         self.lib.ref_qp_stats(C.byref(a), C.byref(b), C.byref(c))
@@ -64,6 +71,13 @@ class RefFilter:
         dims = np.zeros(6, dtype=np.int32)
         lib.lib.ref_dims(h, dims.ctypes.data_as(_ip))
         self.nx, self.nu, self.n_relax, self.nc, self.nv, self.n_diag = (int(v) for v in dims)
+
+    def update_options(self, opts):
+        """the class's updateOptions(options); returns its code (1, or 2 / 3 when satSharpness was clamped)"""
+        o = np.ascontiguousarray(opts, dtype=np.float64)
+        self.lib.lib.ref_update_options.argtypes = [C.c_void_p, _dp, C.c_int]
+        self.lib.lib.ref_update_options.restype = C.c_int32
+        return int(self.lib.lib.ref_update_options(self.h, _d(o), o.size))
 
     def set_learning(self, dims, blob):
         """Options.use_learning = true with these networks (implicit classes only)."""

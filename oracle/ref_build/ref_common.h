@@ -18,6 +18,8 @@ struct RefFilter {
 	/* learned residual of the implicit classes (include/asif_learning_utils.h): dims[8] in the order of the
 	 * LearningData fields, blob = w1,b1,w2,b2,w3,b3 of the drift net then of the actuation net (column-major weights) */
 	virtual int set_learning(const uint32_t *dims, const double *blob) { (void)dims; (void)blob; return -1; }
+	/* the class's updateOptions(options) with a new option vector (same layout as at creation); returns its code, -100 = not wired */
+	virtual int32_t update_options(const double *opts, int n_opts) { (void)opts; (void)n_opts; return -100; }
 };
 
 #ifdef ASIF_REF_WITH_LEARNING_HELPER

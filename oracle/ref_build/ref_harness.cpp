@@ -41,6 +41,12 @@ int ref_set_learning(void *h, const uint32_t *dims, const double *blob)
 	return f ? f->set_learning(dims, blob) : -1;
 }
 
+int32_t ref_update_options(void *h, const double *opts, int n_opts)
+{
+	RefFilter *f = (RefFilter *)h;
+	return f ? f->update_options(opts, n_opts) : -101;
+}
+
 int ref_dims(void *h, int32_t *dims)
 {
 	RefFilter *f = (RefFilter *)h;

@@ -45,6 +45,15 @@ struct DiExplicit : RefFilter {
 		return rc;
 	}
 	void plant(const double *x, double *fo, double *go) override { ex_di::dynamics(x, fo, go); }
+	int32_t update_options(const double *opts, int n_opts) override
+	{
+		ASIF::ASIF::Options o;
+		if (opts && n_opts >= 2) {
+			o.relaxLb = opts[0];
+			o.relaxCost = opts[1];
+		}
+		return f.updateOptions(o);
+	}
 };
 
 struct TbAccess : ASIF::ASIFimplicitTB {
@@ -131,6 +140,12 @@ struct DiTb : RefFilter {
 		return rc;
 	}
 	void plant(const double *x, double *fo, double *go) override { ex_di_tb::dynamics(x, fo, go); }
+	int32_t update_options(const double *opts, int n_opts) override /* src/asif_implicit_tb.cpp:365-405 */
+	{
+		ASIF::ASIFimplicitTB::Options o;
+		ref_tb_options(opts, n_opts, o);
+		return f.updateOptions(o);
+	}
 };
 } // namespace
 

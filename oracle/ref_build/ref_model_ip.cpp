@@ -38,6 +38,20 @@ struct IpImplicit : RefFilter {
 	{
 		return (opts && n_opts >= 7 && opts[6] >= 1.0 && opts[6] <= 16.0) ? (uint32_t)opts[6] : ex_ip_implicit::npBTSS;
 	}
+	int32_t update_options(const double *opts, int n_opts) override /* src/asif_implicit.cpp:369-401 */
+	{
+		ASIF::ASIFimplicit::Options o = o_;
+		if (opts && n_opts >= 6) {
+			o.relaxCost = opts[0];
+			o.relaxReachLb = opts[1];
+			o.relaxSafeLb = opts[2];
+			o.backTrajHorizon = opts[3];
+			o.backTrajDt = opts[4];
+			o.satSharpness = opts[5];
+		}
+		o_ = o;
+		return f.updateOptions(o);
+	}
 	IpImplicit(const double *opts, int n_opts)
 	    : f(ex_ip_implicit::nx, ex_ip_implicit::nu, ex_ip_implicit::npSS, ex_ip_implicit::npBS, np(opts, n_opts),
 	        ex_ip_implicit::safetySet, ex_ip_implicit::backupSet, ex_ip_implicit::dynamics,

@@ -61,6 +61,12 @@ struct SegwayTb : RefFilter {
 		return rc;
 	}
 	void plant(const double *x, double *fo, double *go) override { ex_segway::dynamics(x, fo, go); }
+	int32_t update_options(const double *opts, int n_opts) override
+	{
+		ASIF::ASIFimplicitTB::Options o;
+		ref_tb_options(opts, n_opts, o);
+		return f->updateOptions(o);
+	}
 };
 } // namespace
 
