@@ -70,7 +70,8 @@ _lib = None
 
 
 def lib_path():
-    return os.path.join(HERE, "libasif_b200.so")
+    # ASIF_B200_LIB: an experimental build of the same library (scripts/build_variant.sh A/B runs); default = the in-tree product
+    return os.environ.get("ASIF_B200_LIB") or os.path.join(HERE, "libasif_b200.so")
 
 
 def load_library():

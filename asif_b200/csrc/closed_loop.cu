@@ -1,6 +1,7 @@
 // closed_loop.cu -- asif_engine_closed_loop: the example main loops for a fleet, state resident on the device.
 // Host orchestration only: per control sample one filter launch (any filter class) and one
 // closed_loop_step_kernel launch, all on one stream, nothing synchronised until the end.
+#define ASIF_QP_POLISH_INLINE_ROWS 1 // qp_gi.cuh: the form of the vertex polish that costs this unit's kernels least
 #include "closed_loop_kernel.cuh"
 #include "engine_internal.cuh"
 
@@ -131,7 +132,7 @@ int32_t asif_engine_closed_loop(asif_engine *e, int64_t n, const asif_loop_confi
 	if (n_log > 0) CUDA_TRY(cudaMemsetAsync(dlog, 0, sizeof(double) * n_log * n_rec * W, st));
 	CUDA_TRY(cudaMemsetAsync(bhist.p, 0, sizeof(unsigned long long) * 8, st));
 	CUDA_TRY(cudaMemsetAsync(bufh.p, 0, sizeof(double) * n * nu, st)); // uActNow = {0.0} before the first call
-	CUDA_TRY(cudaMemsetAsync(e->d_counters, 0, sizeof(unsigned long long), st));
+	CUDA_TRY(cudaMemsetAsync(e->d_counters, 0, N_COUNTERS * sizeof(unsigned long long), st));
 	// smoothBounds start at the rate limiter's own limits (examples/DoubleIntegrator_RealizableSampled.cpp:107)
 	fill_pairs_kernel<<<(unsigned)((n + LOOP_THREADS - 1) / LOOP_THREADS), LOOP_THREADS, 0, st>>>(bsm.as<double>(), n, c->smooth_lb, c->smooth_ub);
 	CUDA_TRY(cudaGetLastError());

@@ -2,6 +2,7 @@
 // Host side: option handling exactly as the reference's initialize() methods, device buffers,
 // chunked H2D / kernel / D2H pipelining for host-memory batches, kernel dispatch.  No CPU
 // fallback anywhere: every compute entry point needs a CUDA device and says so if there is none.
+#define ASIF_QP_POLISH_INLINE_ROWS 1 // qp_gi.cuh: the form of the vertex polish that costs this unit's kernels least
 #include "../../include/asif_b200.h"
 
 #include "explicit_kernel.cuh"
@@ -640,8 +641,8 @@ int32_t asif_engine_create(const asif_engine_config *cfg, asif_engine **out)
 		return fail(ASIF_ERR_UNSUPPORTED, "filter %d not implemented yet", cfg->filter);
 	}
 	cudaError_t err = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
-	if (err == cudaSuccess) err = cudaMalloc(&e->d_counters, 16 * sizeof(unsigned long long));
-	if (err == cudaSuccess) err = cudaMemset(e->d_counters, 0, 16 * sizeof(unsigned long long));
+	if (err == cudaSuccess) err = cudaMalloc(&e->d_counters, N_COUNTERS * sizeof(unsigned long long));
+	if (err == cudaSuccess) err = cudaMemset(e->d_counters, 0, N_COUNTERS * sizeof(unsigned long long));
 	if (err != cudaSuccess) {
 		asif_engine_destroy(e);
 		return fail(ASIF_ERR_CUDA, "engine allocation failed: %s", cudaGetErrorString(err));
@@ -741,8 +742,9 @@ bool bounce_enabled()
 //             time per state against link time per state) AND on what else uses the box's host side - with one GPU the
 //             in-place launch wins for the trajectory-integrating classes (C2 5.27 vs 6.06 ms per 1e7 states), with four
 //             GPUs sharing the host bridge the copy engines' larger PCIe payloads won (round 1, SCALE N = 4).  So the
-//             first large batch runs the class default (below), the second the other mode, later ones the faster of the
-//             two (wall clock per state, exponentially averaged), and every 32nd batch re-tries the slower one.  Results
+//             first four large batches alternate between the class default (below) and the other mode (the first batch of
+//             a mode pays for its buffers and is not counted), later ones run the faster of the two (wall clock per
+//             state, exponentially averaged), and every 32nd batch re-tries the slower one.  Results
 //             are the same bits in every mode, so the choice is free.  asif_engine_host_io_stats reports the averages.
 //             Small batches (< 2^18 states) keep the class default: "inout" for the trajectory-integrating and realizable
 //             filters, "staged" for the explicit and robust ones (ms per batch staged / out / inout, one GPU: C1 0.73 /
@@ -774,8 +776,12 @@ int host_io_mode(asif_engine *e, int64_t n, bool *probe)
 	const int dflt = host_io_class_default(e), other = dflt == 2 ? 0 : 2;
 	if (n < HOST_IO_PROBE_MIN_STATES) return dflt;
 	*probe = true;
+	// two batches per mode before anything is decided: a mode's first batch pays for its buffers (slot allocations, the
+	// first touch of the pinned mappings) and its time is replaced, not averaged, by the second
 	if (e->io_samples[dflt] == 0) return dflt;
 	if (e->io_samples[other] == 0) return other;
+	if (e->io_samples[dflt] == 1) return dflt;
+	if (e->io_samples[other] == 1) return other;
 	const int best = e->io_ms_per_state[other] < e->io_ms_per_state[dflt] ? other : dflt;
 	if (++e->io_calls % 32 == 0) return best == dflt ? other : dflt; // conditions change (other ranks start or stop): look again
 	return best;
@@ -784,7 +790,7 @@ int host_io_mode(asif_engine *e, int64_t n, bool *probe)
 void host_io_record(asif_engine *e, int mode, int64_t n, double ms)
 {
 	const double per = ms / (double)n;
-	e->io_ms_per_state[mode] = e->io_samples[mode] ? 0.5 * e->io_ms_per_state[mode] + 0.5 * per : per;
+	e->io_ms_per_state[mode] = e->io_samples[mode] >= 2 ? 0.5 * e->io_ms_per_state[mode] + 0.5 * per : per;
 	e->io_samples[mode]++;
 }
 
@@ -807,7 +813,7 @@ int32_t filter_batch_impl(asif_engine *e, int64_t n, const double *x, const doub
 	CUDA_TRY(cudaSetDevice(e->cfg.device));
 	if (mem == ASIF_MEM_DEVICE) {
 		cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
-		CUDA_TRY(cudaMemsetAsync(e->d_counters, 0, sizeof(unsigned long long), st));
+		CUDA_TRY(cudaMemsetAsync(e->d_counters, 0, N_COUNTERS * sizeof(unsigned long long), st));
 		e->ex.lfh = e->lie_lfh;
 		e->ex.lgh = e->lie_lgh;
 		int r = launch_filter(e, n, x, u_des, u_act, relax, rc, diag, st);
@@ -834,7 +840,7 @@ int32_t filter_batch_impl(asif_engine *e, int64_t n, const double *x, const doub
 			char *h = e->small_h;
 			memcpy(h + o_x, x, sizeof(double) * n * nx);
 			memcpy(h + o_ud, u_des, sizeof(double) * n * cw);
-			CUDA_TRY(cudaMemsetAsync(e->d_counters, 0, sizeof(unsigned long long), st));
+			CUDA_TRY(cudaMemsetAsync(e->d_counters, 0, N_COUNTERS * sizeof(unsigned long long), st));
 			e->ex.lfh = e->lie_lfh;
 			e->ex.lgh = e->lie_lgh;
 			e->last_host_io = ASIF_HOST_IO_INOUT;
@@ -859,7 +865,7 @@ int32_t filter_batch_impl(asif_engine *e, int64_t n, const double *x, const doub
 	}
 	// the QP-work counter is zeroed on the engine's own stream and waited for: the slot streams are non-blocking and
 	// do not order against the legacy default stream a plain cudaMemset would run on
-	CUDA_TRY(cudaMemsetAsync(e->d_counters, 0, sizeof(unsigned long long), e->stream));
+	CUDA_TRY(cudaMemsetAsync(e->d_counters, 0, N_COUNTERS * sizeof(unsigned long long), e->stream));
 	CUDA_TRY(cudaStreamSynchronize(e->stream));
 	// device aliases of the caller's output arrays (nullptr: pageable or unmapped memory, staged copies then)
 	double *m_ua = nullptr, *m_relax = nullptr, *m_diag = nullptr;
@@ -1093,7 +1099,7 @@ int32_t asif_engine_rollout(asif_engine *e, int64_t n, int32_t steps, double dt,
 	const int nx = e->nx, nu = e->nu;
 	if (mem == ASIF_MEM_DEVICE) {
 		cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
-		CUDA_TRY(cudaMemsetAsync(e->d_counters, 0, 9 * sizeof(unsigned long long), st));
+		CUDA_TRY(cudaMemsetAsync(e->d_counters, 0, N_COUNTERS * sizeof(unsigned long long), st));
 		int r = launch_rollout(e, n, steps, dt, x, u_des, u_act_last, rc_last, st);
 		if (r) return r;
 		if (rc_hist || !stream) {
@@ -1110,7 +1116,7 @@ int32_t asif_engine_rollout(asif_engine *e, int64_t n, int32_t steps, double dt,
 	Slot &s = e->slot[0];
 	int r = ensure_slot(e, s, n, false);
 	if (r) return r;
-	CUDA_TRY(cudaMemsetAsync(e->d_counters, 0, 9 * sizeof(unsigned long long), s.stream));
+	CUDA_TRY(cudaMemsetAsync(e->d_counters, 0, N_COUNTERS * sizeof(unsigned long long), s.stream));
 	CUDA_TRY(cudaMemcpyAsync(s.x, x, sizeof(double) * n * nx, cudaMemcpyHostToDevice, s.stream));
 	CUDA_TRY(cudaMemcpyAsync(s.ud, u_des, sizeof(double) * n * nu, cudaMemcpyHostToDevice, s.stream));
 	r = launch_rollout(e, n, steps, dt, s.x, s.ud, s.ua, s.rc, s.stream);
@@ -1233,8 +1239,9 @@ int32_t asif_engine_last_qp_iterations(asif_engine *e, uint64_t *rows_processed)
 	if (!e || !rows_processed) return fail(ASIF_ERR_INVALID_ARGUMENT, "NULL argument");
 	CUDA_TRY(cudaSetDevice(e->cfg.device));
 	CUDA_TRY(cudaDeviceSynchronize());
-	unsigned long long v = 0;
-	CUDA_TRY(cudaMemcpy(&v, e->d_counters, sizeof(v), cudaMemcpyDeviceToHost));
+	unsigned long long part[QP_CTR_SPREAD], v = 0;
+	CUDA_TRY(cudaMemcpy(part, e->d_counters + QP_CTR_BASE, sizeof(part), cudaMemcpyDeviceToHost));
+	for (int i = 0; i < QP_CTR_SPREAD; i++) v += part[i];
 	*rows_processed = (uint64_t)v;
 	return ASIF_OK;
 }

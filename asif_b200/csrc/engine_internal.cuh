@@ -113,30 +113,11 @@ int set_smem(K kernel, size_t bytes)
 	return ASIF_OK;
 }
 
-// ---- kernel dispatch -------------------------------------------------------------------------
-// Launch geometry of the TB kernels.  nx = 2: one CTA per tile of TB_THREADS states, snapshots in shared memory.
-// nx = 4: persistent grid over a global snapshot scratch; the grid is the largest one that fits the SMs, shrunk so
-// that every CTA runs the same number of tiles (no ragged last wave).
-template <class M, int NPBTSS>
-int tb_geometry(asif_engine *e, int64_t n, cudaStream_t st, unsigned &blocks, size_t &smem, double *&gsnap, int &buf)
+// A scratch buffer of `need` bytes for a launch on stream st, out of the engine's ring: one last used on this same stream
+// (stream order protects it), else an idle one, else an unallocated one, else the next in the ring after waiting for its
+// last user.  The caller launches and then calls tb_release(e, buf, st).
+inline int acquire_scratch(asif_engine *e, const size_t need, cudaStream_t st, int &buf)
 {
-	const int64_t tiles = (n + TB_THREADS - 1) / TB_THREADS;
-	const size_t per_cta = sizeof(double) * tb_smem_doubles_per_thread<M, NPBTSS>() * TB_THREADS;
-	gsnap = nullptr;
-	buf = -1;
-	if (!tb_global_snapshots<M>()) {
-		blocks = (unsigned)tiles;
-		smem = per_cta;
-		return ASIF_OK;
-	}
-	const int64_t resident = (int64_t)e->num_sms * tb_min_blocks<M>();
-	const int64_t rounds = (tiles + resident - 1) / resident;
-	blocks = (unsigned)((tiles + rounds - 1) / rounds);
-	if (blocks < 1) blocks = 1;
-	smem = 0;
-	const size_t need = sizeof(double) * TB_SCRATCH_HEADER + per_cta * (size_t)resident;
-	// pick a scratch buffer: one last used on this same stream (stream order protects it), else an idle one, else an
-	// unallocated one, else the next in the ring after waiting for its last user
 	int pick = -1;
 	for (int i = 0; i < N_SNAP_BUFS && pick < 0; i++) {
 		asif_engine::SnapBuf &c = e->snapbuf[i];
@@ -167,6 +148,35 @@ int tb_geometry(asif_engine *e, int64_t n, cudaStream_t st, unsigned &blocks, si
 	}
 	if (!b.ev) CUDA_TRY(cudaEventCreateWithFlags(&b.ev, cudaEventDisableTiming));
 	if (b.used && b.last != st) CUDA_TRY(cudaStreamWaitEvent(st, b.ev, 0));
+	return ASIF_OK;
+}
+
+// ---- kernel dispatch -------------------------------------------------------------------------
+// Launch geometry of the TB kernels.  nx = 2: one CTA per tile of TB_THREADS states, snapshots in shared memory.
+// nx = 4: persistent grid over a global snapshot scratch; the grid is the largest one that fits the SMs, shrunk so
+// that every CTA runs the same number of tiles (no ragged last wave).
+template <class M, int NPBTSS>
+int tb_geometry(asif_engine *e, int64_t n, cudaStream_t st, unsigned &blocks, size_t &smem, double *&gsnap, int &buf)
+{
+	const int64_t tiles = (n + TB_THREADS - 1) / TB_THREADS;
+	const size_t per_cta = sizeof(double) * tb_smem_doubles_per_thread<M, NPBTSS>() * TB_THREADS;
+	gsnap = nullptr;
+	buf = -1;
+	if (!tb_global_snapshots<M>()) {
+		blocks = (unsigned)tiles;
+		smem = per_cta;
+		return ASIF_OK;
+	}
+	const int64_t resident = (int64_t)e->num_sms * tb_min_blocks<M>();
+	const int64_t rounds = (tiles + resident - 1) / resident;
+	blocks = (unsigned)((tiles + rounds - 1) / rounds);
+	if (blocks < 1) blocks = 1;
+	smem = 0;
+	const size_t need = sizeof(double) * TB_SCRATCH_HEADER + per_cta * (size_t)resident;
+	int r_;
+	r_ = acquire_scratch(e, need, st, buf);
+	if (r_) return r_;
+	asif_engine::SnapBuf &b = e->snapbuf[buf];
 	CUDA_TRY(cudaMemsetAsync(b.p, 0, sizeof(double) * TB_SCRATCH_HEADER, st)); // tile counter
 	gsnap = b.p;
 	return ASIF_OK;
@@ -242,9 +252,51 @@ template <class M, int NPBTSS, bool RB, int SAT_LO>
 int launch_implicit_t(asif_engine *e, int64_t n, const double *x, const double *ud, double *ua, double *relax, int32_t *rc,
                       double *diag, cudaStream_t st)
 {
+	const bool pow2 = e->im.sat_mode >= SAT_POW2;
+	// checkpointed kernel (no snapshots in the hot loop, persistent grid over a global scratch) whenever the horizon fits
+	// its checkpoint table and the scratch stays below 2 GB; ASIF_B200_IMPLICIT_SMEM=1 forces the shared-memory kernel
+	static const bool force_smem = []() {
+		const char *v = getenv("ASIF_B200_IMPLICIT_SMEM");
+		return v && v[0] == '1';
+	}();
+	const int ck_log = imp_ck_log(e->im.npBT);
+	if (!force_smem && ck_log > 0) {
+		e->im.ck_log = ck_log;
+		const size_t smem2 = sizeof(double) * imp2_smem_doubles_per_thread<NPBTSS>() * IMP2_THREADS;
+		const size_t per_cta = sizeof(double) * imp_scratch_doubles_per_thread<M, NPBTSS, RB>(e->im.npBT, ck_log) * IMP2_THREADS;
+		const int64_t tiles = (n + IMP2_THREADS - 1) / IMP2_THREADS;
+		auto launch = [&](auto kern) -> int {
+			int per_sm = 0;
+			CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, IMP2_THREADS, smem2));
+			if (per_sm < 1) per_sm = 1;
+			const int64_t resident = (int64_t)e->num_sms * per_sm;
+			// every CTA runs the same number of tiles (no ragged last wave), as for the persistent TB kernels
+			const int64_t rounds = (tiles + resident - 1) / resident;
+			const unsigned blocks2 = (unsigned)((tiles + rounds - 1) / rounds);
+			const size_t need = per_cta * (size_t)blocks2;
+			if (need > ((size_t)2 << 30)) return 1; // fall back
+			int buf;
+			int r = acquire_scratch(e, need, st, buf);
+			if (r) return r;
+			kern<<<blocks2, IMP2_THREADS, smem2, st>>>(e->im, n, x, ud, ua, relax, rc, diag, e->d_counters, e->snapbuf[buf].p);
+			CUDA_TRY(cudaGetLastError());
+			return tb_release(e, buf, st);
+		};
+		// symmetric input bounds (lb == -ub for every input) in the contracted unit: the cheaper form of SAT_RECIP, same bits
+		bool sym = (SAT_LO == SAT_RECIP);
+		for (int i = 0; i < e->nu; i++) sym = sym && (e->im.lb[i] == -e->im.ub[i]);
+		constexpr int SAT_SYM = (SAT_LO == SAT_RECIP) ? SAT_RECIP_SYM : SAT_LO;
+		int r;
+		if (diag)
+			r = pow2 ? launch(implicit_ckpt_kernel<M, NPBTSS, true, SAT_POW2, RB>) : launch(implicit_ckpt_kernel<M, NPBTSS, true, SAT_LO, RB>);
+		else if (sym && !pow2)
+			r = launch(implicit_ckpt_kernel<M, NPBTSS, false, SAT_SYM, RB>);
+		else
+			r = pow2 ? launch(implicit_ckpt_kernel<M, NPBTSS, false, SAT_POW2, RB>) : launch(implicit_ckpt_kernel<M, NPBTSS, false, SAT_LO, RB>);
+		if (r != 1) return r;
+	}
 	const size_t smem = sizeof(double) * (diag ? imp_smem_doubles_per_thread<M, NPBTSS, true>() : imp_smem_doubles_per_thread<M, NPBTSS, false>()) * IMP_THREADS;
 	const unsigned blocks = (unsigned)((n + IMP_THREADS - 1) / IMP_THREADS);
-	const bool pow2 = e->im.sat_mode >= SAT_POW2;
 	if (diag) {
 		auto k = pow2 ? implicit_filter_kernel<M, NPBTSS, true, SAT_POW2, RB> : implicit_filter_kernel<M, NPBTSS, true, SAT_LO, RB>;
 		int r = set_smem(k, smem);

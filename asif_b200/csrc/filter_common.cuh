@@ -32,7 +32,9 @@ enum : int {
 	SAT_GENERAL = 0,  // 2*(u-middle)/range
 	SAT_POW2 = 1,     // range is a power of two: (u-middle)*(2/range), all operations exact
 	SAT_IDENTITY = 2, // middle == 0 and range == 2 (e.g. u in [-1,1]): uc == u
-	SAT_RECIP = 3     // (u-middle)*fl(2/range): last-bit differences; only for models without bit parity (kernels_contract.cu)
+	SAT_RECIP = 3,    // (u-middle)*fl(2/range): last-bit differences; only for models without bit parity (kernels_contract.cu)
+	SAT_RECIP_SYM = 4 // SAT_RECIP with lb == -ub (middle == 0): uc = u*fl(2/range), bound = copysign(ub, uc) - the same bits as
+	                  // SAT_RECIP (u - 0 == u, +-ub are the bounds themselves) without the subtraction and the select of two loads
 };
 
 // Structural patterns a model may declare for its callback outputs: an entry that is the literal
@@ -78,6 +80,17 @@ struct ExplicitParams {
 	const double *lfh, *lgh;
 };
 
+// Engine counters (device, unsigned long long): [0] unused, [1..8] return-code histogram of the rollouts, and from
+// QP_CTR_BASE on QP_CTR_SPREAD partial sums of "rows processed by the active-set solver" (the K-bar statistic).  One
+// warp-aggregated atomicAdd per warp to ONE address was the bottleneck of the explicit filter at 1e8 states (3.1e6
+// same-address atomics serialise in L2 at about 1.2 ns each = the whole 3.7 ms of the launch); spread over 256 addresses
+// by block index they no longer queue.  The host sums the partials (asif_engine_last_qp_iterations).
+constexpr int QP_CTR_BASE = 16, QP_CTR_SPREAD = 256, N_COUNTERS = QP_CTR_BASE + QP_CTR_SPREAD;
+__device__ __forceinline__ void qp_rows_add(unsigned long long *counters, const unsigned long long it)
+{
+	atomicAdd(counters + QP_CTR_BASE + (blockIdx.x & (QP_CTR_SPREAD - 1)), it);
+}
+
 // src/asif_implicit_tb.cpp:821-830
 __device__ __forceinline__ double input_saturate(double u, double lb, double ub)
 {
@@ -97,13 +110,14 @@ __device__ __forceinline__ void input_saturate_soft(const SoftSat &s, int i, dou
 	if (SATMODE == SAT_IDENTITY) uc = u;
 	else if (SATMODE == SAT_POW2) uc = (u - middle) * s.uc_scale_exact[i];
 	else if (SATMODE == SAT_RECIP) uc = (u - middle) * s.uc_scale[i];
+	else if (SATMODE == SAT_RECIP_SYM) uc = u * s.uc_scale[i];
 	else uc = 2 * (u - middle) / range;
 	const double a = fabs(uc);
 	// clamp and pass-through legs as selects (no branch, no register shuffling between the legs) ...
 	const bool sat = a >= s.bevelStop;
 	const bool bevel = !sat && (a > s.bevelStart); // false for NaN: pass through, as the reference's last else
 	// SAT_IDENTITY means lb = -1, ub = 1: the bound is the sign of uc on 1.0 (uc = 0 never saturates)
-	const double bound = (SATMODE == SAT_IDENTITY) ? copysign(1.0, uc) : ((uc > 0) ? ub : lb);
+	const double bound = (SATMODE == SAT_IDENTITY) ? copysign(1.0, uc) : ((SATMODE == SAT_RECIP_SYM) ? copysign(ub, uc) : ((uc > 0) ? ub : lb));
 	uSat = sat ? bound : u;
 	DuSat = sat ? 0.0 : 1.0;
 	// ... the circular bevel (sqrt + division) is rare: a real branch, entered only by the lanes that need it

@@ -81,6 +81,7 @@ struct ImplicitParams {
 	int32_t sat_mode;
 	int32_t npBTSS; // critical trajectory points (read by the run-time-count instantiation only)
 	int32_t custom_cost; // filter(x, H, c, ...) (src/asif_implicit.cpp:296-303): u_des holds c[n][nv]
+	int32_t ck_log;      // checkpoint spacing of implicit_ckpt_kernel (imp_ck_log(npBT)), set by the launcher
 	SoftSat sat;
 	double gi[MAX_NV], gih[MAX_NV];
 	// ASIFimplicitRB only (include/asif_implicit_robust.h:22-38)
@@ -469,7 +470,382 @@ implicit_filter_kernel(const ImplicitParams p, const int64_t n, const double *__
 		unsigned int it = live ? (unsigned int)iters : 0u;
 #pragma unroll
 		for (int o = 16; o > 0; o >>= 1) it += __shfl_xor_sync(0xffffffffu, it, o);
-		if ((threadIdx.x & 31) == 0 && it) atomicAdd(qp_iter_sum, (unsigned long long)it);
+		if ((threadIdx.x & 31) == 0 && it) qp_rows_add(qp_iter_sum, (unsigned long long)it);
+	}
+}
+
+// =====================================================================================================================
+// Checkpointed variant (round 2): the same filter with NO snapshots in the hot loop.
+//
+// The kernel above keeps the (x_i, Q_i) snapshot of every point that enters the running list of the CAP smallest min-h
+// points: 480 B of shared memory per state for CAP = 10, which caps the SM at 12 warps, and a trajectory whose min h keeps
+// falling (a pendulum the saturated backup input cannot catch: a third of the C3a draw) stores a snapshot on every one
+// of its 5000 steps.  ncu (profiles/r01_c3a_*): FP64 pipe 43 % busy, 0.86 eligible warps per cycle - latency bound.
+//
+// Here pass A integrates (x, Q) and keeps only the list itself - keys and trajectory indices, 120 B of shared memory per
+// state - plus one CHECKPOINT of (x, Q) [and the zero-order-hold state of ASIFimplicitRB] every 16 / 32 / 64 steps in a
+// global scratch (coalesced 256 B stores per warp, 15 KB per resident thread for C3a, written once per tile).  Pass B then re-integrates, from the
+// checkpoint before it, up to each selected point and stores its snapshot (global scratch as well: written once, read by
+// the one or two row scans of the QP).  The Euler step is the same inlined function in both passes, so pass B retraces
+// pass A's trajectory bit for bit.  In pass B every lane works on its own segments (the lanes of a warp gather different
+// checkpoints and run the same instructions on them).  Cost: at most np segments of <= 64 steps per state against the
+// npBT - 1 steps of pass A (typically 1-2 segments: the selected points cluster at the start, at the end or around one excursion).
+// The scratch belongs to the resident grid, not to the batch: the kernel is persistent (grid = SMs x CTAs per SM, tiles
+// strided), every thread re-uses its own area for all its tiles.  Used up to npBT = 20481; longer horizons run the kernel above.
+// Checkpoint spacing 2^ck_log steps, chosen per engine (imp_ck_log): 16 steps up to npBT 5121 (C3a: 313 checkpoints, 15 KB of
+// scratch per resident thread), 32 up to 10241, 64 up to 20481 - pass B costs a warp at most (2^ck_log - 1) steps per round.
+constexpr int IMP_MAX_CKPT = 320;
+__host__ __device__ inline int imp_ck_log(const int npBT)
+{
+	for (int l = 4; l <= 6; l++)
+		if ((((npBT - 1) >> l) + 1) <= IMP_MAX_CKPT) return l;
+	return -1; // too long for the checkpoint table: the shared-memory kernel runs
+}
+constexpr int IMP2_THREADS = 128;
+
+template <class M, bool RB>
+__host__ __device__ constexpr int imp_ckpt_doubles()
+{
+	return M::NX + M::NX * M::NX + (RB ? M::NU + M::NU * M::NX + 1 : 0);
+}
+// doubles of global scratch per thread for a trajectory of npBT points
+template <class M, int NPBTSS, bool RB>
+__host__ __device__ constexpr size_t imp_scratch_doubles_per_thread(const int npBT, const int ck_log)
+{
+	return (size_t)(((npBT - 1) >> ck_log) + 1) * imp_ckpt_doubles<M, RB>() + (size_t)np_capacity(NPBTSS) * (M::NX + M::NX * M::NX);
+}
+template <int NPBTSS>
+__host__ __device__ constexpr int imp2_smem_doubles_per_thread()
+{
+	return np_capacity(NPBTSS) + (np_capacity(NPBTSS) + 1) / 2;
+}
+
+// one Euler step of the augmented backup flow, X_i = X_{i-1} + dt rhs(X_{i-1}) (src/asif_implicit.cpp:461-484), and min_j h_j(x_i)
+template <class M, int SATMODE, bool RB>
+__device__ __forceinline__ double imp_advance(const ImplicitParams &p, const int i, double (&X)[M::NX + M::NX * M::NX], ZohState<M> &zoh)
+{
+	constexpr int NX = M::NX, NPSS = M::NPSS, NS = NX + NX * NX;
+	double Xd[NS], DfCL[NX * NX];
+	if (RB) // the reference hands t = i*backTrajDt to the rhs (src/asif_implicit_robust.cpp:550)
+		backup_cl_dynamics_zoh<M, SATMODE>(p.sat, p.lb, p.ub, X, (double)(unsigned)i * p.backTrajDt, p.backTrajDt, p.backContDt, zoh, Xd, DfCL);
+	else
+		backup_cl_dynamics<M, SATMODE>(p.sat, p.lb, p.ub, X, Xd, DfCL);
+	sensitivity_rhs<M>(DfCL, X + NX, Xd + NX);
+#pragma unroll
+	for (int e = 0; e < NS; e++) X[e] = Xd[e] * p.backTrajDt + X[e];
+	if (M::HAS_SAFETY_MIN) return M::safety_min(X);
+	double hs[NPSS], Dhs[NPSS * NX];
+	M::safety_set(X, hs, Dhs);
+	double hmin = hs[0];
+#pragma unroll
+	for (int j = 1; j < NPSS; j++) hmin = (hs[j] < hmin) ? hs[j] : hmin;
+	return hmin;
+}
+
+#ifndef IMP2_MIN_BLOCKS
+#define IMP2_MIN_BLOCKS 5 // 5 CTAs = 20 warps per SM at <= 102 registers: measured 25.5 ms against 31.1 (4) and 28.6 (3) on C3a
+#endif
+template <class M, int NPBTSS, bool WITH_DIAG, int SATMODE, bool RB = false>
+__global__ void __launch_bounds__(IMP2_THREADS, IMP2_MIN_BLOCKS)
+implicit_ckpt_kernel(const ImplicitParams p, const int64_t n, const double *__restrict__ x_in, const double *__restrict__ u_des,
+                     double *__restrict__ u_act, double *__restrict__ relax_out, int32_t *__restrict__ rc_out,
+                     double *__restrict__ diag, unsigned long long *__restrict__ qp_iter_sum, double *gscratch)
+{
+	constexpr int NX = M::NX, NU = M::NU, NPSS = M::NPSS, NPBS = M::NPBS;
+	constexpr int NS = NX + NX * NX, NSC = imp_ckpt_doubles<M, RB>();
+	constexpr int NV = NU + 2, CAP = np_capacity(NPBTSS), T = IMP2_THREADS;
+	const int np = np_runtime(NPBTSS) ? p.npBTSS : NPBTSS;
+	const int NC = np * NPSS + NPBS;
+	const int NDIAG = 2 + np + NC * NV + NC;
+	const int N = p.npBT;
+	const int IMP_CK_LOG = p.ck_log, IMP_CK = 1 << IMP_CK_LOG; // run-time spacing (see imp_ck_log)
+	const int NCK = ((N - 1) >> IMP_CK_LOG) + 1;
+
+	extern __shared__ double smem[];
+	double *keys = smem + threadIdx.x;                                              // [slot]
+	int *kidx = reinterpret_cast<int *>(smem + CAP * T) + threadIdx.x;              // [slot]
+	// this thread's scratch: checkpoints [c][e], then snapshots [slot][e]; element stride T (coalesced across the warp)
+	double *ck = gscratch + (size_t)blockIdx.x * ((size_t)NCK * NSC + (size_t)CAP * NS) * T + threadIdx.x;
+	double *snap = ck + (size_t)NCK * NSC * T;
+
+	const int64_t tiles = (n + T - 1) / T;
+	for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+		const int64_t k = tile * T + threadIdx.x;
+		const bool live = k < n;
+		const int64_t kk = live ? k : (n - 1);
+		double x0[NX], c[NU + 2];
+#pragma unroll
+		for (int i = 0; i < NX; i++) x0[i] = x_in[kk * NX + i];
+		if (p.custom_cost) { // the caller's c, all nv entries
+#pragma unroll
+			for (int i = 0; i < NU + 2; i++) c[i] = u_des[kk * (NU + 2) + i];
+		} else { // updateCost(uDes) + the relax entries of initialize() (:238-254, :653-664)
+#pragma unroll
+			for (int i = 0; i < NU; i++) c[i] = -2.0 * u_des[kk * NU + i];
+			c[NU] = -2.0 * p.relaxCost * p.relaxSafeLb;
+			c[NU + 1] = -2.0 * p.relaxCost * p.relaxReachLb;
+		}
+		double hSafetyNow;
+		{
+			double hs[NPSS], Dhs[NPSS * NX];
+			M::safety_set(x0, hs, Dhs);
+			hSafetyNow = hs[0];
+#pragma unroll
+			for (int j = 1; j < NPSS; j++) hSafetyNow = (hs[j] < hSafetyNow) ? hs[j] : hSafetyNow;
+		}
+		ImpRows<M, NPBTSS, RB> R;
+		if (RB) {
+#pragma unroll
+			for (int i = 0; i < NX; i++) R.x_unc[i] = p.x_unc[i];
+		}
+		R.np = np;
+		R.snap = snap;
+		R.T = T;
+		double X[NS];
+#pragma unroll
+		for (int i = 0; i < NS; i++) X[i] = 0.0;
+#pragma unroll
+		for (int i = 0; i < NX; i++) X[i] = x0[i];
+#pragma unroll
+		for (int i = 0; i < NX; i++) X[NX + i * (NX + 1)] = 1.0;
+		ZohState<M> zoh;
+#pragma unroll
+		for (int i = 0; i < NU; i++) zoh.u[i] = 0.0;
+#pragma unroll
+		for (int i = 0; i < NU * NX; i++) zoh.Du[i] = 0.0;
+		zoh.t_last = -1.;
+#pragma unroll
+		for (int s = 1; s < CAP; s++) {
+			keys[s * T] = INFINITY;
+			kidx[s * T] = -1;
+		}
+		keys[0] = hSafetyNow;
+		kidx[0] = 0;
+		R.order.init();
+		double kmin = hSafetyNow, kmax = (CAP > 1) ? INFINITY : hSafetyNow;
+		// checkpoint 0 = the initial point
+#pragma unroll
+		for (int e = 0; e < NS; e++) ck[e * T] = X[e];
+		if (RB) {
+#pragma unroll
+			for (int i = 0; i < NU; i++) ck[(NS + i) * T] = zoh.u[i];
+#pragma unroll
+			for (int i = 0; i < NU * NX; i++) ck[(NS + NU + i) * T] = zoh.Du[i];
+			ck[(NS + NU + NU * NX) * T] = zoh.t_last;
+		}
+
+		// ---- pass A: the whole horizon; list of the CAP smallest points (key, index) and a checkpoint every IMP_CK steps
+		// (two nested loops: the checkpoint store sits between the inner loops instead of behind a per-step test)
+		for (int c0 = 0; c0 < N - 1; c0 += IMP_CK) {
+		const int iend = (c0 + IMP_CK < N - 1) ? c0 + IMP_CK : N - 1;
+		for (int i = c0 + 1; i <= iend; i++) {
+			const double hmin = imp_advance<M, SATMODE, RB>(p, i, X, zoh);
+			if (hmin < kmax) {
+				const int slot = R.order.last(); // the evicted (largest) entry's slot takes the new point
+				if (hmin < kmin) {
+					R.order.push_front(slot);
+					kmin = hmin;
+				} else {
+					int pl = 1; // first place whose key is larger (behind equal keys: ties keep the earlier index first)
+					while (pl < CAP - 1 && !(hmin < keys[R.order.slot(pl) * T])) pl++;
+					R.order.insert_at(pl, slot);
+				}
+				keys[slot * T] = hmin;
+				kidx[slot * T] = i;
+				kmax = keys[R.order.last() * T];
+			}
+		}
+		if (iend == c0 + IMP_CK) { // the state after step iend = a multiple of the spacing: checkpoint iend >> ck_log
+			double *q = ck + (size_t)(iend >> IMP_CK_LOG) * NSC * T;
+#pragma unroll
+			for (int e = 0; e < NS; e++) q[e * T] = X[e];
+			if (RB) {
+#pragma unroll
+				for (int t = 0; t < NU; t++) q[(NS + t) * T] = zoh.u[t];
+#pragma unroll
+				for (int t = 0; t < NU * NX; t++) q[(NS + NU + t) * T] = zoh.Du[t];
+				q[(NS + NU + NU * NX) * T] = zoh.t_last;
+			}
+		}
+		}
+		// open-loop dynamics at the current state (:414-416) and the backup rows at the trajectory end (:542-554)
+		M::dynamics(x0, R.f, R.g);
+		double hBackupEnd;
+		{
+			double hB[NPBS], DhB[NPBS * NX];
+			M::backup_set_rows(X, hB, DhB);
+			hBackupEnd = hB[0];
+#pragma unroll
+			for (int r = 1; r < NPBS; r++) hBackupEnd = (hB[r] < hBackupEnd) ? hB[r] : hBackupEnd;
+#pragma unroll
+			for (int r = 0; r < NPBS; r++) {
+				double dh[NX];
+#pragma unroll
+				for (int cc = 0; cc < NX; cc++) {
+					double acc = DhB[r] * X[NX + cc * NX];
+#pragma unroll
+					for (int m = 1; m < NX; m++) acc = acc + DhB[r + m * NPBS] * X[NX + m + cc * NX];
+					dh[cc] = acc;
+				}
+				double lf = dh[0] * R.f[0];
+#pragma unroll
+				for (int m = 1; m < NX; m++) lf = lf + dh[m] * R.f[m];
+#pragma unroll
+				for (int i = 0; i < NU; i++) {
+					double lg = dh[0] * R.g[i * NX];
+#pragma unroll
+					for (int m = 1; m < NX; m++) lg = lg + dh[m] * R.g[m + i * NX];
+					R.lgB[r][i] = lg;
+				}
+				R.hB[r] = hB[r];
+				R.rhsB[r] = -lf;
+			}
+		}
+
+		// ---- pass B: snapshots of the np selected points, re-integrated from the checkpoints
+#ifndef IMP2_SKIP_PASS_B // (timing experiments only: results are garbage without it)
+		// Every lane works on ITS OWN next segment (lanes gather their checkpoints from different places and run the same
+		// instruction stream on them), so a round costs the warp one segment's worth of steps whatever the lanes' segments are,
+		// and the number of rounds is the largest number of distinct segments any one lane needs (typically 1-2, at most np).
+		{
+			int done = -1;
+			for (;;) {
+				int mine = 0x7fffffff;
+#pragma unroll 1
+				for (int s = 0; s < np; s++) {
+					const int seg = kidx[R.order.slot(s) * T] >> IMP_CK_LOG;
+					if (seg > done && seg < mine) mine = seg;
+				}
+				const bool have = mine != 0x7fffffff;
+				if (!__any_sync(0xffffffffu, have)) break;
+				unsigned long long need = 0ull;
+				int last = -1;
+				if (have) {
+					const double *q = ck + (size_t)mine * NSC * T;
+#pragma unroll
+					for (int e = 0; e < NS; e++) X[e] = q[e * T];
+					if (RB) {
+#pragma unroll
+						for (int t = 0; t < NU; t++) zoh.u[t] = q[(NS + t) * T];
+#pragma unroll
+						for (int t = 0; t < NU * NX; t++) zoh.Du[t] = q[(NS + NU + t) * T];
+						zoh.t_last = q[(NS + NU + NU * NX) * T];
+					}
+#pragma unroll 1
+					for (int s = 0; s < np; s++) {
+						const int is = kidx[R.order.slot(s) * T];
+						if ((is >> IMP_CK_LOG) == mine) {
+							const int j = is & (IMP_CK - 1);
+							need |= 1ull << j;
+							last = j > last ? j : last;
+						}
+					}
+					done = mine;
+				}
+				const int base_i = have ? (mine << IMP_CK_LOG) : 0;
+				const int wlast = __reduce_max_sync(0xffffffffu, last);
+				for (int j = 0; j <= wlast; j++) {
+					if (j <= last) {
+						if (j > 0) imp_advance<M, SATMODE, RB>(p, base_i + j, X, zoh);
+						if ((need >> j) & 1ull) {
+#pragma unroll 1
+							for (int s = 0; s < np; s++) {
+								const int sl = R.order.slot(s);
+								if (kidx[sl * T] == base_i + j) {
+#pragma unroll
+									for (int e = 0; e < NS; e++) snap[(size_t)(sl * NS + e) * T] = X[e];
+								}
+							}
+						}
+					}
+				}
+			}
+		}
+#endif
+		R.learn = p.learn.blob != nullptr;
+		R.dLf = 0.0;
+#pragma unroll
+		for (int i = 0; i < NU; i++) R.dLg[i] = 0.0;
+		if (R.learn) {
+			// Dh_index_ = DhSS(x_c) Q_c of the first critical point, npSS x nx column-major; its first nx entries
+			// (src/asif_implicit.cpp:533-537, include/asif_learning_utils.h:127-129)
+			double xs[NS], hq[NPSS], Dq[NPSS * NX], dhi[NX];
+#pragma unroll
+			for (int e = 0; e < NS; e++) xs[e] = snap[(size_t)(R.order.slot(0) * NS + e) * T];
+			M::safety_set(xs, hq, Dq);
+#pragma unroll
+			for (int i = 0; i < NX; i++) {
+				const int row = i % NPSS, col = i / NPSS;
+				double acc = 0.0;
+#pragma unroll
+				for (int m = 0; m < NX; m++) acc = acc + Dq[row + m * NPSS] * xs[NX + m + col * NX];
+				dhi[i] = acc;
+			}
+			learned_residual<NX, NU>(p.learn, x0, dhi, R.dLf, R.dLg);
+		}
+		// cost, bounds (:238-254), QP, post-solve (:334-353)
+		double v[NV];
+		DiagMetric<NV> mt;
+#pragma unroll
+		for (int i = 0; i < NU; i++) {
+			R.lb[i] = p.lb[i];
+			R.ub[i] = p.ub[i];
+		}
+		R.lb[NU] = p.relaxSafeLb;
+		R.lb[NU + 1] = p.relaxReachLb;
+		R.ub[NU] = p.inf;
+		R.ub[NU + 1] = p.inf;
+#pragma unroll
+		for (int i = 0; i < NV; i++) {
+			mt.gi[i] = p.gi[i];
+			mt.gih[i] = p.gih[i];
+		}
+		int iters = 0;
+		const int st = qp_gi_solve<NV>(mt, c, R, v, &iters);
+		double uo[NU], r0 = 0.0, r1 = 0.0;
+		int32_t rc;
+		if (st == QP_OK) {
+#pragma unroll
+			for (int i = 0; i < NU; i++) uo[i] = input_saturate(v[i], p.lb[i], p.ub[i]);
+			r0 = v[NU];
+			r1 = v[NU + 1];
+			rc = 1;
+		} else {
+			double Du[NU * NX];
+			M::backup_controller(x0, uo, Du);
+#pragma unroll
+			for (int i = 0; i < NU; i++) uo[i] = input_saturate(uo[i], p.lb[i], p.ub[i]);
+			rc = -1;
+		}
+		if (live) {
+#pragma unroll
+			for (int i = 0; i < NU; i++) u_act[k * NU + i] = uo[i];
+			relax_out[k * 2] = r0;
+			relax_out[k * 2 + 1] = r1;
+			rc_out[k] = rc;
+			if (WITH_DIAG) {
+				double *d = diag + k * NDIAG;
+				d[0] = hSafetyNow;
+				d[1] = hBackupEnd;
+#pragma unroll
+				for (int s = 0; s < CAP; s++)
+					if (s < np) d[2 + s] = (double)kidx[R.order.slot(s) * T];
+				double *A = d + 2 + np, *b = A + NC * NV;
+				R.scan(
+				    [&](const int j, const double(&nn)[NV], const double rhs) {
+#pragma unroll
+					    for (int i = 0; i < NV; i++) A[j + i * NC] = nn[i];
+					    b[j] = rhs;
+				    },
+				    [](const int, const int, const bool, const double) {});
+			}
+		}
+		if (qp_iter_sum) {
+			unsigned int it = live ? (unsigned int)iters : 0u;
+#pragma unroll
+			for (int o = 16; o > 0; o >>= 1) it += __shfl_xor_sync(0xffffffffu, it, o);
+			if ((threadIdx.x & 31) == 0 && it) qp_rows_add(qp_iter_sum, (unsigned long long)it);
+		}
 	}
 }
 

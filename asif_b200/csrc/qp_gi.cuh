@@ -234,7 +234,7 @@ static __device__ __noinline__ bool qp_vertex_solve(double (&M)[NV][NV + 1], dou
 
 // N = the active rows [normal | rhs]; v is replaced by the direct solve when that satisfies the rows at least as well
 template <int NV>
-static __device__ __noinline__ void qp_vertex_polish(const double (&N)[NV][NV + 1], double (&v)[NV])
+static __device__ __noinline__ void qp_vertex_polish_rows(const double (&N)[NV][NV + 1], double (&v)[NV])
 {
 	double M[NV][NV + 1], vp[NV];
 	for (int a = 0; a < NV; a++)
@@ -253,6 +253,23 @@ static __device__ __noinline__ void qp_vertex_polish(const double (&N)[NV][NV + 
 	}
 	if (r_new <= r_old)
 		for (int i = 0; i < NV; i++) v[i] = vp[i];
+}
+
+// The same with the rows fetched out of line: the row functor arrives as a pointer to a COPY the caller makes inside its rare branch: the solver's own functor never has
+// its address taken and stays in registers (passing it by reference cost the hot kernels 2-7 %, round-2 A/B).
+template <int NV, class Rows>
+static __device__ __noinline__ void qp_vertex_polish(const Rows *rows, const int *act, double *v)
+{
+	double N[NV][NV + 1], vv[NV];
+	for (int a = 0; a < NV; a++) {
+		double n[NV], rhs = 0.0;
+		rows->get(act[a], n, rhs);
+		for (int i = 0; i < NV; i++) N[a][i] = n[i];
+		N[a][NV] = rhs;
+	}
+	for (int i = 0; i < NV; i++) vv[i] = v[i];
+	qp_vertex_polish_rows<NV>(N, vv);
+	for (int i = 0; i < NV; i++) v[i] = vv[i];
 }
 
 // v returns the minimiser when the result is QP_OK.
@@ -447,12 +464,20 @@ __device__ __forceinline__ int qp_gi_solve(const Metric &mt, const double (&c)[N
 		}
 	}
 	if (iters) *iters = it;
+#ifndef ASIF_QP_NO_POLISH // (A/B switch of scripts/build_variant.sh; the product is always built with the polish)
 	if (status == QP_OK && w.q == NV) {
 		double rmin = w.R[0][0];
 #pragma unroll
 		for (int a = 1; a < NV; a++) rmin = (w.R[a][a] < rmin) ? w.R[a][a] : rmin;
-		if (rmin < QP_POLISH_SIN) { // rare; only plain arrays go out of line (the row functor stays in registers)
-			double N[NV][NV + 1], vv[NV];
+		if (rmin < QP_POLISH_SIN) { // rare
+			double vv[NV];
+#pragma unroll
+			for (int i = 0; i < NV; i++) vv[i] = w.v[i];
+#ifdef ASIF_QP_POLISH_INLINE_ROWS
+			// rows fetched here, only plain arrays go out of line.  Which of the two forms costs the hot kernels less was
+			// measured per translation unit (round-2 A/B, 1e7 C2 states / 1e6 C5 states; no polish 3.45 / 12.10 ms):
+			// this form 3.54 / 12.92 ms, the copy form below 3.59 / 12.73 ms - engine.cu defines the macro, kernels_contract.cu not.
+			double N[NV][NV + 1];
 #pragma unroll 1
 			for (int a = 0; a < NV; a++) {
 				double n[NV], rhs = 0.0;
@@ -464,13 +489,19 @@ __device__ __forceinline__ int qp_gi_solve(const Metric &mt, const double (&c)[N
 				for (int i = 0; i < NV; i++) N[a][i] = n[i];
 				N[a][NV] = rhs;
 			}
+			qp_vertex_polish_rows<NV>(N, vv);
+#else
+			const Rows rows_copy = rows; // copies go to local memory here and only here
+			int act[NV];
 #pragma unroll
-			for (int i = 0; i < NV; i++) vv[i] = w.v[i];
-			qp_vertex_polish<NV>(N, vv);
+			for (int i = 0; i < NV; i++) act[i] = w.act[i];
+			qp_vertex_polish<NV, Rows>(&rows_copy, act, vv);
+#endif
 #pragma unroll
 			for (int i = 0; i < NV; i++) w.v[i] = vv[i];
 		}
 	}
+#endif
 #pragma unroll
 	for (int i = 0; i < NV; i++) v[i] = w.v[i];
 	return status;

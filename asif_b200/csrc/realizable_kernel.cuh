@@ -322,7 +322,7 @@ realizable_ip_filter_kernel(const RealizableParams p, const int64_t n, const dou
 		unsigned int it = live ? (unsigned int)iters : 0u;
 #pragma unroll
 		for (int o = 16; o > 0; o >>= 1) it += __shfl_xor_sync(0xffffffffu, it, o);
-		if ((threadIdx.x & 31) == 0 && it) atomicAdd(qp_iter_sum, (unsigned long long)it);
+		if ((threadIdx.x & 31) == 0 && it) qp_rows_add(qp_iter_sum, (unsigned long long)it);
 	}
 }
 

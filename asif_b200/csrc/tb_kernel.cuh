@@ -607,7 +607,7 @@ __device__ __forceinline__ void tb_filter_tile(const TbParams &p, const int64_t 
 		unsigned int it = live ? (unsigned int)qp_iters : 0u;
 #pragma unroll
 		for (int o = 16; o > 0; o >>= 1) it += __shfl_xor_sync(0xffffffffu, it, o);
-		if ((threadIdx.x & 31) == 0 && it) atomicAdd(qp_iter_sum, (unsigned long long)it);
+		if ((threadIdx.x & 31) == 0 && it) qp_rows_add(qp_iter_sum, (unsigned long long)it);
 	}
 }
 
@@ -721,7 +721,7 @@ tb_rollout_kernel(const TbParams p, const int64_t n, const int32_t steps, const 
 		unsigned long long it = iters;
 #pragma unroll
 		for (int o = 16; o > 0; o >>= 1) it += __shfl_xor_sync(0xffffffffu, it, o);
-		if ((threadIdx.x & 31) == 0 && it) atomicAdd(qp_iter_sum, it);
+		if ((threadIdx.x & 31) == 0 && it) qp_rows_add(qp_iter_sum, it);
 	}
 }
 

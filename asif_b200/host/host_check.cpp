@@ -65,10 +65,78 @@ static int update_options_mode(const char *in_path, const char *out_path)
 	return out ? 0 : fail("update-options: write");
 }
 
+// host_check --latency: microseconds per single-state filter() through the C++ host classes (no Python in the path),
+// the way the reference's example mains call it (examples/DoubleIntegrator_implicit_tb.cpp:117-131), and per
+// QPWrapperB200::solve(); median and 90th percentile of 2000 calls after 200 warm-up calls.
+#include <algorithm>
+#include <chrono>
+static void report_latency(const char *what, std::vector<double> &us)
+{
+	std::sort(us.begin(), us.end());
+	std::printf("latency %-46s median %6.2f us   p90 %6.2f us   min %6.2f us\n", what, us[us.size() / 2], us[us.size() * 9 / 10], us[0]);
+}
+static int latency_mode(void)
+{
+	using namespace ASIF;
+	typedef std::chrono::steady_clock clk;
+	const int warm = 200, reps = 2000;
+	std::vector<double> us(reps);
+	{
+		b200::FilterBatchExplicit asif(b200::Model::DoubleIntegrator);
+		const double lb[1] = {-1.0}, ub[1] = {1.0};
+		if (asif.initialize(lb, ub) != 1) return fail("latency: FilterBatchExplicit::initialize");
+		double x[2] = {0.3, 0.2}, uDes[1] = {0.9}, uAct[1] = {0.0}, relax = 0.0;
+		for (int i = 0; i < warm + reps; i++) {
+			x[0] = 0.3 + 1e-4 * (i % 100);
+			const clk::time_point t0 = clk::now();
+			asif.filter(x, uDes, uAct, relax);
+			if (i >= warm) us[i - warm] = std::chrono::duration<double, std::micro>(clk::now() - t0).count();
+		}
+		report_latency("C1 FilterBatchExplicit::filter (one state)", us);
+	}
+	{
+		b200::FilterBatchImplicitTB asif(b200::Model::DoubleIntegratorTB, 4);
+		b200::FilterBatchImplicitTB::Options o;
+		o.relaxSafeLb = 10.0; o.relaxTTS = 5.0; o.relaxMinOrtho = 5.0; o.backTrajHorizon = 10.0; o.backTrajExtend = 0.0; o.backTrajDt = 0.1;
+		const double lb[1] = {-1.0}, ub[1] = {1.0};
+		if (asif.initialize(lb, ub, o) != 1) return fail("latency: FilterBatchImplicitTB::initialize");
+		double x[2] = {0.3, 0.2}, uDes[1] = {0.9}, uAct[1] = {0.0}, relax = 0.0;
+		for (int i = 0; i < warm + reps; i++) {
+			x[0] = 0.3 + 1e-4 * (i % 100);
+			const clk::time_point t0 = clk::now();
+			asif.filter(x, uDes, uAct, relax);
+			if (i >= warm) us[i - warm] = std::chrono::duration<double, std::micro>(clk::now() - t0).count();
+		}
+		report_latency("C2 FilterBatchImplicitTB::filter (npBT 101)", us);
+	}
+	{
+		QPWrapperB200 qp(2, 18, true);
+		double H[4] = {1, 0, 0, 50}, c[2] = {-1.0, -1000}, A[36], b[18], lb[2] = {-1, 10}, ub[2] = {1, 1e20};
+		for (int i = 0; i < 18; i++) {
+			A[i] = (i % 3) - 1.0;
+			A[18 + i] = 0.1 * i;
+			b[i] = -1.0 - i;
+		}
+		if (qp.initialize(H, c, A, b, lb, ub) != 0) return fail("latency: QPWrapperB200::initialize");
+		for (int i = 0; i < warm + reps; i++) {
+			c[0] = -1.0 + 1e-3 * (i % 100);
+			const clk::time_point t0 = clk::now();
+			qp.updateCost(nullptr, c);
+			qp.updateA(A);
+			qp.updateb(b);
+			qp.solve();
+			if (i >= warm) us[i - warm] = std::chrono::duration<double, std::micro>(clk::now() - t0).count();
+		}
+		report_latency("QPWrapperB200 updateCost+updateA+updateb+solve", us);
+	}
+	return 0;
+}
+
 int main(int argc, char **argv)
 {
 	using namespace ASIF;
 	if (argc == 4 && std::string(argv[1]) == "--update-options") return update_options_mode(argv[2], argv[3]);
+	if (argc == 2 && std::string(argv[1]) == "--latency") return latency_mode();
 	// --- 1. the QP backend behind the abstract interface: min (v0-2)^2 + 50 (v1-10)^2, v0 + v1 >= 13, 0<=v0<=1
 	{
 		std::unique_ptr<QPWrapperAbstract> qp(new QPWrapperB200(2, 1, true));

@@ -24,3 +24,22 @@ if "c2" in which:
     x, ud = cf.c2_inputs(10_000_000)
     bc.run("C2 ASIFimplicitTB / DoubleIntegrator npBT=101, 1e7 states",
            ab.Engine(ab.FILTER_IMPLICIT_TB, ab.MODEL_DOUBLE_INTEGRATOR_TB, **cf.tb_engine_kwargs(cf.C2_TB_OPTS)), x, ud)
+if "c1big" in which:
+    x, ud = cf.c1_inputs(100_000_000)
+    bc.run("C1 ASIF explicit / DoubleIntegrator, 1e8 states",
+           ab.Engine(ab.FILTER_EXPLICIT, ab.MODEL_DOUBLE_INTEGRATOR, relaxLb=cf.C1_OPTS[0], relaxCost=cf.C1_OPTS[1]), x, ud, reps=5)
+if "c5roll" in which:
+    import time, torch
+    n, steps = 100_000, 1000
+    x, ud = cf.c5_inputs(n)
+    eng = ab.Engine(ab.FILTER_IMPLICIT_TB, ab.MODEL_SEGWAY, **cf.tb_engine_kwargs(cf.SEGWAY_TB_OPTS))
+    xd, udd = torch.from_numpy(x).cuda(), torch.from_numpy(ud).cuda()
+    ua = torch.empty((n, 1), dtype=torch.float64, device="cuda")
+    rc = torch.empty((n,), dtype=torch.int32, device="cuda")
+    xw = xd.clone()
+    eng.rollout_into(n, 10, 1e-3, xw, udd, ua, rc)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    hist = eng.rollout_into(n, steps, 1e-3, xd, udd, ua, rc, want_hist=True)
+    torch.cuda.synchronize()
+    print(json.dumps({"config": "C5 rollout 1e5 x 1000", "seconds": time.perf_counter() - t0, "hist": hist.tolist()}), flush=True)

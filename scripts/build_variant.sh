@@ -7,6 +7,7 @@ F="-O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -
 nvcc $F -fmad=false "$@" -c -o $out/obj_$name/engine.o asif_b200/csrc/engine.cu &
 nvcc $F -fmad=false "$@" -c -o $out/obj_$name/closed_loop.o asif_b200/csrc/closed_loop.cu &
 nvcc $F -fmad=true "$@" -c -o $out/obj_$name/kernels_contract.o asif_b200/csrc/kernels_contract.cu &
+nvcc $F -fmad=false "$@" -c -o $out/obj_$name/group.o asif_b200/csrc/group.cu &
 wait
 nvcc -shared -gencode arch=compute_100a,code=sm_100a -o $out/$name.so $out/obj_$name/*.o
 rm -rf $out/obj_$name
