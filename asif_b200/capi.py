@@ -102,6 +102,7 @@ def load_library():
     L.asif_engine_last_qp_iterations.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
     L.asif_engine_last_host_io.argtypes = [C.c_void_p, C.POINTER(C.c_int32)]
     L.asif_engine_host_io_stats.argtypes = [C.c_void_p, _dp, _ip]
+    L.asif_engine_latency_server.argtypes = [C.c_void_p, C.c_int32]
     L.asif_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_uint64]
     L.asif_host_free.argtypes = [C.c_void_p]
     L.asif_host_register.argtypes = [C.c_void_p, C.c_uint64]
@@ -354,6 +355,10 @@ class Engine:
         v = C.c_int32()
         _check(load_library().asif_engine_last_host_io(self._h, C.byref(v)))
         return int(v.value)
+
+    def latency_server(self, on=True):
+        """asif_engine_latency_server: a resident warp serves host batches of up to 32 states without a kernel launch"""
+        _check(load_library().asif_engine_latency_server(self._h, 1 if on else 0))
 
     def host_io_stats(self):
         """{mode name: (ms per 1e6 states, batches measured)} of the "auto" host-IO policy"""

@@ -98,6 +98,7 @@ int32_t asif_engine_closed_loop(asif_engine *e, int64_t n, const asif_loop_confi
 	const int64_t n_rec = log_records(c);
 	if (n_log > 0 && !log) return fail(ASIF_ERR_INVALID_ARGUMENT, "closed loop: log buffer is NULL");
 	CUDA_TRY(cudaSetDevice(e->cfg.device));
+	ServerPause pause(e); // scratch buffers are allocated and freed per call
 	const int nx = e->nx, nu = e->nu, nr = e->n_relax, W = log_width(e);
 	const bool host = mem == ASIF_MEM_HOST;
 	cudaStream_t st = (!host && stream) ? (cudaStream_t)stream : e->stream;

@@ -13,6 +13,7 @@
 #include "models.cuh"
 #include "qp_batch_kernel.cuh"
 #include "tb_kernel.cuh"
+#include "latency_server.cuh"
 
 #include <chrono>
 #include <cmath>
@@ -30,6 +31,8 @@ using namespace asifb;
 
 namespace {
 thread_local char g_err[512] = "";
+int server_stop(asif_engine *e);  // latency server, defined with the host-batch code below
+int server_start(asif_engine *e);
 }
 
 namespace asifb {
@@ -107,9 +110,9 @@ int launch_explicit(asif_engine *e, int64_t n, const double *x, const double *ud
 {
 	const unsigned blocks = (unsigned)((n + EXPL_THREADS - 1) / EXPL_THREADS);
 	if (diag)
-		explicit_filter_kernel<M, true><<<blocks, EXPL_THREADS, 0, st>>>(e->ex, n, x, ud, ua, relax, rc, diag, e->d_counters);
+		explicit_filter_kernel<M, true><<<blocks, EXPL_THREADS, 0, st>>>(e->ex, n, x, ud, ua, relax, rc, diag, e->ctr);
 	else
-		explicit_filter_kernel<M, false><<<blocks, EXPL_THREADS, 0, st>>>(e->ex, n, x, ud, ua, relax, rc, nullptr, e->d_counters);
+		explicit_filter_kernel<M, false><<<blocks, EXPL_THREADS, 0, st>>>(e->ex, n, x, ud, ua, relax, rc, nullptr, e->ctr);
 	CUDA_TRY(cudaGetLastError());
 	return ASIF_OK;
 }
@@ -123,9 +126,9 @@ int launch_robust(asif_engine *e, int64_t n, const double *x, const double *ud, 
 	if (!r) r = set_smem(robust_ip_filter_kernel<false>, smem);
 	if (r) return r;
 	if (diag)
-		robust_ip_filter_kernel<true><<<blocks, ROB_THREADS, smem, st>>>(e->rb, n, x, ud, ua, relax, rc, diag, e->d_counters);
+		robust_ip_filter_kernel<true><<<blocks, ROB_THREADS, smem, st>>>(e->rb, n, x, ud, ua, relax, rc, diag, e->ctr);
 	else
-		robust_ip_filter_kernel<false><<<blocks, ROB_THREADS, smem, st>>>(e->rb, n, x, ud, ua, relax, rc, nullptr, e->d_counters);
+		robust_ip_filter_kernel<false><<<blocks, ROB_THREADS, smem, st>>>(e->rb, n, x, ud, ua, relax, rc, nullptr, e->ctr);
 	CUDA_TRY(cudaGetLastError());
 	return ASIF_OK;
 }
@@ -135,9 +138,9 @@ int launch_realizable(asif_engine *e, int64_t n, const double *x, const double *
 {
 	const unsigned blocks = (unsigned)((n + RZ_THREADS - 1) / RZ_THREADS);
 	if (diag)
-		realizable_ip_filter_kernel<true><<<blocks, RZ_THREADS, e->rz_smem, st>>>(e->rz, n, x, ud, ua, relax, rc, diag, e->d_counters);
+		realizable_ip_filter_kernel<true><<<blocks, RZ_THREADS, e->rz_smem, st>>>(e->rz, n, x, ud, ua, relax, rc, diag, e->ctr);
 	else
-		realizable_ip_filter_kernel<false><<<blocks, RZ_THREADS, e->rz_smem, st>>>(e->rz, n, x, ud, ua, relax, rc, nullptr, e->d_counters);
+		realizable_ip_filter_kernel<false><<<blocks, RZ_THREADS, e->rz_smem, st>>>(e->rz, n, x, ud, ua, relax, rc, nullptr, e->ctr);
 	CUDA_TRY(cudaGetLastError());
 	return ASIF_OK;
 }
@@ -183,6 +186,8 @@ int launch_filter(asif_engine *e, int64_t n, const double *x, const double *ud, 
 } // namespace
 
 namespace asifb {
+int server_suspend(asif_engine *e) { return server_stop(e); }
+int server_resume(asif_engine *e) { return server_start(e); }
 int launch_filter_any(asif_engine *e, int64_t n, const double *x, const double *ud, double *ua, double *relax, int32_t *rc,
                       double *diag, cudaStream_t st)
 {
@@ -647,6 +652,7 @@ int32_t asif_engine_create(const asif_engine_config *cfg, asif_engine **out)
 		asif_engine_destroy(e);
 		return fail(ASIF_ERR_CUDA, "engine allocation failed: %s", cudaGetErrorString(err));
 	}
+	e->ctr = e->d_counters;
 	*out = e;
 	return ASIF_OK;
 }
@@ -655,6 +661,9 @@ int32_t asif_engine_destroy(asif_engine *e)
 {
 	if (!e) return ASIF_OK;
 	cudaSetDevice(e->cfg.device);
+	server_stop(e);
+	if (e->srv_stream) cudaStreamDestroy(e->srv_stream);
+	if (e->srv_mailbox) cudaFreeHost(e->srv_mailbox);
 	for (Slot &s : e->slot) {
 		if (s.stream) {
 			cudaStreamSynchronize(s.stream);
@@ -692,6 +701,113 @@ int32_t asif_engine_dims(const asif_engine *e, int32_t dims[6])
 } // extern "C"
 
 namespace {
+// ---- latency server (latency_server.cuh) ---------------------------------------------------------------------------
+constexpr size_t SRV_MAILBOX_BYTES = 16 << 10;
+
+int server_stop(asif_engine *e)
+{
+	if (!e->srv_on) return ASIF_OK;
+	volatile unsigned long long *hdr = reinterpret_cast<volatile unsigned long long *>(e->srv_mailbox);
+	__atomic_store_n(const_cast<unsigned long long *>(hdr), SRV_EXIT, __ATOMIC_RELEASE);
+	e->srv_on = false;
+	// bounded wait: a resident kernel that no longer polls its mailbox cannot be killed, but it must not hang the caller
+	const auto t0 = std::chrono::steady_clock::now();
+	for (;;) {
+		const cudaError_t q = cudaStreamQuery(e->srv_stream);
+		if (q == cudaSuccess) return ASIF_OK;
+		if (q != cudaErrorNotReady) return fail(ASIF_ERR_CUDA, "latency server ended with: %s", cudaGetErrorString(q));
+		if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 5.0)
+			return fail(ASIF_ERR_CUDA, "latency server did not stop within 5 s");
+	}
+}
+
+int server_start(asif_engine *e)
+{
+	if (e->srv_on) return ASIF_OK;
+	const bool tb_di = e->cfg.filter == ASIF_FILTER_IMPLICIT_TB && e->cfg.model == ASIF_MODEL_DOUBLE_INTEGRATOR_TB && e->cfg.npBTSS == 4;
+	const bool expl = e->cfg.filter == ASIF_FILTER_EXPLICIT && e->cfg.model == ASIF_MODEL_DOUBLE_INTEGRATOR;
+	if (!tb_di && !expl)
+		return fail(ASIF_ERR_UNSUPPORTED, "the latency server is built for ASIF / DoubleIntegrator and ASIFimplicitTB / DoubleIntegrator "
+		                                  "(npBTSS 4); other classes keep the launch path");
+	CUDA_TRY(cudaSetDevice(e->cfg.device));
+	if (!e->srv_mailbox) {
+		CUDA_TRY(cudaHostAlloc((void **)&e->srv_mailbox, SRV_MAILBOX_BYTES, cudaHostAllocMapped));
+		CUDA_TRY(cudaHostGetDevicePointer((void **)&e->srv_mailbox_dev, e->srv_mailbox, 0));
+	}
+	if (!e->srv_stream) CUDA_TRY(cudaStreamCreateWithFlags(&e->srv_stream, cudaStreamNonBlocking));
+	memset(e->srv_mailbox, 0, SRV_MAILBOX_BYTES);
+	e->srv_seq = 0;
+	if (expl) {
+		ExplicitParams p = e->ex;
+		p.custom_cost = 0;
+		p.lfh = p.lgh = nullptr;
+		explicit_server_kernel<DoubleIntegratorExplicit><<<1, 32, 0, e->srv_stream>>>(p, e->srv_mailbox_dev);
+	} else {
+		using M = DoubleIntegratorTB;
+		TbParams p = e->tb;
+		p.custom_cost = 0;
+		const size_t smem = sizeof(double) * tb_smem_doubles_per_thread<M, 4>() * TB_THREADS; // stride of the snapshots: a full CTA's
+		if (p.sat_mode == SAT_IDENTITY)
+			tb_server_kernel<M, 4, SAT_IDENTITY><<<1, 32, smem, e->srv_stream>>>(p, e->srv_mailbox_dev, nullptr);
+		else if (p.sat_mode >= SAT_POW2)
+			tb_server_kernel<M, 4, SAT_POW2><<<1, 32, smem, e->srv_stream>>>(p, e->srv_mailbox_dev, nullptr);
+		else
+			tb_server_kernel<M, 4, SAT_GENERAL><<<1, 32, smem, e->srv_stream>>>(p, e->srv_mailbox_dev, nullptr);
+	}
+	CUDA_TRY(cudaGetLastError());
+	e->srv_on = true;
+	return ASIF_OK;
+}
+
+// one batch of n <= 32 states through the resident warp; returns ASIF_OK, or a negative code (then the caller's arrays are untouched)
+int server_call(asif_engine *e, int64_t n, const double *x, const double *u_des, double *u_act, double *relax, int32_t *rc)
+{
+	const int nx = e->nx, nu = e->nu, nr = e->n_relax;
+	double *mb = e->srv_mailbox;
+	double *mx = mb + SRV_HDR, *mud = mx + SRV_MAX_STATES * nx, *mua = mud + SRV_MAX_STATES * nu, *mrl = mua + SRV_MAX_STATES * nu;
+	int32_t *mrc = reinterpret_cast<int32_t *>(mrl + SRV_MAX_STATES * nr);
+	memcpy(mx, x, sizeof(double) * n * nx);
+	memcpy(mud, u_des, sizeof(double) * n * nu);
+	unsigned long long *hdr = reinterpret_cast<unsigned long long *>(mb);
+	const unsigned long long seq = ++e->srv_seq;
+	__atomic_store_n(hdr + 1, (unsigned long long)n, __ATOMIC_RELEASE);
+	__atomic_store_n(hdr, seq, __ATOMIC_RELEASE);
+	const auto t0 = std::chrono::steady_clock::now();
+	for (unsigned spins = 0;; spins++) {
+		if (__atomic_load_n(hdr + 2, __ATOMIC_ACQUIRE) == seq) break;
+		if ((spins & 0xffff) == 0xffff) { // every ~65k polls: has the kernel died, or are we waiting absurdly long?
+			const cudaError_t q = cudaStreamQuery(e->srv_stream);
+			if (q != cudaErrorNotReady) {
+				e->srv_on = false;
+				return fail(ASIF_ERR_CUDA, "latency server stopped: %s", cudaGetErrorString(q));
+			}
+			if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 10.0) {
+				server_stop(e);
+				return fail(ASIF_ERR_CUDA, "latency server did not answer within 10 s");
+			}
+		}
+	}
+	memcpy(u_act, mua, sizeof(double) * n * nu);
+	memcpy(relax, mrl, sizeof(double) * n * nr);
+	memcpy(rc, mrc, sizeof(int32_t) * n);
+	return ASIF_OK;
+}
+
+// Allocation calls (cudaMalloc / cudaFree / cudaHostAlloc ...) may wait for the whole device, i.e. for ever while the
+// server's warp is resident (observed: cudaHostAlloc of the small-batch scratch never returned).  Every entry point that
+// can allocate therefore stops the server for its duration and restarts it on the way out (ServerPause, engine_internal.cuh;
+// ~20 us, and such calls move megabytes).  The device-pointer filter path of the two server classes allocates nothing and
+// runs beside the server.
+
+// every stream this engine launches on (never cudaDeviceSynchronize: it would wait for a running latency server for ever)
+int sync_engine_streams(asif_engine *e)
+{
+	if (e->stream) CUDA_TRY(cudaStreamSynchronize(e->stream));
+	for (Slot &sl : e->slot)
+		if (sl.stream) CUDA_TRY(cudaStreamSynchronize(sl.stream));
+	return ASIF_OK;
+}
+
 // Device alias of a caller's host range when the device can address it (cudaHostAlloc'ed memory, or memory registered
 // with cudaHostRegisterMapped; under unified addressing both report a device pointer), else nullptr.
 template <class T>
@@ -829,10 +945,15 @@ int32_t filter_batch_impl(asif_engine *e, int64_t n, const double *x, const doub
 	// driver calls that each wait for the one before.  Instead the arrays are copied by the CPU into a pinned scratch the
 	// device can address, one launch reads and writes it over PCIe, one synchronise, and the results are copied back.
 	// ASIF_B200_SMALL_INPLACE=0 switches it off.
+	const size_t o_x = 0, o_ud = o_x + sizeof(double) * n * nx, o_ua = o_ud + sizeof(double) * n * cw,
+	             o_relax = o_ua + sizeof(double) * n * nu, o_diag = o_relax + sizeof(double) * n * nr,
+	             o_rc = o_diag + (diag ? sizeof(double) * n * nd : 0), total = o_rc + sizeof(int32_t) * n;
+	if (e->srv_on && n <= SRV_MAX_STATES && !diag && cw == nu && !e->lie_lfh) { // latency server: no launch at all
+		e->last_host_io = ASIF_HOST_IO_INOUT;
+		return server_call(e, n, x, u_des, u_act, relax, rc);
+	}
+	ServerPause pause(e); // everything below may allocate
 	{
-		const size_t o_x = 0, o_ud = o_x + sizeof(double) * n * nx, o_ua = o_ud + sizeof(double) * n * cw,
-		             o_relax = o_ua + sizeof(double) * n * nu, o_diag = o_relax + sizeof(double) * n * nr,
-		             o_rc = o_diag + (diag ? sizeof(double) * n * nd : 0), total = o_rc + sizeof(int32_t) * n;
 		if (total <= SMALL_BATCH_BYTES && small_inplace_enabled()) {
 			if (!e->small_h) CUDA_TRY(cudaHostAlloc((void **)&e->small_h, SMALL_BATCH_BYTES, cudaHostAllocMapped));
 			if (!e->slot[0].stream) CUDA_TRY(cudaStreamCreateWithFlags(&e->slot[0].stream, cudaStreamNonBlocking));
@@ -840,12 +961,14 @@ int32_t filter_batch_impl(asif_engine *e, int64_t n, const double *x, const doub
 			char *h = e->small_h;
 			memcpy(h + o_x, x, sizeof(double) * n * nx);
 			memcpy(h + o_ud, u_des, sizeof(double) * n * cw);
-			CUDA_TRY(cudaMemsetAsync(e->d_counters, 0, N_COUNTERS * sizeof(unsigned long long), st));
 			e->ex.lfh = e->lie_lfh;
 			e->ex.lgh = e->lie_lgh;
 			e->last_host_io = ASIF_HOST_IO_INOUT;
+			// latency path: the QP-work statistic is not collected (no counter reset to enqueue, no atomics in the kernel)
+			e->ctr = nullptr;
 			const int r = launch_filter(e, n, (const double *)(h + o_x), (const double *)(h + o_ud), (double *)(h + o_ua),
 			                            (double *)(h + o_relax), (int32_t *)(h + o_rc), diag ? (double *)(h + o_diag) : nullptr, st);
+			e->ctr = e->d_counters;
 			if (r) return r;
 			CUDA_TRY(cudaStreamSynchronize(st));
 			memcpy(u_act, h + o_ua, sizeof(double) * n * nu);
@@ -1028,7 +1151,18 @@ int32_t asif_engine_set_input_cost(asif_engine *e, const double *H)
 			gis[t][i] = 1.0 / (2.0 * H[i + i * nu]);
 			gihs[t][i] = sqrt(gis[t][i]);
 		}
+	if (e->srv_on) { // the resident kernel holds its parameters by value: restart it with the new Hessian
+		int r = server_stop(e);
+		if (!r) r = server_start(e);
+		if (r) return r;
+	}
 	return ASIF_OK;
+}
+
+int32_t asif_engine_latency_server(asif_engine *e, int32_t on)
+{
+	if (!e) return fail(ASIF_ERR_INVALID_ARGUMENT, "engine is NULL");
+	return on ? server_start(e) : server_stop(e);
 }
 
 int32_t asif_engine_filter_batch_cost(asif_engine *e, int64_t n, const double *x, const double *H, const double *c,
@@ -1058,6 +1192,7 @@ int32_t asif_engine_filter_batch_lie(asif_engine *e, int64_t n, const double *x,
 	if (!Lfh || !Lgh) return fail(ASIF_ERR_INVALID_ARGUMENT, "Lfh / Lgh is NULL");
 	if (n <= 0) return n < 0 ? fail(ASIF_ERR_INVALID_ARGUMENT, "n < 0") : ASIF_OK;
 	CUDA_TRY(cudaSetDevice(e->cfg.device));
+	ServerPause pause(e);
 	set_custom_cost(e, 0);
 	double *dl = nullptr, *dg = nullptr;
 	if (mem == ASIF_MEM_DEVICE) {
@@ -1081,7 +1216,7 @@ int32_t asif_engine_filter_batch_lie(asif_engine *e, int64_t n, const double *x,
 	e->lie_lfh = e->lie_lgh = nullptr;
 	e->ex.lfh = e->ex.lgh = nullptr;
 	if (dl || dg) {
-		cudaDeviceSynchronize();
+		sync_engine_streams(e);
 		cudaFree(dl);
 		cudaFree(dg);
 	}
@@ -1113,6 +1248,7 @@ int32_t asif_engine_rollout(asif_engine *e, int64_t n, int32_t steps, double dt,
 		return ASIF_OK;
 	}
 	if (mem != ASIF_MEM_HOST) return fail(ASIF_ERR_INVALID_ARGUMENT, "mem must be ASIF_MEM_HOST or ASIF_MEM_DEVICE");
+	ServerPause pause(e);
 	Slot &s = e->slot[0];
 	int r = ensure_slot(e, s, n, false);
 	if (r) return r;
@@ -1238,7 +1374,10 @@ int32_t asif_engine_last_qp_iterations(asif_engine *e, uint64_t *rows_processed)
 {
 	if (!e || !rows_processed) return fail(ASIF_ERR_INVALID_ARGUMENT, "NULL argument");
 	CUDA_TRY(cudaSetDevice(e->cfg.device));
-	CUDA_TRY(cudaDeviceSynchronize());
+	{
+		const int r = sync_engine_streams(e);
+		if (r) return r;
+	}
 	unsigned long long part[QP_CTR_SPREAD], v = 0;
 	CUDA_TRY(cudaMemcpy(part, e->d_counters + QP_CTR_BASE, sizeof(part), cudaMemcpyDeviceToHost));
 	for (int i = 0; i < QP_CTR_SPREAD; i++) v += part[i];

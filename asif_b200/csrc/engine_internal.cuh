@@ -82,7 +82,8 @@ struct asif_engine {
 	const double *lie_lfh = nullptr, *lie_lgh = nullptr; // device arrays of the current filter_batch_lie call (explicit filter)
 	Slot slot[N_SLOTS];
 	cudaStream_t stream = nullptr; // device-memory calls without a caller stream
-	unsigned long long *d_counters = nullptr; // [0] qp rows processed, [1..8] rc histogram
+	unsigned long long *d_counters = nullptr; // counters on the device (filter_common.cuh: rc histogram, QP-work partial sums)
+	unsigned long long *ctr = nullptr;        // what the filter launches pass: d_counters, or nullptr while a small (latency) batch runs
 	uint64_t last_qp_rows = 0;
 	HostCopier *copier = nullptr; // created by the first large pageable batch
 	int copy_threads = 0;         // its thread count; 0 = HostCopier::default_threads() (a group shares the cores out)
@@ -93,6 +94,11 @@ struct asif_engine {
 	int io_samples[3] = {0, 0, 0};
 	unsigned io_calls = 0;
 	int num_sms = 148;
+	// latency server (latency_server.cuh): pinned mailbox the device can address, its stream, the last sequence number
+	double *srv_mailbox = nullptr, *srv_mailbox_dev = nullptr, *srv_snap = nullptr;
+	cudaStream_t srv_stream = nullptr;
+	bool srv_on = false;
+	unsigned long long srv_seq = 0;
 	// snapshot scratch of the persistent nx = 4 kernels: a ring, so that launches on different streams never share
 	// a buffer that may still be in use (the next user waits on the previous user's event)
 	struct SnapBuf {
@@ -206,12 +212,12 @@ int launch_tb_mode(asif_engine *e, int64_t n, const double *x, const double *ud,
 		auto k = tb_filter_kernel<M, NPBTSS, true, SATMODE>;
 		r = set_smem(k, smem);
 		if (r) return r;
-		k<<<blocks, TB_THREADS, smem, st>>>(e->tb, n, x, ud, ua, relax, rc, diag, e->d_counters, gsnap);
+		k<<<blocks, TB_THREADS, smem, st>>>(e->tb, n, x, ud, ua, relax, rc, diag, e->ctr, gsnap);
 	} else {
 		auto k = tb_filter_kernel<M, NPBTSS, false, SATMODE>;
 		r = set_smem(k, smem);
 		if (r) return r;
-		k<<<blocks, TB_THREADS, smem, st>>>(e->tb, n, x, ud, ua, relax, rc, nullptr, e->d_counters, gsnap);
+		k<<<blocks, TB_THREADS, smem, st>>>(e->tb, n, x, ud, ua, relax, rc, nullptr, e->ctr, gsnap);
 	}
 	CUDA_TRY(cudaGetLastError());
 	return tb_release(e, buf, st);
@@ -278,7 +284,7 @@ int launch_implicit_t(asif_engine *e, int64_t n, const double *x, const double *
 			int buf;
 			int r = acquire_scratch(e, need, st, buf);
 			if (r) return r;
-			kern<<<blocks2, IMP2_THREADS, smem2, st>>>(e->im, n, x, ud, ua, relax, rc, diag, e->d_counters, e->snapbuf[buf].p);
+			kern<<<blocks2, IMP2_THREADS, smem2, st>>>(e->im, n, x, ud, ua, relax, rc, diag, e->ctr, e->snapbuf[buf].p);
 			CUDA_TRY(cudaGetLastError());
 			return tb_release(e, buf, st);
 		};
@@ -301,17 +307,38 @@ int launch_implicit_t(asif_engine *e, int64_t n, const double *x, const double *
 		auto k = pow2 ? implicit_filter_kernel<M, NPBTSS, true, SAT_POW2, RB> : implicit_filter_kernel<M, NPBTSS, true, SAT_LO, RB>;
 		int r = set_smem(k, smem);
 		if (r) return r;
-		k<<<blocks, IMP_THREADS, smem, st>>>(e->im, n, x, ud, ua, relax, rc, diag, e->d_counters);
+		k<<<blocks, IMP_THREADS, smem, st>>>(e->im, n, x, ud, ua, relax, rc, diag, e->ctr);
 	} else {
 		auto k = pow2 ? implicit_filter_kernel<M, NPBTSS, false, SAT_POW2, RB> : implicit_filter_kernel<M, NPBTSS, false, SAT_LO, RB>;
 		int r = set_smem(k, smem);
 		if (r) return r;
-		k<<<blocks, IMP_THREADS, smem, st>>>(e->im, n, x, ud, ua, relax, rc, nullptr, e->d_counters);
+		k<<<blocks, IMP_THREADS, smem, st>>>(e->im, n, x, ud, ua, relax, rc, nullptr, e->ctr);
 	}
 	CUDA_TRY(cudaGetLastError());
 	return ASIF_OK;
 }
 
+
+// defined in engine.cu: the latency server's stop / start (latency_server.cuh)
+namespace asifb {
+int server_suspend(asif_engine *e);
+int server_resume(asif_engine *e);
+}
+// RAII: stops the latency server for the duration of a call that may allocate, restarts it on the way out (see engine.cu)
+struct ServerPause {
+	asif_engine *e;
+	bool was_on;
+	explicit ServerPause(asif_engine *e_) : e(e_), was_on(e_->srv_on)
+	{
+		if (was_on) asifb::server_suspend(e);
+	}
+	~ServerPause()
+	{
+		if (was_on) asifb::server_resume(e);
+	}
+	ServerPause(const ServerPause &) = delete;
+	ServerPause &operator=(const ServerPause &) = delete;
+};
 
 // defined in engine.cu: dispatch of one filter launch on device pointers
 namespace asifb {

@@ -51,18 +51,17 @@ struct RegRows {
 	}
 };
 
+// one state (index k) of the explicit filter; shared by the batch kernel and the latency server (latency_server.cuh)
 template <class M, bool WITH_DIAG>
-__global__ void __launch_bounds__(EXPL_THREADS)
-explicit_filter_kernel(const ExplicitParams p, const int64_t n, const double *__restrict__ x_in,
-                       const double *__restrict__ u_des, double *__restrict__ u_act, double *__restrict__ relax_out,
-                       int32_t *__restrict__ rc_out, double *__restrict__ diag,
-                       unsigned long long *__restrict__ qp_iter_sum)
+__device__ __forceinline__ void explicit_filter_tile(const ExplicitParams &p, const int64_t n, const int64_t k, const double *__restrict__ x_in,
+                                                     const double *__restrict__ u_des, double *__restrict__ u_act,
+                                                     double *__restrict__ relax_out, int32_t *__restrict__ rc_out,
+                                                     double *__restrict__ diag, unsigned long long *__restrict__ qp_iter_sum)
 {
 	constexpr int NX = M::NX, NU = M::NU, NPSS = M::NPSS, NV = NU + 1, NC = NPSS;
 	__shared__ double smem[NC * (NV + 1) * EXPL_THREADS];
 	const int T = EXPL_THREADS;
 	double *rows = smem + threadIdx.x;
-	const int64_t k = (int64_t)blockIdx.x * T + threadIdx.x;
 	const bool live = k < n;
 	const int64_t kk = live ? k : (n - 1);
 	double x[NX], c[NU + 1];
@@ -222,6 +221,17 @@ explicit_filter_kernel(const ExplicitParams p, const int64_t n, const double *__
 		for (int o = 16; o > 0; o >>= 1) it += __shfl_xor_sync(0xffffffffu, it, o);
 		if ((threadIdx.x & 31) == 0 && it) qp_rows_add(qp_iter_sum, (unsigned long long)it);
 	}
+}
+
+template <class M, bool WITH_DIAG>
+__global__ void __launch_bounds__(EXPL_THREADS)
+explicit_filter_kernel(const ExplicitParams p, const int64_t n, const double *__restrict__ x_in,
+                       const double *__restrict__ u_des, double *__restrict__ u_act, double *__restrict__ relax_out,
+                       int32_t *__restrict__ rc_out, double *__restrict__ diag,
+                       unsigned long long *__restrict__ qp_iter_sum)
+{
+	explicit_filter_tile<M, WITH_DIAG>(p, n, (int64_t)blockIdx.x * EXPL_THREADS + threadIdx.x, x_in, u_des, u_act, relax_out, rc_out, diag,
+	                                   qp_iter_sum);
 }
 
 } // namespace asifb

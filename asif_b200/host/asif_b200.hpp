@@ -225,6 +225,14 @@ namespace ASIF
 				devices_ = devices;
 				useGroup_ = true;
 			}
+			// Latency server for the single-state filter() calls (asif_engine_latency_server): call after initialize();
+			// returns 0, or ASIF_ERR_UNSUPPORTED for the classes that keep the launch path.  updateOptions() rebuilds the
+			// engine: switch it on again afterwards.
+			int32_t setLowLatency(const bool on)
+			{
+				if (engine_ == nullptr) return ASIF_ERR_INVALID_ARGUMENT;
+				return asif_engine_latency_server(engine_, on ? 1 : 0);
+			}
 			uint32_t nDevices(void) const { return group_ ? (uint32_t)asif_engine_group_size(group_) : (engine_ ? 1u : 0u); }
 			// filter(x, uDes, uAct, relax) of the reference class on n states; host arrays
 			// X[n*nx], UDes[n*nu], UAct[n*nu], Relax[n*nRelax], rc[n]; returns 0 or a negative ASIF_ERR_* (<= -101)

@@ -93,6 +93,16 @@ static int latency_mode(void)
 			if (i >= warm) us[i - warm] = std::chrono::duration<double, std::micro>(clk::now() - t0).count();
 		}
 		report_latency("C1 FilterBatchExplicit::filter (one state)", us);
+		double uLaunch = uAct[0];
+		if (asif.setLowLatency(true) != 0) return fail("latency: setLowLatency (explicit)");
+		for (int i = 0; i < warm + reps; i++) {
+			x[0] = 0.3 + 1e-4 * (i % 100);
+			const clk::time_point t0 = clk::now();
+			if (asif.filter(x, uDes, uAct, relax) <= -100) return fail("latency: engine error through the server (explicit)");
+			if (i >= warm) us[i - warm] = std::chrono::duration<double, std::micro>(clk::now() - t0).count();
+		}
+		report_latency("C1 ... through the latency server", us);
+		if (uAct[0] != uLaunch) return fail("latency: server and launch path differ (explicit)");
 	}
 	{
 		b200::FilterBatchImplicitTB asif(b200::Model::DoubleIntegratorTB, 4);
@@ -108,6 +118,16 @@ static int latency_mode(void)
 			if (i >= warm) us[i - warm] = std::chrono::duration<double, std::micro>(clk::now() - t0).count();
 		}
 		report_latency("C2 FilterBatchImplicitTB::filter (npBT 101)", us);
+		const double uLaunch = uAct[0], rLaunch = relax;
+		if (asif.setLowLatency(true) != 0) return fail("latency: setLowLatency (TB)");
+		for (int i = 0; i < warm + reps; i++) {
+			x[0] = 0.3 + 1e-4 * (i % 100);
+			const clk::time_point t0 = clk::now();
+			if (asif.filter(x, uDes, uAct, relax) <= -100) return fail("latency: engine error through the server (TB)");
+			if (i >= warm) us[i - warm] = std::chrono::duration<double, std::micro>(clk::now() - t0).count();
+		}
+		report_latency("C2 ... through the latency server", us);
+		if (uAct[0] != uLaunch || relax != rLaunch) return fail("latency: server and launch path differ (TB)");
 	}
 	{
 		QPWrapperB200 qp(2, 18, true);

@@ -172,6 +172,16 @@ int32_t asif_engine_last_host_io(const asif_engine *e, int32_t *mode);
 int32_t asif_engine_host_io_stats(const asif_engine *e, double ms_per_1e6_states[3], int32_t samples[3]);
 
 /*
+ * Latency server (the single-state user of the example mains, one filter() per control step).  on = 1
+ * keeps one warp resident on the device; host batches of up to 32 states (filter(x, uDes, ...), no diag) then go through a
+ * pinned mailbox instead of a kernel launch: the same per-state code, the same bits, about 10 us less per call.  Built for
+ * ASIF / DoubleIntegrator and ASIFimplicitTB / DoubleIntegrator (npBTSS 4); ASIF_ERR_UNSUPPORTED otherwise (the launch path
+ * stays).  on = 0 stops it; asif_engine_destroy stops it too.  While it runs, do not call cudaDeviceSynchronize on this
+ * device from the same thread of control (it waits for the resident kernel): synchronise streams instead.
+ */
+int32_t asif_engine_latency_server(asif_engine *e, int32_t on);
+
+/*
  * The filter(x, H, c, uAct[, relax]) overloads (src/asif_implicit_tb.cpp:252-363, src/asif.cpp:153-210,
  * src/asif_implicit.cpp:296-356, src/asif_implicit_robust.cpp:384-441): the caller supplies the linear cost c of the
  * whole decision vector, c[n][nv] per state (the input part AND the relax entries, which updateCost(uDes) would

@@ -236,3 +236,55 @@ def test_small_batches_in_place_match_the_copy_path(ab, monkeypatch):
             assert eng.last_host_io() == (ab.HOST_IO_INOUT if small else ab.HOST_IO_STAGED)
             for a, b in zip(out, ref):
                 assert np.array_equal(a, b, equal_nan=True)
+
+
+@pytest.mark.parametrize("which", ["explicit", "tb"])
+def test_latency_server_matches_launch_path(which):
+    """asif_engine_latency_server: host batches of <= 32 states through the resident warp return the bits of the launch
+    path; larger batches, diag requests and the (H, c) overload keep the launch path while it runs; stop / start / H change."""
+    import asif_b200 as ab
+    if which == "explicit":
+        eng = ab.Engine(ab.FILTER_EXPLICIT, ab.MODEL_DOUBLE_INTEGRATOR, relaxLb=cf.C1_OPTS[0], relaxCost=cf.C1_OPTS[1])
+        x, ud = cf.c1_inputs(4000, seed=321)
+    else:
+        eng = ab.Engine(ab.FILTER_IMPLICIT_TB, ab.MODEL_DOUBLE_INTEGRATOR_TB, **cf.tb_engine_kwargs(cf.C2_TB_OPTS))
+        x, ud = cf.c2_inputs(4000, seed=322)
+    want = eng.filter_batch(x, ud)
+    eng.latency_server(True)
+    for lo, hi in ((0, 1), (1, 2), (2, 34), (34, 66), (66, 97), (100, 131)):  # 1, 1, 32, 32, 31, 31 states
+        for a in range(lo, hi, 32):
+            b = min(hi, a + 32)
+            got = eng.filter_batch(x[a:b], ud[a:b])
+            for p, q in zip(got, want):
+                assert np.array_equal(p, q[a:b]), (which, a, b)
+    for k in range(200, 700):  # the example main loop's pattern: one state per call
+        got = eng.filter_batch(x[k:k + 1], ud[k:k + 1])
+        assert got[2][0] == want[2][k] and got[0][0, 0] == want[0][k, 0] and got[1][0, 0] == want[1][k, 0]
+    big = eng.filter_batch(x, ud)  # a large batch while the server is resident: launch path, same bits
+    for p, q in zip(big, want):
+        assert np.array_equal(p, q)
+    d1 = eng.filter_batch(x[:8], ud[:8], want_diag=True)  # diag: launch path
+    assert np.array_equal(d1[0], want[0][:8])
+    if which == "tb":
+        H, c = cf.custom_cost(ud[:16], eng.nv, seed=9)
+        a = eng.filter_batch_cost(x[:16], c, H)             # (H, c): launch path, and the server restarts with the new H
+        eng.latency_server(False)
+        b = eng.filter_batch_cost(x[:16], c, None)
+        for p, q in zip(a, b):
+            assert np.array_equal(p, q)
+        eng.latency_server(True)
+        s1 = eng.filter_batch(x[:16], ud[:16])              # server with H = 2.5 in force
+        eng.latency_server(False)
+        s2 = eng.filter_batch(x[:16], ud[:16])
+        for p, q in zip(s1, s2):
+            assert np.array_equal(p, q)
+    eng.latency_server(False)
+    eng.latency_server(False)
+    eng.close()
+
+
+def test_latency_server_refused_for_other_classes():
+    import asif_b200 as ab
+    eng = ab.Engine(ab.FILTER_IMPLICIT, ab.MODEL_INVERTED_PENDULUM, **cf.implicit_engine_kwargs(cf.C3A_SHORT_OPTS))
+    with pytest.raises(ab.AsifError):
+        eng.latency_server(True)
