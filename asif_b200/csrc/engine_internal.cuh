@@ -94,6 +94,7 @@ struct asif_engine {
 	int io_samples[3] = {0, 0, 0};
 	unsigned io_calls = 0;
 	int num_sms = 148;
+	long long l2_persist_max = -1, l2_window_max = 0; // persisting-L2 limits of the device (-1: not queried yet)
 	// latency server (latency_server.cuh): pinned mailbox the device can address, its stream, the last sequence number
 	double *srv_mailbox = nullptr, *srv_mailbox_dev = nullptr, *srv_snap = nullptr;
 	cudaStream_t srv_stream = nullptr;
@@ -117,6 +118,45 @@ int set_smem(K kernel, size_t bytes)
 {
 	if (bytes > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
 	return ASIF_OK;
+}
+
+// L2 residency of a scratch buffer for the launches that follow on stream st (bytes = 0 clears the window again).
+// The snapshot scratch of the persistent nx = 4 kernels is rewritten tile after tile by the same threads and only ever read
+// back by them: nothing in it needs to reach HBM, but with the default policy its lines were evicted between two uses and
+// 119 of the 142 MB of DRAM traffic of a 2e5-state segway launch were such write-backs (profiles/r01_c5_*; 11.8x the 12 MB
+// of algorithmic traffic).  Marking the window persisting (set-aside L2, cudaLimitPersistingL2CacheSize) keeps the lines on
+// chip until they are overwritten.  ASIF_B200_L2_PERSIST=0 switches it off.  Failures are ignored: this is a hint.
+inline void scratch_l2_window(asif_engine *e, cudaStream_t st, void *p, size_t bytes)
+{
+	static const bool enabled = []() {
+		const char *v = getenv("ASIF_B200_L2_PERSIST");
+		return !(v && v[0] == '0');
+	}();
+	if (!enabled) return;
+	if (e->l2_persist_max < 0) { // once per engine: the device's limits, and the set-aside at its maximum
+		cudaDeviceProp prop;
+		e->l2_persist_max = 0;
+		if (cudaGetDeviceProperties(&prop, e->cfg.device) == cudaSuccess && prop.persistingL2CacheMaxSize > 0) {
+			if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)prop.persistingL2CacheMaxSize) == cudaSuccess) {
+				e->l2_persist_max = (long long)prop.persistingL2CacheMaxSize;
+				e->l2_window_max = (long long)prop.accessPolicyMaxWindowSize;
+			}
+		}
+		cudaGetLastError();
+	}
+	if (e->l2_persist_max <= 0) return;
+	cudaStreamAttrValue a;
+	memset(&a, 0, sizeof(a));
+	if (bytes > 0) {
+		const size_t win = bytes < (size_t)e->l2_window_max ? bytes : (size_t)e->l2_window_max;
+		a.accessPolicyWindow.base_ptr = p;
+		a.accessPolicyWindow.num_bytes = win;
+		a.accessPolicyWindow.hitRatio = win <= (size_t)e->l2_persist_max ? 1.0f : (float)((double)e->l2_persist_max / (double)win);
+		a.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+		a.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+	}
+	cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &a);
+	cudaGetLastError();
 }
 
 // A scratch buffer of `need` bytes for a launch on stream st, out of the engine's ring: one last used on this same stream
@@ -185,12 +225,14 @@ int tb_geometry(asif_engine *e, int64_t n, cudaStream_t st, unsigned &blocks, si
 	asif_engine::SnapBuf &b = e->snapbuf[buf];
 	CUDA_TRY(cudaMemsetAsync(b.p, 0, sizeof(double) * TB_SCRATCH_HEADER, st)); // tile counter
 	gsnap = b.p;
+	scratch_l2_window(e, st, b.p, need);
 	return ASIF_OK;
 }
 
 inline int tb_release(asif_engine *e, int buf, cudaStream_t st)
 {
 	if (buf >= 0) {
+		scratch_l2_window(e, st, nullptr, 0); // the window applies to the launch just made, not to what the stream runs next
 		CUDA_TRY(cudaEventRecord(e->snapbuf[buf].ev, st));
 		e->snapbuf[buf].used = true;
 		e->snapbuf[buf].last = st;
