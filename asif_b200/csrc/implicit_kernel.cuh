@@ -517,7 +517,7 @@ __host__ __device__ constexpr size_t imp_scratch_doubles_per_thread(const int np
 template <int NPBTSS>
 __host__ __device__ constexpr int imp2_smem_doubles_per_thread()
 {
-	return np_capacity(NPBTSS) + (np_capacity(NPBTSS) + 1) / 2;
+	return 2 * (np_capacity(NPBTSS) + (np_capacity(NPBTSS) + 1) / 2); // block list + point list: keys and indices
 }
 
 // one Euler step of the augmented backup flow, X_i = X_{i-1} + dt rhs(X_{i-1}) (src/asif_implicit.cpp:461-484), and min_j h_j(x_i)
@@ -562,8 +562,11 @@ implicit_ckpt_kernel(const ImplicitParams p, const int64_t n, const double *__re
 	const int NCK = ((N - 1) >> IMP_CK_LOG) + 1;
 
 	extern __shared__ double smem[];
-	double *keys = smem + threadIdx.x;                                              // [slot]
-	int *kidx = reinterpret_cast<int *>(smem + CAP * T) + threadIdx.x;              // [slot]
+	constexpr int LST = CAP + (CAP + 1) / 2; // doubles of one list per thread
+	double *keys = smem + threadIdx.x;                                              // point list: min h by slot
+	int *kidx = reinterpret_cast<int *>(smem + CAP * T) + threadIdx.x;              //             trajectory index by slot
+	double *bkeys = smem + LST * T + threadIdx.x;                                   // block list: min over the block by slot
+	int *bidx = reinterpret_cast<int *>(smem + (LST + CAP) * T) + threadIdx.x;      //             block number by slot
 	// this thread's scratch: checkpoints [c][e], then snapshots [slot][e]; element stride T (coalesced across the warp)
 	double *ck = gscratch + (size_t)blockIdx.x * ((size_t)NCK * NSC + (size_t)CAP * NS) * T + threadIdx.x;
 	double *snap = ck + (size_t)NCK * NSC * T;
@@ -615,14 +618,13 @@ implicit_ckpt_kernel(const ImplicitParams p, const int64_t n, const double *__re
 		for (int i = 0; i < NU * NX; i++) zoh.Du[i] = 0.0;
 		zoh.t_last = -1.;
 #pragma unroll
-		for (int s = 1; s < CAP; s++) {
-			keys[s * T] = INFINITY;
-			kidx[s * T] = -1;
+		for (int s = 0; s < CAP; s++) {
+			bkeys[s * T] = INFINITY;
+			bidx[s * T] = -1;
 		}
-		keys[0] = hSafetyNow;
-		kidx[0] = 0;
-		R.order.init();
-		double kmin = hSafetyNow, kmax = (CAP > 1) ? INFINITY : hSafetyNow;
+		ImpOrder<CAP> ob; // order of the block list
+		ob.init();
+		double bkmin = INFINITY, bkmax = INFINITY;
 		// checkpoint 0 = the initial point
 #pragma unroll
 		for (int e = 0; e < NS; e++) ck[e * T] = X[e];
@@ -634,39 +636,44 @@ implicit_ckpt_kernel(const ImplicitParams p, const int64_t n, const double *__re
 			ck[(NS + NU + NU * NX) * T] = zoh.t_last;
 		}
 
-		// ---- pass A: the whole horizon; list of the CAP smallest points (key, index) and a checkpoint every IMP_CK steps
-		// (two nested loops: the checkpoint store sits between the inner loops instead of behind a per-step test)
+		// ---- pass A: the whole horizon.  Per step only the running minimum of min h over the current BLOCK (the IMP_CK points
+		// that follow a checkpoint); per block one insert into the list of the CAP blocks with the smallest minimum, ties
+		// keeping the earlier block first, and the checkpoint store.  The CAP smallest POINTS (by min h, ties by index) all
+		// lie in those blocks: a point p of block B among them has (min of B, B) <= p, and CAP blocks ahead of B in the list
+		// would each hold a point ahead of p.  Point 0 is not in any block; pass B starts the point list with it.
 		for (int c0 = 0; c0 < N - 1; c0 += IMP_CK) {
-		const int iend = (c0 + IMP_CK < N - 1) ? c0 + IMP_CK : N - 1;
-		for (int i = c0 + 1; i <= iend; i++) {
-			const double hmin = imp_advance<M, SATMODE, RB>(p, i, X, zoh);
-			if (hmin < kmax) {
-				const int slot = R.order.last(); // the evicted (largest) entry's slot takes the new point
-				if (hmin < kmin) {
-					R.order.push_front(slot);
-					kmin = hmin;
+			const int iend = (c0 + IMP_CK < N - 1) ? c0 + IMP_CK : N - 1;
+			double bmin = INFINITY;
+			for (int i = c0 + 1; i <= iend; i++) {
+				const double hmin = imp_advance<M, SATMODE, RB>(p, i, X, zoh);
+				bmin = (hmin < bmin) ? hmin : bmin;
+			}
+			if (bmin < bkmax) {
+				const int slot = ob.last(); // the evicted (largest) entry's slot takes the new block
+				if (bmin < bkmin) {
+					ob.push_front(slot);
+					bkmin = bmin;
 				} else {
-					int pl = 1; // first place whose key is larger (behind equal keys: ties keep the earlier index first)
-					while (pl < CAP - 1 && !(hmin < keys[R.order.slot(pl) * T])) pl++;
-					R.order.insert_at(pl, slot);
+					int pl = 1; // first place whose key is larger (behind equal keys: ties keep the earlier block first)
+					while (pl < CAP - 1 && !(bmin < bkeys[ob.slot(pl) * T])) pl++;
+					ob.insert_at(pl, slot);
 				}
-				keys[slot * T] = hmin;
-				kidx[slot * T] = i;
-				kmax = keys[R.order.last() * T];
+				bkeys[slot * T] = bmin;
+				bidx[slot * T] = c0 >> IMP_CK_LOG;
+				bkmax = bkeys[ob.last() * T];
 			}
-		}
-		if (iend == c0 + IMP_CK) { // the state after step iend = a multiple of the spacing: checkpoint iend >> ck_log
-			double *q = ck + (size_t)(iend >> IMP_CK_LOG) * NSC * T;
+			if (iend == c0 + IMP_CK) { // the state after step iend = a multiple of the spacing: checkpoint iend >> ck_log
+				double *q = ck + (size_t)(iend >> IMP_CK_LOG) * NSC * T;
 #pragma unroll
-			for (int e = 0; e < NS; e++) q[e * T] = X[e];
-			if (RB) {
+				for (int e = 0; e < NS; e++) q[e * T] = X[e];
+				if (RB) {
 #pragma unroll
-				for (int t = 0; t < NU; t++) q[(NS + t) * T] = zoh.u[t];
+					for (int t = 0; t < NU; t++) q[(NS + t) * T] = zoh.u[t];
 #pragma unroll
-				for (int t = 0; t < NU * NX; t++) q[(NS + NU + t) * T] = zoh.Du[t];
-				q[(NS + NU + NU * NX) * T] = zoh.t_last;
+					for (int t = 0; t < NU * NX; t++) q[(NS + NU + t) * T] = zoh.Du[t];
+					q[(NS + NU + NU * NX) * T] = zoh.t_last;
+				}
 			}
-		}
 		}
 		// open-loop dynamics at the current state (:414-416) and the backup rows at the trajectory end (:542-554)
 		M::dynamics(x0, R.f, R.g);
@@ -702,24 +709,50 @@ implicit_ckpt_kernel(const ImplicitParams p, const int64_t n, const double *__re
 			}
 		}
 
-		// ---- pass B: snapshots of the np selected points, re-integrated from the checkpoints
+		// ---- pass B: the point list (the CAP smallest points by (min h, index)) and its snapshots, from the listed blocks
+		// re-integrated out of their checkpoints.  Blocks are taken in ascending order of their minimum; once the point list is
+		// full, a block whose minimum cannot get in ends the lane's work (every later block has a larger minimum or the same
+		// minimum and a later index).  A visited block always leaves its minimum in the final list (later blocks only hold
+		// points behind it), so the number of rounds is the number of blocks that hold final points: typically 1-2, the
+		// selected points cluster at the start, at the end or around one excursion.  Every lane works on ITS OWN block (the
+		// lanes gather their checkpoints from different places and run the same instruction stream on them); a round costs
+		// the warp one block's worth of steps.  The Euler step is the same inlined function as in pass A: bit for bit the
+		// same trajectory.
 #ifndef IMP2_SKIP_PASS_B // (timing experiments only: results are garbage without it)
-		// Every lane works on ITS OWN next segment (lanes gather their checkpoints from different places and run the same
-		// instruction stream on them), so a round costs the warp one segment's worth of steps whatever the lanes' segments are,
-		// and the number of rounds is the largest number of distinct segments any one lane needs (typically 1-2, at most np).
 		{
-			int done = -1;
+#pragma unroll
+			for (int s = 1; s < CAP; s++) {
+				keys[s * T] = INFINITY;
+				kidx[s * T] = -1;
+			}
+			keys[0] = hSafetyNow; // point 0 = the current state, Q = I
+			kidx[0] = 0;
+			R.order.init();
+#pragma unroll
+			for (int e = 0; e < NS; e++) snap[(size_t)e * T] = 0.0;
+#pragma unroll
+			for (int e = 0; e < NX; e++) snap[(size_t)e * T] = x0[e];
+#pragma unroll
+			for (int e = 0; e < NX; e++) snap[(size_t)(NX + e * (NX + 1)) * T] = 1.0;
+			double kmax = (CAP > 1) ? INFINITY : hSafetyNow;
+			int nb = 0; // blocks of the list looked at so far
 			for (;;) {
-				int mine = 0x7fffffff;
-#pragma unroll 1
-				for (int s = 0; s < np; s++) {
-					const int seg = kidx[R.order.slot(s) * T] >> IMP_CK_LOG;
-					if (seg > done && seg < mine) mine = seg;
+				int mine = -1;
+				if (nb < CAP) {
+					const int sl = ob.slot(nb);
+					const int b = bidx[sl * T];
+					const double bk = bkeys[sl * T];
+					nb++;
+					const bool wanted = b >= 0 && ((bk < kmax) || (bk == kmax && (b << IMP_CK_LOG) + 1 < kidx[R.order.last() * T]));
+					if (wanted)
+						mine = b;
+					else
+						nb = CAP;
 				}
-				const bool have = mine != 0x7fffffff;
+				const bool have = mine >= 0;
 				if (!__any_sync(0xffffffffu, have)) break;
-				unsigned long long need = 0ull;
-				int last = -1;
+				int nsteps = 0;
+				const int base_i = have ? (mine << IMP_CK_LOG) : 0;
 				if (have) {
 					const double *q = ck + (size_t)mine * NSC * T;
 #pragma unroll
@@ -731,31 +764,28 @@ implicit_ckpt_kernel(const ImplicitParams p, const int64_t n, const double *__re
 						for (int t = 0; t < NU * NX; t++) zoh.Du[t] = q[(NS + NU + t) * T];
 						zoh.t_last = q[(NS + NU + NU * NX) * T];
 					}
-#pragma unroll 1
-					for (int s = 0; s < np; s++) {
-						const int is = kidx[R.order.slot(s) * T];
-						if ((is >> IMP_CK_LOG) == mine) {
-							const int j = is & (IMP_CK - 1);
-							need |= 1ull << j;
-							last = j > last ? j : last;
-						}
-					}
-					done = mine;
+					nsteps = (N - 1 - base_i < IMP_CK) ? (N - 1 - base_i) : IMP_CK;
 				}
-				const int base_i = have ? (mine << IMP_CK_LOG) : 0;
-				const int wlast = __reduce_max_sync(0xffffffffu, last);
-				for (int j = 0; j <= wlast; j++) {
-					if (j <= last) {
-						if (j > 0) imp_advance<M, SATMODE, RB>(p, base_i + j, X, zoh);
-						if ((need >> j) & 1ull) {
-#pragma unroll 1
-							for (int s = 0; s < np; s++) {
-								const int sl = R.order.slot(s);
-								if (kidx[sl * T] == base_i + j) {
-#pragma unroll
-									for (int e = 0; e < NS; e++) snap[(size_t)(sl * NS + e) * T] = X[e];
-								}
+				const int wsteps = __reduce_max_sync(0xffffffffu, nsteps);
+				for (int j = 1; j <= wsteps; j++) {
+					if (j <= nsteps) {
+						const int i = base_i + j;
+						const double hmin = imp_advance<M, SATMODE, RB>(p, i, X, zoh);
+						const int slot = R.order.last(); // the evicted (largest) entry's slot takes the new point
+						if (hmin < kmax || (hmin == kmax && i < kidx[slot * T])) {
+							int pl = 0; // first place that (hmin, i) comes before: ties keep the earlier index first
+							while (pl < CAP - 1) {
+								const int sp = R.order.slot(pl);
+								const double kp = keys[sp * T];
+								if (hmin < kp || (hmin == kp && i < kidx[sp * T])) break;
+								pl++;
 							}
+							R.order.insert_at(pl, slot);
+							keys[slot * T] = hmin;
+							kidx[slot * T] = i;
+#pragma unroll
+							for (int e = 0; e < NS; e++) snap[(size_t)(slot * NS + e) * T] = X[e];
+							kmax = keys[R.order.last() * T];
 						}
 					}
 				}
