@@ -157,11 +157,9 @@ __device__ __forceinline__ void backup_cl_from_input(const SoftSat &sat, const d
 	constexpr int NX = M::NX, NU = M::NU;
 	double f[NX], g[NX * NU], uSat[NU], DuSat[NU];
 	double d[NX * NX], Dg[M::FUSED_GRADIENT ? 1 : NX * NU * NX];
-#pragma unroll
-	for (int k = 0; k < NU; k++) input_saturate_soft<SATMODE>(sat, k, lb[k], ub[k], u[k], uSat[k], DuSat[k]);
-	if (M::FUSED_GRADIENT) {
-		M::dynamics_with_gradient(x, uSat, f, g, d);
-	} else {
+	// control-affine models: f, g and their gradients do not depend on the input, so they are evaluated BEFORE the soft
+	// saturation - its rare bevel branch then comes after the model's long chains instead of fencing them off
+	if (!M::FUSED_GRADIENT) {
 		if (M::HAS_DYNAMICS_ALL) {
 			M::dynamics_all(x, f, g, d, Dg); // shares sub-expressions (trig of the same argument) between f, g and Df, Dg
 		} else {
@@ -169,6 +167,9 @@ __device__ __forceinline__ void backup_cl_from_input(const SoftSat &sat, const d
 			M::dynamics_gradients(x, d, Dg);
 		}
 	}
+#pragma unroll
+	for (int k = 0; k < NU; k++) input_saturate_soft<SATMODE>(sat, k, lb[k], ub[k], u[k], uSat[k], DuSat[k]);
+	if (M::FUSED_GRADIENT) M::dynamics_with_gradient(x, uSat, f, g, d);
 #pragma unroll
 	for (int i = 0; i < NX; i++)
 #pragma unroll

@@ -494,10 +494,13 @@ implicit_filter_kernel(const ImplicitParams p, const int64_t n, const double *__
 // strided), every thread re-uses its own area for all its tiles.  Used up to npBT = 20481; longer horizons run the kernel above.
 // Checkpoint spacing 2^ck_log steps, chosen per engine (imp_ck_log): 16 steps up to npBT 5121 (C3a: 313 checkpoints, 15 KB of
 // scratch per resident thread), 32 up to 10241, 64 up to 20481 - pass B costs a warp at most (2^ck_log - 1) steps per round.
+#ifndef IMP_CK_LOG_MIN
+#define IMP_CK_LOG_MIN 4
+#endif
 constexpr int IMP_MAX_CKPT = 320;
 __host__ __device__ inline int imp_ck_log(const int npBT)
 {
-	for (int l = 4; l <= 6; l++)
+	for (int l = IMP_CK_LOG_MIN; l <= 6; l++)
 		if ((((npBT - 1) >> l) + 1) <= IMP_MAX_CKPT) return l;
 	return -1; // too long for the checkpoint table: the shared-memory kernel runs
 }

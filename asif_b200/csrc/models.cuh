@@ -47,12 +47,16 @@ static __constant__ double kSinCosC[18] = {
 
 __device__ __forceinline__ void sincos_model(const double x, double *sp, double *cp)
 {
-	if (!(fabs(x) <= kSinCosC[16])) { // huge or NaN: the library path (never on a sane trajectory)
-		sincos(x, sp, cp);
-		return;
-	}
-	const int k = __double2int_rn(x * kSinCosC[0]);
-	const double kd = (double)k;
+	// The fast path is computed unconditionally and the huge / NaN case (never on a sane trajectory) is a fix-up branch
+	// BEHIND it: the polynomial chains then sit in the caller's basic block, where ptxas can interleave them with whatever
+	// else the step computes that does not depend on them (a guard branch in front would fence them off).
+	// k = rint(x 2/pi) by the add-and-subtract of 1.5 * 2^52: one FMA rounds the exact product to an integer in the last
+	// place, the low word of the sum IS k (two's complement), and kd comes back by one subtraction - two fixed-latency FP64
+	// instructions instead of DMUL + F2I + I2F, whose conversions went through the short-scoreboard path at the head of
+	// every step's dependency chain.
+	const double t = fma(x, kSinCosC[0], 6755399441055744.0);
+	const int k = __double2loint(t);
+	const double kd = t - 6755399441055744.0;
 	double r = fma(-kd, kSinCosC[1], x);
 	r = fma(-kd, kSinCosC[2], r);
 	r = fma(-kd, kSinCosC[3], r);
@@ -73,6 +77,9 @@ __device__ __forceinline__ void sincos_model(const double x, double *sp, double 
 	// quadrants 2,3 negate the sine, quadrants 1,2 the cosine: flip the sign bit with integer logic (one LOP3 each)
 	*sp = __hiloint2double(__double2hiint(a) ^ ((k & 2) << 30), __double2loint(a));
 	*cp = __hiloint2double(__double2hiint(b) ^ (((k + 1) & 2) << 30), __double2loint(b));
+	// |x| >= 1e5, infinite or NaN: the library path.  1e5 = 0x40F86A00'00000000, so the test is one integer compare of
+	// the high word (ALU) instead of a DSETP on the FP64 pipe.
+	if ((__double2hiint(x) & 0x7fffffff) >= 0x40F86A00) sincos(x, sp, cp);
 }
 
 // ------------------------------------------------------------------ DoubleIntegrator (explicit)

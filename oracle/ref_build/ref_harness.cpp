@@ -3,6 +3,15 @@
 #include "ref_common.h"
 #include "osqp.h"
 #include <vector>
+#ifdef ASIF_REF_REAL_OSQP /* a real OSQP's osqp.h does not declare the stand-in's hooks: osqp_real_glue.cpp defines them as no-ops */
+extern "C" {
+void osqp_shim_configure(double eps_abs_rel, int polish, int warm_start, int max_iter);
+void osqp_shim_configure_refine(int polish_refine_iter);
+int osqp_shim_last_status(int *iters);
+long long osqp_shim_inexact_count(void);
+void osqp_shim_stats(long long *n_solves, long long *n_iters, long long *n_polish_ok);
+}
+#endif
 
 extern "C" {
 

@@ -5,10 +5,10 @@
 # (scripts/ncu_summary.py) and gpurun_out/r02_<cfg>_source.csv (per-instruction page); KEEP_REP=1 keeps the report as well.
 mkdir -p gpurun_out
 for c in "$@"; do
-  python scripts/profile_cfg.py $c > gpurun_out/plain_$c.log 2>&1 || { echo "$c: plain run failed"; tail -3 gpurun_out/plain_$c.log; continue; }
+  python scripts/profile_cfg.py $c $NSTATES > gpurun_out/plain_$c.log 2>&1 || { echo "$c: plain run failed"; tail -3 gpurun_out/plain_$c.log; continue; }
   cat gpurun_out/plain_$c.log
   ncu --set full --clock-control none --import-source on -k regex:'filter_kernel|ckpt_kernel|deferred_kernel' -s 3 -c 1 -f -o gpurun_out/prof_$c \
-      python scripts/profile_cfg.py $c > gpurun_out/ncu_$c.log 2>&1; echo "$c ncu rc=$?"
+      python scripts/profile_cfg.py $c $NSTATES > gpurun_out/ncu_$c.log 2>&1; echo "$c ncu rc=$?"
   python scripts/ncu_summary.py gpurun_out/prof_$c.ncu-rep gpurun_out/r02_${c}_kernel > /dev/null 2>&1
   ncu -i gpurun_out/prof_$c.ncu-rep --page source --csv > gpurun_out/r02_${c}_source.csv 2>/dev/null
   [ -n "$KEEP_REP" ] || rm -f gpurun_out/prof_$c.ncu-rep
