@@ -111,6 +111,8 @@ int launch_explicit(asif_engine *e, int64_t n, const double *x, const double *ud
 	const unsigned blocks = (unsigned)((n + EXPL_THREADS - 1) / EXPL_THREADS);
 	if (diag)
 		explicit_filter_kernel<M, true><<<blocks, EXPL_THREADS, 0, st>>>(e->ex, n, x, ud, ua, relax, rc, diag, e->ctr);
+	else if (e->ex.npSSmax >= M::NPSS) // every safety function keeps its row: the instantiation without the rank computation
+		explicit_filter_kernel<M, false, false><<<blocks, EXPL_THREADS, 0, st>>>(e->ex, n, x, ud, ua, relax, rc, nullptr, e->ctr);
 	else
 		explicit_filter_kernel<M, false><<<blocks, EXPL_THREADS, 0, st>>>(e->ex, n, x, ud, ua, relax, rc, nullptr, e->ctr);
 	CUDA_TRY(cudaGetLastError());

@@ -52,7 +52,9 @@ struct RegRows {
 };
 
 // one state (index k) of the explicit filter; shared by the batch kernel and the latency server (latency_server.cuh)
-template <class M, bool WITH_DIAG>
+// SELECT = false is the common case npSSmax >= npSS (every safety function keeps its own row): the rank computation and the
+// per-row "is it among the selected" tests are compiled out; the launcher picks the instantiation from p.npSSmax.
+template <class M, bool WITH_DIAG, bool SELECT = true>
 __device__ __forceinline__ void explicit_filter_tile(const ExplicitParams &p, const int64_t n, const int64_t k, const double *__restrict__ x_in,
                                                      const double *__restrict__ u_des, double *__restrict__ u_act,
                                                      double *__restrict__ relax_out, int32_t *__restrict__ rc_out,
@@ -81,18 +83,53 @@ __device__ __forceinline__ void explicit_filter_tile(const ExplicitParams &p, co
 	M::dynamics(x, f, g);
 	// optional row selection: the npSSmax smallest h, ascending, ties keep the lower index (src/asif.cpp:250-268;
 	// std::sort leaves tie order unspecified).  pos[j] = rank of safety function j.
-	const int ncUse = p.npSSmax;
+	const int ncUse = SELECT ? p.npSSmax : NPSS;
 	int pos[NPSS];
 #pragma unroll
 	for (int j = 0; j < NPSS; j++) {
 		int r = 0;
+		if (SELECT) {
 #pragma unroll
-		for (int q = 0; q < NPSS; q++) r += (h[q] < h[j] || (h[q] == h[j] && q < j)) ? 1 : 0;
-		pos[j] = (ncUse < NPSS) ? r : j;
+			for (int q = 0; q < NPSS; q++) r += (h[q] < h[j] || (h[q] == h[j] && q < j)) ? 1 : 0;
+		}
+		pos[j] = (SELECT && ncUse < NPSS) ? r : j;
 	}
 	// Lfh = Dh f, Lgh = Dh g (src/asif.cpp:276-285), A = [Lgh | h], b = -Lfh (:295-303); safety function j lands in row
 	// pos[j] when it is among the selected ones
 	double lgv[NPSS][NU], rhsv[NPSS];
+	if constexpr (M::HAS_PATTERNS) {
+		// products with the literal 0 / +-1 entries of DhSS, f and g are not formed (x * 0 = +-0 and acc + +-0 = acc, 1 * x = x:
+		// the same values as the reference's full sums, up to the sign of an exact zero); what remains is in the reference's order
+#pragma unroll
+		for (int j = 0; j < NPSS; j++) {
+			bool have = false;
+			double lf = 0.0;
+#pragma unroll
+			for (int m = 0; m < NX; m++) {
+				const int pt = M::dhs_pat(j + m * NPSS);
+				if (pt == PZ || M::f_pat(m) == PZ) continue;
+				const double t = (pt == P1) ? f[m] : ((pt == PM1) ? -f[m] : Dh[j + m * NPSS] * f[m]);
+				lf = have ? lf + t : t;
+				have = true;
+			}
+			rhsv[j] = -lf;
+#pragma unroll
+			for (int i = 0; i < NU; i++) {
+				bool hv = false;
+				double lg = 0.0;
+#pragma unroll
+				for (int m = 0; m < NX; m++) {
+					const int pt = M::dhs_pat(j + m * NPSS), pg = M::g_pat(m + i * NX);
+					if (pt == PZ || pg == PZ) continue;
+					const double d = (pt == P1) ? 1.0 : ((pt == PM1) ? -1.0 : Dh[j + m * NPSS]);
+					const double t = (pg == P1) ? d : ((pt == P1) ? g[m + i * NX] : ((pt == PM1) ? -g[m + i * NX] : d * g[m + i * NX]));
+					lg = hv ? lg + t : t;
+					hv = true;
+				}
+				lgv[j][i] = lg;
+			}
+		}
+	} else {
 #pragma unroll
 	for (int j = 0; j < NPSS; j++) {
 		double lf = Dh[j] * f[0];
@@ -106,6 +143,7 @@ __device__ __forceinline__ void explicit_filter_tile(const ExplicitParams &p, co
 			for (int m = 1; m < NX; m++) lg = lg + Dh[j + m * NPSS] * g[m + i * NX];
 			lgv[j][i] = lg;
 		}
+	}
 	}
 	if (p.lfh != nullptr) { // use_custom_ineq_: row pos[j] takes the caller's values (src/asif.cpp:287-292)
 #pragma unroll
@@ -162,12 +200,12 @@ __device__ __forceinline__ void explicit_filter_tile(const ExplicitParams &p, co
 		feasible = feasible && (rlo * ahi >= rhi * alo);
 		// unconstrained minimiser of H00 u^2 + c0 u; with the default cost (H00 = 1, c0 = -2 uDes) this is uDes bit for bit
 		double u = -(p.gi[0] * c[0]);
-		if (u * alo < rlo) {
-			u = rlo / alo;
-			iters = row_lo ? 1 : 0;
-		} else if (u * ahi < rhi) {
-			u = rhi / ahi;
-			iters = row_hi ? 1 : 0;
+		// (one division site for both bounds: the two legs are the same instruction sequence on different operands, and a warp
+		// usually holds lanes of both kinds)
+		const bool below = u * alo < rlo, above = !below && (u * ahi < rhi);
+		if (below || above) {
+			u = (below ? rlo : rhi) / (below ? alo : ahi);
+			iters = (below ? row_lo : row_hi) ? 1 : 0;
 		}
 		v[0] = u;
 		v[NU] = p.relaxLb;
@@ -216,22 +254,22 @@ __device__ __forceinline__ void explicit_filter_tile(const ExplicitParams &p, co
 		}
 	}
 	if (qp_iter_sum) {
-		unsigned int it = live ? (unsigned int)iters : 0u;
-#pragma unroll
-		for (int o = 16; o > 0; o >>= 1) it += __shfl_xor_sync(0xffffffffu, it, o);
+		const unsigned int it = __reduce_add_sync(0xffffffffu, live ? (unsigned int)iters : 0u); // one REDUX instead of a shuffle tree
 		if ((threadIdx.x & 31) == 0 && it) qp_rows_add(qp_iter_sum, (unsigned long long)it);
 	}
 }
 
-template <class M, bool WITH_DIAG>
+template <class M, bool WITH_DIAG, bool SELECT = true>
 __global__ void __launch_bounds__(EXPL_THREADS)
 explicit_filter_kernel(const ExplicitParams p, const int64_t n, const double *__restrict__ x_in,
                        const double *__restrict__ u_des, double *__restrict__ u_act, double *__restrict__ relax_out,
                        int32_t *__restrict__ rc_out, double *__restrict__ diag,
                        unsigned long long *__restrict__ qp_iter_sum)
 {
-	explicit_filter_tile<M, WITH_DIAG>(p, n, (int64_t)blockIdx.x * EXPL_THREADS + threadIdx.x, x_in, u_des, u_act, relax_out, rc_out, diag,
-	                                   qp_iter_sum);
+	// (An L2 prefetch of the input lines of the CTA 888 / 1776 / 3552 blocks ahead was measured and is not in: 1e7 states
+	// 113 -> 109 us, 1e8 states 0.956 -> 0.91-1.03 ms, inside the run-to-run spread; gpurun_out/r02_c1_prefetch_ab.log.)
+	explicit_filter_tile<M, WITH_DIAG, SELECT>(p, n, (int64_t)blockIdx.x * EXPL_THREADS + threadIdx.x, x_in, u_des, u_act, relax_out, rc_out,
+	                                           diag, qp_iter_sum);
 }
 
 } // namespace asifb

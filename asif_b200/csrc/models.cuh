@@ -86,6 +86,24 @@ __device__ __forceinline__ void sincos_model(const double x, double *sp, double 
 // examples/DoubleIntegrator.cpp:12-61
 struct DoubleIntegratorExplicit {
 	static constexpr int NX = 2, NU = 1, NPSS = 4;
+	// structural patterns (filter_common.cuh) read by explicit_kernel.cuh: DhSS column-major {-1, 1, 0, 0 | *, *, 1, -1}
+	// (entries 4 and 5 are -x1 or 0 depending on the sign of x1: general), f = {x1, 0}, g = {0, 1}
+	static constexpr bool HAS_PATTERNS = true;
+	__host__ __device__ static constexpr int dhs_pat(int i)
+	{
+		constexpr int t[8] = {3, 1, 0, 0, 2, 2, 1, 3};
+		return t[i];
+	}
+	__host__ __device__ static constexpr int f_pat(int i)
+	{
+		constexpr int t[2] = {2, 0};
+		return t[i];
+	}
+	__host__ __device__ static constexpr int g_pat(int i)
+	{
+		constexpr int t[2] = {0, 1};
+		return t[i];
+	}
 	__device__ static void safety_set(const double *x, double *h, double *Dh)
 	{
 		if (x[1] > 0) {

@@ -199,8 +199,11 @@ __device__ __forceinline__ void qp_scan_rows(const Rows &rows, const double (&)[
 // Rare (a few states in 1e4), so it is kept out of line and works on local arrays.
 constexpr double QP_POLISH_SIN = 1e-2; // polish when some R[a][a] (sine of the angle to the earlier active rows) is below this
 
+#ifndef QP_POLISH_CALL
+#define QP_POLISH_CALL __noinline__
+#endif
 template <int NV>
-static __device__ __noinline__ bool qp_vertex_solve(double (&M)[NV][NV + 1], double (&out)[NV])
+static __device__ QP_POLISH_CALL bool qp_vertex_solve(double (&M)[NV][NV + 1], double (&out)[NV])
 {
 	for (int c = 0; c < NV; c++) {
 		int piv = c;
@@ -234,7 +237,7 @@ static __device__ __noinline__ bool qp_vertex_solve(double (&M)[NV][NV + 1], dou
 
 // N = the active rows [normal | rhs]; v is replaced by the direct solve when that satisfies the rows at least as well
 template <int NV>
-static __device__ __noinline__ void qp_vertex_polish_rows(const double (&N)[NV][NV + 1], double (&v)[NV])
+static __device__ QP_POLISH_CALL void qp_vertex_polish_rows(const double (&N)[NV][NV + 1], double (&v)[NV])
 {
 	double M[NV][NV + 1], vp[NV];
 	for (int a = 0; a < NV; a++)

@@ -111,7 +111,10 @@ __device__ __forceinline__ void qp_scan_rows(const RealizableRows &rows, const d
 
 // diag: [nCrit, critFacet[max_crit] (-1 absent), barrierFacet[npSSmax], per slot LgLo, LgHi, LfLo, LfHi, per barrier row Lgh, b]
 template <bool WITH_DIAG>
-__global__ void __launch_bounds__(RZ_THREADS)
+#ifndef RZ_MIN_BLOCKS
+#define RZ_MIN_BLOCKS 1 // 238 registers, 8 warps/SM; forcing 3 / 4 / 5 CTAs spills the facet pass: 0.853 -> 0.884 / 1.09 / 1.65 ms per 1e6 C4 states
+#endif
+__global__ void __launch_bounds__(RZ_THREADS, RZ_MIN_BLOCKS)
 realizable_ip_filter_kernel(const RealizableParams p, const int64_t n, const double *__restrict__ x_in,
                             const double *__restrict__ u_des, double *__restrict__ u_act, double *__restrict__ relax_out,
                             int32_t *__restrict__ rc_out, double *__restrict__ diag, unsigned long long *__restrict__ qp_iter_sum)

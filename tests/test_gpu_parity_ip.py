@@ -197,3 +197,33 @@ def test_learning_refused_elsewhere(ab):
     eng = ab.Engine(ab.FILTER_IMPLICIT_TB, ab.MODEL_DOUBLE_INTEGRATOR_TB, **cf.tb_engine_kwargs(cf.C2_TB_OPTS))
     with pytest.raises(ab.AsifError):
         eng.set_learning(cf.LEARN_DIMS, cf.learning_blob())
+
+
+def test_tied_min_h_keys(ab, oracle):
+    """Ties among the min-h keys: a pendulum parked at the upright equilibrium has the SAME state at every
+    one of its npBT trajectory points, so every key ties.  The reference orders them with std::sort, which leaves the
+    order of equal keys unspecified; the CUDA kernels keep the earliest indices (documented rule).  Whatever indices are
+    picked, the rows - and with them the QP - are the same, which is what is compared against the oracle here; a second
+    batch ties only part of the horizon (a trajectory that reaches the equilibrium exactly is not constructible in floating
+    point, so the partial tie is made with a mirrored pair: x and -x give keys that tie pairwise across the two states,
+    not within one - the check there is the symmetry u(-x, -uDes) = -u(x, uDes))."""
+    for opts in (cf.C3A_SHORT_OPTS, cf.C3A_OPTS):
+        n = 64
+        x = np.zeros((n, 2))
+        ud = np.linspace(-1.0, 1.0, n).reshape(n, 1)
+        eng = ab.Engine(ab.FILTER_IMPLICIT, ab.MODEL_INVERTED_PENDULUM, **cf.implicit_engine_kwargs(opts))
+        u, relax, rc, diag = eng.filter_batch(x, ud, want_diag=True)
+        u0, relax0, rc0, diag0 = oracle.filter_batch(3, x, ud, opts, want_diag=True)
+        assert np.array_equal(diag[:, 2:12], np.tile(np.arange(10.0), (n, 1)))  # the tie rule: earliest indices, ascending
+        cf.assert_parity("tied keys", (u, relax, rc), (u0, relax0, rc0))
+        # the rows do not depend on which of the tied points were taken
+        assert np.abs(diag[:, 12:] - diag0[:, 12:]).max() <= 1e-12
+        u2, relax2, rc2 = eng.filter_batch(x, ud)  # the non-diagnostic kernel
+        assert np.array_equal(u, u2) and np.array_equal(relax, relax2) and np.array_equal(rc, rc2)
+        # odd symmetry of the pendulum, its backup controller and the (symmetric) sets
+        xs, uds = cf.c3a_inputs(2000, seed=cf.SEED + 97)
+        ua, ra, ca = eng.filter_batch(xs, uds)
+        ub, rb, cb = eng.filter_batch(-xs, -uds)
+        same = ca == cb
+        assert same.mean() > 0.999
+        assert np.abs(ua[same] + ub[same]).max() <= 1e-9 and np.abs(ra[same] - rb[same]).max() <= 1e-6
