@@ -190,6 +190,17 @@ __device__ __forceinline__ void qp_scan_rows(const Rows &rows, const double (&)[
 	rows.scan(fn, fb);
 }
 
+// Row functors whose scans are long and whose single rows are cheap to fetch again (the 100 half-planes of the robust
+// filter) opt into the index-only scan: declare  static constexpr bool SCAN_INDEX_ONLY = true;
+template <class Rows, class = void>
+struct qp_scan_index_only {
+	static constexpr bool value = false;
+};
+template <class Rows>
+struct qp_scan_index_only<Rows, decltype((void)Rows::SCAN_INDEX_ONLY)> {
+	static constexpr bool value = Rows::SCAN_INDEX_ONLY;
+};
+
 // Vertex polish.  At a vertex (NV active rows) the minimiser is fixed by the rows alone: N v = rhs.  The dual method reaches
 // it by steps along directions orthogonalised in hat space, whose error is eps / sin(angle between active rows) times the
 // length of the step - for a safety row with h ~ 1e-6 against the orthogonality row (3.7e-7 rad apart in hat space, the
@@ -299,6 +310,57 @@ __device__ __forceinline__ int qp_gi_solve(const Metric &mt, const double (&c)[N
 		double np_[NV];
 #pragma unroll
 		for (int i = 0; i < NV; i++) np_[i] = 0.0;
+		bool scanned = false;
+		if (qp_scan_index_only<Rows>::value) {
+			// Index-only scan.  In the scan below the "a more violated row" body runs ~ln(rows) times per lane, each time for
+			// that lane alone (55-60 times per warp and scan over 100 half-planes: a quarter of the scan's issue slots at 1-2
+			// lanes).  Here the loop only tracks the smallest residual and its row number with selects; the tolerance and
+			// active-set tests are applied once, to the winner.  If the winner passes them it is exactly the row the scan
+			// below would pick (the smallest residual among the rows that pass, first index on ties); if its residual is not
+			// below -tol no row's is and the solve is finished; only a winner that is violated AND fails a test (active, or
+			// inside its own scaled tolerance - a knife edge) sends the lane through the full scan.
+			int pr = -1;
+			double sr = 0.0;
+			qp_scan_rows(
+			    rows, w.v,
+			    [&](const int j, const double(&n)[NV], const double rhs) {
+				    double s = -rhs;
+#pragma unroll
+				    for (int i = 0; i < NV; i++) s += n[i] * w.v[i];
+				    const bool better = s < sr;
+				    sr = better ? s : sr;
+				    pr = better ? j : pr;
+			    },
+			    [&](const int j, const int var, const bool upper, const double bnd) {
+				    double vv = 0.0;
+#pragma unroll
+				    for (int i = 0; i < NV; i++) vv = (i == var) ? w.v[i] : vv;
+				    const double s = (upper ? -vv : vv) - bnd;
+				    const bool better = s < sr;
+				    sr = better ? s : sr;
+				    pr = better ? j : pr;
+			    });
+			scanned = true;
+			if (pr >= 0 && sr < -QP_FEAS_TOL) {
+				double n[NV], rhs;
+				rows.get(pr, n, rhs);
+				double nmax = 1.0;
+#pragma unroll
+				for (int i = 0; i < NV; i++) nmax = (fabs(n[i]) > nmax) ? fabs(n[i]) : nmax;
+				bool is_act = false;
+#pragma unroll
+				for (int a = 0; a < NV; a++) is_act |= (a < w.q) && (w.act[a] == pr);
+				if (!is_act && sr < -QP_FEAS_TOL * nmax) {
+					p = pr;
+					sp = sr;
+#pragma unroll
+					for (int i = 0; i < NV; i++) np_[i] = n[i];
+				} else {
+					scanned = false; // knife edge: the full scan decides
+				}
+			}
+		}
+		if (!scanned)
 		qp_scan_rows(
 		    rows, w.v,
 		    [&](const int j, const double(&n)[NV], const double rhs) {

@@ -34,6 +34,10 @@ struct RobustParams {
 
 struct RobustRows {
 	static constexpr int NV = 2;
+#ifndef ROB_SCAN_INDEX_ONLY
+#define ROB_SCAN_INDEX_ONLY 1
+#endif
+	static constexpr bool SCAN_INDEX_ONLY = ROB_SCAN_INDEX_ONLY != 0; // qp_gi.cuh: 100 half-planes per scan, rows cheap to fetch again
 	const double *tab; // shared memory, [K][4] = a0, a1, Lg- / Dh-independent part, Lg+ (the last two staged per CTA)
 	int K;
 	double x0, x1, f0, f1;

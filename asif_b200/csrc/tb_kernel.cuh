@@ -53,6 +53,10 @@ __host__ __device__ constexpr int tb_smem_doubles_per_thread()
 // Rows of the TB QP (src/asif_implicit_tb.cpp:554-674), computed on demand.
 template <class M, int NPBTSS>
 struct TbRows {
+#ifndef ASIF_TB_SCAN_INDEX_ONLY
+#define ASIF_TB_SCAN_INDEX_ONLY 0 // qp_gi.cuh index-only scan: measured on C2 / C5, see DESIGN.md
+#endif
+	static constexpr bool SCAN_INDEX_ONLY = ASIF_TB_SCAN_INDEX_ONLY != 0;
 	static constexpr int NX = M::NX, NU = M::NU, NPSS = M::NPSS, NS = NX + NX * NX;
 	static constexpr int CAP = np_capacity(NPBTSS), NV = NU + 1;
 	__device__ __forceinline__ int count_np() const { return np_runtime(NPBTSS) ? np : NPBTSS; }

@@ -565,7 +565,7 @@ def main():
     line["roofline"]["credited_vs_executed"] = (
         "credited %.0f flop/state (SURVEY 8d: 88 per Euler step + assembly + QP); the kernel executes ~33 FP64 instructions per "
         "Euler step with FMA contraction off and structural zeros skipped, i.e. credited/executed ~ 2.1: the hardware-side view "
-        "is ncu's FP64-pipe utilisation in profiles/ (r01: 70 %% busy, 72 %% issue slots)" % fl)
+        "is ncu's FP64-pipe utilisation in profiles/r02_c2_1e7_summary.md (68.4 %% busy, 70.7 %% issue slots, 23.9 of 32 lanes)" % fl)
     if traffic is not None:
         line["roofline"]["traffic_source"] = "profiles/traffic.json (one ncu --set full capture; see its 'source' field for the build)"
     if extra:

@@ -244,6 +244,12 @@ def main():
     inp["C5"] = (6, cf.SEGWAY_TB_OPTS, *cf.c5_inputs(sz(100_000)))
     inp["RB-IP"] = (7, cf.RB_IP_OPTS, *cf.c3a_inputs(sz(100_000), seed=cf.SEED + 91))
     inp["RB-DI"] = (8, cf.RB_DI_OPTS, *cf.c2_inputs(sz(100_000), seed=cf.SEED + 92))
+    # ASIF_PARITY_ONLY=C3b,C1 restricts the run to those configs (a kernel that changed after the full report); "cost" and
+    # "rollout" name the two extra legs
+    only = {t for t in os.environ.get("ASIF_PARITY_ONLY", "").split(",") if t}
+    if only:
+        inp = {k: v for k, v in inp.items() if k in only}
+    do_cost = do_roll = (not only) or bool(only & {"cost", "rollout"})  # the two extra legs run together
     xc, udc = cf.c2_inputs(sz(100_000), seed=cf.SEED + 93)
     Hc, cc = cf.custom_cost(udc, 2, seed=2)
     n_roll, steps_roll = sz(1000), 1000 if SCALE >= 1 else 100
@@ -263,12 +269,14 @@ def main():
                 t0 = time.time()
                 ref[k] = ref_parallel(pool, "filter", cfg, opts, x[:m], ud[:m])
                 sys.stderr.write("reference build %s: %d states in %.1f s\n" % (k, m, time.time() - t0))
-            ref["cost"] = ref_parallel(pool, "cost", 2, cf.C2_TB_OPTS, xc, cc, Hc)
+            if do_cost:
+                ref["cost"] = ref_parallel(pool, "cost", 2, cf.C2_TB_OPTS, xc, cc, Hc)
             t0 = time.time()
-            ref["rollout"] = ref_parallel(pool, "rollout", 6, cf.SEGWAY_TB_OPTS, xr0, udr, (steps_roll, 1e-3))
-            # yardstick: the reference build against ITSELF from initial states moved by one part in 1e13
-            ref["rollout_perturbed"] = ref_parallel(pool, "rollout", 6, cf.SEGWAY_TB_OPTS, xr0 * (1.0 + 1e-13), udr, (steps_roll, 1e-3))
-            sys.stderr.write("reference build rollout: %d agents x %d steps in %.1f s\n" % (n_roll, steps_roll, time.time() - t0))
+            if do_roll:
+                ref["rollout"] = ref_parallel(pool, "rollout", 6, cf.SEGWAY_TB_OPTS, xr0, udr, (steps_roll, 1e-3))
+                # yardstick: the reference build against ITSELF from initial states moved by one part in 1e13
+                ref["rollout_perturbed"] = ref_parallel(pool, "rollout", 6, cf.SEGWAY_TB_OPTS, xr0 * (1.0 + 1e-13), udr, (steps_roll, 1e-3))
+                sys.stderr.write("reference build rollout: %d agents x %d steps in %.1f s\n" % (n_roll, steps_roll, time.time() - t0))
     else:
         sys.stderr.write("oracle/_ref/libasif_ref.so missing: vs_reference legs skipped\n")
 
@@ -350,6 +358,9 @@ def main():
                     relax_cols=rcols, note="reference build = unmodified sources + OSQP-algorithm stand-in (eps 1e-8, polish, cold start)")
         eng.close()
 
+    if not do_cost and not do_roll:
+        sys.stderr.write("parity report: %.0f s\n" % (time.time() - t_start))
+        return
     # ---- the filter(x, H, c, ...) overloads on the headline config: fresh engine, first call -------------------------
     eng = ab.Engine(ab.FILTER_IMPLICIT_TB, ab.MODEL_DOUBLE_INTEGRATOR_TB, **cf.tb_engine_kwargs(cf.C2_TB_OPTS))
     got = eng.filter_batch_cost(xc, cc, Hc, want_diag=True)
