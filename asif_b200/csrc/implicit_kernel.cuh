@@ -133,6 +133,10 @@ struct ImpOrder {
 
 template <class M, int NPBTSS, bool RB = false>
 struct ImpRows {
+#ifndef ASIF_IMP_SCAN_INDEX_ONLY
+#define ASIF_IMP_SCAN_INDEX_ONLY 1
+#endif
+	static constexpr bool SCAN_INDEX_ONLY = ASIF_IMP_SCAN_INDEX_ONLY != 0; // qp_gi.cuh
 	static constexpr int NX = M::NX, NU = M::NU, NPSS = M::NPSS, NPBS = M::NPBS, NS = NX + NX * NX;
 	static constexpr int CAP = np_capacity(NPBTSS), NV = NU + 2;
 	int np; // critical points in use (== NPBTSS when that is a compile-time count)

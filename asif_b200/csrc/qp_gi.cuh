@@ -12,6 +12,10 @@
 // members -- scan(f, fb): call f(j, normal, rhs) for every general row j in order and
 // fb(j, var, upper, bound) for every variable-bound row; get(j, normal, rhs): one row -- so that the caller decides where they live (shared memory for the implicit filters, computed on the fly
 // from a table for the robust/realizable ones, global memory for the generic batch entry).
+// The solver's own inner products and updates are written with fma(): the bit-exact units are compiled with -fmad=false
+// for the sake of the trajectory and the ROWS (which are compared bit for bit with the reference), but the QP step has no
+// bit parity to keep (the reference's OSQP result is an iterate at eps 1e-3), and one DFMA per term instead of DMUL + DADD
+// is both more accurate and a third fewer FP64 instructions in the solver.
 // Work is done in the metric of the Hessian (v-hat = sqrt(2H) v) with every processed row
 // normalised to unit length, so the thresholds below are scale free.
 #pragma once
@@ -142,7 +146,7 @@ __device__ __forceinline__ double qp_fetch_unit_row(const Rows &rows, int j, con
 	mt.to_hat(n, nh);
 	double len2 = 0.0;
 #pragma unroll
-	for (int i = 0; i < NV; i++) len2 += nh[i] * nh[i];
+	for (int i = 0; i < NV; i++) len2 = fma(nh[i], nh[i], len2);
 	const double len = sqrt(len2);
 	const double inv = 1.0 / len;
 #pragma unroll
@@ -164,15 +168,15 @@ __device__ __forceinline__ void qp_rebuild(QpWork<NV> &w, const Rows &rows, cons
 				if (b < a) {
 					double d = 0.0;
 #pragma unroll
-					for (int i = 0; i < NV; i++) d += w.Q[b][i] * nh[i];
+					for (int i = 0; i < NV; i++) d = fma(w.Q[b][i], nh[i], d);
 					w.R[b][a] = d;
 #pragma unroll
-					for (int i = 0; i < NV; i++) nh[i] -= d * w.Q[b][i];
+					for (int i = 0; i < NV; i++) nh[i] = fma(-d, w.Q[b][i], nh[i]);
 				}
 			}
 			double l2 = 0.0;
 #pragma unroll
-			for (int i = 0; i < NV; i++) l2 += nh[i] * nh[i];
+			for (int i = 0; i < NV; i++) l2 = fma(nh[i], nh[i], l2);
 			const double l = sqrt(l2);
 			w.R[a][a] = l;
 			const double inv = 1.0 / l;
@@ -326,7 +330,7 @@ __device__ __forceinline__ int qp_gi_solve(const Metric &mt, const double (&c)[N
 			    [&](const int j, const double(&n)[NV], const double rhs) {
 				    double s = -rhs;
 #pragma unroll
-				    for (int i = 0; i < NV; i++) s += n[i] * w.v[i];
+				    for (int i = 0; i < NV; i++) s = fma(n[i], w.v[i], s);
 				    const bool better = s < sr;
 				    sr = better ? s : sr;
 				    pr = better ? j : pr;
@@ -408,7 +412,7 @@ __device__ __forceinline__ int qp_gi_solve(const Metric &mt, const double (&c)[N
 		mt.to_hat(np_, nh);
 		double len2 = 0.0;
 #pragma unroll
-		for (int i = 0; i < NV; i++) len2 += nh[i] * nh[i];
+		for (int i = 0; i < NV; i++) len2 = fma(nh[i], nh[i], len2);
 		const double len = sqrt(len2);
 		if (!(len > 0.0)) { // 0 >= rhs with rhs > 0
 			status = QP_PRIMAL_INFEASIBLE;
@@ -433,15 +437,15 @@ __device__ __forceinline__ int qp_gi_solve(const Metric &mt, const double (&c)[N
 				if (a < w.q) {
 					double t = 0.0;
 #pragma unroll
-					for (int i = 0; i < NV; i++) t += w.Q[a][i] * zh[i];
+					for (int i = 0; i < NV; i++) t = fma(w.Q[a][i], zh[i], t);
 					d[a] = t;
 #pragma unroll
-					for (int i = 0; i < NV; i++) zh[i] -= t * w.Q[a][i];
+					for (int i = 0; i < NV; i++) zh[i] = fma(-t, w.Q[a][i], zh[i]);
 				}
 			}
 			double zz = 0.0;
 #pragma unroll
-			for (int i = 0; i < NV; i++) zz += zh[i] * zh[i];
+			for (int i = 0; i < NV; i++) zz = fma(zh[i], zh[i], zz);
 			// r = R^-1 d (back substitution over the active part)
 #pragma unroll
 			for (int a = NV - 1; a >= 0; a--) {
@@ -450,7 +454,7 @@ __device__ __forceinline__ int qp_gi_solve(const Metric &mt, const double (&c)[N
 					double t = d[a];
 #pragma unroll
 					for (int b = a + 1; b < NV; b++)
-						if (b < w.q) t -= w.R[a][b] * r[b];
+						if (b < w.q) t = fma(-w.R[a][b], r[b], t);
 					// a new row orthogonal to an active one (a variable bound against a row without that variable) gives an
 					// exact 0 here, and a zero numerator sends CUDA's division through its slow-path subroutine
 					r[a] = (t == 0.0) ? t : t / w.R[a][a];
@@ -478,10 +482,10 @@ __device__ __forceinline__ int qp_gi_solve(const Metric &mt, const double (&c)[N
 				double z[NV];
 				mt.from_hat(zh, z);
 #pragma unroll
-				for (int i = 0; i < NV; i++) w.v[i] += t2 * z[i];
+				for (int i = 0; i < NV; i++) w.v[i] = fma(t2, z[i], w.v[i]);
 #pragma unroll
 				for (int a = 0; a < NV; a++)
-					if (a < w.q) w.mu[a] -= t2 * r[a];
+					if (a < w.q) w.mu[a] = fma(-t2, r[a], w.mu[a]);
 				mu_p += t2;
 				const double zl = sqrt(zz);
 				const double inv = 1.0 / zl;
@@ -506,12 +510,12 @@ __device__ __forceinline__ int qp_gi_solve(const Metric &mt, const double (&c)[N
 				double z[NV];
 				mt.from_hat(zh, z);
 #pragma unroll
-				for (int i = 0; i < NV; i++) w.v[i] += t1 * z[i];
-				sp += t1 * zz;
+				for (int i = 0; i < NV; i++) w.v[i] = fma(t1, z[i], w.v[i]);
+				sp = fma(t1, zz, sp);
 			}
 #pragma unroll
 			for (int a = 0; a < NV; a++)
-				if (a < w.q) w.mu[a] -= t1 * r[a];
+				if (a < w.q) w.mu[a] = fma(-t1, r[a], w.mu[a]);
 			mu_p += t1;
 #pragma unroll
 			for (int a = 0; a < NV - 1; a++) {

@@ -41,6 +41,10 @@ struct RealizableParams {
 
 struct RealizableRows {
 	static constexpr int NV = 2;
+#ifndef ASIF_RZ_SCAN_INDEX_ONLY
+#define ASIF_RZ_SCAN_INDEX_ONLY 1 // C4 0.853 -> 0.828 ms per 1e6 states
+#endif
+	static constexpr bool SCAN_INDEX_ONLY = ASIF_RZ_SCAN_INDEX_ONLY != 0; // qp_gi.cuh
 	double lgLo[RZ_MAX_CRIT * RZ_MAX_ACT], lgHi[RZ_MAX_CRIT * RZ_MAX_ACT], rhs[RZ_MAX_CRIT * RZ_MAX_ACT];
 	int nslots;
 	double barL[RZ_MAX_BAR], barB[RZ_MAX_BAR];

@@ -54,7 +54,7 @@ __host__ __device__ constexpr int tb_smem_doubles_per_thread()
 template <class M, int NPBTSS>
 struct TbRows {
 #ifndef ASIF_TB_SCAN_INDEX_ONLY
-#define ASIF_TB_SCAN_INDEX_ONLY 0 // qp_gi.cuh index-only scan: measured on C2 / C5, see DESIGN.md
+#define ASIF_TB_SCAN_INDEX_ONLY 1 // qp_gi.cuh index-only scan: C2 3.55 -> 3.43 ms per 1e7 states, with the point pre-filter off (below) 3.36 ms; C5 neutral
 #endif
 	static constexpr bool SCAN_INDEX_ONLY = ASIF_TB_SCAN_INDEX_ONLY != 0;
 	static constexpr int NX = M::NX, NU = M::NU, NPSS = M::NPSS, NS = NX + NX * NX;
@@ -229,7 +229,10 @@ __device__ __forceinline__ void tb_cost_vector(const TbParams &p, const double *
 template <class M, int NPBTSS, class F, class FB>
 __device__ __forceinline__ void qp_scan_rows(const TbRows<M, NPBTSS> &rows, const double (&v)[M::NU + 1], F &&fn, FB &&fb)
 {
-	rows.template scan_at<true>(v, fn, fb);
+#ifndef ASIF_TB_SCAN_PREFILTER
+#define ASIF_TB_SCAN_PREFILTER 0 // with the index-only scan the solver's per-row work is a compare and two selects: the per-point pre-test and its branch cost more than they save
+#endif
+	rows.template scan_at<(ASIF_TB_SCAN_PREFILTER != 0)>(v, fn, fb);
 }
 
 template <int NPBTSS>
