@@ -147,11 +147,10 @@ __device__ __forceinline__ double qp_fetch_unit_row(const Rows &rows, int j, con
 	double len2 = 0.0;
 #pragma unroll
 	for (int i = 0; i < NV; i++) len2 = fma(nh[i], nh[i], len2);
-	const double len = sqrt(len2);
-	const double inv = 1.0 / len;
+	const double inv = rsqrt(len2); // one rsqrt (18 instructions, no slow path) instead of sqrt + division (45 + two subroutines)
 #pragma unroll
 	for (int i = 0; i < NV; i++) nh[i] *= inv;
-	return len;
+	return len2 * inv;
 }
 
 // rebuild Q, R from the current active set (modified Gram-Schmidt in hat space)
@@ -177,9 +176,8 @@ __device__ __forceinline__ void qp_rebuild(QpWork<NV> &w, const Rows &rows, cons
 			double l2 = 0.0;
 #pragma unroll
 			for (int i = 0; i < NV; i++) l2 = fma(nh[i], nh[i], l2);
-			const double l = sqrt(l2);
-			w.R[a][a] = l;
-			const double inv = 1.0 / l;
+			const double inv = rsqrt(l2);
+			w.R[a][a] = l2 * inv;
 #pragma unroll
 			for (int i = 0; i < NV; i++) w.Q[a][i] = nh[i] * inv;
 		}
@@ -413,17 +411,16 @@ __device__ __forceinline__ int qp_gi_solve(const Metric &mt, const double (&c)[N
 		double len2 = 0.0;
 #pragma unroll
 		for (int i = 0; i < NV; i++) len2 = fma(nh[i], nh[i], len2);
-		const double len = sqrt(len2);
-		if (!(len > 0.0)) { // 0 >= rhs with rhs > 0
+		if (!(len2 > 0.0)) { // 0 >= rhs with rhs > 0
 			status = QP_PRIMAL_INFEASIBLE;
 			break;
 		}
 		{
-			const double inv = 1.0 / len;
+			const double inv = rsqrt(len2);
 #pragma unroll
 			for (int i = 0; i < NV; i++) nh[i] *= inv;
+			sp = sp * inv;
 		}
-		sp = sp / len;
 		double mu_p = 0.0;
 		bool failed = false;
 		// ---- primal/dual steps until row p becomes active (at most q drops)
@@ -487,8 +484,8 @@ __device__ __forceinline__ int qp_gi_solve(const Metric &mt, const double (&c)[N
 				for (int a = 0; a < NV; a++)
 					if (a < w.q) w.mu[a] = fma(-t2, r[a], w.mu[a]);
 				mu_p += t2;
-				const double zl = sqrt(zz);
-				const double inv = 1.0 / zl;
+				const double inv = rsqrt(zz);
+				const double zl = zz * inv;
 #pragma unroll
 				for (int a = 0; a < NV; a++) {
 					if (a == w.q) {

