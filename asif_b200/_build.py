@@ -17,7 +17,7 @@ NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a",
 # Translation units and their contraction setting.  kernels_contract.cu holds the kernels of models that call
 # sin/cos/tanh per step (bit identity with glibc is unattainable there; see the note in the file).
 UNITS = [("engine.cu", "-fmad=false"), ("closed_loop.cu", "-fmad=false"), ("kernels_contract.cu", "-fmad=true"),
-         ("group.cu", "-fmad=false")]  # group.cu: host code only (multi-device entry)
+         ("group.cu", "-fmad=false"), ("qp_admm.cu", "-fmad=true")]  # group.cu: host code only (multi-device entry)
 
 
 def sources():

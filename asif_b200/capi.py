@@ -114,6 +114,8 @@ def load_library():
         [C.POINTER(C.c_int64), C.c_void_p, C.c_int32, C.c_void_p]
     L.asif_qp_solve_batch.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int32] + [C.c_void_p] * 9 + \
                                      [C.c_int32, C.c_int32, C.c_void_p]
+    L.asif_qp_configure.argtypes = [C.c_double, C.c_int32, C.c_int32, C.c_int32]
+    L.asif_qp_last_info.argtypes = [_ip]
     L.asif_measure_fp64_peak.argtypes = [C.c_int32, _dp, _dp]
     L.asif_engine_group_create.argtypes = [C.POINTER(EngineConfig), _ip, C.c_int32, C.POINTER(C.c_void_p)]
     L.asif_engine_group_destroy.argtypes = [C.c_void_p]
@@ -501,3 +503,15 @@ def qp_solve_batch(H, c, A, b, lb, ub, be=None, diagonal_cost=True, device=0):
                                               Acm.ctypes.data, b.ctypes.data, lb.ctypes.data, ub.ctypes.data, bep,
                                               sol.ctypes.data, status.ctypes.data, share, MEM_HOST, None))
     return sol, status
+
+
+def qp_configure(eps=0.0, max_iter=0, polish=-1, polish_refine_iter=-1):
+    """Accuracy settings of the nv > 4 solver (asif_qp_configure); the defaults restore 1e-8 / 20000 / polish / 10."""
+    _check(load_library().asif_qp_configure(float(eps), int(max_iter), int(polish), int(polish_refine_iter)))
+
+
+def qp_last_info():
+    """(ADMM iterations, rho updates, polish state, active rows) of the first problem of this thread's last host call."""
+    info = np.zeros(4, dtype=np.int32)
+    _check(load_library().asif_qp_last_info(info.ctypes.data_as(_ip)))
+    return tuple(int(v) for v in info)

@@ -46,6 +46,12 @@ int fail(int code, const char *fmt, ...)
 }
 } // namespace asifb
 
+namespace asifb {
+int launch_qp_admm(int device, int nv, int nc, int64_t n, int diag_cost, const double *H, const double *c, const double *A,
+                   const double *b, const double *lb, const double *ub, const uint8_t *be, double *sol, int32_t *status,
+                   int share_flags, cudaStream_t st, bool fetch_info); // qp_admm.cu
+}
+
 namespace {
 
 int ensure_slot(asif_engine *e, Slot &s, int64_t n, bool want_diag)
@@ -1411,13 +1417,28 @@ int launch_qp(int64_t n, int nc, int diag_cost, const double *H, const double *c
 	CUDA_TRY(cudaGetLastError());
 	return ASIF_OK;
 }
+
+// nv <= MAX_NV: one problem per thread, exact dual active-set method (qp_gi.cuh); nv > MAX_NV: one cluster per problem,
+// operator splitting + polish (qp_admm.cuh / qp_admm.cu)
+int launch_qp_any(int device, int nv, int64_t n, int nc, int diag_cost, const double *H, const double *c, const double *A,
+                  const double *b, const double *lb, const double *ub, const uint8_t *be, double *sol, int32_t *status, int share,
+                  cudaStream_t st, bool host_call)
+{
+	switch (nv) {
+	case 1: return launch_qp<1>(n, nc, diag_cost, H, c, A, b, lb, ub, be, sol, status, share, st);
+	case 2: return launch_qp<2>(n, nc, diag_cost, H, c, A, b, lb, ub, be, sol, status, share, st);
+	case 3: return launch_qp<3>(n, nc, diag_cost, H, c, A, b, lb, ub, be, sol, status, share, st);
+	case 4: return launch_qp<4>(n, nc, diag_cost, H, c, A, b, lb, ub, be, sol, status, share, st);
+	default: return asifb::launch_qp_admm(device, nv, nc, n, diag_cost, H, c, A, b, lb, ub, be, sol, status, share, st, host_call);
+	}
+}
 } // namespace
 
 extern "C" int32_t asif_qp_solve_batch(int32_t device, int32_t nv, int32_t nc, int64_t n, int32_t diagonal_cost, const double *H,
                             const double *c, const double *A, const double *b, const double *lb, const double *ub,
                             const uint8_t *be, double *sol, int32_t *status, int32_t share_flags, int32_t mem, void *stream)
 {
-	if (nv < 1 || nv > MAX_NV) return fail(ASIF_ERR_UNSUPPORTED, "qp_solve_batch supports 1 <= nv <= %d (got %d)", MAX_NV, nv);
+	if (nv < 1) return fail(ASIF_ERR_UNSUPPORTED, "qp_solve_batch needs nv >= 1 (got %d)", nv);
 	if (nc < 0 || n < 0) return fail(ASIF_ERR_INVALID_ARGUMENT, "nc < 0 or n < 0");
 	if (n == 0) return ASIF_OK;
 	if (!H || !c || (nc > 0 && (!A || !b)) || !lb || !ub || !sol || !status) return fail(ASIF_ERR_INVALID_ARGUMENT, "NULL pointer");
@@ -1470,12 +1491,8 @@ extern "C" int32_t asif_qp_solve_batch(int32_t device, int32_t nv, int32_t nc, i
 		memcpy(hub, ub, sB * 8);
 		if (be) memcpy(hbe, be, nc);
 		int r;
-		switch (nv) { // unified addressing: the mapped host pointers are valid device pointers
-		case 1: r = launch_qp<1>(n, nc, diagonal_cost, hH, hc, hA, hb, hlb, hub, be ? hbe : nullptr, hsol, hst, share_flags, st); break;
-		case 2: r = launch_qp<2>(n, nc, diagonal_cost, hH, hc, hA, hb, hlb, hub, be ? hbe : nullptr, hsol, hst, share_flags, st); break;
-		case 3: r = launch_qp<3>(n, nc, diagonal_cost, hH, hc, hA, hb, hlb, hub, be ? hbe : nullptr, hsol, hst, share_flags, st); break;
-		default: r = launch_qp<4>(n, nc, diagonal_cost, hH, hc, hA, hb, hlb, hub, be ? hbe : nullptr, hsol, hst, share_flags, st); break;
-		}
+		// unified addressing: the mapped host pointers are valid device pointers
+		r = launch_qp_any(device, nv, n, nc, diagonal_cost, hH, hc, hA, hb, hlb, hub, be ? hbe : nullptr, hsol, hst, share_flags, st, true);
 		if (r) return r;
 		CUDA_TRY(cudaStreamSynchronize(st));
 		memcpy(sol, hsol, ssol * 8);
@@ -1539,12 +1556,7 @@ extern "C" int32_t asif_qp_solve_batch(int32_t device, int32_t nv, int32_t nc, i
 		return fail(ASIF_ERR_INVALID_ARGUMENT, "mem must be ASIF_MEM_HOST or ASIF_MEM_DEVICE");
 	}
 	int r;
-	switch (nv) {
-	case 1: r = launch_qp<1>(n, nc, diagonal_cost, dH, dc, dA, db, dlb, dub, dbe, dsol, dstatus, share_flags, st); break;
-	case 2: r = launch_qp<2>(n, nc, diagonal_cost, dH, dc, dA, db, dlb, dub, dbe, dsol, dstatus, share_flags, st); break;
-	case 3: r = launch_qp<3>(n, nc, diagonal_cost, dH, dc, dA, db, dlb, dub, dbe, dsol, dstatus, share_flags, st); break;
-	default: r = launch_qp<4>(n, nc, diagonal_cost, dH, dc, dA, db, dlb, dub, dbe, dsol, dstatus, share_flags, st); break;
-	}
+	r = launch_qp_any(device, nv, n, nc, diagonal_cost, dH, dc, dA, db, dlb, dub, dbe, dsol, dstatus, share_flags, st, mem == ASIF_MEM_HOST);
 	if (mem == ASIF_MEM_HOST) {
 		cudaError_t err = cudaSuccess;
 		if (!r) {

@@ -128,11 +128,10 @@ namespace ASIF
 		virtual int32_t initialize(const double H[], const double c[], const double A[], const double b[],
 		                           const double lb[], const double ub[], const bool be[] = nullptr)
 		{
-			// nv > 4 (the LP-dual formulations of ASIFrobust / ASIFrealizable: nv = 402 / 38) is not a problem this backend
-			// solves - those classes run on the B200 through FilterBatchRobust / FilterBatchRealizable, which eliminate the
-			// multipliers.  Every reference caller ignores initialize()'s return value (src/asif.cpp:102), so solve() fails
-			// loudly as well: it returns ASIF_ERR_UNSUPPORTED (-102), a value no OSQP status and no filter code uses.
-			if (nv_ < 1 || nv_ > 4) return ASIF_ERR_UNSUPPORTED;
+			// nv <= 4 runs the per-thread exact dual active-set solver; nv > 4 (the LP-dual formulations of ASIFrobust /
+			// ASIFrealizable: nv = 402 / 38, Hessian only semi-definite) the cluster-cooperative operator-splitting solver
+			// with polish (csrc/qp_admm.cuh) - asif_qp_solve_batch picks by nv.
+			if (nv_ < 1) return ASIF_ERR_UNSUPPORTED;
 			if (be != nullptr) {
 				for (uint32_t i = 0; i < nc_; i++) {
 					be_[i] = be[i];

@@ -297,12 +297,26 @@ int32_t asif_engine_last_qp_iterations(asif_engine *e, uint64_t *rows_processed)
  * The QPWrapper backend: n independent dense QPs of identical shape
  *      min v'Hv + c'v   s.t.  A v >= b (row i equality where be[i]),  lb <= v <= ub
  * replacing QPWrapperOsqp::initialize/updateCost/updateA/updateb/solve/getSolution
- * (src/qpwrapper_osqp.cpp:55-261) for nv <= 4.  Layout per problem as in the reference:
+ * (src/qpwrapper_osqp.cpp:55-261).  Layout per problem as in the reference:
  * H[nv*nv] (diagonal_cost: only the diagonal is read, src/qpwrapper_osqp.cpp:267-283), c[nv],
  * A[nc*nv] column-major, b[nc], lb[nv], ub[nv]; problems are consecutive.  H, lb, ub, be may be
  * shared by all problems (stride flags).  status[k] = 1 (QPWrapperAbstract::SOLVER_STATUS::FEASIBLE)
- * or the OSQP code the reference would pass through (-3 primal infeasible, -2 iteration limit).
+ * or the OSQP code the reference would pass through (-3 primal infeasible, -2 iteration limit, -4 dual
+ * infeasible, -7 not convex, 3 / 4 the "inaccurate" infeasibility verdicts).
+ * Two solvers, picked by nv:
+ *   nv <= 4  (every QP the batched filter classes pose, H positive definite): one problem per THREAD, exact
+ *            dual active-set method in registers (csrc/qp_gi.cuh);
+ *   nv  > 4  (the LP-dual formulations of ASIFrobust / ASIFrealizable, nv = 402 / 38, src/asif_robust.cpp:21-22;
+ *            H may be positive semi-definite): one problem per thread-block CLUSTER, the OSQP algorithm (ADMM
+ *            with cached explicit inverse, adaptive rho, infeasibility certificates, active-set polish) at
+ *            eps_abs = eps_rel = 1e-8 (csrc/qp_admm.cuh); nv <= 1024, nc <= 4096; solution is NaN where OSQP
+ *            returns none.  asif_qp_configure changes its accuracy settings (process-wide; arguments <= 0 / < 0
+ *            restore the defaults 1e-8, 20000, polish on, 10 refinement steps); asif_qp_last_info returns
+ *            {ADMM iterations, rho updates, polish 1 accepted / -1 rejected / 0 not run, active rows} of the
+ *            first problem of the calling thread's last ASIF_MEM_HOST call.
  */
+int32_t asif_qp_configure(double eps_abs_rel, int32_t max_iter, int32_t polish, int32_t polish_refine_iter);
+int32_t asif_qp_last_info(int32_t info[4]);
 #define ASIF_QP_SHARED_H 1      /* one H for all problems */
 #define ASIF_QP_SHARED_BOUNDS 2 /* one lb/ub for all problems */
 int32_t asif_qp_solve_batch(int32_t device, int32_t nv, int32_t nc, int64_t n, int32_t diagonal_cost,
