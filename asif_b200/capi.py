@@ -511,7 +511,8 @@ def qp_configure(eps=0.0, max_iter=0, polish=-1, polish_refine_iter=-1):
 
 
 def qp_last_info():
-    """(ADMM iterations, rho updates, polish state, active rows) of the first problem of this thread's last host call."""
-    info = np.zeros(4, dtype=np.int32)
+    """(ADMM iterations, rho updates, polish state, active rows, us equilibration / factorisations / iterations / polish)
+    of the first problem of this thread's last host call."""
+    info = np.zeros(8, dtype=np.int32)
     _check(load_library().asif_qp_last_info(info.ctypes.data_as(_ip)))
     return tuple(int(v) for v in info)

@@ -34,8 +34,11 @@ struct ClusterTeam {
 	static constexpr int LANES = 32;
 	int tid, nthreads, lane, warp, nwarps;
 	bool single;
-	__device__ __forceinline__ ClusterTeam()
+	double *scratch; // this warp's slice of the CTA's dynamic shared memory (scratch_len doubles)
+	__device__ __forceinline__ double *warp_scratch() const { return scratch; }
+	__device__ __forceinline__ ClusterTeam(double *smem, int scratch_len)
 	{
+		scratch = smem + (size_t)(threadIdx.x >> 5) * scratch_len;
 		cg::cluster_group cl = cg::this_cluster();
 		const unsigned cr = cl.block_rank(), cs = cl.num_blocks();
 		tid = (int)(cr * blockDim.x + threadIdx.x);
@@ -53,6 +56,7 @@ struct ClusterTeam {
 		else cg::this_cluster().sync();
 	}
 	__device__ __forceinline__ void warp_sync() const { __syncwarp(); }
+	__device__ __forceinline__ double warp_bcast(double v, int src) const { return __shfl_sync(0xffffffffu, v, src); }
 	__device__ __forceinline__ double warp_sum(double v) const
 	{
 #pragma unroll
@@ -78,13 +82,16 @@ struct BatchArgs {
 	size_t work_stride; // doubles per cluster
 };
 
-__global__ void __launch_bounds__(QA_THREADS, 1) qp_admm_kernel(const BatchArgs a, const qpadmm::Settings st)
+__global__ void __launch_bounds__(QA_THREADS, 1) qp_admm_kernel(const __grid_constant__ BatchArgs a, const __grid_constant__ qpadmm::Settings st)
 {
-	ClusterTeam tm;
+	extern __shared__ double qa_smem[];
+	ClusterTeam tm(qa_smem, (a.nv + 1) & ~1);
 	cg::cluster_group cl = cg::this_cluster();
 	const unsigned csize = cl.num_blocks();
 	const int64_t cluster_id = blockIdx.x / csize, n_clusters = gridDim.x / csize;
-	const qpadmm::Work w = qpadmm::carve(a.work + (size_t)cluster_id * a.work_stride, a.nv, a.nc);
+	__shared__ qpadmm::Work w;
+	if (threadIdx.x == 0) w = qpadmm::carve(a.work + (size_t)cluster_id * a.work_stride, a.nv, a.nc);
+	__syncthreads();
 	for (int64_t k = cluster_id; k < a.n; k += n_clusters) {
 		qpadmm::Problem pb;
 		pb.nv = a.nv;
@@ -99,7 +106,7 @@ __global__ void __launch_bounds__(QA_THREADS, 1) qp_admm_kernel(const BatchArgs 
 		pb.be = a.be;
 		pb.sol = a.sol + k * a.nv;
 		pb.status = a.status + k;
-		pb.info = a.info ? a.info + 4 * k : nullptr;
+		pb.info = a.info ? a.info + qpadmm::NINFO * k : nullptr;
 		qpadmm::Solver<ClusterTeam> s(tm, st, a.nv, a.nc, w);
 		const int32_t code = s.solve(pb);
 		// the QPWrapper convention (src/qpwrapper_osqp.cpp:217-237): 1 = FEASIBLE for solved / solved inaccurate, else
@@ -118,7 +125,7 @@ struct DevBuf {
 	int dev = -1;
 };
 thread_local DevBuf tl_work, tl_info;
-thread_local int32_t tl_last_info[4] = {0, 0, 0, 0};
+thread_local int32_t tl_last_info[qpadmm::NINFO] = {0};
 
 int ensure(DevBuf &b, int device, size_t bytes)
 {
@@ -167,7 +174,8 @@ int launch_qp_admm(int device, int nv, int nc, int64_t n, int diag_cost, const d
 	attr[0].val.clusterDim.y = 1;
 	attr[0].val.clusterDim.z = 1;
 	lc.blockDim = dim3(QA_THREADS);
-	lc.dynamicSmemBytes = 0;
+	lc.dynamicSmemBytes = sizeof(double) * (size_t)((nv + 1) & ~1) * (QA_THREADS / 32); // one column per warp (Solver::factor)
+	QA_CUDA_TRY(cudaFuncSetAttribute(qp_admm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lc.dynamicSmemBytes));
 	lc.stream = st;
 	lc.attrs = attr;
 	lc.numAttrs = 1;
@@ -179,7 +187,7 @@ int launch_qp_admm(int device, int nv, int nc, int64_t n, int diag_cost, const d
 	const size_t stride = (qpadmm::work_doubles(nv, nc) + 31) & ~(size_t)31;
 	int r = ensure(tl_work, device, stride * sizeof(double) * (size_t)n_clusters);
 	if (r) return r;
-	r = ensure(tl_info, device, sizeof(int32_t) * 4 * (size_t)n);
+	r = ensure(tl_info, device, sizeof(int32_t) * qpadmm::NINFO * (size_t)n);
 	if (r) return r;
 	BatchArgs a;
 	a.nv = nv;
@@ -215,9 +223,9 @@ extern "C" int32_t asif_qp_configure(double eps_abs_rel, int32_t max_iter, int32
 	return ASIF_OK;
 }
 
-extern "C" int32_t asif_qp_last_info(int32_t info[4])
+extern "C" int32_t asif_qp_last_info(int32_t info[8])
 {
 	if (!info) return fail(ASIF_ERR_INVALID_ARGUMENT, "info is NULL");
-	for (int i = 0; i < 4; i++) info[i] = tl_last_info[i];
+	for (int i = 0; i < qpadmm::NINFO; i++) info[i] = tl_last_info[i];
 	return ASIF_OK;
 }

@@ -39,6 +39,19 @@
 
 namespace qpadmm {
 
+// wall clock for the phase statistics (ns); 0 on the host
+QA_FN unsigned long long now_ns()
+{
+#if defined(__CUDA_ARCH__)
+	unsigned long long t;
+	asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+	return t;
+#else
+	return 0ull;
+#endif
+}
+constexpr int NINFO = 8; // per problem: iterations, rho updates, polish state, active rows, us in: scaling, factorisations, iterations, polish
+
 constexpr double QA_INFTY = 1e30; // OSQP_INFTY
 constexpr double RHO_MIN = 1e-6, RHO_MAX = 1e6, RHO_EQ_OVER_RHO_INEQ = 1e3, RHO_TOL = 1e-4;
 constexpr double MIN_SCALING = 1e-4, MAX_SCALING = 1e4;
@@ -91,7 +104,7 @@ struct Problem {
 	const uint8_t *be;
 	double *sol;
 	int32_t *status;
-	int32_t *info; // optional [4]: ADMM iterations, rho updates, polish (1 accepted / -1 rejected / 0 not run), active rows
+	int32_t *info; // optional [NINFO]: ADMM iterations, rho updates, polish (1 accepted / -1 rejected / 0 not run), active rows, then us per phase
 };
 
 // ---- workspace ------------------------------------------------------------------------------------------------------
@@ -115,7 +128,7 @@ QA_FN size_t work_doubles(int n, int mA)
 	d += (size_t)n * n * 4;        // P, K, Xinv, Kinv
 	d += (size_t)mA * n * 2;       // A, At
 	d += N * N * 2;                // LR, LC
-	d += (size_t)n * 15 + m * 16 + N * 5;
+	d += (size_t)n * 15 + m * 16 + N * 8; // tcol holds N x PB (= 4) doubles
 	d += 2 * NRED * MAX_TEAM_WARPS;
 	d += (2 * m + 8 + 1) / 2 + 2;  // ints
 	return d + 256;                // alignment slack (every vector is rounded up to 16 bytes)
@@ -145,7 +158,7 @@ QA_FN Work carve(double *base, int n, int mA)
 	w.l = take(m); w.u = take(m); w.E = take(m); w.Einv = take(m); w.rho_vec = take(m); w.rho_inv = take(m);
 	w.z0 = take(m); w.z1 = take(m); w.y = take(m); w.zt = take(m); w.dy = take(m); w.Et = take(m); w.Ax = take(m);
 	w.tmpm = take(m); w.yp = take(m); w.zp = take(m);
-	w.prhs = take(N); w.psol = take(N); w.pres = take(N); w.tcol = take(N); w.pd = take(N);
+	w.prhs = take(N); w.psol = take(N); w.pres = take(N); w.tcol = take(N * 4); w.pd = take(N);
 	w.red = take(2 * NRED * MAX_TEAM_WARPS);
 	w.ctype = (int32_t *)p;
 	w.rows = w.ctype + m;
@@ -157,9 +170,11 @@ QA_FN Work carve(double *base, int n, int mA)
 template <class T>
 struct Solver {
 	T &tm;
-	const Settings st;
+	const Settings &st; // device: the kernel's __grid_constant__ parameter (constant bank)
 	const int n, mA, m;
-	Work w;
+	const Work &w;      // device: one copy per CTA in shared memory - 60 pointers do not fit in registers, and left to
+	                    // itself the compiler re-derives them from the base address at every use (a third of all
+	                    // executed instructions in the first ncu capture)
 	double cscale, cinv, rho;
 	int red_slot;
 
@@ -191,37 +206,64 @@ struct Solver {
 		}
 	}
 
-	// -- products with the constraint matrix [A ; diag(Ib)] and with P: one warp per output element, no barrier inside
+	// -- `count` dot products of length `len` against one vector: a warp takes R rows at a time and four steps of the
+	//    lane loop at once, so that 4R + 4 independent loads are in flight per lane (the phases are bound by the latency
+	//    of L2 - every cluster barrier invalidates L1 - not by bandwidth); rowptr(i) -> first element of row i,
+	//    store(i, sum) runs on lane 0
+	template <int R, class RowPtr, class Store>
+	QA_FN void warp_dots(const int count, const int len, RowPtr rowptr, const double *vec, Store store) const
+	{
+		constexpr int L = T::LANES;
+		for (int base = tm.warp * R; base < count; base += tm.nwarps * R) {
+			const double *rp[R];
+			double s[R];
+#pragma unroll
+			for (int r = 0; r < R; r++) {
+				rp[r] = rowptr(base + r < count ? base + r : count - 1);
+				s[r] = 0.0;
+			}
+			int k = tm.lane;
+			for (; k + 3 * L < len; k += 4 * L) {
+				const double v0 = vec[k], v1 = vec[k + L], v2 = vec[k + 2 * L], v3 = vec[k + 3 * L];
+				double a[R][4];
+#pragma unroll
+				for (int r = 0; r < R; r++) {
+					a[r][0] = rp[r][k];
+					a[r][1] = rp[r][k + L];
+					a[r][2] = rp[r][k + 2 * L];
+					a[r][3] = rp[r][k + 3 * L];
+				}
+#pragma unroll
+				for (int r = 0; r < R; r++) s[r] = fma(a[r][3], v3, fma(a[r][2], v2, fma(a[r][1], v1, fma(a[r][0], v0, s[r]))));
+			}
+			for (; k < len; k += L) {
+				const double v0 = vec[k];
+#pragma unroll
+				for (int r = 0; r < R; r++) s[r] = fma(rp[r][k], v0, s[r]);
+			}
+#pragma unroll
+			for (int r = 0; r < R; r++) s[r] = tm.warp_sum(s[r]);
+			if (tm.lane == 0) {
+#pragma unroll
+				for (int r = 0; r < R; r++)
+					if (base + r < count) store(base + r, s[r]);
+			}
+		}
+	}
+
+	// -- products with the constraint matrix [A ; diag(Ib)] and with P, no barrier inside
 	QA_FN void mv_A(const double *v, double *out) const
 	{
-		for (int i = tm.warp; i < mA; i += tm.nwarps) {
-			const double *row = w.At + (size_t)i * n;
-			double s = 0.0;
-			for (int j = tm.lane; j < n; j += T::LANES) s = fma(row[j], v[j], s);
-			s = tm.warp_sum(s);
-			if (tm.lane == 0) out[i] = s;
-		}
+		warp_dots<4>(mA, n, [&](int i) { return w.At + (size_t)i * n; }, v, [&](int i, double s) { out[i] = s; });
 		for (int j = tm.tid; j < n; j += tm.nthreads) out[mA + j] = w.Ib[j] * v[j];
 	}
 	QA_FN void mv_At(const double *y, double *out) const
 	{
-		for (int j = tm.warp; j < n; j += tm.nwarps) {
-			const double *col = w.A + (size_t)j * mA;
-			double s = 0.0;
-			for (int i = tm.lane; i < mA; i += T::LANES) s = fma(col[i], y[i], s);
-			s = tm.warp_sum(s);
-			if (tm.lane == 0) out[j] = s + w.Ib[j] * y[mA + j];
-		}
+		warp_dots<4>(n, mA, [&](int j) { return w.A + (size_t)j * mA; }, y, [&](int j, double s) { out[j] = s + w.Ib[j] * y[mA + j]; });
 	}
 	QA_FN void mv_P(const double *v, double *out) const
 	{
-		for (int j = tm.warp; j < n; j += tm.nwarps) {
-			const double *col = w.P + (size_t)j * n;
-			double s = 0.0;
-			for (int i = tm.lane; i < n; i += T::LANES) s = fma(col[i], v[i], s);
-			s = tm.warp_sum(s);
-			if (tm.lane == 0) out[j] = s;
-		}
+		warp_dots<4>(n, n, [&](int j) { return w.P + (size_t)j * n; }, v, [&](int j, double s) { out[j] = s; });
 	}
 
 	static QA_FN double limit_scaling(double v)
@@ -347,61 +389,152 @@ struct Solver {
 	}
 
 	// -- in-place LDL' of the symmetric N x N matrix held (fully) in LRm (row-major == column-major); on return the
-	//    strict lower triangle of LRm holds L by rows, LCm (if given) holds L by columns, d the pivots.  Left-looking:
-	//    column j needs one sweep of dot products over the finished columns - two barriers per column.
-	//    Returns false (on every thread) when a pivot is zero or not finite.
-	QA_FN bool ldl_factor(double *LRm, double *LCm, double *d, double *tcol, const int N, const bool want_positive)
+	//    strict lower triangle of LRm holds L by rows, LCm (if given) holds L by columns, d the pivots.  Left-looking by
+	//    PANELS of PB columns: one sweep of dot products over the finished columns gives the panel's PB columns at once
+	//    (a row's loads are shared by the PB sums); the coupling inside the panel is a PB x PB factorisation that every
+	//    thread repeats in registers for the rows it owns - two barriers per panel instead of two per column.
+	//    tbuf: N x PB doubles.  Returns false (on every thread) when a pivot is zero, not finite or (want_positive) negative.
+	static constexpr int PB = 4;
+	QA_FN bool ldl_factor(double *LRm, double *LCm, double *d, double *tbuf, const int N, const bool want_positive)
 	{
+		constexpr int L = T::LANES;
 		bool ok = true;
-		for (int j = 0; j < N; j++) {
-			const double *rj = LRm + (size_t)j * N;
-			for (int i = j + tm.warp; i < N; i += tm.nwarps) {
+		for (int j0 = 0; j0 < N && ok; j0 += PB) {
+			const int nb = (N - j0 < PB) ? N - j0 : PB;
+			const double *rj[PB];
+#pragma unroll
+			for (int c = 0; c < PB; c++) rj[c] = LRm + (size_t)(j0 + (c < nb ? c : nb - 1)) * N;
+			for (int i = j0 + tm.warp; i < N; i += tm.nwarps) {
 				const double *ri = LRm + (size_t)i * N;
-				double s = 0.0;
-				for (int k = tm.lane; k < j; k += T::LANES) s = fma(ri[k] * d[k], rj[k], s);
-				s = tm.warp_sum(s);
-				if (tm.lane == 0) tcol[i] = ri[j] - s;
+				double s[PB];
+#pragma unroll
+				for (int c = 0; c < PB; c++) s[c] = 0.0;
+				int k = tm.lane;
+				for (; k + L < j0; k += 2 * L) {
+					const double a0 = ri[k] * d[k], a1 = ri[k + L] * d[k + L];
+					double b0[PB], b1[PB];
+#pragma unroll
+					for (int c = 0; c < PB; c++) {
+						b0[c] = rj[c][k];
+						b1[c] = rj[c][k + L];
+					}
+#pragma unroll
+					for (int c = 0; c < PB; c++) s[c] = fma(a1, b1[c], fma(a0, b0[c], s[c]));
+				}
+				if (k < j0) {
+					const double a0 = ri[k] * d[k];
+#pragma unroll
+					for (int c = 0; c < PB; c++) s[c] = fma(a0, rj[c][k], s[c]);
+				}
+#pragma unroll
+				for (int c = 0; c < PB; c++) s[c] = tm.warp_sum(s[c]);
+				if (tm.lane == 0) {
+#pragma unroll
+					for (int c = 0; c < PB; c++)
+						if (c < nb) tbuf[(size_t)i * PB + c] = ri[j0 + c] - s[c];
+				}
 			}
 			tm.sync();
-			const double dj = tcol[j];
-			if (!(fabs(dj) > 0.0) || !(fabs(dj) < INFINITY) || (want_positive && dj < 0.0)) ok = false;
-			const double dinv = 1.0 / dj;
-			for (int i = j + 1 + tm.tid; i < N; i += tm.nthreads) {
-				const double lij = tcol[i] * dinv;
-				LRm[(size_t)i * N + j] = lij;
-				if (LCm) LCm[(size_t)j * N + i] = lij;
+			// the panel's own PB x PB block: Lp (strict lower), dd - the same numbers on every thread
+			double Lp[PB][PB], dd[PB], di[PB];
+#pragma unroll
+			for (int c = 0; c < PB; c++) {
+				dd[c] = 1.0;
+				di[c] = 1.0;
+#pragma unroll
+				for (int r = 0; r < PB; r++) Lp[r][c] = 0.0;
 			}
-			if (tm.tid == 0) d[j] = dj;
+#pragma unroll
+			for (int c = 0; c < PB; c++) {
+				if (c < nb) {
+					double v = tbuf[(size_t)(j0 + c) * PB + c];
+#pragma unroll
+					for (int e = 0; e < c; e++) v = fma(-Lp[c][e] * dd[e], Lp[c][e], v);
+					dd[c] = v;
+					if (!(fabs(v) > 0.0) || !(fabs(v) < INFINITY) || (want_positive && v < 0.0)) ok = false;
+					di[c] = 1.0 / v;
+#pragma unroll
+					for (int r = c + 1; r < PB; r++) {
+						if (r < nb) {
+							double t = tbuf[(size_t)(j0 + r) * PB + c];
+#pragma unroll
+							for (int e = 0; e < c; e++) t = fma(-Lp[r][e] * dd[e], Lp[c][e], t);
+							Lp[r][c] = t * di[c];
+						}
+					}
+				}
+			}
+			if (ok) {
+				for (int i = j0 + 1 + tm.tid; i < N; i += tm.nthreads) {
+					const int cmax = (i - j0 < nb) ? i - j0 : nb; // columns j0 .. j0 + cmax - 1 lie left of the diagonal
+					double li[PB];
+#pragma unroll
+					for (int c = 0; c < PB; c++) {
+						li[c] = 0.0;
+						if (c < cmax) {
+							double t = tbuf[(size_t)i * PB + c];
+#pragma unroll
+							for (int e = 0; e < c; e++) t = fma(-li[e] * dd[e], Lp[c][e], t);
+							li[c] = t * di[c];
+							LRm[(size_t)i * N + j0 + c] = li[c];
+							if (LCm) LCm[(size_t)(j0 + c) * N + i] = li[c];
+						}
+					}
+				}
+				if (tm.tid == 0)
+					for (int c = 0; c < nb; c++) d[j0 + c] = dd[c];
+			}
 			tm.sync();
-			if (!ok) break; // dj is the same value on every thread
 		}
 		return ok;
 	}
 
-	// -- solve L D L' s = b in place by ONE warp (rows of L for the forward sweep, columns for the backward one)
-	QA_FN void ldl_solve_warp0(const double *LRm, const double *LCm, const double *d, double *b, const int N)
+	// -- solve L D L' s = b in place, blocked by LANES: the diagonal block is solved by warp 0 with one row per lane
+	//    (its elements loaded ahead of the shuffle chain), the rest of the right-hand side is updated by the whole team,
+	//    one row per thread reading ITS contiguous LANES elements - rows of L (LRm) going forward, columns (LCm) going back
+	QA_FN void ldl_solve(const double *LRm, const double *LCm, const double *d, double *b, const int N)
 	{
-		if (tm.warp == 0) {
-			for (int i = 0; i < N; i++) {
-				const double *ri = LRm + (size_t)i * N;
-				double s = 0.0;
-				for (int k = tm.lane; k < i; k += T::LANES) s = fma(ri[k], b[k], s);
-				s = tm.warp_sum(s);
-				if (tm.lane == 0) b[i] -= s;
-				tm.warp_sync();
+		constexpr int BS = T::LANES;
+		const int nblk = (N + BS - 1) / BS;
+		for (int sweep = 0; sweep < 2; sweep++) {
+			const double *M = sweep == 0 ? LRm : LCm;
+			for (int q = 0; q < nblk; q++) {
+				const int blk = sweep == 0 ? q : nblk - 1 - q;
+				const int k0 = blk * BS, nb = (N - k0 < BS) ? N - k0 : BS;
+				if (tm.warp == 0) {
+					const bool live = tm.lane < nb;
+					const double *mine = M + (size_t)(k0 + (live ? tm.lane : 0)) * N + k0;
+					double br = live ? b[k0 + tm.lane] : 0.0;
+#pragma unroll 8
+					for (int q2 = 0; q2 < BS; q2++) {
+						const int c = sweep == 0 ? q2 : BS - 1 - q2;
+						const bool use = live && c < nb && (sweep == 0 ? c < tm.lane : c > tm.lane);
+						const double l = use ? mine[c] : 0.0;
+						const double xc = tm.warp_bcast(br, c);
+						br = fma(-l, xc, br);
+					}
+					if (live) b[k0 + tm.lane] = br;
+				}
+				tm.sync();
+				const int lo = sweep == 0 ? k0 + nb : 0, hi = sweep == 0 ? N : k0;
+				for (int i = lo + tm.tid; i < hi; i += tm.nthreads) {
+					const double *mi = M + (size_t)i * N + k0;
+					double s0 = 0.0, s1 = 0.0;
+					int c = 0;
+					for (; c + 1 < nb; c += 2) {
+						s0 = fma(mi[c], b[k0 + c], s0);
+						s1 = fma(mi[c + 1], b[k0 + c + 1], s1);
+					}
+					if (c < nb) s0 = fma(mi[c], b[k0 + c], s0);
+					b[i] -= s0 + s1;
+				}
+				tm.sync();
 			}
-			for (int i = tm.lane; i < N; i += T::LANES) b[i] /= d[i];
-			tm.warp_sync();
-			for (int i = N - 1; i >= 0; i--) {
-				const double *ci = LCm + (size_t)i * N;
-				double s = 0.0;
-				for (int k = i + 1 + tm.lane; k < N; k += T::LANES) s = fma(ci[k], b[k], s);
-				s = tm.warp_sum(s);
-				if (tm.lane == 0) b[i] -= s;
-				tm.warp_sync();
+			if (sweep == 0) {
+				for (int i = tm.tid; i < N; i += tm.nthreads) b[i] /= d[i];
+				tm.sync();
 			}
 		}
-		tm.sync();
 	}
 
 	// -- K = P + sigma I + [A;I]' R [A;I], factored and inverted explicitly; false when K is not positive definite
@@ -425,21 +558,20 @@ struct Solver {
 		tm.sync();
 		if (!ldl_factor(w.K, nullptr, w.kd, w.tcol, n, true)) return false;
 		for (int i = tm.tid; i < n; i += tm.nthreads) w.pcol[i] = 1.0 / w.kd[i];
-		// X = L^-1 by rows (X[i][j] at Xinv[i*n + j]): thread j owns column j; the lanes of a warp walk the same
-		// (i, k) so that L[i][k] is one broadcast load and X[k][j] a coalesced one
-		for (int j = tm.tid; j < n; j += tm.nthreads) {
-			const int k0 = j - (j % T::LANES);
-			for (int i = k0; i < n; i++) {
+		// X = L^-1 (X[i][j] at Xinv[i*n + j]): one warp per column j, the column under construction in the warp's scratch
+		// (shared memory), every row one coalesced dot product over L's row i
+		for (int j = tm.warp; j < n; j += tm.nwarps) {
+			double *xs = tm.warp_scratch();
+			for (int i = j; i < n; i++) {
 				const double *li = w.K + (size_t)i * n;
-				double s0 = 0.0, s1 = 0.0;
-				int k = k0;
-				for (; k + 1 < i; k += 2) {
-					s0 = fma(li[k], w.Xinv[(size_t)k * n + j], s0);
-					s1 = fma(li[k + 1], w.Xinv[(size_t)(k + 1) * n + j], s1);
-				}
-				if (k < i) s0 = fma(li[k], w.Xinv[(size_t)k * n + j], s0);
-				w.Xinv[(size_t)i * n + j] = (i == j ? 1.0 : 0.0) - (s0 + s1);
+				double s = 0.0;
+				for (int k = j + tm.lane; k < i; k += T::LANES) s = fma(li[k], xs[k], s);
+				s = tm.warp_sum(s);
+				if (tm.lane == 0) xs[i] = (i == j ? 1.0 : 0.0) - s;
+				tm.warp_sync();
 			}
+			for (int i = j + tm.lane; i < n; i += T::LANES) w.Xinv[(size_t)i * n + j] = xs[i];
+			tm.warp_sync();
 		}
 		tm.sync();
 		// K^-1[a][b] = sum_{i >= max(a,b)} X[i][a] X[i][b] / d_i
@@ -622,7 +754,7 @@ struct Solver {
 		if (!ldl_factor(w.LR, w.LC, w.pd, w.tcol, N, false)) return false;
 		for (int i = tm.tid; i < N; i += tm.nthreads) w.psol[i] = w.prhs[i];
 		tm.sync();
-		ldl_solve_warp0(w.LR, w.LC, w.pd, w.psol, N);
+		ldl_solve(w.LR, w.LC, w.pd, w.psol, N);
 		for (int it = 0; it < st.polish_refine_iter; it++) {
 			// residual of the UNregularised system: [P x + A_act' y ; A_act x]
 			for (int i = tm.tid; i < m; i += tm.nthreads) w.tmpm[i] = 0.0;
@@ -637,7 +769,7 @@ struct Solver {
 			for (int j = tm.tid; j < n; j += tm.nthreads) w.pres[j] = w.prhs[j] - w.Px[j] - w.Aty[j];
 			for (int a = tm.tid; a < na; a += tm.nthreads) w.pres[n + a] = w.prhs[n + a] - w.Ax[w.rows[a]];
 			tm.sync();
-			ldl_solve_warp0(w.LR, w.LC, w.pd, w.pres, N);
+			ldl_solve(w.LR, w.LC, w.pd, w.pres, N);
 			double r[NRED] = {0, 0, 0, 0, 0, 0, 0, 0};
 			for (int i = tm.tid; i < N; i += tm.nthreads) {
 				const double s = w.psol[i] + w.pres[i];
@@ -672,17 +804,23 @@ struct Solver {
 	// -- the whole solve: status code, solution written to pb.sol (NaN when there is none, as OSQP)
 	QA_FN int32_t solve(const Problem &pb)
 	{
+		unsigned long long t0 = now_ns(), t_factor = 0, t_polish = 0;
 		load_and_scale(pb);
 		rho = st.rho;
 		set_rho_vec();
+		const unsigned long long t_scale = now_ns() - t0;
 		int32_t status = ST_UNSOLVED, iter = 0, rho_updates = 0, polish_state = 0, n_active = 0;
 		const double *xf = nullptr;
-		if (!factor()) {
+		const unsigned long long t_loop0 = now_ns();
+		t0 = t_loop0;
+		const bool f0 = factor();
+		t_factor += now_ns() - t0;
+		if (!f0) {
 			status = ST_NON_CVX;
 		} else {
 			double *x = w.x0, *xprev = w.x1, *z = w.z0, *zprev = w.z1;
 			for (int j = tm.tid; j < n; j += tm.nthreads) x[j] = xprev[j] = w.dx[j] = 0.0;
-			for (int i = tm.tid; i < m; i += tm.nthreads) z[i] = zprev[i] = w.y[i] = w.dy[i] = 0.0;
+			for (int i = tm.tid; i < m; i += tm.nthreads) z[i] = zprev[i] = w.y[i] = w.dy[i] = w.zt[i] = 0.0;
 			tm.sync();
 			const double alpha = st.alpha, sigma = st.sigma;
 			Res r = {0, 0, 0, 0, 0};
@@ -696,41 +834,26 @@ struct Solver {
 					z = zprev;
 					zprev = t;
 				}
-				// rhs = sigma x_prev - q + [A;I]'(R z_prev - y)
-				for (int j = tm.warp; j < n; j += tm.nwarps) {
-					const double *col = w.A + (size_t)j * mA;
-					double s = 0.0;
-					for (int i = tm.lane; i < mA; i += T::LANES) s = fma(col[i], w.rho_vec[i] * zprev[i] - w.y[i], s);
-					s = tm.warp_sum(s);
-					if (tm.lane == 0)
-						w.rhs[j] = s + w.Ib[j] * (w.rho_vec[mA + j] * zprev[mA + j] - w.y[mA + j]) + sigma * xprev[j] - w.q[j];
-				}
+				// rhs = sigma x_prev - q + [A;I]'(R z_prev - y); the vector R z - y is carried in w.zt from the last pass
+				warp_dots<4>(n, mA, [&](int j) { return w.A + (size_t)j * mA; }, w.zt, [&](int j, double s) {
+					w.rhs[j] = s + w.Ib[j] * w.zt[mA + j] + sigma * xprev[j] - w.q[j];
+				});
 				tm.sync();
 				// x-tilde = K^-1 rhs
-				for (int j = tm.warp; j < n; j += tm.nwarps) {
-					const double *row = w.Kinv + (size_t)j * n;
-					double s = 0.0;
-					for (int k = tm.lane; k < n; k += T::LANES) s = fma(row[k], w.rhs[k], s);
-					s = tm.warp_sum(s);
-					if (tm.lane == 0) w.xt[j] = s;
-				}
+				warp_dots<4>(n, n, [&](int j) { return w.Kinv + (size_t)j * n; }, w.rhs, [&](int j, double s) { w.xt[j] = s; });
 				tm.sync();
 				// z-tilde = [A;I] x-tilde, then the relaxed x, the projected z and the dual step, row by row
-				for (int i = tm.warp; i < mA; i += tm.nwarps) {
-					const double *row = w.At + (size_t)i * n;
-					double s = 0.0;
-					for (int j = tm.lane; j < n; j += T::LANES) s = fma(row[j], w.xt[j], s);
-					s = tm.warp_sum(s);
-					if (tm.lane == 0) {
-						const double zr = alpha * s + (1.0 - alpha) * zprev[i];
-						double zi = zr + w.y[i] * w.rho_inv[i];
-						zi = fmin(fmax(zi, w.l[i]), w.u[i]);
-						z[i] = zi;
-						const double d = w.rho_vec[i] * (zr - zi);
-						w.dy[i] = d;
-						w.y[i] += d;
-					}
-				}
+				warp_dots<4>(mA, n, [&](int i) { return w.At + (size_t)i * n; }, w.xt, [&](int i, double s) {
+					const double zr = alpha * s + (1.0 - alpha) * zprev[i];
+					double zi = zr + w.y[i] * w.rho_inv[i];
+					zi = fmin(fmax(zi, w.l[i]), w.u[i]);
+					z[i] = zi;
+					const double d = w.rho_vec[i] * (zr - zi);
+					w.dy[i] = d;
+					const double yn = w.y[i] + d;
+					w.y[i] = yn;
+					w.zt[i] = w.rho_vec[i] * zi - yn;
+				});
 				for (int j = tm.tid; j < n; j += tm.nthreads) {
 					const double xtj = w.xt[j];
 					const double xn = alpha * xtj + (1.0 - alpha) * xprev[j];
@@ -743,7 +866,9 @@ struct Solver {
 					z[i] = zi;
 					const double d = w.rho_vec[i] * (zr - zi);
 					w.dy[i] = d;
-					w.y[i] += d;
+					const double yn = w.y[i] + d;
+					w.y[i] = yn;
+					w.zt[i] = w.rho_vec[i] * zi - yn;
 				}
 				tm.sync();
 				checked = st.check_termination > 0 && (iter % st.check_termination == 0);
@@ -757,8 +882,12 @@ struct Solver {
 					if (rn > rho * st.adaptive_rho_tolerance || rn < rho / st.adaptive_rho_tolerance) {
 						rho = rn;
 						set_rho_vec();
+						for (int i = tm.tid; i < m; i += tm.nthreads) w.zt[i] = w.rho_vec[i] * z[i] - w.y[i];
 						rho_updates++;
-						if (!factor()) {
+						t0 = now_ns();
+						const bool fk = factor();
+						t_factor += now_ns() - t0;
+						if (!fk) {
 							status = ST_NON_CVX;
 							break;
 						}
@@ -777,7 +906,9 @@ struct Solver {
 				}
 				xf = x;
 				if (st.polish && status == ST_SOLVED) {
+					t0 = now_ns();
 					const bool ok = polish(x, z, w.y, r, n_active);
+					t_polish = now_ns() - t0;
 					polish_state = ok ? 1 : -1;
 					if (ok) xf = w.xp;
 				}
@@ -792,6 +923,11 @@ struct Solver {
 				pb.info[1] = rho_updates;
 				pb.info[2] = polish_state;
 				pb.info[3] = n_active;
+				const unsigned long long t_all = now_ns() - t_loop0;
+				pb.info[4] = (int32_t)(t_scale / 1000);
+				pb.info[5] = (int32_t)(t_factor / 1000);
+				pb.info[6] = (int32_t)((t_all - t_factor - t_polish) / 1000);
+				pb.info[7] = (int32_t)(t_polish / 1000);
 			}
 		}
 		tm.sync();

@@ -312,11 +312,12 @@ int32_t asif_engine_last_qp_iterations(asif_engine *e, uint64_t *rows_processed)
  *            eps_abs = eps_rel = 1e-8 (csrc/qp_admm.cuh); nv <= 1024, nc <= 4096; solution is NaN where OSQP
  *            returns none.  asif_qp_configure changes its accuracy settings (process-wide; arguments <= 0 / < 0
  *            restore the defaults 1e-8, 20000, polish on, 10 refinement steps); asif_qp_last_info returns
- *            {ADMM iterations, rho updates, polish 1 accepted / -1 rejected / 0 not run, active rows} of the
- *            first problem of the calling thread's last ASIF_MEM_HOST call.
+ *            {ADMM iterations, rho updates, polish 1 accepted / -1 rejected / 0 not run, active rows, and the
+ *            microseconds spent in equilibration, factorisations, iterations, polish} of the first problem of
+ *            the calling thread's last ASIF_MEM_HOST call.
  */
 int32_t asif_qp_configure(double eps_abs_rel, int32_t max_iter, int32_t polish, int32_t polish_refine_iter);
-int32_t asif_qp_last_info(int32_t info[4]);
+int32_t asif_qp_last_info(int32_t info[8]);
 #define ASIF_QP_SHARED_H 1      /* one H for all problems */
 #define ASIF_QP_SHARED_BOUNDS 2 /* one lb/ub for all problems */
 int32_t asif_qp_solve_batch(int32_t device, int32_t nv, int32_t nc, int64_t n, int32_t diagonal_cost,

@@ -17,12 +17,15 @@ namespace {
 struct HostTeam {
 	static constexpr int LANES = 1;
 	int tid = 0, nthreads = 1, lane = 0, warp = 0, nwarps = 1;
+	std::vector<double> scratch_;
+	double *warp_scratch() { return scratch_.data(); }
 	void sync() {}
 	void warp_sync() {}
+	double warp_bcast(double v, int) const { return v; }
 	double warp_sum(double v) const { return v; }
 	double warp_max(double v) const { return v; }
 };
-int32_t g_info[4] = {0, 0, 0, 0};
+int32_t g_info[qpadmm::NINFO] = {0};
 } // namespace
 
 extern "C" {
@@ -57,7 +60,9 @@ int32_t asif_qp_solve_batch(int32_t, int32_t nv, int32_t nc, int64_t n, int32_t 
 		pb.status = &stt;
 		pb.info = g_info;
 		HostTeam tm;
-		qpadmm::Solver<HostTeam> s(tm, st, nv, nc, qpadmm::carve(ws.data(), nv, nc));
+		tm.scratch_.resize(nv + 2);
+		const qpadmm::Work wk = qpadmm::carve(ws.data(), nv, nc);
+		qpadmm::Solver<HostTeam> s(tm, st, nv, nc, wk);
 		s.solve(pb);
 		status[k] = (stt == qpadmm::ST_SOLVED || stt == qpadmm::ST_SOLVED_INACCURATE) ? 1 : stt;
 		if (getenv("HOSTEMU_TRACE"))
