@@ -80,17 +80,23 @@ struct BatchArgs {
 	int32_t *status, *info;
 	double *work;
 	size_t work_stride; // doubles per cluster
+	int32_t near_in_smem; // one-CTA teams: the near part of the workspace (everything but the KKT factor) is in shared memory
+	int32_t scratch_len;  // doubles of warp scratch per warp
 };
 
 __global__ void __launch_bounds__(QA_THREADS, 1) qp_admm_kernel(const __grid_constant__ BatchArgs a, const __grid_constant__ qpadmm::Settings st)
 {
 	extern __shared__ double qa_smem[];
-	ClusterTeam tm(qa_smem, (a.nv + 1) & ~1);
+	ClusterTeam tm(qa_smem, a.scratch_len);
 	cg::cluster_group cl = cg::this_cluster();
 	const unsigned csize = cl.num_blocks();
 	const int64_t cluster_id = blockIdx.x / csize, n_clusters = gridDim.x / csize;
 	__shared__ qpadmm::Work w;
-	if (threadIdx.x == 0) w = qpadmm::carve(a.work + (size_t)cluster_id * a.work_stride, a.nv, a.nc);
+	if (threadIdx.x == 0) {
+		double *glob = a.work + (size_t)cluster_id * a.work_stride;
+		if (a.near_in_smem) w = qpadmm::carve(qa_smem + (size_t)a.scratch_len * (QA_THREADS / 32), glob, a.nv, a.nc, QA_THREADS / 32);
+		else w = qpadmm::carve(glob, a.nv, a.nc);
+	}
 	__syncthreads();
 	for (int64_t k = cluster_id; k < a.n; k += n_clusters) {
 		qpadmm::Problem pb;
@@ -174,8 +180,13 @@ int launch_qp_admm(int device, int nv, int nc, int64_t n, int diag_cost, const d
 	attr[0].val.clusterDim.y = 1;
 	attr[0].val.clusterDim.z = 1;
 	lc.blockDim = dim3(QA_THREADS);
-	lc.dynamicSmemBytes = sizeof(double) * (size_t)((nv + 1) & ~1) * (QA_THREADS / 32); // one column per warp (Solver::factor)
-	QA_CUDA_TRY(cudaFuncSetAttribute(qp_admm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lc.dynamicSmemBytes));
+	const int scratch_len = (nv + 2) & ~1; // one column per warp (Solver::factor)
+	size_t smem = sizeof(double) * (size_t)scratch_len * (QA_THREADS / 32);
+	const size_t near_bytes = sizeof(double) * qpadmm::work_near_doubles(nv, nc, QA_THREADS / 32);
+	const bool near_in_smem = csize == 1 && smem + near_bytes <= 200 * 1024 && !getenv("ASIF_B200_QP_NO_SMEM");
+	if (near_in_smem) smem += near_bytes;
+	lc.dynamicSmemBytes = smem;
+	QA_CUDA_TRY(cudaFuncSetAttribute(qp_admm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
 	lc.stream = st;
 	lc.attrs = attr;
 	lc.numAttrs = 1;
@@ -202,6 +213,8 @@ int launch_qp_admm(int device, int nv, int nc, int64_t n, int diag_cost, const d
 	a.info = (int32_t *)tl_info.p;
 	a.work = (double *)tl_work.p;
 	a.work_stride = stride;
+	a.near_in_smem = near_in_smem ? 1 : 0;
+	a.scratch_len = scratch_len;
 	lc.gridDim = dim3((unsigned)(n_clusters * csize));
 	QA_CUDA_TRY(cudaLaunchKernelEx(&lc, qp_admm_kernel, a, cfg));
 	QA_CUDA_TRY(cudaGetLastError());

@@ -117,41 +117,51 @@ struct Work {
 	double *l, *u, *E, *Einv, *rho_vec, *rho_inv, *z0, *z1, *y, *zt, *dy, *Et, *Ax, *tmpm, *yp, *zp;
 	// length-N (= n + m) vectors of the polish
 	double *prhs, *psol, *pres, *tcol, *pd;
-	double *red; // 2 x NRED x MAX_TEAM_WARPS
+	double *red; // 2 x NRED x red_stride (>= the team's warps)
+	int32_t red_stride;
 	int32_t *ctype, *rows, *ints; // ints[0] = n_low, ints[1] = na, ints[2] = failure flag of the factorisation
 };
 
-QA_FN size_t work_doubles(int n, int mA)
+// The workspace has two parts: the polish's KKT factor (LR, LC: 2 (2n + nc)^2 doubles), which always lives in global
+// memory, and everything else ("near" part: P, A in both orientations, K, its inverse, every vector), which a
+// one-CTA team keeps in SHARED memory when it fits (the 38-variable problem: 117 KB) - the phases of a small problem are
+// chains of dependent loads, and the vectors one phase writes are exactly what the next one reads.
+QA_FN size_t work_far_doubles(int n, int mA)
+{
+	const size_t N = (size_t)2 * n + mA;
+	return 2 * N * N + 8;
+}
+QA_FN size_t work_near_doubles(int n, int mA, int team_warps)
 {
 	const size_t m = (size_t)mA + n, N = (size_t)n + m;
 	size_t d = 0;
-	d += (size_t)n * n * 4;        // P, K, Xinv, Kinv
-	d += (size_t)mA * n * 2;       // A, At
-	d += N * N * 2;                // LR, LC
-	d += (size_t)n * 15 + m * 16 + N * 8; // tcol holds N x PB (= 4) doubles
-	d += 2 * NRED * MAX_TEAM_WARPS;
-	d += (2 * m + 8 + 1) / 2 + 2;  // ints
-	return d + 256;                // alignment slack (every vector is rounded up to 16 bytes)
+	d += (size_t)n * n * 4;                // P, K, Xinv, Kinv
+	d += (size_t)mA * n * 2;               // A, At
+	d += (size_t)n * 15 + m * 16 + N * 8;  // tcol holds N x PB (= 4) doubles
+	d += 2 * NRED * (size_t)team_warps;
+	d += (2 * m + 8 + 1) / 2 + 2;          // ints
+	return d + 128;                        // every array is rounded up to 16 bytes
 }
+QA_FN size_t work_doubles(int n, int mA) { return work_near_doubles(n, mA, MAX_TEAM_WARPS) + work_far_doubles(n, mA); }
 
-QA_FN Work carve(double *base, int n, int mA)
+QA_FN Work carve(double *near_base, double *far_base, int n, int mA, int team_warps)
 {
 	const size_t m = (size_t)mA + n, N = (size_t)n + m;
 	Work w;
-	double *p = base;
+	double *p = near_base;
 	auto take = [&](size_t k) {
 		double *r = p;
 		p += (k + 1) & ~(size_t)1; // keep 16-byte alignment
 		return r;
 	};
+	w.LR = far_base;
+	w.LC = far_base + ((N * N + 1) & ~(size_t)1);
 	w.P = take((size_t)n * n);
 	w.K = take((size_t)n * n);
 	w.Xinv = take((size_t)n * n);
 	w.Kinv = take((size_t)n * n);
 	w.A = take((size_t)mA * n);
 	w.At = take((size_t)mA * n);
-	w.LR = take(N * N);
-	w.LC = take(N * N);
 	w.q = take(n); w.D = take(n); w.Dinv = take(n); w.Ib = take(n); w.x0 = take(n); w.x1 = take(n); w.xt = take(n);
 	w.dx = take(n); w.rhs = take(n); w.Dt = take(n); w.pcol = take(n); w.Px = take(n); w.Aty = take(n); w.xp = take(n);
 	w.kd = take(n);
@@ -159,11 +169,17 @@ QA_FN Work carve(double *base, int n, int mA)
 	w.z0 = take(m); w.z1 = take(m); w.y = take(m); w.zt = take(m); w.dy = take(m); w.Et = take(m); w.Ax = take(m);
 	w.tmpm = take(m); w.yp = take(m); w.zp = take(m);
 	w.prhs = take(N); w.psol = take(N); w.pres = take(N); w.tcol = take(N * 4); w.pd = take(N);
-	w.red = take(2 * NRED * MAX_TEAM_WARPS);
+	w.red = take(2 * NRED * (size_t)team_warps);
+	w.red_stride = team_warps;
 	w.ctype = (int32_t *)p;
 	w.rows = w.ctype + m;
 	w.ints = w.rows + m;
 	return w;
+}
+// one block of global memory for both parts
+QA_FN Work carve(double *base, int n, int mA)
+{
+	return carve(base + ((work_far_doubles(n, mA) + 1) & ~(size_t)1), base, n, mA, MAX_TEAM_WARPS);
 }
 
 // ---- the solver -----------------------------------------------------------------------------------------------------
@@ -186,12 +202,13 @@ struct Solver {
 	// -- team reduction of NRED values; bit k of summask: sum, else max.  Every thread returns the same bits.
 	QA_FN void reduce(double (&v)[NRED], unsigned summask)
 	{
-		double *slot = w.red + (size_t)red_slot * NRED * MAX_TEAM_WARPS;
+		const int rs = w.red_stride;
+		double *slot = w.red + (size_t)red_slot * NRED * rs;
 		red_slot ^= 1;
 #pragma unroll
 		for (int k = 0; k < NRED; k++) {
 			const double r = ((summask >> k) & 1u) ? tm.warp_sum(v[k]) : tm.warp_max(v[k]);
-			if (tm.lane == 0) slot[k * MAX_TEAM_WARPS + tm.warp] = r;
+			if (tm.lane == 0) slot[k * rs + tm.warp] = r;
 		}
 		tm.sync();
 #pragma unroll
@@ -199,7 +216,7 @@ struct Solver {
 			const bool sum = (summask >> k) & 1u;
 			double a = sum ? 0.0 : -INFINITY;
 			for (int i = tm.lane; i < tm.nwarps; i += T::LANES) {
-				const double e = slot[k * MAX_TEAM_WARPS + i];
+				const double e = slot[k * rs + i];
 				a = sum ? a + e : fmax(a, e);
 			}
 			v[k] = sum ? tm.warp_sum(a) : tm.warp_max(a);
