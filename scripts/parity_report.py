@@ -357,6 +357,27 @@ def main():
             compare(names[k], "vs_reference", (u[:m], relax[:m], rc[:m]), (ur, rr, rcr), arbiter=(u0[:m], relax0[:m], rc0[:m]), qp_status=st,
                     relax_cols=rcols, note="reference build = unmodified sources + OSQP-algorithm stand-in (eps 1e-8, polish, cold start)")
         eng.close()
+        # ---- the reference's OWN class on ASIF::QPWrapperB200 (nv > 4: csrc/qp_admm.cuh), state by state -----------------
+        if k in ("C3b", "C4") and k in ref and os.path.exists(pyref.REF_B200_SO):
+            ur, rr, rcr, st = ref[k]
+            mw = min(len(rcr), sz(320) if k == "C3b" else sz(5000))
+            RB = pyref.RefLib(pyref.REF_B200_SO)
+            RB.set_qp_mode()
+            RB.select_backend(1)
+            fw = RB.create(cfg, opts)
+            RB.select_backend(0)
+            t0 = time.time()
+            uw, rw, rcw = fw.filter_batch(x[:mw], ud[:mw])
+            per_call = (time.time() - t0) / mw
+            rw = np.asarray(rw).reshape(mw, -1)
+            nm = names[k] + ": the reference's own class on QPWrapperB200 (%d-variable QP, cluster solver), %.2f ms per filter()" % (
+                402 if k == "C3b" else 38, per_call * 1e3)
+            compare(nm, "vs_oracle", (uw, rw, rcw), (u0[:mw], relax0[:mw], rc0[:mw]), relax_cols=rcols,
+                    note="this backend IS the OSQP algorithm (ADMM to eps 1e-8 + polish), so it shares the OSQP stand-in's deviations from the "
+                         "exact optimum on degenerate states; the statement for it is the vs_reference leg")
+            compare(nm, "vs_reference", (uw, rw, rcw), (ur[:mw], rr[:mw], rcr[:mw]), arbiter=(u0[:mw], relax0[:mw], rc0[:mw]),
+                    qp_status=st[:mw], relax_cols=rcols,
+                    note="same unmodified class, QP backend switched: OSQP-algorithm stand-in (CPU) vs QPWrapperB200 (GPU)")
 
     if not do_cost and not do_roll:
         sys.stderr.write("parity report: %.0f s\n" % (time.time() - t_start))
