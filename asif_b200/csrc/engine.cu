@@ -618,12 +618,14 @@ int32_t asif_engine_create(const asif_engine_config *cfg, asif_engine **out)
 		p.npSSmax = nb;
 		const size_t bV = sizeof(double) * 2 * nV, bN = sizeof(double) * 2 * nF, bL = sizeof(double) * 4 * nF * mA;
 		const size_t bFV = sizeof(int32_t) * 2 * nF, bFA = sizeof(int32_t) * nF * mA;
-		e->rz_smem = bV + bN + bL + bFV + bFA;
-		if (e->rz_smem > 96 * 1024) {
+		const size_t bTable = bV + bN + bL + bFV + bFA;
+		// + the per-thread slot lists of the critical-facet rows (realizable_kernel.cuh)
+		e->rz_smem = bTable + sizeof(uint16_t) * RZ_MAX_CRIT * RZ_MAX_ACT * RZ_THREADS;
+		if (e->rz_smem > 96 * 1024 || (size_t)nF * mA > 65535) {
 			delete e;
 			return fail(ASIF_ERR_UNSUPPORTED, "polytope kernel too large for the shared-memory staging (%zu B)", e->rz_smem);
 		}
-		cudaError_t te = cudaMalloc(&e->d_kernel, e->rz_smem);
+		cudaError_t te = cudaMalloc(&e->d_kernel, bTable);
 		char *base = (char *)e->d_kernel;
 		if (te == cudaSuccess) te = cudaMemcpy(base, cfg->kernel_vertices, bV, cudaMemcpyHostToDevice);
 		if (te == cudaSuccess) te = cudaMemcpy(base + bV, cfg->facet_normals, bN, cudaMemcpyHostToDevice);

@@ -45,8 +45,13 @@ struct RealizableRows {
 #define ASIF_RZ_SCAN_INDEX_ONLY 1 // C4 0.853 -> 0.828 ms per 1e6 states
 #endif
 	static constexpr bool SCAN_INDEX_ONLY = ASIF_RZ_SCAN_INDEX_ONLY != 0; // qp_gi.cuh
-	double lgLo[RZ_MAX_CRIT * RZ_MAX_ACT], lgHi[RZ_MAX_CRIT * RZ_MAX_ACT], rhs[RZ_MAX_CRIT * RZ_MAX_ACT];
+	// The facet rows are NOT stored per state: a slot is the index of its entry [LfLo, LfHi, LgLo, LgHi] in the shared-memory
+	// facet table (16 bits, list [slot][thread] in shared memory), and the solver's scans read the three numbers from the
+	// table.  (Round 1 kept 3 x 32 doubles per thread, dynamically indexed: a 1 KB stack frame, 242 registers, 8 warps/SM.)
+	const double *lie;    // shared-memory facet table, 4 doubles per (facet, active constraint)
+	const uint16_t *slot; // this thread's list, stride RZ_THREADS
 	int nslots;
+	__device__ __forceinline__ const double *entry(const int s) const { return lie + 4 * (int)slot[s * RZ_THREADS]; }
 	double barL[RZ_MAX_BAR], barB[RZ_MAX_BAR];
 	int nbar;
 	double lb[NV], ub[NV];
@@ -55,10 +60,12 @@ struct RealizableRows {
 	__device__ __forceinline__ void scan(F &&fn, FB &&fb) const
 	{
 		for (int s = 0; s < nslots; s++) {
-			double n[NV] = {lgLo[s], 0.0};
-			fn(2 * s, n, rhs[s]);
-			n[0] = lgHi[s];
-			fn(2 * s + 1, n, rhs[s]);
+			const double *t = entry(s);
+			double n[NV] = {t[2], 0.0};
+			const double r = -t[0];
+			fn(2 * s, n, r);
+			n[0] = t[3];
+			fn(2 * s + 1, n, r);
 		}
 		for (int i = 0; i < nbar; i++) {
 			const double n[NV] = {barL[i], 1.0};
@@ -74,8 +81,9 @@ struct RealizableRows {
 	{
 		const bool lower = v[0] >= 0.0;
 		for (int s = 0; s < nslots; s++) {
-			const double n[NV] = {lower ? lgLo[s] : lgHi[s], 0.0};
-			fn(2 * s + (lower ? 0 : 1), n, rhs[s]);
+			const double *t = entry(s);
+			const double n[NV] = {lower ? t[2] : t[3], 0.0};
+			fn(2 * s + (lower ? 0 : 1), n, -t[0]);
 		}
 		for (int i = 0; i < nbar; i++) {
 			const double n[NV] = {barL[i], 1.0};
@@ -99,10 +107,10 @@ struct RealizableRows {
 			n[1] = 1.0;
 			r = barB[j - 2 * nslots];
 		} else {
-			const int s = j >> 1;
-			n[0] = (j & 1) ? lgHi[s] : lgLo[s];
+			const double *t = entry(j >> 1);
+			n[0] = (j & 1) ? t[3] : t[2];
 			n[1] = 0.0;
-			r = rhs[s];
+			r = -t[0];
 		}
 	}
 };
@@ -116,7 +124,10 @@ __device__ __forceinline__ void qp_scan_rows(const RealizableRows &rows, const d
 // diag: [nCrit, critFacet[max_crit] (-1 absent), barrierFacet[npSSmax], per slot LgLo, LgHi, LfLo, LfHi, per barrier row Lgh, b]
 template <bool WITH_DIAG>
 #ifndef RZ_MIN_BLOCKS
-#define RZ_MIN_BLOCKS 1 // 238 registers, 8 warps/SM; forcing 3 / 4 / 5 CTAs spills the facet pass: 0.853 -> 0.884 / 1.09 / 1.65 ms per 1e6 C4 states
+// Round 1 / early round 2: rows stored per thread, 242 registers, 8 warps/SM, 0.81 ms per 1e6 C4 states (forcing occupancy
+// spilled the facet pass: 0.884 / 1.09 / 1.65 ms at 3 / 4 / 5 CTAs).  With the rows read from the shared-memory table through a
+// slot list: 134 registers; 1 / 4 / 5 / 6 CTAs per SM = 0.547 / 0.454 / 0.407 / 0.399 ms (profiles/experiments/r02_ab_c4_slots.txt)
+#define RZ_MIN_BLOCKS 6
 #endif
 __global__ void __launch_bounds__(RZ_THREADS, RZ_MIN_BLOCKS)
 realizable_ip_filter_kernel(const RealizableParams p, const int64_t n, const double *__restrict__ x_in,
@@ -130,6 +141,7 @@ realizable_ip_filter_kernel(const RealizableParams p, const int64_t n, const dou
 	double *sLie = sN + 2 * nF;      // [nF][mA][4]
 	int32_t *sFV = (int32_t *)(sLie + 4 * nF * mA); // [nF][2]
 	int32_t *sFA = sFV + 2 * nF;                     // [nF][mA]
+	uint16_t *sSlot = (uint16_t *)(sFA + nF * mA) + threadIdx.x; // [RZ_MAX_CRIT * RZ_MAX_ACT][RZ_THREADS]: slot lists
 	for (int i = threadIdx.x; i < 2 * nV; i += blockDim.x) sV[i] = p.vertices[i];
 	for (int i = threadIdx.x; i < 2 * nF; i += blockDim.x) {
 		sN[i] = p.normals[i];
@@ -215,6 +227,8 @@ realizable_ip_filter_kernel(const RealizableParams p, const int64_t n, const dou
 	// barrier keys only hold the first nb entries
 	// (iii) rows from the facet table
 	RealizableRows R;
+	R.lie = sLie;
+	R.slot = sSlot;
 	R.nslots = 0;
 	R.nbar = nb;
 #pragma unroll
@@ -223,15 +237,7 @@ realizable_ip_filter_kernel(const RealizableParams p, const int64_t n, const dou
 			const int fc = crit[c];
 			for (int j = 0; j < mA; j++) {
 				if (sFA[mA * fc + j] < 0) continue;
-				const double *t = sLie + 4 * (mA * fc + j);
-#pragma unroll
-				for (int s = 0; s < RZ_MAX_CRIT * RZ_MAX_ACT; s++) {
-					if (s == R.nslots) {
-						R.lgLo[s] = t[2];
-						R.lgHi[s] = t[3];
-						R.rhs[s] = -t[0];
-					}
-				}
+				sSlot[R.nslots * RZ_THREADS] = (uint16_t)(mA * fc + j);
 				R.nslots++;
 			}
 		}
