@@ -328,13 +328,24 @@ struct SegwayTB {
 #ifndef ASIF_SEGWAY_COMPACT
 #define ASIF_SEGWAY_COMPACT 1
 #endif
+#ifndef ASIF_SEGWAY_DOUBLE_ANGLE
+#define ASIF_SEGWAY_DOUBLE_ANGLE 1 // sin 2t, cos 2t from sin t, cos t: C5 9.86 -> 9.38 ms, rows 1.25e-10 -> 1.30e-10 off the oracle
+#endif
+#ifndef ASIF_SEGWAY_TANH_FAST
+#define ASIF_SEGWAY_TANH_FAST 0 // measured neutral (9.353 vs 9.327 ms per 1e6 C5 states): CUDA's tanh has its own early exit
+#endif
 	// sin/cos of theta and 2 theta are shared by f, g and their gradients: one sincos pair per evaluation point
 	static constexpr bool HAS_DYNAMICS_ALL = true;
 	__device__ static void dynamics_all(const double *x, double *f, double *g, double *Df, double *Dg)
 	{
 		double s1, c1, s2, c2;
 		sincos_model(x[2], &s1, &c1);
+#if ASIF_SEGWAY_DOUBLE_ANGLE
+		s2 = 2.0 * s1 * c1;
+		c2 = fma(-2.0 * s1, s1, 1.0);
+#else
 		sincos_model(2.0 * x[2], &s2, &c2);
+#endif
 #if ASIF_SEGWAY_COMPACT
 		all_compact(x, s1, c1, s2, c2, f, g, Df, Dg);
 #else
@@ -379,8 +390,16 @@ struct SegwayTB {
 		g[1] = ((E0 + E1 * c1) + E2 * s1) * ginv;
 		g[2] = 0.0;
 		g[3] = ((F0 + F1 * c1) + F2 * s1) * den;
-		// gradients; t23 of the generated code is -den
-		const double th = tanh(x[1] * 1000.0);
+		// gradients; t23 of the generated code is -den.  tanh(1000 v): |argument| >= 20 rounds to +-1 exactly in double
+		// (1 - tanh 20 = 8.5e-18 < half an ulp of 1, in glibc and in CUDA alike), which is every state whose wheel speed is
+		// not within 0.02 of zero: those lanes skip the library call
+		const double tz = x[1] * 1000.0;
+#if ASIF_SEGWAY_TANH_FAST
+		double th = copysign(1.0, tz);
+		if (fabs(tz) < 20.0) th = tanh(tz);
+#else
+		const double th = tanh(tz);
+#endif
 		const double q = th * th - 1.0;
 		const double t25 = th * 15.13175750513302 - 40.918271887954823;
 		const double t26s = w2 * (3.3849959169972448 * 0.0975) + th * (30.26351501026604 * 0.0975);

@@ -314,7 +314,40 @@ def all_config_legs(torch, ab, dev, device_index, p64, hbm_peak):
                  "roofline": {"bound": "fp64", "flops_per_state": fl, "achieved_tflops": fl * n * steps / sec / 1e12,
                               "frac": fl * n * steps / sec / 1e12 / p64}})
     e.close()
+    legs[-2]["note"] += ("; credited = the operation count of the reference's generated model expressions (SURVEY 8d); the kernel "
+                         "evaluates them in collected form (literals folded per monomial, two reciprocals instead of seven)")
+    legs.extend(qp_backend_legs(ab, device_index))
     return legs
+
+
+def qp_backend_legs(ab, device_index):
+    """The QPWrapper backend for nv > 4 (csrc/qp_admm.cuh): batches of synthetic QPs with a semi-definite Hessian (only a
+    quarter of the variables carry cost, the rest are LP directions inside a box), through asif_qp_solve_batch with host arrays."""
+    from asif_b200 import capi
+    out = []
+    for nv, nc, n, label in ((40, 60, 296, "one CTA per problem, workspace in shared memory"),
+                             (400, 300, 18, "one 8-CTA cluster per problem (the size of ASIFrobust's LP-dual QP)")):
+        g = np.random.Generator(np.random.Philox(key=1234 + nv))
+        Hd = np.zeros(nv)
+        Hd[:nv // 4] = g.uniform(0.5, 20.0, nv // 4)
+        c = g.normal(0, 3, (n, nv))
+        A = g.normal(0, 1, (n, nc, nv))
+        A[g.random((n, nc, nv)) < 0.8] = 0.0
+        lb, ub = -g.uniform(0.5, 3, nv), g.uniform(0.5, 3, nv)
+        vstar = g.uniform(0.7 * lb, 0.7 * ub, (n, nv))
+        b = np.einsum("kij,kj->ki", A, vstar) - g.exponential(0.5, (n, nc)) * (g.random((n, nc)) < 0.7)
+        ab.qp_solve_batch(np.diag(Hd), c[:2], A[:2], b[:2], lb, ub, device=device_index)  # warm-up: allocations
+        t0 = time.perf_counter()
+        sol, st = ab.qp_solve_batch(np.diag(Hd), c, A, b, lb, ub, device=device_index)
+        sec = time.perf_counter() - t0
+        info = capi.qp_last_info()
+        out.append({"config": "QPWrapper backend, nv = %d, nc = %d, %d problems (%s)" % (nv, nc, n, label), "problems": n,
+                    "seconds": sec, "problems_per_s": n / sec, "ms_per_problem_if_serial": 1e3 * sec / n,
+                    "status_histogram": {int(k): int(v) for k, v in zip(*np.unique(st, return_counts=True))},
+                    "first_problem": {"admm_iterations": info[0], "rho_updates": info[1], "polish": info[2], "active_rows": info[3],
+                                      "us_equilibrate_factor_iterate_polish": list(info[4:8])},
+                    "note": "wall clock through the C ABI with host arrays (copies included); eps 1e-8 + polish"})
+    return out
 
 
 def copy_ceiling(torch, dev, n):
