@@ -202,7 +202,8 @@ inline int acquire_scratch(asif_engine *e, const size_t need, cudaStream_t st, i
 // nx = 4: persistent grid over a global snapshot scratch; the grid is the largest one that fits the SMs, shrunk so
 // that every CTA runs the same number of tiles (no ragged last wave).
 template <class M, int NPBTSS>
-int tb_geometry(asif_engine *e, int64_t n, cudaStream_t st, unsigned &blocks, size_t &smem, double *&gsnap, int &buf)
+int tb_geometry(asif_engine *e, int64_t n, cudaStream_t st, unsigned &blocks, size_t &smem, double *&gsnap, int &buf,
+                const int per_sm = tb_min_blocks<M>())
 {
 	const int64_t tiles = (n + TB_THREADS - 1) / TB_THREADS;
 	const size_t per_cta = sizeof(double) * tb_smem_doubles_per_thread<M, NPBTSS>() * TB_THREADS;
@@ -213,7 +214,7 @@ int tb_geometry(asif_engine *e, int64_t n, cudaStream_t st, unsigned &blocks, si
 		smem = per_cta;
 		return ASIF_OK;
 	}
-	const int64_t resident = (int64_t)e->num_sms * tb_min_blocks<M>();
+	const int64_t resident = (int64_t)e->num_sms * per_sm;
 	const int64_t rounds = (tiles + resident - 1) / resident;
 	blocks = (unsigned)((tiles + rounds - 1) / rounds);
 	if (blocks < 1) blocks = 1;
@@ -284,7 +285,7 @@ int launch_tb_rollout(asif_engine *e, int64_t n, int32_t steps, double dt, doubl
 	size_t smem;
 	double *gsnap;
 	int buf;
-	int r = tb_geometry<M, NPBTSS>(e, n, st, blocks, smem, gsnap, buf);
+	int r = tb_geometry<M, NPBTSS>(e, n, st, blocks, smem, gsnap, buf, tb_rollout_min_blocks<M>());
 	if (r) return r;
 	auto k = (e->tb.sat_mode >= SAT_POW2) ? tb_rollout_kernel<M, NPBTSS, SAT_POW2> : tb_rollout_kernel<M, NPBTSS, SAT_GENERAL>;
 	r = set_smem(k, smem);

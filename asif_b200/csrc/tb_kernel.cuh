@@ -539,6 +539,17 @@ __host__ __device__ constexpr int tb_min_blocks()
 {
 	return M::NX <= 2 ? ASIF_TB_MINBLOCKS_NX2 : ASIF_TB_MINBLOCKS_NX4;
 }
+// the fused rollout kernel carries the plant state and the loop bookkeeping on top of the filter: at 168 registers (3 CTAs per
+// SM) the 1e5-agent fleet of BASELINE config 5 runs in 1.11 s against 1.20 s at 128 (its 782 tiles fill 2.6 CTAs per SM either
+// way); a fleet large enough to fill the SM would lose ~1.5 % (measured on the filter kernel: 9.47 vs 9.33 ms per 1e6 states)
+#ifndef ASIF_TB_ROLLOUT_MINBLOCKS_NX4
+#define ASIF_TB_ROLLOUT_MINBLOCKS_NX4 3
+#endif
+template <class M>
+__host__ __device__ constexpr int tb_rollout_min_blocks()
+{
+	return M::NX <= 2 ? ASIF_TB_MINBLOCKS_NX2 : ASIF_TB_ROLLOUT_MINBLOCKS_NX4;
+}
 
 // Where the critical-point snapshots live.  nx = 2: shared memory (30 doubles per thread).  nx = 4: 100 doubles per
 // thread would cap the SM at 8 warps, and the FP64 pipe then idles on dependent-issue latency (ncu: issue slots 54 %
@@ -649,7 +660,7 @@ tb_filter_kernel(const TbParams p, const int64_t n, const double *__restrict__ x
 // Closed-loop rollout (examples/segway_implicit_tb.cpp:251-283): the state never leaves the
 // registers between control steps; one launch covers all steps of every agent.
 template <class M, int NPBTSS, int SATMODE>
-__global__ void __launch_bounds__(TB_THREADS, tb_min_blocks<M>())
+__global__ void __launch_bounds__(TB_THREADS, tb_rollout_min_blocks<M>())
 tb_rollout_kernel(const TbParams p, const int64_t n, const int32_t steps, const double dt_plant, double *__restrict__ x_io,
                   const double *__restrict__ u_des, double *__restrict__ u_act_last, int32_t *__restrict__ rc_last,
                   unsigned long long *__restrict__ rc_hist, unsigned long long *__restrict__ qp_iter_sum, double *__restrict__ gsnap)
