@@ -35,10 +35,13 @@ struct ClusterTeam {
 	int tid, nthreads, lane, warp, nwarps;
 	bool single;
 	double *scratch; // this warp's slice of the CTA's dynamic shared memory (scratch_len doubles)
+	int slen;
 	__device__ __forceinline__ double *warp_scratch() const { return scratch; }
+	__device__ __forceinline__ int scratch_len() const { return slen; }
 	__device__ __forceinline__ ClusterTeam(double *smem, int scratch_len)
 	{
 		scratch = smem + (size_t)(threadIdx.x >> 5) * scratch_len;
+		slen = scratch_len;
 		cg::cluster_group cl = cg::this_cluster();
 		const unsigned cr = cl.block_rank(), cs = cl.num_blocks();
 		tid = (int)(cr * blockDim.x + threadIdx.x);
@@ -168,32 +171,48 @@ int launch_qp_admm(int device, int nv, int nc, int64_t n, int diag_cost, const d
 	}
 	// small problems: one CTA per problem; large ones: a cluster, so that eight SMs' L2 bandwidth serves the factorisations
 	const size_t mat = (size_t)nv * nv + (size_t)nv * nc;
-	int csize = mat > 16384 ? QA_CLUSTER : 1;
+	// (measured on the 402-variable QP: 2 / 4 / 8 / 16 CTAs = 61 / 35 / 21.7 / see DESIGN ms per solve); 16 needs the non-portable
+	// cluster size and a GPC with 16 free SMs: asked for first, 8 is the fallback
+	int want = mat > 16384 ? (mat > 200000 ? 16 : QA_CLUSTER) : 1;
 	if (const char *e = getenv("ASIF_B200_QP_CLUSTER")) {
 		const int v = atoi(e);
-		if (v == 1 || v == 2 || v == 4 || v == 8) csize = v;
+		if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) want = v;
+	}
+	// warp scratch of Solver::factor: four columns per warp when 16 warps' worth fits beside nothing else (cluster teams), one otherwise
+	const int ld_col = (nv + 2) & ~1;
+	const int scratch_len = (want > 1 && (size_t)4 * ld_col * (QA_THREADS / 32) * sizeof(double) <= 180 * 1024) ? 4 * ld_col : ld_col;
+	// per device, cheap: set at every launch
+	QA_CUDA_TRY(cudaFuncSetAttribute(qp_admm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+	if (want > 8 && cudaFuncSetAttribute(qp_admm_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+		cudaGetLastError();
+		want = 8;
 	}
 	cudaLaunchConfig_t lc = {};
 	cudaLaunchAttribute attr[1];
-	attr[0].id = cudaLaunchAttributeClusterDimension;
-	attr[0].val.clusterDim.x = (unsigned)csize;
-	attr[0].val.clusterDim.y = 1;
-	attr[0].val.clusterDim.z = 1;
-	lc.blockDim = dim3(QA_THREADS);
-	const int scratch_len = (nv + 2) & ~1; // one column per warp (Solver::factor)
-	size_t smem = sizeof(double) * (size_t)scratch_len * (QA_THREADS / 32);
-	const size_t near_bytes = sizeof(double) * qpadmm::work_near_doubles(nv, nc, QA_THREADS / 32);
-	const bool near_in_smem = csize == 1 && smem + near_bytes <= 200 * 1024 && !getenv("ASIF_B200_QP_NO_SMEM");
-	if (near_in_smem) smem += near_bytes;
-	lc.dynamicSmemBytes = smem;
-	QA_CUDA_TRY(cudaFuncSetAttribute(qp_admm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
-	lc.stream = st;
-	lc.attrs = attr;
-	lc.numAttrs = 1;
-	lc.gridDim = dim3((unsigned)csize);
-	int max_clusters = 0;
-	QA_CUDA_TRY(cudaOccupancyMaxActiveClusters(&max_clusters, qp_admm_kernel, &lc));
-	if (max_clusters < 1) return fail(ASIF_ERR_CUDA, "qp_solve_batch: no cluster of %d CTAs fits on this device", csize);
+	int csize = want, max_clusters = 0;
+	size_t smem = 0;
+	bool near_in_smem = false;
+	for (;; csize /= 2) {
+		attr[0].id = cudaLaunchAttributeClusterDimension;
+		attr[0].val.clusterDim.x = (unsigned)csize;
+		attr[0].val.clusterDim.y = 1;
+		attr[0].val.clusterDim.z = 1;
+		smem = sizeof(double) * (size_t)scratch_len * (QA_THREADS / 32);
+		const size_t near_bytes = sizeof(double) * qpadmm::work_near_doubles(nv, nc, QA_THREADS / 32);
+		near_in_smem = csize == 1 && smem + near_bytes <= 200 * 1024 && !getenv("ASIF_B200_QP_NO_SMEM");
+		if (near_in_smem) smem += near_bytes;
+		lc.blockDim = dim3(QA_THREADS);
+		lc.dynamicSmemBytes = smem;
+		lc.stream = st;
+		lc.attrs = attr;
+		lc.numAttrs = 1;
+		lc.gridDim = dim3((unsigned)csize);
+		max_clusters = 0;
+		const cudaError_t qe = cudaOccupancyMaxActiveClusters(&max_clusters, qp_admm_kernel, &lc);
+		if (qe == cudaSuccess && max_clusters >= 1) break;
+		cudaGetLastError();
+		if (csize == 1) return fail(ASIF_ERR_CUDA, "qp_solve_batch: the solver kernel does not fit on this device (%s)", cudaGetErrorString(qe));
+	}
 	const int64_t n_clusters = n < max_clusters ? n : max_clusters;
 	const size_t stride = (qpadmm::work_doubles(nv, nc) + 31) & ~(size_t)31;
 	int r = ensure(tl_work, device, stride * sizeof(double) * (size_t)n_clusters);

@@ -557,46 +557,89 @@ struct Solver {
 	// -- K = P + sigma I + [A;I]' R [A;I], factored and inverted explicitly; false when K is not positive definite
 	QA_FN bool factor()
 	{
-		for (size_t p = tm.warp; p < (size_t)n * n; p += tm.nwarps) {
-			const int a = (int)(p / n), b = (int)(p % n);
-			if (b > a) continue;
-			const double *ca = w.A + (size_t)a * mA, *cb = w.A + (size_t)b * mA;
-			double s = 0.0;
-			for (int i = tm.lane; i < mA; i += T::LANES) s = fma(ca[i] * w.rho_vec[i], cb[i], s);
-			s = tm.warp_sum(s);
-			if (tm.lane == 0) {
-				double v = w.P[(size_t)a * n + b] + s;
-				if (a == b) v += st.sigma + w.Ib[a] * w.Ib[a] * w.rho_vec[mA + a];
-				w.K[(size_t)a * n + b] = v;
-				w.K[(size_t)b * n + a] = v;
+		// lower triangle of A'RA, a warp per column a, four columns b at a time sharing the loads of R a
+		for (int a = tm.warp; a < n; a += tm.nwarps) {
+			const double *ca = w.A + (size_t)a * mA;
+			for (int b0 = 0; b0 <= a; b0 += 4) {
+				const double *cb[4];
+				double s[4];
+#pragma unroll
+				for (int r = 0; r < 4; r++) {
+					cb[r] = w.A + (size_t)(b0 + r <= a ? b0 + r : a) * mA;
+					s[r] = 0.0;
+				}
+				for (int i = tm.lane; i < mA; i += T::LANES) {
+					const double t = ca[i] * w.rho_vec[i];
+#pragma unroll
+					for (int r = 0; r < 4; r++) s[r] = fma(t, cb[r][i], s[r]);
+				}
+#pragma unroll
+				for (int r = 0; r < 4; r++) s[r] = tm.warp_sum(s[r]);
+				if (tm.lane == 0) {
+#pragma unroll
+					for (int r = 0; r < 4; r++) {
+						const int b = b0 + r;
+						if (b <= a) {
+							double v = w.P[(size_t)a * n + b] + s[r];
+							if (a == b) v += st.sigma + w.Ib[a] * w.Ib[a] * w.rho_vec[mA + a];
+							w.K[(size_t)a * n + b] = v;
+							w.K[(size_t)b * n + a] = v;
+						}
+					}
+				}
 			}
 		}
 		for (size_t e = tm.tid; e < (size_t)n * n; e += tm.nthreads) w.Xinv[e] = 0.0;
 		tm.sync();
 		if (!ldl_factor(w.K, nullptr, w.kd, w.tcol, n, true)) return false;
 		for (int i = tm.tid; i < n; i += tm.nthreads) w.pcol[i] = 1.0 / w.kd[i];
-		// X = L^-1 (X[i][j] at Xinv[i*n + j]): one warp per column j, the column under construction in the warp's scratch
-		// (shared memory), every row one coalesced dot product over L's row i
-		for (int j = tm.warp; j < n; j += tm.nwarps) {
+		// X = L^-1 (X[i][j] at Xinv[i*n + j]): a warp takes up to four adjacent columns at a time (as many as its scratch in
+		// shared memory holds), the columns under construction live in the scratch, every row is one coalesced sweep over
+		// L's row i feeding the four dot products and their interleaved shuffle reductions
+		{
+			const int ld = (n + 2) & ~1;
+			int G = tm.scratch_len() / ld;
+			G = G < 1 ? 1 : (G > 4 ? 4 : G);
 			double *xs = tm.warp_scratch();
-			for (int i = j; i < n; i++) {
-				const double *li = w.K + (size_t)i * n;
-				double s = 0.0;
-				for (int k = j + tm.lane; k < i; k += T::LANES) s = fma(li[k], xs[k], s);
-				s = tm.warp_sum(s);
-				if (tm.lane == 0) xs[i] = (i == j ? 1.0 : 0.0) - s;
+			for (int j0 = tm.warp * G; j0 < n; j0 += tm.nwarps * G) {
+				const int ng = (n - j0 < G) ? n - j0 : G;
+				for (int i = j0; i < n; i++) {
+					const double *li = w.K + (size_t)i * n;
+					double s[4] = {0.0, 0.0, 0.0, 0.0};
+					for (int k = j0 + tm.lane; k < i; k += T::LANES) {
+						const double l = li[k];
+#pragma unroll
+						for (int c = 0; c < 4; c++)
+							if (c < ng) s[c] = fma(l, xs[c * ld + k], s[c]);
+					}
+#pragma unroll
+					for (int c = 0; c < 4; c++) s[c] = tm.warp_sum(s[c]);
+					if (tm.lane == 0) {
+#pragma unroll
+						for (int c = 0; c < 4; c++)
+							if (c < ng) xs[c * ld + i] = (i == j0 + c ? 1.0 : 0.0) - s[c];
+					}
+					tm.warp_sync();
+				}
+				for (int c = 0; c < ng; c++)
+					for (int i = j0 + c + tm.lane; i < n; i += T::LANES) w.Xinv[(size_t)i * n + j0 + c] = xs[c * ld + i];
 				tm.warp_sync();
 			}
-			for (int i = j + tm.lane; i < n; i += T::LANES) w.Xinv[(size_t)i * n + j] = xs[i];
-			tm.warp_sync();
 		}
 		tm.sync();
 		// K^-1[a][b] = sum_{i >= max(a,b)} X[i][a] X[i][b] / d_i
 		for (size_t e = tm.tid; e < (size_t)n * n; e += tm.nthreads) {
 			const int a = (int)(e / n), b = (int)(e % n);
-			double s = 0.0;
-			for (int i = (a > b ? a : b); i < n; i++) s = fma(w.Xinv[(size_t)i * n + a] * w.pcol[i], w.Xinv[(size_t)i * n + b], s);
-			w.Kinv[e] = s;
+			if (b > a) continue; // the lower triangle, mirrored
+			double s0 = 0.0, s1 = 0.0;
+			int i = a;
+			for (; i + 1 < n; i += 2) {
+				s0 = fma(w.Xinv[(size_t)i * n + a] * w.pcol[i], w.Xinv[(size_t)i * n + b], s0);
+				s1 = fma(w.Xinv[(size_t)(i + 1) * n + a] * w.pcol[i + 1], w.Xinv[(size_t)(i + 1) * n + b], s1);
+			}
+			if (i < n) s0 = fma(w.Xinv[(size_t)i * n + a] * w.pcol[i], w.Xinv[(size_t)i * n + b], s0);
+			w.Kinv[e] = s0 + s1;
+			w.Kinv[(size_t)b * n + a] = s0 + s1;
 		}
 		tm.sync();
 		return true;

@@ -19,6 +19,7 @@ struct HostTeam {
 	int tid = 0, nthreads = 1, lane = 0, warp = 0, nwarps = 1;
 	std::vector<double> scratch_;
 	double *warp_scratch() { return scratch_.data(); }
+	int scratch_len() const { return (int)scratch_.size(); }
 	void sync() {}
 	void warp_sync() {}
 	double warp_bcast(double v, int) const { return v; }
@@ -60,7 +61,7 @@ int32_t asif_qp_solve_batch(int32_t, int32_t nv, int32_t nc, int64_t n, int32_t 
 		pb.status = &stt;
 		pb.info = g_info;
 		HostTeam tm;
-		tm.scratch_.resize(nv + 2);
+		tm.scratch_.resize(2 * (nv + 2)); /* two columns at a time: exercises the grouped inverse */
 		const qpadmm::Work wk = qpadmm::carve(ws.data(), nv, nc);
 		qpadmm::Solver<HostTeam> s(tm, st, nv, nc, wk);
 		s.solve(pb);
