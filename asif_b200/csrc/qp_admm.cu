@@ -171,7 +171,7 @@ int launch_qp_admm(int device, int nv, int nc, int64_t n, int diag_cost, const d
 	}
 	// small problems: one CTA per problem; large ones: a cluster, so that eight SMs' L2 bandwidth serves the factorisations
 	const size_t mat = (size_t)nv * nv + (size_t)nv * nc;
-	// (measured on the 402-variable QP: 2 / 4 / 8 / 16 CTAs = 61 / 35 / 21.7 / see DESIGN ms per solve); 16 needs the non-portable
+	// (measured on the 402-variable QP: 2 / 4 / 8 / 16 CTAs = 61 / 35 / 19.3 / 15.8 ms per solve); 16 needs the non-portable
 	// cluster size and a GPC with 16 free SMs: asked for first, 8 is the fallback
 	int want = mat > 16384 ? (mat > 200000 ? 16 : QA_CLUSTER) : 1;
 	if (const char *e = getenv("ASIF_B200_QP_CLUSTER")) {

@@ -838,7 +838,7 @@ struct Solver {
 				w.psol[i] = s;
 			}
 			reduce(r, 0u);
-			if (!(r[0] > 1e-15 * r[1])) break; // the correction no longer changes the solution
+			if (!(r[0] > 1e-13 * r[1])) break; // the correction is five orders below the solver's own tolerance: done
 		}
 		double bad[NRED] = {0, 0, 0, 0, 0, 0, 0, 0};
 		for (int j = tm.tid; j < n; j += tm.nthreads) {
