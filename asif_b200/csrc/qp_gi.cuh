@@ -203,6 +203,16 @@ struct qp_scan_index_only<Rows, decltype((void)Rows::SCAN_INDEX_ONLY)> {
 	static constexpr bool value = Rows::SCAN_INDEX_ONLY;
 };
 
+// ... and may bring their own search for the smallest residual:  static constexpr bool HAS_SCAN_MIN = true;  scan_min(v, sr, pr)
+template <class Rows, class = void>
+struct qp_has_scan_min {
+	static constexpr bool value = false;
+};
+template <class Rows>
+struct qp_has_scan_min<Rows, decltype((void)Rows::HAS_SCAN_MIN)> {
+	static constexpr bool value = Rows::HAS_SCAN_MIN;
+};
+
 // Vertex polish.  At a vertex (NV active rows) the minimiser is fixed by the rows alone: N v = rhs.  The dual method reaches
 // it by steps along directions orthogonalised in hat space, whose error is eps / sin(angle between active rows) times the
 // length of the step - for a safety row with h ~ 1e-6 against the orthogonality row (3.7e-7 rad apart in hat space, the
@@ -323,6 +333,9 @@ __device__ __forceinline__ int qp_gi_solve(const Metric &mt, const double (&c)[N
 			// inside its own scaled tolerance - a knife edge) sends the lane through the full scan.
 			int pr = -1;
 			double sr = 0.0;
+			if constexpr (qp_has_scan_min<Rows>::value) {
+				rows.scan_min(w.v, sr, pr); // the row functor's own minimum search (robust_kernel.cuh)
+			} else
 			qp_scan_rows(
 			    rows, w.v,
 			    [&](const int j, const double(&n)[NV], const double rhs) {

@@ -93,6 +93,38 @@ struct RobustRows {
 #pragma unroll
 		for (int k = 0; k < 2 * NV; k++) fb(2 * K + k, k >> 1, (k & 1) != 0, (k & 1) ? -ub[k >> 1] : lb[k >> 1]);
 	}
+	// The index-only scan of the solver (qp_gi.cuh) needs only the smallest residual and its row number.  The residual of a
+	// half-plane row at the iterate (u, d) is  Lg u + h d + Lfh  with  h = 1 - a.x  and  Lfh = -a.f,  i.e.
+	//     (Lg u + d) - a0 (x0 d + f0) - a1 (x1 d + f1):
+	// three fused multiply-adds per half-plane on two numbers formed once per scan, instead of forming h and Lfh (seven
+	// operations) and then the inner product.  Same number up to its last bits; the solver fetches the winner again with get()
+	// and works on the exact row, so only a tie within rounding could pick another row, and then both are equally violated.
+#ifndef ROB_SCAN_MIN
+#define ROB_SCAN_MIN 1
+#endif
+	static constexpr bool HAS_SCAN_MIN = ROB_SCAN_MIN != 0;
+	__device__ __forceinline__ void scan_min(const double (&v)[NV], double &sr, int &pr) const
+	{
+		const bool lower = v[0] >= 0.0;
+		const double P = fma(x0, v[1], f0), Q = fma(x1, v[1], f1);
+		const double *t = tab + (lower ? 2 : 3);
+		const int off = lower ? 0 : 1;
+		for (int k = 0; k < K; k++) {
+			const double s = fma(-tab[4 * k + 1], Q, fma(-tab[4 * k], P, fma(t[4 * k], v[0], v[1])));
+			const bool better = s < sr;
+			sr = better ? s : sr;
+			pr = better ? 2 * k + off : pr;
+		}
+#pragma unroll
+		for (int k = 0; k < 2 * NV; k++) {
+			const bool upper = (k & 1) != 0;
+			const double vv = v[k >> 1];
+			const double s = (upper ? -vv : vv) - (upper ? -ub[k >> 1] : lb[k >> 1]);
+			const bool better = s < sr;
+			sr = better ? s : sr;
+			pr = better ? 2 * K + k : pr;
+		}
+	}
 	__device__ __forceinline__ void get(const int j, double (&n)[NV], double &rhs) const
 	{
 		if (j >= 2 * K) {
