@@ -170,6 +170,83 @@ struct TbRows {
 #pragma unroll
 		for (int k = 0; k < 2 * NV; k++) fb(nc() + k, k >> 1, (k & 1) != 0, (k & 1) ? -ub[k >> 1] : lb[k >> 1]);
 	}
+	// The solver's index-only scan needs the smallest residual and its row number, not the rows.  The residual of safety row j
+	// of a critical point (x_i, Q_i) at the iterate (u, d) is  Lgh u + h d + Lfh  with  Lfh = Dh Q f,  Lgh = Dh Q g,  i.e.
+	//     Dh_j . (Q_i (f + g u)) + h_j d:
+	// one nx x nx product per POINT on a vector formed once per scan, then one patterned inner product per row - instead of Dh Q
+	// (per row), two inner products for Lfh and Lgh, and the residual's own.  Same number up to its last bits; the winner is
+	// fetched again with get() and the solver works on the exact row (robust_kernel.cuh: scan_min).
+#ifndef ASIF_TB_SCAN_MIN
+#define ASIF_TB_SCAN_MIN 0 // measured neutral: C2 3.242 vs 3.238 ms per 1e7 states, C5 9.29 vs 9.31 ms per 1e6 (the scans of these kernels are bound by the snapshot loads and by lane divergence, not by the row arithmetic)
+#endif
+	static constexpr bool HAS_SCAN_MIN = ASIF_TB_SCAN_MIN != 0;
+	__device__ __forceinline__ void scan_min(const double (&v)[NV], double &sr, int &pr) const
+	{
+		auto upd = [&](const double s, const int j) {
+			const bool better = s < sr;
+			sr = better ? s : sr;
+			pr = better ? j : pr;
+		};
+		if (!trivial) {
+			const int NC = nc();
+			const int nk = nkept < count_np() ? nkept : count_np();
+			const double dl = v[NU];
+			double wv[NX];
+#pragma unroll
+			for (int m = 0; m < NX; m++) {
+				double a = (M::f_pat(m) == PZ) ? 0.0 : f[m];
+#pragma unroll
+				for (int i = 0; i < NU; i++) {
+					const int pg = M::g_pat(m + i * NX);
+					if (pg == PZ) continue;
+					a = (pg == P1) ? a + v[i] : fma(g[m + i * NX], v[i], a);
+				}
+				wv[m] = a;
+			}
+#pragma unroll 1
+			for (int s = 0; s < nk; s++) {
+				const int slot = slot_of(s);
+				double xs[NS], hs[NPSS], Dhs[NPSS * NX], y[NX];
+#pragma unroll
+				for (int e = 0; e < NS; e++) xs[e] = snap[(slot * NS + e) * T];
+				M::safety_set(xs, hs, Dhs);
+#pragma unroll
+				for (int m = 0; m < NX; m++) {
+					double a = 0.0;
+#pragma unroll
+					for (int cc = 0; cc < NX; cc++) a = fma(xs[NX + m + cc * NX], wv[cc], a);
+					y[m] = a;
+				}
+#pragma unroll
+				for (int j = 0; j < NPSS; j++) {
+					double r = hs[j] * dl;
+#pragma unroll
+					for (int m = 0; m < NX; m++) {
+						const int pt = M::dhs_pat(j + m * NPSS);
+						if (pt == PZ) continue;
+						r = (pt == P1) ? r + y[m] : ((pt == PM1) ? r - y[m] : fma(Dhs[j + m * NPSS], y[m], r));
+					}
+					upd(r, s * NPSS + j);
+				}
+			}
+			if (nk < count_np()) upd(dl, nk * NPSS); // missing points: rows (0, 1), rhs 0, all with the same residual - the first one counts
+			double rT = -rhsT, rO = -rhsO;
+#pragma unroll
+			for (int i = 0; i < NU; i++) {
+				rT = fma(lgT[i], v[i], rT);
+				rO = fma(lgO[i], v[i], rO);
+			}
+			upd(rT, NC - 2);
+			upd(rO, NC - 1);
+		}
+		const int NCb = nc();
+#pragma unroll
+		for (int k = 0; k < 2 * NV; k++) {
+			const bool upper = (k & 1) != 0;
+			const double vv = v[k >> 1];
+			upd((upper ? -vv : vv) - (upper ? -ub[k >> 1] : lb[k >> 1]), NCb + k);
+		}
+	}
 	__device__ __forceinline__ void get(const int j, double (&n)[NV], double &rhs) const
 	{
 		const int NC = nc();
