@@ -620,7 +620,7 @@ int32_t asif_engine_create(const asif_engine_config *cfg, asif_engine **out)
 		const size_t bFV = sizeof(int32_t) * 2 * nF, bFA = sizeof(int32_t) * nF * mA;
 		const size_t bTable = bV + bN + bL + bFV + bFA;
 		// + the per-thread slot lists of the critical-facet rows (realizable_kernel.cuh)
-		e->rz_smem = bTable + sizeof(uint16_t) * RZ_MAX_CRIT * RZ_MAX_ACT * RZ_THREADS;
+		e->rz_smem = bTable + sizeof(uint16_t) * RZ_MAX_CRIT * RZ_MAX_ACT * RZ_THREADS + sizeof(double) * (4 * nF + 1); // + inflated boxes (8-byte aligned)
 		if (e->rz_smem > 96 * 1024 || (size_t)nF * mA > 65535) {
 			delete e;
 			return fail(ASIF_ERR_UNSUPPORTED, "polytope kernel too large for the shared-memory staging (%zu B)", e->rz_smem);

@@ -142,6 +142,9 @@ realizable_ip_filter_kernel(const RealizableParams p, const int64_t n, const dou
 	int32_t *sFV = (int32_t *)(sLie + 4 * nF * mA); // [nF][2]
 	int32_t *sFA = sFV + 2 * nF;                     // [nF][mA]
 	uint16_t *sSlot = (uint16_t *)(sFA + nF * mA) + threadIdx.x; // [RZ_MAX_CRIT * RZ_MAX_ACT][RZ_THREADS]: slot lists
+	// bounding box of every facet inflated by the uncertainty bounds (:407-415): state independent, so formed once per CTA -
+	// the same four operations per facet the per-state test did, hence the same bits
+	double *sBox = (double *)(((uintptr_t)((uint16_t *)(sFA + nF * mA) + RZ_MAX_CRIT * RZ_MAX_ACT * RZ_THREADS) + 7) & ~(uintptr_t)7); // [nF][4]
 	for (int i = threadIdx.x; i < 2 * nV; i += blockDim.x) sV[i] = p.vertices[i];
 	for (int i = threadIdx.x; i < 2 * nF; i += blockDim.x) {
 		sN[i] = p.normals[i];
@@ -149,6 +152,15 @@ realizable_ip_filter_kernel(const RealizableParams p, const int64_t n, const dou
 	}
 	for (int i = threadIdx.x; i < 4 * nF * mA; i += blockDim.x) sLie[i] = p.facet_lie[i];
 	for (int i = threadIdx.x; i < nF * mA; i += blockDim.x) sFA[i] = p.facet_active[i];
+	for (int i = threadIdx.x; i < nF; i += blockDim.x) {
+		const double *v0 = p.vertices + 2 * p.facet_vertices[2 * i], *v1 = p.vertices + 2 * p.facet_vertices[2 * i + 1];
+		const double b0lo = fmin(v0[0], v1[0]), b0hi = fmax(v0[0], v1[0]);
+		const double b1lo = fmin(v0[1], v1[1]), b1hi = fmax(v0[1], v1[1]);
+		sBox[4 * i] = b0lo - p.unc[0];
+		sBox[4 * i + 1] = b0hi + p.unc[0];
+		sBox[4 * i + 2] = b1lo - p.unc[1];
+		sBox[4 * i + 3] = b1hi + p.unc[1];
+	}
 	__syncthreads();
 
 	const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -193,13 +205,10 @@ realizable_ip_filter_kernel(const RealizableParams p, const int64_t n, const dou
 			}
 		}
 		if (nCrit < p.max_crit) {
-			const double *v0 = sV + 2 * sFV[2 * i], *v1 = sV + 2 * sFV[2 * i + 1];
-			// bounding box inflated by the uncertainty (:407-415)
-			const double b0lo = fmin(v0[0], v1[0]), b0hi = fmax(v0[0], v1[0]);
-			const double b1lo = fmin(v0[1], v1[1]), b1hi = fmax(v0[1], v1[1]);
-			const bool potential = !(x0 < (b0lo - p.unc[0]) || x0 > (b0hi + p.unc[0]) || x1 < (b1lo - p.unc[1]) ||
-			                         x1 > (b1hi + p.unc[1]));
+			// bounding box inflated by the uncertainty (:407-415), staged per CTA
+			const bool potential = !(x0 < sBox[4 * i] || x0 > sBox[4 * i + 1] || x1 < sBox[4 * i + 2] || x1 > sBox[4 * i + 3]);
 			if (potential) {
+				const double *v0 = sV + 2 * sFV[2 * i], *v1 = sV + 2 * sFV[2 * i + 1];
 				// p(t) = t v0 + (1-t) v1 inside [x - unc, x + unc] for some t in [0,1]?   (:419-440, exact)
 				double tlo = 0.0, thi = 1.0;
 				bool ok = true;
