@@ -81,6 +81,9 @@ def test_product_does_not_touch_oracle():
                 txt = open(os.path.join(d, f), errors="ignore").read()
                 if re.search(r"oracle[/.]|liboracle|libasif_ref|pyref", txt):
                     bad.append(os.path.join(d, f))
+                # nor may it include, import or load the test-only host team of the QP solver (tests/hostemu)
+                if re.search(r"(#include|import|CDLL|dlopen)[^\n]*hostemu", txt):
+                    bad.append(os.path.join(d, f))
     assert not bad, bad
     so = os.path.join(ROOT, "asif_b200", "libasif_b200.so")
     if os.path.exists(so):
