@@ -817,10 +817,10 @@ struct Solver {
 		ldl_solve(w.LR, w.LC, w.pd, w.psol, N);
 		for (int it = 0; it < st.polish_refine_iter; it++) {
 			// residual of the UNregularised system: [P x + A_act' y ; A_act x]
+			// (a row is in at most one of the two lists: "lower" needs y < -(z - l) <= 0, "upper" y > u - z >= 0)
 			for (int i = tm.tid; i < m; i += tm.nthreads) w.tmpm[i] = 0.0;
 			tm.sync();
-			if (tm.tid == 0)
-				for (int a = 0; a < na; a++) w.tmpm[w.rows[a]] += w.psol[n + a];
+			for (int a = tm.tid; a < na; a += tm.nthreads) w.tmpm[w.rows[a]] = w.psol[n + a];
 			tm.sync();
 			mv_P(w.psol, w.Px);
 			mv_At(w.tmpm, w.Aty);
@@ -848,8 +848,7 @@ struct Solver {
 		for (int i = tm.tid; i < m; i += tm.nthreads) w.yp[i] = 0.0;
 		reduce(bad, 0u);
 		if (bad[0] != 0.0) return false;
-		if (tm.tid == 0)
-			for (int a = 0; a < na; a++) w.yp[w.rows[a]] = w.psol[n + a]; // a later (upper) entry wins, as OSQP's get_ypol_from_yred
+		for (int a = tm.tid; a < na; a += tm.nthreads) w.yp[w.rows[a]] = w.psol[n + a]; // OSQP's get_ypol_from_yred (no row is listed twice)
 		mv_A(w.xp, w.zp);
 		tm.sync();
 		for (int i = tm.tid; i < m; i += tm.nthreads) w.zp[i] = fmin(fmax(w.zp[i], w.l[i]), w.u[i]);
