@@ -150,9 +150,27 @@ __host__ __device__ constexpr int dfcl_pattern(int i, int j)
 // f_pat(i) == PZ marks a drift component that is the literal 0.0 (then g uSat + 0.0 == g uSat).
 // The part after the backup controller: u is the input handed to the saturation, Du the controller Jacobian that
 // enters DfCL (for ASIFimplicitRB these can be the zero-order-held values, see backup_cl_dynamics_zoh).
-template <class M, int SATMODE>
+// Optional carrier of sin / cos of the model's angle for the Euler loops that advance them by the angle-addition recurrence
+// (implicit_kernel.cuh, ASIF_IMP_TRIG_RECURRENCE); NoTrig = the model evaluates its own trigonometry.
+struct NoTrig {};
+struct TrigSC {
+	double s, c, x0;
+};
+template <class M>
+__device__ __forceinline__ void model_dynamics_all(const double *x, const NoTrig &, double *f, double *g, double *d, double *Dg)
+{
+	M::dynamics_all(x, f, g, d, Dg);
+}
+template <class M>
+__device__ __forceinline__ void model_dynamics_all(const double *x, const TrigSC &t, double *f, double *g, double *d, double *Dg)
+{
+	M::dynamics_all_sc(x, t.s, t.c, f, g, d, Dg);
+}
+
+template <class M, int SATMODE, class TR = NoTrig>
 __device__ __forceinline__ void backup_cl_from_input(const SoftSat &sat, const double *lb, const double *ub, const double *x,
-                                                     const double *u, const double *Du, double *fCL, double *DfCL)
+                                                     const double *u, const double *Du, double *fCL, double *DfCL,
+                                                     const TR &tr = TR())
 {
 	constexpr int NX = M::NX, NU = M::NU;
 	double f[NX], g[NX * NU], uSat[NU], DuSat[NU];
@@ -161,7 +179,7 @@ __device__ __forceinline__ void backup_cl_from_input(const SoftSat &sat, const d
 	// saturation - its rare bevel branch then comes after the model's long chains instead of fencing them off
 	if (!M::FUSED_GRADIENT) {
 		if (M::HAS_DYNAMICS_ALL) {
-			M::dynamics_all(x, f, g, d, Dg); // shares sub-expressions (trig of the same argument) between f, g and Df, Dg
+			model_dynamics_all<M>(x, tr, f, g, d, Dg); // shares sub-expressions (trig of the same argument) between f, g and Df, Dg
 		} else {
 			M::dynamics(x, f, g);
 			M::dynamics_gradients(x, d, Dg);
@@ -220,13 +238,13 @@ __device__ __forceinline__ void backup_cl_from_input(const SoftSat &sat, const d
 	}
 }
 
-template <class M, int SATMODE>
+template <class M, int SATMODE, class TR = NoTrig>
 __device__ __forceinline__ void backup_cl_dynamics(const SoftSat &sat, const double *lb, const double *ub, const double *x,
-                                                   double *fCL, double *DfCL)
+                                                   double *fCL, double *DfCL, const TR &tr = TR())
 {
 	double u[M::NU], Du[M::NU * M::NX];
 	M::backup_controller(x, u, Du);
-	backup_cl_from_input<M, SATMODE>(sat, lb, ub, x, u, Du, fCL, DfCL);
+	backup_cl_from_input<M, SATMODE, TR>(sat, lb, ub, x, u, Du, fCL, DfCL, tr);
 }
 
 // Zero-order-hold backup controller of ASIFimplicitRB (src/asif_implicit_robust.cpp:878-903): the controller is
@@ -241,10 +259,10 @@ struct ZohState {
 	double t_last;
 };
 
-template <class M, int SATMODE>
+template <class M, int SATMODE, class TR = NoTrig>
 __device__ __forceinline__ void backup_cl_dynamics_zoh(const SoftSat &sat, const double *lb, const double *ub, const double *x,
                                                        const double t, const double backTrajDt, const double backContDt,
-                                                       ZohState<M> &z, double *fCL, double *DfCL)
+                                                       ZohState<M> &z, double *fCL, double *DfCL, const TR &tr = TR())
 {
 	constexpr int NX = M::NX, NU = M::NU;
 	double u[NU], Du[NU * NX];
@@ -257,7 +275,7 @@ __device__ __forceinline__ void backup_cl_dynamics_zoh(const SoftSat &sat, const
 		for (int i = 0; i < NU * NX; i++) z.Du[i] = Du[i];
 		z.t_last = t;
 	}
-	backup_cl_from_input<M, SATMODE>(sat, lb, ub, x, z.u, M::FUSED_GRADIENT ? z.Du : Du, fCL, DfCL);
+	backup_cl_from_input<M, SATMODE, TR>(sat, lb, ub, x, z.u, M::FUSED_GRADIENT ? z.Du : Du, fCL, DfCL, tr);
 }
 
 // Q-dot = DfCL Q (src/asif_implicit_tb.cpp:906-908) with the structural pattern of DfCL

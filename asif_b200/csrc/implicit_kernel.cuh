@@ -13,6 +13,7 @@
 // computes are never used, :689-738).  Selection of the critical points still uses the nominal min h (:572).
 #pragma once
 #include "filter_common.cuh"
+#include "models.cuh" // sincos_model (imp_advance)
 #include "qp_gi.cuh"
 
 namespace asifb {
@@ -528,11 +529,52 @@ __host__ __device__ constexpr int imp2_smem_doubles_per_thread()
 }
 
 // one Euler step of the augmented backup flow, X_i = X_{i-1} + dt rhs(X_{i-1}) (src/asif_implicit.cpp:461-484), and min_j h_j(x_i)
+// EXPERIMENT (off): sin / cos of the model's angle advanced by the angle-addition recurrence between full evaluations every 16
+// steps.  The increment d = x_i - x_{i-1} of the ROUNDED state is exact (Sterbenz), sin d and cos d are three- and four-term
+// Taylor sums (|d| < 0.03: truncation below 1e-18), so the only error is the rounding of the rotation itself, ~3 ulp per step.
+// Both passes of the checkpoint kernel re-synchronise at the same indices ((i - 1) % 16 == 0), hence produce the same bits.
+#ifndef ASIF_IMP_TRIG_RECURRENCE
+#define ASIF_IMP_TRIG_RECURRENCE 0
+#endif
+template <class M, class = void>
+struct model_has_trig {
+	static constexpr bool value = false;
+};
+template <class M>
+struct model_has_trig<M, decltype((void)M::HAS_TRIG_STATE)> {
+	static constexpr bool value = M::HAS_TRIG_STATE;
+};
+template <class M>
+__host__ __device__ constexpr bool imp_use_trig()
+{
+	return ASIF_IMP_TRIG_RECURRENCE != 0 && model_has_trig<M>::value;
+}
+
 template <class M, int SATMODE, bool RB>
-__device__ __forceinline__ double imp_advance(const ImplicitParams &p, const int i, double (&X)[M::NX + M::NX * M::NX], ZohState<M> &zoh)
+__device__ __forceinline__ double imp_advance(const ImplicitParams &p, const int i, double (&X)[M::NX + M::NX * M::NX], ZohState<M> &zoh,
+                                              TrigSC &tr)
 {
 	constexpr int NX = M::NX, NPSS = M::NPSS, NS = NX + NX * NX;
 	double Xd[NS], DfCL[NX * NX];
+	if constexpr (imp_use_trig<M>()) {
+		const double a = X[M::TRIG_ANGLE];
+		const double dl = a - tr.x0;
+		if ((((i - 1) & 15) == 0) || !(fabs(dl) < 0.03)) {
+			sincos_model(a, &tr.s, &tr.c);
+		} else {
+			const double d2 = dl * dl;
+			const double sd = dl * fma(d2, fma(d2, 1.0 / 120.0, -1.0 / 6.0), 1.0);
+			const double cd = fma(d2, fma(d2, fma(d2, -1.0 / 720.0, 1.0 / 24.0), -0.5), 1.0);
+			const double ns = fma(tr.c, sd, tr.s * cd), nc = fma(-tr.s, sd, tr.c * cd);
+			tr.s = ns;
+			tr.c = nc;
+		}
+		tr.x0 = a;
+		if (RB)
+			backup_cl_dynamics_zoh<M, SATMODE, TrigSC>(p.sat, p.lb, p.ub, X, (double)(unsigned)i * p.backTrajDt, p.backTrajDt, p.backContDt, zoh, Xd, DfCL, tr);
+		else
+			backup_cl_dynamics<M, SATMODE, TrigSC>(p.sat, p.lb, p.ub, X, Xd, DfCL, tr);
+	} else
 	if (RB) // the reference hands t = i*backTrajDt to the rhs (src/asif_implicit_robust.cpp:550)
 		backup_cl_dynamics_zoh<M, SATMODE>(p.sat, p.lb, p.ub, X, (double)(unsigned)i * p.backTrajDt, p.backTrajDt, p.backContDt, zoh, Xd, DfCL);
 	else
@@ -619,6 +661,7 @@ implicit_ckpt_kernel(const ImplicitParams p, const int64_t n, const double *__re
 #pragma unroll
 		for (int i = 0; i < NX; i++) X[NX + i * (NX + 1)] = 1.0;
 		ZohState<M> zoh;
+		TrigSC trig = {0.0, 1.0, 0.0}; // (imp_advance: re-synchronised at the first step after every checkpoint)
 #pragma unroll
 		for (int i = 0; i < NU; i++) zoh.u[i] = 0.0;
 #pragma unroll
@@ -652,7 +695,7 @@ implicit_ckpt_kernel(const ImplicitParams p, const int64_t n, const double *__re
 			const int iend = (c0 + IMP_CK < N - 1) ? c0 + IMP_CK : N - 1;
 			double bmin = INFINITY;
 			for (int i = c0 + 1; i <= iend; i++) {
-				const double hmin = imp_advance<M, SATMODE, RB>(p, i, X, zoh);
+				const double hmin = imp_advance<M, SATMODE, RB>(p, i, X, zoh, trig);
 				bmin = (hmin < bmin) ? hmin : bmin;
 			}
 			if (bmin < bkmax) {
@@ -777,7 +820,7 @@ implicit_ckpt_kernel(const ImplicitParams p, const int64_t n, const double *__re
 				for (int j = 1; j <= wsteps; j++) {
 					if (j <= nsteps) {
 						const int i = base_i + j;
-						const double hmin = imp_advance<M, SATMODE, RB>(p, i, X, zoh);
+						const double hmin = imp_advance<M, SATMODE, RB>(p, i, X, zoh, trig);
 						const int slot = R.order.last(); // the evicted (largest) entry's slot takes the new point
 						if (hmin < kmax || (hmin == kmax && i < kidx[slot * T])) {
 							int pl = 0; // first place that (hmin, i) comes before: ties keep the earlier index first

@@ -640,6 +640,19 @@ struct InvertedPendulumImplicit {
 		Df[1] = c;  Df[3] = 0.;
 		Dg[0] = Dg[1] = Dg[2] = Dg[3] = 0.0;
 	}
+	// the same with sin x0, cos x0 supplied by the caller (filter_common.cuh: TrigSC)
+	static constexpr bool HAS_TRIG_STATE = true;
+	static constexpr int TRIG_ANGLE = 0;
+	__device__ static void dynamics_all_sc(const double *x, const double s, const double c, double *f, double *g, double *Df, double *Dg)
+	{
+		f[0] = x[1];
+		f[1] = s;
+		g[0] = 0.;
+		g[1] = 1.;
+		Df[0] = 0.; Df[2] = 1.;
+		Df[1] = c;  Df[3] = 0.;
+		Dg[0] = Dg[1] = Dg[2] = Dg[3] = 0.0;
+	}
 	__device__ static void dynamics_with_gradient(const double *, const double *, double *, double *, double *) {}
 };
 

@@ -326,7 +326,7 @@ def qp_backend_legs(ab, device_index):
     from asif_b200 import capi
     out = []
     for nv, nc, n, label in ((40, 60, 296, "one CTA per problem, workspace in shared memory"),
-                             (400, 300, 18, "one 8-CTA cluster per problem (the size of ASIFrobust's LP-dual QP)")):
+                             (400, 300, 18, "one thread-block cluster per problem (the size of ASIFrobust's LP-dual QP)")):
         g = np.random.Generator(np.random.Philox(key=1234 + nv))
         Hd = np.zeros(nv)
         Hd[:nv // 4] = g.uniform(0.5, 20.0, nv // 4)
