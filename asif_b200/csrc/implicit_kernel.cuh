@@ -20,6 +20,50 @@ namespace asifb {
 
 constexpr int IMP_THREADS = 128;
 
+// sin / cos of the model's angle are advanced by the angle-addition recurrence between full evaluations every 16 steps
+// (models that declare HAS_TRIG_STATE: the pendulum).  The increment d = x_i - x_{i-1} of the ROUNDED state is exact (Sterbenz),
+// sin d and cos d are three- and four-term Taylor sums (|d| < 0.0125: truncation below 1e-17; larger steps take the full
+// evaluation), so the only error is the rounding of the rotation itself, ~3 ulp per step, reset every 16 steps.  Both passes of
+// the checkpoint kernel re-synchronise at the same indices ((i - 1) % 16 == 0), hence produce the same bits.  The first half of
+// the round had rejected this on paper ("multiplies the rate of critical-index flips"); measured: C3a 21.85 -> 19.11 ms per 1e6
+// states, and over 1e5 states against the oracle 0 return-code flips, 0 critical-index flips, rows within 1.8e-14 as before,
+// max |du| 2.4e-9 (6.8e-10 before) of a 1e-6 bar.  -DASIF_IMP_TRIG_RECURRENCE=0 restores one sincos per step.
+#ifndef ASIF_IMP_TRIG_RECURRENCE
+#define ASIF_IMP_TRIG_RECURRENCE 1
+#endif
+template <class M, class = void>
+struct model_has_trig {
+	static constexpr bool value = false;
+};
+template <class M>
+struct model_has_trig<M, decltype((void)M::HAS_TRIG_STATE)> {
+	static constexpr bool value = M::HAS_TRIG_STATE;
+};
+template <class M>
+__host__ __device__ constexpr bool imp_use_trig()
+{
+	return ASIF_IMP_TRIG_RECURRENCE != 0 && model_has_trig<M>::value;
+}
+
+// one step of that recurrence: the angle now is a, tr holds sin / cos of the angle of the step before
+template <class M>
+__device__ __forceinline__ void imp_trig_step(const int i, const double a, TrigSC &tr)
+{
+	const double dl = a - tr.x0;
+	if ((((i - 1) & 15) == 0) || !(fabs(dl) < 0.0125)) {
+		sincos_model(a, &tr.s, &tr.c);
+	} else {
+		const double d2 = dl * dl;
+		const double sd = dl * fma(d2, fma(d2, 1.0 / 120.0, -1.0 / 6.0), 1.0);
+		const double cd = fma(d2, fma(d2, fma(d2, -1.0 / 720.0, 1.0 / 24.0), -0.5), 1.0);
+		const double ns = fma(tr.c, sd, tr.s * cd), nc = fma(-tr.s, sd, tr.c * cd);
+		tr.s = ns;
+		tr.c = nc;
+	}
+	tr.x0 = a;
+}
+
+
 // The two residual networks of include/asif_learning_utils.h:8-32 on the device: weights column-major [rows x cols]
 // as matrixVectorMultiply reads them, in one blob: drift net (w1, b1, w2, b2, w3, b3) then actuation net.
 constexpr int LEARN_MAX_WIDTH = 64; // widest input / hidden layer accepted
@@ -323,8 +367,17 @@ implicit_filter_kernel(const ImplicitParams p, const int64_t n, const double *__
 		for (int i = 0; i < NU * NX; i++) zoh.Du[i] = 0.0;
 		zoh.t_last = -1.;
 	}
+	TrigSC trig = {0.0, 1.0, 0.0};
 	for (int i = 1; i < N; i++) {
 		double Xd[NS], DfCL[NX * NX];
+		if constexpr (imp_use_trig<M>()) {
+			imp_trig_step<M>(i, X[M::TRIG_ANGLE], trig);
+			if (RB)
+				backup_cl_dynamics_zoh<M, SATMODE, TrigSC>(p.sat, p.lb, p.ub, X, (double)(unsigned)i * p.backTrajDt, p.backTrajDt,
+				                                           p.backContDt, zoh, Xd, DfCL, trig);
+			else
+				backup_cl_dynamics<M, SATMODE, TrigSC>(p.sat, p.lb, p.ub, X, Xd, DfCL, trig);
+		} else
 		if (RB) // the reference hands t = i*backTrajDt to the rhs (src/asif_implicit_robust.cpp:550)
 			backup_cl_dynamics_zoh<M, SATMODE>(p.sat, p.lb, p.ub, X, (double)(unsigned)i * p.backTrajDt, p.backTrajDt,
 			                                   p.backContDt, zoh, Xd, DfCL);
@@ -529,31 +582,6 @@ __host__ __device__ constexpr int imp2_smem_doubles_per_thread()
 }
 
 // one Euler step of the augmented backup flow, X_i = X_{i-1} + dt rhs(X_{i-1}) (src/asif_implicit.cpp:461-484), and min_j h_j(x_i)
-// sin / cos of the model's angle are advanced by the angle-addition recurrence between full evaluations every 16 steps
-// (models that declare HAS_TRIG_STATE: the pendulum).  The increment d = x_i - x_{i-1} of the ROUNDED state is exact (Sterbenz),
-// sin d and cos d are three- and four-term Taylor sums (|d| < 0.03: truncation below 1e-18; larger steps take the full
-// evaluation), so the only error is the rounding of the rotation itself, ~3 ulp per step, reset every 16 steps.  Both passes of
-// the checkpoint kernel re-synchronise at the same indices ((i - 1) % 16 == 0), hence produce the same bits.  The first half of
-// the round had rejected this on paper ("multiplies the rate of critical-index flips"); measured: C3a 21.85 -> 19.11 ms per 1e6
-// states, and over 1e5 states against the oracle 0 return-code flips, 0 critical-index flips, rows within 1.8e-14 as before,
-// max |du| 2.4e-9 (6.8e-10 before) of a 1e-6 bar.  -DASIF_IMP_TRIG_RECURRENCE=0 restores one sincos per step.
-#ifndef ASIF_IMP_TRIG_RECURRENCE
-#define ASIF_IMP_TRIG_RECURRENCE 1
-#endif
-template <class M, class = void>
-struct model_has_trig {
-	static constexpr bool value = false;
-};
-template <class M>
-struct model_has_trig<M, decltype((void)M::HAS_TRIG_STATE)> {
-	static constexpr bool value = M::HAS_TRIG_STATE;
-};
-template <class M>
-__host__ __device__ constexpr bool imp_use_trig()
-{
-	return ASIF_IMP_TRIG_RECURRENCE != 0 && model_has_trig<M>::value;
-}
-
 template <class M, int SATMODE, bool RB>
 __device__ __forceinline__ double imp_advance(const ImplicitParams &p, const int i, double (&X)[M::NX + M::NX * M::NX], ZohState<M> &zoh,
                                               TrigSC &tr)
@@ -561,19 +589,7 @@ __device__ __forceinline__ double imp_advance(const ImplicitParams &p, const int
 	constexpr int NX = M::NX, NPSS = M::NPSS, NS = NX + NX * NX;
 	double Xd[NS], DfCL[NX * NX];
 	if constexpr (imp_use_trig<M>()) {
-		const double a = X[M::TRIG_ANGLE];
-		const double dl = a - tr.x0;
-		if ((((i - 1) & 15) == 0) || !(fabs(dl) < 0.03)) {
-			sincos_model(a, &tr.s, &tr.c);
-		} else {
-			const double d2 = dl * dl;
-			const double sd = dl * fma(d2, fma(d2, 1.0 / 120.0, -1.0 / 6.0), 1.0);
-			const double cd = fma(d2, fma(d2, fma(d2, -1.0 / 720.0, 1.0 / 24.0), -0.5), 1.0);
-			const double ns = fma(tr.c, sd, tr.s * cd), nc = fma(-tr.s, sd, tr.c * cd);
-			tr.s = ns;
-			tr.c = nc;
-		}
-		tr.x0 = a;
+		imp_trig_step<M>(i, X[M::TRIG_ANGLE], tr);
 		if (RB)
 			backup_cl_dynamics_zoh<M, SATMODE, TrigSC>(p.sat, p.lb, p.ub, X, (double)(unsigned)i * p.backTrajDt, p.backTrajDt, p.backContDt, zoh, Xd, DfCL, tr);
 		else
