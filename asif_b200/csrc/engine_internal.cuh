@@ -310,9 +310,7 @@ int launch_implicit_t(asif_engine *e, int64_t n, const double *x, const double *
 	}();
 	const int ck_log = imp_ck_log(e->im.npBT);
 	if (!force_smem && ck_log > 0) {
-		e->im.ck_log = ck_log;
 		const size_t smem2 = sizeof(double) * imp2_smem_doubles_per_thread<NPBTSS>() * IMP2_THREADS;
-		const size_t per_cta = sizeof(double) * imp_scratch_doubles_per_thread<M, NPBTSS, RB>(e->im.npBT, ck_log) * IMP2_THREADS;
 		const int64_t tiles = (n + IMP2_THREADS - 1) / IMP2_THREADS;
 		auto launch = [&](auto kern) -> int {
 			int per_sm = 0;
@@ -322,8 +320,16 @@ int launch_implicit_t(asif_engine *e, int64_t n, const double *x, const double *
 			// every CTA runs the same number of tiles (no ragged last wave), as for the persistent TB kernels
 			const int64_t rounds = (tiles + resident - 1) / resident;
 			const unsigned blocks2 = (unsigned)((tiles + rounds - 1) / rounds);
-			const size_t need = per_cta * (size_t)blocks2;
+			// a scratch beyond 2 GB (ASIFimplicitRB at npBT 5001: 10 doubles per checkpoint, 2.4 GB at 16 steps) takes a coarser
+			// spacing first: any multiple of 16 keeps the checkpoints on the re-synchronisation steps of the trig recurrence
+			int l = ck_log;
+			size_t need;
+			for (;; l++) {
+				need = sizeof(double) * imp_scratch_doubles_per_thread<M, NPBTSS, RB>(e->im.npBT, l) * IMP2_THREADS * (size_t)blocks2;
+				if (need <= ((size_t)2 << 30) || l == 6) break;
+			}
 			if (need > ((size_t)2 << 30)) return 1; // fall back
+			e->im.ck_log = l;
 			int buf;
 			int r = acquire_scratch(e, need, st, buf);
 			if (r) return r;

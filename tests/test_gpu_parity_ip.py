@@ -127,6 +127,29 @@ def test_implicit_rb(ab, oracle, cfg, model, opts, gen, bit_exact):
     assert np.array_equal(rc, rc2) and np.array_equal(u, u2) and np.array_equal(relax, relax2)
 
 
+def test_implicit_rb_long_horizon(ab, oracle):
+    """ASIFimplicitRB at the example horizon (npBT 5001, hold 10 ms = 10 Euler steps): 10 doubles per checkpoint would need
+    2.4 GB of scratch at the 16-step spacing, so the launcher takes 32 steps (launch_implicit_t); both passes of the
+    checkpoint kernel must still re-synchronise the trig recurrence on the same steps.  Against the oracle."""
+    opts = [50.0, 5.0, 10.0, 5.0, 0.001, 0.1, 10.0, 0.01, 0.05, 0.08]
+    n = 3000
+    x, ud = cf.c3a_inputs(n, seed=cf.SEED + 377)
+    eng = ab.Engine(ab.FILTER_IMPLICIT_RB, ab.MODEL_INVERTED_PENDULUM, **cf.rb_engine_kwargs(opts))
+    u, relax, rc, diag = eng.filter_batch(x, ud, want_diag=True)
+    u0, relax0, rc0, diag0 = oracle.filter_batch(7, x, ud, opts, want_diag=True)
+    flips = np.nonzero(rc != rc0)[0]
+    print("implicitRB npBT 5001 rc", dict(zip(*np.unique(rc0, return_counts=True))), "flips", flips.size)
+    assert flips.size <= 2
+    keep = rc == rc0
+    cf.assert_parity("implicitRB-5001", (u[keep], relax[keep], rc[keep]), (u0[keep], relax0[keep], rc0[keep]))
+    same = keep & np.all(diag[:, 2:12] == diag0[:, 2:12], axis=1)
+    print("  states with identical critical indices: %.4f" % same[keep].mean())
+    assert same[keep].mean() > 0.995
+    assert (np.abs(diag[same] - diag0[same]) / (1.0 + np.abs(diag0[same]))).max() <= 1e-9
+    u2, relax2, rc2 = eng.filter_batch(x, ud)
+    assert np.array_equal(rc, rc2) and np.array_equal(u, u2) and np.array_equal(relax, relax2)
+
+
 def test_implicit_rb_reduces_to_implicit(ab):
     """x_unc = 0, hold period = Euler step: the RB kernel returns what the implicit kernel returns."""
     x, ud = cf.c3a_inputs(5000, seed=9)
