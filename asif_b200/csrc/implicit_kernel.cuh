@@ -34,6 +34,7 @@ constexpr int IMP_THREADS = 128;
 #ifndef ASIF_IMP_PEEL_UNROLL
 #define ASIF_IMP_PEEL_UNROLL 1
 #endif
+constexpr int IMP_PEEL_UNROLL = ASIF_IMP_PEEL_UNROLL; // (#pragma unroll does not expand macros)
 #ifndef ASIF_IMP_PEEL
 #define ASIF_IMP_PEEL 1 // pass A of the checkpoint kernel: re-synchronisation step peeled out of the step loop (C3a 19.04 -> 18.44 ms, same bits)
 #endif
@@ -729,7 +730,7 @@ implicit_ckpt_kernel(const ImplicitParams p, const int64_t n, const double *__re
 					const int gend = (g0 + 16 < iend) ? g0 + 16 : iend;
 					const double h1 = imp_advance<M, SATMODE, RB, 1>(p, g0 + 1, X, zoh, trig);
 					bmin = (h1 < bmin) ? h1 : bmin;
-#pragma unroll ASIF_IMP_PEEL_UNROLL
+#pragma unroll IMP_PEEL_UNROLL
 					for (int i = g0 + 2; i <= gend; i++) {
 						const double hmin = imp_advance<M, SATMODE, RB, 2>(p, i, X, zoh, trig);
 						bmin = (hmin < bmin) ? hmin : bmin;
