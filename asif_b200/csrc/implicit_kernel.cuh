@@ -623,8 +623,11 @@ __device__ __forceinline__ double imp_advance(const ImplicitParams &p, const int
 #ifndef IMP2_MIN_BLOCKS
 #define IMP2_MIN_BLOCKS 5 // 5 CTAs = 20 warps per SM at <= 102 registers: measured 25.5 ms against 31.1 (4) and 28.6 (3) on C3a
 #endif
+#ifndef IMP2_MIN_BLOCKS_RB
+#define IMP2_MIN_BLOCKS_RB 6 // with the zero-order hold: 80 registers, 24 warps per SM: 21.78 -> 21.33 ms at npBT 5001 (C3a: 18.00 / 18.06, kept at 5)
+#endif
 template <class M, int NPBTSS, bool WITH_DIAG, int SATMODE, bool RB = false>
-__global__ void __launch_bounds__(IMP2_THREADS, IMP2_MIN_BLOCKS)
+__global__ void __launch_bounds__(IMP2_THREADS, RB ? IMP2_MIN_BLOCKS_RB : IMP2_MIN_BLOCKS)
 implicit_ckpt_kernel(const ImplicitParams p, const int64_t n, const double *__restrict__ x_in, const double *__restrict__ u_des,
                      double *__restrict__ u_act, double *__restrict__ relax_out, int32_t *__restrict__ rc_out,
                      double *__restrict__ diag, unsigned long long *__restrict__ qp_iter_sum, double *gscratch)
